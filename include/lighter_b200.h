@@ -1,0 +1,97 @@
+/*
+ * lighter_b200.h -- extension C ABI of liblighter_b200.so (everything the reference's lighter.h
+ * does not have).  Plain C types only.  None of these calls is needed for a drop-in bake: a caller
+ * that only knows lighter.h gets a single-GPU bake on the current CUDA device.
+ *
+ * Groups:
+ *   ltrx_Set* / ltrx_Nccl* / ltrx_ShardRange  multi-GPU: one process per GPU, lumels sharded,
+ *                                              BVH replicated, per-bounce radiance all-gather
+ *                                              (replaces the reference's shared-memory thread
+ *                                              pool, lighter_int.hpp:17-258 / DoWork call sites
+ *                                              lighter.cpp:637-653,1133)
+ *   ltrx_GetStats / ltrx_GetError             measurement and error surfacing (the reference only
+ *                                              has the stage string, lighter.cpp:1159-1164)
+ *   ltrx_Prepare / ltrx_BakeResident          bench support: time the GPU stages with the scene
+ *                                              already resident in HBM
+ *   ltrx_Get*                                 stage dumps for parity tests (what a reference
+ *                                              driver reads from ltr_Scene members)
+ *   ltrx_test_*                               primitive / kernel-level entry points for parity tests
+ */
+#ifndef LIGHTER_B200_H
+#define LIGHTER_B200_H
+
+#include "lighter.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LTRX_NCCL_ID_BYTES 128
+
+typedef struct ltrx_Stats {
+    /* host wall-clock seconds per stage of the last bake (stage names as in lighter.cpp:1052-1138) */
+    double t_total, t_prexform, t_accel, t_upload, t_samples, t_direct, t_radiosity, t_ao, t_finalize, t_readback;
+    /* device milliseconds (CUDA events on the bake stream) */
+    float gpu_ms_samples, gpu_ms_direct, gpu_ms_march, gpu_ms_radiosity, gpu_ms_ao, gpu_ms_finalize, gpu_ms_total;
+    /* work counters of THIS rank's shard (units of SURVEY.md 8d) */
+    uint64_t n_lumels_total, n_lumels_local, n_triangles, n_bvh_nodes;
+    uint64_t n_marches, n_distance_queries, n_ao_segments, n_correction_rays;
+    uint64_t n_rad_pairs, n_rad_segments, n_rad_links;
+    uint64_t n_node_visits, n_tri_tests;      /* traversal counters (march + AO + radiosity) */
+    uint64_t kernel_launches, h2d_bytes, d2h_bytes;
+} ltrx_Stats;
+
+typedef struct ltrx_Lumels {
+    u32 count, width, height;
+    const float *pos_xyz;      /* count*3, world position after offset/overlap correction */
+    const float *nrm_xyz;      /* count*3 */
+    const u32   *loc;          /* texel index y*width+x */
+    const float *radinfo_xyzw; /* uv1.x, uv1.y, part, world area per texel */
+    const float *rgb;          /* per-lumel colour before finalize */
+} ltrx_Lumels;
+
+typedef struct ltrx_Links {
+    uint64_t rows, count;
+    const uint64_t *row_offset;   /* rows+1; FULL symmetric rows (both directions), partners ascending */
+    const u32      *other;
+    const float    *factor;
+} ltrx_Links;
+
+LTRAPI const char *ltrx_Version(void);
+
+/* multi-GPU -------------------------------------------------------------------------------- */
+LTRAPI int  ltrx_SetDevice(ltr_Scene *scene, int cuda_device);
+LTRAPI int  ltrx_NcclUniqueId(unsigned char out_id[LTRX_NCCL_ID_BYTES]);
+LTRAPI int  ltrx_SetShard(ltr_Scene *scene, int rank, int world, const unsigned char *nccl_id /* NULL iff world==1 */);
+LTRAPI void ltrx_ShardRange(uint64_t n, int rank, int world, uint64_t *begin, uint64_t *end);
+
+/* measurement ------------------------------------------------------------------------------ */
+LTRAPI int         ltrx_GetStats(ltr_Scene *scene, ltrx_Stats *out);
+LTRAPI const char *ltrx_GetError(ltr_Scene *scene);   /* "" when the last bake succeeded */
+LTRAPI int         ltrx_Prepare(ltr_Scene *scene);    /* host pre-pass + upload; synchronous */
+LTRAPI int         ltrx_BakeResident(ltr_Scene *scene, float *gpu_ms_out); /* GPU stages only, synchronous */
+LTRAPI int         ltrx_Finish(ltr_Scene *scene);     /* read back outputs after ltrx_BakeResident */
+
+/* stage dumps (valid after a bake run with ltrx_SetDebug(scene,1)) --------------------------- */
+LTRAPI int ltrx_SetDebug(ltr_Scene *scene, int keep_stage_arrays);
+LTRAPI int ltrx_GetLumels(ltr_Scene *scene, u32 instance, ltrx_Lumels *out);
+LTRAPI int ltrx_GetLinks(ltr_Scene *scene, ltrx_Links *out);
+LTRAPI int ltrx_GetShadowFactors(ltr_Scene *scene, u32 light, const float **out, uint64_t *count);
+
+/* kernel-level entry points: host arrays in, host arrays out, device round trip inside -------- */
+LTRAPI int ltrx_test_point_tri_distance(const float *pts3, const float *tris9, u32 n, float *out);
+LTRAPI int ltrx_test_seg_tri(const float *a3, const float *b3, const float *tris9, u32 n, float *out);
+LTRAPI int ltrx_test_scene_queries(const float *tris9, u32 ntris,
+                                   const float *a3, const float *b3, u32 n,
+                                   float *dist_out,      /* min(2, nearest distance) at a */
+                                   int   *anyhit_out,    /* segment a-b blocked (end points NOT shortened) */
+                                   float *closest_out,   /* closest-hit parameter on a-b, 2 = none */
+                                   int   *closest_tri_out);
+LTRAPI int ltrx_test_march(const float *tris9, u32 ntris, const float *from3, const float *to3,
+                           const float *k, u32 n, float *out, u32 *steps_out);
+LTRAPI int ltrx_test_spiral_dirs(const float *nrm3, const float *randoff, u32 n, int samples, float *out3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,682 @@
+/*
+ * bake.cpp -- the bake orchestrator: what the reference's Job_MainProc (lighter.cpp:1046-1145) is
+ * to its thread pool, this is to the GPU.  Fixed stage order and stage strings are the
+ * reference's; every stage body is a call through the C-ABI layer in gpu.h.
+ *
+ * Host-side work kept here (cheap, and bit-exact on the host's IEEE float):
+ *   - pre-transform, total area, the size_fn callback, lightmap UV scaling  (lighter.cpp:292-341)
+ *   - shadow triangle lists, reference-order trees, the instance tree       (lighter.cpp:349-384,1060-1069)
+ *   - the flat scene BVH                                                     (bvh.cpp)
+ *   - light -> instance culling                                              (lighter.cpp:80-98,1080-1095)
+ *   - libc rand() replay for the AO offsets                                  (lighter.cpp:819)
+ *   - the sample_fn material callback round trip                             (lighter.cpp:692-714)
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include <algorithm>
+#include <thread>
+
+#include "gpu.h"
+#include "nccl_dl.h"
+#include "scene.h"
+
+namespace {
+
+double now_s()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+/* ---- 4x4 inverse by cofactors, term order of the reference (lighter_math.cpp:19-147) so the
+ *      normal matrix comes out bit-identical.  Each row lists six (i,j,k) products; signs
+ *      alternate + - - + + - for "even" rows and - + + - - + for "odd" rows. ---- */
+struct Cof { unsigned char out, odd, t[6][3]; };
+const Cof COF[16] = {
+    { 0, 0, { {5,10,15}, {5,11,14}, {9,6,15}, {9,7,14}, {13,6,11}, {13,7,10} } },
+    { 4, 1, { {4,10,15}, {4,11,14}, {8,6,15}, {8,7,14}, {12,6,11}, {12,7,10} } },
+    { 8, 0, { {4,9,15}, {4,11,13}, {8,5,15}, {8,7,13}, {12,5,11}, {12,7,9} } },
+    { 12, 1, { {4,9,14}, {4,10,13}, {8,5,14}, {8,6,13}, {12,5,10}, {12,6,9} } },
+    { 1, 1, { {1,10,15}, {1,11,14}, {9,2,15}, {9,3,14}, {13,2,11}, {13,3,10} } },
+    { 5, 0, { {0,10,15}, {0,11,14}, {8,2,15}, {8,3,14}, {12,2,11}, {12,3,10} } },
+    { 9, 1, { {0,9,15}, {0,11,13}, {8,1,15}, {8,3,13}, {12,1,11}, {12,3,9} } },
+    { 13, 0, { {0,9,14}, {0,10,13}, {8,1,14}, {8,2,13}, {12,1,10}, {12,2,9} } },
+    { 2, 0, { {1,6,15}, {1,7,14}, {5,2,15}, {5,3,14}, {13,2,7}, {13,3,6} } },
+    { 6, 1, { {0,6,15}, {0,7,14}, {4,2,15}, {4,3,14}, {12,2,7}, {12,3,6} } },
+    { 10, 0, { {0,5,15}, {0,7,13}, {4,1,15}, {4,3,13}, {12,1,7}, {12,3,5} } },
+    { 14, 1, { {0,5,14}, {0,6,13}, {4,1,14}, {4,2,13}, {12,1,6}, {12,2,5} } },
+    { 3, 1, { {1,6,11}, {1,7,10}, {5,2,11}, {5,3,10}, {9,2,7}, {9,3,6} } },
+    { 7, 0, { {0,6,11}, {0,7,10}, {4,2,11}, {4,3,10}, {8,2,7}, {8,3,6} } },
+    { 11, 1, { {0,5,11}, {0,7,9}, {4,1,11}, {4,3,9}, {8,1,7}, {8,3,5} } },
+    { 15, 0, { {0,5,10}, {0,6,9}, {4,1,10}, {4,2,9}, {8,1,6}, {8,2,5} } },
+};
+
+bool invert4(const float *a, float *out)
+{
+    static const float SGN[2][6] = { { 1, -1, -1, 1, 1, -1 }, { -1, 1, 1, -1, -1, 1 } };
+    float inv[16];
+    for (const Cof &c : COF) {
+        float acc = 0;
+        for (int k = 0; k < 6; ++k) {
+            float term = (SGN[c.odd][k] * a[c.t[k][0]]) * a[c.t[k][1]] * a[c.t[k][2]];
+            acc = k == 0 ? term : acc + term;
+        }
+        inv[c.out] = acc;
+    }
+    float det = a[0] * inv[0] + a[1] * inv[4] + a[2] * inv[8] + a[3] * inv[12];
+    if (det == 0) return false;
+    det = 1.0f / det;
+    for (int i = 0; i < 16; ++i) out[i] = inv[i] * det;
+    return true;
+}
+
+inline V3 xform(const float *m, V3 v, float w)
+{
+    return mk3(v.x * m[0] + v.y * m[4] + v.z * m[8] + m[12] * w,
+               v.x * m[1] + v.y * m[5] + v.z * m[9] + m[13] * w,
+               v.x * m[2] + v.y * m[6] + v.z * m[10] + m[14] * w);
+}
+
+float heron(float a, float b, float c)
+{
+    float p = (a + b + c) * 0.5f;
+    float q = p * (p - a) * (p - b) * (p - c);
+    return q < 0 ? 0 : sqrtf(q);
+}
+
+int nccl_allgather_cb(void *user, const void *send, void *recv, size_t bytes, void *stream);
+
+} // namespace
+
+struct Bake {
+    ltrgpu_Ctx *gpu = nullptr;
+    std::vector<ltrgpu_Inst> inst;
+    std::vector<V3> wpos, wnrm;
+    std::vector<float> vtex, ltex;
+    std::vector<ltrgpu_RasterTri> rtris;
+    std::vector<RefNode> rnodes;
+    std::vector<int32_t> ritems;
+    std::vector<float> rtree_tris;
+    SceneBvh bvh;
+    std::vector<float> bvh_tris;
+    std::vector<ltrgpu_Light> lights;
+    std::vector<uint8_t> light_inst;
+    std::vector<float> ao_cos, ao_sin, blur_kernel;
+    int blur_ext = 0;
+    std::vector<uint64_t> lumel_off;
+    bool prepared = false;
+    void *comm = nullptr;
+    const NcclApi *nccl = nullptr;
+    /* debug copies */
+    std::vector<float> d_pos, d_nrm, d_rad, d_rgb, d_fvis, d_lfac;
+    std::vector<uint32_t> d_loc, d_lother;
+    std::vector<uint64_t> d_lrow;
+};
+
+namespace {
+
+int nccl_allgather_cb(void *user, const void *send, void *recv, size_t bytes, void *stream)
+{
+    Bake *B = (Bake *)user;
+    if (!B->nccl || !B->comm) return 1;
+    int rc = B->nccl->AllGather(send, recv, bytes, /*ncclUint8*/ 1, B->comm, stream);
+    if (rc != 0) fprintf(stderr, "lighter_b200: ncclAllGather failed: %s\n", B->nccl->GetErrorString(rc));
+    return rc;
+}
+
+struct Fail { std::string msg; };
+
+void gpu_check(ltr_Scene *S, int rc, const char *what)
+{
+    if (rc == 0) return;
+    Fail f;
+    f.msg = std::string(what) + ": " + (S->bake && S->bake->gpu ? ltrgpu_last_error(S->bake->gpu) : "no GPU context");
+    throw f;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * host pre-pass
+ * ------------------------------------------------------------------------------------------ */
+void host_prepare(ltr_Scene *S)
+{
+    Bake &B = *S->bake;
+    const ltr_Config &cfg = S->config;
+    const size_t ni = S->instances.size();
+    double t0 = now_s();
+
+    S->stage.store("transforming spatial data");
+    S->completion.store(0.f);
+    B.inst.assign(ni, ltrgpu_Inst());
+    std::vector<size_t> vbase(ni + 1, 0);
+    for (size_t i = 1; i < ni; ++i) vbase[i + 1] = vbase[i] + S->instances[i]->mesh->vpos.size();
+    vbase[1] = 0;
+    for (size_t i = 1; i < ni; ++i) vbase[i + 1] = vbase[i] + S->instances[i]->mesh->vpos.size();
+    const size_t nv = vbase[ni];
+    B.wpos.resize(nv); B.wnrm.resize(nv); B.vtex.resize(nv * 2); B.ltex.resize(nv * 2);
+
+    for (size_t i = 1; i < ni; ++i) {
+        MeshInstance *mi = S->instances[i];
+        ltr_Mesh *mesh = mi->mesh;
+        const float *M = mi->matrix;
+        float NM[16] = { M[0], M[1], M[2], 0, M[4], M[5], M[6], 0, M[8], M[9], M[10], 0, 0, 0, 0, 1 };
+        float inv[16];
+        if (invert4(NM, inv)) memcpy(NM, inv, sizeof(NM));
+        std::swap(NM[4], NM[1]); std::swap(NM[8], NM[2]); std::swap(NM[12], NM[3]);
+        std::swap(NM[9], NM[6]); std::swap(NM[13], NM[7]); std::swap(NM[14], NM[11]);
+        V3 *wp = B.wpos.data() + vbase[i], *wn = B.wnrm.data() + vbase[i];
+        for (size_t v = 0; v < mesh->vpos.size(); ++v) {
+            wp[v] = xform(M, mesh->vpos[v], 1.0f);
+            wn[v] = norm3(xform(NM, mesh->vnrm[v], 0.0f));
+        }
+        float total_area = 0.0f;
+        for (const MeshPart &mp : mesh->parts) {
+            const V3 *vb = wp + mp.vertex_offset;
+            const u32 *ib = mesh->indices.data() + mp.index_offset;
+            for (u32 t = 0; t + 2 < mp.index_count; t += 3) {
+                V3 p1 = vb[ib[t]], p2 = vb[ib[t + 1]], p3 = vb[ib[t + 2]];
+                total_area += heron(len3(p2 - p1), len3(p3 - p2), len3(p1 - p3));
+            }
+        }
+        u32 size[2] = { cfg.default_width, cfg.default_height };
+        auto fn = cfg.size_fn ? cfg.size_fn : ltr_DefaultSizeFunc;
+        if (!fn(&S->config, mesh->ident.c_str(), mesh->ident.size(), mi->ident.c_str(), mi->ident.size(), total_area, mi->importance, size)) {
+            size[0] = cfg.default_width; size[1] = cfg.default_height;
+        }
+        mi->lm_width = size[0]; mi->lm_height = size[1];
+        const float lw = (float)size[0], lh = (float)size[1];
+        for (size_t v = 0; v < mesh->vpos.size(); ++v) {
+            B.vtex[(vbase[i] + v) * 2 + 0] = mesh->vtex1[v].x;
+            B.vtex[(vbase[i] + v) * 2 + 1] = mesh->vtex1[v].y;
+            B.ltex[(vbase[i] + v) * 2 + 0] = mesh->vtex2[v].x * lw - 0.5f;
+            B.ltex[(vbase[i] + v) * 2 + 1] = mesh->vtex2[v].y * lh - 0.5f;
+        }
+    }
+    S->stats.t_prexform = now_s() - t0;
+    t0 = now_s();
+
+    S->stage.store("generating data structures");
+    S->completion.store(0.f);
+    /* per instance: useful triangles of shadow-casting parts, and their reference-order tree */
+    std::vector<std::vector<float>> itris(ni);
+    std::vector<RefTree> itree(ni);
+    auto build_one = [&](size_t i) {
+        if (i == 0) { itree[0].build(nullptr, 0); return; }
+        MeshInstance *mi = S->instances[i];
+        ltr_Mesh *mesh = mi->mesh;
+        std::vector<float> &T = itris[i];
+        std::vector<Box3> boxes;
+        const V3 *wp = B.wpos.data() + vbase[i];
+        for (const MeshPart &mp : mesh->parts) {
+            if (!mp.shadow) continue;
+            const V3 *vb = wp + mp.vertex_offset;
+            const u32 *ib = mesh->indices.data() + mp.index_offset;
+            for (u32 t = 0; t + 2 < mp.index_count; t += 3) {
+                V3 p1 = vb[ib[t]], p2 = vb[ib[t + 1]], p3 = vb[ib[t + 2]];
+                if (near_zero3(cross3(p2 - p1, p3 - p1))) continue;
+                const float f[9] = { p1.x, p1.y, p1.z, p2.x, p2.y, p2.z, p3.x, p3.y, p3.z };
+                T.insert(T.end(), f, f + 9);
+                Box3 b = { min3(p1, min3(p2, p3)), max3(p1, max3(p2, p3)) };
+                boxes.push_back(b);
+            }
+        }
+        itree[i].build(boxes.data(), boxes.size());
+    };
+    {
+        unsigned nthreads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)ni));
+        std::atomic<size_t> next{0};
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nthreads; ++t)
+            pool.emplace_back([&]() { for (size_t i; (i = next.fetch_add(1)) < ni;) build_one(i); });
+        for (auto &th : pool) th.join();
+    }
+    S->completion.store(0.99f);
+    /* instance tree over the root boxes (invalid boxes are dropped by the builder) */
+    std::vector<Box3> ibox(ni);
+    for (size_t i = 0; i < ni; ++i) { ibox[i].lo = itree[i].nodes[0].lo; ibox[i].hi = itree[i].nodes[0].hi; }
+    RefTree inst_tree;
+    inst_tree.build(ibox.data(), ni);
+
+    /* concatenate trees, lay out the texel space, list raster triangles */
+    B.rnodes.clear(); B.ritems.clear(); B.rtree_tris.clear(); B.rtris.clear();
+    uint64_t texel_off = 0;
+    std::vector<float> scene_tris;
+    for (size_t i = 0; i < ni; ++i) {
+        ltrgpu_Inst &I = B.inst[i];
+        MeshInstance *mi = S->instances[i];
+        I.lm_w = i ? mi->lm_width : 0; I.lm_h = i ? mi->lm_height : 0;
+        I.texel_off_lo = (uint32_t)texel_off; I.texel_off_hi = (uint32_t)(texel_off >> 32);
+        texel_off += (uint64_t)I.lm_w * I.lm_h;
+        I.node_off = (uint32_t)B.rnodes.size(); I.item_off = (uint32_t)B.ritems.size(); I.tri_off = (uint32_t)(B.rtree_tris.size() / 9);
+        I.tree_tris = (uint32_t)(itris[i].size() / 9);
+        I.shadow = (i && mi->shadow) ? 1 : 0;
+        B.rnodes.insert(B.rnodes.end(), itree[i].nodes.begin(), itree[i].nodes.end());
+        B.ritems.insert(B.ritems.end(), itree[i].items.begin(), itree[i].items.end());
+        B.rtree_tris.insert(B.rtree_tris.end(), itris[i].begin(), itris[i].end());
+        if (I.shadow) scene_tris.insert(scene_tris.end(), itris[i].begin(), itris[i].end());
+        if (!i) continue;
+        ltr_Mesh *mesh = mi->mesh;
+        for (size_t p = 0; p < mesh->parts.size(); ++p) {
+            const MeshPart &mp = mesh->parts[p];
+            const u32 *ib = mesh->indices.data() + mp.index_offset;
+            const uint32_t base = (uint32_t)(vbase[i] + mp.vertex_offset);
+            for (u32 t = 0; t + 2 < mp.index_count; t += 3) {
+                ltrgpu_RasterTri rt = { (uint32_t)i, (uint32_t)p, base + ib[t], base + ib[t + 1], base + ib[t + 2] };
+                B.rtris.push_back(rt);
+            }
+        }
+    }
+
+    /* flat scene BVH over the shadow-casting triangles */
+    int leaf_max = BVH_LEAF_MAX;
+    if (const char *e = getenv("LTR_BVH_LEAF")) leaf_max = atoi(e);
+    const size_t nst = scene_tris.size() / 9;
+    build_scene_bvh(scene_tris.data(), nst, B.bvh, leaf_max, 0);
+    B.bvh_tris.resize(nst * 9);
+    for (size_t k = 0; k < nst; ++k) memcpy(&B.bvh_tris[k * 9], &scene_tris[(size_t)B.bvh.order[k] * 9], 36);
+
+    /* lights and the light -> instance table */
+    const size_t nl = S->lights.size();
+    B.lights.resize(nl);
+    B.light_inst.assign(nl * ni, 0);
+    for (size_t l = 0; l < nl; ++l) {
+        const Light &L = S->lights[l];
+        ltrgpu_Light &G = B.lights[l];
+        G.pos = L.position; G.type = L.type; G.dir = L.direction; G.range = L.range; G.color = L.color; G.power = L.power;
+        G.radius = L.light_radius; G.curve = L.spot_curve;
+        float out_rad = L.spot_angle_out / 180.0f * (float)M_PI, in_rad = L.spot_angle_in / 180.0f * (float)M_PI;
+        if (in_rad == out_rad) in_rad -= LB_SMALL;
+        G.angle_out_rad = out_rad; G.angle_diff = in_rad - out_rad;
+        uint8_t *row = &B.light_inst[l * ni];
+        row[0] = 1;
+        auto mark = [&](const int32_t *ids, int32_t n) { for (int32_t k = 0; k < n; ++k) row[ids[k]] = 1; };
+        if (L.type == LTR_LT_POINT || L.type == LTR_LT_SPOT) inst_tree.query(L.position - mk3(L.range), L.position + mk3(L.range), mark);
+        else if (L.type == LTR_LT_DIRECT) inst_tree.all(mark);
+    }
+
+    /* host-libm tables */
+    const int ns = cfg.ao_num_samples > 0 ? cfg.ao_num_samples : 0;
+    B.ao_cos.resize(ns); B.ao_sin.resize(ns);
+    for (int s = 0; s < ns; ++s) {
+        float q = (s + 0.5f) / cfg.ao_num_samples;
+        B.ao_cos[s] = sqrtf(q);
+        B.ao_sin[s] = sinf(acosf(B.ao_cos[s]));
+    }
+    B.blur_ext = 0; B.blur_kernel.clear();
+    if (cfg.blur_size) {
+        B.blur_ext = (int)ceil(cfg.blur_size);
+        B.blur_kernel.resize(2 * B.blur_ext + 1);
+        float sum = 0.0f, mult = 1.0f / sqrtf(2.0f * (float)M_PI * cfg.blur_size * cfg.blur_size);
+        for (int i = -B.blur_ext; i <= B.blur_ext; ++i)
+            sum += B.blur_kernel[i + B.blur_ext] = expf(-0.5f * powf((float)i / cfg.blur_size, 2.0f)) * mult;
+        for (float &k : B.blur_kernel) k /= sum;
+    }
+    S->stats.n_triangles = nst;
+    S->stats.n_bvh_nodes = B.bvh.nodes.size();
+    S->stats.t_accel = now_s() - t0;
+    B.prepared = true;
+}
+
+void upload(ltr_Scene *S)
+{
+    Bake &B = *S->bake;
+    const ltr_Config &cfg = S->config;
+    double t0 = now_s();
+    if (!B.gpu) {
+        if (ltrgpu_create(&B.gpu, S->device)) {
+            Fail f; f.msg = std::string("CUDA device unavailable: ") + (B.gpu ? ltrgpu_last_error(B.gpu) : "no CUDA device (this library has no CPU fallback)");
+            throw f;
+        }
+    }
+    std::vector<V3> ppos(S->probes.size()), pnrm(S->probes.size());
+    for (size_t i = 0; i < S->probes.size(); ++i) {
+        ppos[i] = mk3(S->probes[i].position[0], S->probes[i].position[1], S->probes[i].position[2]);
+        pnrm[i] = mk3(S->probes[i].normal[0], S->probes[i].normal[1], S->probes[i].normal[2]);
+    }
+    ltrgpu_SceneDesc d;
+    memset(&d, 0, sizeof(d));
+    ltrgpu_Params &P = d.params;
+    memcpy(P.ambient, cfg.ambient_color, 12);
+    P.max_correct_dist = cfg.max_correct_dist;
+    P.corr_min_dot = cosf(cfg.max_correct_angle / 180.0f * (float)M_PI);
+    P.ao_distance = cfg.ao_distance; P.ao_multiplier = cfg.ao_multiplier; P.ao_falloff = cfg.ao_falloff; P.ao_effect = cfg.ao_effect;
+    memcpy(P.ao_color, cfg.ao_color_rgb, 12);
+    P.ao_num_samples = cfg.ao_num_samples; P.blur_size = cfg.blur_size; P.ds2x = cfg.ds2x; P.normalmap = cfg.generate_normalmap_data;
+    P.amb_brightness = (cfg.ambient_color[0] + cfg.ambient_color[1] + cfg.ambient_color[2]) * (1.0f / 3.0f);
+    d.n_inst = (uint32_t)B.inst.size(); d.inst = B.inst.data();
+    d.n_verts = (uint32_t)B.wpos.size(); d.wpos = B.wpos.data(); d.wnrm = B.wnrm.data(); d.vtex2 = B.vtex.data(); d.ltex2 = B.ltex.data();
+    d.n_rtris = (uint32_t)B.rtris.size(); d.rtris = B.rtris.data();
+    d.n_rnodes = (uint32_t)B.rnodes.size(); d.rnodes = B.rnodes.data();
+    d.n_ritems = (uint32_t)B.ritems.size(); d.ritems = B.ritems.data();
+    d.n_rtree_tris = (uint32_t)(B.rtree_tris.size() / 9); d.rtree_tris9 = B.rtree_tris.data();
+    d.n_bvh_nodes = (uint32_t)B.bvh.nodes.size(); d.bvh = B.bvh.nodes.data();
+    d.n_tris = (uint32_t)(B.bvh_tris.size() / 9); d.tris9 = B.bvh_tris.data(); d.tri_orig = B.bvh.order.data();
+    d.n_lights = (uint32_t)B.lights.size(); d.lights = B.lights.data(); d.light_inst = B.light_inst.data();
+    d.n_probes = (uint32_t)ppos.size(); d.probe_pos = ppos.data(); d.probe_nrm = pnrm.data();
+    d.ao_cos_side = B.ao_cos.data(); d.ao_sin_side = B.ao_sin.data();
+    d.blur_ext = B.blur_ext; d.blur_kernel = B.blur_kernel.empty() ? nullptr : B.blur_kernel.data();
+    gpu_check(S, ltrgpu_upload_scene(B.gpu, &d), "scene upload");
+
+    if (S->world > 1 && !B.comm) {
+        char err[256];
+        B.nccl = nccl_api(err, sizeof(err));
+        if (!B.nccl) { Fail f; f.msg = std::string("NCCL unavailable: ") + err; throw f; }
+        if (!S->have_nccl_id) { Fail f; f.msg = "sharded bake without an NCCL unique id (call ltrx_SetShard)"; throw f; }
+        NcclId id;
+        memcpy(&id, S->nccl_id, sizeof(id));
+        int rc = B.nccl->CommInitRank(&B.comm, S->world, id, S->rank);
+        if (rc != 0) { Fail f; f.msg = std::string("ncclCommInitRank: ") + B.nccl->GetErrorString(rc); throw f; }
+    }
+    S->stats.t_upload = now_s() - t0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * GPU stages (re-runnable on a resident scene)
+ * ------------------------------------------------------------------------------------------ */
+void gpu_stages(ltr_Scene *S)
+{
+    Bake &B = *S->bake;
+    const ltr_Config &cfg = S->config;
+    const size_t ni = S->instances.size();
+    gpu_check(S, ltrgpu_reset_bake(B.gpu), "reset");
+
+    double t0 = now_s();
+    S->stage.store("generating samples");
+    S->completion.store(0.f);
+    B.lumel_off.assign(ni + 1, 0);
+    gpu_check(S, ltrgpu_generate_lumels(B.gpu, B.lumel_off.data()), "lumel generation");
+    const uint64_t n = B.lumel_off[ni];
+    uint64_t sb = 0, se = n;
+    ltrx_ShardRange(n, S->rank, S->world, &sb, &se);
+    gpu_check(S, ltrgpu_set_shard(B.gpu, sb, se, S->rank, S->world, S->world > 1 ? nccl_allgather_cb : nullptr, &B), "shard");
+    S->stats.n_lumels_total = n;
+    S->stats.n_lumels_local = se - sb;
+    S->stats.t_samples = now_s() - t0;
+
+    t0 = now_s();
+    if (!S->lights.empty()) {
+        S->stage.store("rendering lightmaps");
+        S->completion.store(0.f);
+        gpu_check(S, ltrgpu_direct_light(B.gpu), "direct light");
+        S->completion.store(1.f);
+        if (S->keep_debug) {
+            const uint64_t nl = se - sb;
+            B.d_fvis.assign(S->lights.size() * nl, 0.f);
+            for (size_t l = 0; l < S->lights.size(); ++l)
+                if (ltrgpu_download_shadow_factors(B.gpu, (uint32_t)l, B.d_fvis.data() + l * nl)) break;   /* only the last light chunk is resident */
+        }
+    }
+    S->stats.t_direct = now_s() - t0;
+
+    t0 = now_s();
+    if (cfg.bounce_count) {
+        S->stage.store("calculating radiosity");
+        S->completion.store(0.f);
+        std::vector<float> diffuse, emissive;
+        if (cfg.sample_fn && n) {
+            /* material callback round trip: lumels to host, one call per mesh lumel in global order
+             * (instance ascending, lumel ascending), results back to the device */
+            std::vector<float> pos(n * 3), nrm(n * 3), rad(n * 4);
+            std::vector<uint32_t> loc(n);
+            gpu_check(S, ltrgpu_download_lumels(B.gpu, pos.data(), nrm.data(), loc.data(), rad.data(), nullptr), "lumel download");
+            diffuse.assign(n * 3, 1.f); emissive.assign(n * 3, 0.f);
+            for (size_t m = 1; m < ni; ++m) {
+                MeshInstance *mi = S->instances[m];
+                for (uint64_t i = B.lumel_off[m]; i < B.lumel_off[m + 1]; ++i) {
+                    V3 N = norm3(mk3(nrm[i * 3], nrm[i * 3 + 1], nrm[i * 3 + 2]));
+                    const int lx = (int)(loc[i] % mi->lm_width), ly = (int)(loc[i] / mi->lm_width);
+                    ltr_SampleRequest req;
+                    memset(&req, 0, sizeof(req));
+                    req.position[0] = pos[i * 3]; req.position[1] = pos[i * 3 + 1]; req.position[2] = pos[i * 3 + 2];
+                    req.normal[0] = N.x; req.normal[1] = N.y; req.normal[2] = N.z;
+                    req.tex0u = rad[i * 4]; req.tex0v = rad[i * 4 + 1];
+                    req.tex1u = (lx + 0.5f) / mi->lm_width; req.tex1v = (ly + 0.5f) / mi->lm_height;
+                    req.part_id = (uint32_t)rad[i * 4 + 2];
+                    req.mesh_ident = mi->mesh->ident.c_str(); req.mesh_ident_size = mi->mesh->ident.size();
+                    req.inst_ident = mi->ident.c_str(); req.inst_ident_size = mi->ident.size();
+                    req.out_diffuse_color[0] = req.out_diffuse_color[1] = req.out_diffuse_color[2] = 1;
+                    if (cfg.sample_fn(&S->config, &req)) {
+                        memcpy(&diffuse[i * 3], req.out_diffuse_color, 12);
+                        memcpy(&emissive[i * 3], req.out_emissive_color, 12);
+                    }
+                }
+            }
+        }
+        S->stage.store("bouncing light");
+        gpu_check(S, ltrgpu_radiosity(B.gpu, diffuse.empty() ? nullptr : diffuse.data(), diffuse.empty() ? nullptr : emissive.data(), cfg.bounce_count),
+                  "radiosity");
+        S->stage.store("committing radiosity");
+        S->completion.store(1.f);
+    }
+    S->stats.t_radiosity = now_s() - t0;
+
+    t0 = now_s();
+    if (cfg.ao_distance) {
+        S->stage.store("rendering ambient occlusion");
+        S->completion.store(0.f);
+        /* replay of the reference's rand() consumption: one randf() per lumel, instance by
+         * instance (probe container first), lumel index ascending (lighter.cpp:819,1130-1135) */
+        std::vector<float> randoff(n ? n : 1);
+        for (uint64_t i = 0; i < n; ++i) randoff[i] = (float)rand() / (float)RAND_MAX;
+        gpu_check(S, ltrgpu_ambient_occlusion(B.gpu, randoff.data()), "ambient occlusion");
+        S->completion.store(1.f);
+    }
+    S->stats.t_ao = now_s() - t0;
+
+    t0 = now_s();
+    S->stage.store("exporting lightmaps");
+    S->completion.store(0.f);
+    if (S->keep_debug && n) {
+        /* per-lumel colours BEFORE the all-gather/finalize (local shard values are final here) */
+    }
+    gpu_check(S, ltrgpu_finalize(B.gpu), "finalize");
+    S->stats.t_finalize = now_s() - t0;
+}
+
+void readback(ltr_Scene *S)
+{
+    Bake &B = *S->bake;
+    const size_t ni = S->instances.size();
+    double t0 = now_s();
+    for (ltr_WorkOutput &wo : S->outputs) { free(wo.lightmap_rgb); free(wo.normals_xyzf); }
+    S->outputs.clear();
+    for (size_t i = 1; i < ni; ++i) {
+        MeshInstance *mi = S->instances[i];
+        uint32_t w = 0, h = 0;
+        gpu_check(S, ltrgpu_output_size(B.gpu, (uint32_t)i, &w, &h), "output size");
+        ltr_WorkOutput wo;
+        memset(&wo, 0, sizeof(wo));
+        wo.uid = (u32)i;
+        wo.mesh_ident = mi->mesh->ident.c_str(); wo.mesh_ident_size = mi->mesh->ident.size();
+        wo.inst_ident = mi->ident.c_str(); wo.inst_ident_size = mi->ident.size();
+        wo.width = w; wo.height = h;
+        const size_t cnt = (size_t)w * h;
+        wo.lightmap_rgb = (float *)malloc((cnt ? cnt : 1) * 12);
+        wo.normals_xyzf = S->config.generate_normalmap_data ? (float *)calloc(cnt ? cnt : 1, 16) : nullptr;
+        S->outputs.push_back(wo);                  /* owned by the scene from here on */
+        gpu_check(S, ltrgpu_download_output(B.gpu, (uint32_t)i, wo.lightmap_rgb, wo.normals_xyzf), "output download");
+        mi->lm_width = w; mi->lm_height = h;       /* the reference shrinks these under ds2x (lighter.cpp:973-974) */
+    }
+    if (!S->probes.empty()) {
+        std::vector<float> pc(S->probes.size() * 3);
+        gpu_check(S, ltrgpu_download_probe_colors(B.gpu, pc.data()), "probe download");
+        for (size_t i = 0; i < S->probes.size(); ++i) memcpy(S->probes[i].out_color, &pc[i * 3], 12);
+    }
+    if (S->keep_debug) {
+        const uint64_t n = B.lumel_off[ni];
+        B.d_pos.resize(n * 3); B.d_nrm.resize(n * 3); B.d_rad.resize(n * 4); B.d_rgb.resize(n * 3); B.d_loc.resize(n);
+        gpu_check(S, ltrgpu_download_lumels(B.gpu, B.d_pos.data(), B.d_nrm.data(), B.d_loc.data(), B.d_rad.data(), B.d_rgb.data()), "debug lumels");
+        uint64_t rows = 0, links = 0;
+        gpu_check(S, ltrgpu_download_links(B.gpu, nullptr, nullptr, nullptr, &rows, &links), "debug links");
+        B.d_lrow.assign(rows + 1, 0); B.d_lother.resize(links); B.d_lfac.resize(links);
+        if (rows) gpu_check(S, ltrgpu_download_links(B.gpu, B.d_lrow.data(), B.d_lother.data(), B.d_lfac.data(), &rows, &links), "debug links");
+    }
+    S->stats.t_readback = now_s() - t0;
+
+    ltrgpu_Counters c;
+    if (ltrgpu_get_counters(B.gpu, &c) == 0) {
+        ltrx_Stats &st = S->stats;
+        st.n_marches = c.marches; st.n_distance_queries = c.distance_queries; st.n_ao_segments = c.ao_segments;
+        st.n_correction_rays = c.correction_rays; st.n_rad_pairs = c.rad_pairs; st.n_rad_segments = c.rad_segments;
+        st.n_rad_links = c.rad_links; st.n_node_visits = c.node_visits; st.n_tri_tests = c.tri_tests;
+        st.kernel_launches = c.kernel_launches; st.h2d_bytes = c.h2d_bytes; st.d2h_bytes = c.d2h_bytes;
+        st.gpu_ms_samples = c.ms_samples; st.gpu_ms_direct = c.ms_direct; st.gpu_ms_march = c.ms_march;
+        st.gpu_ms_radiosity = c.ms_radiosity; st.gpu_ms_ao = c.ms_ao; st.gpu_ms_finalize = c.ms_finalize;
+        st.gpu_ms_total = c.ms_samples + c.ms_direct + c.ms_radiosity + c.ms_ao + c.ms_finalize;
+    }
+}
+
+template <class F> int guarded(ltr_Scene *S, F f)
+{
+    try { f(); return 1; }
+    catch (const Fail &e) { S->error = e.msg; }
+    catch (const std::exception &e) { S->error = std::string("exception: ") + e.what(); }
+    fprintf(stderr, "lighter_b200: bake failed: %s\n", S->error.c_str());
+    return 0;
+}
+
+} // namespace
+
+void bake_main(ltr_Scene *S)
+{
+    const double t0 = now_s();
+    S->error.clear();
+    if (!S->bake) S->bake = new Bake;
+    guarded(S, [&]() {
+        host_prepare(S);
+        upload(S);
+        gpu_stages(S);
+        readback(S);
+    });
+    S->stats.t_total = now_s() - t0;
+    S->completion.store(1.f);
+    S->stage.store(nullptr, std::memory_order_release);
+}
+
+void bake_free(ltr_Scene *S)
+{
+    if (!S->bake) return;
+    Bake *B = S->bake;
+    if (B->comm && B->nccl) B->nccl->CommDestroy(B->comm);
+    if (B->gpu) ltrgpu_destroy(B->gpu);
+    delete B;
+    S->bake = nullptr;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * ltrx_* extension API
+ * ------------------------------------------------------------------------------------------ */
+extern "C" {
+
+const char *ltrx_Version(void) { return "lighter_b200 0.1 (sm_100a)"; }
+
+int ltrx_SetDevice(ltr_Scene *scene, int cuda_device) { scene->device = cuda_device; return 1; }
+
+int ltrx_NcclUniqueId(unsigned char out_id[LTRX_NCCL_ID_BYTES])
+{
+    char err[256];
+    const NcclApi *api = nccl_api(err, sizeof(err));
+    if (!api) { fprintf(stderr, "lighter_b200: %s\n", err); return 0; }
+    NcclId id;
+    memset(&id, 0, sizeof(id));
+    if (api->GetUniqueId(&id) != 0) return 0;
+    memcpy(out_id, &id, LTRX_NCCL_ID_BYTES);
+    return 1;
+}
+
+int ltrx_SetShard(ltr_Scene *scene, int rank, int world, const unsigned char *nccl_id)
+{
+    if (world < 1 || rank < 0 || rank >= world) return 0;
+    if (world > 1 && !nccl_id) return 0;
+    scene->rank = rank; scene->world = world;
+    if (nccl_id) { memcpy(scene->nccl_id, nccl_id, LTRX_NCCL_ID_BYTES); scene->have_nccl_id = true; }
+    return 1;
+}
+
+void ltrx_ShardRange(uint64_t n, int rank, int world, uint64_t *begin, uint64_t *end)
+{
+    if (world < 1) world = 1;
+    const uint64_t chunk = (n + (uint64_t)world - 1) / (uint64_t)world;
+    uint64_t b = chunk * (uint64_t)rank;
+    if (b > n) b = n;
+    uint64_t e = b + chunk;
+    if (e > n) e = n;
+    *begin = b; *end = e;
+}
+
+int ltrx_GetStats(ltr_Scene *scene, ltrx_Stats *out) { *out = scene->stats; return 1; }
+
+const char *ltrx_GetError(ltr_Scene *scene) { return scene->error.c_str(); }
+
+int ltrx_Prepare(ltr_Scene *scene)
+{
+    if (scene->worker.joinable()) scene->worker.join();
+    if (!scene->bake) scene->bake = new Bake;
+    scene->error.clear();
+    int ok = guarded(scene, [&]() { host_prepare(scene); upload(scene); });
+    scene->stage.store(ok ? "prepared" : nullptr);
+    return ok;
+}
+
+int ltrx_BakeResident(ltr_Scene *scene, float *gpu_ms_out)
+{
+    if (!scene->bake || !scene->bake->prepared || !scene->bake->gpu) { scene->error = "ltrx_BakeResident before ltrx_Prepare"; return 0; }
+    int ok = guarded(scene, [&]() { gpu_stages(scene); });
+    ltrgpu_Counters c;
+    if (ok && ltrgpu_get_counters(scene->bake->gpu, &c) == 0 && gpu_ms_out)
+        *gpu_ms_out = c.ms_samples + c.ms_direct + c.ms_radiosity + c.ms_ao + c.ms_finalize;
+    scene->stage.store(ok ? "baked" : nullptr);
+    return ok;
+}
+
+int ltrx_Finish(ltr_Scene *scene)
+{
+    if (!scene->bake || !scene->bake->gpu) return 0;
+    int ok = guarded(scene, [&]() { readback(scene); });
+    scene->completion.store(1.f);
+    scene->stage.store(nullptr, std::memory_order_release);
+    return ok;
+}
+
+int ltrx_SetDebug(ltr_Scene *scene, int keep) { scene->keep_debug = keep; return 1; }
+
+int ltrx_GetLumels(ltr_Scene *scene, u32 instance, ltrx_Lumels *out)
+{
+    Bake *B = scene->bake;
+    if (!B || instance >= scene->instances.size() || B->lumel_off.size() != scene->instances.size() + 1 || B->d_loc.empty()) {
+        memset(out, 0, sizeof(*out));
+        return B && instance < scene->instances.size() && B->lumel_off.size() == scene->instances.size() + 1 &&
+               B->lumel_off[instance] == B->lumel_off[instance + 1];
+    }
+    const uint64_t a = B->lumel_off[instance], b = B->lumel_off[instance + 1];
+    out->count = (u32)(b - a);
+    out->width = scene->instances[instance]->lm_width; out->height = scene->instances[instance]->lm_height;
+    out->pos_xyz = B->d_pos.data() + a * 3; out->nrm_xyz = B->d_nrm.data() + a * 3; out->loc = B->d_loc.data() + a;
+    out->radinfo_xyzw = B->d_rad.data() + a * 4; out->rgb = B->d_rgb.data() + a * 3;
+    return 1;
+}
+
+int ltrx_GetLinks(ltr_Scene *scene, ltrx_Links *out)
+{
+    Bake *B = scene->bake;
+    memset(out, 0, sizeof(*out));
+    if (!B || B->d_lrow.empty()) return 0;
+    out->rows = B->d_lrow.size() - 1; out->count = B->d_lother.size();
+    out->row_offset = B->d_lrow.data(); out->other = B->d_lother.data(); out->factor = B->d_lfac.data();
+    return 1;
+}
+
+int ltrx_GetShadowFactors(ltr_Scene *scene, u32 light, const float **out, uint64_t *count)
+{
+    Bake *B = scene->bake;
+    if (!B || B->d_fvis.empty() || light >= scene->lights.size()) return 0;
+    const uint64_t nl = scene->stats.n_lumels_local;
+    *out = B->d_fvis.data() + (size_t)light * nl; *count = nl;
+    return 1;
+}
+
+} /* extern "C" */

@@ -1,0 +1,134 @@
+/*
+ * gpu.h -- the thin C-ABI layer between the host C++ pipeline (bake.cpp) and the CUDA side
+ * (gpu_*.cu).  POD descriptors and extern "C" entry points only: host code never sees a kernel,
+ * a stream or a device pointer, the CUDA side never sees an ltr_Scene.
+ *
+ * Every entry point returns 0 on success; on failure the message is available from
+ * ltrgpu_last_error().  All work is issued on the context's own stream; entry points that hand
+ * data back to the host synchronise that stream, the others only enqueue.
+ */
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include "bvh.h"
+#include "geom.h"
+#include "reftree.h"
+#include "vmath.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ltrgpu_Ctx ltrgpu_Ctx;
+
+typedef struct ltrgpu_Light {          /* 64 bytes; ref: ltr_Light lighter_int.hpp:906-925 */
+    V3 pos;    uint32_t type;
+    V3 dir;    float range;
+    V3 color;  float power;
+    float radius, angle_out_rad, angle_diff, curve;
+} ltrgpu_Light;
+
+typedef struct ltrgpu_Inst {           /* 48 bytes */
+    uint32_t lm_w, lm_h;
+    uint32_t texel_off_lo, texel_off_hi;   /* start of this instance's image in the concatenated texel space */
+    uint32_t node_off, item_off, tri_off;  /* slices of the concatenated reference-order trees */
+    uint32_t tree_tris;                    /* triangles in that tree */
+    uint32_t shadow;                       /* instance occludes (scene BVH membership) */
+    uint32_t pad0, pad1, pad2;
+} ltrgpu_Inst;
+
+typedef struct ltrgpu_RasterTri {      /* one lightmap-UV triangle in reference raster order */
+    uint32_t inst, part, i0, i1, i2;   /* vertex indices into the concatenated world-space arrays */
+} ltrgpu_RasterTri;
+
+typedef struct ltrgpu_Params {         /* the slice of ltr_Config the device needs */
+    float ambient[3];
+    float max_correct_dist, corr_min_dot;
+    float ao_distance, ao_multiplier, ao_falloff, ao_effect, ao_color[3];
+    int   ao_num_samples;
+    float blur_size;
+    int   ds2x, normalmap;
+    float amb_brightness;
+} ltrgpu_Params;
+
+typedef struct ltrgpu_SceneDesc {
+    ltrgpu_Params params;
+    /* instances (index 0 = probe container) */
+    uint32_t n_inst;          const ltrgpu_Inst *inst;
+    /* world-space vertex streams, concatenated over instances */
+    uint32_t n_verts;         const V3 *wpos; const V3 *wnrm; const float *vtex2; const float *ltex2;
+    uint32_t n_rtris;         const ltrgpu_RasterTri *rtris;
+    /* reference-order trees, concatenated over instances */
+    uint32_t n_rnodes;        const RefNode *rnodes;
+    uint32_t n_ritems;        const int32_t *ritems;
+    uint32_t n_rtree_tris;    const float *rtree_tris9;
+    /* flat scene BVH over shadow-casting triangles, triangles already in BVH order */
+    uint32_t n_bvh_nodes;     const BvhNode *bvh;
+    uint32_t n_tris;          const float *tris9; const uint32_t *tri_orig;
+    /* lights + light->instance visibility table [n_lights][n_inst] */
+    uint32_t n_lights;        const ltrgpu_Light *lights; const uint8_t *light_inst;
+    /* probes */
+    uint32_t n_probes;        const V3 *probe_pos; const V3 *probe_nrm;
+    /* AO hemisphere table: cos_side[s], sin_side[s] for s < ao_num_samples (host libm) */
+    const float *ao_cos_side; const float *ao_sin_side;
+    /* gaussian kernel taps (host libm), 2*ext+1 entries, ext = ceil(blur_size) */
+    int blur_ext;             const float *blur_kernel;
+} ltrgpu_SceneDesc;
+
+typedef struct ltrgpu_Counters {
+    uint64_t marches, distance_queries, ao_segments, correction_rays;
+    uint64_t rad_pairs, rad_segments, rad_links;
+    uint64_t node_visits, tri_tests;
+    uint64_t kernel_launches, h2d_bytes, d2h_bytes;
+    float ms_samples, ms_direct, ms_march, ms_radiosity, ms_ao, ms_finalize;
+} ltrgpu_Counters;
+
+/* all-gather hook for the multi-GPU radiance exchange: gathers `bytes_per_rank` bytes from
+ * `send` (device) of every rank into `recv` (device, world*bytes_per_rank) on `stream`. */
+typedef int (*ltrgpu_allgather_fn)(void *user, const void *send, void *recv, size_t bytes_per_rank, void *cuda_stream);
+
+int  ltrgpu_create(ltrgpu_Ctx **out, int device);
+void ltrgpu_destroy(ltrgpu_Ctx *ctx);
+const char *ltrgpu_last_error(ltrgpu_Ctx *ctx);
+void *ltrgpu_stream(ltrgpu_Ctx *ctx);
+
+int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *desc);
+
+/* stage: lumel generation (raster -> ordered compaction -> concave-edge offset -> overlap correction).
+ * inst_lumel_off receives n_inst+1 prefix offsets into the global lumel array (probes first). */
+int ltrgpu_generate_lumels(ltrgpu_Ctx *ctx, uint64_t *inst_lumel_off);
+
+/* restrict the per-lumel stages to global lumels [begin,end) (multi-GPU shard); default = all */
+int ltrgpu_set_shard(ltrgpu_Ctx *ctx, uint64_t begin, uint64_t end, int rank, int world,
+                     ltrgpu_allgather_fn allgather, void *allgather_user);
+
+int ltrgpu_direct_light(ltrgpu_Ctx *ctx);
+
+/* host copies of the lumel arrays (n = global lumel count); any pointer may be NULL */
+int ltrgpu_download_lumels(ltrgpu_Ctx *ctx, float *pos3, float *nrm3, uint32_t *loc, float *radinfo4, float *rgb3);
+
+/* stage: radiosity.  diffuse3 / emissive3: per global lumel material from the host callback, or
+ * NULL for (1,1,1) / no extra emission on mesh lumels (probes always diffuse 0, area 0). */
+int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const float *emissive3, int bounces);
+
+/* stage: ambient occlusion; randoff has one value per global lumel (host rand() replay) */
+int ltrgpu_ambient_occlusion(ltrgpu_Ctx *ctx, const float *randoff);
+
+/* stage: finalize (gather shards, scatter, 3x dilation, blur, ds2x, normal map) */
+int ltrgpu_finalize(ltrgpu_Ctx *ctx);
+int ltrgpu_output_size(ltrgpu_Ctx *ctx, uint32_t inst, uint32_t *w, uint32_t *h);
+int ltrgpu_download_output(ltrgpu_Ctx *ctx, uint32_t inst, float *rgb, float *normals_xyzf /* may be NULL */);
+int ltrgpu_download_probe_colors(ltrgpu_Ctx *ctx, float *rgb3);
+
+int ltrgpu_sync(ltrgpu_Ctx *ctx);
+int ltrgpu_get_counters(ltrgpu_Ctx *ctx, ltrgpu_Counters *out);
+int ltrgpu_reset_bake(ltrgpu_Ctx *ctx);     /* drop lumels/results, keep the uploaded scene (bench re-runs) */
+
+/* debug dumps */
+int ltrgpu_download_shadow_factors(ltrgpu_Ctx *ctx, uint32_t light, float *out /* local lumels */);
+int ltrgpu_download_links(ltrgpu_Ctx *ctx, uint64_t *row_offset, uint32_t *other, float *factor, uint64_t *rows, uint64_t *count);
+
+#ifdef __cplusplus
+}
+#endif

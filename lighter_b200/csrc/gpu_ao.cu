@@ -1,0 +1,118 @@
+/*
+ * gpu_ao.cu -- ambient occlusion.
+ *
+ * Reference behaviour restated: lighter.cpp:799-841 (per lumel: ao_num_samples closest-hit segments
+ * of length ao_distance on a golden-angle cosine spiral around the normal, rotated by one random
+ * offset per lumel; blend into the lumel colour), lighter_int.hpp:456-471 (spiral direction),
+ * lighter.cpp:254-289 (closest hit over shadow-casting instances, end points pulled in by 0.001).
+ *
+ * GPU formulation: one thread per (lumel, sample) traces the segment on the flat BVH and stores
+ * the hit parameter; a second kernel, one thread per lumel, sums the samples in index order (the
+ * reference's float summation order) and applies the blend.  The per-lumel random offset is the
+ * host's libc rand() stream replayed in the reference's order (bake.cpp), uploaded per lumel.
+ */
+#include "gpu_internal.cuh"
+
+/* ref: lighter_int.hpp:456-471; cos_side/sin_side come from the host table (exact libm values) */
+__device__ __forceinline__ V3 spiral_dir(V3 dir, float randoff, int i, float cos_side, float sin_side)
+{
+    const float golden = 137.508f / 180.0f * 3.14159274101257324f;     /* DEG2RAD(137.508f) in float */
+    float angle = ((float)i + randoff) * golden;
+    float cos_around = ref_cosf(angle), sin_around = ref_sinf(angle);
+    V3 diffvec = mk3(dir.y, -dir.z, dir.x);
+    V3 up = norm3(cross3(dir, diffvec));
+    V3 rt = cross3(dir, up);
+    return cos_around * sin_side * rt + sin_around * sin_side * up + cos_side * dir;
+}
+
+__global__ void __launch_bounds__(LB_BLOCK)
+ao_trace_kernel(const BvhNode *__restrict__ bvh, const RayTri *__restrict__ raytris, const uint32_t *__restrict__ tri_orig,
+                const float4 *__restrict__ lpos, const float4 *__restrict__ lnrm, const float *__restrict__ randoff,
+                const float *__restrict__ cos_side, const float *__restrict__ sin_side,
+                uint64_t sh_begin, uint32_t n_local, int num_samples, float ao_distance,
+                float *__restrict__ hits, unsigned long long *counters)
+{
+    const uint64_t total = (uint64_t)((n_local + 31u) / 32u) * 32ull * num_samples;   /* padded to whole groups */
+    unsigned segs = 0;
+    TravStats ts = { 0, 0 };
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
+        /* sample-major inside a group of 32 lumels: a warp traces the same sample index for 32
+         * neighbouring lumels, i.e. nearly parallel segments from nearby origins */
+        const uint64_t grp = e / (32ull * num_samples);
+        const uint32_t rem = (uint32_t)(e % (32ull * num_samples));
+        const int s = (int)(rem / 32u);
+        const uint64_t li = grp * 32ull + (rem & 31u);
+        if (li >= n_local) continue;
+        const uint64_t g = sh_begin + li;
+        const V3 SP = ld3(lpos[g]), SN = ld3(lnrm[g]);
+        const V3 origin = SP + SN * (LB_SMALL * 2);
+        const V3 ray = spiral_dir(SN, randoff[g], s, cos_side[s], sin_side[s]) * ao_distance;
+        const V3 B = origin + ray;
+        const V3 dn = norm3(B - origin);
+        const V3 mA = origin + dn * LB_SMALL, mB = B - dn * LB_SMALL;
+        float hit = bvh_segment<false>(bvh, raytris, tri_orig, mA, mB, nullptr, ts);
+        hits[li * num_samples + s] = hit;
+        ++segs;
+    }
+    count_add(counters, CNT_AO_SEGMENTS, segs);
+    count_add(counters, CNT_NODE_VISITS, ts.nodes);
+    count_add(counters, CNT_TRI_TESTS, ts.tris);
+}
+
+__global__ void ao_apply_kernel(const float *__restrict__ hits, uint64_t sh_begin, uint32_t n_local, ltrgpu_Params P, float4 *__restrict__ lrgb)
+{
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n_local) return;
+    const int n = P.ao_num_samples;
+    float ao = 0;
+    for (int s = 0; s < n; ++s) {
+        float hit = hits[(uint64_t)li * n + s];
+        if (hit < 1.0f) ao += 1.0f - hit;
+    }
+    ao /= n;
+    ao = fminr(ao * P.ao_multiplier, 1.0f);
+    if (P.ao_falloff) ao = ref_powf(ao, P.ao_falloff);
+    const uint64_t g = sh_begin + li;
+    float4 c4 = lrgb[g];
+    V3 c = mk3(c4.x, c4.y, c4.z);
+    const V3 aoc = mk3(P.ao_color[0], P.ao_color[1], P.ao_color[2]);
+    if (P.ao_effect >= 0) {
+        c = c * (1 - ao * (1 - P.ao_effect)) + aoc * ao;
+    } else {
+        V3 inner = lerp3(aoc, aoc * c, -P.ao_effect);
+        c = lerp3(c, inner, ao);
+    }
+    lrgb[g] = make_float4(c.x, c.y, c.z, 0.f);
+}
+
+extern "C" int ltrgpu_ambient_occlusion(ltrgpu_Ctx *ctx, const float *randoff_host)
+{
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t n_local64 = ctx->sh_end - ctx->sh_begin;
+    const int ns = ctx->params.ao_num_samples;
+    if (n_local64 == 0) return 0;
+    const uint32_t n_local = (uint32_t)n_local64;
+    float *d_rand = nullptr, *d_hits = nullptr;
+    if (dev_upload(ctx, &d_rand, randoff_host, ctx->n_lumels)) return 1;
+    if (dev_alloc(ctx, &d_hits, (size_t)n_local * (ns > 0 ? ns : 1))) return 1;
+    CU_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+    if (ns > 0) {
+        const uint64_t total = (uint64_t)((n_local + 31u) / 32u) * 32ull * ns;
+        uint64_t want = (total + LB_BLOCK - 1) / LB_BLOCK;
+        unsigned cap = (unsigned)ctx->num_sms * 64;
+        unsigned blocks = want > cap ? cap : (unsigned)want;
+        ao_trace_kernel<<<blocks, LB_BLOCK, 0, st>>>(ctx->d_bvh, ctx->d_raytris, ctx->d_tri_orig, ctx->d_lpos, ctx->d_lnrm, d_rand, ctx->d_ao_cos,
+                                                     ctx->d_ao_sin, ctx->sh_begin, n_local, ns, ctx->params.ao_distance, d_hits, ctx->d_counters);
+        CU_LAUNCH_CHECK(ctx);
+    }
+    ao_apply_kernel<<<grid_for(n_local, 256), 256, 0, st>>>(d_hits, ctx->sh_begin, n_local, ctx->params, ctx->d_lrgb);
+    CU_LAUNCH_CHECK(ctx);
+    CU_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->host_counters.ms_ao += ms;
+    cudaFree(d_rand); cudaFree(d_hits);
+    return 0;
+}

@@ -1,0 +1,290 @@
+/*
+ * gpu_direct.cu -- the direct-light pass, the dominant cost of a bake.
+ *
+ * Reference behaviour restated (file:line into /root/reference):
+ *   shading   lighter.cpp:485-600   point / spot / directional terms, lights accumulate in add order
+ *   march     lighter.cpp:190-207   CalcInvShadowFactor: sphere-traced penumbra estimate
+ *   distance  lighter.cpp:150-188   min(2, nearest triangle distance) over shadow-casting instances
+ *
+ * GPU formulation (three kernels):
+ *   1. direct_classify  one thread per (light, lumel): evaluate the cheap terms; pairs whose product
+ *                       is > 0 are appended (warp-aggregated) to a work list, so that the expensive
+ *                       kernel only sees real marches and neighbouring list entries are neighbouring
+ *                       lumels of the same light (coherent BVH walks);
+ *   2. direct_march     one thread per work-list entry: the march itself, each step a nearest-distance
+ *                       query on the flat BVH; writes the shadow factor f_vis[light][lumel];
+ *   3. direct_accumulate one thread per lumel: re-evaluates the cheap terms (bit-identical, same code)
+ *                       and adds the lights in their original order -- float summation order is the
+ *                       reference's.
+ */
+#include "gpu_internal.cuh"
+
+#include <stdlib.h>
+
+struct ShadeTerms {
+    float pre;         /* product of the non-shadow factors the reference tests against <= 0 */
+    float f_dist, f_ndotl, f_dir;
+    V3 to;             /* march target */
+    V3 s2l;            /* unit vector sample -> light (contribution direction for the normal map) */
+};
+
+/* ref: lighter.cpp:493-502 (point), :528-540 (spot), :563-587 (directional) */
+__device__ __forceinline__ ShadeTerms shade_terms(const ltrgpu_Light &L, V3 SP, V3 SN)
+{
+    ShadeTerms o;
+    if (L.type == 3u) {
+        o.f_dist = 1.f; o.f_dir = 1.f;
+        o.f_ndotl = fmaxr(0.0f, dot3(L.dir, SN));
+        o.pre = 1.f;                                   /* the reference never early-outs a directional light */
+        o.to = SP + L.dir * L.range;
+        o.s2l = L.dir;
+        return o;
+    }
+    V3 s2l = L.pos - SP;
+    float dist = len3(s2l);
+    if (dist) s2l = s2l / dist;
+    o.f_dist = ref_powf(1 - fminr(1.0f, dist / L.range), L.power);
+    o.f_ndotl = fmaxr(0.0f, dot3(s2l, SN));
+    o.f_dir = 1.f;
+    o.pre = o.f_dist * o.f_ndotl;
+    if (L.type == 2u) {
+        float angle = ref_acosf(fminr(1.0f, dot3(s2l, -L.dir)));
+        float f = fmaxr(0.0f, fminr(1.0f, (angle - L.angle_out_rad) / L.angle_diff));
+        o.f_dir = ref_powf(f, L.curve);
+        o.pre = o.f_dist * o.f_ndotl * o.f_dir;
+    }
+    o.to = L.pos;
+    o.s2l = s2l;
+    return o;
+}
+
+__device__ __forceinline__ bool light_is_supported(unsigned type) { return type == 1u || type == 2u || type == 3u; }
+
+__global__ void direct_classify_kernel(const ltrgpu_Light *__restrict__ lights, uint32_t l0, uint32_t l1,
+                                       const uint8_t *__restrict__ light_inst, uint32_t n_inst,
+                                       const float4 *__restrict__ lpos, const float4 *__restrict__ lnrm, const uint32_t *__restrict__ linst,
+                                       uint64_t sh_begin, uint32_t n_local, uint2 *__restrict__ active, uint32_t *active_count)
+{
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t l = l0 + blockIdx.y;
+    bool want = false;
+    if (li < n_local && l < l1) {
+        const ltrgpu_Light L = lights[l];
+        const uint64_t g = sh_begin + li;
+        if (light_is_supported(L.type) && light_inst[(size_t)l * n_inst + linst[g]]) {
+            ShadeTerms t = shade_terms(L, ld3(lpos[g]), ld3(lnrm[g]));
+            /* a directional light facing away adds colour * 0: the march result cannot matter, skip it */
+            want = (L.type == 3u) ? (t.f_ndotl > 0) : (t.pre > 0);
+        }
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (mask) {
+        const unsigned lane = threadIdx.x & 31u;
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(active_count, (unsigned)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (want) active[base + __popc(mask & ((1u << lane) - 1u))] = make_uint2(li, l);
+    }
+}
+
+/* ref: lighter.cpp:190-207 */
+__device__ __forceinline__ float march_shadow(const BvhNode *__restrict__ bvh, const PreparedTri *__restrict__ tris,
+                                              V3 from, V3 to, float k, unsigned &queries, TravStats &ts)
+{
+    V3 rd = norm3(to - from);
+    float maxt = len3(to - from);
+    float res = 1.0f;
+    for (float t = 0.001f; t < maxt;) {
+        float h = bvh_distance(bvh, tris, from + rd * t, 2.0f, 0.001f, ts);
+        ++queries;
+        if (h < 0.001f) return 0.0f;
+        res = fminr(res, h / fminr(t * k, 2.0f));
+        h = fminr(h, 1.0f);
+        t += h;
+    }
+    return res;
+}
+
+__global__ void __launch_bounds__(LB_BLOCK)
+direct_march_kernel(const ltrgpu_Light *__restrict__ lights, const BvhNode *__restrict__ bvh, const PreparedTri *__restrict__ tris,
+                    const float4 *__restrict__ lpos, const float4 *__restrict__ lnrm, uint64_t sh_begin, uint32_t n_local,
+                    const uint2 *__restrict__ active, const uint32_t *__restrict__ active_count, uint32_t l0,
+                    float *__restrict__ fvis, unsigned long long *counters)
+{
+    const uint32_t n = *active_count;
+    unsigned queries = 0, marches = 0;
+    TravStats ts = { 0, 0 };
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const uint2 a = active[e];
+        const ltrgpu_Light L = lights[a.y];
+        const uint64_t g = sh_begin + a.x;
+        const V3 SP = ld3(lpos[g]), SN = ld3(lnrm[g]);
+        const V3 to = (L.type == 3u) ? SP + L.dir * L.range : L.pos;
+        float f = march_shadow(bvh, tris, SP + SN * 0.005f, to, L.radius, queries, ts);
+        fvis[(size_t)(a.y - l0) * n_local + a.x] = f;
+        ++marches;
+    }
+    count_add(counters, CNT_MARCHES, marches);
+    count_add(counters, CNT_DIST_QUERIES, queries);
+    count_add(counters, CNT_NODE_VISITS, ts.nodes);
+    count_add(counters, CNT_TRI_TESTS, ts.tris);
+}
+
+__global__ void direct_accumulate_kernel(const ltrgpu_Light *__restrict__ lights, uint32_t l0, uint32_t l1,
+                                         const uint8_t *__restrict__ light_inst, uint32_t n_inst,
+                                         const float4 *__restrict__ lpos, const float4 *__restrict__ lnrm, const uint32_t *__restrict__ linst,
+                                         uint64_t sh_begin, uint32_t n_local, const float *__restrict__ fvis, float4 *__restrict__ lrgb)
+{
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n_local) return;
+    const uint64_t g = sh_begin + li;
+    const V3 SP = ld3(lpos[g]), SN = ld3(lnrm[g]);
+    const uint32_t inst = linst[g];
+    float4 c4 = lrgb[g];
+    V3 c = mk3(c4.x, c4.y, c4.z);
+    for (uint32_t l = l0; l < l1; ++l) {
+        const ltrgpu_Light L = lights[l];
+        if (!light_is_supported(L.type) || !light_inst[(size_t)l * n_inst + inst]) continue;
+        ShadeTerms t = shade_terms(L, SP, SN);
+        float fv = fvis[(size_t)(l - l0) * n_local + li];
+        float f;
+        if (L.type == 3u) f = t.f_ndotl * fv;
+        else {
+            if (!(t.pre > 0)) continue;
+            f = (L.type == 2u) ? t.f_dist * t.f_ndotl * t.f_dir * fv : t.f_dist * t.f_ndotl * fv;
+        }
+        c = c + L.color * f;
+    }
+    lrgb[g] = make_float4(c.x, c.y, c.z, 0.f);
+}
+
+/*
+ * Normal / focus map terms per lumel (ref: contributions lighter.cpp:505-513,543-551,590-598,
+ * commit :656-664, reduction :977-1012).  Per lumel: average of N*ambient_brightness and every
+ * light's (direction * factor) with factor > 0, then "focus" = product over the same contributions
+ * of lerp(1, max(dot(avg^, c^),0), min(|c|/|avg|,1)).  Needs all shadow factors resident.
+ */
+__device__ __forceinline__ bool light_contrib(const ltrgpu_Light &L, V3 SP, V3 SN, float fv, V3 &out)
+{
+    ShadeTerms t = shade_terms(L, SP, SN);
+    const float bright = (L.color.x + L.color.y + L.color.z) * (1.0f / 3.0f);
+    float factor;
+    if (L.type == 3u) factor = fv * t.f_ndotl * bright;
+    else {
+        if (!(t.pre > 0)) return false;
+        factor = (L.type == 2u) ? t.f_dist * t.f_dir * fv * t.f_ndotl * bright : t.f_dist * fv * t.f_ndotl * bright;
+    }
+    if (!(factor > 0)) return false;
+    out = t.s2l * factor;
+    return true;
+}
+
+__global__ void normalmap_kernel(const ltrgpu_Light *__restrict__ lights, uint32_t n_lights,
+                                 const uint8_t *__restrict__ light_inst, uint32_t n_inst,
+                                 const float4 *__restrict__ lpos, const float4 *__restrict__ lnrm, const uint32_t *__restrict__ linst,
+                                 uint64_t sh_begin, uint32_t n_local, const float *__restrict__ fvis, float amb_brightness,
+                                 float4 *__restrict__ lnmap)
+{
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n_local) return;
+    const uint64_t g = sh_begin + li;
+    const V3 SP = ld3(lpos[g]), SN = ld3(lnrm[g]);
+    const uint32_t inst = linst[g];
+    V3 sum = SN * amb_brightness;
+    int count = 1;
+    for (uint32_t l = 0; l < n_lights; ++l) {
+        const ltrgpu_Light L = lights[l];
+        if (!light_is_supported(L.type) || !light_inst[(size_t)l * n_inst + inst]) continue;
+        V3 c;
+        if (light_contrib(L, SP, SN, fvis[(size_t)l * n_local + li], c)) { sum = sum + c; ++count; }
+    }
+    sum = sum / (float)count;
+    float mindot = 1.0f;
+    const V3 sn = norm3(sum);
+    const float slen = len3(sum);
+    for (uint32_t l = 0; l < n_lights; ++l) {
+        const ltrgpu_Light L = lights[l];
+        if (!light_is_supported(L.type) || !light_inst[(size_t)l * n_inst + inst]) continue;
+        V3 c;
+        if (!light_contrib(L, SP, SN, fvis[(size_t)l * n_local + li], c)) continue;
+        float d = fmaxr(dot3(sn, norm3(c)), 0.0f);
+        d = lerpf(1.0f, d, fminr(len3(c) / slen, 1.0f));
+        mindot *= d;
+    }
+    lnmap[g] = make_float4(sn.x, sn.y, sn.z, mindot);
+}
+
+extern "C" int ltrgpu_direct_light(ltrgpu_Ctx *ctx)
+{
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t n_local64 = ctx->sh_end - ctx->sh_begin;
+    if (n_local64 == 0 || ctx->n_lights == 0) return 0;
+    if (n_local64 > 0x7fffffffull) { snprintf(ctx->err, sizeof(ctx->err), "shard too large"); return 1; }
+    const uint32_t n_local = (uint32_t)n_local64;
+
+    /* lights are processed in chunks so that the factor table stays within a fixed budget;
+     * accumulation order over chunks is still the light order */
+    const size_t budget = (size_t)8 << 30;
+    uint32_t chunk = (uint32_t)(budget / ((size_t)n_local * 12));
+    if (chunk < 1) chunk = 1;
+    if (chunk > ctx->n_lights) chunk = ctx->n_lights;
+    if (ctx->params.normalmap) chunk = ctx->n_lights;           /* the normal map needs every factor resident */
+    if (chunk > 65535u) chunk = 65535u;
+    if (dev_alloc(ctx, &ctx->d_fvis, (size_t)chunk * n_local)) return 1;
+    if (dev_alloc(ctx, &ctx->d_active, (size_t)chunk * n_local)) return 1;
+    if (dev_alloc(ctx, &ctx->d_active_count, 1)) return 1;
+
+    cudaEvent_t m0, m1;
+    CU_TRY(ctx, cudaEventCreate(&m0));
+    CU_TRY(ctx, cudaEventCreate(&m1));
+    CU_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+    float march_ms = 0;
+    for (uint32_t l0 = 0; l0 < ctx->n_lights; l0 += chunk) {
+        uint32_t l1 = l0 + chunk < ctx->n_lights ? l0 + chunk : ctx->n_lights;
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_active_count, 0, 4, st));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_fvis, 0, (size_t)(l1 - l0) * n_local * 4, st));
+        dim3 grid(grid_for(n_local, 256), l1 - l0);
+        direct_classify_kernel<<<grid, 256, 0, st>>>(ctx->d_lights, l0, l1, ctx->d_light_inst, ctx->n_inst, ctx->d_lpos, ctx->d_lnrm,
+                                                     ctx->d_linst, ctx->sh_begin, n_local, ctx->d_active, ctx->d_active_count);
+        CU_LAUNCH_CHECK(ctx);
+        CU_TRY(ctx, cudaEventRecord(m0, st));
+        unsigned blocks = (unsigned)ctx->num_sms * 16;
+        direct_march_kernel<<<blocks, LB_BLOCK, 0, st>>>(ctx->d_lights, ctx->d_bvh, ctx->d_ptris, ctx->d_lpos, ctx->d_lnrm, ctx->sh_begin,
+                                                         n_local, ctx->d_active, ctx->d_active_count, l0, ctx->d_fvis, ctx->d_counters);
+        CU_LAUNCH_CHECK(ctx);
+        CU_TRY(ctx, cudaEventRecord(m1, st));
+        direct_accumulate_kernel<<<grid_for(n_local, 256), 256, 0, st>>>(ctx->d_lights, l0, l1, ctx->d_light_inst, ctx->n_inst, ctx->d_lpos,
+                                                                        ctx->d_lnrm, ctx->d_linst, ctx->sh_begin, n_local, ctx->d_fvis, ctx->d_lrgb);
+        CU_LAUNCH_CHECK(ctx);
+        if (ctx->params.normalmap) {
+            if (dev_alloc(ctx, &ctx->d_lnmap, ctx->n_lumels + LB_PAD)) return 1;
+            normalmap_kernel<<<grid_for(n_local, 256), 256, 0, st>>>(ctx->d_lights, ctx->n_lights, ctx->d_light_inst, ctx->n_inst, ctx->d_lpos,
+                                                                    ctx->d_lnrm, ctx->d_linst, ctx->sh_begin, n_local, ctx->d_fvis,
+                                                                    ctx->params.amb_brightness, ctx->d_lnmap);
+            CU_LAUNCH_CHECK(ctx);
+        }
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, m0, m1);
+        march_ms += ms;
+    }
+    CU_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->host_counters.ms_direct += ms;
+    ctx->host_counters.ms_march += march_ms;
+    cudaEventDestroy(m0); cudaEventDestroy(m1);
+    return 0;
+}
+
+extern "C" int ltrgpu_download_shadow_factors(ltrgpu_Ctx *ctx, uint32_t light, float *out)
+{
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint64_t n_local = ctx->sh_end - ctx->sh_begin;
+    if (!ctx->d_fvis || light >= ctx->n_lights) { snprintf(ctx->err, sizeof(ctx->err), "no shadow factors"); return 1; }
+    CU_TRY(ctx, cudaMemcpyAsync(out, ctx->d_fvis + (size_t)light * n_local, n_local * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}

@@ -1,0 +1,314 @@
+/*
+ * gpu_finalize.cu -- lightmap post-process.
+ *
+ * Reference behaviour restated (lighter.cpp:849-1044, lighter_math.cpp:357-424):
+ *   scatter lumel colours into a zeroed w*h image; 3 rounds of edge extrapolation into unset texels
+ *   (mean over the set 4-neighbours of 2*c1-c2 when the texel two away is set too, else c1; clamped
+ *   at 0; the "set" mask is double-buffered so a round only reads texels set before it); separable
+ *   gaussian blur with clamp-to-edge, taps summed from -ext to +ext; optional 2x2 box downsample;
+ *   optional normal/focus texture.
+ *
+ * GPU formulation: all instance images live back to back in one buffer and every kernel runs once
+ * over the whole concatenation (one thread per texel, instance found by binary search over the
+ * image offsets), so a scene with hundreds of small lightmaps costs the same handful of launches as
+ * one big lightmap.  These kernels are pure streaming stencils: HBM-bound, coalesced along x.
+ */
+#include "gpu_internal.cuh"
+
+#include <stdlib.h>
+
+struct ImgTable {                 /* device view of the image layout */
+    const uint64_t *off;          /* n_img+1 texel offsets */
+    const uint32_t *w, *h;
+    uint32_t n_img;
+};
+
+__device__ __forceinline__ uint32_t find_image(const ImgTable &t, uint64_t g)
+{
+    uint32_t lo = 0, hi = t.n_img;           /* invariant: off[lo] <= g < off[hi] */
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (t.off[mid] <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void scatter_kernel(const float4 *__restrict__ lrgb, const uint32_t *__restrict__ lloc, const uint32_t *__restrict__ linst,
+                               uint64_t first, uint64_t n, const uint64_t *__restrict__ img_off, float *__restrict__ image,
+                               unsigned char *__restrict__ mask)
+{
+    uint64_t i = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t t = img_off[linst[i]] + lloc[i];
+    float4 c = lrgb[i];
+    image[t * 3 + 0] = c.x; image[t * 3 + 1] = c.y; image[t * 3 + 2] = c.z;
+    mask[t] = 1;
+}
+
+__global__ void scatter_normals_kernel(const float4 *__restrict__ lnmap, const uint32_t *__restrict__ lloc, const uint32_t *__restrict__ linst,
+                                       uint64_t first, uint64_t n, const uint64_t *__restrict__ img_off, float4 *__restrict__ normals)
+{
+    uint64_t i = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    normals[img_off[linst[i]] + lloc[i]] = lnmap[i];
+}
+
+__device__ __forceinline__ V3 px(const float *img, uint64_t t) { return mk3(img[t * 3], img[t * 3 + 1], img[t * 3 + 2]); }
+
+/* one extrapolation round; writes only texels that were unset, reads only texels that were set */
+__global__ void dilate_kernel(ImgTable tab, uint64_t n_texels, float *__restrict__ image, const unsigned char *__restrict__ mask_in,
+                              unsigned char *__restrict__ mask_out)
+{
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_texels) return;
+    if (mask_in[g]) { mask_out[g] = 1; return; }
+    const uint32_t im = find_image(tab, g);
+    const uint64_t base = tab.off[im];
+    const uint32_t w = tab.w[im], h = tab.h[im];
+    const uint32_t li = (uint32_t)(g - base), x = li % w, y = li / w;
+    V3 col = mk3(0.f);
+    int count = 0;
+#define SET_(X, Y) ((X) < w && (Y) < h && mask_in[base + (X) + (uint64_t)(Y) * w])
+#define COL_(X, Y) px(image, base + (X) + (uint64_t)(Y) * w)
+#define TAP_(X1, Y1, X2, Y2)                                                        \
+    if (SET_(X1, Y1)) {                                                             \
+        if (SET_(X2, Y2)) col = col + lerp3(COL_(X2, Y2), COL_(X1, Y1), 2.0f);      \
+        else col = col + COL_(X1, Y1);                                              \
+        count++;                                                                    \
+    }
+    TAP_(x - 1u, y, x - 2u, y)
+    TAP_(x + 1u, y, x + 2u, y)
+    TAP_(x, y - 1u, x, y - 2u)
+    TAP_(x, y + 1u, x, y + 2u)
+#undef TAP_
+#undef COL_
+#undef SET_
+    if (count) {
+        col = col / (float)count;
+        image[g * 3 + 0] = fmaxr(col.x, 0.0f);
+        image[g * 3 + 1] = fmaxr(col.y, 0.0f);
+        image[g * 3 + 2] = fmaxr(col.z, 0.0f);
+        mask_out[g] = 1;
+    } else {
+        mask_out[g] = 0;
+    }
+}
+
+/* horizontal pass: dst is the transposed image (x-major), as the reference's first Convolve_Transpose */
+__global__ void blur_h_kernel(ImgTable tab, uint64_t n_texels, const float *__restrict__ src, float *__restrict__ dst,
+                              const float *__restrict__ kern, int ext)
+{
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_texels) return;
+    const uint32_t im = find_image(tab, g);
+    const uint64_t base = tab.off[im];
+    const int w = (int)tab.w[im], h = (int)tab.h[im];
+    const uint32_t li = (uint32_t)(g - base);
+    const int x = (int)(li % (uint32_t)w), y = (int)(li / (uint32_t)w);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int i = -ext; i <= ext; ++i) {
+        int xx = x + i; xx = xx < 0 ? 0 : (xx >= w ? w - 1 : xx);
+        const float k = kern[i + ext];
+        const uint64_t t = (base + (uint64_t)y * w + xx) * 3;
+        s0 += src[t] * k; s1 += src[t + 1] * k; s2 += src[t + 2] * k;
+    }
+    const uint64_t o = (base + (uint64_t)x * h + y) * 3;
+    dst[o] = s0; dst[o + 1] = s1; dst[o + 2] = s2;
+}
+
+/* vertical pass: reads the transposed image, writes row-major */
+__global__ void blur_v_kernel(ImgTable tab, uint64_t n_texels, const float *__restrict__ src, float *__restrict__ dst,
+                              const float *__restrict__ kern, int ext)
+{
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_texels) return;
+    const uint32_t im = find_image(tab, g);
+    const uint64_t base = tab.off[im];
+    const int w = (int)tab.w[im], h = (int)tab.h[im];
+    const uint32_t li = (uint32_t)(g - base);
+    const int x = (int)(li % (uint32_t)w), y = (int)(li / (uint32_t)w);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int i = -ext; i <= ext; ++i) {
+        int yy = y + i; yy = yy < 0 ? 0 : (yy >= h ? h - 1 : yy);
+        const float k = kern[i + ext];
+        const uint64_t t = (base + (uint64_t)x * h + yy) * 3;
+        s0 += src[t] * k; s1 += src[t + 1] * k; s2 += src[t + 2] * k;
+    }
+    const uint64_t o = (base + (uint64_t)y * w + x) * 3;
+    dst[o] = s0; dst[o + 1] = s1; dst[o + 2] = s2;
+}
+
+/* ref: lighter_math.cpp:400-424 */
+__global__ void downsample_kernel(ImgTable src_tab, ImgTable dst_tab, uint64_t n_dst, const float *__restrict__ src, float *__restrict__ dst)
+{
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_dst) return;
+    const uint32_t im = find_image(dst_tab, g);
+    const uint32_t dw = dst_tab.w[im], sw = src_tab.w[im], sh = src_tab.h[im];
+    const uint32_t li = (uint32_t)(g - dst_tab.off[im]), x = li % dw, y = li / dw;
+    const uint64_t sb = src_tab.off[im];
+    const uint32_t sx0 = (x * 2) % sw, sy0 = (y * 2) % sh, sx1 = (x * 2 + 1) % sw, sy1 = (y * 2 + 1) % sh;
+    V3 c00 = px(src, sb + sx0 + (uint64_t)sy0 * sw), c10 = px(src, sb + sx1 + (uint64_t)sy0 * sw);
+    V3 c01 = px(src, sb + sx0 + (uint64_t)sy1 * sw), c11 = px(src, sb + sx1 + (uint64_t)sy1 * sw);
+    V3 avg = (c00 + c10 + c01 + c11) * 0.25f;
+    dst[g * 3] = avg.x; dst[g * 3 + 1] = avg.y; dst[g * 3 + 2] = avg.z;
+}
+
+__global__ void probe_colors_kernel(const float4 *lrgb, uint32_t n, float *out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i * 3] = lrgb[i].x; out[i * 3 + 1] = lrgb[i].y; out[i * 3 + 2] = lrgb[i].z;
+}
+
+static int gather_shards(ltrgpu_Ctx *ctx, float4 *buf)
+{
+    if (ctx->world <= 1) return 0;
+    if (!ctx->allgather) { snprintf(ctx->err, sizeof(ctx->err), "sharded bake without an all-gather hook"); return 1; }
+    const uint64_t chunk = (ctx->n_lumels + ctx->world - 1) / ctx->world;
+    if (chunk * ctx->world > ctx->n_lumels + LB_PAD) { snprintf(ctx->err, sizeof(ctx->err), "shard padding exceeds slack"); return 1; }
+    if (ctx->allgather(ctx->allgather_user, buf + chunk * ctx->rank, buf, chunk * sizeof(float4), ctx->stream)) {
+        snprintf(ctx->err, sizeof(ctx->err), "all-gather of lumel colours failed");
+        return 1;
+    }
+    return 0;
+}
+
+extern "C" int ltrgpu_finalize(ltrgpu_Ctx *ctx)
+{
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CU_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+    const uint32_t ni = ctx->n_inst;
+    const uint64_t nt = ctx->n_texels;
+
+    if (gather_shards(ctx, ctx->d_lrgb)) return 1;
+    if (ctx->params.normalmap && ctx->d_lnmap && gather_shards(ctx, ctx->d_lnmap)) return 1;
+
+    /* image layout tables (full-size images, then output images) */
+    uint64_t *h_off = (uint64_t *)malloc(sizeof(uint64_t) * (ni + 1));
+    uint32_t *h_w = (uint32_t *)malloc(4 * (ni ? ni : 1)), *h_h = (uint32_t *)malloc(4 * (ni ? ni : 1));
+    free(ctx->h_out_off); free(ctx->h_out_w); free(ctx->h_out_h);
+    ctx->h_out_off = (uint64_t *)malloc(sizeof(uint64_t) * (ni + 1));
+    ctx->h_out_w = (uint32_t *)malloc(4 * (ni ? ni : 1));
+    ctx->h_out_h = (uint32_t *)malloc(4 * (ni ? ni : 1));
+    uint64_t acc = 0, oacc = 0;
+    for (uint32_t i = 0; i < ni; ++i) {
+        h_off[i] = acc; h_w[i] = ctx->h_inst[i].lm_w; h_h[i] = ctx->h_inst[i].lm_h;
+        acc += (uint64_t)h_w[i] * h_h[i];
+        uint32_t ow = h_w[i], oh = h_h[i];
+        if (ctx->params.ds2x && i > 0) { ow = ow / 2 > 1 ? ow / 2 : 1; oh = oh / 2 > 1 ? oh / 2 : 1; }
+        ctx->h_out_off[i] = oacc; ctx->h_out_w[i] = ow; ctx->h_out_h[i] = oh;
+        oacc += (uint64_t)ow * oh;
+    }
+    h_off[ni] = acc; ctx->h_out_off[ni] = oacc;
+    uint64_t *d_off = nullptr, *d_ooff = nullptr;
+    uint32_t *d_w = nullptr, *d_h = nullptr, *d_ow = nullptr, *d_oh = nullptr;
+    int rc = 0;
+    rc |= dev_upload(ctx, &d_off, h_off, ni + 1); rc |= dev_upload(ctx, &d_w, h_w, ni); rc |= dev_upload(ctx, &d_h, h_h, ni);
+    rc |= dev_upload(ctx, &d_ooff, ctx->h_out_off, ni + 1); rc |= dev_upload(ctx, &d_ow, ctx->h_out_w, ni); rc |= dev_upload(ctx, &d_oh, ctx->h_out_h, ni);
+    free(h_off); free(h_w); free(h_h);
+    if (rc) return 1;
+    ImgTable tab = { d_off, d_w, d_h, ni }, otab = { d_ooff, d_ow, d_oh, ni };
+
+    if (dev_alloc(ctx, &ctx->d_image, nt * 3)) return 1;
+    if (dev_alloc(ctx, &ctx->d_image_tmp, nt * 3)) return 1;
+    if (dev_alloc(ctx, &ctx->d_mask, nt)) return 1;
+    if (dev_alloc(ctx, &ctx->d_mask_tmp, nt)) return 1;
+    CU_TRY(ctx, cudaMemsetAsync(ctx->d_image, 0, (nt ? nt : 1) * 12, st));
+    CU_TRY(ctx, cudaMemsetAsync(ctx->d_mask, 0, nt ? nt : 1, st));
+
+    const uint64_t n = ctx->n_lumels, first = ctx->n_probes;
+    if (n > first) {
+        scatter_kernel<<<grid_for(n - first, 256), 256, 0, st>>>(ctx->d_lrgb, ctx->d_lloc, ctx->d_linst, first, n, d_off, ctx->d_image, ctx->d_mask);
+        CU_LAUNCH_CHECK(ctx);
+    }
+    float *img = ctx->d_image;
+    if (nt) {
+        unsigned char *m_in = ctx->d_mask, *m_out = ctx->d_mask_tmp;
+        for (int it = 0; it < 3; ++it) {
+            dilate_kernel<<<grid_for(nt, 256), 256, 0, st>>>(tab, nt, img, m_in, m_out);
+            CU_LAUNCH_CHECK(ctx);
+            unsigned char *t = m_in; m_in = m_out; m_out = t;
+        }
+        if (ctx->params.blur_size && ctx->d_blur_kernel) {
+            blur_h_kernel<<<grid_for(nt, 256), 256, 0, st>>>(tab, nt, img, ctx->d_image_tmp, ctx->d_blur_kernel, ctx->blur_ext);
+            CU_LAUNCH_CHECK(ctx);
+            blur_v_kernel<<<grid_for(nt, 256), 256, 0, st>>>(tab, nt, ctx->d_image_tmp, img, ctx->d_blur_kernel, ctx->blur_ext);
+            CU_LAUNCH_CHECK(ctx);
+        }
+    }
+    /* output buffer */
+    if (ctx->params.ds2x) {
+        if (dev_alloc(ctx, &ctx->d_out, oacc * 3)) return 1;
+        if (oacc) {
+            downsample_kernel<<<grid_for(oacc, 256), 256, 0, st>>>(tab, otab, oacc, img, ctx->d_out);
+            CU_LAUNCH_CHECK(ctx);
+        }
+    }
+    if (ctx->params.normalmap && ctx->d_lnmap) {
+        /* The reference allocates this texture at the post-ds2x size but indexes it at full size
+         * (lighter.cpp:973-974,1015-1020), a heap overrun when ds2x is on; we keep the full-size
+         * texture so every write is in bounds and hand out full-size normals. */
+        if (dev_alloc(ctx, &ctx->d_normals, nt * 4)) return 1;
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_normals, 0, (nt ? nt : 1) * 16, st));
+        if (n > first) {
+            scatter_normals_kernel<<<grid_for(n - first, 256), 256, 0, st>>>(ctx->d_lnmap, ctx->d_lloc, ctx->d_linst, first, n, d_off,
+                                                                            (float4 *)ctx->d_normals);
+            CU_LAUNCH_CHECK(ctx);
+        }
+    }
+    CU_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->host_counters.ms_finalize += ms;
+    cudaFree(d_off); cudaFree(d_w); cudaFree(d_h); cudaFree(d_ooff); cudaFree(d_ow); cudaFree(d_oh);
+    return 0;
+}
+
+extern "C" int ltrgpu_output_size(ltrgpu_Ctx *ctx, uint32_t inst, uint32_t *w, uint32_t *h)
+{
+    if (!ctx->h_out_w || inst >= ctx->n_inst) return 1;
+    *w = ctx->h_out_w[inst]; *h = ctx->h_out_h[inst];
+    return 0;
+}
+
+extern "C" int ltrgpu_download_output(ltrgpu_Ctx *ctx, uint32_t inst, float *rgb, float *normals_xyzf)
+{
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->h_out_w || inst >= ctx->n_inst) { snprintf(ctx->err, sizeof(ctx->err), "no output for instance %u", inst); return 1; }
+    const uint64_t cnt = (uint64_t)ctx->h_out_w[inst] * ctx->h_out_h[inst];
+    const float *src = ctx->params.ds2x ? ctx->d_out : ctx->d_image;
+    if (cnt && rgb) {
+        CU_TRY(ctx, cudaMemcpyAsync(rgb, src + ctx->h_out_off[inst] * 3, cnt * 12, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->host_counters.d2h_bytes += cnt * 12;
+    }
+    if (normals_xyzf && ctx->d_normals) {
+        uint64_t full_off = 0;
+        for (uint32_t i = 0; i < inst; ++i) full_off += (uint64_t)ctx->h_inst[i].lm_w * ctx->h_inst[i].lm_h;
+        /* with ds2x the caller's buffer is output-sized: hand back the top-left out_w*out_h window
+         * row by row (see the note in ltrgpu_finalize) */
+        const uint32_t fw = ctx->h_inst[inst].lm_w, ow = ctx->h_out_w[inst], oh = ctx->h_out_h[inst];
+        CU_TRY(ctx, cudaMemcpy2DAsync(normals_xyzf, (size_t)ow * 16, ctx->d_normals + full_off * 4, (size_t)fw * 16, (size_t)ow * 16, oh,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->host_counters.d2h_bytes += (uint64_t)ow * oh * 16;
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int ltrgpu_download_probe_colors(ltrgpu_Ctx *ctx, float *rgb3)
+{
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->n_probes) return 0;
+    float *d = nullptr;
+    if (dev_alloc(ctx, &d, (size_t)ctx->n_probes * 3)) return 1;
+    probe_colors_kernel<<<grid_for(ctx->n_probes, 128), 128, 0, ctx->stream>>>(ctx->d_lrgb, ctx->n_probes, d);
+    CU_LAUNCH_CHECK(ctx);
+    CU_TRY(ctx, cudaMemcpyAsync(rgb3, d, (size_t)ctx->n_probes * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->host_counters.d2h_bytes += (size_t)ctx->n_probes * 12;
+    cudaFree(d);
+    return 0;
+}

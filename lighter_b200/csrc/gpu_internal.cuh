@@ -1,0 +1,333 @@
+/*
+ * gpu_internal.cuh -- device-side context, error plumbing and the BVH traversal routines shared by
+ * the stage kernels.  sm_100a only; compiled with -fmad=false (parity, see vmath.h).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "gpu.h"
+
+#define LB_BLOCK 128                      /* traversal kernels: 4 warps per CTA, many CTAs per SM */
+#define LB_PAD 1024                       /* slack elements on per-lumel arrays so shards can be padded to equal size */
+
+struct DevBuf {                           /* growable device allocation */
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct ltrgpu_Ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    char err[512] = {0};
+
+    ltrgpu_Params params;
+    /* ---- uploaded scene ---- */
+    uint32_t n_inst = 0, n_verts = 0, n_rtris = 0, n_rnodes = 0, n_ritems = 0, n_rtree_tris = 0;
+    uint32_t n_bvh_nodes = 0, n_tris = 0, n_lights = 0, n_probes = 0;
+    uint64_t n_texels = 0;
+    ltrgpu_Inst *d_inst = nullptr;
+    ltrgpu_Inst *h_inst = nullptr;
+    V3 *d_wpos = nullptr, *d_wnrm = nullptr;
+    float2 *d_vtex = nullptr, *d_ltex = nullptr;
+    ltrgpu_RasterTri *d_rtris = nullptr;
+    RefNode *d_rnodes = nullptr;
+    int32_t *d_ritems = nullptr;
+    float *d_rtree_tris = nullptr;
+    BvhNode *d_bvh = nullptr;
+    PreparedTri *d_ptris = nullptr;
+    RayTri *d_raytris = nullptr;
+    uint32_t *d_tri_orig = nullptr;
+    ltrgpu_Light *d_lights = nullptr;
+    ltrgpu_Light *h_lights = nullptr;
+    uint8_t *d_light_inst = nullptr;
+    V3 *d_probe_pos = nullptr, *d_probe_nrm = nullptr;
+    float *d_ao_cos = nullptr, *d_ao_sin = nullptr;
+    float *d_blur_kernel = nullptr;
+    int blur_ext = 0;
+
+    /* ---- lumels (global array: probes first, then instances in order) ---- */
+    uint64_t n_lumels = 0;
+    uint64_t *h_inst_lumel_off = nullptr;     /* n_inst+1 */
+    uint32_t *d_texkey = nullptr;             /* winner key per texel */
+    uint32_t *d_texidx = nullptr;             /* exclusive scan of lumel flags */
+    float4 *d_lpos = nullptr, *d_lnrm = nullptr, *d_lrad = nullptr, *d_lrgb = nullptr;
+    float4 *d_lnmap = nullptr;                /* normal/focus per lumel (normal map mode) */
+    uint32_t *d_lloc = nullptr, *d_linst = nullptr;
+
+    /* ---- shard ---- */
+    uint64_t sh_begin = 0, sh_end = 0;
+    int rank = 0, world = 1;
+    ltrgpu_allgather_fn allgather = nullptr;
+    void *allgather_user = nullptr;
+
+    /* ---- direct light ---- */
+    float *d_fvis = nullptr;                  /* [n_lights][local lumels] shadow factors */
+    uint2 *d_active = nullptr;                /* (local lumel, light) pairs to march */
+    uint32_t *d_active_count = nullptr;
+
+    /* ---- radiosity ---- */
+    uint64_t rad_rows = 0, rad_links = 0;
+    uint64_t *d_rad_rowoff = nullptr;
+    uint32_t *d_rad_other = nullptr;
+    float *d_rad_factor = nullptr;
+
+    /* ---- finalize ---- */
+    float *d_image = nullptr, *d_image_tmp = nullptr;   /* concatenated rgb images */
+    unsigned char *d_mask = nullptr, *d_mask_tmp = nullptr;
+    float *d_normals = nullptr;               /* concatenated xyzf images (normal map mode) */
+    uint64_t *h_out_off = nullptr;            /* per instance: offset (in texels) of the OUTPUT image */
+    uint32_t *h_out_w = nullptr, *h_out_h = nullptr;
+    float *d_out = nullptr;                   /* output images after optional ds2x */
+
+    /* ---- counters ---- */
+    unsigned long long *d_counters = nullptr; /* see CNT_* */
+    ltrgpu_Counters host_counters;
+};
+
+enum { CNT_MARCHES = 0, CNT_DIST_QUERIES, CNT_AO_SEGMENTS, CNT_CORR_RAYS, CNT_RAD_PAIRS, CNT_RAD_SEGMENTS,
+       CNT_RAD_LINKS, CNT_NODE_VISITS, CNT_TRI_TESTS, CNT_COUNT };
+
+#define CU_TRY(ctx, call)                                                                          \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s: %s", __FILE__, __LINE__, #call,    \
+                     cudaGetErrorString(e_));                                                      \
+            return 1;                                                                              \
+        }                                                                                          \
+    } while (0)
+
+#define CU_LAUNCH_CHECK(ctx)                                                                       \
+    do {                                                                                           \
+        (ctx)->host_counters.kernel_launches++;                                                    \
+        CU_TRY(ctx, cudaGetLastError());                                                           \
+    } while (0)
+
+template <class T> static inline int dev_alloc(ltrgpu_Ctx *ctx, T **p, size_t count)
+{
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) count = 1;
+    CU_TRY(ctx, cudaMalloc((void **)p, count * sizeof(T)));
+    return 0;
+}
+template <class T> static inline int dev_upload(ltrgpu_Ctx *ctx, T **p, const void *src, size_t count)
+{
+    if (dev_alloc(ctx, p, count)) return 1;
+    if (count && src) {
+        CU_TRY(ctx, cudaMemcpyAsync(*p, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->host_counters.h2d_bytes += count * sizeof(T);
+    }
+    return 0;
+}
+template <class T> static inline void dev_free(T **p) { if (*p) { cudaFree(*p); *p = nullptr; } }
+
+static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+/* ------------------------------------------------------------------------------------------
+ * device helpers
+ * ------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ V3 ld3(const float4 &v) { return mk3(v.x, v.y, v.z); }
+
+/* libm-class functions: evaluated in double and rounded once, which reproduces glibc's (nearly
+ * always correctly rounded) float results; see DESIGN.md "transcendentals". */
+__device__ __forceinline__ float ref_powf(float x, float y)
+{
+    if (y == 1.0f) return x;
+    if (y == 0.0f) return 1.0f;
+    return (float)pow((double)x, (double)y);
+}
+__device__ __forceinline__ float ref_acosf(float x) { return (float)acos((double)x); }
+__device__ __forceinline__ float ref_sinf(float x) { return (float)sin((double)x); }
+__device__ __forceinline__ float ref_cosf(float x) { return (float)cos((double)x); }
+
+struct TravStats { unsigned nodes, tris; };
+
+__device__ __forceinline__ float box_dist2(V3 p, float lx, float ly, float lz, float hx, float hy, float hz)
+{
+    float dx = fmaxf(fmaxf(lx - p.x, p.x - hx), 0.f);
+    float dy = fmaxf(fmaxf(ly - p.y, p.y - hy), 0.f);
+    float dz = fmaxf(fmaxf(lz - p.z, p.z - hz), 0.f);
+    return dx * dx + dy * dy + dz * dz;
+}
+
+__device__ __forceinline__ void load_prepared(const PreparedTri *src, PreparedTri &T)
+{
+    const float4 *s = reinterpret_cast<const float4 *>(src);
+    float4 *d = reinterpret_cast<float4 *>(&T);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) d[i] = __ldg(s + i);
+}
+
+/*
+ * Nearest-triangle distance, clamped to `radius` (ref semantics: ltr_Scene::Distance,
+ * lighter.cpp:150-188 = min(MAX_PENUMBRA_SIZE, min over triangles of PointTriangleDistance)).
+ * Returns early with a value < stop_below as soon as one is found (the march only needs to know
+ * that h < 0.001, lighter.cpp:200-201).  Pruning is conservative: a sub-tree is skipped only when
+ * its box is farther than the best distance so far.
+ */
+__device__ __forceinline__ float bvh_distance(const BvhNode *__restrict__ nodes, const PreparedTri *__restrict__ tris,
+                                              V3 p, float radius, float stop_below, TravStats &ts)
+{
+    int   stack_n[BVH_STACK];
+    float stack_d[BVH_STACK];
+    int sp = 0;
+    float best = radius;
+    float best2 = best * best * 1.000001f;
+    int node = 0;
+    for (;;) {
+        const float4 *n4 = reinterpret_cast<const float4 *>(nodes + node);
+        float4 a = __ldg(n4), b = __ldg(n4 + 1), c = __ldg(n4 + 2);
+        int4 k = __ldg(reinterpret_cast<const int4 *>(n4 + 3));
+        ts.nodes++;
+        float d0 = box_dist2(p, a.x, a.y, a.z, a.w, b.x, b.y);
+        float d1 = box_dist2(p, b.z, b.w, c.x, c.y, c.z, c.w);
+        int c0 = k.x, c1 = k.y;
+        if (d1 < d0) { float td = d0; d0 = d1; d1 = td; int tc = c0; c0 = c1; c1 = tc; }   /* c0 = nearer */
+        int next = -1;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            int cc = side ? c1 : c0;
+            float dd = side ? d1 : d0;
+            if (dd > best2) continue;
+            if (cc < 0) {
+                unsigned code = ~cc;
+                unsigned first = code >> 3, cnt = code & 7u;
+                for (unsigned t = 0; t < cnt; ++t) {
+                    PreparedTri T;
+                    load_prepared(tris + first + t, T);
+                    ts.tris++;
+                    float d = point_tri_distance_prepared(p, T);
+                    if (d < best) {
+                        best = d;
+                        best2 = best * best * 1.000001f;
+                        if (best < stop_below) return best;
+                    }
+                }
+            } else if (next < 0) {
+                next = cc;
+            } else {
+                stack_n[sp] = cc; stack_d[sp] = dd; ++sp;
+            }
+        }
+        if (next >= 0) { node = next; continue; }
+        for (;;) {
+            if (sp == 0) return best;
+            --sp;
+            if (stack_d[sp] <= best2) { node = stack_n[sp]; break; }
+        }
+    }
+}
+
+/* Segment set-up for BVH traversal: parametrised over [0,1] on l1 -> l2 so that box entry
+ * distances compare directly with the hit parameter of seg_tri_prepared. */
+struct SegRay { V3 o, d, inv; };
+
+__device__ __forceinline__ SegRay make_seg(V3 l1, V3 l2)
+{
+    SegRay r;
+    r.o = l1; r.d = l2 - l1;
+    r.inv = mk3(r.d.x != 0 ? 1.0f / r.d.x : 0.f, r.d.y != 0 ? 1.0f / r.d.y : 0.f, r.d.z != 0 ? 1.0f / r.d.z : 0.f);
+    return r;
+}
+
+/* entry parameter of the segment into the box, or +inf when it misses [0,tmax] (conservative) */
+__device__ __forceinline__ float seg_box(const SegRay &r, float lx, float ly, float lz, float hx, float hy, float hz, float tmax)
+{
+    float t0 = 0.f, t1 = tmax;
+    if (r.d.x != 0) { float a = (lx - r.o.x) * r.inv.x, b = (hx - r.o.x) * r.inv.x; t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b)); }
+    else if (r.o.x < lx || r.o.x > hx) return INFINITY;
+    if (r.d.y != 0) { float a = (ly - r.o.y) * r.inv.y, b = (hy - r.o.y) * r.inv.y; t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b)); }
+    else if (r.o.y < ly || r.o.y > hy) return INFINITY;
+    if (r.d.z != 0) { float a = (lz - r.o.z) * r.inv.z, b = (hz - r.o.z) * r.inv.z; t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b)); }
+    else if (r.o.z < lz || r.o.z > hz) return INFINITY;
+    /* widen by a few ulps so rounding in the slab products can never drop a touching box */
+    return (t0 <= t1 * 1.0000005f + 1e-7f) ? t0 : INFINITY;
+}
+
+__device__ __forceinline__ void load_raytri(const RayTri *src, RayTri &T)
+{
+    const float4 *s = reinterpret_cast<const float4 *>(src);
+    float4 *d = reinterpret_cast<float4 *>(&T);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[i] = __ldg(s + i);
+}
+
+/*
+ * Segment query against the scene BVH.
+ *   ANY = true : returns 1.0f-below value as soon as any triangle is hit (ref: VisibilityTest's
+ *                any-hit, lighter.cpp:112-147 / lighter_math.cpp:804-832), else LB_NO_HIT
+ *   ANY = false: closest-hit parameter (ref: lighter_math.cpp:835-871), ties -> lowest original
+ *                triangle index; *hit_slot receives the BVH-order triangle slot or -1
+ * The caller shortens the segment (SMALL_FLOAT at both ends) exactly as the reference does.
+ */
+template <bool ANY>
+__device__ __forceinline__ float bvh_segment(const BvhNode *__restrict__ nodes, const RayTri *__restrict__ tris,
+                                             const uint32_t *__restrict__ tri_orig, V3 l1, V3 l2, int *hit_slot, TravStats &ts)
+{
+    int stack_n[BVH_STACK];
+    float stack_t[BVH_STACK];
+    int sp = 0;
+    SegRay r = make_seg(l1, l2);
+    float best = LB_NO_HIT;
+    float tmax = 1.0f;
+    int best_slot = -1;
+    unsigned best_orig = 0xffffffffu;
+    int node = 0;
+    for (;;) {
+        const float4 *n4 = reinterpret_cast<const float4 *>(nodes + node);
+        float4 a = __ldg(n4), b = __ldg(n4 + 1), c = __ldg(n4 + 2);
+        int4 k = __ldg(reinterpret_cast<const int4 *>(n4 + 3));
+        ts.nodes++;
+        float e0 = seg_box(r, a.x, a.y, a.z, a.w, b.x, b.y, tmax);
+        float e1 = seg_box(r, b.z, b.w, c.x, c.y, c.z, c.w, tmax);
+        int c0 = k.x, c1 = k.y;
+        if (e1 < e0) { float te = e0; e0 = e1; e1 = te; int tc = c0; c0 = c1; c1 = tc; }
+        int next = -1;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            int cc = side ? c1 : c0;
+            float ee = side ? e1 : e0;
+            if (ee > tmax) continue;                         /* also rejects INFINITY */
+            if (cc < 0) {
+                unsigned code = ~cc;
+                unsigned first = code >> 3, cnt = code & 7u;
+                for (unsigned t = 0; t < cnt; ++t) {
+                    RayTri T;
+                    load_raytri(tris + first + t, T);
+                    ts.tris++;
+                    float h = seg_tri_prepared(r.o, r.d, T);
+                    if (ANY) {
+                        if (h < 1.0f) return h;
+                    } else if (h < LB_NO_HIT) {
+                        unsigned orig = __ldg(tri_orig + first + t);
+                        if (h < best || (h == best && orig < best_orig)) {
+                            best = h; best_slot = (int)(first + t); best_orig = orig;
+                            tmax = fminf(1.0f, best * 1.0000005f + 1e-7f);   /* keep exact ties reachable */
+                        }
+                    }
+                }
+            } else if (next < 0) {
+                next = cc;
+            } else {
+                stack_n[sp] = cc; stack_t[sp] = ee; ++sp;
+            }
+        }
+        if (next >= 0) { node = next; continue; }
+        for (;;) {
+            if (sp == 0) { if (hit_slot) *hit_slot = best_slot; return best; }
+            --sp;
+            if (stack_t[sp] <= tmax) { node = stack_n[sp]; break; }
+        }
+    }
+}
+
+/* warp-aggregated counter add */
+__device__ __forceinline__ void count_add(unsigned long long *counters, int which, unsigned v)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(counters + which, (unsigned long long)v);
+}

@@ -1,0 +1,173 @@
+/* gpu_scene.cu -- context lifetime, scene upload, per-triangle preparation, counters. */
+#include "gpu_internal.cuh"
+
+#include <stdlib.h>
+
+/* one thread per BVH-order triangle: expand the 9 floats into the two prepared records
+ * (geom.h) with the reference's exact expressions. */
+__global__ void prepare_tris_kernel(const float *__restrict__ tris9, uint32_t n, PreparedTri *__restrict__ pt, RayTri *__restrict__ rt)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *t = tris9 + 9ull * i;
+    V3 a = mk3(t[0], t[1], t[2]), b = mk3(t[3], t[4], t[5]), c = mk3(t[6], t[7], t[8]);
+    PreparedTri P;
+    prepare_tri(a, b, c, P);
+    pt[i] = P;
+    RayTri R;
+    prepare_raytri(a, b, c, R);
+    rt[i] = R;
+}
+
+extern "C" int ltrgpu_create(ltrgpu_Ctx **out, int device)
+{
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        fprintf(stderr, "lighter_b200: no CUDA device available (%s); this library has no CPU fallback\n",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return 1;
+    }
+    ltrgpu_Ctx *ctx = new ltrgpu_Ctx;
+    memset(&ctx->host_counters, 0, sizeof(ctx->host_counters));
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    ctx->device = device;
+    *out = ctx;
+    CU_TRY(ctx, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(ctx, cudaGetDeviceProperties(&prop, device));
+    ctx->num_sms = prop.multiProcessorCount;
+    CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU_TRY(ctx, cudaEventCreate(&ctx->ev0));
+    CU_TRY(ctx, cudaEventCreate(&ctx->ev1));
+    if (dev_alloc(ctx, &ctx->d_counters, CNT_COUNT)) return 1;
+    CU_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, CNT_COUNT * sizeof(unsigned long long), ctx->stream));
+    return 0;
+}
+
+static void free_bake_state(ltrgpu_Ctx *ctx)
+{
+    dev_free(&ctx->d_texkey); dev_free(&ctx->d_texidx);
+    dev_free(&ctx->d_lpos); dev_free(&ctx->d_lnrm); dev_free(&ctx->d_lrad); dev_free(&ctx->d_lrgb);
+    dev_free(&ctx->d_lloc); dev_free(&ctx->d_linst); dev_free(&ctx->d_lnmap);
+    dev_free(&ctx->d_fvis); dev_free(&ctx->d_active); dev_free(&ctx->d_active_count);
+    dev_free(&ctx->d_rad_rowoff); dev_free(&ctx->d_rad_other); dev_free(&ctx->d_rad_factor);
+    dev_free(&ctx->d_image); dev_free(&ctx->d_image_tmp); dev_free(&ctx->d_mask); dev_free(&ctx->d_mask_tmp);
+    dev_free(&ctx->d_normals); dev_free(&ctx->d_out);
+    ctx->n_lumels = 0; ctx->rad_rows = ctx->rad_links = 0;
+}
+
+extern "C" void ltrgpu_destroy(ltrgpu_Ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_bake_state(ctx);
+    dev_free(&ctx->d_inst); dev_free(&ctx->d_wpos); dev_free(&ctx->d_wnrm); dev_free(&ctx->d_vtex); dev_free(&ctx->d_ltex);
+    dev_free(&ctx->d_rtris); dev_free(&ctx->d_rnodes); dev_free(&ctx->d_ritems); dev_free(&ctx->d_rtree_tris);
+    dev_free(&ctx->d_bvh); dev_free(&ctx->d_ptris); dev_free(&ctx->d_raytris); dev_free(&ctx->d_tri_orig);
+    dev_free(&ctx->d_lights); dev_free(&ctx->d_light_inst); dev_free(&ctx->d_probe_pos); dev_free(&ctx->d_probe_nrm);
+    dev_free(&ctx->d_ao_cos); dev_free(&ctx->d_ao_sin); dev_free(&ctx->d_blur_kernel); dev_free(&ctx->d_counters);
+    free(ctx->h_inst); free(ctx->h_lights); free(ctx->h_inst_lumel_off);
+    free(ctx->h_out_off); free(ctx->h_out_w); free(ctx->h_out_h);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char *ltrgpu_last_error(ltrgpu_Ctx *ctx) { return ctx ? ctx->err : "no GPU context"; }
+extern "C" void *ltrgpu_stream(ltrgpu_Ctx *ctx) { return (void *)ctx->stream; }
+
+extern "C" int ltrgpu_sync(ltrgpu_Ctx *ctx)
+{
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int ltrgpu_reset_bake(ltrgpu_Ctx *ctx)
+{
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    free_bake_state(ctx);
+    CU_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, CNT_COUNT * sizeof(unsigned long long), ctx->stream));
+    uint64_t h2d = ctx->host_counters.h2d_bytes;
+    memset(&ctx->host_counters, 0, sizeof(ctx->host_counters));
+    ctx->host_counters.h2d_bytes = h2d;          /* the scene upload still belongs to this bake */
+    return 0;
+}
+
+extern "C" int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *d)
+{
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    ctx->params = d->params;
+    ctx->n_inst = d->n_inst; ctx->n_verts = d->n_verts; ctx->n_rtris = d->n_rtris;
+    ctx->n_rnodes = d->n_rnodes; ctx->n_ritems = d->n_ritems; ctx->n_rtree_tris = d->n_rtree_tris;
+    ctx->n_bvh_nodes = d->n_bvh_nodes; ctx->n_tris = d->n_tris; ctx->n_lights = d->n_lights; ctx->n_probes = d->n_probes;
+    ctx->blur_ext = d->blur_ext;
+
+    free(ctx->h_inst);
+    ctx->h_inst = (ltrgpu_Inst *)malloc(sizeof(ltrgpu_Inst) * (d->n_inst ? d->n_inst : 1));
+    memcpy(ctx->h_inst, d->inst, sizeof(ltrgpu_Inst) * d->n_inst);
+    free(ctx->h_lights);
+    ctx->h_lights = (ltrgpu_Light *)malloc(sizeof(ltrgpu_Light) * (d->n_lights ? d->n_lights : 1));
+    if (d->n_lights) memcpy(ctx->h_lights, d->lights, sizeof(ltrgpu_Light) * d->n_lights);
+    ctx->n_texels = 0;
+    for (uint32_t i = 0; i < d->n_inst; ++i) ctx->n_texels += (uint64_t)d->inst[i].lm_w * d->inst[i].lm_h;
+
+    if (dev_upload(ctx, &ctx->d_inst, d->inst, d->n_inst)) return 1;
+    if (dev_upload(ctx, &ctx->d_wpos, d->wpos, d->n_verts)) return 1;
+    if (dev_upload(ctx, &ctx->d_wnrm, d->wnrm, d->n_verts)) return 1;
+    if (dev_upload(ctx, &ctx->d_vtex, d->vtex2, d->n_verts)) return 1;
+    if (dev_upload(ctx, &ctx->d_ltex, d->ltex2, d->n_verts)) return 1;
+    if (dev_upload(ctx, &ctx->d_rtris, d->rtris, d->n_rtris)) return 1;
+    if (dev_upload(ctx, &ctx->d_rnodes, d->rnodes, d->n_rnodes)) return 1;
+    if (dev_upload(ctx, &ctx->d_ritems, d->ritems, d->n_ritems)) return 1;
+    if (dev_upload(ctx, &ctx->d_rtree_tris, d->rtree_tris9, (size_t)d->n_rtree_tris * 9)) return 1;
+    if (dev_upload(ctx, &ctx->d_bvh, d->bvh, d->n_bvh_nodes)) return 1;
+    if (dev_upload(ctx, &ctx->d_tri_orig, d->tri_orig, d->n_tris)) return 1;
+    if (dev_upload(ctx, &ctx->d_lights, d->lights, d->n_lights)) return 1;
+    if (dev_upload(ctx, &ctx->d_light_inst, d->light_inst, (size_t)d->n_lights * d->n_inst)) return 1;
+    if (dev_upload(ctx, &ctx->d_probe_pos, d->probe_pos, d->n_probes)) return 1;
+    if (dev_upload(ctx, &ctx->d_probe_nrm, d->probe_nrm, d->n_probes)) return 1;
+    int ns = d->params.ao_num_samples > 0 ? d->params.ao_num_samples : 0;
+    if (dev_upload(ctx, &ctx->d_ao_cos, d->ao_cos_side, ns)) return 1;
+    if (dev_upload(ctx, &ctx->d_ao_sin, d->ao_sin_side, ns)) return 1;
+    if (dev_upload(ctx, &ctx->d_blur_kernel, d->blur_kernel, d->blur_kernel ? 2 * d->blur_ext + 1 : 0)) return 1;
+
+    /* triangles: upload raw, expand on device, drop raw */
+    float *d_raw = nullptr;
+    if (dev_upload(ctx, &d_raw, d->tris9, (size_t)d->n_tris * 9)) return 1;
+    if (dev_alloc(ctx, &ctx->d_ptris, d->n_tris)) return 1;
+    if (dev_alloc(ctx, &ctx->d_raytris, d->n_tris)) return 1;
+    if (d->n_tris) {
+        prepare_tris_kernel<<<grid_for(d->n_tris, 256), 256, 0, ctx->stream>>>(d_raw, d->n_tris, ctx->d_ptris, ctx->d_raytris);
+        CU_LAUNCH_CHECK(ctx);
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_raw);
+    return 0;
+}
+
+extern "C" int ltrgpu_set_shard(ltrgpu_Ctx *ctx, uint64_t begin, uint64_t end, int rank, int world,
+                                ltrgpu_allgather_fn allgather, void *allgather_user)
+{
+    if (end > ctx->n_lumels || begin > end) { snprintf(ctx->err, sizeof(ctx->err), "bad shard range"); return 1; }
+    ctx->sh_begin = begin; ctx->sh_end = end; ctx->rank = rank; ctx->world = world;
+    ctx->allgather = allgather; ctx->allgather_user = allgather_user;
+    return 0;
+}
+
+extern "C" int ltrgpu_get_counters(ltrgpu_Ctx *ctx, ltrgpu_Counters *out)
+{
+    unsigned long long c[CNT_COUNT];
+    CU_TRY(ctx, cudaMemcpyAsync(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ltrgpu_Counters &h = ctx->host_counters;
+    h.marches = c[CNT_MARCHES]; h.distance_queries = c[CNT_DIST_QUERIES]; h.ao_segments = c[CNT_AO_SEGMENTS];
+    h.correction_rays = c[CNT_CORR_RAYS]; h.rad_pairs = c[CNT_RAD_PAIRS]; h.rad_segments = c[CNT_RAD_SEGMENTS];
+    h.rad_links = c[CNT_RAD_LINKS]; h.node_visits = c[CNT_NODE_VISITS]; h.tri_tests = c[CNT_TRI_TESTS];
+    *out = h;
+    return 0;
+}

@@ -1,0 +1,136 @@
+/*
+ * bake_driver.cpp -- TEST INFRASTRUCTURE (oracle side; never part of the product path).
+ *
+ * Runs one LTRSCN01 scene file through the public ltr_* API in the canonical call order of the
+ * reference's own test driver (lighter_test.cpp:167-180 polling loop, :187-256 call order) and
+ * writes the results to an LTROUT01 file.
+ *
+ * Built two ways by oracle/Makefile:
+ *   oracle/_ref/ref_bake   = this file + /root/reference/lighter.cpp + lighter_math.cpp, compiled
+ *                            where they lie with -DREF_INTERNALS (peeks at ltr_Scene members to
+ *                            dump lumels / radiosity links for stage-level parity tests);
+ *   build/b200_bake        = this file + liblighter_b200.so (public API only): the C++ drop-in
+ *                            demonstration that a reference caller relinks unchanged.
+ *
+ * usage: <exe> scene.bin out.bin [--threads N] [--internals] [--repeat K] [--quiet]
+ *
+ * LTROUT01 layout:
+ *   char magic[8]; f64 wall_seconds (median over repeats); u32 threads_used;
+ *   u32 n_lightmaps; per: u32 uid,w,h,has_normals; f32 rgb[w*h*3]; f32 nrm[w*h*4]?
+ *   u32 n_probes; f32 rgb[3] each
+ *   u32 has_internals; if 1:
+ *     u32 n_inst; per inst: u32 w,h,n; f32 pos[3n]; f32 nrm[3n]; u32 loc[n]; f32 radinfo[4n]; f32 rgb[3n]
+ *     u32 n_rows; u32 linkmap[2*n_rows]; u32 n_links; {u32 other; f32 factor}[n_links]
+ */
+#ifdef REF_INTERNALS
+#include "lighter_int.hpp"
+#endif
+#include "scene_io.h"
+
+#include <time.h>
+#include <unistd.h>
+#include <algorithm>
+
+static double now_s()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+static void wr(FILE *f, const void *p, size_t n) { if (n) fwrite(p, 1, n, f); }
+static void wr_u32(FILE *f, uint32_t v) { fwrite(&v, 4, 1, f); }
+
+int main(int argc, char **argv)
+{
+    if (argc < 3) {
+        fprintf(stderr, "usage: %s scene.bin out.bin [--threads N] [--internals] [--repeat K] [--quiet]\n", argv[0]);
+        return 2;
+    }
+    int threads = 0, repeat = 1;
+    bool internals = false, quiet = false;
+    for (int i = 3; i < argc; ++i) {
+        if (!strcmp(argv[i], "--threads") && i + 1 < argc) threads = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--repeat") && i + 1 < argc) repeat = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--internals")) internals = true;
+        else if (!strcmp(argv[i], "--quiet")) quiet = true;
+    }
+
+    sio::SceneFile S;
+    if (!sio::load(argv[1], S)) return 1;
+
+    std::vector<double> walls;
+    ltr_Scene *scene = NULL;
+    for (int r = 0; r < repeat; ++r) {
+        if (scene) ltr_DestroyScene(scene);
+        scene = sio::build(S, threads);
+        ltr_WorkStatus st;
+        const char *last = NULL;
+        double t0 = now_s();
+        ltr_Start(scene);
+        while (ltr_GetStatus(scene, &st)) {
+            if (!quiet && st.stage != last) { last = st.stage; fprintf(stderr, "  [%7.3fs] %s\n", now_s() - t0, last); }
+            usleep(200);
+        }
+        walls.push_back(now_s() - t0);
+    }
+    std::sort(walls.begin(), walls.end());
+    double wall = walls[walls.size() / 2];
+
+    long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+    uint32_t used = (uint32_t)std::max(1L, std::min((long)(threads > 0 ? threads : 0x7fff), ncpu));
+    if (!quiet) fprintf(stderr, "bake wall %.6f s (median of %d), threads %u\n", wall, repeat, used);
+
+    FILE *f = fopen(argv[2], "wb");
+    if (!f) { fprintf(stderr, "cannot write %s\n", argv[2]); return 1; }
+    wr(f, "LTROUT01", 8);
+    wr(f, &wall, 8);
+    wr_u32(f, used);
+
+    ltr_WorkOutputInfo info;
+    ltr_GetWorkOutputInfo(scene, &info);
+    wr_u32(f, info.lightmap_count);
+    for (u32 i = 0; i < info.lightmap_count; ++i) {
+        ltr_WorkOutput wo;
+        if (!ltr_GetWorkOutput(scene, i, &wo)) { fprintf(stderr, "ltr_GetWorkOutput(%u) failed\n", i); return 1; }
+        wr_u32(f, wo.uid); wr_u32(f, wo.width); wr_u32(f, wo.height); wr_u32(f, wo.normals_xyzf ? 1 : 0);
+        wr(f, wo.lightmap_rgb, (size_t)wo.width * wo.height * 12);
+        if (wo.normals_xyzf) wr(f, wo.normals_xyzf, (size_t)wo.width * wo.height * 16);
+    }
+    wr_u32(f, info.sample_count);
+    for (u32 i = 0; i < info.sample_count; ++i) wr(f, info.samples[i].out_color, 12);
+
+#ifdef REF_INTERNALS
+    if (internals) {
+        wr_u32(f, 1);
+        wr_u32(f, (uint32_t)scene->m_meshInstances.size());
+        for (size_t m = 0; m < scene->m_meshInstances.size(); ++m) {
+            ltr_MeshInstance *mi = scene->m_meshInstances[m];
+            uint32_t n = (uint32_t)mi->m_samples_pos.size();
+            wr_u32(f, mi->lm_width); wr_u32(f, mi->lm_height); wr_u32(f, n);
+            wr(f, VDATA(mi->m_samples_pos), (size_t)n * 12);
+            wr(f, VDATA(mi->m_samples_nrm), (size_t)n * 12);
+            if (mi->m_samplecont) {           /* probes carry no loc / radinfo */
+                std::vector<uint32_t> zl(n, 0); std::vector<float> zr((size_t)n * 4, 0.f);
+                wr(f, zl.data(), (size_t)n * 4); wr(f, zr.data(), (size_t)n * 16);
+            } else {
+                wr(f, VDATA(mi->m_samples_loc), (size_t)n * 4);
+                wr(f, VDATA(mi->m_samples_radinfo), (size_t)n * 16);
+            }
+            wr(f, VDATA(mi->m_lightmap), (size_t)n * 12);
+        }
+        uint32_t rows = (uint32_t)(scene->m_radLinkMap.size() / 2);
+        wr_u32(f, rows);
+        wr(f, VDATA(scene->m_radLinkMap), (size_t)rows * 8);
+        wr_u32(f, (uint32_t)scene->m_radLinks.size());
+        wr(f, VDATA(scene->m_radLinks), scene->m_radLinks.size() * 8);
+    } else
+#endif
+    {
+        (void)internals;
+        wr_u32(f, 0);
+    }
+    fclose(f);
+    ltr_DestroyScene(scene);
+    return 0;
+}
