@@ -33,6 +33,7 @@ typedef struct ltrx_Stats {
     double t_total, t_prexform, t_accel, t_upload, t_samples, t_direct, t_radiosity, t_ao, t_finalize, t_readback;
     /* device milliseconds (CUDA events on the bake stream) */
     float gpu_ms_samples, gpu_ms_direct, gpu_ms_march, gpu_ms_radiosity, gpu_ms_ao, gpu_ms_finalize, gpu_ms_total;
+    float gpu_ms_rad_pairs, gpu_ms_rad_vis, gpu_ms_span;   /* radiosity pair sweep / visibility kernels; first-to-last event span of the bake */
     /* work counters of THIS rank's shard (units of SURVEY.md 8d) */
     uint64_t n_lumels_total, n_lumels_local, n_triangles, n_bvh_nodes;
     uint64_t n_marches, n_distance_queries, n_ao_segments, n_correction_rays;
@@ -90,6 +91,11 @@ LTRAPI int ltrx_test_scene_queries(const float *tris9, u32 ntris,
 LTRAPI int ltrx_test_march(const float *tris9, u32 ntris, const float *from3, const float *to3,
                            const float *k, u32 n, float *out, u32 *steps_out);
 LTRAPI int ltrx_test_spiral_dirs(const float *nrm3, const float *randoff, u32 n, int samples, float *out3);
+/* host-only builders (no GPU): the reference-order tree (8 words per node: lo3, hi3, ch, ido; item stream
+ * "<count> ids...") and the flat scene BVH with a structural self-check (returns 0 when it fails) */
+LTRAPI int ltrx_test_reftree(const float *tris9, u32 ntris, void *nodes_out, u32 nodes_cap, int32_t *items_out, u32 items_cap,
+                             u32 *n_nodes, u32 *n_items);
+LTRAPI int ltrx_test_bvh(const float *tris9, u32 ntris, int leaf_max, u32 *n_nodes, u32 *depth, u32 *order_out, float *bounds6);
 
 #ifdef __cplusplus
 }

@@ -90,7 +90,8 @@ class Stats(C.Structure):
     _fields_ = ([(n, C.c_double) for n in ("t_total", "t_prexform", "t_accel", "t_upload", "t_samples", "t_direct",
                                            "t_radiosity", "t_ao", "t_finalize", "t_readback")] +
                 [(n, C.c_float) for n in ("gpu_ms_samples", "gpu_ms_direct", "gpu_ms_march", "gpu_ms_radiosity",
-                                          "gpu_ms_ao", "gpu_ms_finalize", "gpu_ms_total")] +
+                                          "gpu_ms_ao", "gpu_ms_finalize", "gpu_ms_total", "gpu_ms_rad_pairs", "gpu_ms_rad_vis",
+                                          "gpu_ms_span")] +
                 [(n, C.c_uint64) for n in ("n_lumels_total", "n_lumels_local", "n_triangles", "n_bvh_nodes", "n_marches",
                                            "n_distance_queries", "n_ao_segments", "n_correction_rays", "n_rad_pairs",
                                            "n_rad_segments", "n_rad_links", "n_node_visits", "n_tri_tests",
@@ -118,7 +119,7 @@ LTR_SYMBOLS = ["ltr_DefaultSizeFunc", "ltr_CreateScene", "ltr_DestroyScene", "lt
 LTRX_SYMBOLS = ["ltrx_Version", "ltrx_SetDevice", "ltrx_NcclUniqueId", "ltrx_SetShard", "ltrx_ShardRange", "ltrx_GetStats",
                 "ltrx_GetError", "ltrx_Prepare", "ltrx_BakeResident", "ltrx_Finish", "ltrx_SetDebug", "ltrx_GetLumels",
                 "ltrx_GetLinks", "ltrx_GetShadowFactors", "ltrx_test_point_tri_distance", "ltrx_test_seg_tri",
-                "ltrx_test_scene_queries", "ltrx_test_march", "ltrx_test_spiral_dirs"]
+                "ltrx_test_scene_queries", "ltrx_test_march", "ltrx_test_spiral_dirs", "ltrx_test_reftree", "ltrx_test_bvh"]
 
 _lib = None
 
@@ -175,6 +176,8 @@ def lib() -> C.CDLL:
     L.ltrx_test_scene_queries.argtypes = [fp, u32, fp, fp, u32, fp, ip, fp, ip]
     L.ltrx_test_march.argtypes = [fp, u32, fp, fp, fp, u32, fp, C.POINTER(u32)]
     L.ltrx_test_spiral_dirs.argtypes = [fp, fp, u32, C.c_int, fp]
+    L.ltrx_test_reftree.argtypes = [fp, u32, C.c_void_p, u32, C.c_void_p, u32, C.POINTER(u32), C.POINTER(u32)]
+    L.ltrx_test_bvh.argtypes = [fp, u32, C.c_int, C.POINTER(u32), C.POINTER(u32), C.c_void_p, fp]
     _lib = L
     return L
 
@@ -440,3 +443,25 @@ def test_spiral_dirs(nrm: np.ndarray, randoff: np.ndarray, samples: int) -> np.n
     if not lib().ltrx_test_spiral_dirs(_fp(nrm), _fp(randoff), len(nrm), samples, _fp(out)):
         raise RuntimeError("ltrx_test_spiral_dirs failed (no CUDA device?)")
     return out
+
+
+def test_reftree(tris: np.ndarray) -> tuple:
+    """Host-only: build the reference-order box tree over triangle boxes -> (nodes[n,8] as u32 words, items)."""
+    tris = np.ascontiguousarray(tris, np.float32)
+    cap_n, cap_i = 2 * len(tris) + 8, 3 * len(tris) + 8
+    nodes = np.zeros((cap_n, 8), np.uint32)
+    items = np.zeros(cap_i, np.int32)
+    nn, ni = u32(), u32()
+    if not lib().ltrx_test_reftree(_fp(tris), len(tris), nodes.ctypes.data, cap_n, items.ctypes.data, cap_i, C.byref(nn), C.byref(ni)):
+        raise RuntimeError("ltrx_test_reftree: capacity")
+    return nodes[:nn.value], items[:ni.value]
+
+
+def test_bvh(tris: np.ndarray, leaf_max: int = 4) -> dict:
+    """Host-only: build the flat scene BVH and run its structural self-check."""
+    tris = np.ascontiguousarray(tris, np.float32)
+    nn, depth = u32(), u32()
+    order = np.zeros(max(len(tris), 1), np.uint32)
+    bounds = np.zeros(6, np.float32)
+    ok = lib().ltrx_test_bvh(_fp(tris), len(tris), leaf_max, C.byref(nn), C.byref(depth), order.ctypes.data, _fp(bounds))
+    return dict(ok=bool(ok), n_nodes=nn.value, depth=depth.value, order=order[:len(tris)], bounds=bounds)

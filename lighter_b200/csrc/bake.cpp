@@ -383,6 +383,7 @@ void gpu_stages(ltr_Scene *S)
     const ltr_Config &cfg = S->config;
     const size_t ni = S->instances.size();
     gpu_check(S, ltrgpu_reset_bake(B.gpu), "reset");
+    gpu_check(S, ltrgpu_span_begin(B.gpu), "span");
 
     double t0 = now_s();
     S->stage.store("generating samples");
@@ -474,6 +475,7 @@ void gpu_stages(ltr_Scene *S)
         /* per-lumel colours BEFORE the all-gather/finalize (local shard values are final here) */
     }
     gpu_check(S, ltrgpu_finalize(B.gpu), "finalize");
+    gpu_check(S, ltrgpu_span_end(B.gpu), "span");
     S->stats.t_finalize = now_s() - t0;
 }
 
@@ -527,7 +529,23 @@ void readback(ltr_Scene *S)
         st.gpu_ms_samples = c.ms_samples; st.gpu_ms_direct = c.ms_direct; st.gpu_ms_march = c.ms_march;
         st.gpu_ms_radiosity = c.ms_radiosity; st.gpu_ms_ao = c.ms_ao; st.gpu_ms_finalize = c.ms_finalize;
         st.gpu_ms_total = c.ms_samples + c.ms_direct + c.ms_radiosity + c.ms_ao + c.ms_finalize;
+        st.gpu_ms_rad_pairs = c.ms_rad_pairs; st.gpu_ms_rad_vis = c.ms_rad_vis; st.gpu_ms_span = c.ms_span;
     }
+}
+
+void collect_counters(ltr_Scene *S)
+{
+    ltrgpu_Counters c;
+    if (!S->bake || !S->bake->gpu || ltrgpu_get_counters(S->bake->gpu, &c) != 0) return;
+    ltrx_Stats &st = S->stats;
+    st.n_marches = c.marches; st.n_distance_queries = c.distance_queries; st.n_ao_segments = c.ao_segments;
+    st.n_correction_rays = c.correction_rays; st.n_rad_pairs = c.rad_pairs; st.n_rad_segments = c.rad_segments;
+    st.n_rad_links = c.rad_links; st.n_node_visits = c.node_visits; st.n_tri_tests = c.tri_tests;
+    st.kernel_launches = c.kernel_launches; st.h2d_bytes = c.h2d_bytes; st.d2h_bytes = c.d2h_bytes;
+    st.gpu_ms_samples = c.ms_samples; st.gpu_ms_direct = c.ms_direct; st.gpu_ms_march = c.ms_march;
+    st.gpu_ms_radiosity = c.ms_radiosity; st.gpu_ms_ao = c.ms_ao; st.gpu_ms_finalize = c.ms_finalize;
+    st.gpu_ms_total = c.ms_samples + c.ms_direct + c.ms_radiosity + c.ms_ao + c.ms_finalize;
+    st.gpu_ms_rad_pairs = c.ms_rad_pairs; st.gpu_ms_rad_vis = c.ms_rad_vis; st.gpu_ms_span = c.ms_span;
 }
 
 template <class F> int guarded(ltr_Scene *S, F f)
@@ -626,9 +644,10 @@ int ltrx_BakeResident(ltr_Scene *scene, float *gpu_ms_out)
 {
     if (!scene->bake || !scene->bake->prepared || !scene->bake->gpu) { scene->error = "ltrx_BakeResident before ltrx_Prepare"; return 0; }
     int ok = guarded(scene, [&]() { gpu_stages(scene); });
-    ltrgpu_Counters c;
-    if (ok && ltrgpu_get_counters(scene->bake->gpu, &c) == 0 && gpu_ms_out)
-        *gpu_ms_out = c.ms_samples + c.ms_direct + c.ms_radiosity + c.ms_ao + c.ms_finalize;
+    if (ok) {
+        collect_counters(scene);
+        if (gpu_ms_out) *gpu_ms_out = scene->stats.gpu_ms_span;     /* first-to-last CUDA event on the bake stream */
+    }
     scene->stage.store(ok ? "baked" : nullptr);
     return ok;
 }
@@ -667,6 +686,51 @@ int ltrx_GetLinks(ltr_Scene *scene, ltrx_Links *out)
     if (!B || B->d_lrow.empty()) return 0;
     out->rows = B->d_lrow.size() - 1; out->count = B->d_lother.size();
     out->row_offset = B->d_lrow.data(); out->other = B->d_lother.data(); out->factor = B->d_lfac.data();
+    return 1;
+}
+
+/* host-only test hooks: the reference-order tree and the flat BVH builders (no GPU involved) */
+int ltrx_test_reftree(const float *tris9, u32 ntris, void *nodes_out, u32 nodes_cap, int32_t *items_out, u32 items_cap, u32 *n_nodes, u32 *n_items)
+{
+    std::vector<Box3> boxes(ntris);
+    for (u32 i = 0; i < ntris; ++i) {
+        const float *t = tris9 + 9 * (size_t)i;
+        V3 a = mk3(t[0], t[1], t[2]), b = mk3(t[3], t[4], t[5]), c = mk3(t[6], t[7], t[8]);
+        boxes[i].lo = min3(a, min3(b, c)); boxes[i].hi = max3(a, max3(b, c));
+    }
+    RefTree T;
+    T.build(boxes.data(), boxes.size());
+    *n_nodes = (u32)T.nodes.size(); *n_items = (u32)T.items.size();
+    if (T.nodes.size() > nodes_cap || T.items.size() > items_cap) return 0;
+    memcpy(nodes_out, T.nodes.data(), T.nodes.size() * sizeof(RefNode));
+    if (!T.items.empty()) memcpy(items_out, T.items.data(), T.items.size() * 4);
+    return 1;
+}
+
+int ltrx_test_bvh(const float *tris9, u32 ntris, int leaf_max, u32 *n_nodes, u32 *depth, u32 *order_out, float *bounds6)
+{
+    SceneBvh bvh;
+    build_scene_bvh(tris9, ntris, bvh, leaf_max, 0);
+    *n_nodes = (u32)bvh.nodes.size(); *depth = (u32)bvh.depth;
+    if (order_out && ntris) memcpy(order_out, bvh.order.data(), (size_t)ntris * 4);
+    if (bounds6) { bounds6[0] = bvh.bounds.lo.x; bounds6[1] = bvh.bounds.lo.y; bounds6[2] = bvh.bounds.lo.z; bounds6[3] = bvh.bounds.hi.x; bounds6[4] = bvh.bounds.hi.y; bounds6[5] = bvh.bounds.hi.z; }
+    /* structural self-check: every triangle appears in exactly one leaf and inside its leaf box */
+    std::vector<int> seen(ntris, 0);
+    for (const BvhNode &n : bvh.nodes) {
+        const int32_t cs[2] = { n.c0, n.c1 };
+        const float lo[2][3] = { { n.lo0x, n.lo0y, n.lo0z }, { n.lo1x, n.lo1y, n.lo1z } }, hi[2][3] = { { n.hi0x, n.hi0y, n.hi0z }, { n.hi1x, n.hi1y, n.hi1z } };
+        for (int k = 0; k < 2; ++k) {
+            if (cs[k] >= 0) continue;
+            uint32_t code = ~cs[k], first = code >> 3, cnt = code & 7u;
+            for (uint32_t t = first; t < first + cnt; ++t) {
+                if (t >= ntris) return 0;
+                seen[t]++;
+                const float *v = tris9 + 9 * (size_t)bvh.order[t];
+                for (int c = 0; c < 9; ++c) if (v[c] < lo[k][c % 3] || v[c] > hi[k][c % 3]) return 0;
+            }
+        }
+    }
+    for (u32 t = 0; t < ntris; ++t) if (seen[t] != 1) return 0;
     return 1;
 }
 

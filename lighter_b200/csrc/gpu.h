@@ -81,7 +81,7 @@ typedef struct ltrgpu_Counters {
     uint64_t rad_pairs, rad_segments, rad_links;
     uint64_t node_visits, tri_tests;
     uint64_t kernel_launches, h2d_bytes, d2h_bytes;
-    float ms_samples, ms_direct, ms_march, ms_radiosity, ms_ao, ms_finalize;
+    float ms_samples, ms_direct, ms_march, ms_radiosity, ms_ao, ms_finalize, ms_rad_pairs, ms_rad_vis, ms_span;
 } ltrgpu_Counters;
 
 /* all-gather hook for the multi-GPU radiance exchange: gathers `bytes_per_rank` bytes from
@@ -124,6 +124,8 @@ int ltrgpu_download_probe_colors(ltrgpu_Ctx *ctx, float *rgb3);
 int ltrgpu_sync(ltrgpu_Ctx *ctx);
 int ltrgpu_get_counters(ltrgpu_Ctx *ctx, ltrgpu_Counters *out);
 int ltrgpu_reset_bake(ltrgpu_Ctx *ctx);     /* drop lumels/results, keep the uploaded scene (bench re-runs) */
+int ltrgpu_span_begin(ltrgpu_Ctx *ctx);     /* CUDA events on the bake stream bracketing all GPU stages of one bake */
+int ltrgpu_span_end(ltrgpu_Ctx *ctx);
 
 /* debug dumps */
 int ltrgpu_download_shadow_factors(ltrgpu_Ctx *ctx, uint32_t light, float *out /* local lumels */);

@@ -215,8 +215,10 @@ extern "C" int ltrgpu_finalize(ltrgpu_Ctx *ctx)
     if (dev_alloc(ctx, &ctx->d_image_tmp, nt * 3)) return 1;
     if (dev_alloc(ctx, &ctx->d_mask, nt)) return 1;
     if (dev_alloc(ctx, &ctx->d_mask_tmp, nt)) return 1;
-    CU_TRY(ctx, cudaMemsetAsync(ctx->d_image, 0, (nt ? nt : 1) * 12, st));
-    CU_TRY(ctx, cudaMemsetAsync(ctx->d_mask, 0, nt ? nt : 1, st));
+    if (nt) {
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_image, 0, nt * 12, st));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_mask, 0, nt, st));
+    }
 
     const uint64_t n = ctx->n_lumels, first = ctx->n_probes;
     if (n > first) {
@@ -251,7 +253,7 @@ extern "C" int ltrgpu_finalize(ltrgpu_Ctx *ctx)
          * (lighter.cpp:973-974,1015-1020), a heap overrun when ds2x is on; we keep the full-size
          * texture so every write is in bounds and hand out full-size normals. */
         if (dev_alloc(ctx, &ctx->d_normals, nt * 4)) return 1;
-        CU_TRY(ctx, cudaMemsetAsync(ctx->d_normals, 0, (nt ? nt : 1) * 16, st));
+        if (nt) CU_TRY(ctx, cudaMemsetAsync(ctx->d_normals, 0, nt * 16, st));
         if (n > first) {
             scatter_normals_kernel<<<grid_for(n - first, 256), 256, 0, st>>>(ctx->d_lnmap, ctx->d_lloc, ctx->d_linst, first, n, d_off,
                                                                             (float4 *)ctx->d_normals);

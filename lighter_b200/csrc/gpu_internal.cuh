@@ -21,7 +21,7 @@ struct ltrgpu_Ctx {
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_span0 = nullptr, ev_span1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     char err[512] = {0};
 
     ltrgpu_Params params;
@@ -70,7 +70,8 @@ struct ltrgpu_Ctx {
     uint32_t *d_active_count = nullptr;
 
     /* ---- radiosity ---- */
-    uint64_t rad_rows = 0, rad_links = 0;
+    uint64_t rad_rows = 0, rad_links = 0, rad_k0 = 0, rad_n = 0;
+    uint32_t *d_rad_sidx = nullptr;           /* Morton order: sorted position -> original lumel index */
     uint64_t *d_rad_rowoff = nullptr;
     uint32_t *d_rad_other = nullptr;
     float *d_rad_factor = nullptr;

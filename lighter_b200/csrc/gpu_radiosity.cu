@@ -11,15 +11,21 @@
  *   totalLight and inputEnergy in ascending partner order; out <- in after each bounce; the lumel
  *   colour becomes totalLight.
  *
- * GPU formulation:
- *   - the O(N^2) pair loop becomes a tiled sweep: 128-lumel row tiles x 128-lumel column tiles, tile
- *     pairs farther apart than sqrt(1/(0.001*pi)) = 17.85 units can never link (f < 0.001 because
- *     dotA*dotB <= len^2) and are skipped by a box test;
- *   - pairs passing the arithmetic test go to a candidate list (warp-aggregated append), one thread
- *     per candidate then traces the any-hit segment on the scene BVH; survivors are sorted by
- *     (row, partner) so each row's links are in the reference's accumulation order (CSR);
- *   - rows are FULL (both directions) so a bounce is a pure gather, one thread per row, and rows can
- *     be sharded across GPUs: only E_j = (out_j*diffuse_j)*area_j is exchanged per bounce.
+ * GPU formulation (the reference's loop is a serial O(N^2) sweep with a stored link list):
+ *   1. lumels are sorted along a Morton curve so that 128 consecutive lumels form a spatially compact
+ *      TILE with a tight position box and a tight box of normal components;
+ *   2. a tile pair is skipped when NO pair in it can link: box distance > 17.85 (f < 0.001 because
+ *      dotA*dotB <= len^2), or interval bounds give max dotA <= 0.001, max dotB <= 0.001, or
+ *      max dotA * max dotB / (min len^4 * pi) < 0.001 -- exact pruning, no approximation;
+ *   3. surviving tile pairs are swept once per UNORDERED pair (the factor is symmetric bit for bit:
+ *      P_j-P_i == -(P_i-P_j) exactly in IEEE arithmetic); pairs passing the arithmetic test go
+ *      through a per-CTA shared-memory queue to a candidate list;
+ *   4. one thread per candidate traces the any-hit segment (from the lower lumel index to the
+ *      higher, as the reference does) on the scene BVH; blocked pairs become two directed links;
+ *   5. links are radix-sorted by (row, partner index) -> CSR rows in the reference's accumulation
+ *      order; a bounce is a pure gather, one thread per row.
+ * Multi-GPU: rows are sharded by Morton position (contiguous tile ranges = compact regions); per
+ * bounce only E_j = (out_j*diffuse_j)*area_j (16 B/lumel) is all-gathered over NCCL.
  */
 #include "gpu_internal.cuh"
 
@@ -28,25 +34,35 @@
 
 #define RAD_TILE 128
 #define RAD_CUTOFF 17.85f       /* > sqrt(1/(0.001*pi)) = 17.8412; conservative */
+#define RAD_SKIP_BELOW 0.0009f  /* interval bounds below this cannot reach the 0.001 thresholds even with rounding */
+#define RAD_QUEUE 2048          /* per-CTA shared-memory candidate queue */
 
-struct RadCand { uint32_t row, col; float factor; };
+struct RadCand { uint32_t a, b; float factor; };       /* sorted positions of the two lumels */
 
-__global__ void rad_geom_kernel(const float4 *__restrict__ lpos, const float4 *__restrict__ lnrm, uint64_t n, float4 *__restrict__ gpos, float4 *__restrict__ gnrm)
+struct TileBounds { float4 plo, phi, nlo, nhi; };      /* 64 bytes: position box, normal-component box */
+
+__global__ void rad_morton_kernel(const float4 *__restrict__ lpos, uint64_t n, float3 lo, float3 inv_ext, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    gpos[i] = lpos[i];
-    V3 N = norm3(ld3(lnrm[i]));                   /* the reference re-normalises here (lighter.cpp:680) */
-    gnrm[i] = make_float4(N.x, N.y, N.z, 0.f);
+    float4 p = lpos[i];
+    auto q = [](float v) { int x = (int)(v * 1023.0f); x = x < 0 ? 0 : (x > 1023 ? 1023 : x); return (uint32_t)x; };
+    auto spread = [](uint32_t x) { x &= 0x3ffu; x = (x | (x << 16)) & 0x30000ffu; x = (x | (x << 8)) & 0x300f00fu; x = (x | (x << 4)) & 0x30c30c3u; x = (x | (x << 2)) & 0x9249249u; return x; };
+    uint32_t k = spread(q((p.x - lo.x) * inv_ext.x)) | (spread(q((p.y - lo.y) * inv_ext.y)) << 1) | (spread(q((p.z - lo.z) * inv_ext.z)) << 2);
+    keys[i] = k;
+    vals[i] = (uint32_t)i;
 }
 
-/* per 128-lumel tile: bounding box of the positions */
-__global__ void rad_tile_bounds_kernel(const float4 *__restrict__ gpos, uint64_t n, float4 *__restrict__ tlo, float4 *__restrict__ thi)
+__global__ void rad_bounds_reduce_kernel(const float4 *__restrict__ lpos, uint64_t n, float *__restrict__ out6)
 {
-    __shared__ float slo[3][RAD_TILE / 32], shi[3][RAD_TILE / 32];
-    const uint64_t i = (uint64_t)blockIdx.x * RAD_TILE + threadIdx.x;
+    /* scene bounds of the lumel positions: min/max via float atomics on the ordered-int trick */
+    __shared__ float slo[3][8], shi[3][8];
     float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
-    if (i < n) { float4 p = gpos[i]; lo[0] = hi[0] = p.x; lo[1] = hi[1] = p.y; lo[2] = hi[2] = p.z; }
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        float4 p = lpos[i];
+        lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+        hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+    }
     for (int a = 0; a < 3; ++a)
         for (int o = 16; o > 0; o >>= 1) {
             lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
@@ -54,111 +70,194 @@ __global__ void rad_tile_bounds_kernel(const float4 *__restrict__ gpos, uint64_t
         }
     if ((threadIdx.x & 31) == 0) for (int a = 0; a < 3; ++a) { slo[a][threadIdx.x >> 5] = lo[a]; shi[a][threadIdx.x >> 5] = hi[a]; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int a = 0; a < 3; ++a)
-            for (int w = 1; w < RAD_TILE / 32; ++w) { slo[a][0] = fminf(slo[a][0], slo[a][w]); shi[a][0] = fmaxf(shi[a][0], shi[a][w]); }
-        tlo[blockIdx.x] = make_float4(slo[0][0], slo[1][0], slo[2][0], 0.f);
-        thi[blockIdx.x] = make_float4(shi[0][0], shi[1][0], shi[2][0], 0.f);
+    if (threadIdx.x < 3) {
+        int a = threadIdx.x;
+        float l = slo[a][0], h = shi[a][0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { l = fminf(l, slo[a][w]); h = fmaxf(h, shi[a][w]); }
+        /* float atomic min/max through the sign-aware integer ordering */
+        int *pl = (int *)(out6 + a), *ph = (int *)(out6 + 3 + a);
+        if (l >= 0) atomicMin(pl, __float_as_int(l)); else atomicMax((unsigned *)pl, __float_as_uint(l));
+        if (h >= 0) atomicMax(ph, __float_as_int(h)); else atomicMin((unsigned *)ph, __float_as_uint(h));
     }
 }
 
-/* form factor of the ordered pair (a < b); returns false when the reference drops the pair */
-__device__ __forceinline__ bool rad_pair_factor(V3 Pa, V3 Na, V3 Pb, V3 Nb, float &factor)
+/* gather the sorted geometry; the reference re-normalises the normal here (lighter.cpp:680) */
+__global__ void rad_gather_kernel(const float4 *__restrict__ lpos, const float4 *__restrict__ lnrm, const uint32_t *__restrict__ sidx, uint64_t n,
+                                  uint64_t n_pad, float4 *__restrict__ spos, float4 *__restrict__ snrm)
 {
-    V3 d = Pb - Pa;
-    float dotA = dot3(Na, d);
-    float dotB = dot3(Nb, -d);
-    if (dotA <= LB_SMALL || dotB <= LB_SMALL) return false;
-    float lensq = lensq3(d);
-    factor = dotA * dotB / (lensq * lensq * 3.14159274101257324f);
-    return !(factor < LB_SMALL);
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_pad) return;
+    if (k < n) {
+        const uint32_t i = sidx[k];
+        spos[k] = lpos[i];
+        V3 N = norm3(ld3(lnrm[i]));
+        snrm[k] = make_float4(N.x, N.y, N.z, 0.f);
+    } else {                                    /* padding lumels can never link: zero normal */
+        spos[k] = make_float4(3.0e30f, 3.0e30f, 3.0e30f, 0.f);
+        snrm[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 }
 
-/* one CTA = one row tile; sweeps the column tiles in ascending order */
+__global__ void rad_tile_bounds_kernel(const float4 *__restrict__ spos, const float4 *__restrict__ snrm, uint64_t n, TileBounds *__restrict__ tb)
+{
+    __shared__ float s[12][RAD_TILE / 32];
+    const uint64_t k = (uint64_t)blockIdx.x * RAD_TILE + threadIdx.x;
+    float v[12];
+    for (int a = 0; a < 6; ++a) { v[a] = INFINITY; v[6 + a] = -INFINITY; }          /* [0..2] plo, [3..5] nlo, [6..8] phi, [9..11] nhi */
+    if (k < n) {
+        float4 p = spos[k], q = snrm[k];
+        v[0] = v[6] = p.x; v[1] = v[7] = p.y; v[2] = v[8] = p.z;
+        v[3] = v[9] = q.x; v[4] = v[10] = q.y; v[5] = v[11] = q.z;
+    }
+    for (int a = 0; a < 12; ++a)
+        for (int o = 16; o > 0; o >>= 1) {
+            float t = __shfl_xor_sync(0xffffffffu, v[a], o);
+            v[a] = a < 6 ? fminf(v[a], t) : fmaxf(v[a], t);
+        }
+    if ((threadIdx.x & 31) == 0) for (int a = 0; a < 12; ++a) s[a][threadIdx.x >> 5] = v[a];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int a = 0; a < 12; ++a)
+            for (int w = 1; w < RAD_TILE / 32; ++w) s[a][0] = a < 6 ? fminf(s[a][0], s[a][w]) : fmaxf(s[a][0], s[a][w]);
+        TileBounds t;
+        t.plo = make_float4(s[0][0], s[1][0], s[2][0], 0.f); t.nlo = make_float4(s[3][0], s[4][0], s[5][0], 0.f);
+        t.phi = make_float4(s[6][0], s[7][0], s[8][0], 0.f); t.nhi = make_float4(s[9][0], s[10][0], s[11][0], 0.f);
+        tb[blockIdx.x] = t;
+    }
+}
+
+/* max over n in [nl,nh], d in [dl,dh] of n*d (one axis) */
+__device__ __forceinline__ float imax_prod(float nl, float nh, float dl, float dh)
+{
+    return fmaxf(fmaxf(nl * dl, nl * dh), fmaxf(nh * dl, nh * dh));
+}
+
+/* can any lumel pair of the two tiles link?  Conservative (never rejects a linking pair). */
+__device__ __forceinline__ bool tile_pair_may_link(const TileBounds &R, const TileBounds &C)
+{
+    /* d = P_c - P_r per axis */
+    const float dlx = C.plo.x - R.phi.x, dhx = C.phi.x - R.plo.x;
+    const float dly = C.plo.y - R.phi.y, dhy = C.phi.y - R.plo.y;
+    const float dlz = C.plo.z - R.phi.z, dhz = C.phi.z - R.plo.z;
+    const float gx = fmaxf(fmaxf(dlx, -dhx), 0.f), gy = fmaxf(fmaxf(dly, -dhy), 0.f), gz = fmaxf(fmaxf(dlz, -dhz), 0.f);
+    const float min_len2 = gx * gx + gy * gy + gz * gz;
+    if (!(min_len2 <= RAD_CUTOFF * RAD_CUTOFF)) return false;         /* also rejects padding tiles (inf/nan) */
+    const float maxA = imax_prod(R.nlo.x, R.nhi.x, dlx, dhx) + imax_prod(R.nlo.y, R.nhi.y, dly, dhy) + imax_prod(R.nlo.z, R.nhi.z, dlz, dhz);
+    const float maxB = imax_prod(C.nlo.x, C.nhi.x, -dhx, -dlx) + imax_prod(C.nlo.y, C.nhi.y, -dhy, -dly) + imax_prod(C.nlo.z, C.nhi.z, -dhz, -dlz);
+    if (maxA < RAD_SKIP_BELOW || maxB < RAD_SKIP_BELOW) return false;
+    if (min_len2 > 0.f && maxA * maxB < RAD_SKIP_BELOW * 3.14159265f * min_len2 * min_len2) return false;
+    return true;
+}
+
+/*
+ * One CTA = one row tile (128 threads = 128 row lumels held in registers); sweeps the column tiles.
+ * Tile pairs are visited once: column tile ct >= row tile rt, except that column tiles owned by
+ * ANOTHER rank are always visited (that rank builds its own rows from its side).
+ */
 __global__ void __launch_bounds__(RAD_TILE)
-rad_candidates_kernel(const float4 *__restrict__ gpos, const float4 *__restrict__ gnrm, uint64_t n,
-                      const float4 *__restrict__ tlo, const float4 *__restrict__ thi, uint32_t n_tiles,
-                      uint64_t row_begin, uint64_t row_end, uint32_t first_row_tile,
-                      RadCand *__restrict__ cand, unsigned long long cand_cap, unsigned long long *cand_count,
-                      unsigned long long *counters)
+rad_candidates_kernel(const float4 *__restrict__ spos, const float4 *__restrict__ snrm, const TileBounds *__restrict__ tb,
+                      uint32_t n_tiles, uint32_t my_t0, uint32_t my_t1, uint32_t first_row_tile,
+                      RadCand *__restrict__ cand, unsigned long long cand_cap, unsigned long long *cand_count, unsigned long long *counters)
 {
     __shared__ float4 sp[RAD_TILE], sn[RAD_TILE];
+    __shared__ RadCand queue[RAD_QUEUE];
+    __shared__ unsigned q_count;
+    __shared__ unsigned long long q_base;
     const uint32_t rt = first_row_tile + blockIdx.x;
-    const uint64_t r = (uint64_t)rt * RAD_TILE + threadIdx.x;
-    const bool row_ok = r < n && r >= row_begin && r < row_end;
-    V3 Pr = mk3(0.f), Nr = mk3(0.f);
-    if (r < n) { Pr = ld3(gpos[r]); Nr = ld3(gnrm[r]); }
-    const float4 rlo = tlo[rt], rhi = thi[rt];
-    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t r = rt * RAD_TILE + threadIdx.x;
+    const V3 Pr = ld3(spos[r]), Nr = ld3(snrm[r]);
+    const TileBounds R = tb[rt];
     unsigned tested = 0;
+    if (threadIdx.x == 0) q_count = 0;
+    __syncthreads();
     for (uint32_t ct = 0; ct < n_tiles; ++ct) {
-        const float4 clo = tlo[ct], chi = thi[ct];
-        float dx = fmaxf(fmaxf(clo.x - rhi.x, rlo.x - chi.x), 0.f);
-        float dy = fmaxf(fmaxf(clo.y - rhi.y, rlo.y - chi.y), 0.f);
-        float dz = fmaxf(fmaxf(clo.z - rhi.z, rlo.z - chi.z), 0.f);
-        if (dx * dx + dy * dy + dz * dz > RAD_CUTOFF * RAD_CUTOFF) continue;       /* CTA-uniform */
+        const bool mine = ct >= my_t0 && ct < my_t1;
+        if (mine && ct < rt) continue;                                   /* CTA-uniform: pair seen from the other tile */
+        const TileBounds C = tb[ct];
+        if (!tile_pair_may_link(R, C)) continue;                          /* CTA-uniform */
         __syncthreads();
-        const uint64_t cj = (uint64_t)ct * RAD_TILE + threadIdx.x;
-        if (cj < n) { sp[threadIdx.x] = gpos[cj]; sn[threadIdx.x] = gnrm[cj]; }
+        const uint32_t cj = ct * RAD_TILE + threadIdx.x;
+        sp[threadIdx.x] = spos[cj]; sn[threadIdx.x] = snrm[cj];
         __syncthreads();
-        const uint32_t cnt = (uint32_t)((uint64_t)ct * RAD_TILE + RAD_TILE <= n ? RAD_TILE : n - (uint64_t)ct * RAD_TILE);
-        for (uint32_t k = 0; k < cnt; ++k) {
-            const uint64_t j = (uint64_t)ct * RAD_TILE + k;
-            bool keep = false;
-            float f = 0.f;
-            if (row_ok && j != r) {
-                V3 Pj = ld3(sp[k]), Nj = ld3(sn[k]);
-                keep = (j > r) ? rad_pair_factor(Pr, Nr, Pj, Nj, f) : rad_pair_factor(Pj, Nj, Pr, Nr, f);
-                ++tested;
+        const uint32_t k0 = (ct == rt) ? threadIdx.x + 1 : 0;             /* diagonal tile: each unordered pair once */
+        for (uint32_t k = k0; k < RAD_TILE; ++k) {
+            const V3 d = ld3(sp[k]) - Pr;
+            const V3 Nj = ld3(sn[k]);
+            const float dr = dot3(Nr, d);
+            const float dj = -dot3(Nj, d);
+            ++tested;
+            if (dr <= LB_SMALL || dj <= LB_SMALL) continue;
+            const float lensq = lensq3(d);
+            const float f = dr * dj / (lensq * lensq * 3.14159274101257324f);
+            if (f < LB_SMALL) continue;
+            RadCand c; c.a = r; c.b = ct * RAD_TILE + k; c.factor = f;
+            const unsigned at = atomicAdd(&q_count, 1u);
+            if (at < RAD_QUEUE) queue[at] = c;
+            else {                                                        /* queue full: straight to global memory */
+                const unsigned long long g = atomicAdd(cand_count, 1ull);
+                if (g < cand_cap) cand[g] = c;
             }
-            const unsigned mask = __ballot_sync(0xffffffffu, keep);
-            if (mask) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(cand_count, (unsigned long long)__popc(mask));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (keep) {
-                    unsigned long long at = base + __popc(mask & ((1u << lane) - 1u));
-                    if (at < cand_cap) { RadCand c; c.row = (uint32_t)r; c.col = (uint32_t)j; c.factor = f; cand[at] = c; }
-                }
-            }
+        }
+        __syncthreads();
+        if (q_count >= RAD_QUEUE / 2) {                                   /* CTA-uniform flush */
+            const unsigned cnt = q_count < RAD_QUEUE ? q_count : RAD_QUEUE;
+            if (threadIdx.x == 0) q_base = atomicAdd(cand_count, (unsigned long long)cnt);
+            __syncthreads();
+            for (unsigned e = threadIdx.x; e < cnt; e += RAD_TILE) if (q_base + e < cand_cap) cand[q_base + e] = queue[e];
+            __syncthreads();
+            if (threadIdx.x == 0) q_count = 0;
+        }
+    }
+    __syncthreads();
+    {
+        const unsigned cnt = q_count < RAD_QUEUE ? q_count : RAD_QUEUE;
+        if (cnt) {
+            if (threadIdx.x == 0) q_base = atomicAdd(cand_count, (unsigned long long)cnt);
+            __syncthreads();
+            for (unsigned e = threadIdx.x; e < cnt; e += RAD_TILE) if (q_base + e < cand_cap) cand[q_base + e] = queue[e];
         }
     }
     count_add(counters, CNT_RAD_PAIRS, tested);
 }
 
-/* one thread per candidate: blocked segment -> link */
+/* one thread per candidate: blocked segment -> directed link(s) keyed (row sorted position, partner original index) */
 __global__ void __launch_bounds__(LB_BLOCK)
-rad_visibility_kernel(const BvhNode *__restrict__ bvh, const RayTri *__restrict__ raytris, const float4 *__restrict__ gpos,
-                      const RadCand *__restrict__ cand, unsigned long long n_cand,
-                      unsigned long long *__restrict__ keys, float *__restrict__ factors, unsigned long long *link_count,
-                      unsigned long long *counters)
+rad_visibility_kernel(const BvhNode *__restrict__ bvh, const RayTri *__restrict__ raytris, const float4 *__restrict__ spos,
+                      const uint32_t *__restrict__ sidx, const RadCand *__restrict__ cand, unsigned long long n_cand,
+                      uint32_t my_k0, uint32_t my_k1, unsigned long long *__restrict__ keys, float *__restrict__ factors,
+                      unsigned long long *link_count, unsigned long long *counters)
 {
     unsigned segs = 0;
     TravStats ts = { 0, 0 };
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long n_pad = (n_cand + 31ull) & ~31ull;
     for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_pad; e += (unsigned long long)gridDim.x * blockDim.x) {
-        bool keep = false;
+        unsigned emit = 0;                        /* bit 0: row a is mine, bit 1: row b is mine */
         RadCand c = { 0, 0, 0.f };
+        uint32_t oa = 0, ob = 0;
         if (e < n_cand) {
             c = cand[e];
-            const uint32_t a = c.row < c.col ? c.row : c.col, b = c.row < c.col ? c.col : c.row;
-            const V3 A = ld3(gpos[a]), B = ld3(gpos[b]);
+            oa = sidx[c.a]; ob = sidx[c.b];
+            const bool a_first = oa < ob;         /* the reference traces from the lower lumel index */
+            const V3 A = ld3(spos[a_first ? c.a : c.b]), B = ld3(spos[a_first ? c.b : c.a]);
             const V3 dn = norm3(B - A);
             const V3 mA = A + dn * LB_SMALL, mB = B - dn * LB_SMALL;
-            keep = bvh_segment<true>(bvh, raytris, nullptr, mA, mB, nullptr, ts) < 1.0f;
             ++segs;
+            if (bvh_segment<true>(bvh, raytris, nullptr, mA, mB, nullptr, ts) < 1.0f)
+                emit = ((c.a >= my_k0 && c.a < my_k1) ? 1u : 0u) | ((c.b >= my_k0 && c.b < my_k1) ? 2u : 0u);
         }
-        const unsigned mask = __ballot_sync(0xffffffffu, keep);
-        if (mask) {
+        const unsigned cnt = __popc(emit);
+        /* warp-aggregated append: exclusive prefix of cnt over the warp */
+        unsigned pre = cnt;
+        for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= (unsigned)o) pre += t; }
+        const unsigned total = __shfl_sync(0xffffffffu, pre, 31);
+        if (total) {
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(link_count, (unsigned long long)__popc(mask));
+            if (lane == 0) base = atomicAdd(link_count, (unsigned long long)total);
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (keep) {
-                unsigned long long at = base + __popc(mask & ((1u << lane) - 1u));
-                keys[at] = ((unsigned long long)c.row << 32) | c.col;
-                factors[at] = c.factor;
-            }
+            unsigned long long at = base + (pre - cnt);
+            if (emit & 1u) { keys[at] = ((unsigned long long)c.a << 32) | ob; factors[at] = c.factor; ++at; }
+            if (emit & 2u) { keys[at] = ((unsigned long long)c.b << 32) | oa; factors[at] = c.factor; }
         }
     }
     count_add(counters, CNT_RAD_SEGMENTS, segs);
@@ -183,63 +282,66 @@ __global__ void rad_split_keys_kernel(const unsigned long long *__restrict__ key
     if (i < n) other[i] = (uint32_t)(keys[i] & 0xffffffffull);
 }
 
-/* material / energy state: diffuse, total, out per lumel (float4 each) */
+/* material / energy state per SORTED row: diffuse(+area), total, out */
 __global__ void rad_init_kernel(const float4 *__restrict__ lrgb, const float4 *__restrict__ lrad, const float *__restrict__ diffuse3,
-                                const float *__restrict__ emissive3, uint32_t n_probes, uint64_t begin, uint64_t end,
-                                float4 *__restrict__ diff, float4 *__restrict__ total, float4 *__restrict__ out)
+                                const float *__restrict__ emissive3, const uint32_t *__restrict__ sidx, uint32_t n_probes, uint64_t n,
+                                uint64_t k0, uint64_t k1, float4 *__restrict__ diff, float4 *__restrict__ total, float4 *__restrict__ out)
 {
-    uint64_t i = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= end) return;
+    uint64_t k = k0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= k1) return;
+    if (k >= n) { diff[k] = total[k] = out[k] = make_float4(0.f, 0.f, 0.f, 0.f); return; }
+    const uint32_t i = sidx[k];
     const bool probe = i < n_probes;
     V3 d = probe ? mk3(0.f) : mk3(1.f);
     V3 e = ld3(lrgb[i]);
     if (!probe && diffuse3) {
-        d = mk3(diffuse3[i * 3], diffuse3[i * 3 + 1], diffuse3[i * 3 + 2]);
-        e = e + mk3(emissive3[i * 3], emissive3[i * 3 + 1], emissive3[i * 3 + 2]);
+        d = mk3(diffuse3[(size_t)i * 3], diffuse3[(size_t)i * 3 + 1], diffuse3[(size_t)i * 3 + 2]);
+        e = e + mk3(emissive3[(size_t)i * 3], emissive3[(size_t)i * 3 + 1], emissive3[(size_t)i * 3 + 2]);
     }
     const float area = probe ? 0.f : lrad[i].w;
-    diff[i] = make_float4(d.x, d.y, d.z, area);
-    total[i] = make_float4(e.x, e.y, e.z, 0.f);
-    out[i] = make_float4(e.x, e.y, e.z, 0.f);
+    diff[k] = make_float4(d.x, d.y, d.z, area);
+    total[k] = make_float4(e.x, e.y, e.z, 0.f);
+    out[k] = make_float4(e.x, e.y, e.z, 0.f);
 }
 
-/* E_j = (out_j * diffuse_j) * area_j, the quantity that crosses a link (and NVLink) */
-__global__ void rad_energy_kernel(const float4 *__restrict__ diff, const float4 *__restrict__ out, uint64_t begin, uint64_t end, float4 *__restrict__ E)
+/* E = (out * diffuse) * area for my sorted rows, the quantity that crosses a link (and NVLink) */
+__global__ void rad_energy_kernel(const float4 *__restrict__ diff, const float4 *__restrict__ out, uint64_t k0, uint64_t k1, float4 *__restrict__ Es)
 {
-    uint64_t i = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= end) return;
-    const float4 d = diff[i], o = out[i];
+    uint64_t k = k0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= k1) return;
+    const float4 d = diff[k], o = out[k];
     V3 e = (ld3(o) * ld3(d)) * d.w;
-    E[i] = make_float4(e.x, e.y, e.z, 0.f);
+    Es[k] = make_float4(e.x, e.y, e.z, 0.f);
+}
+
+/* sorted layout -> original lumel order (links name partners by original index) */
+__global__ void rad_unpermute_kernel(const float4 *__restrict__ src_sorted, const uint32_t *__restrict__ sidx, uint64_t n, float4 *__restrict__ dst_orig)
+{
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) dst_orig[sidx[k]] = src_sorted[k];
 }
 
 __global__ void rad_bounce_kernel(const uint64_t *__restrict__ rowoff, const uint32_t *__restrict__ other, const float *__restrict__ factor,
-                                  const float4 *__restrict__ E, uint64_t begin, uint64_t end, float4 *__restrict__ total, float4 *__restrict__ out)
+                                  const float4 *__restrict__ Eo, uint64_t k0, uint64_t k1, float4 *__restrict__ total, float4 *__restrict__ out)
 {
-    uint64_t i = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= end) return;
-    const uint64_t a = rowoff[i - begin], b = rowoff[i - begin + 1];
-    V3 t = ld3(total[i]);
+    uint64_t k = k0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= k1) return;
+    const uint64_t a = rowoff[k - k0], b = rowoff[k - k0 + 1];
+    V3 t = ld3(total[k]);
     V3 in = mk3(0.f);
-    for (uint64_t k = a; k < b; ++k) {
-        const V3 c = ld3(__ldg(E + other[k])) * factor[k];
+    for (uint64_t e = a; e < b; ++e) {
+        const V3 c = ld3(__ldg(Eo + other[e])) * factor[e];
         t = t + c;
         in = in + c;
     }
-    total[i] = make_float4(t.x, t.y, t.z, 0.f);
-    out[i] = make_float4(in.x, in.y, in.z, 0.f);
+    total[k] = make_float4(t.x, t.y, t.z, 0.f);
+    out[k] = make_float4(in.x, in.y, in.z, 0.f);
 }
 
-__global__ void rad_commit_kernel(const float4 *__restrict__ total, uint64_t begin, uint64_t end, float4 *__restrict__ lrgb)
-{
-    uint64_t i = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < end) lrgb[i] = total[i];
-}
-
-template <class T> static int grow(ltrgpu_Ctx *ctx, T **p, size_t *cap, size_t used, size_t need)
+template <class T> static int grow_buf(ltrgpu_Ctx *ctx, T **p, size_t *cap, size_t used, size_t need)
 {
     if (need <= *cap) return 0;
-    size_t ncap = *cap ? *cap : 1 << 20;
+    size_t ncap = *cap ? *cap : (size_t)1 << 20;
     while (ncap < need) ncap *= 2;
     T *q = nullptr;
     CU_TRY(ctx, cudaMalloc((void **)&q, ncap * sizeof(T)));
@@ -250,20 +352,38 @@ template <class T> static int grow(ltrgpu_Ctx *ctx, T **p, size_t *cap, size_t u
     return 0;
 }
 
+static int rad_allgather(ltrgpu_Ctx *ctx, float4 *buf, uint64_t chunk_elems, const char *what)
+{
+    if (ctx->world <= 1) return 0;
+    if (!ctx->allgather || ctx->allgather(ctx->allgather_user, buf + chunk_elems * ctx->rank, buf, chunk_elems * sizeof(float4), ctx->stream)) {
+        snprintf(ctx->err, sizeof(ctx->err), "radiosity: all-gather of %s failed", what);
+        return 1;
+    }
+    return 0;
+}
+
 extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const float *emissive3, int bounces)
 {
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const uint64_t n = ctx->n_lumels;
     if (n == 0 || bounces <= 0) return 0;
-    if (n > 0xfffffff0ull) { snprintf(ctx->err, sizeof(ctx->err), "too many lumels for radiosity"); return 1; }
+    if (n > 0x7ffffff0ull) { snprintf(ctx->err, sizeof(ctx->err), "too many lumels for radiosity"); return 1; }
     CU_TRY(ctx, cudaEventRecord(ctx->ev0, st));
-    const uint64_t rb = ctx->sh_begin, re = ctx->sh_end, n_rows = re - rb;
-    const uint32_t n_tiles = (uint32_t)((n + RAD_TILE - 1) / RAD_TILE);
 
-    float4 *gpos = nullptr, *gnrm = nullptr, *tlo = nullptr, *thi = nullptr;
-    float4 *diff = nullptr, *total = nullptr, *out = nullptr, *E = nullptr;
-    float *d_diffuse = nullptr, *d_emissive = nullptr;
+    /* tiles, padded so every rank owns the same number of whole tiles */
+    const uint32_t world = (uint32_t)(ctx->world > 0 ? ctx->world : 1);
+    const uint32_t tiles_raw = (uint32_t)((n + RAD_TILE - 1) / RAD_TILE);
+    const uint32_t tiles_per_rank = (tiles_raw + world - 1) / world;
+    const uint32_t n_tiles = tiles_per_rank * world;
+    const uint64_t n_pad = (uint64_t)n_tiles * RAD_TILE;
+    const uint32_t my_t0 = tiles_per_rank * (uint32_t)ctx->rank, my_t1 = my_t0 + tiles_per_rank;
+    const uint64_t k0 = (uint64_t)my_t0 * RAD_TILE, k1 = (uint64_t)my_t1 * RAD_TILE, n_rows = k1 - k0;
+
+    float4 *spos = nullptr, *snrm = nullptr, *diff = nullptr, *total = nullptr, *out = nullptr, *Es = nullptr, *Eo = nullptr, *lrgb_full = nullptr;
+    TileBounds *tb = nullptr;
+    uint32_t *mkeys = nullptr, *mkeys_alt = nullptr, *sidx = nullptr, *sidx_alt = nullptr;
+    float *d_bounds = nullptr, *d_diffuse = nullptr, *d_emissive = nullptr;
     RadCand *cand = nullptr;
     unsigned long long *d_cnt = nullptr;           /* [0] candidates, [1] links */
     unsigned long long *keys = nullptr, *keys_alt = nullptr;
@@ -271,65 +391,96 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
     size_t link_cap = 0, link_cap_f = 0, link_used = 0;
     void *sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0;
+    float ms_pairs = 0, ms_vis = 0;
     int rc = 1;
 
 #define RAD_TRY(x) do { if (x) goto done; } while (0)
 #define RAD_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); goto done; } } while (0)
+#define RAD_LAUNCHED() do { ctx->host_counters.kernel_launches++; RAD_CU(cudaGetLastError()); } while (0)
 
     {
-        RAD_TRY(dev_alloc(ctx, &gpos, n + LB_PAD)); RAD_TRY(dev_alloc(ctx, &gnrm, n + LB_PAD));
-        RAD_TRY(dev_alloc(ctx, &tlo, n_tiles)); RAD_TRY(dev_alloc(ctx, &thi, n_tiles));
-        RAD_TRY(dev_alloc(ctx, &diff, n + LB_PAD)); RAD_TRY(dev_alloc(ctx, &total, n + LB_PAD));
-        RAD_TRY(dev_alloc(ctx, &out, n + LB_PAD)); RAD_TRY(dev_alloc(ctx, &E, n + LB_PAD));
+        /* the emitted light of EVERY lumel is needed: gather the direct-light shards first */
+        if (world > 1) {
+            const uint64_t chunk = (n + world - 1) / world;
+            RAD_TRY(rad_allgather(ctx, ctx->d_lrgb, chunk, "direct light"));
+        }
+        lrgb_full = ctx->d_lrgb;
+
+        /* ---- 1. Morton sort ---- */
+        RAD_TRY(dev_alloc(ctx, &mkeys, n)); RAD_TRY(dev_alloc(ctx, &mkeys_alt, n));
+        RAD_TRY(dev_alloc(ctx, &sidx, n_pad)); RAD_TRY(dev_alloc(ctx, &sidx_alt, n));
+        RAD_TRY(dev_alloc(ctx, &d_bounds, 6));
+        {
+            const float init[6] = { INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY };
+            RAD_CU(cudaMemcpyAsync(d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, st));
+            rad_bounds_reduce_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(ctx->d_lpos, n, d_bounds);
+            RAD_LAUNCHED();
+            float hb[6];
+            RAD_CU(cudaMemcpyAsync(hb, d_bounds, sizeof(hb), cudaMemcpyDeviceToHost, st));
+            RAD_CU(cudaStreamSynchronize(st));
+            float3 lo = make_float3(hb[0], hb[1], hb[2]);
+            float3 inv = make_float3(hb[3] > hb[0] ? 1.0f / (hb[3] - hb[0]) : 0.f, hb[4] > hb[1] ? 1.0f / (hb[4] - hb[1]) : 0.f, hb[5] > hb[2] ? 1.0f / (hb[5] - hb[2]) : 0.f);
+            rad_morton_kernel<<<grid_for(n, 256), 256, 0, st>>>(ctx->d_lpos, n, lo, inv, mkeys, sidx);
+            RAD_LAUNCHED();
+            cub::DoubleBuffer<uint32_t> kb(mkeys, mkeys_alt), vb(sidx, sidx_alt);
+            RAD_CU(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, kb, vb, (int)n, 0, 30, st));
+            RAD_CU(cudaMalloc(&sort_tmp, sort_tmp_bytes ? sort_tmp_bytes : 16));
+            RAD_CU(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_tmp_bytes, kb, vb, (int)n, 0, 30, st));
+            ctx->host_counters.kernel_launches += 4;
+            if (vb.Current() != sidx) RAD_CU(cudaMemcpyAsync(sidx, vb.Current(), n * 4, cudaMemcpyDeviceToDevice, st));
+            RAD_CU(cudaStreamSynchronize(st));
+            cudaFree(sort_tmp); sort_tmp = nullptr; sort_tmp_bytes = 0;
+        }
+        RAD_TRY(dev_alloc(ctx, &spos, n_pad)); RAD_TRY(dev_alloc(ctx, &snrm, n_pad));
+        RAD_TRY(dev_alloc(ctx, &tb, n_tiles));
+        rad_gather_kernel<<<grid_for(n_pad, 256), 256, 0, st>>>(ctx->d_lpos, ctx->d_lnrm, sidx, n, n_pad, spos, snrm);
+        RAD_LAUNCHED();
+        rad_tile_bounds_kernel<<<n_tiles, RAD_TILE, 0, st>>>(spos, snrm, n, tb);
+        RAD_LAUNCHED();
+
+        /* ---- 2-4. candidates and visibility, in batches of row tiles bounded by the candidate buffer ---- */
         RAD_TRY(dev_alloc(ctx, &d_cnt, 2));
-        if (diffuse3) { RAD_TRY(dev_upload(ctx, &d_diffuse, diffuse3, n * 3)); RAD_TRY(dev_upload(ctx, &d_emissive, emissive3, n * 3)); }
-
-        rad_geom_kernel<<<grid_for(n, 256), 256, 0, st>>>(ctx->d_lpos, ctx->d_lnrm, n, gpos, gnrm);
-        ctx->host_counters.kernel_launches++;
-        rad_tile_bounds_kernel<<<n_tiles, RAD_TILE, 0, st>>>(gpos, n, tlo, thi);
-        ctx->host_counters.kernel_launches++;
-        RAD_CU(cudaGetLastError());
-
-        /* ---- link generation, in batches of row tiles bounded by the candidate buffer ---- */
-        const unsigned long long cand_cap = 32ull << 20;             /* 32 Mi candidates = 384 MiB */
+        const unsigned long long cand_cap = 48ull << 20;             /* 48 Mi candidates = 576 MiB */
         RAD_TRY(dev_alloc(ctx, &cand, cand_cap));
-        const uint32_t t_begin = (uint32_t)(rb / RAD_TILE), t_end = (uint32_t)((re + RAD_TILE - 1) / RAD_TILE);
-        uint32_t batch = 1024;
-        for (uint32_t t0 = t_begin; t0 < t_end;) {
-            uint32_t t1 = t0 + batch < t_end ? t0 + batch : t_end;
+        uint32_t batch = 2048;
+        for (uint32_t t0 = my_t0; t0 < my_t1;) {
+            uint32_t t1 = t0 + batch < my_t1 ? t0 + batch : my_t1;
             RAD_CU(cudaMemsetAsync(d_cnt, 0, 16, st));
-            rad_candidates_kernel<<<t1 - t0, RAD_TILE, 0, st>>>(gpos, gnrm, n, tlo, thi, n_tiles, rb, re, t0, cand, cand_cap, d_cnt, ctx->d_counters);
-            ctx->host_counters.kernel_launches++;
-            RAD_CU(cudaGetLastError());
+            RAD_CU(cudaEventRecord(ctx->ev_k0, st));
+            rad_candidates_kernel<<<t1 - t0, RAD_TILE, 0, st>>>(spos, snrm, tb, n_tiles, my_t0, my_t1, t0, cand, cand_cap, d_cnt, ctx->d_counters);
+            RAD_LAUNCHED();
+            RAD_CU(cudaEventRecord(ctx->ev_k1, st));
             unsigned long long h_cnt[2];
             RAD_CU(cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, st));
             RAD_CU(cudaStreamSynchronize(st));
+            { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1); ms_pairs += ms; }
             if (h_cnt[0] > cand_cap) {
                 if (batch == 1) { snprintf(ctx->err, sizeof(ctx->err), "radiosity: one row tile produced %llu candidates (> %llu)", h_cnt[0], cand_cap); goto done; }
-                batch = batch / 2 ? batch / 2 : 1;
-                /* the counters of the aborted attempt are discarded below by recounting: subtract them */
-                continue;
+                batch = batch / 4 ? batch / 4 : 1;
+                continue;                                             /* redo this batch smaller */
             }
             const unsigned long long nc = h_cnt[0];
             if (nc) {
-                RAD_TRY(grow(ctx, &keys, &link_cap, link_used, link_used + nc));
-                RAD_TRY(grow(ctx, &fac, &link_cap_f, link_used, link_used + nc));
+                RAD_TRY(grow_buf(ctx, &keys, &link_cap, link_used, link_used + 2 * nc));
+                RAD_TRY(grow_buf(ctx, &fac, &link_cap_f, link_used, link_used + 2 * nc));
                 unsigned long long want = (nc + LB_BLOCK - 1) / LB_BLOCK;
                 unsigned cap = (unsigned)ctx->num_sms * 32;
                 unsigned blocks = want > cap ? cap : (unsigned)want;
-                rad_visibility_kernel<<<blocks, LB_BLOCK, 0, st>>>(ctx->d_bvh, ctx->d_raytris, gpos, cand, nc, keys + link_used, fac + link_used,
-                                                                  d_cnt + 1, ctx->d_counters);
-                ctx->host_counters.kernel_launches++;
-                RAD_CU(cudaGetLastError());
+                RAD_CU(cudaEventRecord(ctx->ev_k0, st));
+                rad_visibility_kernel<<<blocks, LB_BLOCK, 0, st>>>(ctx->d_bvh, ctx->d_raytris, spos, sidx, cand, nc, (uint32_t)k0, (uint32_t)k1,
+                                                                  keys + link_used, fac + link_used, d_cnt + 1, ctx->d_counters);
+                RAD_LAUNCHED();
+                RAD_CU(cudaEventRecord(ctx->ev_k1, st));
                 RAD_CU(cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, st));
                 RAD_CU(cudaStreamSynchronize(st));
+                { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1); ms_vis += ms; }
                 link_used += h_cnt[1];
             }
             t0 = t1;
         }
-
-        /* ---- sort links by (row, partner) -> CSR in reference accumulation order ---- */
         dev_free(&cand);
+
+        /* ---- 5. sort links by (row, partner) -> CSR in reference accumulation order ---- */
         if (link_used) {
             RAD_TRY(dev_alloc(ctx, &keys_alt, link_used)); RAD_TRY(dev_alloc(ctx, &fac_alt, link_used));
             cub::DoubleBuffer<unsigned long long> kb(keys, keys_alt);
@@ -341,19 +492,21 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
             RAD_CU(cudaStreamSynchronize(st));
             if (kb.Current() != keys) { unsigned long long *t = keys; keys = keys_alt; keys_alt = t; }
             if (vb.Current() != fac) { float *t = fac; fac = fac_alt; fac_alt = t; }
+            dev_free(&keys_alt); dev_free(&fac_alt);
         }
-        dev_free(&ctx->d_rad_rowoff); dev_free(&ctx->d_rad_other); dev_free(&ctx->d_rad_factor);
+        dev_free(&ctx->d_rad_rowoff); dev_free(&ctx->d_rad_other); dev_free(&ctx->d_rad_factor); dev_free(&ctx->d_rad_sidx);
         RAD_TRY(dev_alloc(ctx, &ctx->d_rad_rowoff, n_rows + 1));
         RAD_TRY(dev_alloc(ctx, &ctx->d_rad_other, link_used));
-        rad_row_offsets_kernel<<<grid_for(n_rows + 1, 256), 256, 0, st>>>(keys, link_used, rb, n_rows, ctx->d_rad_rowoff);
-        ctx->host_counters.kernel_launches++;
+        rad_row_offsets_kernel<<<grid_for(n_rows + 1, 256), 256, 0, st>>>(keys, link_used, k0, n_rows, ctx->d_rad_rowoff);
+        RAD_LAUNCHED();
         if (link_used) {
             rad_split_keys_kernel<<<grid_for(link_used, 256), 256, 0, st>>>(keys, link_used, ctx->d_rad_other);
-            ctx->host_counters.kernel_launches++;
+            RAD_LAUNCHED();
         }
-        RAD_CU(cudaGetLastError());
+        dev_free(&keys);
         ctx->d_rad_factor = fac; fac = nullptr;
-        ctx->rad_rows = n_rows; ctx->rad_links = link_used;
+        ctx->d_rad_sidx = sidx; sidx = nullptr;
+        ctx->rad_rows = n_rows; ctx->rad_links = link_used; ctx->rad_k0 = k0; ctx->rad_n = n;
         {
             unsigned long long lc = link_used;
             RAD_CU(cudaMemcpyAsync(ctx->d_counters + CNT_RAD_LINKS, &lc, 8, cudaMemcpyHostToDevice, st));
@@ -361,56 +514,79 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
         }
 
         /* ---- bounces ---- */
-        if (n_rows) {
-            rad_init_kernel<<<grid_for(n_rows, 256), 256, 0, st>>>(ctx->d_lrgb, ctx->d_lrad, d_diffuse, d_emissive, ctx->n_probes, rb, re, diff, total, out);
-            ctx->host_counters.kernel_launches++;
-        }
+        RAD_TRY(dev_alloc(ctx, &diff, n_pad)); RAD_TRY(dev_alloc(ctx, &total, n_pad)); RAD_TRY(dev_alloc(ctx, &out, n_pad));
+        RAD_TRY(dev_alloc(ctx, &Es, n_pad)); RAD_TRY(dev_alloc(ctx, &Eo, n + LB_PAD));
+        if (diffuse3) { RAD_TRY(dev_upload(ctx, &d_diffuse, diffuse3, n * 3)); RAD_TRY(dev_upload(ctx, &d_emissive, emissive3, n * 3)); }
+        rad_init_kernel<<<grid_for(n_rows, 256), 256, 0, st>>>(lrgb_full, ctx->d_lrad, d_diffuse, d_emissive, ctx->d_rad_sidx, ctx->n_probes, n, k0, k1, diff, total, out);
+        RAD_LAUNCHED();
         for (int b = 0; b < bounces; ++b) {
-            if (n_rows) {
-                rad_energy_kernel<<<grid_for(n_rows, 256), 256, 0, st>>>(diff, out, rb, re, E);
-                ctx->host_counters.kernel_launches++;
-            }
-            if (ctx->world > 1) {
-                const uint64_t chunk = (n + ctx->world - 1) / ctx->world;
-                if (!ctx->allgather || ctx->allgather(ctx->allgather_user, E + chunk * ctx->rank, E, chunk * sizeof(float4), st)) {
-                    snprintf(ctx->err, sizeof(ctx->err), "radiosity: per-bounce all-gather failed");
-                    goto done;
-                }
-            }
-            if (n_rows) {
-                rad_bounce_kernel<<<grid_for(n_rows, 128), 128, 0, st>>>(ctx->d_rad_rowoff, ctx->d_rad_other, ctx->d_rad_factor, E, rb, re, total, out);
-                ctx->host_counters.kernel_launches++;
-            }
-            RAD_CU(cudaGetLastError());
+            rad_energy_kernel<<<grid_for(n_rows, 256), 256, 0, st>>>(diff, out, k0, k1, Es);
+            RAD_LAUNCHED();
+            RAD_TRY(rad_allgather(ctx, Es, (uint64_t)tiles_per_rank * RAD_TILE, "bounce energy"));
+            rad_unpermute_kernel<<<grid_for(n, 256), 256, 0, st>>>(Es, ctx->d_rad_sidx, n, Eo);
+            RAD_LAUNCHED();
+            rad_bounce_kernel<<<grid_for(n_rows, 128), 128, 0, st>>>(ctx->d_rad_rowoff, ctx->d_rad_other, ctx->d_rad_factor, Eo, k0, k1, total, out);
+            RAD_LAUNCHED();
         }
-        if (n_rows) {
-            rad_commit_kernel<<<grid_for(n_rows, 256), 256, 0, st>>>(total, rb, re, ctx->d_lrgb);
-            ctx->host_counters.kernel_launches++;
-        }
+        /* commit: total light back to original lumel order, for every lumel on every rank */
+        RAD_TRY(rad_allgather(ctx, total, (uint64_t)tiles_per_rank * RAD_TILE, "total light"));
+        rad_unpermute_kernel<<<grid_for(n, 256), 256, 0, st>>>(total, ctx->d_rad_sidx, n, ctx->d_lrgb);
+        RAD_LAUNCHED();
         RAD_CU(cudaEventRecord(ctx->ev1, st));
         RAD_CU(cudaStreamSynchronize(st));
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
         ctx->host_counters.ms_radiosity += ms;
+        ctx->host_counters.ms_rad_pairs += ms_pairs;
+        ctx->host_counters.ms_rad_vis += ms_vis;
         rc = 0;
     }
 done:
-    cudaFree(gpos); cudaFree(gnrm); cudaFree(tlo); cudaFree(thi); cudaFree(diff); cudaFree(total); cudaFree(out); cudaFree(E);
+    cudaFree(spos); cudaFree(snrm); cudaFree(diff); cudaFree(total); cudaFree(out); cudaFree(Es); cudaFree(Eo); cudaFree(tb);
+    cudaFree(mkeys); cudaFree(mkeys_alt); cudaFree(sidx); cudaFree(sidx_alt); cudaFree(d_bounds);
     cudaFree(d_diffuse); cudaFree(d_emissive); cudaFree(cand); cudaFree(d_cnt); cudaFree(keys); cudaFree(keys_alt);
     cudaFree(fac); cudaFree(fac_alt); cudaFree(sort_tmp);
     return rc;
 #undef RAD_TRY
 #undef RAD_CU
+#undef RAD_LAUNCHED
 }
 
+/* debug dump: rows are in SORTED (Morton) order on the device; hand them back in original lumel order */
 extern "C" int ltrgpu_download_links(ltrgpu_Ctx *ctx, uint64_t *row_offset, uint32_t *other, float *factor, uint64_t *rows, uint64_t *count)
 {
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    *rows = ctx->rad_rows; *count = ctx->rad_links;
-    if (!ctx->d_rad_rowoff) return 0;
-    if (row_offset) CU_TRY(ctx, cudaMemcpyAsync(row_offset, ctx->d_rad_rowoff, (ctx->rad_rows + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (other && ctx->rad_links) CU_TRY(ctx, cudaMemcpyAsync(other, ctx->d_rad_other, ctx->rad_links * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (factor && ctx->rad_links) CU_TRY(ctx, cudaMemcpyAsync(factor, ctx->d_rad_factor, ctx->rad_links * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    return 0;
+    *rows = ctx->world > 1 ? ctx->rad_rows : ctx->rad_n;
+    *count = ctx->rad_links;
+    if (!ctx->d_rad_rowoff || !row_offset) return 0;
+    const uint64_t nr = ctx->rad_rows, nl = ctx->rad_links, n = ctx->rad_n;
+    uint64_t *ro = (uint64_t *)malloc((nr + 1) * 8);
+    uint32_t *oth = (uint32_t *)malloc((nl ? nl : 1) * 4), *sidx = (uint32_t *)malloc((n ? n : 1) * 4);
+    float *fa = (float *)malloc((nl ? nl : 1) * 4);
+    cudaError_t e = cudaMemcpyAsync(ro, ctx->d_rad_rowoff, (nr + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && nl) e = cudaMemcpyAsync(oth, ctx->d_rad_other, nl * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && nl) e = cudaMemcpyAsync(fa, ctx->d_rad_factor, nl * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sidx, ctx->d_rad_sidx, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    int rc = 0;
+    if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "download_links: %s", cudaGetErrorString(e)); rc = 1; }
+    else if (ctx->world > 1) {                      /* sharded: rows stay in this rank's sorted order */
+        memcpy(row_offset, ro, (nr + 1) * 8);
+        if (nl) { memcpy(other, oth, nl * 4); memcpy(factor, fa, nl * 4); }
+    } else {
+        /* single GPU: permute rows back to original lumel order (row k of the device CSR is lumel sidx[k]) */
+        uint64_t *len = (uint64_t *)calloc(n + 1, 8);
+        for (uint64_t k = 0; k < n && k < nr; ++k) len[sidx[k]] = ro[k + 1] - ro[k];
+        uint64_t acc = 0;
+        for (uint64_t i = 0; i < n; ++i) { row_offset[i] = acc; acc += len[i]; }
+        row_offset[n] = acc;
+        for (uint64_t k = 0; k < n && k < nr; ++k) {
+            const uint64_t dst = row_offset[sidx[k]];
+            memcpy(other + dst, oth + ro[k], (ro[k + 1] - ro[k]) * 4);
+            memcpy(factor + dst, fa + ro[k], (ro[k + 1] - ro[k]) * 4);
+        }
+        free(len);
+    }
+    free(ro); free(oth); free(sidx); free(fa);
+    return rc;
 }

@@ -41,6 +41,10 @@ extern "C" int ltrgpu_create(ltrgpu_Ctx **out, int device)
     CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU_TRY(ctx, cudaEventCreate(&ctx->ev0));
     CU_TRY(ctx, cudaEventCreate(&ctx->ev1));
+    CU_TRY(ctx, cudaEventCreate(&ctx->ev_span0));
+    CU_TRY(ctx, cudaEventCreate(&ctx->ev_span1));
+    CU_TRY(ctx, cudaEventCreate(&ctx->ev_k0));
+    CU_TRY(ctx, cudaEventCreate(&ctx->ev_k1));
     if (dev_alloc(ctx, &ctx->d_counters, CNT_COUNT)) return 1;
     CU_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, CNT_COUNT * sizeof(unsigned long long), ctx->stream));
     return 0;
@@ -52,7 +56,7 @@ static void free_bake_state(ltrgpu_Ctx *ctx)
     dev_free(&ctx->d_lpos); dev_free(&ctx->d_lnrm); dev_free(&ctx->d_lrad); dev_free(&ctx->d_lrgb);
     dev_free(&ctx->d_lloc); dev_free(&ctx->d_linst); dev_free(&ctx->d_lnmap);
     dev_free(&ctx->d_fvis); dev_free(&ctx->d_active); dev_free(&ctx->d_active_count);
-    dev_free(&ctx->d_rad_rowoff); dev_free(&ctx->d_rad_other); dev_free(&ctx->d_rad_factor);
+    dev_free(&ctx->d_rad_rowoff); dev_free(&ctx->d_rad_other); dev_free(&ctx->d_rad_factor); dev_free(&ctx->d_rad_sidx);
     dev_free(&ctx->d_image); dev_free(&ctx->d_image_tmp); dev_free(&ctx->d_mask); dev_free(&ctx->d_mask_tmp);
     dev_free(&ctx->d_normals); dev_free(&ctx->d_out);
     ctx->n_lumels = 0; ctx->rad_rows = ctx->rad_links = 0;
@@ -73,6 +77,10 @@ extern "C" void ltrgpu_destroy(ltrgpu_Ctx *ctx)
     free(ctx->h_out_off); free(ctx->h_out_w); free(ctx->h_out_h);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_span0) cudaEventDestroy(ctx->ev_span0);
+    if (ctx->ev_span1) cudaEventDestroy(ctx->ev_span1);
+    if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
+    if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -83,6 +91,24 @@ extern "C" void *ltrgpu_stream(ltrgpu_Ctx *ctx) { return (void *)ctx->stream; }
 extern "C" int ltrgpu_sync(ltrgpu_Ctx *ctx)
 {
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int ltrgpu_span_begin(ltrgpu_Ctx *ctx)
+{
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_span0, ctx->stream));
+    return 0;
+}
+
+extern "C" int ltrgpu_span_end(ltrgpu_Ctx *ctx)
+{
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_span1, ctx->stream));
+    CU_TRY(ctx, cudaEventSynchronize(ctx->ev_span1));
+    float ms = 0;
+    CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_span0, ctx->ev_span1));
+    ctx->host_counters.ms_span = ms;
     return 0;
 }
 

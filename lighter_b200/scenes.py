@@ -323,3 +323,207 @@ NAMED = {
     "basic": scene_basic, "hugeoverlap": scene_hugeoverlap, "mesh1": scene_mesh1,
     "mesh2": scene_mesh2, "rad1": scene_rad1,
 }
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic scenes of the BASELINE.json configs 3-5: seeded tile generator
+# --------------------------------------------------------------------------------------------
+def _height(x, y):
+    return np.float32(0.25) * np.sin(np.float32(0.9) * x) * np.cos(np.float32(0.7) * y)
+
+
+def _grid_patch(origin, du, dv, nu, nv, normal_fn, uv_rect, pos_fn=None):
+    """(nu x nv) quads spanning origin + s*du + t*dv, s,t in [0,1]; CCW w.r.t. cross(du, dv).
+    uv_rect = (u0, v0, u1, v1) receives the patch.  Returns pos, nrm, uv, idx (local indices)."""
+    s, t = np.meshgrid(np.linspace(0, 1, nu + 1), np.linspace(0, 1, nv + 1), indexing="xy")
+    s, t = s.ravel(), t.ravel()
+    pos = origin[None, :] + s[:, None] * du[None, :] + t[:, None] * dv[None, :]
+    if pos_fn is not None:
+        pos = pos_fn(pos)
+    nrm = normal_fn(pos)
+    u0, v0, u1, v1 = uv_rect
+    uv = np.stack([u0 + s * (u1 - u0), v0 + t * (v1 - v0)], 1)
+    i, j = np.meshgrid(np.arange(nu), np.arange(nv), indexing="xy")
+    a = (j * (nu + 1) + i).ravel()
+    b, c, d = a + 1, a + nu + 2, a + nu + 1
+    idx = np.stack([a, b, c, c, d, a], 1).ravel()
+    return pos.astype(np.float32), nrm.astype(np.float32), uv.astype(np.float32), idx.astype(np.uint32)
+
+
+def _tile_part(rng, ox, oy, size, floor_n, ceil_n, height, ceiling, pillar, walls, pillar_q=6, wall_q=6, uv_rect=(0.0, 0.0, 1.0, 1.0),
+               world_coords=False):
+    """One tile: heightfield floor, optional ceiling, optional pillar, boundary walls.  Geometry is in
+    tile-local x,y (translated by the instance matrix) unless world_coords."""
+    g = 3.0 / 256.0
+    U0, V0, U1, V1 = uv_rect
+
+    def rect(a, b, c, d):            # sub-rectangle of this tile's atlas square
+        return (U0 + a * (U1 - U0), V0 + b * (V1 - V0), U0 + c * (U1 - U0), V0 + d * (V1 - V0))
+
+    lx, ly = (ox, oy) if world_coords else (0.0, 0.0)
+    chunks = []
+
+    def floor_pos(p):
+        p = p.copy()
+        wx, wy = p[:, 0] + (0.0 if world_coords else ox), p[:, 1] + (0.0 if world_coords else oy)
+        p[:, 2] = _height(wx.astype(np.float32), wy.astype(np.float32))
+        return p
+
+    def floor_nrm(p):
+        wx, wy = p[:, 0] + (0.0 if world_coords else ox), p[:, 1] + (0.0 if world_coords else oy)
+        dzdx = 0.25 * 0.9 * np.cos(0.9 * wx) * np.cos(0.7 * wy)
+        dzdy = -0.25 * 0.7 * np.sin(0.9 * wx) * np.sin(0.7 * wy)
+        n = np.stack([-dzdx, -dzdy, np.ones_like(wx)], 1)
+        return n / np.linalg.norm(n, axis=1, keepdims=True)
+
+    const = lambda v: (lambda p: np.tile(np.asarray(v, np.float64), (len(p), 1)))
+    chunks.append(_grid_patch(np.array([lx, ly, 0.0]), np.array([size, 0, 0.0]), np.array([0, size, 0.0]), floor_n, floor_n, floor_nrm,
+                              rect(g, g, 0.60, 0.60), floor_pos))
+    if ceiling:
+        chunks.append(_grid_patch(np.array([lx, ly + size, height]), np.array([size, 0, 0.0]), np.array([0, -size, 0.0]), ceil_n, ceil_n,
+                                  const((0, 0, -1)), rect(0.62 + g, g, 1 - g, 0.36)))
+    if pillar:
+        pw = rng.uniform(0.6, 1.6)
+        ph = rng.uniform(2.0, max(2.5, height - 0.5))
+        cx, cy = lx + size * rng.uniform(0.3, 0.7), ly + size * rng.uniform(0.3, 0.7)
+        x0, x1, y0, y1, z0, z1 = cx - pw / 2, cx + pw / 2, cy - pw / 2, cy + pw / 2, -0.3, ph
+        faces = [  # origin, du, dv, outward normal
+            (np.array([x0, y0, z0]), np.array([pw, 0, 0.0]), np.array([0, 0, z1 - z0]), (0, -1, 0)),
+            (np.array([x1, y0, z0]), np.array([0, pw, 0.0]), np.array([0, 0, z1 - z0]), (1, 0, 0)),
+            (np.array([x1, y1, z0]), np.array([-pw, 0, 0.0]), np.array([0, 0, z1 - z0]), (0, 1, 0)),
+            (np.array([x0, y1, z0]), np.array([0, -pw, 0.0]), np.array([0, 0, z1 - z0]), (-1, 0, 0)),
+            (np.array([x0, y0, z1]), np.array([pw, 0, 0.0]), np.array([0, pw, 0.0]), (0, 0, 1)),
+        ]
+        for k, (o, du, dv, nn) in enumerate(faces):
+            chunks.append(_grid_patch(o, du, dv, pillar_q, pillar_q, const(nn), rect(k * 0.19 + g, 0.64, (k + 1) * 0.19 - g, 0.80)))
+    wall_defs = [  # west, east, south, north: inward normals
+        (np.array([lx, ly + size, -0.3]), np.array([0, -size, 0.0]), (1, 0, 0)),
+        (np.array([lx + size, ly, -0.3]), np.array([0, size, 0.0]), (-1, 0, 0)),
+        (np.array([lx, ly, -0.3]), np.array([size, 0, 0.0]), (0, 1, 0)),
+        (np.array([lx + size, ly + size, -0.3]), np.array([-size, 0, 0.0]), (0, -1, 0)),
+    ]
+    for k, on in enumerate(walls):
+        if on:
+            o, du, nn = wall_defs[k]
+            chunks.append(_grid_patch(o, du, np.array([0, 0, height + 0.3]), wall_q, wall_q, const(nn), rect(k * 0.25 + g, 0.83, (k + 1) * 0.25 - g, 1 - g)))
+    pos, nrm, uv, idx, base = [], [], [], [], 0
+    for p, n, t, i in chunks:
+        pos.append(p); nrm.append(n); uv.append(t); idx.append(i + base); base += len(p)
+    pos, nrm, uv, idx = np.concatenate(pos), np.concatenate(nrm), np.concatenate(uv), np.concatenate(idx)
+    return Part(pos, nrm, uv.copy(), uv, idx, 1)
+
+
+def scene_synthetic(name: str, tiles: int, tile_size: float, target_tris: int, lm_size: int, ceiling: bool, height: float = 6.0,
+                    merge: bool = False, seed: int = 20261017, pillar_fraction: float = 0.7) -> Scene:
+    """tiles x tiles instances (or one merged instance), each with a forced lm_size^2 lightmap
+    (merge: one (tiles*lm_size)^2 lightmap).  Floor resolution is tuned so the total triangle count
+    lands within 1 % of target_tris."""
+    rng = np.random.Generator(np.random.MT19937(seed))
+    nt = tiles * tiles
+    pillars = rng.uniform(0, 1, nt) < pillar_fraction
+    ceil_n, pq, wq = 8, 6, 6
+    fixed = 0
+    for k in range(nt):
+        i, j = k % tiles, k // tiles
+        fixed += (2 * ceil_n * ceil_n if ceiling else 0) + (10 * pq * pq if pillars[k] else 0)
+        fixed += 2 * wq * wq * ((i == 0) + (i == tiles - 1) + (j == 0) + (j == tiles - 1))
+    per_tile_floor = max(2.0, (target_tris - fixed) / nt)
+    m0 = max(1, int(np.floor(np.sqrt(per_tile_floor / 2))))
+    floor_n = np.full(nt, m0)
+    total = fixed + 2 * m0 * m0 * nt
+    k = 0
+    while total + (2 * (m0 + 1) ** 2 - 2 * m0 * m0) <= target_tris * 1.005 and k < nt:      # bump tiles one by one
+        floor_n[k] = m0 + 1
+        total += 2 * (m0 + 1) ** 2 - 2 * m0 * m0
+        k += 1
+    s = Scene(name)
+    s.cfg["size_fn_kind"] = 1
+    s.cfg["max_lightmap_size"] = 8192
+    merged = []
+    for k in range(nt):
+        i, j = k % tiles, k // tiles
+        ox, oy = i * tile_size, j * tile_size
+        walls = (i == 0, i == tiles - 1, j == 0, j == tiles - 1)
+        uv_rect = (i / tiles, j / tiles, (i + 1) / tiles, (j + 1) / tiles) if merge else (0.0, 0.0, 1.0, 1.0)
+        part = _tile_part(rng, ox, oy, tile_size, int(floor_n[k]), ceil_n, height, ceiling, bool(pillars[k]), walls, pq, wq, uv_rect, world_coords=merge)
+        if merge:
+            merged.append(part)
+            continue
+        s.meshes.append(Mesh(f"tile{k}", [part]))
+        m = IDENTITY.copy()
+        m[3, 0], m[3, 1] = ox, oy
+        s.instances.append(Instance(k, m, 1.0, 1, f"t{k}", (lm_size, lm_size)))
+    if merge:
+        s.meshes.append(Mesh("merged", merged))              # one part per tile
+        s.instances.append(Instance(0, IDENTITY.copy(), 1.0, 1, "t0", (lm_size * tiles, lm_size * tiles)))
+    return s
+
+
+def _grid_lights(rng, nx, ny, extent, zlo, zhi, rng_range, n_spot_every=2, ssc=16) -> list:
+    out = []
+    for k in range(nx * ny):
+        i, j = k % nx, k // nx
+        x = (i + 0.5 + rng.uniform(-0.3, 0.3)) * extent / nx
+        y = (j + 0.5 + rng.uniform(-0.3, 0.3)) * extent / ny
+        z = rng.uniform(zlo, zhi)
+        col = tuple(float(c) for c in rng.uniform(0.3, 1.0, 3))
+        rad = float(rng.uniform(0.1, 0.3))
+        if k % n_spot_every == 1:
+            tilt = np.radians(rng.uniform(-15, 15, 2))
+            d = np.array([np.sin(tilt[0]), np.sin(tilt[1]), -1.0])
+            d /= np.linalg.norm(d)
+            out.append(Light(LT_SPOT, (x, y, z), tuple(float(c) for c in d), (1.0, 0.0, 0.0), col, rng_range, 1.0, rad, ssc, 45.0, 25.0, 0.5))
+        else:
+            out.append(Light(LT_POINT, (x, y, z), color_rgb=col, range=rng_range, power=1.0, light_radius=rad, shadow_sample_count=ssc))
+    return out
+
+
+def scene_config3(tiles: int = 8, lm_size: int = 256, target_tris: int = 250_000, merge: bool = False, n_lights: tuple = (4, 8)) -> Scene:
+    """BASELINE config 3: closed 40x40x6 interior, 250k tris, 2048^2 texels (64 x 256^2 or merged), 32 lights."""
+    s = scene_synthetic("config3" + ("A" if merge else "B"), tiles, 40.0 / 8, target_tris, lm_size, ceiling=True, merge=merge)
+    rng = np.random.Generator(np.random.MT19937(20261018))
+    s.lights = _grid_lights(rng, n_lights[0], n_lights[1], tiles * 5.0, 4.0, 5.5, 14.0)
+    s.cfg.update(ao_distance=0.0, bounce_count=0, blur_size=0.5)
+    return s
+
+
+def scene_config4(tiles: int = 16, lm_size: int = 256, target_tris: int = 1_000_000, bounces: int = 3, merge: bool = False) -> Scene:
+    """BASELINE config 4: open-air 400x400 terrain with pillars, 1M tris, 4096^2 texels (256 x 256^2),
+    8 local lights + 1 directional (range 60), AO 17 samples, 3 radiosity bounces."""
+    s = scene_synthetic("config4", tiles, 25.0, target_tris, lm_size, ceiling=False, height=6.0, merge=merge)
+    rng = np.random.Generator(np.random.MT19937(20261019))
+    gx, gy = (2, 4) if tiles >= 8 else (1, 2)
+    s.lights = _grid_lights(rng, gx, gy, tiles * 25.0, 8.0, 12.0, 60.0)
+    d = np.array([0.4, 0.3, 0.85]); d /= np.linalg.norm(d)
+    s.lights.append(Light(LT_DIRECT, (0.0, 0.0, 0.0), tuple(float(c) for c in d), color_rgb=(0.6, 0.55, 0.5), range=60.0, power=1.0,
+                          light_radius=0.2, shadow_sample_count=16))
+    s.cfg.update(ao_distance=2.0, ao_num_samples=17, bounce_count=bounces, blur_size=0.5)
+    return s
+
+
+def scene_config5(n_lights: int = 16, samples: int = 16, tiles: int = 8, lm_size: int = 128, target_tris: int = 500_000) -> Scene:
+    """BASELINE config 5 (sweep member): one merged 500k-tri instance, 1024^2 lightmap, L lights."""
+    s = scene_synthetic("config5", tiles, 5.0, target_tris, lm_size, ceiling=True, merge=True)
+    rng = np.random.Generator(np.random.MT19937(20261020))
+    nx = int(np.ceil(np.sqrt(n_lights)))
+    ny = (n_lights + nx - 1) // nx
+    s.lights = _grid_lights(rng, nx, ny, tiles * 5.0, 4.0, 5.5, 14.0, ssc=samples)[:n_lights]
+    s.cfg.update(ao_distance=0.0, bounce_count=0, blur_size=0.5)
+    return s
+
+
+WORKLOADS = {
+    # name: (builder, kwargs) -- full-size GPU workloads and the scaled-down siblings the CPU reference can finish
+    "config3": (scene_config3, {}),
+    "config3_sibling": (scene_config3, dict(tiles=2, lm_size=64, target_tris=250_000 // 16, n_lights=(2, 2))),
+    "config4": (scene_config4, {}),
+    "config4_sibling": (scene_config4, dict(tiles=2, lm_size=64, target_tris=1_000_000 // 64)),
+    "config4_quarter": (scene_config4, dict(tiles=8, lm_size=256, target_tris=250_000)),
+    "mesh1": (scene_mesh1, {}),
+    "mesh2": (scene_mesh2, {}),
+}
+
+
+def workload(name: str) -> Scene:
+    fn, kw = WORKLOADS[name]
+    return fn(**kw)

@@ -31,6 +31,35 @@
 #include <unistd.h>
 #include <algorithm>
 
+#ifdef REF_COUNT_CALLS
+/* Counting build only (oracle/_ref/ref_bake_count, never the timed binary): the reference's
+ * lighter.cpp is compiled with -finstrument-functions and this hook counts entries into the five
+ * scene-level query functions (lighter.cpp:138,183,190,242,280), giving the reference's own ray
+ * counts for a workload without touching its source.  Run with --threads 1. */
+extern "C" void __cyg_profile_func_enter(void *fn, void *site) __attribute__((no_instrument_function));
+extern "C" void __cyg_profile_func_exit(void *fn, void *site) __attribute__((no_instrument_function));
+static void *g_count_fn[5];
+static unsigned long long g_count[5];
+extern "C" void __cyg_profile_func_enter(void *fn, void *)
+{
+    for (int k = 0; k < 5; ++k) if (fn == g_count_fn[k]) { ++g_count[k]; return; }
+}
+extern "C" void __cyg_profile_func_exit(void *, void *) {}
+static void __attribute__((no_instrument_function)) count_setup()
+{
+    typedef bool (*f_vis)(ltr_Scene *, const Vec3 &, const Vec3 &);
+    typedef float (*f_dist)(ltr_Scene *, const Vec3 &);
+    typedef float (*f_march)(ltr_Scene *, const Vec3 &, const Vec3 &, float);
+    typedef float (*f_dt)(ltr_Scene *, const Vec3 &, const Vec3 &, Vec3 *);
+    typedef float (*f_bbt)(ltr_Scene *, const Vec3 &, const Vec3 &);
+    g_count_fn[0] = (void *)(f_march)(&ltr_Scene::CalcInvShadowFactor);
+    g_count_fn[1] = (void *)(f_dist)(&ltr_Scene::Distance);
+    g_count_fn[2] = (void *)(f_vis)(&ltr_Scene::VisibilityTest);
+    g_count_fn[3] = (void *)(f_bbt)(&ltr_Scene::DistanceTestBBT);
+    g_count_fn[4] = (void *)(f_dt)(&ltr_Scene::DistanceTest);
+}
+#endif
+
 static double now_s()
 {
     struct timespec ts;
@@ -58,6 +87,9 @@ int main(int argc, char **argv)
 
     sio::SceneFile S;
     if (!sio::load(argv[1], S)) return 1;
+#ifdef REF_COUNT_CALLS
+    count_setup();
+#endif
 
     std::vector<double> walls;
     ltr_Scene *scene = NULL;
@@ -132,5 +164,9 @@ int main(int argc, char **argv)
     }
     fclose(f);
     ltr_DestroyScene(scene);
+#ifdef REF_COUNT_CALLS
+    printf("{\"marches\": %llu, \"distance_queries\": %llu, \"visibility_segments\": %llu, \"ao_segments\": %llu, \"correction_rays\": %llu}\n",
+           g_count[0], g_count[1], g_count[2], g_count[3], g_count[4]);
+#endif
     return 0;
 }

@@ -1,0 +1,230 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against (a) the committed golden
+fixtures generated from the unmodified reference, (b) the plain-C oracle on fresh seeded inputs, and
+(c) the reference itself run live on the host when oracle/_ref travelled to the box.
+
+Bars (BASELINE.json north_star): integer/index work bit-exact (lumel counts, texel locations, link
+sets, hit/miss); positions and primitive results bit-exact; final 8-bit texels MAE <= 1/255 and
+<= 2/255 on >= 99.5 % of texels (we measure 0 on every scenario; libm-class functions may differ by
+an ulp in the float image)."""
+import numpy as np
+import pytest
+
+from conftest import bits_equal, scene_tris
+from lighter_b200 import api, parity, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- primitives ------------------------------------------------------------------------------------
+def test_point_triangle_distance_bit_exact(prims, oracle):
+    assert bits_equal(api.test_point_tri_distance(prims["ptd_pts"], prims["ptd_tris"]), prims["ptd_out"])
+    rng = np.random.default_rng(11)
+    n = 20000
+    tris = (rng.uniform(-9, 9, (n, 1, 3)) + rng.uniform(-2, 2, (n, 3, 3))).astype(np.float32).reshape(n, 9)
+    pts = rng.uniform(-10, 10, (n, 3)).astype(np.float32)
+    assert bits_equal(api.test_point_tri_distance(pts, tris), oracle.point_tri_distance(pts, tris))
+
+
+def test_segment_triangle_bit_exact(prims, oracle):
+    assert bits_equal(api.test_seg_tri(prims["seg_a"], prims["seg_b"], prims["seg_tris"]), prims["seg_out"])
+    rng = np.random.default_rng(12)
+    n = 20000
+    tris = (rng.uniform(-3, 3, (n, 1, 3)) + rng.uniform(-2, 2, (n, 3, 3))).astype(np.float32).reshape(n, 9)
+    a, b = rng.uniform(-5, 5, (n, 3)).astype(np.float32), rng.uniform(-5, 5, (n, 3)).astype(np.float32)
+    assert bits_equal(api.test_seg_tri(a, b, tris), oracle.seg_tri(a, b, tris))
+
+
+def test_spiral_directions(prims):
+    got = api.test_spiral_dirs(prims["spiral_nrm"], prims["spiral_randoff"], 17)
+    want = prims["spiral_out17"]
+    # sin/cos of the rotation angle come from the device's double-precision libm rounded to float:
+    # equal to glibc's sinf/cosf except for rare last-bit differences
+    assert np.abs(got - want).max() <= 2.4e-7
+    assert (got.view(np.uint32) == want.view(np.uint32)).mean() > 0.99
+
+
+def test_bvh_queries_equal_reference_tree(prims):
+    """distance / any-hit / closest-hit on the flat BVH vs the reference's TriTree (golden)."""
+    q = api.test_scene_queries(prims["soup"], prims["q_a"], prims["q_b"])
+    assert bits_equal(q["dist"], prims["q_dist"])
+    assert np.array_equal(q["anyhit"], prims["q_anyhit"])
+    assert bits_equal(q["closest"], prims["q_closest"])
+    hit = prims["q_closest"] < 2.0
+    assert np.array_equal(q["closest_tri"][hit], prims["q_closest_tri"][hit])
+    assert (q["closest_tri"][~hit] == -1).all()
+
+
+@pytest.mark.parametrize("ntris,leaf", [(1, 4), (2, 4), (37, 1), (2000, 2), (20000, 4), (20000, 7)])
+def test_bvh_queries_equal_brute_force(oracle, ntris, leaf, monkeypatch):
+    monkeypatch.setenv("LTR_BVH_LEAF", str(leaf))
+    rng = np.random.default_rng(100 + ntris + leaf)
+    tris = (rng.uniform(-6, 6, (ntris, 1, 3)) + rng.uniform(-0.5, 0.5, (ntris, 3, 3))).astype(np.float32).reshape(ntris, 9)
+    n = 600
+    a = rng.uniform(-7, 7, (n, 3)).astype(np.float32)
+    b = (a + rng.normal(0, 2.0, (n, 3))).astype(np.float32)
+    q = api.test_scene_queries(tris, a, b)
+    assert bits_equal(q["dist"], oracle.scene_distance(tris, a))
+    assert np.array_equal(q["anyhit"], oracle.anyhit_raw(tris, a, b))
+    c, tid = oracle.closest_raw(tris, a, b)
+    assert bits_equal(q["closest"], c) and np.array_equal(q["closest_tri"], tid)
+
+
+def test_empty_scene_queries():
+    a = np.zeros((4, 3), np.float32); b = np.ones((4, 3), np.float32)
+    q = api.test_scene_queries(np.zeros((0, 9), np.float32), a, b)
+    assert (q["dist"] == 2.0).all() and (q["anyhit"] == 0).all() and (q["closest"] == 2.0).all() and (q["closest_tri"] == -1).all()
+
+
+def test_shadow_march_equals_oracle(oracle):
+    sc = scenes.scene_mesh1()
+    tris = scene_tris(sc)
+    rng = np.random.default_rng(21)
+    n = 400
+    frm = rng.uniform([-4, -8, -4], [4, 8, 4], (n, 3)).astype(np.float32)
+    to = np.tile(np.array([[2.18, 4.04, 1.40]], np.float32), (n, 1))
+    to[::3] = frm[::3] + np.array([577.35, 577.35, 577.35], np.float32)        # a directional-light style long march
+    k = rng.choice(np.array([0.1, 0.2, 0.5], np.float32), n)
+    got, steps = api.test_march(tris, frm, to, k)
+    want, wsteps = oracle.march(tris, frm, to, k)
+    assert bits_equal(got, want) and np.array_equal(steps, wsteps)
+    assert (got == 0).any() and (got == 1).any() and ((got > 0) & (got < 1)).any()
+
+
+# ---- full bakes against the golden fixtures ----------------------------------------------------------
+@pytest.mark.parametrize("name", ["basic", "hugeoverlap", "mesh1", "rad1"])
+def test_bake_matches_reference_golden(name, bakes):
+    sc = scenes.NAMED[name]()
+    out = api.bake(sc, debug=True)
+    assert [i["n"] for i in out["instances"]] == bakes[f"{name}_lumel_counts"].tolist()
+    assert out["stats"]["kernel_launches"] > 10
+    for lm in out["lightmaps"]:
+        p = parity.texel_parity(lm["rgb"], bakes[f"{name}_lm{lm['uid']}_rgb"])
+        assert p["mae"] == 0 and p["within2"] == 1.0 and p["float_max_abs"] < 1e-6, (name, lm["uid"], p)
+    if name in ("basic", "mesh1", "rad1"):
+        for i, inst in enumerate(out["instances"]):
+            if not inst["n"]:
+                continue
+            assert np.array_equal(inst["loc"], bakes[f"{name}_inst{i}_loc"])
+            assert bits_equal(inst["pos"], bakes[f"{name}_inst{i}_pos"]), "lumel positions (offset + overlap correction)"
+            assert bits_equal(inst["nrm"], bakes[f"{name}_inst{i}_nrm"])
+            assert bits_equal(inst["radinfo"], bakes[f"{name}_inst{i}_radinfo"])
+            assert np.abs(inst["rgb"] - bakes[f"{name}_inst{i}_rgb"]).max() < 1e-6
+    if name in ("basic", "hugeoverlap"):                      # no libm-class calls beyond pow(x,1): bit-exact images
+        for lm in out["lightmaps"]:
+            assert bits_equal(lm["rgb"], bakes[f"{name}_lm{lm['uid']}_rgb"])
+    assert out["stages"][-1] == "exporting lightmaps" and "generating samples" in out["stages"]
+
+
+def test_mesh2_two_mesh_scene_with_normal_map(bakes):
+    """BASELINE config 2: inter-mesh shadowing, 4 lights incl. a directional one, AO, normal/focus map."""
+    out = api.bake(scenes.scene_mesh2())
+    assert len(out["lightmaps"]) == 2
+    for lm in out["lightmaps"]:
+        q, nq = bakes[f"mesh2_lm{lm['uid']}_q8"].astype(np.int32), bakes[f"mesh2_lm{lm['uid']}_nq8"].astype(np.int32)
+        d = np.abs(parity.quantize8(lm["rgb"]) - q)
+        assert d.mean() <= 1.0 and (d.max(axis=2) <= 2).mean() >= 0.995 and d.max() <= 1
+        dn = np.abs(parity.quantize8(lm["normals"] * 0.5 + 0.5) - nq)
+        assert dn.mean() <= 0.01 and (dn.max(axis=2) <= 2).mean() >= 0.995
+    st = out["stats"]
+    assert st["n_lumels_total"] == 84737 and st["n_ao_segments"] == 84737 * 17
+
+
+def test_radiosity_links_equal_reference(bakes):
+    """rad1: the link set (pairs kept only when the segment is blocked) and factors, both directions."""
+    out = api.bake(scenes.scene_rad1(), debug=True)
+    lk = out["links"]
+    li, lj, lf = bakes["rad1_link_i"], bakes["rad1_link_j"], bakes["rad1_link_f"]
+    rows = np.repeat(np.arange(lk["rows"], dtype=np.uint32), np.diff(lk["row_offset"]).astype(np.int64))
+    assert len(rows) == 2 * len(li) == 62684
+    fwd = rows < lk["other"]
+    assert np.array_equal(rows[fwd], li) and np.array_equal(lk["other"][fwd], lj) and bits_equal(lk["factor"][fwd], lf)
+    # rows are complete and sorted: the reverse direction is the transpose
+    key = lambda a, b: a.astype(np.uint64) << np.uint64(32) | b.astype(np.uint64)
+    assert np.array_equal(np.sort(key(lk["other"][~fwd], rows[~fwd])), np.sort(key(li, lj)))
+    assert (np.diff(key(rows, lk["other"]).astype(np.int64)) > 0).all()
+    st = out["stats"]
+    assert st["n_rad_links"] == 62684 and st["n_rad_segments"] == 288042           # 288 042 segments, one per pair i<j
+
+
+def test_ray_counts_equal_reference_instrumented_counts():
+    """SURVEY 3.3 work counts of the reference on mesh1 (instrumented copy): 19 735 marches,
+    422 636 distance queries, 161 466 AO segments, 9 498 correction rays."""
+    st = api.bake(scenes.scene_mesh1())["stats"]
+    assert (st["n_marches"], st["n_distance_queries"], st["n_ao_segments"], st["n_correction_rays"]) == (19735, 422636, 161466, 9498)
+
+
+# ---- live against the reference on this host (when oracle/_ref travelled) ----------------------------
+def _variant(name):
+    sc = scenes.NAMED[name.split("+")[0]]()
+    if "+ds2x" in name:
+        sc.cfg["ds2x"] = 1
+    if "+blur" in name:
+        sc.cfg["blur_size"] = 2.2
+    if "+aoneg" in name:
+        sc.cfg.update(ao_effect=-0.6, ao_color=(0.1, 0.05, 0.2), ao_falloff=2.0)
+    if "+ambient" in name:
+        sc.cfg["ambient_color"] = (0.05, 0.1, 0.15)
+    if "+probes" in name:
+        sc.probes = [(1, (0.5, 0.5, 1.0), (0.0, 0.0, 1.0)), (2, (-1.0, 2.0, 0.5), (0.0, 1.0, 1.0)), (3, (0.0, 0.0, -3.0), (0.0, 0.0, -2.0))]
+    if "+power0" in name:
+        for lt in sc.lights:
+            lt.power = 0.0
+    if "+noshadowinst" in name:
+        sc.instances[0].shadow = 0
+    return sc
+
+
+@pytest.mark.parametrize("name", ["mesh1+ds2x+blur", "mesh1+aoneg+ambient+probes", "rad1+probes+ambient", "basic+power0",
+                                  "mesh2+noshadowinst", "basic+probes"])
+def test_config_variants_against_live_reference(name):
+    if not parity.have_reference():
+        pytest.skip("oracle/_ref not on this box")
+    sc = _variant(name)
+    ref = parity.run_reference(sc, threads=1, internals=True)
+    out = api.bake(sc, debug=True)
+    assert [i["n"] for i in out["instances"]] == [i["n"] for i in ref["instances"]]
+    assert len(out["lightmaps"]) == len(ref["lightmaps"])
+    for a, b in zip(out["lightmaps"], ref["lightmaps"]):
+        assert (a["uid"], a["width"], a["height"]) == (b["uid"], b["width"], b["height"])
+        p = parity.texel_parity(a["rgb"], b["rgb"])
+        assert parity.meets_bar(p) and p["max"] <= 1, (name, p)
+    for a, b in zip(out["instances"], ref["instances"]):
+        if a["n"]:
+            assert bits_equal(a["pos"], b["pos"])
+    if len(ref["probes"]):
+        assert np.abs(out["probes"] - ref["probes"]).max() < 1e-6
+
+
+def test_degenerate_inputs():
+    """Empty scene, scene without lights, instance without shadow-casting parts, zero-area triangles."""
+    sc = scenes.Scene("empty")
+    out = api.bake(sc)
+    assert out["lightmaps"] == [] and out["stats"]["n_lumels_total"] == 0
+    sc = scenes.scene_basic(); sc.lights = []
+    out = api.bake(sc)
+    assert len(out["lightmaps"]) == 3 and all((lm["rgb"] == 0).all() for lm in out["lightmaps"])
+    sc = scenes.scene_basic()
+    sc.meshes[0].parts[0].shadow = 0                                   # nothing occludes: shadow factor 1 everywhere
+    out = api.bake(sc, debug=True)
+    assert out["stats"]["n_triangles"] == 0 and out["stats"]["n_marches"] == 0   # instances without a tree are not lit by point lights
+    sc = scenes.scene_basic()
+    p = sc.meshes[0].parts[0]
+    p.idx = np.concatenate([p.idx, np.array([0, 0, 1, 2, 2, 2], np.uint32)])   # two degenerate triangles
+    out2 = api.bake(sc)
+    base = api.bake(scenes.scene_basic())
+    for a, b in zip(out2["lightmaps"], base["lightmaps"]):
+        assert bits_equal(a["rgb"], b["rgb"])
+
+
+def test_rebake_on_resident_scene_is_idempotent():
+    """ltrx_Prepare / ltrx_BakeResident (the bench path): two bakes of the same resident scene agree."""
+    sc = scenes.scene_rad1(); sc.cfg["ao_distance"] = 0.0           # no rand() consumption -> deterministic
+    with api.BakeHandle(sc) as b:
+        b.prepare()
+        b.bake_resident(); b.finish()
+        first = b.outputs()["lightmaps"][0]["rgb"]
+        b.bake_resident(); b.finish()
+        second = b.outputs()["lightmaps"][0]["rgb"]
+    assert bits_equal(first, second)
+    ref = api.bake(sc)["lightmaps"][0]["rgb"]
+    assert bits_equal(first, ref)

@@ -1,0 +1,112 @@
+"""CPU tests of the host-side logic: shard partitioning (single process and a world_size-2 gloo
+job), scene-file round trip through the C++ reader, the reference-order tree builder against the
+reference's own tree dump, and the flat BVH builder's structural invariants."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from lighter_b200 import api, parity, scenes
+
+
+def test_shard_ranges_tile_the_lumel_array():
+    for n in (0, 1, 7, 8, 9, 1000, 16_777_216, 12_345_677):
+        for world in (1, 2, 3, 4, 8):
+            edges = [api.shard_range(n, r, world) for r in range(world)]
+            chunk = (n + world - 1) // world
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            for r, (b, e) in enumerate(edges):
+                assert b == min(r * chunk, n) and e == min(b + chunk, n)       # equal-size chunks: in-place all-gather layout
+                if r:
+                    assert b == edges[r - 1][1]
+
+
+def test_world_size_2_gloo_sharding(tmp_path):
+    """Two CPU processes over gloo agree on a lumel count, take their ltrx_ShardRange slices, and
+    all-gather padded per-rank payloads the way the radiance exchange lays them out."""
+    script = tmp_path / "w2.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {ROOT!r})
+        import numpy as np, torch, torch.distributed as dist
+        from lighter_b200 import api
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        n = 1001                                   # deliberately not divisible by the world size
+        t = torch.tensor([n if rank == 0 else -1])
+        dist.broadcast(t, 0)
+        n = int(t.item())
+        b, e = api.shard_range(n, rank, world)
+        chunk = (n + world - 1) // world
+        payload = torch.zeros(chunk, dtype=torch.float32)
+        payload[: e - b] = torch.arange(b, e, dtype=torch.float32)       # "radiance" of my lumels
+        gathered = [torch.zeros(chunk) for _ in range(world)]
+        dist.all_gather(gathered, payload)
+        full = torch.cat(gathered)[:n]
+        assert torch.equal(full, torch.arange(n, dtype=torch.float32)), "gathered lumel array is not contiguous"
+        # a 128-byte id travels from rank 0 to everyone, as the NCCL unique id does
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            ident = torch.arange(128, dtype=torch.uint8)
+        dist.broadcast(ident, 0)
+        assert ident[127].item() == 127
+        print("rank", rank, "ok", b, e)
+        dist.destroy_process_group()
+    """))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29611", str(script)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "rank 0 ok 0 501" in r.stdout and "rank 1 ok 501 1001" in r.stdout
+
+
+def test_scene_file_roundtrip_through_reference_driver(tmp_path):
+    """scenes.Scene.write -> oracle/scene_io.h reader -> reference bake: the basic scenario must give
+    the reference's lightmap sizes 8, 1, 16 and three lightmaps with uids 1..3."""
+    if not parity.have_reference():
+        pytest.skip("oracle/_ref not built")
+    out = parity.run_reference(scenes.scene_basic(), threads=1)
+    assert [(lm["uid"], lm["width"], lm["height"]) for lm in out["lightmaps"]] == [(1, 8, 8), (2, 1, 1), (3, 16, 16)]
+    assert [i["n"] for i in out["instances"]] == [0, 64, 1, 196]
+
+
+def test_mesh_import_counts():
+    assert [len(scenes.load_mesh(n).idx) // 3 for n in ("test-mesh", "test-set2-mesh1", "test-set2-mesh2")] == [214, 246, 2048]
+    sc = scenes.scene_mesh2()
+    assert sc.triangle_count() == 246 + 2048
+
+
+def test_reference_order_tree_equals_reference_dump(refprims):
+    import ctypes as C
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 4, 5, 33, 700, 6000):
+        tris = (rng.uniform(-5, 5, (n, 1, 3)) + rng.uniform(-0.6, 0.6, (n, 3, 3))).astype(np.float32).reshape(n, 9)
+        if n >= 33:                                   # big triangles that must stay in inner nodes
+            tris[::11] = (tris[::11].reshape(-1, 3, 3) * np.float32(6)).reshape(-1, 9)
+        nodes, items = api.test_reftree(tris)
+        h = refprims.L.refp_tritree_create(tris.ctypes.data_as(C.POINTER(C.c_float)), n)
+        assert refprims.L.refp_tritree_tri_count(h) == n
+        rn = np.zeros((refprims.L.refp_tritree_node_count(h), 8), np.uint32)
+        ri = np.zeros(max(refprims.L.refp_tritree_item_count(h), 1), np.int32)
+        refprims.L.refp_tritree_dump(h, rn.ctypes.data, ri.ctypes.data)
+        refprims.L.refp_tritree_destroy(h)
+        assert np.array_equal(rn, nodes), n
+        assert np.array_equal(ri[:len(items)], items), n
+
+
+def test_flat_bvh_invariants():
+    rng = np.random.default_rng(5)
+    for n, leaf in ((0, 4), (1, 4), (2, 1), (100, 2), (5000, 4), (5000, 7)):
+        tris = (rng.uniform(-5, 5, (n, 1, 3)) + rng.uniform(-0.3, 0.3, (n, 3, 3))).astype(np.float32).reshape(n, 9)
+        b = api.test_bvh(tris, leaf)
+        assert b["ok"], (n, leaf)
+        assert sorted(b["order"].tolist()) == list(range(n))
+        if n:
+            assert np.allclose(b["bounds"][:3], tris.reshape(-1, 3).min(0)) and np.allclose(b["bounds"][3:], tris.reshape(-1, 3).max(0))
+    # 4000 coincident triangles cannot be separated spatially: the builder must still terminate with bounded depth
+    tris = np.tile(np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32), (4000, 1))
+    b = api.test_bvh(tris, 4)
+    assert b["ok"] and b["depth"] <= 20
