@@ -92,6 +92,7 @@ int  ltrgpu_create(ltrgpu_Ctx **out, int device);
 void ltrgpu_destroy(ltrgpu_Ctx *ctx);
 const char *ltrgpu_last_error(ltrgpu_Ctx *ctx);
 void *ltrgpu_stream(ltrgpu_Ctx *ctx);
+void ltrgpu_release_memory(void);           /* return the caching allocator's idle device blocks to the driver */
 
 int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *desc);
 

@@ -113,6 +113,6 @@ extern "C" int ltrgpu_ambient_occlusion(ltrgpu_Ctx *ctx, const float *randoff_ho
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->host_counters.ms_ao += ms;
-    cudaFree(d_rand); cudaFree(d_hits);
+    lb_free(d_rand); lb_free(d_hits);
     return 0;
 }

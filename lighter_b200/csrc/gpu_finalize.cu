@@ -265,7 +265,7 @@ extern "C" int ltrgpu_finalize(ltrgpu_Ctx *ctx)
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->host_counters.ms_finalize += ms;
-    cudaFree(d_off); cudaFree(d_w); cudaFree(d_h); cudaFree(d_ooff); cudaFree(d_ow); cudaFree(d_oh);
+    lb_free(d_off); lb_free(d_w); lb_free(d_h); lb_free(d_ooff); lb_free(d_ow); lb_free(d_oh);
     return 0;
 }
 
@@ -311,6 +311,6 @@ extern "C" int ltrgpu_download_probe_colors(ltrgpu_Ctx *ctx, float *rgb3)
     CU_TRY(ctx, cudaMemcpyAsync(rgb3, d, (size_t)ctx->n_probes * 12, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->host_counters.d2h_bytes += (size_t)ctx->n_probes * 12;
-    cudaFree(d);
+    lb_free(d);
     return 0;
 }

@@ -108,11 +108,19 @@ enum { CNT_MARCHES = 0, CNT_DIST_QUERIES, CNT_AO_SEGMENTS, CNT_CORR_RAYS, CNT_RA
         CU_TRY(ctx, cudaGetLastError());                                                           \
     } while (0)
 
+/* Caching device allocator (gpu_scene.cu): a bake allocates and drops dozens of large buffers; going
+ * to cudaMalloc/cudaFree each time costs tens of milliseconds and a device-wide sync per call, so
+ * freed blocks are kept per device and reused by size class.  Trimmed by ltrgpu_destroy. */
+cudaError_t lb_malloc(void **p, size_t bytes);
+template <class T> static inline cudaError_t lb_malloc(T **p, size_t bytes) { return lb_malloc((void **)p, bytes); }
+void lb_free(void *p);
+void lb_trim(void);
+
 template <class T> static inline int dev_alloc(ltrgpu_Ctx *ctx, T **p, size_t count)
 {
-    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (*p) { lb_free(*p); *p = nullptr; }
     if (count == 0) count = 1;
-    CU_TRY(ctx, cudaMalloc((void **)p, count * sizeof(T)));
+    CU_TRY(ctx, lb_malloc((void **)p, count * sizeof(T)));
     return 0;
 }
 template <class T> static inline int dev_upload(ltrgpu_Ctx *ctx, T **p, const void *src, size_t count)
@@ -124,7 +132,7 @@ template <class T> static inline int dev_upload(ltrgpu_Ctx *ctx, T **p, const vo
     }
     return 0;
 }
-template <class T> static inline void dev_free(T **p) { if (*p) { cudaFree(*p); *p = nullptr; } }
+template <class T> static inline void dev_free(T **p) { if (*p) { lb_free(*p); *p = nullptr; } }
 
 static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 

@@ -464,7 +464,7 @@ extern "C" int ltrgpu_generate_lumels(ltrgpu_Ctx *ctx, uint64_t *inst_lumel_off)
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->host_counters.ms_samples += ms;
-    cudaFree(d_block_sums); cudaFree(d_total); cudaFree(d_off);
+    lb_free(d_block_sums); lb_free(d_total); lb_free(d_off);
     ctx->sh_begin = 0; ctx->sh_end = n; ctx->rank = 0; ctx->world = 1;
     return 0;
 }

@@ -167,19 +167,34 @@ rad_candidates_kernel(const float4 *__restrict__ spos, const float4 *__restrict_
     const uint32_t r = rt * RAD_TILE + threadIdx.x;
     const V3 Pr = ld3(spos[r]), Nr = ld3(snrm[r]);
     const TileBounds R = tb[rt];
+    __shared__ uint32_t tile_list[RAD_TILE];
+    __shared__ unsigned tile_cnt;
     unsigned tested = 0;
     if (threadIdx.x == 0) q_count = 0;
-    __syncthreads();
-    for (uint32_t ct = 0; ct < n_tiles; ++ct) {
-        const bool mine = ct >= my_t0 && ct < my_t1;
-        if (mine && ct < rt) continue;                                   /* CTA-uniform: pair seen from the other tile */
-        const TileBounds C = tb[ct];
-        if (!tile_pair_may_link(R, C)) continue;                          /* CTA-uniform */
+    for (uint32_t base = 0; base < n_tiles; base += RAD_TILE) {
+      /* cooperative culling: each thread tests ONE column tile of this chunk, survivors are compacted */
+      __syncthreads();
+      if (threadIdx.x == 0) tile_cnt = 0;
+      __syncthreads();
+      {
+        const uint32_t c = base + threadIdx.x;
+        bool ok = c < n_tiles;
+        if (ok) {
+            const bool mine = c >= my_t0 && c < my_t1;
+            ok = !(mine && c < rt) && tile_pair_may_link(R, tb[c]);       /* mine && c<rt: pair seen from the other tile */
+        }
+        if (ok) tile_list[atomicAdd(&tile_cnt, 1u)] = c;
+      }
+      __syncthreads();
+      const unsigned n_list = tile_cnt;
+      for (unsigned li = 0; li < n_list; ++li) {
+        const uint32_t ct = tile_list[li];
         __syncthreads();
         const uint32_t cj = ct * RAD_TILE + threadIdx.x;
         sp[threadIdx.x] = spos[cj]; sn[threadIdx.x] = snrm[cj];
         __syncthreads();
         const uint32_t k0 = (ct == rt) ? threadIdx.x + 1 : 0;             /* diagonal tile: each unordered pair once */
+#pragma unroll 4
         for (uint32_t k = k0; k < RAD_TILE; ++k) {
             const V3 d = ld3(sp[k]) - Pr;
             const V3 Nj = ld3(sn[k]);
@@ -207,6 +222,7 @@ rad_candidates_kernel(const float4 *__restrict__ spos, const float4 *__restrict_
             __syncthreads();
             if (threadIdx.x == 0) q_count = 0;
         }
+      }
     }
     __syncthreads();
     {
@@ -344,10 +360,10 @@ template <class T> static int grow_buf(ltrgpu_Ctx *ctx, T **p, size_t *cap, size
     size_t ncap = *cap ? *cap : (size_t)1 << 20;
     while (ncap < need) ncap *= 2;
     T *q = nullptr;
-    CU_TRY(ctx, cudaMalloc((void **)&q, ncap * sizeof(T)));
+    CU_TRY(ctx, lb_malloc((void **)&q, ncap * sizeof(T)));
     if (*p && used) CU_TRY(ctx, cudaMemcpyAsync(q, *p, used * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (*p) cudaFree(*p);
+    if (*p) lb_free(*p);
     *p = q; *cap = ncap;
     return 0;
 }
@@ -424,12 +440,12 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
             RAD_LAUNCHED();
             cub::DoubleBuffer<uint32_t> kb(mkeys, mkeys_alt), vb(sidx, sidx_alt);
             RAD_CU(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, kb, vb, (int)n, 0, 30, st));
-            RAD_CU(cudaMalloc(&sort_tmp, sort_tmp_bytes ? sort_tmp_bytes : 16));
+            RAD_CU(lb_malloc(&sort_tmp, sort_tmp_bytes ? sort_tmp_bytes : 16));
             RAD_CU(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_tmp_bytes, kb, vb, (int)n, 0, 30, st));
             ctx->host_counters.kernel_launches += 4;
             if (vb.Current() != sidx) RAD_CU(cudaMemcpyAsync(sidx, vb.Current(), n * 4, cudaMemcpyDeviceToDevice, st));
             RAD_CU(cudaStreamSynchronize(st));
-            cudaFree(sort_tmp); sort_tmp = nullptr; sort_tmp_bytes = 0;
+            lb_free(sort_tmp); sort_tmp = nullptr; sort_tmp_bytes = 0;
         }
         RAD_TRY(dev_alloc(ctx, &spos, n_pad)); RAD_TRY(dev_alloc(ctx, &snrm, n_pad));
         RAD_TRY(dev_alloc(ctx, &tb, n_tiles));
@@ -440,9 +456,19 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
 
         /* ---- 2-4. candidates and visibility, in batches of row tiles bounded by the candidate buffer ---- */
         RAD_TRY(dev_alloc(ctx, &d_cnt, 2));
-        const unsigned long long cand_cap = 48ull << 20;             /* 48 Mi candidates = 576 MiB */
+        /* candidate buffer: a sixth of the free HBM, between 16 Mi and 384 Mi records (12 B each) */
+        unsigned long long cand_cap = 16ull << 20;
+        {
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+                unsigned long long want = (unsigned long long)(free_b / 6 / sizeof(RadCand));
+                if (want > cand_cap) cand_cap = want;
+                if (cand_cap > (384ull << 20)) cand_cap = 384ull << 20;
+            }
+        }
         RAD_TRY(dev_alloc(ctx, &cand, cand_cap));
-        uint32_t batch = 2048;
+        /* batch of row tiles: probe with 16 CTAs per SM, then size each batch from the measured yield */
+        uint32_t batch = (uint32_t)ctx->num_sms * 16;
         for (uint32_t t0 = my_t0; t0 < my_t1;) {
             uint32_t t1 = t0 + batch < my_t1 ? t0 + batch : my_t1;
             RAD_CU(cudaMemsetAsync(d_cnt, 0, 16, st));
@@ -456,8 +482,10 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
             { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1); ms_pairs += ms; }
             if (h_cnt[0] > cand_cap) {
                 if (batch == 1) { snprintf(ctx->err, sizeof(ctx->err), "radiosity: one row tile produced %llu candidates (> %llu)", h_cnt[0], cand_cap); goto done; }
-                batch = batch / 4 ? batch / 4 : 1;
-                continue;                                             /* redo this batch smaller */
+                /* redo this batch smaller: scale by the overshoot with 30 % headroom */
+                uint32_t nb = (uint32_t)((double)(t1 - t0) * (double)cand_cap / (double)h_cnt[0] * 0.7);
+                batch = nb ? nb : 1;
+                continue;
             }
             const unsigned long long nc = h_cnt[0];
             if (nc) {
@@ -476,6 +504,13 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
                 { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1); ms_vis += ms; }
                 link_used += h_cnt[1];
             }
+            {
+                const double per_tile = (double)(nc ? nc : 1) / (double)(t1 - t0);
+                double nb = 0.7 * (double)cand_cap / per_tile;
+                if (nb < (double)ctx->num_sms) nb = (double)ctx->num_sms;
+                if (nb > 1.0e9) nb = 1.0e9;
+                batch = (uint32_t)nb;
+            }
             t0 = t1;
         }
         dev_free(&cand);
@@ -486,7 +521,7 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
             cub::DoubleBuffer<unsigned long long> kb(keys, keys_alt);
             cub::DoubleBuffer<float> vb(fac, fac_alt);
             RAD_CU(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, kb, vb, (int64_t)link_used, 0, 64, st));
-            RAD_CU(cudaMalloc(&sort_tmp, sort_tmp_bytes ? sort_tmp_bytes : 16));
+            RAD_CU(lb_malloc(&sort_tmp, sort_tmp_bytes ? sort_tmp_bytes : 16));
             RAD_CU(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_tmp_bytes, kb, vb, (int64_t)link_used, 0, 64, st));
             ctx->host_counters.kernel_launches += 8;
             RAD_CU(cudaStreamSynchronize(st));
@@ -542,10 +577,10 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
         rc = 0;
     }
 done:
-    cudaFree(spos); cudaFree(snrm); cudaFree(diff); cudaFree(total); cudaFree(out); cudaFree(Es); cudaFree(Eo); cudaFree(tb);
-    cudaFree(mkeys); cudaFree(mkeys_alt); cudaFree(sidx); cudaFree(sidx_alt); cudaFree(d_bounds);
-    cudaFree(d_diffuse); cudaFree(d_emissive); cudaFree(cand); cudaFree(d_cnt); cudaFree(keys); cudaFree(keys_alt);
-    cudaFree(fac); cudaFree(fac_alt); cudaFree(sort_tmp);
+    lb_free(spos); lb_free(snrm); lb_free(diff); lb_free(total); lb_free(out); lb_free(Es); lb_free(Eo); lb_free(tb);
+    lb_free(mkeys); lb_free(mkeys_alt); lb_free(sidx); lb_free(sidx_alt); lb_free(d_bounds);
+    lb_free(d_diffuse); lb_free(d_emissive); lb_free(cand); lb_free(d_cnt); lb_free(keys); lb_free(keys_alt);
+    lb_free(fac); lb_free(fac_alt); lb_free(sort_tmp);
     return rc;
 #undef RAD_TRY
 #undef RAD_CU

@@ -3,6 +3,80 @@
 
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <unordered_map>
+
+/* ---- caching device allocator (see gpu_internal.cuh) ------------------------------------------ */
+namespace {
+struct Pool {
+    std::mutex mu;
+    std::unordered_map<void *, std::pair<int, size_t>> live;       /* ptr -> (device, bytes) */
+    std::multimap<std::pair<int, size_t>, void *> idle;            /* (device, bytes) -> ptr */
+};
+Pool &pool() { static Pool p; return p; }
+size_t size_class(size_t bytes)
+{
+    if (bytes < 4096) return 4096;
+    /* round up to 1/8 steps of the enclosing power of two: <= 12.5 % slack, few distinct classes */
+    size_t p2 = 4096;
+    while (p2 < bytes) p2 <<= 1;
+    const size_t step = p2 >> 4;
+    return (bytes + step - 1) / step * step;
+}
+} // namespace
+
+cudaError_t lb_malloc(void **p, size_t bytes)
+{
+    Pool &P = pool();
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t cls = size_class(bytes ? bytes : 1);
+    {
+        std::lock_guard<std::mutex> g(P.mu);
+        auto it = P.idle.find({ dev, cls });
+        if (it != P.idle.end()) {
+            *p = it->second;
+            P.idle.erase(it);
+            P.live[*p] = { dev, cls };
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, cls);
+    if (e != cudaSuccess) {                       /* out of memory: give cached blocks back and retry once */
+        cudaGetLastError();
+        lb_trim();
+        e = cudaMalloc(p, cls);
+    }
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> g(P.mu);
+        P.live[*p] = { dev, cls };
+    }
+    return e;
+}
+
+void lb_free(void *p)
+{
+    if (!p) return;
+    Pool &P = pool();
+    std::lock_guard<std::mutex> g(P.mu);
+    auto it = P.live.find(p);
+    if (it == P.live.end()) { cudaFree(p); return; }
+    P.idle.insert({ it->second, p });
+    P.live.erase(it);
+}
+
+void lb_trim(void)
+{
+    Pool &P = pool();
+    std::lock_guard<std::mutex> g(P.mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto &kv : P.idle) { cudaSetDevice(kv.first.first); cudaFree(kv.second); }
+    P.idle.clear();
+    cudaSetDevice(cur);
+}
+
 /* one thread per BVH-order triangle: expand the 9 floats into the two prepared records
  * (geom.h) with the reference's exact expressions. */
 __global__ void prepare_tris_kernel(const float *__restrict__ tris9, uint32_t n, PreparedTri *__restrict__ pt, RayTri *__restrict__ rt)
@@ -82,9 +156,11 @@ extern "C" void ltrgpu_destroy(ltrgpu_Ctx *ctx)
     if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
     if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    /* cached device blocks stay in the pool for the next bake of this process (ltrgpu_release_memory drops them) */
     delete ctx;
 }
 
+extern "C" void ltrgpu_release_memory(void) { lb_trim(); }
 extern "C" const char *ltrgpu_last_error(ltrgpu_Ctx *ctx) { return ctx ? ctx->err : "no GPU context"; }
 extern "C" void *ltrgpu_stream(ltrgpu_Ctx *ctx) { return (void *)ctx->stream; }
 
@@ -172,7 +248,7 @@ extern "C" int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *d)
         CU_LAUNCH_CHECK(ctx);
     }
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_raw);
+    lb_free(d_raw);
     return 0;
 }
 

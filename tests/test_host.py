@@ -57,8 +57,12 @@ def test_world_size_2_gloo_sharding(tmp_path):
         print("rank", rank, "ok", b, e)
         dist.destroy_process_group()
     """))
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29611", str(script)], capture_output=True, text=True, timeout=300)
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "rank 0 ok 0 501" in r.stdout and "rank 1 ok 501 1001" in r.stdout
 
