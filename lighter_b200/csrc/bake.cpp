@@ -18,6 +18,8 @@
 #include <time.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <thread>
 
 #include "gpu.h"
@@ -368,8 +370,20 @@ void upload(ltr_Scene *S)
         if (!S->have_nccl_id) { Fail f; f.msg = "sharded bake without an NCCL unique id (call ltrx_SetShard)"; throw f; }
         NcclId id;
         memcpy(&id, S->nccl_id, sizeof(id));
-        int rc = B.nccl->CommInitRank(&B.comm, S->world, id, S->rank);
-        if (rc != 0) { Fail f; f.msg = std::string("ncclCommInitRank: ") + B.nccl->GetErrorString(rc); throw f; }
+        /* One communicator per (unique id, rank, world) per process, shared by every scene that names
+         * the same id: an NCCL unique id can seed ncclCommInitRank only once. */
+        static std::mutex comm_mu;
+        static std::map<std::string, void *> comm_cache;
+        std::string key((const char *)S->nccl_id, sizeof(S->nccl_id));
+        key += "/" + std::to_string(S->rank) + "/" + std::to_string(S->world);
+        std::lock_guard<std::mutex> g(comm_mu);
+        auto it = comm_cache.find(key);
+        if (it != comm_cache.end()) B.comm = it->second;
+        else {
+            int rc = B.nccl->CommInitRank(&B.comm, S->world, id, S->rank);
+            if (rc != 0) { B.comm = nullptr; Fail f; f.msg = std::string("ncclCommInitRank: ") + B.nccl->GetErrorString(rc); throw f; }
+            comm_cache[key] = B.comm;
+        }
     }
     S->stats.t_upload = now_s() - t0;
 }
@@ -579,7 +593,7 @@ void bake_free(ltr_Scene *S)
 {
     if (!S->bake) return;
     Bake *B = S->bake;
-    if (B->comm && B->nccl) B->nccl->CommDestroy(B->comm);
+    /* communicators are process-lifetime (cached by unique id in upload()); nothing to destroy here */
     if (B->gpu) ltrgpu_destroy(B->gpu);
     delete B;
     S->bake = nullptr;

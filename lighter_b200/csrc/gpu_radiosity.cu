@@ -31,11 +31,15 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <stdlib.h>
+#include <time.h>
+
+#include <vector>
 
 #define RAD_TILE 128
 #define RAD_CUTOFF 17.85f       /* > sqrt(1/(0.001*pi)) = 17.8412; conservative */
 #define RAD_SKIP_BELOW 0.0009f  /* interval bounds below this cannot reach the 0.001 thresholds even with rounding */
-#define RAD_QUEUE 2048          /* per-CTA shared-memory candidate queue */
+#define RAD_QUEUE 1024          /* per-CTA shared-memory candidate queue */
+#define RAD_PAD 0xffffffffu     /* storage slot without a lumel */
 
 struct RadCand { uint32_t a, b; float factor; };       /* sorted positions of the two lumels */
 
@@ -81,14 +85,28 @@ __global__ void rad_bounds_reduce_kernel(const float4 *__restrict__ lpos, uint64
     }
 }
 
+/* Morton order -> storage order.  Tiles of 128 consecutive Morton positions are dealt round-robin
+ * to the ranks, each rank's tiles stored contiguously: every rank gets a statistically identical
+ * sample of the scene (vertical surfaces generate far more candidates than floors; a contiguous
+ * split of the curve measured 4x imbalance), and its rows stay one contiguous all-gather chunk. */
+__global__ void rad_deal_kernel(const uint32_t *__restrict__ smort, uint64_t n, uint64_t n_pad, uint32_t world, uint32_t tiles_per_rank,
+                                uint32_t *__restrict__ sidx)
+{
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_pad) return;
+    const uint32_t t = (uint32_t)(k / RAD_TILE), w = (uint32_t)(k % RAD_TILE);
+    const uint32_t st = (t % world) * tiles_per_rank + t / world;
+    sidx[(uint64_t)st * RAD_TILE + w] = k < n ? smort[k] : RAD_PAD;
+}
+
 /* gather the sorted geometry; the reference re-normalises the normal here (lighter.cpp:680) */
 __global__ void rad_gather_kernel(const float4 *__restrict__ lpos, const float4 *__restrict__ lnrm, const uint32_t *__restrict__ sidx, uint64_t n,
                                   uint64_t n_pad, float4 *__restrict__ spos, float4 *__restrict__ snrm)
 {
     uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_pad) return;
-    if (k < n) {
-        const uint32_t i = sidx[k];
+    const uint32_t i = sidx[k];
+    if (i != RAD_PAD) {
         spos[k] = lpos[i];
         V3 N = norm3(ld3(lnrm[i]));
         snrm[k] = make_float4(N.x, N.y, N.z, 0.f);
@@ -98,13 +116,14 @@ __global__ void rad_gather_kernel(const float4 *__restrict__ lpos, const float4 
     }
 }
 
-__global__ void rad_tile_bounds_kernel(const float4 *__restrict__ spos, const float4 *__restrict__ snrm, uint64_t n, TileBounds *__restrict__ tb)
+__global__ void rad_tile_bounds_kernel(const float4 *__restrict__ spos, const float4 *__restrict__ snrm, const uint32_t *__restrict__ sidx, TileBounds *__restrict__ tb,
+                                       TileBounds *__restrict__ tb32 /* per 32-lumel sub-tile: 4 per tile */)
 {
     __shared__ float s[12][RAD_TILE / 32];
     const uint64_t k = (uint64_t)blockIdx.x * RAD_TILE + threadIdx.x;
     float v[12];
     for (int a = 0; a < 6; ++a) { v[a] = INFINITY; v[6 + a] = -INFINITY; }          /* [0..2] plo, [3..5] nlo, [6..8] phi, [9..11] nhi */
-    if (k < n) {
+    if (sidx[k] != RAD_PAD) {
         float4 p = spos[k], q = snrm[k];
         v[0] = v[6] = p.x; v[1] = v[7] = p.y; v[2] = v[8] = p.z;
         v[3] = v[9] = q.x; v[4] = v[10] = q.y; v[5] = v[11] = q.z;
@@ -114,7 +133,13 @@ __global__ void rad_tile_bounds_kernel(const float4 *__restrict__ spos, const fl
             float t = __shfl_xor_sync(0xffffffffu, v[a], o);
             v[a] = a < 6 ? fminf(v[a], t) : fmaxf(v[a], t);
         }
-    if ((threadIdx.x & 31) == 0) for (int a = 0; a < 12; ++a) s[a][threadIdx.x >> 5] = v[a];
+    if ((threadIdx.x & 31) == 0) {
+        for (int a = 0; a < 12; ++a) s[a][threadIdx.x >> 5] = v[a];
+        TileBounds w;
+        w.plo = make_float4(v[0], v[1], v[2], 0.f); w.nlo = make_float4(v[3], v[4], v[5], 0.f);
+        w.phi = make_float4(v[6], v[7], v[8], 0.f); w.nhi = make_float4(v[9], v[10], v[11], 0.f);
+        tb32[(size_t)blockIdx.x * (RAD_TILE / 32) + (threadIdx.x >> 5)] = w;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int a = 0; a < 12; ++a)
@@ -156,7 +181,8 @@ __device__ __forceinline__ bool tile_pair_may_link(const TileBounds &R, const Ti
  */
 __global__ void __launch_bounds__(RAD_TILE)
 rad_candidates_kernel(const float4 *__restrict__ spos, const float4 *__restrict__ snrm, const TileBounds *__restrict__ tb,
-                      uint32_t n_tiles, uint32_t my_t0, uint32_t my_t1, uint32_t first_row_tile,
+                      const TileBounds *__restrict__ tb32,
+                      uint32_t n_tiles, uint32_t world, uint32_t tiles_per_rank, uint32_t first_row_tile,
                       RadCand *__restrict__ cand, unsigned long long cand_cap, unsigned long long *cand_count, unsigned long long *counters)
 {
     __shared__ float4 sp[RAD_TILE], sn[RAD_TILE];
@@ -167,6 +193,8 @@ rad_candidates_kernel(const float4 *__restrict__ spos, const float4 *__restrict_
     const uint32_t r = rt * RAD_TILE + threadIdx.x;
     const V3 Pr = ld3(spos[r]), Nr = ld3(snrm[r]);
     const TileBounds R = tb[rt];
+    const uint32_t mrt = (rt % tiles_per_rank) * world + rt / tiles_per_rank;
+    const TileBounds Rw = tb32[(size_t)rt * (RAD_TILE / 32) + (threadIdx.x >> 5)];
     __shared__ uint32_t tile_list[RAD_TILE];
     __shared__ unsigned tile_cnt;
     unsigned tested = 0;
@@ -180,8 +208,10 @@ rad_candidates_kernel(const float4 *__restrict__ spos, const float4 *__restrict_
         const uint32_t c = base + threadIdx.x;
         bool ok = c < n_tiles;
         if (ok) {
-            const bool mine = c >= my_t0 && c < my_t1;
-            ok = !(mine && c < rt) && tile_pair_may_link(R, tb[c]);       /* mine && c<rt: pair seen from the other tile */
+            /* every unordered tile pair is swept exactly once in the whole job: by the owner of the tile
+             * that comes first on the Morton curve (storage index -> Morton tile index, see rad_deal_kernel) */
+            const uint32_t mc = (c % tiles_per_rank) * world + c / tiles_per_rank;
+            ok = mc >= mrt && tile_pair_may_link(R, tb[c]);
         }
         if (ok) tile_list[atomicAdd(&tile_cnt, 1u)] = c;
       }
@@ -194,8 +224,12 @@ rad_candidates_kernel(const float4 *__restrict__ spos, const float4 *__restrict_
         sp[threadIdx.x] = spos[cj]; sn[threadIdx.x] = snrm[cj];
         __syncthreads();
         const uint32_t k0 = (ct == rt) ? threadIdx.x + 1 : 0;             /* diagonal tile: each unordered pair once */
+        for (uint32_t sub = 0; sub < RAD_TILE / 32; ++sub) {
+        /* warp-level culling: my warp's 32 rows against this 32-lumel column sub-tile (warp-uniform branch) */
+        if (!tile_pair_may_link(Rw, tb32[(size_t)ct * (RAD_TILE / 32) + sub])) continue;
+        const uint32_t kb = sub * 32u > k0 ? sub * 32u : k0;
 #pragma unroll 4
-        for (uint32_t k = k0; k < RAD_TILE; ++k) {
+        for (uint32_t k = kb; k < sub * 32u + 32u; ++k) {
             const V3 d = ld3(sp[k]) - Pr;
             const V3 Nj = ld3(sn[k]);
             const float dr = dot3(Nr, d);
@@ -212,6 +246,7 @@ rad_candidates_kernel(const float4 *__restrict__ spos, const float4 *__restrict_
                 const unsigned long long g = atomicAdd(cand_count, 1ull);
                 if (g < cand_cap) cand[g] = c;
             }
+        }
         }
         __syncthreads();
         if (q_count >= RAD_QUEUE / 2) {                                   /* CTA-uniform flush */
@@ -241,14 +276,15 @@ __global__ void __launch_bounds__(LB_BLOCK)
 rad_visibility_kernel(const BvhNode *__restrict__ bvh, const RayTri *__restrict__ raytris, const float4 *__restrict__ spos,
                       const uint32_t *__restrict__ sidx, const RadCand *__restrict__ cand, unsigned long long n_cand,
                       uint32_t my_k0, uint32_t my_k1, unsigned long long *__restrict__ keys, float *__restrict__ factors,
-                      unsigned long long *link_count, unsigned long long *counters)
+                      unsigned long long *link_count, uint4 *__restrict__ mirror, unsigned long long mirror_cap, unsigned long long *mirror_count,
+                      unsigned long long *counters)
 {
     unsigned segs = 0;
     TravStats ts = { 0, 0 };
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long n_pad = (n_cand + 31ull) & ~31ull;
     for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_pad; e += (unsigned long long)gridDim.x * blockDim.x) {
-        unsigned emit = 0;                        /* bit 0: row a is mine, bit 1: row b is mine */
+        unsigned emit = 0;                        /* bit 0: link for row a (always mine), bit 1: row b is mine too, bit 2: row b lives on another rank */
         RadCand c = { 0, 0, 0.f };
         uint32_t oa = 0, ob = 0;
         if (e < n_cand) {
@@ -260,9 +296,9 @@ rad_visibility_kernel(const BvhNode *__restrict__ bvh, const RayTri *__restrict_
             const V3 mA = A + dn * LB_SMALL, mB = B - dn * LB_SMALL;
             ++segs;
             if (bvh_segment<true>(bvh, raytris, nullptr, mA, mB, nullptr, ts) < 1.0f)
-                emit = ((c.a >= my_k0 && c.a < my_k1) ? 1u : 0u) | ((c.b >= my_k0 && c.b < my_k1) ? 2u : 0u);
+                emit = 1u | ((c.b >= my_k0 && c.b < my_k1) ? 2u : 4u);
         }
-        const unsigned cnt = __popc(emit);
+        const unsigned cnt = __popc(emit & 3u);
         /* warp-aggregated append: exclusive prefix of cnt over the warp */
         unsigned pre = cnt;
         for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= (unsigned)o) pre += t; }
@@ -275,10 +311,49 @@ rad_visibility_kernel(const BvhNode *__restrict__ bvh, const RayTri *__restrict_
             if (emit & 1u) { keys[at] = ((unsigned long long)c.a << 32) | ob; factors[at] = c.factor; ++at; }
             if (emit & 2u) { keys[at] = ((unsigned long long)c.b << 32) | oa; factors[at] = c.factor; }
         }
+        /* mirrored link for a row owned by another rank: queued for the exchange */
+        const unsigned mm = __ballot_sync(0xffffffffu, (emit & 4u) != 0);
+        if (mm) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(mirror_count, (unsigned long long)__popc(mm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (emit & 4u) {
+                const unsigned long long at = base + __popc(mm & ((1u << lane) - 1u));
+                if (at < mirror_cap) mirror[at] = make_uint4(c.b, oa, __float_as_uint(c.factor), 0u);
+            }
+        }
     }
     count_add(counters, CNT_RAD_SEGMENTS, segs);
     count_add(counters, CNT_NODE_VISITS, ts.nodes);
     count_add(counters, CNT_TRI_TESTS, ts.tris);
+}
+
+/* after the exchange: keep the mirrored links whose row is mine */
+__global__ void rad_mirror_filter_kernel(const uint4 *__restrict__ all, unsigned long long stride, const unsigned long long *__restrict__ counts,
+                                         uint32_t world, uint32_t me, uint32_t my_k0, uint32_t my_k1,
+                                         unsigned long long *__restrict__ keys, float *__restrict__ factors, unsigned long long *link_count)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    for (uint32_t q = 0; q < world; ++q) {
+        if (q == me) continue;
+        const unsigned long long nq = counts[q], n_pad = (nq + 31ull) & ~31ull;
+        for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_pad; e += (unsigned long long)gridDim.x * blockDim.x) {
+            uint4 r = make_uint4(0, 0, 0, 0);
+            bool keep = false;
+            if (e < nq) { r = all[(unsigned long long)q * stride + e]; keep = r.x >= my_k0 && r.x < my_k1; }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (m) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(link_count, (unsigned long long)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (keep) {
+                    const unsigned long long at = base + __popc(m & ((1u << lane) - 1u));
+                    keys[at] = ((unsigned long long)r.x << 32) | r.y;
+                    factors[at] = __uint_as_float(r.z);
+                }
+            }
+        }
+    }
 }
 
 __global__ void rad_row_offsets_kernel(const unsigned long long *__restrict__ keys, unsigned long long n_links, uint64_t row_begin,
@@ -305,8 +380,8 @@ __global__ void rad_init_kernel(const float4 *__restrict__ lrgb, const float4 *_
 {
     uint64_t k = k0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= k1) return;
-    if (k >= n) { diff[k] = total[k] = out[k] = make_float4(0.f, 0.f, 0.f, 0.f); return; }
     const uint32_t i = sidx[k];
+    if (i == RAD_PAD) { diff[k] = total[k] = out[k] = make_float4(0.f, 0.f, 0.f, 0.f); return; }
     const bool probe = i < n_probes;
     V3 d = probe ? mk3(0.f) : mk3(1.f);
     V3 e = ld3(lrgb[i]);
@@ -334,7 +409,7 @@ __global__ void rad_energy_kernel(const float4 *__restrict__ diff, const float4 
 __global__ void rad_unpermute_kernel(const float4 *__restrict__ src_sorted, const uint32_t *__restrict__ sidx, uint64_t n, float4 *__restrict__ dst_orig)
 {
     uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) dst_orig[sidx[k]] = src_sorted[k];
+    if (k < n && sidx[k] != RAD_PAD) dst_orig[sidx[k]] = src_sorted[k];
 }
 
 __global__ void rad_bounce_kernel(const uint64_t *__restrict__ rowoff, const uint32_t *__restrict__ other, const float *__restrict__ factor,
@@ -397,11 +472,14 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
     const uint64_t k0 = (uint64_t)my_t0 * RAD_TILE, k1 = (uint64_t)my_t1 * RAD_TILE, n_rows = k1 - k0;
 
     float4 *spos = nullptr, *snrm = nullptr, *diff = nullptr, *total = nullptr, *out = nullptr, *Es = nullptr, *Eo = nullptr, *lrgb_full = nullptr;
-    TileBounds *tb = nullptr;
+    TileBounds *tb = nullptr, *tb32 = nullptr;
     uint32_t *mkeys = nullptr, *mkeys_alt = nullptr, *sidx = nullptr, *sidx_alt = nullptr;
     float *d_bounds = nullptr, *d_diffuse = nullptr, *d_emissive = nullptr;
     RadCand *cand = nullptr;
-    unsigned long long *d_cnt = nullptr;           /* [0] candidates, [1] links */
+    unsigned long long *d_cnt = nullptr;           /* [0] candidates, [1] links, [2] mirrored links */
+    uint4 *mirror = nullptr, *mirror_all = nullptr;
+    unsigned long long *d_mcounts = nullptr;
+    size_t mirror_cap = 0, mirror_used = 0;
     unsigned long long *keys = nullptr, *keys_alt = nullptr;
     float *fac = nullptr, *fac_alt = nullptr;
     size_t link_cap = 0, link_cap_f = 0, link_used = 0;
@@ -413,6 +491,11 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
 #define RAD_TRY(x) do { if (x) goto done; } while (0)
 #define RAD_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); goto done; } } while (0)
 #define RAD_LAUNCHED() do { ctx->host_counters.kernel_launches++; RAD_CU(cudaGetLastError()); } while (0)
+    /* LTR_TRACE=1: host-side phase timings on stderr (adds a stream sync per phase) */
+    const bool trace = getenv("LTR_TRACE") != nullptr;
+    struct timespec tr0; clock_gettime(CLOCK_MONOTONIC, &tr0);
+#define RAD_TRACE(label) do { if (trace) { cudaStreamSynchronize(st); struct timespec t_; clock_gettime(CLOCK_MONOTONIC, &t_); \
+        fprintf(stderr, "[ltr rank %d] radiosity %-22s %8.2f ms\n", ctx->rank, label, (t_.tv_sec - tr0.tv_sec) * 1e3 + (t_.tv_nsec - tr0.tv_nsec) * 1e-6); tr0 = t_; } } while (0)
 
     {
         /* the emitted light of EVERY lumel is needed: gather the direct-light shards first */
@@ -421,6 +504,7 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
             RAD_TRY(rad_allgather(ctx, ctx->d_lrgb, chunk, "direct light"));
         }
         lrgb_full = ctx->d_lrgb;
+        RAD_TRACE("gather direct light");
 
         /* ---- 1. Morton sort ---- */
         RAD_TRY(dev_alloc(ctx, &mkeys, n)); RAD_TRY(dev_alloc(ctx, &mkeys_alt, n));
@@ -447,15 +531,24 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
             RAD_CU(cudaStreamSynchronize(st));
             lb_free(sort_tmp); sort_tmp = nullptr; sort_tmp_bytes = 0;
         }
+        {
+            uint32_t *sdeal = nullptr;
+            RAD_TRY(dev_alloc(ctx, &sdeal, n_pad));
+            rad_deal_kernel<<<grid_for(n_pad, 256), 256, 0, st>>>(sidx, n, n_pad, world, tiles_per_rank, sdeal);
+            RAD_LAUNCHED();
+            lb_free(sidx);
+            sidx = sdeal;
+        }
+        RAD_TRACE("morton sort");
         RAD_TRY(dev_alloc(ctx, &spos, n_pad)); RAD_TRY(dev_alloc(ctx, &snrm, n_pad));
-        RAD_TRY(dev_alloc(ctx, &tb, n_tiles));
+        RAD_TRY(dev_alloc(ctx, &tb, n_tiles)); RAD_TRY(dev_alloc(ctx, &tb32, (size_t)n_tiles * (RAD_TILE / 32)));
         rad_gather_kernel<<<grid_for(n_pad, 256), 256, 0, st>>>(ctx->d_lpos, ctx->d_lnrm, sidx, n, n_pad, spos, snrm);
         RAD_LAUNCHED();
-        rad_tile_bounds_kernel<<<n_tiles, RAD_TILE, 0, st>>>(spos, snrm, n, tb);
+        rad_tile_bounds_kernel<<<n_tiles, RAD_TILE, 0, st>>>(spos, snrm, sidx, tb, tb32);
         RAD_LAUNCHED();
 
         /* ---- 2-4. candidates and visibility, in batches of row tiles bounded by the candidate buffer ---- */
-        RAD_TRY(dev_alloc(ctx, &d_cnt, 2));
+        RAD_TRY(dev_alloc(ctx, &d_cnt, 4));
         /* candidate buffer: a sixth of the free HBM, between 16 Mi and 384 Mi records (12 B each) */
         unsigned long long cand_cap = 16ull << 20;
         {
@@ -471,13 +564,13 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
         uint32_t batch = (uint32_t)ctx->num_sms * 16;
         for (uint32_t t0 = my_t0; t0 < my_t1;) {
             uint32_t t1 = t0 + batch < my_t1 ? t0 + batch : my_t1;
-            RAD_CU(cudaMemsetAsync(d_cnt, 0, 16, st));
+            RAD_CU(cudaMemsetAsync(d_cnt, 0, 32, st));
             RAD_CU(cudaEventRecord(ctx->ev_k0, st));
-            rad_candidates_kernel<<<t1 - t0, RAD_TILE, 0, st>>>(spos, snrm, tb, n_tiles, my_t0, my_t1, t0, cand, cand_cap, d_cnt, ctx->d_counters);
+            rad_candidates_kernel<<<t1 - t0, RAD_TILE, 0, st>>>(spos, snrm, tb, tb32, n_tiles, world, tiles_per_rank, t0, cand, cand_cap, d_cnt, ctx->d_counters);
             RAD_LAUNCHED();
             RAD_CU(cudaEventRecord(ctx->ev_k1, st));
-            unsigned long long h_cnt[2];
-            RAD_CU(cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, st));
+            unsigned long long h_cnt[4];
+            RAD_CU(cudaMemcpyAsync(h_cnt, d_cnt, 32, cudaMemcpyDeviceToHost, st));
             RAD_CU(cudaStreamSynchronize(st));
             { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1); ms_pairs += ms; }
             if (h_cnt[0] > cand_cap) {
@@ -491,18 +584,22 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
             if (nc) {
                 RAD_TRY(grow_buf(ctx, &keys, &link_cap, link_used, link_used + 2 * nc));
                 RAD_TRY(grow_buf(ctx, &fac, &link_cap_f, link_used, link_used + 2 * nc));
+                if (world > 1) RAD_TRY(grow_buf(ctx, &mirror, &mirror_cap, mirror_used, mirror_used + nc));
                 unsigned long long want = (nc + LB_BLOCK - 1) / LB_BLOCK;
                 unsigned cap = (unsigned)ctx->num_sms * 32;
                 unsigned blocks = want > cap ? cap : (unsigned)want;
                 RAD_CU(cudaEventRecord(ctx->ev_k0, st));
                 rad_visibility_kernel<<<blocks, LB_BLOCK, 0, st>>>(ctx->d_bvh, ctx->d_raytris, spos, sidx, cand, nc, (uint32_t)k0, (uint32_t)k1,
-                                                                  keys + link_used, fac + link_used, d_cnt + 1, ctx->d_counters);
+                                                                  keys + link_used, fac + link_used, d_cnt + 1,
+                                                                  mirror ? mirror + mirror_used : nullptr, mirror ? mirror_cap - mirror_used : 0, d_cnt + 2,
+                                                                  ctx->d_counters);
                 RAD_LAUNCHED();
                 RAD_CU(cudaEventRecord(ctx->ev_k1, st));
-                RAD_CU(cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, st));
+                RAD_CU(cudaMemcpyAsync(h_cnt, d_cnt, 32, cudaMemcpyDeviceToHost, st));
                 RAD_CU(cudaStreamSynchronize(st));
                 { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1); ms_vis += ms; }
                 link_used += h_cnt[1];
+                mirror_used += h_cnt[2];
             }
             {
                 const double per_tile = (double)(nc ? nc : 1) / (double)(t1 - t0);
@@ -514,6 +611,47 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
             t0 = t1;
         }
         dev_free(&cand);
+        RAD_TRACE("candidates+visibility");
+        if (trace) {
+            unsigned long long c[CNT_COUNT];
+            cudaMemcpy(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[ltr rank %d] radiosity pairs %llu segments %llu links(local) %zu  pairs-kernel %.1f ms  visibility-kernel %.1f ms\n", ctx->rank,
+                    c[CNT_RAD_PAIRS], c[CNT_RAD_SEGMENTS], link_used, ms_pairs, ms_vis);
+        }
+
+        /* ---- 4b. exchange the mirrored links: each rank's records are all-gathered (padded to the largest
+         *          count), every rank keeps the ones whose row it owns.  ~16 B per cross-rank link. ---- */
+        if (world > 1) {
+            RAD_TRY(dev_alloc(ctx, &d_mcounts, world));
+            RAD_CU(cudaMemsetAsync(d_mcounts, 0, 8 * world, st));
+            unsigned long long mine_cnt = mirror_used;
+            RAD_CU(cudaMemcpyAsync(d_mcounts + ctx->rank, &mine_cnt, 8, cudaMemcpyHostToDevice, st));
+            if (!ctx->allgather || ctx->allgather(ctx->allgather_user, d_mcounts + ctx->rank, d_mcounts, 8, st)) {
+                snprintf(ctx->err, sizeof(ctx->err), "radiosity: all-gather of link counts failed"); goto done;
+            }
+            std::vector<unsigned long long> hc(world);
+            RAD_CU(cudaMemcpyAsync(hc.data(), d_mcounts, 8 * world, cudaMemcpyDeviceToHost, st));
+            RAD_CU(cudaStreamSynchronize(st));
+            unsigned long long stride = 1, incoming = 0;
+            for (uint32_t q = 0; q < world; ++q) { if (hc[q] > stride) stride = hc[q]; if (q != (uint32_t)ctx->rank) incoming += hc[q]; }
+            RAD_TRY(dev_alloc(ctx, &mirror_all, (size_t)stride * world));
+            if (mirror_used) RAD_CU(cudaMemcpyAsync(mirror_all + (size_t)stride * ctx->rank, mirror, mirror_used * sizeof(uint4), cudaMemcpyDeviceToDevice, st));
+            if (ctx->allgather(ctx->allgather_user, mirror_all + (size_t)stride * ctx->rank, mirror_all, (size_t)stride * sizeof(uint4), st)) {
+                snprintf(ctx->err, sizeof(ctx->err), "radiosity: all-gather of mirrored links failed"); goto done;
+            }
+            RAD_TRY(grow_buf(ctx, &keys, &link_cap, link_used, link_used + incoming));
+            RAD_TRY(grow_buf(ctx, &fac, &link_cap_f, link_used, link_used + incoming));
+            RAD_CU(cudaMemsetAsync(d_cnt, 0, 32, st));
+            rad_mirror_filter_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(mirror_all, stride, d_mcounts, world, (uint32_t)ctx->rank, (uint32_t)k0, (uint32_t)k1,
+                                                                     keys + link_used, fac + link_used, d_cnt + 1);
+            RAD_LAUNCHED();
+            unsigned long long got[4];
+            RAD_CU(cudaMemcpyAsync(got, d_cnt, 32, cudaMemcpyDeviceToHost, st));
+            RAD_CU(cudaStreamSynchronize(st));
+            link_used += got[1];
+            dev_free(&mirror_all); dev_free(&mirror);
+            RAD_TRACE("mirror link exchange");
+        }
 
         /* ---- 5. sort links by (row, partner) -> CSR in reference accumulation order ---- */
         if (link_used) {
@@ -548,6 +686,7 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
             RAD_CU(cudaStreamSynchronize(st));
         }
 
+        RAD_TRACE("link sort + CSR");
         /* ---- bounces ---- */
         RAD_TRY(dev_alloc(ctx, &diff, n_pad)); RAD_TRY(dev_alloc(ctx, &total, n_pad)); RAD_TRY(dev_alloc(ctx, &out, n_pad));
         RAD_TRY(dev_alloc(ctx, &Es, n_pad)); RAD_TRY(dev_alloc(ctx, &Eo, n + LB_PAD));
@@ -558,17 +697,19 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
             rad_energy_kernel<<<grid_for(n_rows, 256), 256, 0, st>>>(diff, out, k0, k1, Es);
             RAD_LAUNCHED();
             RAD_TRY(rad_allgather(ctx, Es, (uint64_t)tiles_per_rank * RAD_TILE, "bounce energy"));
-            rad_unpermute_kernel<<<grid_for(n, 256), 256, 0, st>>>(Es, ctx->d_rad_sidx, n, Eo);
+            rad_unpermute_kernel<<<grid_for(n_pad, 256), 256, 0, st>>>(Es, ctx->d_rad_sidx, n_pad, Eo);
             RAD_LAUNCHED();
             rad_bounce_kernel<<<grid_for(n_rows, 128), 128, 0, st>>>(ctx->d_rad_rowoff, ctx->d_rad_other, ctx->d_rad_factor, Eo, k0, k1, total, out);
             RAD_LAUNCHED();
         }
+        RAD_TRACE("bounces");
         /* commit: total light back to original lumel order, for every lumel on every rank */
         RAD_TRY(rad_allgather(ctx, total, (uint64_t)tiles_per_rank * RAD_TILE, "total light"));
-        rad_unpermute_kernel<<<grid_for(n, 256), 256, 0, st>>>(total, ctx->d_rad_sidx, n, ctx->d_lrgb);
+        rad_unpermute_kernel<<<grid_for(n_pad, 256), 256, 0, st>>>(total, ctx->d_rad_sidx, n_pad, ctx->d_lrgb);
         RAD_LAUNCHED();
         RAD_CU(cudaEventRecord(ctx->ev1, st));
         RAD_CU(cudaStreamSynchronize(st));
+        RAD_TRACE("commit");
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
         ctx->host_counters.ms_radiosity += ms;
@@ -577,14 +718,15 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
         rc = 0;
     }
 done:
-    lb_free(spos); lb_free(snrm); lb_free(diff); lb_free(total); lb_free(out); lb_free(Es); lb_free(Eo); lb_free(tb);
+    lb_free(spos); lb_free(snrm); lb_free(diff); lb_free(total); lb_free(out); lb_free(Es); lb_free(Eo); lb_free(tb); lb_free(tb32);
     lb_free(mkeys); lb_free(mkeys_alt); lb_free(sidx); lb_free(sidx_alt); lb_free(d_bounds);
     lb_free(d_diffuse); lb_free(d_emissive); lb_free(cand); lb_free(d_cnt); lb_free(keys); lb_free(keys_alt);
-    lb_free(fac); lb_free(fac_alt); lb_free(sort_tmp);
+    lb_free(fac); lb_free(fac_alt); lb_free(sort_tmp); lb_free(mirror); lb_free(mirror_all); lb_free(d_mcounts);
     return rc;
 #undef RAD_TRY
 #undef RAD_CU
 #undef RAD_LAUNCHED
+#undef RAD_TRACE
 }
 
 /* debug dump: rows are in SORTED (Morton) order on the device; hand them back in original lumel order */
