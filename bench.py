@@ -204,17 +204,48 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
     stage_ms = {"march": stats["gpu_ms_march"], "radiosity_pairs": stats["gpu_ms_rad_pairs"], "radiosity_visibility": stats["gpu_ms_rad_vis"],
                 "ao": stats["gpu_ms_ao"], "lumels": stats["gpu_ms_samples"], "finalize": stats["gpu_ms_finalize"]}
-    march_bytes = 0.0
-    roofline = None
-    if stats["gpu_ms_march"] > 0:
-        # node visits / triangle tests are counted over march + AO + radiosity rays; the march owns the point queries
-        tri_b, node_b = 160.0, 64.0
-        march_bytes = stats["n_node_visits"] * node_b + stats["n_tri_tests"] * tri_b + stats["n_marches"] * 36.0
-        trav_ms = stats["gpu_ms_march"] + stats["gpu_ms_ao"] + stats["gpu_ms_rad_vis"]
-        ach = march_bytes / (trav_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "BVH traversal kernels (direct_march + ao_trace + rad_visibility)", "achieved": ach, "peak": peak,
-                    "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                    "note": "algorithmic bytes = 64 B/node visit + 160 B/triangle test + 36 B/march; working set is L2-resident, see DESIGN.md"}
+    # Per-launch DRAM traffic measured once with `ncu --set full` (profiles/r01_traffic.json; None when not captured)
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload, {})
+
+    def roof(kernel, nbytes, ms, launches, note, extra=None):
+        if not ms or ms <= 0:
+            return None
+        ach = nbytes / (ms * 1e-3) / 1e9
+        r = {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+             "traffic": traffic.get(kernel), "peak_source": peak_src, "launches_per_step": launches,
+             "algorithmic_bytes_per_step": nbytes, "kernel_ms_per_step": ms, "note": note}
+        if extra:
+            r.update(extra)
+        return r
+
+    # SURVEY 8d unit costs: 64 B per BVH node visit, 160 B per point/triangle test (PreparedTri), 64 B per
+    # segment/triangle test (RayTri), 36 B per march (lumel in, factor out), 32 B per segment.
+    roofs = {
+        "rad_candidates_kernel": roof(
+            "rad_candidates_kernel",
+            stats["n_rad_tile_loads"] * 4096.0 + stats["n_rad_segments"] * 12.0 + stats["n_lumels_local"] * 32.0,
+            stats["gpu_ms_rad_pairs"], None,
+            "compulsory HBM bytes = 4 KiB per staged column tile + 12 B per candidate written + 32 B per row lumel; the kernel is "
+            "FP32-issue/LDS bound (no FMA by design, ncu: FMA pipe 40 % active), so the HBM fraction is small by construction",
+            {"pair_tests_per_s": stats["n_rad_pairs"] / (stats["gpu_ms_rad_pairs"] * 1e-3) if stats["gpu_ms_rad_pairs"] else None}),
+        "rad_visibility_kernel": roof(
+            "rad_visibility_kernel",
+            (stats["n_ray_node_visits"] - 0) * 64.0 + stats["n_ray_tri_tests"] * 64.0 + (stats["n_rad_segments"] + stats["n_ao_segments"]) * 32.0,
+            stats["gpu_ms_rad_vis"] + stats["gpu_ms_ao"], None,
+            "segment traversal (radiosity visibility + AO): 64 B/node + 64 B/triangle test + 32 B/segment; bytes are served by L1/L2 "
+            "(scene is cache resident), so this is cache bandwidth, not HBM utilisation"),
+        "direct_march_kernel": roof(
+            "direct_march_kernel",
+            stats["n_node_visits"] * 64.0 + stats["n_tri_tests"] * 160.0 + stats["n_marches"] * 36.0,
+            stats["gpu_ms_march"], None,
+            "distance-query traversal: 64 B/node + 160 B/point-triangle test + 36 B/march; L1/L2 served"),
+    }
+    roofs = {k: v for k, v in roofs.items() if v}
+    dominant = max(roofs, key=lambda k: roofs[k]["kernel_ms_per_step"]) if roofs else None
+    roofline = roofs.get(dominant)
 
     # ---- end-to-end arm: public C API, host buffers in, host lightmaps out ---------------------------
     e2e_walls, e2e_stats = [], None
@@ -242,13 +273,14 @@ def main():
         "rays_per_step": rays_step,
         "stage_ms": stage_ms,
         "counters": {k: int(stats[k]) for k in ("n_marches", "n_distance_queries", "n_ao_segments", "n_rad_pairs", "n_rad_segments", "n_rad_links",
-                                                 "n_node_visits", "n_tri_tests")},
+                                                 "n_node_visits", "n_tri_tests", "n_ray_node_visits", "n_ray_tri_tests", "n_rad_tile_loads")},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": int(e2e_stats["h2d_bytes"]), "d2h_bytes_per_step": int(e2e_stats["d2h_bytes"]),
                 "bake_wall_s": sum(e2e_walls) / len(e2e_walls), "steps": len(e2e_walls),
                 "host_s": {k: e2e_stats[k] for k in ("t_prexform", "t_accel", "t_upload", "t_samples", "t_direct", "t_radiosity", "t_ao", "t_finalize", "t_readback")}},
         "gpu_launches": int(launches_step * args.steps),
         "roofline": roofline,
+        "roofline_other": {k: v for k, v in roofs.items() if k != dominant},
     }
     h.close()
 

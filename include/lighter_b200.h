@@ -38,7 +38,9 @@ typedef struct ltrx_Stats {
     uint64_t n_lumels_total, n_lumels_local, n_triangles, n_bvh_nodes;
     uint64_t n_marches, n_distance_queries, n_ao_segments, n_correction_rays;
     uint64_t n_rad_pairs, n_rad_segments, n_rad_links;
-    uint64_t n_node_visits, n_tri_tests;      /* traversal counters (march + AO + radiosity) */
+    uint64_t n_node_visits, n_tri_tests;      /* distance-query traversal (march): BVH nodes visited, point/triangle tests */
+    uint64_t n_ray_node_visits, n_ray_tri_tests; /* segment traversal (AO + radiosity visibility) */
+    uint64_t n_rad_tile_loads;                /* 4 KiB column tiles staged by the radiosity pair sweep */
     uint64_t kernel_launches, h2d_bytes, d2h_bytes;
 } ltrx_Stats;
 

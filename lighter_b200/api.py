@@ -95,6 +95,7 @@ class Stats(C.Structure):
                 [(n, C.c_uint64) for n in ("n_lumels_total", "n_lumels_local", "n_triangles", "n_bvh_nodes", "n_marches",
                                            "n_distance_queries", "n_ao_segments", "n_correction_rays", "n_rad_pairs",
                                            "n_rad_segments", "n_rad_links", "n_node_visits", "n_tri_tests",
+                                           "n_ray_node_visits", "n_ray_tri_tests", "n_rad_tile_loads",
                                            "kernel_launches", "h2d_bytes", "d2h_bytes")])
 
     def as_dict(self) -> dict:

@@ -403,6 +403,7 @@ void gpu_stages(ltr_Scene *S)
     S->stage.store("generating samples");
     S->completion.store(0.f);
     B.lumel_off.assign(ni + 1, 0);
+    gpu_check(S, ltrgpu_set_world(B.gpu, S->rank, S->world, S->world > 1 ? nccl_allgather_cb : nullptr, &B), "world");
     gpu_check(S, ltrgpu_generate_lumels(B.gpu, B.lumel_off.data()), "lumel generation");
     const uint64_t n = B.lumel_off[ni];
     uint64_t sb = 0, se = n;
@@ -539,6 +540,7 @@ void readback(ltr_Scene *S)
         st.n_marches = c.marches; st.n_distance_queries = c.distance_queries; st.n_ao_segments = c.ao_segments;
         st.n_correction_rays = c.correction_rays; st.n_rad_pairs = c.rad_pairs; st.n_rad_segments = c.rad_segments;
         st.n_rad_links = c.rad_links; st.n_node_visits = c.node_visits; st.n_tri_tests = c.tri_tests;
+        st.n_ray_node_visits = c.ray_node_visits; st.n_ray_tri_tests = c.ray_tri_tests; st.n_rad_tile_loads = c.rad_tile_loads;
         st.kernel_launches = c.kernel_launches; st.h2d_bytes = c.h2d_bytes; st.d2h_bytes = c.d2h_bytes;
         st.gpu_ms_samples = c.ms_samples; st.gpu_ms_direct = c.ms_direct; st.gpu_ms_march = c.ms_march;
         st.gpu_ms_radiosity = c.ms_radiosity; st.gpu_ms_ao = c.ms_ao; st.gpu_ms_finalize = c.ms_finalize;
@@ -555,6 +557,7 @@ void collect_counters(ltr_Scene *S)
     st.n_marches = c.marches; st.n_distance_queries = c.distance_queries; st.n_ao_segments = c.ao_segments;
     st.n_correction_rays = c.correction_rays; st.n_rad_pairs = c.rad_pairs; st.n_rad_segments = c.rad_segments;
     st.n_rad_links = c.rad_links; st.n_node_visits = c.node_visits; st.n_tri_tests = c.tri_tests;
+        st.n_ray_node_visits = c.ray_node_visits; st.n_ray_tri_tests = c.ray_tri_tests; st.n_rad_tile_loads = c.rad_tile_loads;
     st.kernel_launches = c.kernel_launches; st.h2d_bytes = c.h2d_bytes; st.d2h_bytes = c.d2h_bytes;
     st.gpu_ms_samples = c.ms_samples; st.gpu_ms_direct = c.ms_direct; st.gpu_ms_march = c.ms_march;
     st.gpu_ms_radiosity = c.ms_radiosity; st.gpu_ms_ao = c.ms_ao; st.gpu_ms_finalize = c.ms_finalize;

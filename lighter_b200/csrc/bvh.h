@@ -22,7 +22,7 @@ struct BvhNode {                 /* 64 bytes */
     int32_t pad0, pad1;
 };
 
-#define BVH_LEAF_MAX 4
+#define BVH_LEAF_MAX 2      /* measured on B200 (configs 3, 4): leaves of <=2 beat 4 by 10-12 % and 7 by 25-30 % on the traversal kernels */
 #define BVH_STACK 64
 
 struct SceneBvh {

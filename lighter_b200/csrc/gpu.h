@@ -79,7 +79,9 @@ typedef struct ltrgpu_SceneDesc {
 typedef struct ltrgpu_Counters {
     uint64_t marches, distance_queries, ao_segments, correction_rays;
     uint64_t rad_pairs, rad_segments, rad_links;
-    uint64_t node_visits, tri_tests;
+    uint64_t node_visits, tri_tests;           /* distance queries (march): 64 B nodes, 160 B prepared triangles */
+    uint64_t ray_node_visits, ray_tri_tests;   /* segment queries (AO, radiosity): 64 B nodes, 64 B ray triangles */
+    uint64_t rad_tile_loads;                   /* 128-lumel column tiles (4 KiB) staged into shared memory by the pair sweep */
     uint64_t kernel_launches, h2d_bytes, d2h_bytes;
     float ms_samples, ms_direct, ms_march, ms_radiosity, ms_ao, ms_finalize, ms_rad_pairs, ms_rad_vis, ms_span;
 } ltrgpu_Counters;
@@ -99,6 +101,9 @@ int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *desc);
 /* stage: lumel generation (raster -> ordered compaction -> concave-edge offset -> overlap correction).
  * inst_lumel_off receives n_inst+1 prefix offsets into the global lumel array (probes first). */
 int ltrgpu_generate_lumels(ltrgpu_Ctx *ctx, uint64_t *inst_lumel_off);
+
+/* multi-GPU identity of this context and the all-gather hook; call before ltrgpu_generate_lumels */
+int ltrgpu_set_world(ltrgpu_Ctx *ctx, int rank, int world, ltrgpu_allgather_fn allgather, void *allgather_user);
 
 /* restrict the per-lumel stages to global lumels [begin,end) (multi-GPU shard); default = all */
 int ltrgpu_set_shard(ltrgpu_Ctx *ctx, uint64_t begin, uint64_t end, int rank, int world,

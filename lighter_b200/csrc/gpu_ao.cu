@@ -55,8 +55,8 @@ ao_trace_kernel(const BvhNode *__restrict__ bvh, const RayTri *__restrict__ rayt
         ++segs;
     }
     count_add(counters, CNT_AO_SEGMENTS, segs);
-    count_add(counters, CNT_NODE_VISITS, ts.nodes);
-    count_add(counters, CNT_TRI_TESTS, ts.tris);
+    count_add(counters, CNT_RAY_NODE_VISITS, ts.nodes);
+    count_add(counters, CNT_RAY_TRI_TESTS, ts.tris);
 }
 
 __global__ void ao_apply_kernel(const float *__restrict__ hits, uint64_t sh_begin, uint32_t n_local, ltrgpu_Params P, float4 *__restrict__ lrgb)

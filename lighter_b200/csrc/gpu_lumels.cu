@@ -449,11 +449,28 @@ extern "C" int ltrgpu_generate_lumels(ltrgpu_Ctx *ctx, uint64_t *inst_lumel_off)
         CU_LAUNCH_CHECK(ctx);
     }
     if (n > ctx->n_probes) {
+        /* The two sequential corrections are the expensive part of lumel generation; with several GPUs
+         * each rank corrects its own contiguous lumel range and the positions are all-gathered
+         * (16 B/lumel).  Raster, scan and emit above are replicated: they are cheap and deterministic. */
+        const uint64_t world = ctx->world > 0 ? (uint64_t)ctx->world : 1;
+        const uint64_t chunk = (n + world - 1) / world;
+        uint64_t b = chunk * (uint64_t)ctx->rank, e = b + chunk;
+        if (b > n) b = n;
+        if (e > n) e = n;
+        if (b < ctx->n_probes) b = ctx->n_probes;
         RefView all = { ctx->d_rnodes, ctx->d_ritems, ctx->d_rtree_tris };
-        lumel_fix_kernel<<<grid_for(n - ctx->n_probes, LB_BLOCK), LB_BLOCK, 0, st>>>(
-            ctx->d_inst, ctx->n_inst, all, ctx->d_bvh, ctx->d_raytris, ctx->d_ptris, ctx->d_tri_orig, ctx->n_probes, n,
-            ctx->params.max_correct_dist, ctx->params.corr_min_dot, ctx->d_lpos, ctx->d_lnrm, ctx->d_lrad, ctx->d_counters);
-        CU_LAUNCH_CHECK(ctx);
+        if (e > b) {
+            lumel_fix_kernel<<<grid_for(e - b, LB_BLOCK), LB_BLOCK, 0, st>>>(
+                ctx->d_inst, ctx->n_inst, all, ctx->d_bvh, ctx->d_raytris, ctx->d_ptris, ctx->d_tri_orig, b, e,
+                ctx->params.max_correct_dist, ctx->params.corr_min_dot, ctx->d_lpos, ctx->d_lnrm, ctx->d_lrad, ctx->d_counters);
+            CU_LAUNCH_CHECK(ctx);
+        }
+        if (world > 1) {
+            if (!ctx->allgather || ctx->allgather(ctx->allgather_user, ctx->d_lpos + chunk * ctx->rank, ctx->d_lpos, chunk * sizeof(float4), st)) {
+                snprintf(ctx->err, sizeof(ctx->err), "lumel generation: all-gather of positions failed");
+                return 1;
+            }
+        }
     }
     if (n) {
         fill_rgb_kernel<<<grid_for(n, 256), 256, 0, st>>>(ctx->d_lrgb, n, ctx->params.ambient[0], ctx->params.ambient[1], ctx->params.ambient[2]);
@@ -465,7 +482,7 @@ extern "C" int ltrgpu_generate_lumels(ltrgpu_Ctx *ctx, uint64_t *inst_lumel_off)
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->host_counters.ms_samples += ms;
     lb_free(d_block_sums); lb_free(d_total); lb_free(d_off);
-    ctx->sh_begin = 0; ctx->sh_end = n; ctx->rank = 0; ctx->world = 1;
+    ctx->sh_begin = 0; ctx->sh_end = n;          /* refined by ltrgpu_set_shard */
     return 0;
 }
 

@@ -252,6 +252,13 @@ extern "C" int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *d)
     return 0;
 }
 
+extern "C" int ltrgpu_set_world(ltrgpu_Ctx *ctx, int rank, int world, ltrgpu_allgather_fn allgather, void *allgather_user)
+{
+    if (world < 1 || rank < 0 || rank >= world) { snprintf(ctx->err, sizeof(ctx->err), "bad rank/world"); return 1; }
+    ctx->rank = rank; ctx->world = world; ctx->allgather = allgather; ctx->allgather_user = allgather_user;
+    return 0;
+}
+
 extern "C" int ltrgpu_set_shard(ltrgpu_Ctx *ctx, uint64_t begin, uint64_t end, int rank, int world,
                                 ltrgpu_allgather_fn allgather, void *allgather_user)
 {
@@ -270,6 +277,7 @@ extern "C" int ltrgpu_get_counters(ltrgpu_Ctx *ctx, ltrgpu_Counters *out)
     h.marches = c[CNT_MARCHES]; h.distance_queries = c[CNT_DIST_QUERIES]; h.ao_segments = c[CNT_AO_SEGMENTS];
     h.correction_rays = c[CNT_CORR_RAYS]; h.rad_pairs = c[CNT_RAD_PAIRS]; h.rad_segments = c[CNT_RAD_SEGMENTS];
     h.rad_links = c[CNT_RAD_LINKS]; h.node_visits = c[CNT_NODE_VISITS]; h.tri_tests = c[CNT_TRI_TESTS];
+    h.ray_node_visits = c[CNT_RAY_NODE_VISITS]; h.ray_tri_tests = c[CNT_RAY_TRI_TESTS]; h.rad_tile_loads = c[CNT_RAD_TILE_LOADS];
     *out = h;
     return 0;
 }
