@@ -413,6 +413,22 @@ void gpu_stages(ltr_Scene *S)
     S->stats.n_lumels_local = se - sb;
     S->stats.t_samples = now_s() - t0;
 
+    /* Replay of the reference's rand() consumption for the AO pass: one randf() per lumel, instance by
+     * instance (probe container first), lumel index ascending (lighter.cpp:819,1130-1135).  The draws
+     * only depend on the lumel COUNT, so they are generated on a host thread now, while the GPU runs
+     * the direct-light and radiosity stages (7.8 M draws = ~0.1 s of host time otherwise exposed).
+     * RAII: the thread is always joined, also when a later stage throws. */
+    struct RandJob {
+        std::vector<float> v;
+        std::thread th;
+        ~RandJob() { if (th.joinable()) th.join(); }
+    } randjob;
+    const bool user_code_before_ao = cfg.bounce_count && cfg.sample_fn;   /* a material callback might itself call rand(): keep the reference's order */
+    if (cfg.ao_distance) randjob.v.resize(n ? n : 1);
+    if (cfg.ao_distance && !user_code_before_ao) {
+        randjob.th = std::thread([&randjob, n]() { for (uint64_t i = 0; i < n; ++i) randjob.v[i] = (float)rand() / (float)RAND_MAX; });
+    }
+
     t0 = now_s();
     if (!S->lights.empty()) {
         S->stage.store("rendering lightmaps");
@@ -476,9 +492,9 @@ void gpu_stages(ltr_Scene *S)
         S->completion.store(0.f);
         /* replay of the reference's rand() consumption: one randf() per lumel, instance by
          * instance (probe container first), lumel index ascending (lighter.cpp:819,1130-1135) */
-        std::vector<float> randoff(n ? n : 1);
-        for (uint64_t i = 0; i < n; ++i) randoff[i] = (float)rand() / (float)RAND_MAX;
-        gpu_check(S, ltrgpu_ambient_occlusion(B.gpu, randoff.data()), "ambient occlusion");
+        if (randjob.th.joinable()) randjob.th.join();
+        else for (uint64_t i = 0; i < n; ++i) randjob.v[i] = (float)rand() / (float)RAND_MAX;
+        gpu_check(S, ltrgpu_ambient_occlusion(B.gpu, randjob.v.data()), "ambient occlusion");
         S->completion.store(1.f);
     }
     S->stats.t_ao = now_s() - t0;

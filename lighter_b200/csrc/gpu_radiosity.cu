@@ -186,6 +186,7 @@ rad_candidates_kernel(const float4 *__restrict__ spos, const float4 *__restrict_
                       uint32_t *row_cursor, RadCand *__restrict__ cand, unsigned long long cand_cap, unsigned long long *cand_count, unsigned long long *counters)
 {
     __shared__ float4 sp[RAD_TILE], sn[RAD_TILE];
+    __shared__ TileBounds sub_bounds[RAD_TILE / 32];
     __shared__ RadCand queue[RAD_QUEUE];
     __shared__ unsigned q_count;
     __shared__ unsigned long long q_base;
@@ -226,17 +227,32 @@ rad_candidates_kernel(const float4 *__restrict__ spos, const float4 *__restrict_
       }
       __syncthreads();
       const unsigned n_list = tile_cnt;
+      /* software pipeline: the NEXT column tile (positions, normals, its four sub-tile bounds) is fetched
+       * into registers while the current one is swept from shared memory, so the L2 latency of the tile
+       * switch is hidden behind ~750 instructions of pair tests instead of being paid at every barrier
+       * (ncu before: IPC 1.07, long-scoreboard + short-scoreboard stalls dominate) */
+      float4 pf_p = make_float4(0, 0, 0, 0), pf_n = pf_p, pf_b = pf_p;
+      if (n_list) {
+        const uint32_t c0 = tile_list[0];
+        pf_p = spos[(size_t)c0 * RAD_TILE + threadIdx.x]; pf_n = snrm[(size_t)c0 * RAD_TILE + threadIdx.x];
+        if (threadIdx.x < 16) pf_b = reinterpret_cast<const float4 *>(tb32 + (size_t)c0 * (RAD_TILE / 32))[threadIdx.x];
+      }
       for (unsigned li = 0; li < n_list; ++li) {
         const uint32_t ct = tile_list[li];
         __syncthreads();
-        const uint32_t cj = ct * RAD_TILE + threadIdx.x;
-        sp[threadIdx.x] = spos[cj]; sn[threadIdx.x] = snrm[cj];
+        sp[threadIdx.x] = pf_p; sn[threadIdx.x] = pf_n;
+        if (threadIdx.x < 16) reinterpret_cast<float4 *>(sub_bounds)[threadIdx.x] = pf_b;
         if (threadIdx.x == 0) ++tile_loads;
         __syncthreads();
+        if (li + 1 < n_list) {
+            const uint32_t cn = tile_list[li + 1];
+            pf_p = spos[(size_t)cn * RAD_TILE + threadIdx.x]; pf_n = snrm[(size_t)cn * RAD_TILE + threadIdx.x];
+            if (threadIdx.x < 16) pf_b = reinterpret_cast<const float4 *>(tb32 + (size_t)cn * (RAD_TILE / 32))[threadIdx.x];
+        }
         const uint32_t k0 = (ct == rt) ? threadIdx.x + 1 : 0;             /* diagonal tile: each unordered pair once */
         for (uint32_t sub = 0; sub < RAD_TILE / 32; ++sub) {
         /* warp-level culling: my warp's 32 rows against this 32-lumel column sub-tile (warp-uniform branch) */
-        if (!tile_pair_may_link(Rw, tb32[(size_t)ct * (RAD_TILE / 32) + sub])) continue;
+        if (!tile_pair_may_link(Rw, sub_bounds[sub])) continue;
         const uint32_t kb = sub * 32u > k0 ? sub * 32u : k0;
 #pragma unroll 4
         for (uint32_t k = kb; k < sub * 32u + 32u; ++k) {
