@@ -40,6 +40,7 @@
 #define RAD_SKIP_BELOW 0.0009f  /* interval bounds below this cannot reach the 0.001 thresholds even with rounding */
 #define RAD_QUEUE 1024          /* per-CTA shared-memory candidate queue */
 #define RAD_PAD 0xffffffffu     /* storage slot without a lumel */
+#define RAD_GROUP_DEFAULT 8     /* lumels per column group of the warp-level culling */
 
 struct RadCand { uint32_t a, b; float factor; };       /* sorted positions of the two lumels */
 
@@ -116,8 +117,12 @@ __global__ void rad_gather_kernel(const float4 *__restrict__ lpos, const float4 
     }
 }
 
+/* Bounds of every 128-lumel tile (tb) and of every G-lumel group inside it (tbg, 128/G per tile).
+ * Groups are runs of G consecutive Morton positions: a few texels of one surface, so their position
+ * and normal boxes are tight -- that is what makes the warp-level culling in the pair sweep bite. */
+template <int G>
 __global__ void rad_tile_bounds_kernel(const float4 *__restrict__ spos, const float4 *__restrict__ snrm, const uint32_t *__restrict__ sidx, TileBounds *__restrict__ tb,
-                                       TileBounds *__restrict__ tb32 /* per 32-lumel sub-tile: 4 per tile */)
+                                       TileBounds *__restrict__ tb32 /* per warp of row lumels */, TileBounds *__restrict__ tbg /* per G-lumel column group */)
 {
     __shared__ float s[12][RAD_TILE / 32];
     const uint64_t k = (uint64_t)blockIdx.x * RAD_TILE + threadIdx.x;
@@ -128,11 +133,20 @@ __global__ void rad_tile_bounds_kernel(const float4 *__restrict__ spos, const fl
         v[0] = v[6] = p.x; v[1] = v[7] = p.y; v[2] = v[8] = p.z;
         v[3] = v[9] = q.x; v[4] = v[10] = q.y; v[5] = v[11] = q.z;
     }
-    for (int a = 0; a < 12; ++a)
-        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int a = 0; a < 12; ++a) {
             float t = __shfl_xor_sync(0xffffffffu, v[a], o);
             v[a] = a < 6 ? fminf(v[a], t) : fmaxf(v[a], t);
         }
+        if (G < 32 && o * 2 == G && (threadIdx.x & (G - 1)) == 0) {                            /* the xor butterfly has just covered a G-lane group */
+            TileBounds w;
+            w.plo = make_float4(v[0], v[1], v[2], 0.f); w.nlo = make_float4(v[3], v[4], v[5], 0.f);
+            w.phi = make_float4(v[6], v[7], v[8], 0.f); w.nhi = make_float4(v[9], v[10], v[11], 0.f);
+            tbg[(size_t)blockIdx.x * (RAD_TILE / G) + threadIdx.x / G] = w;
+        }
+    }
     if ((threadIdx.x & 31) == 0) {
         for (int a = 0; a < 12; ++a) s[a][threadIdx.x >> 5] = v[a];
         TileBounds w;
@@ -174,25 +188,91 @@ __device__ __forceinline__ bool tile_pair_may_link(const TileBounds &R, const Ti
     return true;
 }
 
+/* Exact evaluation of one staged pair per lane (the reference's arithmetic, lighter.cpp:735-750) and
+ * warp-aggregated append of the linking ones to the CTA's candidate queue.  `e` = (row lane << 7) | k. */
+__device__ __forceinline__ void rad_exact_pair(unsigned e, const V3 &Pr, const V3 &Nr, const float4 *sp, const float4 *sn, uint32_t row_base, uint32_t col_base,
+                                               bool valid, bool diag, unsigned lane, unsigned lt_mask, RadCand *queue, unsigned *q_count,
+                                               RadCand *__restrict__ cand, unsigned long long cand_cap, unsigned long long *cand_count)
+{
+    const unsigned rl = e >> 7, k = e & 0x7fu;
+    if (diag && k <= (row_base & (RAD_TILE - 1)) + rl) valid = false;     /* diagonal tile: only k > my own position */
+    /* the row lumel lives in the registers of lane rl of this warp */
+    const V3 Pi = mk3(__shfl_sync(0xffffffffu, Pr.x, rl), __shfl_sync(0xffffffffu, Pr.y, rl), __shfl_sync(0xffffffffu, Pr.z, rl));
+    const V3 Ni = mk3(__shfl_sync(0xffffffffu, Nr.x, rl), __shfl_sync(0xffffffffu, Nr.y, rl), __shfl_sync(0xffffffffu, Nr.z, rl));
+    bool ok = false;
+    RadCand c = { 0, 0, 0.f };
+    if (valid) {
+        const V3 d = ld3(sp[k]) - Pi;
+        const float dr = dot3(Ni, d);
+        const float dj = -dot3(ld3(sn[k]), d);
+        if (!(dr <= LB_SMALL || dj <= LB_SMALL)) {
+            const float lensq = lensq3(d);
+            const float f = dr * dj / (lensq * lensq * 3.14159274101257324f);
+            if (!(f < LB_SMALL)) { ok = true; c.a = row_base + rl; c.b = col_base + k; c.factor = f; }
+        }
+    }
+    const unsigned okm = __ballot_sync(0xffffffffu, ok);
+    if (!okm) return;
+    unsigned qb = 0;
+    if (lane == 0) qb = atomicAdd(q_count, (unsigned)__popc(okm));
+    qb = __shfl_sync(0xffffffffu, qb, 0);
+    const unsigned at = qb + __popc(okm & lt_mask);
+    const bool spill = ok && at >= RAD_QUEUE;                             /* queue full: straight to global memory */
+    if (ok && !spill) queue[at] = c;
+    const unsigned sm = __ballot_sync(0xffffffffu, spill);
+    if (sm) {
+        unsigned long long gb = 0;
+        if (lane == 0) gb = atomicAdd(cand_count, (unsigned long long)__popc(sm));
+        gb = __shfl_sync(0xffffffffu, gb, 0);
+        const unsigned long long g = gb + __popc(sm & lt_mask);
+        if (spill && g < cand_cap) cand[g] = c;
+    }
+}
+
 /*
- * One CTA = one row tile (128 threads = 128 row lumels held in registers); sweeps the column tiles.
- * Tile pairs are visited once: column tile ct >= row tile rt, except that column tiles owned by
- * ANOTHER rank are always visited (that rank builds its own rows from its side).
+ * Pair sweep.  One CTA = one row tile at a time (128 threads = 128 row lumels held in registers),
+ * persistent over a cursor of row tiles; sweeps the column tiles.  Tile pairs are visited once:
+ * column tile ct >= row tile rt on the Morton curve, whichever rank owns the column tile.
+ *
+ * Three levels of exact culling, then a two-phase pair test:
+ *   tile x tile     one thread per column tile (128 per round), survivors compacted into tile_list;
+ *   warp x group    a column tile is staged in shared memory together with the bounds of its 128/G
+ *                   groups of G lumels; each lane of a warp tests the warp's 32 rows against one
+ *                   group (all groups in parallel), the ballot is the list of groups to sweep;
+ *   lumel x lumel   FAST filter, all 32 lanes in lock step: FMA dots and the factor inequality
+ *                   without the division, thresholds lowered by 10 % so that rounding differences to
+ *                   the exact arithmetic can only let extra pairs through, never drop one.  Survivors
+ *                   (~3 % of the pairs) are appended to a per-warp stage by ballot/popc;
+ *   drain           whenever 32 survivors are staged, the warp evaluates them one per lane with the
+ *                   reference's exact operation order (mul/add dots, IEEE division) -- full SIMT
+ *                   efficiency on the expensive path, which a per-pair branch does not have (measured
+ *                   before: 60 warp instructions per 32 pairs, 80 % of them in half-empty slow paths).
  */
+#define RAD_STAGE 288            /* per-warp stage: 31 left over + 8 pairs x 32 lanes, (row lane << 7 | k) each */
+
+template <int G>
 __global__ void __launch_bounds__(RAD_TILE)
 rad_candidates_kernel(const float4 *__restrict__ spos, const float4 *__restrict__ snrm, const TileBounds *__restrict__ tb,
-                      const TileBounds *__restrict__ tb32,
+                      const TileBounds *__restrict__ tb32, const TileBounds *__restrict__ tbg,
                       uint32_t n_tiles, uint32_t world, uint32_t tiles_per_rank, uint32_t first_row_tile, uint32_t n_row_tiles,
                       uint32_t *row_cursor, RadCand *__restrict__ cand, unsigned long long cand_cap, unsigned long long *cand_count, unsigned long long *counters)
 {
+    constexpr int NG = RAD_TILE / G;                       /* groups per column tile (<= 32: one per lane) */
+    constexpr int GB4 = NG * 4;                            /* float4s of group bounds per column tile */
+    constexpr int CH = G < 8 ? G : 8;                      /* pairs per lane between two drain checks */
+    static_assert(NG <= 32 && GB4 <= 2 * RAD_TILE, "group size too small");
     __shared__ float4 sp[RAD_TILE], sn[RAD_TILE];
-    __shared__ TileBounds sub_bounds[RAD_TILE / 32];
+    __shared__ TileBounds grp_bounds[NG];
     __shared__ RadCand queue[RAD_QUEUE];
+    __shared__ uint16_t stage[RAD_TILE / 32][RAD_STAGE];
+    __shared__ TileBounds row_bounds, row_warp_bounds[RAD_TILE / 32];
     __shared__ unsigned q_count;
     __shared__ unsigned long long q_base;
     __shared__ uint32_t tile_list[RAD_TILE];
     __shared__ unsigned tile_cnt;
     __shared__ uint32_t next_row_tile;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
     unsigned tested = 0, tile_loads = 0;
     if (threadIdx.x == 0) q_count = 0;
     /* persistent CTAs: row tiles cost anything from nothing (open floor far from geometry) to
@@ -206,9 +286,9 @@ rad_candidates_kernel(const float4 *__restrict__ spos, const float4 *__restrict_
     const uint32_t rt = first_row_tile + next_row_tile;
     const uint32_t r = rt * RAD_TILE + threadIdx.x;
     const V3 Pr = ld3(spos[r]), Nr = ld3(snrm[r]);
-    const TileBounds R = tb[rt];
+    if (threadIdx.x < 4) reinterpret_cast<float4 *>(&row_bounds)[threadIdx.x] = reinterpret_cast<const float4 *>(tb + rt)[threadIdx.x];
+    if (threadIdx.x < 16) reinterpret_cast<float4 *>(row_warp_bounds)[threadIdx.x] = reinterpret_cast<const float4 *>(tb32 + (size_t)rt * (RAD_TILE / 32))[threadIdx.x];
     const uint32_t mrt = (rt % tiles_per_rank) * world + rt / tiles_per_rank;
-    const TileBounds Rw = tb32[(size_t)rt * (RAD_TILE / 32) + (threadIdx.x >> 5)];
     for (uint32_t base = 0; base < n_tiles; base += RAD_TILE) {
       /* cooperative culling: each thread tests ONE column tile of this chunk, survivors are compacted */
       __syncthreads();
@@ -221,66 +301,77 @@ rad_candidates_kernel(const float4 *__restrict__ spos, const float4 *__restrict_
             /* every unordered tile pair is swept exactly once in the whole job: by the owner of the tile
              * that comes first on the Morton curve (storage index -> Morton tile index, see rad_deal_kernel) */
             const uint32_t mc = (c % tiles_per_rank) * world + c / tiles_per_rank;
-            ok = mc >= mrt && tile_pair_may_link(R, tb[c]);
+            ok = mc >= mrt && tile_pair_may_link(row_bounds, tb[c]);
         }
         if (ok) tile_list[atomicAdd(&tile_cnt, 1u)] = c;
       }
       __syncthreads();
       const unsigned n_list = tile_cnt;
-      /* software pipeline: the NEXT column tile (positions, normals, its four sub-tile bounds) is fetched
-       * into registers while the current one is swept from shared memory, so the L2 latency of the tile
-       * switch is hidden behind ~750 instructions of pair tests instead of being paid at every barrier
-       * (ncu before: IPC 1.07, long-scoreboard + short-scoreboard stalls dominate) */
-      float4 pf_p = make_float4(0, 0, 0, 0), pf_n = pf_p, pf_b = pf_p;
+      /* software pipeline: the NEXT column tile (positions, normals, group bounds) is fetched into
+       * registers while the current one is swept from shared memory */
+      float4 pf_p = make_float4(0, 0, 0, 0), pf_n = pf_p, pf_b0 = pf_p, pf_b1 = pf_p;
       if (n_list) {
         const uint32_t c0 = tile_list[0];
         pf_p = spos[(size_t)c0 * RAD_TILE + threadIdx.x]; pf_n = snrm[(size_t)c0 * RAD_TILE + threadIdx.x];
-        if (threadIdx.x < 16) pf_b = reinterpret_cast<const float4 *>(tb32 + (size_t)c0 * (RAD_TILE / 32))[threadIdx.x];
+        const float4 *gb = reinterpret_cast<const float4 *>(tbg + (size_t)c0 * NG);
+        if (threadIdx.x < GB4) pf_b0 = gb[threadIdx.x];
+        if (GB4 > RAD_TILE && threadIdx.x + RAD_TILE < GB4) pf_b1 = gb[threadIdx.x + RAD_TILE];
       }
       for (unsigned li = 0; li < n_list; ++li) {
         const uint32_t ct = tile_list[li];
         __syncthreads();
         sp[threadIdx.x] = pf_p; sn[threadIdx.x] = pf_n;
-        if (threadIdx.x < 16) reinterpret_cast<float4 *>(sub_bounds)[threadIdx.x] = pf_b;
+        if (threadIdx.x < GB4) reinterpret_cast<float4 *>(grp_bounds)[threadIdx.x] = pf_b0;
+        if (GB4 > RAD_TILE && threadIdx.x + RAD_TILE < GB4) reinterpret_cast<float4 *>(grp_bounds)[threadIdx.x + RAD_TILE] = pf_b1;
         if (threadIdx.x == 0) ++tile_loads;
         __syncthreads();
         if (li + 1 < n_list) {
             const uint32_t cn = tile_list[li + 1];
             pf_p = spos[(size_t)cn * RAD_TILE + threadIdx.x]; pf_n = snrm[(size_t)cn * RAD_TILE + threadIdx.x];
-            if (threadIdx.x < 16) pf_b = reinterpret_cast<const float4 *>(tb32 + (size_t)cn * (RAD_TILE / 32))[threadIdx.x];
+            const float4 *gb = reinterpret_cast<const float4 *>(tbg + (size_t)cn * NG);
+            if (threadIdx.x < GB4) pf_b0 = gb[threadIdx.x];
+            if (GB4 > RAD_TILE && threadIdx.x + RAD_TILE < GB4) pf_b1 = gb[threadIdx.x + RAD_TILE];
         }
-        const uint32_t k0 = (ct == rt) ? threadIdx.x + 1 : 0;             /* diagonal tile: each unordered pair once */
-        for (uint32_t sub = 0; sub < RAD_TILE / 32; ++sub) {
-        /* warp-level culling: my warp's 32 rows against this 32-lumel column sub-tile (warp-uniform branch) */
-        if (!tile_pair_may_link(Rw, sub_bounds[sub])) continue;
-        const uint32_t kb = sub * 32u > k0 ? sub * 32u : k0;
-#pragma unroll 4
-        for (uint32_t k = kb; k < sub * 32u + 32u; ++k) {
-            const V3 d = ld3(sp[k]) - Pr;
-            ++tested;
-            /* Fused-multiply-add pre-filter, ONE branch for both facing tests (a per-test early-out was
-             * measured 35 % slower: lanes disagree, the warp pays both paths).  99 % of the pairs fail by
-             * a wide margin; an FMA dot differs from the reference's mul/add dot by < 1e-5 for any pair
-             * close enough to link (|d| <= 17.85), so a value below 0.0009 cannot reach the exact 0.001
-             * threshold, and farther pairs fail the factor test anyway.  Survivors take the exact path. */
-            const V3 Nj = ld3(sn[k]);
-            const float drf = __fmaf_rn(Nr.z, d.z, __fmaf_rn(Nr.y, d.y, Nr.x * d.x));
-            const float djf = __fmaf_rn(Nj.z, d.z, __fmaf_rn(Nj.y, d.y, Nj.x * d.x));
-            if (fminf(drf, -djf) <= RAD_SKIP_BELOW) continue;
-            const float dr = dot3(Nr, d);
-            const float dj = -dot3(Nj, d);
-            if (dr <= LB_SMALL || dj <= LB_SMALL) continue;
-            const float lensq = lensq3(d);
-            const float f = dr * dj / (lensq * lensq * 3.14159274101257324f);
-            if (f < LB_SMALL) continue;
-            RadCand c; c.a = r; c.b = ct * RAD_TILE + k; c.factor = f;
-            const unsigned at = atomicAdd(&q_count, 1u);
-            if (at < RAD_QUEUE) queue[at] = c;
-            else {                                                        /* queue full: straight to global memory */
-                const unsigned long long g = atomicAdd(cand_count, 1ull);
-                if (g < cand_cap) cand[g] = c;
+        const bool diag = ct == rt;                                        /* diagonal tile: each unordered pair once (checked in the exact stage) */
+        /* warp x group culling, one group per lane */
+        unsigned gm = __ballot_sync(0xffffffffu, lane < (unsigned)NG && tile_pair_may_link(row_warp_bounds[warp], grp_bounds[lane < (unsigned)NG ? lane : 0]));
+        tested += (unsigned)__popc(gm) * G;                                /* per lane: pairs this lane goes on to test */
+        unsigned wcount = 0;                                               /* staged survivors of this warp (warp-uniform) */
+        while (gm) {
+            const unsigned g = (unsigned)__ffs(gm) - 1u;
+            gm &= gm - 1u;
+#pragma unroll 1
+            for (unsigned q0 = 0; q0 < (unsigned)G; q0 += CH) {
+#pragma unroll
+                for (unsigned q = 0; q < (unsigned)CH; ++q) {
+                    const unsigned k = g * G + q0 + q;
+                    const float4 pj = sp[k], nj = sn[k];
+                    const float dx = pj.x - Pr.x, dy = pj.y - Pr.y, dz = pj.z - Pr.z;
+                    /* fast filter: an FMA dot differs from the reference's mul/add dot by < 1e-5 for any pair close
+                     * enough to link (|d| <= 17.85), and the factor inequality dr*dj >= 0.001*pi*len^4 is evaluated
+                     * with relative error ~1e-6: with every threshold lowered by 10 % no linking pair is lost */
+                    const float drf = __fmaf_rn(Nr.z, dz, __fmaf_rn(Nr.y, dy, Nr.x * dx));
+                    const float djf = -__fmaf_rn(nj.z, dz, __fmaf_rn(nj.y, dy, nj.x * dx));
+                    const float l2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+                    const bool pass = fminf(drf, djf) > RAD_SKIP_BELOW && drf * djf >= (RAD_SKIP_BELOW * 3.14159265f) * (l2 * l2);
+                    const unsigned pm = __ballot_sync(0xffffffffu, pass);
+                    if (pm) {                                              /* warp-uniform */
+                        if (pass) stage[warp][wcount + __popc(pm & lt_mask)] = (uint16_t)((lane << 7) | k);
+                        wcount += (unsigned)__popc(pm);
+                    }
+                }
+                while (wcount >= 32u) {
+                    __syncwarp();
+                    wcount -= 32u;
+                    rad_exact_pair(stage[warp][wcount + lane], Pr, Nr, sp, sn, rt * RAD_TILE + warp * 32u, ct * RAD_TILE, true, diag, lane, lt_mask,
+                                   queue, &q_count, cand, cand_cap, cand_count);
+                }
             }
         }
+        if (wcount) {                                                     /* partial drain before the column tile is replaced */
+            __syncwarp();
+            rad_exact_pair(lane < wcount ? stage[warp][lane] : (uint16_t)0, Pr, Nr, sp, sn, rt * RAD_TILE + warp * 32u, ct * RAD_TILE, lane < wcount, diag, lane, lt_mask,
+                           queue, &q_count, cand, cand_cap, cand_count);
         }
         __syncthreads();
         if (q_count >= RAD_QUEUE / 2) {                                   /* CTA-uniform flush */
@@ -508,7 +599,7 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
     const uint64_t k0 = (uint64_t)my_t0 * RAD_TILE, k1 = (uint64_t)my_t1 * RAD_TILE, n_rows = k1 - k0;
 
     float4 *spos = nullptr, *snrm = nullptr, *diff = nullptr, *total = nullptr, *out = nullptr, *Es = nullptr, *Eo = nullptr, *lrgb_full = nullptr;
-    TileBounds *tb = nullptr, *tb32 = nullptr;
+    TileBounds *tb = nullptr, *tb32 = nullptr, *tbg = nullptr;
     uint32_t *mkeys = nullptr, *mkeys_alt = nullptr, *sidx = nullptr, *sidx_alt = nullptr;
     float *d_bounds = nullptr, *d_diffuse = nullptr, *d_emissive = nullptr;
     RadCand *cand = nullptr;
@@ -529,6 +620,9 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
 #define RAD_LAUNCHED() do { ctx->host_counters.kernel_launches++; RAD_CU(cudaGetLastError()); } while (0)
     /* LTR_TRACE=1: host-side phase timings on stderr (adds a stream sync per phase) */
     const bool trace = getenv("LTR_TRACE") != nullptr;
+    /* column group size of the warp-level culling (4, 8, 16 or 32 lumels); LTR_RAD_GROUP overrides for experiments */
+    int group = RAD_GROUP_DEFAULT;
+    if (const char *e = getenv("LTR_RAD_GROUP")) { const int g = atoi(e); if (g == 4 || g == 8 || g == 16 || g == 32) group = g; }
     struct timespec tr0; clock_gettime(CLOCK_MONOTONIC, &tr0);
 #define RAD_TRACE(label) do { if (trace) { cudaStreamSynchronize(st); struct timespec t_; clock_gettime(CLOCK_MONOTONIC, &t_); \
         fprintf(stderr, "[ltr rank %d] radiosity %-22s %8.2f ms\n", ctx->rank, label, (t_.tv_sec - tr0.tv_sec) * 1e3 + (t_.tv_nsec - tr0.tv_nsec) * 1e-6); tr0 = t_; } } while (0)
@@ -578,9 +672,15 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
         RAD_TRACE("morton sort");
         RAD_TRY(dev_alloc(ctx, &spos, n_pad)); RAD_TRY(dev_alloc(ctx, &snrm, n_pad));
         RAD_TRY(dev_alloc(ctx, &tb, n_tiles)); RAD_TRY(dev_alloc(ctx, &tb32, (size_t)n_tiles * (RAD_TILE / 32)));
+        if (group != 32) RAD_TRY(dev_alloc(ctx, &tbg, (size_t)n_tiles * (RAD_TILE / group)));
         rad_gather_kernel<<<grid_for(n_pad, 256), 256, 0, st>>>(ctx->d_lpos, ctx->d_lnrm, sidx, n, n_pad, spos, snrm);
         RAD_LAUNCHED();
-        rad_tile_bounds_kernel<<<n_tiles, RAD_TILE, 0, st>>>(spos, snrm, sidx, tb, tb32);
+        switch (group) {
+        case 4:  rad_tile_bounds_kernel<4><<<n_tiles, RAD_TILE, 0, st>>>(spos, snrm, sidx, tb, tb32, tbg); break;
+        case 8:  rad_tile_bounds_kernel<8><<<n_tiles, RAD_TILE, 0, st>>>(spos, snrm, sidx, tb, tb32, tbg); break;
+        case 16: rad_tile_bounds_kernel<16><<<n_tiles, RAD_TILE, 0, st>>>(spos, snrm, sidx, tb, tb32, tbg); break;
+        default: rad_tile_bounds_kernel<32><<<n_tiles, RAD_TILE, 0, st>>>(spos, snrm, sidx, tb, tb32, tb32); break;
+        }
         RAD_LAUNCHED();
 
         /* ---- 2-4. candidates and visibility, in batches of row tiles bounded by the candidate buffer ---- */
@@ -603,10 +703,17 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
             RAD_CU(cudaMemsetAsync(d_cnt, 0, 32, st));
             RAD_CU(cudaEventRecord(ctx->ev_k0, st));
             {
-                const uint32_t resident = (uint32_t)ctx->num_sms * 9;             /* 9 CTAs of 128 threads fit per SM (56 regs, 21 KB smem) */
+                const uint32_t resident = (uint32_t)ctx->num_sms * 8;             /* 8 CTAs of 128 threads per SM (<= 64 regs, ~20 KB smem) */
                 const uint32_t grid = (t1 - t0) < resident ? (t1 - t0) : resident;
-                rad_candidates_kernel<<<grid, RAD_TILE, 0, st>>>(spos, snrm, tb, tb32, n_tiles, world, tiles_per_rank, t0, t1 - t0,
-                                                                 (uint32_t *)(d_cnt + 3), cand, cand_cap, d_cnt, ctx->d_counters);
+#define RAD_SWEEP(GS, TBG) rad_candidates_kernel<GS><<<grid, RAD_TILE, 0, st>>>(spos, snrm, tb, tb32, TBG, n_tiles, world, tiles_per_rank, t0, t1 - t0, \
+                                                                 (uint32_t *)(d_cnt + 3), cand, cand_cap, d_cnt, ctx->d_counters)
+                switch (group) {
+                case 4:  RAD_SWEEP(4, tbg); break;
+                case 8:  RAD_SWEEP(8, tbg); break;
+                case 16: RAD_SWEEP(16, tbg); break;
+                default: RAD_SWEEP(32, tb32); break;
+                }
+#undef RAD_SWEEP
             }
             RAD_LAUNCHED();
             RAD_CU(cudaEventRecord(ctx->ev_k1, st));
@@ -759,7 +866,7 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
         rc = 0;
     }
 done:
-    lb_free(spos); lb_free(snrm); lb_free(diff); lb_free(total); lb_free(out); lb_free(Es); lb_free(Eo); lb_free(tb); lb_free(tb32);
+    lb_free(spos); lb_free(snrm); lb_free(diff); lb_free(total); lb_free(out); lb_free(Es); lb_free(Eo); lb_free(tb); lb_free(tb32); lb_free(tbg);
     lb_free(mkeys); lb_free(mkeys_alt); lb_free(sidx); lb_free(sidx_alt); lb_free(d_bounds);
     lb_free(d_diffuse); lb_free(d_emissive); lb_free(cand); lb_free(d_cnt); lb_free(keys); lb_free(keys_alt);
     lb_free(fac); lb_free(fac_alt); lb_free(sort_tmp); lb_free(mirror); lb_free(mirror_all); lb_free(d_mcounts);

@@ -151,6 +151,43 @@ def test_radiosity_links_equal_reference(bakes):
     assert st["n_rad_links"] == 62684 and st["n_rad_segments"] == 288042           # 288 042 segments, one per pair i<j
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("group", [4, 8, 16, 32])
+def test_radiosity_pair_sweep_group_sizes(group, bakes, monkeypatch):
+    """The warp x group culling and the fast pre-filter of the pair sweep are exact: every group size
+    yields the reference's candidate segments, links and factors (rad1 and a config-4 sibling)."""
+    monkeypatch.setenv("LTR_RAD_GROUP", str(group))
+    out = api.bake(scenes.scene_rad1(), debug=True)
+    st, lk = out["stats"], out["links"]
+    assert st["n_rad_links"] == 62684 and st["n_rad_segments"] == 288042
+    li, lj, lf = bakes["rad1_link_i"], bakes["rad1_link_j"], bakes["rad1_link_f"]
+    rows = np.repeat(np.arange(lk["rows"], dtype=np.uint32), np.diff(lk["row_offset"]).astype(np.int64))
+    fwd = rows < lk["other"]
+    assert np.array_equal(rows[fwd], li) and np.array_equal(lk["other"][fwd], lj) and bits_equal(lk["factor"][fwd], lf)
+
+
+def test_radiosity_pair_sweep_group_sizes_agree_on_config4_sibling(monkeypatch):
+    """Same candidate segments, links and bit-identical lightmaps for every group size on a scene with
+    walls, pillars and terrain; and the reference's texels when oracle/_ref is on the box."""
+    sc = scenes.workload("config4_sibling")
+    base = None
+    for group in (32, 16, 8, 4):
+        monkeypatch.setenv("LTR_RAD_GROUP", str(group))
+        out = api.bake(sc)
+        key = (out["stats"]["n_rad_segments"], out["stats"]["n_rad_links"])
+        if base is None:
+            base = (key, out)
+            assert key[0] > 0 and key[1] > 0
+            continue
+        assert key == base[0], (group, key, base[0])
+        for a, b in zip(out["lightmaps"], base[1]["lightmaps"]):
+            assert bits_equal(a["rgb"], b["rgb"]), group
+    if parity.have_reference():
+        ref = parity.run_reference(sc, threads=1, internals=False)
+        for a, b in zip(base[1]["lightmaps"], ref["lightmaps"]):
+            assert parity.meets_bar(parity.texel_parity(a["rgb"], b["rgb"]))
+
+
 def test_ray_counts_equal_reference_instrumented_counts():
     """SURVEY 3.3 work counts of the reference on mesh1 (instrumented copy): 19 735 marches,
     422 636 distance queries, 161 466 AO segments, 9 498 correction rays."""
