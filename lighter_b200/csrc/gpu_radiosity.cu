@@ -30,6 +30,7 @@
 #include "gpu_internal.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <stdlib.h>
 #include <time.h>
 
@@ -188,10 +189,44 @@ __device__ __forceinline__ bool tile_pair_may_link(const TileBounds &R, const Ti
     return true;
 }
 
+/* ---- mbarrier / bulk-copy (TMA 1-D) primitives: one lane stages a column tile, the warp waits on the barrier ---- */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+#define RAD_STAGE 288            /* per-warp stage: 31 left over + 8 pairs x 32 lanes, (row lane << 7 | k) each */
+#define RAD_CHUNK 1024u          /* candidate slots a warp reserves from the global counter at a time */
+#define RAD_WARPS 4              /* warps per CTA; the warps do not interact */
+
+template <int G> struct __align__(128) RadColBuf {          /* one staged column tile */
+    float4 sp[RAD_TILE], sn[RAD_TILE];
+    TileBounds gb[RAD_TILE / G];
+};
+
+/* Output cursor of one warp into the global candidate array: slots are reserved RAD_CHUNK at a time (one
+ * global atomic per 1024 candidates), unused slots of a chunk are marked RAD_PAD for the visibility pass. */
+struct RadOut { unsigned long long pos, end; bool dead; };
+
+__device__ __forceinline__ void rad_out_pad(RadOut &o, RadCand *__restrict__ cand, unsigned lane)
+{
+    for (unsigned long long e = o.pos + lane; e < o.end; e += 32) cand[e].a = RAD_PAD;
+    o.pos = o.end;
+}
+
 /* Exact evaluation of one staged pair per lane (the reference's arithmetic, lighter.cpp:735-750) and
- * warp-aggregated append of the linking ones to the CTA's candidate queue.  `e` = (row lane << 7) | k. */
+ * warp-aggregated append of the linking ones.  `e` = (row lane << 7) | k. */
 __device__ __forceinline__ void rad_exact_pair(unsigned e, const V3 &Pr, const V3 &Nr, const float4 *sp, const float4 *sn, uint32_t row_base, uint32_t col_base,
-                                               bool valid, bool diag, unsigned lane, unsigned lt_mask, RadCand *queue, unsigned *q_count,
+                                               bool valid, bool diag, unsigned lane, unsigned lt_mask, RadOut &o,
                                                RadCand *__restrict__ cand, unsigned long long cand_cap, unsigned long long *cand_count)
 {
     const unsigned rl = e >> 7, k = e & 0x7fu;
@@ -213,190 +248,238 @@ __device__ __forceinline__ void rad_exact_pair(unsigned e, const V3 &Pr, const V
     }
     const unsigned okm = __ballot_sync(0xffffffffu, ok);
     if (!okm) return;
-    unsigned qb = 0;
-    if (lane == 0) qb = atomicAdd(q_count, (unsigned)__popc(okm));
-    qb = __shfl_sync(0xffffffffu, qb, 0);
-    const unsigned at = qb + __popc(okm & lt_mask);
-    const bool spill = ok && at >= RAD_QUEUE;                             /* queue full: straight to global memory */
-    if (ok && !spill) queue[at] = c;
-    const unsigned sm = __ballot_sync(0xffffffffu, spill);
-    if (sm) {
-        unsigned long long gb = 0;
-        if (lane == 0) gb = atomicAdd(cand_count, (unsigned long long)__popc(sm));
-        gb = __shfl_sync(0xffffffffu, gb, 0);
-        const unsigned long long g = gb + __popc(sm & lt_mask);
-        if (spill && g < cand_cap) cand[g] = c;
+    const unsigned m = (unsigned)__popc(okm);
+    if (o.pos + m > o.end) {                                              /* warp-uniform: next chunk */
+        if (!o.dead) rad_out_pad(o, cand, lane);
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cand_count, (unsigned long long)RAD_CHUNK);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        o.dead = base + RAD_CHUNK > cand_cap;                             /* the host sees count > capacity and redoes the batch smaller */
+        o.pos = base; o.end = base + RAD_CHUNK;
     }
+    if (ok && !o.dead) cand[o.pos + __popc(okm & lt_mask)] = c;
+    o.pos += m;
 }
 
-/*
- * Pair sweep.  One CTA = one row tile at a time (128 threads = 128 row lumels held in registers),
- * persistent over a cursor of row tiles; sweeps the column tiles.  Tile pairs are visited once:
- * column tile ct >= row tile rt on the Morton curve, whichever rank owns the column tile.
- *
- * Three levels of exact culling, then a two-phase pair test:
- *   tile x tile     one thread per column tile (128 per round), survivors compacted into tile_list;
- *   warp x group    a column tile is staged in shared memory together with the bounds of its 128/G
- *                   groups of G lumels; each lane of a warp tests the warp's 32 rows against one
- *                   group (all groups in parallel), the ballot is the list of groups to sweep;
- *   lumel x lumel   FAST filter, all 32 lanes in lock step: FMA dots and the factor inequality
- *                   without the division, thresholds lowered by 10 % so that rounding differences to
- *                   the exact arithmetic can only let extra pairs through, never drop one.  Survivors
- *                   (~3 % of the pairs) are appended to a per-warp stage by ballot/popc;
- *   drain           whenever 32 survivors are staged, the warp evaluates them one per lane with the
- *                   reference's exact operation order (mul/add dots, IEEE division) -- full SIMT
- *                   efficiency on the expensive path, which a per-pair branch does not have (measured
- *                   before: 60 warp instructions per 32 pairs, 80 % of them in half-empty slow paths).
- */
-#define RAD_STAGE 288            /* per-warp stage: 31 left over + 8 pairs x 32 lanes, (row lane << 7 | k) each */
-
+/* Sweep one staged column tile against the warp's 32 row lumels. */
 template <int G>
-__global__ void __launch_bounds__(RAD_TILE)
-rad_candidates_kernel(const float4 *__restrict__ spos, const float4 *__restrict__ snrm, const TileBounds *__restrict__ tb,
-                      const TileBounds *__restrict__ tb32, const TileBounds *__restrict__ tbg,
-                      uint32_t n_tiles, uint32_t world, uint32_t tiles_per_rank, uint32_t first_row_tile, uint32_t n_row_tiles,
-                      uint32_t *row_cursor, RadCand *__restrict__ cand, unsigned long long cand_cap, unsigned long long *cand_count, unsigned long long *counters)
+__device__ __forceinline__ void rad_sweep_tile(const RadColBuf<G> &B, const TileBounds &Rw, uint16_t *stage, const V3 &Pr, const V3 &Nr,
+                                               uint32_t row_base, uint32_t ct, bool diag, unsigned lane, unsigned lt_mask, RadOut &o, unsigned &tested,
+                                               RadCand *__restrict__ cand, unsigned long long cand_cap, unsigned long long *cand_count)
 {
-    constexpr int NG = RAD_TILE / G;                       /* groups per column tile (<= 32: one per lane) */
-    constexpr int GB4 = NG * 4;                            /* float4s of group bounds per column tile */
+    constexpr int NG = RAD_TILE / G;
     constexpr int CH = G < 8 ? G : 8;                      /* pairs per lane between two drain checks */
-    static_assert(NG <= 32 && GB4 <= 2 * RAD_TILE, "group size too small");
-    __shared__ float4 sp[RAD_TILE], sn[RAD_TILE];
-    __shared__ TileBounds grp_bounds[NG];
-    __shared__ RadCand queue[RAD_QUEUE];
-    __shared__ uint16_t stage[RAD_TILE / 32][RAD_STAGE];
-    __shared__ TileBounds row_bounds, row_warp_bounds[RAD_TILE / 32];
-    __shared__ unsigned q_count;
-    __shared__ unsigned long long q_base;
-    __shared__ uint32_t tile_list[RAD_TILE];
-    __shared__ unsigned tile_cnt;
-    __shared__ uint32_t next_row_tile;
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    unsigned tested = 0, tile_loads = 0;
-    if (threadIdx.x == 0) q_count = 0;
-    /* persistent CTAs: row tiles cost anything from nothing (open floor far from geometry) to
-     * thousands of column tiles (next to walls), so CTAs pull the next row tile from a cursor
-     * instead of owning one each -- the tail of a launch is then one tile, not the worst SM's sum */
-    for (;;) {
-    __syncthreads();
-    if (threadIdx.x == 0) next_row_tile = atomicAdd(row_cursor, 1u);
-    __syncthreads();
-    if (next_row_tile >= n_row_tiles) break;
-    const uint32_t rt = first_row_tile + next_row_tile;
-    const uint32_t r = rt * RAD_TILE + threadIdx.x;
-    const V3 Pr = ld3(spos[r]), Nr = ld3(snrm[r]);
-    if (threadIdx.x < 4) reinterpret_cast<float4 *>(&row_bounds)[threadIdx.x] = reinterpret_cast<const float4 *>(tb + rt)[threadIdx.x];
-    if (threadIdx.x < 16) reinterpret_cast<float4 *>(row_warp_bounds)[threadIdx.x] = reinterpret_cast<const float4 *>(tb32 + (size_t)rt * (RAD_TILE / 32))[threadIdx.x];
-    const uint32_t mrt = (rt % tiles_per_rank) * world + rt / tiles_per_rank;
-    for (uint32_t base = 0; base < n_tiles; base += RAD_TILE) {
-      /* cooperative culling: each thread tests ONE column tile of this chunk, survivors are compacted */
-      __syncthreads();
-      if (threadIdx.x == 0) tile_cnt = 0;
-      __syncthreads();
-      {
-        const uint32_t c = base + threadIdx.x;
-        bool ok = c < n_tiles;
-        if (ok) {
-            /* every unordered tile pair is swept exactly once in the whole job: by the owner of the tile
-             * that comes first on the Morton curve (storage index -> Morton tile index, see rad_deal_kernel) */
-            const uint32_t mc = (c % tiles_per_rank) * world + c / tiles_per_rank;
-            ok = mc >= mrt && tile_pair_may_link(row_bounds, tb[c]);
-        }
-        if (ok) tile_list[atomicAdd(&tile_cnt, 1u)] = c;
-      }
-      __syncthreads();
-      const unsigned n_list = tile_cnt;
-      /* software pipeline: the NEXT column tile (positions, normals, group bounds) is fetched into
-       * registers while the current one is swept from shared memory */
-      float4 pf_p = make_float4(0, 0, 0, 0), pf_n = pf_p, pf_b0 = pf_p, pf_b1 = pf_p;
-      if (n_list) {
-        const uint32_t c0 = tile_list[0];
-        pf_p = spos[(size_t)c0 * RAD_TILE + threadIdx.x]; pf_n = snrm[(size_t)c0 * RAD_TILE + threadIdx.x];
-        const float4 *gb = reinterpret_cast<const float4 *>(tbg + (size_t)c0 * NG);
-        if (threadIdx.x < GB4) pf_b0 = gb[threadIdx.x];
-        if (GB4 > RAD_TILE && threadIdx.x + RAD_TILE < GB4) pf_b1 = gb[threadIdx.x + RAD_TILE];
-      }
-      for (unsigned li = 0; li < n_list; ++li) {
-        const uint32_t ct = tile_list[li];
-        __syncthreads();
-        sp[threadIdx.x] = pf_p; sn[threadIdx.x] = pf_n;
-        if (threadIdx.x < GB4) reinterpret_cast<float4 *>(grp_bounds)[threadIdx.x] = pf_b0;
-        if (GB4 > RAD_TILE && threadIdx.x + RAD_TILE < GB4) reinterpret_cast<float4 *>(grp_bounds)[threadIdx.x + RAD_TILE] = pf_b1;
-        if (threadIdx.x == 0) ++tile_loads;
-        __syncthreads();
-        if (li + 1 < n_list) {
-            const uint32_t cn = tile_list[li + 1];
-            pf_p = spos[(size_t)cn * RAD_TILE + threadIdx.x]; pf_n = snrm[(size_t)cn * RAD_TILE + threadIdx.x];
-            const float4 *gb = reinterpret_cast<const float4 *>(tbg + (size_t)cn * NG);
-            if (threadIdx.x < GB4) pf_b0 = gb[threadIdx.x];
-            if (GB4 > RAD_TILE && threadIdx.x + RAD_TILE < GB4) pf_b1 = gb[threadIdx.x + RAD_TILE];
-        }
-        const bool diag = ct == rt;                                        /* diagonal tile: each unordered pair once (checked in the exact stage) */
-        /* warp x group culling, one group per lane */
-        unsigned gm = __ballot_sync(0xffffffffu, lane < (unsigned)NG && tile_pair_may_link(row_warp_bounds[warp], grp_bounds[lane < (unsigned)NG ? lane : 0]));
-        tested += (unsigned)__popc(gm) * G;                                /* per lane: pairs this lane goes on to test */
-        unsigned wcount = 0;                                               /* staged survivors of this warp (warp-uniform) */
-        while (gm) {
-            const unsigned g = (unsigned)__ffs(gm) - 1u;
-            gm &= gm - 1u;
+    /* warp x group culling, one group per lane */
+    unsigned gm = __ballot_sync(0xffffffffu, lane < (unsigned)NG && tile_pair_may_link(Rw, B.gb[lane < (unsigned)NG ? lane : 0]));
+    tested += (unsigned)__popc(gm) * G;                    /* per lane: pairs this lane goes on to test */
+    unsigned wcount = 0;                                   /* staged survivors (warp-uniform) */
+    while (gm) {
+        const unsigned g = (unsigned)__ffs(gm) - 1u;
+        gm &= gm - 1u;
 #pragma unroll 1
-            for (unsigned q0 = 0; q0 < (unsigned)G; q0 += CH) {
+        for (unsigned q0 = 0; q0 < (unsigned)G; q0 += CH) {
+            const unsigned kb = g * G + q0;
+            unsigned bits = 0;
 #pragma unroll
-                for (unsigned q = 0; q < (unsigned)CH; ++q) {
-                    const unsigned k = g * G + q0 + q;
-                    const float4 pj = sp[k], nj = sn[k];
-                    const float dx = pj.x - Pr.x, dy = pj.y - Pr.y, dz = pj.z - Pr.z;
-                    /* fast filter: an FMA dot differs from the reference's mul/add dot by < 1e-5 for any pair close
-                     * enough to link (|d| <= 17.85), and the factor inequality dr*dj >= 0.001*pi*len^4 is evaluated
-                     * with relative error ~1e-6: with every threshold lowered by 10 % no linking pair is lost */
-                    const float drf = __fmaf_rn(Nr.z, dz, __fmaf_rn(Nr.y, dy, Nr.x * dx));
-                    const float djf = -__fmaf_rn(nj.z, dz, __fmaf_rn(nj.y, dy, nj.x * dx));
-                    const float l2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-                    const bool pass = fminf(drf, djf) > RAD_SKIP_BELOW && drf * djf >= (RAD_SKIP_BELOW * 3.14159265f) * (l2 * l2);
-                    const unsigned pm = __ballot_sync(0xffffffffu, pass);
-                    if (pm) {                                              /* warp-uniform */
-                        if (pass) stage[warp][wcount + __popc(pm & lt_mask)] = (uint16_t)((lane << 7) | k);
-                        wcount += (unsigned)__popc(pm);
-                    }
+            for (unsigned q = 0; q < (unsigned)CH; ++q) {
+                const float4 pj = B.sp[kb + q], nj = B.sn[kb + q];
+                const float dx = pj.x - Pr.x, dy = pj.y - Pr.y, dz = pj.z - Pr.z;
+                /* fast filter: an FMA dot differs from the reference's mul/add dot by < 1e-5 for any pair close
+                 * enough to link (|d| <= 17.85), and the factor inequality dr*dj >= 0.001*pi*len^4 is evaluated
+                 * with relative error ~1e-6: with every threshold lowered by 10 % no linking pair is lost */
+                const float drf = __fmaf_rn(Nr.z, dz, __fmaf_rn(Nr.y, dy, Nr.x * dx));
+                const float djf = -__fmaf_rn(nj.z, dz, __fmaf_rn(nj.y, dy, nj.x * dx));
+                const float l2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+                if (fminf(drf, djf) > RAD_SKIP_BELOW && drf * djf >= (RAD_SKIP_BELOW * 3.14159265f) * (l2 * l2)) bits |= 1u << q;
+            }
+            if (__any_sync(0xffffffffu, bits != 0)) {
+                /* compaction: exclusive scan of the per-lane survivor counts, then every lane appends its own */
+                const unsigned cnt = (unsigned)__popc(bits);
+                unsigned incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (unsigned)d) incl += t; }
+                unsigned at = wcount + incl - cnt;
+                wcount += __shfl_sync(0xffffffffu, incl, 31);
+                while (bits) {
+                    const unsigned q = (unsigned)__ffs(bits) - 1u;
+                    bits &= bits - 1u;
+                    stage[at++] = (uint16_t)((lane << 7) | (kb + q));
                 }
                 while (wcount >= 32u) {
                     __syncwarp();
                     wcount -= 32u;
-                    rad_exact_pair(stage[warp][wcount + lane], Pr, Nr, sp, sn, rt * RAD_TILE + warp * 32u, ct * RAD_TILE, true, diag, lane, lt_mask,
-                                   queue, &q_count, cand, cand_cap, cand_count);
+                    rad_exact_pair(stage[wcount + lane], Pr, Nr, B.sp, B.sn, row_base, ct * RAD_TILE, true, diag, lane, lt_mask, o, cand, cand_cap, cand_count);
                 }
+                __syncwarp();
             }
         }
-        if (wcount) {                                                     /* partial drain before the column tile is replaced */
-            __syncwarp();
-            rad_exact_pair(lane < wcount ? stage[warp][lane] : (uint16_t)0, Pr, Nr, sp, sn, rt * RAD_TILE + warp * 32u, ct * RAD_TILE, lane < wcount, diag, lane, lt_mask,
-                           queue, &q_count, cand, cand_cap, cand_count);
-        }
-        __syncthreads();
-        if (q_count >= RAD_QUEUE / 2) {                                   /* CTA-uniform flush */
-            const unsigned cnt = q_count < RAD_QUEUE ? q_count : RAD_QUEUE;
-            if (threadIdx.x == 0) q_base = atomicAdd(cand_count, (unsigned long long)cnt);
-            __syncthreads();
-            for (unsigned e = threadIdx.x; e < cnt; e += RAD_TILE) if (q_base + e < cand_cap) cand[q_base + e] = queue[e];
-            __syncthreads();
-            if (threadIdx.x == 0) q_count = 0;
-        }
-      }
     }
-    }   /* next row tile */
-    __syncthreads();
-    {
-        const unsigned cnt = q_count < RAD_QUEUE ? q_count : RAD_QUEUE;
-        if (cnt) {
-            if (threadIdx.x == 0) q_base = atomicAdd(cand_count, (unsigned long long)cnt);
-            __syncthreads();
-            for (unsigned e = threadIdx.x; e < cnt; e += RAD_TILE) if (q_base + e < cand_cap) cand[q_base + e] = queue[e];
+    if (wcount) {                                          /* partial drain before the buffer is reused */
+        __syncwarp();
+        rad_exact_pair(lane < wcount ? stage[lane] : (uint16_t)0, Pr, Nr, B.sp, B.sn, row_base, ct * RAD_TILE, lane < wcount, diag, lane, lt_mask, o, cand, cand_cap, cand_count);
+    }
+    __syncwarp();
+}
+
+/*
+ * Pair sweep.  The unit of work is a ROW WARP: 32 consecutive (Morton-sorted) lumels, one per lane, held
+ * in registers.  Warps are persistent and independent -- each pulls row warps from a global cursor, so a
+ * warp next to a wall (thousands of column tiles) never holds up its neighbours over open floor, and
+ * there is not a single CTA barrier in the kernel (the previous CTA-per-row-tile version spent most of
+ * its time in barriers with one busy warp out of four).
+ *
+ * Per row warp, four levels of exact culling (interval bounds: no linking pair is ever rejected), then
+ * a two-phase pair test:
+ *   warp x super-tile   32 super-tiles (32 Morton-consecutive tiles = 4096 lumels each) per step, one per lane;
+ *   warp x tile         the 32 tiles of a surviving super-tile, one per lane; a tile pair is swept once in
+ *                       the whole job: by the owner of the tile that comes first on the Morton curve;
+ *   staging             surviving column tiles (positions, normals, group bounds: 5 KB) are brought into
+ *                       this warp's shared-memory double buffer by 1-D bulk copies (TMA) that complete on an
+ *                       mbarrier; the copy of tile i+1 is in flight while tile i is swept;
+ *   warp x group        each lane tests the warp's rows against one group of G column lumels;
+ *   lumel x lumel       FAST filter, all 32 lanes in lock step, no branches: FMA dots and the factor
+ *                       inequality without the division, thresholds lowered by 10 % so that rounding
+ *                       differences to the exact arithmetic can only let extra pairs through.  Survivors
+ *                       (~3 % of the pairs) are compacted into a per-warp stage;
+ *   drain               every 32 staged survivors are evaluated one per lane with the reference's exact
+ *                       operation order (mul/add dots, IEEE division) -- full SIMT efficiency on the
+ *                       expensive path -- and the linking ones appended to the global candidate array.
+ */
+template <int G>
+__global__ void __launch_bounds__(RAD_WARPS * 32)
+rad_candidates_kernel(const float4 *__restrict__ spos, const float4 *__restrict__ snrm, const TileBounds *__restrict__ tb,
+                      const TileBounds *__restrict__ tb32, const TileBounds *__restrict__ tbg, const TileBounds *__restrict__ tbs,
+                      uint32_t n_tiles, uint32_t world, uint32_t tiles_per_rank, const uint2 *__restrict__ items, uint32_t n_items,
+                      uint32_t *item_cursor, RadCand *__restrict__ cand, unsigned long long cand_cap, unsigned long long *cand_count, unsigned long long *counters)
+{
+    constexpr int NG = RAD_TILE / G;
+    constexpr uint32_t TILE_BYTES = RAD_TILE * 16u, GB_BYTES = NG * (uint32_t)sizeof(TileBounds);
+    extern __shared__ __align__(128) unsigned char rad_smem[];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    RadColBuf<G> *buf = reinterpret_cast<RadColBuf<G> *>(rad_smem) + warp * 2;
+    unsigned char *tail = rad_smem + sizeof(RadColBuf<G>) * 2 * RAD_WARPS;
+    TileBounds *Rw = reinterpret_cast<TileBounds *>(tail) + warp;                                  tail += sizeof(TileBounds) * RAD_WARPS;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tail) + warp * 2;                                 tail += 8 * 2 * RAD_WARPS;
+    uint16_t *stage = reinterpret_cast<uint16_t *>(tail) + warp * RAD_STAGE;
+    const uint32_t bar0 = smem_u32(bar);                   /* barrier of buffer b: bar0 + 8 b */
+    if (lane == 0) {
+        mbar_init(bar0, 1); mbar_init(bar0 + 8u, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    unsigned parity = 0;                                   /* bit b: phase parity buffer b's barrier completes next */
+    unsigned nb = 0;                                       /* buffer the next copy goes into */
+    RadOut o = { 0, 0, false };
+    unsigned tested = 0, tile_loads = 0;
+    for (;;) {
+        uint32_t it = 0;
+        if (lane == 0) it = atomicAdd(item_cursor, 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= n_items) break;
+        const uint2 item = items[it];
+        const uint32_t rw = item.x;                        /* rows rw*32 .. rw*32+31 (storage order) */
+        const uint32_t rt = rw / (RAD_TILE / 32);
+        const V3 Pr = ld3(spos[(size_t)rw * 32 + lane]), Nr = ld3(snrm[(size_t)rw * 32 + lane]);
+        __syncwarp();
+        if (lane < 4) reinterpret_cast<float4 *>(Rw)[lane] = reinterpret_cast<const float4 *>(tb32 + rw)[lane];
+        __syncwarp();
+        const uint32_t mrt = (rt % tiles_per_rank) * world + rt / tiles_per_rank;       /* my tile's index on the Morton curve */
+        const uint32_t mt = item.y * 32u + lane;           /* Morton tile index -> storage index (see rad_deal_kernel) */
+        const uint32_t c = (mt % world) * tiles_per_rank + mt / world;
+        unsigned tmask = __ballot_sync(0xffffffffu, mt < n_tiles && mt >= mrt && tile_pair_may_link(*Rw, tb[mt < n_tiles ? c : 0]));
+        int pend = -1;
+        while (tmask) {
+            const unsigned tl = (unsigned)__ffs(tmask) - 1u;
+            tmask &= tmask - 1u;
+            const uint32_t ct = __shfl_sync(0xffffffffu, c, tl);
+            if (lane == 0) {                               /* stage column tile ct into buf[nb] */
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                const uint32_t ba = bar0 + 8u * nb;
+                mbar_expect_tx(ba, 2u * TILE_BYTES + GB_BYTES);
+                bulk_g2s(smem_u32(buf[nb].sp), spos + (size_t)ct * RAD_TILE, TILE_BYTES, ba);
+                bulk_g2s(smem_u32(buf[nb].sn), snrm + (size_t)ct * RAD_TILE, TILE_BYTES, ba);
+                bulk_g2s(smem_u32(buf[nb].gb), tbg + (size_t)ct * NG, GB_BYTES, ba);
+                ++tile_loads;
+            }
+            if (pend >= 0) {
+                const unsigned pb = nb ^ 1u;
+                while (!mbar_try_wait(bar0 + 8u * pb, (parity >> pb) & 1u)) { }
+                parity ^= 1u << pb;
+                rad_sweep_tile<G>(buf[pb], *Rw, stage, Pr, Nr, rw * 32u, (uint32_t)pend, (uint32_t)pend == rt, lane, lt_mask, o, tested, cand, cand_cap, cand_count);
+            }
+            pend = (int)ct;
+            nb ^= 1u;
+        }
+        if (pend >= 0) {
+            const unsigned pb = nb ^ 1u;
+            while (!mbar_try_wait(bar0 + 8u * pb, (parity >> pb) & 1u)) { }
+            parity ^= 1u << pb;
+            rad_sweep_tile<G>(buf[pb], *Rw, stage, Pr, Nr, rw * 32u, (uint32_t)pend, (uint32_t)pend == rt, lane, lt_mask, o, tested, cand, cand_cap, cand_count);
         }
     }
+    if (!o.dead) rad_out_pad(o, cand, lane);
     count_add(counters, CNT_RAD_PAIRS, tested);
     count_add(counters, CNT_RAD_TILE_LOADS, tile_loads);
 }
+
+/* bounds of every super-tile = 32 consecutive tiles ON THE MORTON CURVE (storage order deals tiles round-robin to ranks) */
+__global__ void rad_super_bounds_kernel(const TileBounds *__restrict__ tb, uint32_t n_tiles, uint32_t n_super, uint32_t world, uint32_t tiles_per_rank,
+                                        TileBounds *__restrict__ tbs)
+{
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (s >= n_super) return;
+    const uint32_t mt = s * 32u + lane;
+    float v[12];
+    for (int a = 0; a < 6; ++a) { v[a] = INFINITY; v[6 + a] = -INFINITY; }
+    if (mt < n_tiles) {
+        const TileBounds t = tb[(mt % world) * tiles_per_rank + mt / world];
+        v[0] = t.plo.x; v[1] = t.plo.y; v[2] = t.plo.z; v[3] = t.nlo.x; v[4] = t.nlo.y; v[5] = t.nlo.z;
+        v[6] = t.phi.x; v[7] = t.phi.y; v[8] = t.phi.z; v[9] = t.nhi.x; v[10] = t.nhi.y; v[11] = t.nhi.z;
+    }
+#pragma unroll
+    for (int a = 0; a < 12; ++a)
+        for (int o = 16; o > 0; o >>= 1) {
+            const float t = __shfl_xor_sync(0xffffffffu, v[a], o);
+            v[a] = a < 6 ? fminf(v[a], t) : fmaxf(v[a], t);
+        }
+    if (lane == 0) {
+        TileBounds w;
+        w.plo = make_float4(v[0], v[1], v[2], 0.f); w.nlo = make_float4(v[3], v[4], v[5], 0.f);
+        w.phi = make_float4(v[6], v[7], v[8], 0.f); w.nhi = make_float4(v[9], v[10], v[11], 0.f);
+        tbs[s] = w;
+    }
+}
+
+/*
+ * Work items of the pair sweep: (row warp, super-tile) pairs that survive the interval test.  One warp per
+ * row warp, 32 super-tiles per step (one per lane).  FILL = false counts, FILL = true writes the items at
+ * the scanned offsets -- row-warp-major, so warps running at the same time sweep neighbouring rows against
+ * the same column tiles (L2 locality).  An item is at most 32 column tiles of work, which bounds the tail of
+ * a launch; a whole row warp next to a wall is ~400 tiles = milliseconds.
+ */
+template <bool FILL>
+__global__ void rad_items_kernel(const TileBounds *__restrict__ tb32, const TileBounds *__restrict__ tbs, uint32_t n_super, uint32_t world, uint32_t tiles_per_rank,
+                                 uint32_t first_row_warp, uint32_t n_row_warps, uint32_t *__restrict__ counts, const uint32_t *__restrict__ offsets, uint2 *__restrict__ items)
+{
+    const uint32_t rwi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (rwi >= n_row_warps) return;
+    const uint32_t rw = first_row_warp + rwi, rt = rw / (RAD_TILE / 32);
+    const TileBounds R = tb32[rw];
+    const uint32_t mrt = (rt % tiles_per_rank) * world + rt / tiles_per_rank;
+    uint32_t n = 0;
+    const uint32_t off = FILL ? offsets[rwi] : 0u;
+    for (uint32_t sbase = (mrt / 32u) & ~31u; sbase < n_super; sbase += 32u) {
+        const uint32_t s = sbase + lane;
+        const bool ok = s < n_super && s * 32u + 31u >= mrt && tile_pair_may_link(R, tbs[s < n_super ? s : 0]);
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (FILL && ok) items[off + n + __popc(m & ((1u << lane) - 1u))] = make_uint2(rw, s);
+        n += (uint32_t)__popc(m);
+    }
+    if (!FILL && lane == 0) counts[rwi] = n;
+}
+
+template <int G> static size_t rad_sweep_smem() { return sizeof(RadColBuf<G>) * 2 * RAD_WARPS + sizeof(TileBounds) * RAD_WARPS + 16 * RAD_WARPS + 2 * RAD_STAGE * RAD_WARPS; }
 
 /* one thread per candidate: blocked segment -> directed link(s) keyed (row sorted position, partner original index) */
 __global__ void __launch_bounds__(LB_BLOCK)
@@ -416,6 +499,8 @@ rad_visibility_kernel(const BvhNode *__restrict__ bvh, const RayTri *__restrict_
         uint32_t oa = 0, ob = 0;
         if (e < n_cand) {
             c = cand[e];
+        }
+        if (e < n_cand && c.a != RAD_PAD) {           /* RAD_PAD: unused slot of a warp's output chunk */
             oa = sidx[c.a]; ob = sidx[c.b];
             const bool a_first = oa < ob;         /* the reference traces from the lower lumel index */
             const V3 A = ld3(spos[a_first ? c.a : c.b]), B = ld3(spos[a_first ? c.b : c.a]);
@@ -599,12 +684,14 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
     const uint64_t k0 = (uint64_t)my_t0 * RAD_TILE, k1 = (uint64_t)my_t1 * RAD_TILE, n_rows = k1 - k0;
 
     float4 *spos = nullptr, *snrm = nullptr, *diff = nullptr, *total = nullptr, *out = nullptr, *Es = nullptr, *Eo = nullptr, *lrgb_full = nullptr;
-    TileBounds *tb = nullptr, *tb32 = nullptr, *tbg = nullptr;
+    TileBounds *tb = nullptr, *tb32 = nullptr, *tbg = nullptr, *tbs = nullptr;
     uint32_t *mkeys = nullptr, *mkeys_alt = nullptr, *sidx = nullptr, *sidx_alt = nullptr;
     float *d_bounds = nullptr, *d_diffuse = nullptr, *d_emissive = nullptr;
     RadCand *cand = nullptr;
     unsigned long long *d_cnt = nullptr;           /* [0] candidates, [1] links, [2] mirrored links */
     uint4 *mirror = nullptr, *mirror_all = nullptr;
+    uint32_t *item_cnt = nullptr, *item_off = nullptr;
+    uint2 *items = nullptr;
     unsigned long long *d_mcounts = nullptr;
     size_t mirror_cap = 0, mirror_used = 0;
     unsigned long long *keys = nullptr, *keys_alt = nullptr;
@@ -682,31 +769,75 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
         default: rad_tile_bounds_kernel<32><<<n_tiles, RAD_TILE, 0, st>>>(spos, snrm, sidx, tb, tb32, tb32); break;
         }
         RAD_LAUNCHED();
+        const uint32_t n_super = (n_tiles + 31u) / 32u;
+        RAD_TRY(dev_alloc(ctx, &tbs, n_super));
+        rad_super_bounds_kernel<<<grid_for((uint64_t)n_super * 32, 128), 128, 0, st>>>(tb, n_tiles, n_super, world, tiles_per_rank, tbs);
+        RAD_LAUNCHED();
+        /* pair sweep launch shape: persistent warps, as many CTAs as fit (shared memory bound: two staged column tiles per warp) */
+        size_t sweep_smem = 0;
+        int sweep_ctas = 1;
+        {
+            const void *fn = nullptr;
+            switch (group) {
+            case 4:  fn = (const void *)rad_candidates_kernel<4>;  sweep_smem = rad_sweep_smem<4>();  break;
+            case 8:  fn = (const void *)rad_candidates_kernel<8>;  sweep_smem = rad_sweep_smem<8>();  break;
+            case 16: fn = (const void *)rad_candidates_kernel<16>; sweep_smem = rad_sweep_smem<16>(); break;
+            default: fn = (const void *)rad_candidates_kernel<32>; sweep_smem = rad_sweep_smem<32>(); break;
+            }
+            RAD_CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem));
+            RAD_CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            RAD_CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sweep_ctas, fn, RAD_WARPS * 32, sweep_smem));
+            if (sweep_ctas < 1) sweep_ctas = 1;
+        }
 
-        /* ---- 2-4. candidates and visibility, in batches of row tiles bounded by the candidate buffer ---- */
+        /* ---- 2a. work items: (row warp, super-tile) pairs surviving the interval test, row-warp-major ---- */
+        const uint32_t my_rw0 = my_t0 * (RAD_TILE / 32), my_row_warps = tiles_per_rank * (RAD_TILE / 32);
+        uint32_t n_items = 0;
+        {
+            RAD_TRY(dev_alloc(ctx, &item_cnt, (size_t)my_row_warps + 1)); RAD_TRY(dev_alloc(ctx, &item_off, (size_t)my_row_warps + 1));
+            RAD_CU(cudaMemsetAsync(item_cnt + my_row_warps, 0, 4, st));
+            rad_items_kernel<false><<<grid_for((uint64_t)my_row_warps * 32, 128), 128, 0, st>>>(tb32, tbs, n_super, world, tiles_per_rank, my_rw0, my_row_warps, item_cnt, nullptr, nullptr);
+            RAD_LAUNCHED();
+            RAD_CU(cub::DeviceScan::ExclusiveSum(nullptr, sort_tmp_bytes, item_cnt, item_off, (int)my_row_warps + 1, st));
+            RAD_CU(lb_malloc(&sort_tmp, sort_tmp_bytes ? sort_tmp_bytes : 16));
+            RAD_CU(cub::DeviceScan::ExclusiveSum(sort_tmp, sort_tmp_bytes, item_cnt, item_off, (int)my_row_warps + 1, st));
+            ctx->host_counters.kernel_launches += 2;
+            RAD_CU(cudaMemcpyAsync(&n_items, item_off + my_row_warps, 4, cudaMemcpyDeviceToHost, st));
+            RAD_CU(cudaStreamSynchronize(st));
+            lb_free(sort_tmp); sort_tmp = nullptr; sort_tmp_bytes = 0;
+            RAD_TRY(dev_alloc(ctx, &items, (size_t)n_items));
+            rad_items_kernel<true><<<grid_for((uint64_t)my_row_warps * 32, 128), 128, 0, st>>>(tb32, tbs, n_super, world, tiles_per_rank, my_rw0, my_row_warps, nullptr, item_off, items);
+            RAD_LAUNCHED();
+            dev_free(&item_cnt); dev_free(&item_off);
+        }
+        RAD_TRACE("tile bounds + work items");
+
+        /* ---- 2b-4. candidates and visibility, in batches of work items bounded by the candidate buffer ---- */
         RAD_TRY(dev_alloc(ctx, &d_cnt, 4));
-        /* candidate buffer: a sixth of the free HBM, between 16 Mi and 384 Mi records (12 B each) */
+        /* candidate buffer: an eighth of the free HBM, between 16 Mi and 1 Gi records (12 B each) */
         unsigned long long cand_cap = 16ull << 20;
         {
             size_t free_b = 0, total_b = 0;
             if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-                unsigned long long want = (unsigned long long)(free_b / 6 / sizeof(RadCand));
+                unsigned long long want = (unsigned long long)(free_b / 8 / sizeof(RadCand));
                 if (want > cand_cap) cand_cap = want;
-                if (cand_cap > (384ull << 20)) cand_cap = 384ull << 20;
+                if (cand_cap > (1024ull << 20)) cand_cap = 1024ull << 20;
             }
         }
+        if (const char *e = getenv("LTR_RAD_CAND_CAP")) { const unsigned long long v = strtoull(e, nullptr, 10); if (v >= 4096) cand_cap = v; }   /* tests: force many batches */
         RAD_TRY(dev_alloc(ctx, &cand, cand_cap));
-        /* batch of row tiles: probe with 16 CTAs per SM, then size each batch from the measured yield */
-        uint32_t batch = (uint32_t)ctx->num_sms * 16;
-        for (uint32_t t0 = my_t0; t0 < my_t1;) {
-            uint32_t t1 = t0 + batch < my_t1 ? t0 + batch : my_t1;
+        /* batch of items: probe with a small one, then size each batch from the measured yield */
+        uint32_t batch = (uint32_t)ctx->num_sms * (uint32_t)sweep_ctas * RAD_WARPS * 8u;
+        for (uint32_t i0 = 0; i0 < n_items;) {
+            const uint32_t i1 = batch < n_items - i0 ? i0 + batch : n_items;
             RAD_CU(cudaMemsetAsync(d_cnt, 0, 32, st));
             RAD_CU(cudaEventRecord(ctx->ev_k0, st));
             {
-                const uint32_t resident = (uint32_t)ctx->num_sms * 8;             /* 8 CTAs of 128 threads per SM (<= 64 regs, ~20 KB smem) */
-                const uint32_t grid = (t1 - t0) < resident ? (t1 - t0) : resident;
-#define RAD_SWEEP(GS, TBG) rad_candidates_kernel<GS><<<grid, RAD_TILE, 0, st>>>(spos, snrm, tb, tb32, TBG, n_tiles, world, tiles_per_rank, t0, t1 - t0, \
-                                                                 (uint32_t *)(d_cnt + 3), cand, cand_cap, d_cnt, ctx->d_counters)
+                const uint32_t resident = (uint32_t)ctx->num_sms * (uint32_t)sweep_ctas;
+                const uint32_t want = (i1 - i0 + RAD_WARPS - 1) / RAD_WARPS;
+                const uint32_t grid = want < resident ? want : resident;
+#define RAD_SWEEP(GS, TBG) rad_candidates_kernel<GS><<<grid, RAD_WARPS * 32, sweep_smem, st>>>(spos, snrm, tb, tb32, TBG, tbs, n_tiles, world, tiles_per_rank, \
+                                                                 items + i0, i1 - i0, (uint32_t *)(d_cnt + 3), cand, cand_cap, d_cnt, ctx->d_counters)
                 switch (group) {
                 case 4:  RAD_SWEEP(4, tbg); break;
                 case 8:  RAD_SWEEP(8, tbg); break;
@@ -722,9 +853,9 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
             RAD_CU(cudaStreamSynchronize(st));
             { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1); ms_pairs += ms; }
             if (h_cnt[0] > cand_cap) {
-                if (batch == 1) { snprintf(ctx->err, sizeof(ctx->err), "radiosity: one row tile produced %llu candidates (> %llu)", h_cnt[0], cand_cap); goto done; }
+                if (i1 - i0 == 1) { snprintf(ctx->err, sizeof(ctx->err), "radiosity: one work item produced %llu candidates (> %llu)", h_cnt[0], cand_cap); goto done; }
                 /* redo this batch smaller: scale by the overshoot with 30 % headroom */
-                uint32_t nb = (uint32_t)((double)(t1 - t0) * (double)cand_cap / (double)h_cnt[0] * 0.7);
+                uint32_t nb = (uint32_t)((double)(i1 - i0) * (double)cand_cap / (double)h_cnt[0] * 0.7);
                 batch = nb ? nb : 1;
                 continue;
             }
@@ -750,14 +881,15 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
                 mirror_used += h_cnt[2];
             }
             {
-                const double per_tile = (double)(nc ? nc : 1) / (double)(t1 - t0);
-                double nb = 0.7 * (double)cand_cap / per_tile;
-                if (nb < (double)ctx->num_sms) nb = (double)ctx->num_sms;
-                if (nb > 1.0e9) nb = 1.0e9;
+                const double per_item = (double)(nc ? nc : 1) / (double)(i1 - i0);
+                double nb = 0.7 * (double)cand_cap / per_item;
+                if (nb < 1.0) nb = 1.0;
+                if (nb > 4.0e9) nb = 4.0e9;
                 batch = (uint32_t)nb;
             }
-            t0 = t1;
+            i0 = i1;
         }
+        dev_free(&items);
         dev_free(&cand);
         RAD_TRACE("candidates+visibility");
         if (trace) {
@@ -866,7 +998,7 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
         rc = 0;
     }
 done:
-    lb_free(spos); lb_free(snrm); lb_free(diff); lb_free(total); lb_free(out); lb_free(Es); lb_free(Eo); lb_free(tb); lb_free(tb32); lb_free(tbg);
+    lb_free(spos); lb_free(snrm); lb_free(diff); lb_free(total); lb_free(out); lb_free(Es); lb_free(Eo); lb_free(tb); lb_free(tb32); lb_free(tbg); lb_free(tbs); lb_free(item_cnt); lb_free(item_off); lb_free(items);
     lb_free(mkeys); lb_free(mkeys_alt); lb_free(sidx); lb_free(sidx_alt); lb_free(d_bounds);
     lb_free(d_diffuse); lb_free(d_emissive); lb_free(cand); lb_free(d_cnt); lb_free(keys); lb_free(keys_alt);
     lb_free(fac); lb_free(fac_alt); lb_free(sort_tmp); lb_free(mirror); lb_free(mirror_all); lb_free(d_mcounts);

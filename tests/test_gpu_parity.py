@@ -188,6 +188,22 @@ def test_radiosity_pair_sweep_group_sizes_agree_on_config4_sibling(monkeypatch):
             assert parity.meets_bar(parity.texel_parity(a["rgb"], b["rgb"]))
 
 
+def test_radiosity_small_candidate_buffer_forces_batches_and_retries(bakes, monkeypatch):
+    """A 40 000-record candidate buffer (rad1 produces 288 042 candidates): the pair sweep must overflow,
+    shrink its batches and still deliver exactly the reference's links."""
+    monkeypatch.setenv("LTR_RAD_CAND_CAP", "40000")
+    out = api.bake(scenes.scene_rad1(), debug=True)
+    st, lk = out["stats"], out["links"]
+    assert st["n_rad_links"] == 62684 and st["n_rad_segments"] == 288042
+    li, lj, lf = bakes["rad1_link_i"], bakes["rad1_link_j"], bakes["rad1_link_f"]
+    rows = np.repeat(np.arange(lk["rows"], dtype=np.uint32), np.diff(lk["row_offset"]).astype(np.int64))
+    fwd = rows < lk["other"]
+    assert np.array_equal(rows[fwd], li) and np.array_equal(lk["other"][fwd], lj) and bits_equal(lk["factor"][fwd], lf)
+    for lm in out["lightmaps"]:
+        p = parity.texel_parity(lm["rgb"], bakes[f"rad1_lm{lm['uid']}_rgb"])
+        assert p["mae"] == 0 and p["float_max_abs"] < 1e-6
+
+
 def test_ray_counts_equal_reference_instrumented_counts():
     """SURVEY 3.3 work counts of the reference on mesh1 (instrumented copy): 19 735 marches,
     422 636 distance queries, 161 466 AO segments, 9 498 correction rays."""
