@@ -19,6 +19,7 @@
 #include <time.h>
 #include <unistd.h>
 
+#include "gpu.h"
 #include "scene.h"
 
 ltr_Scene::ltr_Scene() : stage("not started"), completion(0.f)
@@ -37,10 +38,8 @@ ltr_Scene::~ltr_Scene()
     bake_free(this);
     for (MeshInstance *mi : instances) delete mi;
     for (ltr_Mesh *m : meshes) delete m;
-    for (ltr_WorkOutput &wo : outputs) {
-        free(wo.lightmap_rgb);
-        free(wo.normals_xyzf);
-    }
+    for (ltr_WorkOutput &wo : outputs) free(wo.normals_xyzf);     /* lightmap_rgb points into output_arena */
+    ltrgpu_host_free(output_arena);
 }
 
 extern "C" {

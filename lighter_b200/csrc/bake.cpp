@@ -203,6 +203,9 @@ void host_prepare(ltr_Scene *S)
 
     S->stage.store("generating data structures");
     S->completion.store(0.f);
+    const bool trace = getenv("LTR_TRACE") != nullptr;          /* host-side phase timings on stderr */
+    double tt = now_s();
+    auto lap = [&](const char *what) { if (trace) { double t = now_s(); fprintf(stderr, "[ltr host] accel %-28s %8.2f ms\n", what, (t - tt) * 1e3); tt = t; } };
     /* per instance: useful triangles of shadow-casting parts, and their reference-order tree */
     std::vector<std::vector<float>> itris(ni);
     std::vector<RefTree> itree(ni);
@@ -236,6 +239,7 @@ void host_prepare(ltr_Scene *S)
             pool.emplace_back([&]() { for (size_t i; (i = next.fetch_add(1)) < ni;) build_one(i); });
         for (auto &th : pool) th.join();
     }
+    lap("instance trees (threads)");
     S->completion.store(0.99f);
     /* instance tree over the root boxes (invalid boxes are dropped by the builder) */
     std::vector<Box3> ibox(ni);
@@ -243,44 +247,71 @@ void host_prepare(ltr_Scene *S)
     RefTree inst_tree;
     inst_tree.build(ibox.data(), ni);
 
-    /* concatenate trees, lay out the texel space, list raster triangles */
-    B.rnodes.clear(); B.ritems.clear(); B.rtree_tris.clear(); B.rtris.clear();
+    /* concatenate trees, lay out the texel space, list raster triangles: offsets first, then every
+     * instance copies its own slices (threads) -- at 1M triangles this is ~130 MB of host memory */
     uint64_t texel_off = 0;
     std::vector<float> scene_tris;
-    for (size_t i = 0; i < ni; ++i) {
-        ltrgpu_Inst &I = B.inst[i];
-        MeshInstance *mi = S->instances[i];
-        I.lm_w = i ? mi->lm_width : 0; I.lm_h = i ? mi->lm_height : 0;
-        I.texel_off_lo = (uint32_t)texel_off; I.texel_off_hi = (uint32_t)(texel_off >> 32);
-        texel_off += (uint64_t)I.lm_w * I.lm_h;
-        I.node_off = (uint32_t)B.rnodes.size(); I.item_off = (uint32_t)B.ritems.size(); I.tri_off = (uint32_t)(B.rtree_tris.size() / 9);
-        I.tree_tris = (uint32_t)(itris[i].size() / 9);
-        I.shadow = (i && mi->shadow) ? 1 : 0;
-        B.rnodes.insert(B.rnodes.end(), itree[i].nodes.begin(), itree[i].nodes.end());
-        B.ritems.insert(B.ritems.end(), itree[i].items.begin(), itree[i].items.end());
-        B.rtree_tris.insert(B.rtree_tris.end(), itris[i].begin(), itris[i].end());
-        if (I.shadow) scene_tris.insert(scene_tris.end(), itris[i].begin(), itris[i].end());
-        if (!i) continue;
-        ltr_Mesh *mesh = mi->mesh;
-        for (size_t p = 0; p < mesh->parts.size(); ++p) {
-            const MeshPart &mp = mesh->parts[p];
-            const u32 *ib = mesh->indices.data() + mp.index_offset;
-            const uint32_t base = (uint32_t)(vbase[i] + mp.vertex_offset);
-            for (u32 t = 0; t + 2 < mp.index_count; t += 3) {
-                ltrgpu_RasterTri rt = { (uint32_t)i, (uint32_t)p, base + ib[t], base + ib[t + 1], base + ib[t + 2] };
-                B.rtris.push_back(rt);
-            }
+    {
+        std::vector<size_t> o_node(ni + 1, 0), o_item(ni + 1, 0), o_tri(ni + 1, 0), o_stri(ni + 1, 0), o_rtri(ni + 1, 0);
+        for (size_t i = 0; i < ni; ++i) {
+            ltrgpu_Inst &I = B.inst[i];
+            MeshInstance *mi = S->instances[i];
+            I.lm_w = i ? mi->lm_width : 0; I.lm_h = i ? mi->lm_height : 0;
+            I.texel_off_lo = (uint32_t)texel_off; I.texel_off_hi = (uint32_t)(texel_off >> 32);
+            texel_off += (uint64_t)I.lm_w * I.lm_h;
+            I.node_off = (uint32_t)o_node[i]; I.item_off = (uint32_t)o_item[i]; I.tri_off = (uint32_t)o_tri[i];
+            I.tree_tris = (uint32_t)(itris[i].size() / 9);
+            I.shadow = (i && mi->shadow) ? 1 : 0;
+            size_t nrt = 0;
+            if (i) for (const MeshPart &mp : mi->mesh->parts) nrt += mp.index_count / 3;
+            o_node[i + 1] = o_node[i] + itree[i].nodes.size();
+            o_item[i + 1] = o_item[i] + itree[i].items.size();
+            o_tri[i + 1] = o_tri[i] + itris[i].size() / 9;
+            o_stri[i + 1] = o_stri[i] + (I.shadow ? itris[i].size() / 9 : 0);
+            o_rtri[i + 1] = o_rtri[i] + nrt;
         }
+        B.rnodes.resize(o_node[ni]); B.ritems.resize(o_item[ni]); B.rtree_tris.resize(o_tri[ni] * 9); B.rtris.resize(o_rtri[ni]);
+        scene_tris.resize(o_stri[ni] * 9);
+        auto copy_one = [&](size_t i) {
+            const ltrgpu_Inst &I = B.inst[i];
+            if (!itree[i].nodes.empty()) memcpy(&B.rnodes[o_node[i]], itree[i].nodes.data(), itree[i].nodes.size() * sizeof(itree[i].nodes[0]));
+            if (!itree[i].items.empty()) memcpy(&B.ritems[o_item[i]], itree[i].items.data(), itree[i].items.size() * sizeof(itree[i].items[0]));
+            if (!itris[i].empty()) {
+                memcpy(&B.rtree_tris[o_tri[i] * 9], itris[i].data(), itris[i].size() * 4);
+                if (I.shadow) memcpy(&scene_tris[o_stri[i] * 9], itris[i].data(), itris[i].size() * 4);
+            }
+            if (!i) return;
+            MeshInstance *mi = S->instances[i];
+            ltr_Mesh *mesh = mi->mesh;
+            ltrgpu_RasterTri *dst = B.rtris.data() + o_rtri[i];
+            for (size_t p = 0; p < mesh->parts.size(); ++p) {
+                const MeshPart &mp = mesh->parts[p];
+                const u32 *ib = mesh->indices.data() + mp.index_offset;
+                const uint32_t base = (uint32_t)(vbase[i] + mp.vertex_offset);
+                for (u32 t = 0; t + 2 < mp.index_count; t += 3) {
+                    ltrgpu_RasterTri rt = { (uint32_t)i, (uint32_t)p, base + ib[t], base + ib[t + 1], base + ib[t + 2] };
+                    *dst++ = rt;
+                }
+            }
+        };
+        unsigned nthreads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)ni));
+        std::atomic<size_t> next{0};
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nthreads; ++t)
+            pool.emplace_back([&]() { for (size_t i; (i = next.fetch_add(1)) < ni;) copy_one(i); });
+        for (auto &th : pool) th.join();
     }
-
+    lap("concatenate + raster list");
     /* flat scene BVH over the shadow-casting triangles */
     int leaf_max = BVH_LEAF_MAX;
     if (const char *e = getenv("LTR_BVH_LEAF")) leaf_max = atoi(e);
     const size_t nst = scene_tris.size() / 9;
     build_scene_bvh(scene_tris.data(), nst, B.bvh, leaf_max, 0);
+    lap("scene BVH");
     B.bvh_tris.resize(nst * 9);
     for (size_t k = 0; k < nst; ++k) memcpy(&B.bvh_tris[k * 9], &scene_tris[(size_t)B.bvh.order[k] * 9], 36);
 
+    lap("reorder triangles");
     /* lights and the light -> instance table */
     const size_t nl = S->lights.size();
     B.lights.resize(nl);
@@ -361,7 +392,11 @@ void upload(ltr_Scene *S)
     d.n_probes = (uint32_t)ppos.size(); d.probe_pos = ppos.data(); d.probe_nrm = pnrm.data();
     d.ao_cos_side = B.ao_cos.data(); d.ao_sin_side = B.ao_sin.data();
     d.blur_ext = B.blur_ext; d.blur_kernel = B.blur_kernel.empty() ? nullptr : B.blur_kernel.data();
+    const bool trace = getenv("LTR_TRACE") != nullptr;
+    if (trace) fprintf(stderr, "[ltr host] upload context + descriptors      %8.2f ms\n", (now_s() - t0) * 1e3);
+    double tu = now_s();
     gpu_check(S, ltrgpu_upload_scene(B.gpu, &d), "scene upload");
+    if (trace) fprintf(stderr, "[ltr host] upload scene arrays               %8.2f ms\n", (now_s() - tu) * 1e3);
 
     if (S->world > 1 && !B.comm) {
         char err[256];
@@ -515,8 +550,15 @@ void readback(ltr_Scene *S)
     Bake &B = *S->bake;
     const size_t ni = S->instances.size();
     double t0 = now_s();
-    for (ltr_WorkOutput &wo : S->outputs) { free(wo.lightmap_rgb); free(wo.normals_xyzf); }
+    for (ltr_WorkOutput &wo : S->outputs) free(wo.normals_xyzf);
     S->outputs.clear();
+    ltrgpu_host_free(S->output_arena); S->output_arena = nullptr;
+    /* every lightmap in ONE device -> host copy into one page-locked block owned by the scene */
+    std::vector<uint64_t> out_off(ni + 1, 0);
+    gpu_check(S, ltrgpu_output_layout(B.gpu, out_off.data()), "output layout");
+    S->output_arena = (float *)ltrgpu_host_alloc((out_off[ni] ? out_off[ni] : 1) * 12);
+    if (!S->output_arena) { Fail f; f.msg = "out of host memory for the lightmaps"; throw f; }
+    gpu_check(S, ltrgpu_download_outputs_all(B.gpu, S->output_arena), "output download");
     for (size_t i = 1; i < ni; ++i) {
         MeshInstance *mi = S->instances[i];
         uint32_t w = 0, h = 0;
@@ -528,10 +570,10 @@ void readback(ltr_Scene *S)
         wo.inst_ident = mi->ident.c_str(); wo.inst_ident_size = mi->ident.size();
         wo.width = w; wo.height = h;
         const size_t cnt = (size_t)w * h;
-        wo.lightmap_rgb = (float *)malloc((cnt ? cnt : 1) * 12);
+        wo.lightmap_rgb = S->output_arena + out_off[i] * 3;
         wo.normals_xyzf = S->config.generate_normalmap_data ? (float *)calloc(cnt ? cnt : 1, 16) : nullptr;
         S->outputs.push_back(wo);                  /* owned by the scene from here on */
-        gpu_check(S, ltrgpu_download_output(B.gpu, (uint32_t)i, wo.lightmap_rgb, wo.normals_xyzf), "output download");
+        if (wo.normals_xyzf) gpu_check(S, ltrgpu_download_output(B.gpu, (uint32_t)i, nullptr, wo.normals_xyzf), "normal map download");
         mi->lm_width = w; mi->lm_height = h;       /* the reference shrinks these under ds2x (lighter.cpp:973-974) */
     }
     if (!S->probes.empty()) {

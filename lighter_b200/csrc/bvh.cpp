@@ -5,6 +5,12 @@
 #include <algorithm>
 #include <atomic>
 #include <thread>
+#include <memory>
+#include <utility>
+#include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <chrono>
 
 namespace {
 
@@ -14,6 +20,8 @@ struct Tmp {
     Box3 box;
     int32_t left, right;       /* -1 for a leaf */
     uint32_t first, count;
+    int32_t inner;             /* inner nodes in this sub-tree (0 for a leaf); -1 = not known yet */
+    int32_t height;            /* levels of inner nodes below and including this one */
 };
 
 inline void grow(Box3 &b, const Box3 &o) { b.lo = min3(b.lo, o.lo); b.hi = max3(b.hi, o.hi); }
@@ -25,47 +33,111 @@ inline float half_area(const Box3 &b)
 }
 inline float axis_of(V3 v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
 
+/* One primitive of the build: its box and original index, kept in a PERMUTED array so that every pass
+ * over a node's range is sequential in memory (an index array into fixed boxes costs a cache miss per
+ * triangle at the top levels, which is where the time goes at 1M triangles). */
+struct Prim { Box3 b; uint32_t id; };
+inline V3 centroid(const Prim &p) { return (p.b.lo + p.b.hi) * 0.5f; }
+
+const int NB = 16;                                /* SAH bins per axis */
+const uint32_t COOP_MIN = 65536;                  /* nodes above this size are built by all threads together */
+
+struct Bounds { Box3 bb, cb; };
+struct Bins {
+    Box3 box[3][NB];
+    uint32_t cnt[3][NB];
+    void clear() { for (int a = 0; a < 3; ++a) for (int b = 0; b < NB; ++b) { box[a][b].lo = mk3(FMAXV); box[a][b].hi = mk3(-FMAXV); cnt[a][b] = 0; } }
+    void merge(const Bins &o) { for (int a = 0; a < 3; ++a) for (int b = 0; b < NB; ++b) { grow(box[a][b], o.box[a][b]); cnt[a][b] += o.cnt[a][b]; } }
+};
+
+inline void bounds_of(const Prim *p, size_t n, Bounds &o)
+{
+    o.bb.lo = o.cb.lo = mk3(FMAXV); o.bb.hi = o.cb.hi = mk3(-FMAXV);
+    for (size_t i = 0; i < n; ++i) { grow(o.bb, p[i].b); grow(o.cb, centroid(p[i])); }
+}
+inline int bin_of(float c, float lo, float scale)
+{
+    int b = (int)((c - lo) * scale);
+    return b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+}
+/* all three axes in one pass over the primitives */
+inline void bin_range(const Prim *p, size_t n, const Box3 &cb, const bool use[3], const float scale[3], Bins &o)
+{
+    for (size_t i = 0; i < n; ++i) {
+        const V3 c = centroid(p[i]);
+        if (use[0]) { int b = bin_of(c.x, cb.lo.x, scale[0]); o.cnt[0][b]++; grow(o.box[0][b], p[i].b); }
+        if (use[1]) { int b = bin_of(c.y, cb.lo.y, scale[1]); o.cnt[1][b]++; grow(o.box[1][b], p[i].b); }
+        if (use[2]) { int b = bin_of(c.z, cb.lo.z, scale[2]); o.cnt[2][b]++; grow(o.box[2][b], p[i].b); }
+    }
+}
+
+template <class F> void parallel_chunks(int threads, size_t n, F fn)      /* fn(chunk index, begin, end), chunk count == threads */
+{
+    std::vector<std::thread> pool;
+    const size_t per = (n + threads - 1) / threads;
+    for (int t = 1; t < threads; ++t) {
+        const size_t b = std::min(n, per * t), e = std::min(n, b + per);
+        pool.emplace_back([=]() { fn(t, b, e); });
+    }
+    fn(0, 0, std::min(n, per));
+    for (auto &th : pool) th.join();
+}
+
+struct Work { int32_t node; uint32_t first, count; int depth; };
+
 struct Builder {
-    const Box3 *pbox;
-    const V3 *pcen;
-    uint32_t *idx;
-    std::vector<Tmp> tmp;
+    Prim *prim;
+    Prim *scratch;                                /* same size as prim: target of the parallel stable partition */
+    Tmp *tmp;                                     /* 2*count+1 entries, uninitialised (every node is written before it is read) */
     std::atomic<int32_t> next{0};
-    std::atomic<int> free_threads{0};
     int leaf_max;
+    int threads;
 
     int32_t alloc() { return next.fetch_add(1); }
 
-    void build(int32_t me, uint32_t first, uint32_t count, int depth)
+    /* Builds ONE node: bounds, SAH split, partition.  Returns false for a leaf; otherwise the children
+     * (allocated, ranges set) are left in l / r.  coop = use every thread on this node's range.  The tree
+     * does not depend on the thread count: bins merge associatively and the cooperative partition is a
+     * stable one (deterministic), chosen by node size only. */
+    bool split(const Work &w, bool coop, Work &l, Work &r)
     {
-        Box3 bb = { mk3(FMAXV), mk3(-FMAXV) }, cb = bb;
-        for (uint32_t i = first; i < first + count; ++i) { grow(bb, pbox[idx[i]]); grow(cb, pcen[idx[i]]); }
-        Tmp &N = tmp[me];
-        N.box = bb; N.first = first; N.count = count; N.left = N.right = -1;
-        if ((int)count <= leaf_max) return;
+        Prim *P = prim + w.first;
+        const uint32_t count = w.count;
+        const int T = coop ? threads : 1;
+        Bounds nb;
+        if (T > 1) {
+            std::vector<Bounds> part(T);
+            parallel_chunks(T, count, [&](int t, size_t b, size_t e) { bounds_of(P + b, e - b, part[t]); });
+            nb = part[0];
+            for (int t = 1; t < T; ++t) { grow(nb.bb, part[t].bb); grow(nb.cb, part[t].cb); }
+        } else bounds_of(P, count, nb);
+        Tmp &N = tmp[w.node];
+        N.box = nb.bb; N.first = w.first; N.count = count; N.left = N.right = -1; N.inner = 0; N.height = 0;
+        if ((int)count <= leaf_max) return false;
+        N.inner = -1;
 
-        const int NB = 16;
+        const Box3 cb = nb.cb;
+        const float lo3[3] = { cb.lo.x, cb.lo.y, cb.lo.z }, ext3[3] = { cb.hi.x - cb.lo.x, cb.hi.y - cb.lo.y, cb.hi.z - cb.lo.z };
+        bool use[3]; float scale[3];
+        for (int a = 0; a < 3; ++a) { use[a] = ext3[a] > 0; scale[a] = use[a] ? NB / ext3[a] : 0.f; }
+        Bins bins; bins.clear();
+        if (T > 1) {
+            std::vector<Bins> part(T);
+            parallel_chunks(T, count, [&](int t, size_t b, size_t e) { part[t].clear(); bin_range(P + b, e - b, cb, use, scale, part[t]); });
+            for (int t = 0; t < T; ++t) bins.merge(part[t]);
+        } else bin_range(P, count, cb, use, scale, bins);
+
         int best_axis = -1, best_split = 0;
         float best_cost = FMAXV;
         for (int a = 0; a < 3; ++a) {
-            float lo = axis_of(cb.lo, a), ext = axis_of(cb.hi, a) - lo;
-            if (!(ext > 0)) continue;
-            Box3 bbx[NB];
-            uint32_t cnt[NB];
-            for (int b = 0; b < NB; ++b) { bbx[b].lo = mk3(FMAXV); bbx[b].hi = mk3(-FMAXV); cnt[b] = 0; }
-            float scale = NB / ext;
-            for (uint32_t i = first; i < first + count; ++i) {
-                int b = (int)((axis_of(pcen[idx[i]], a) - lo) * scale);
-                b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
-                cnt[b]++; grow(bbx[b], pbox[idx[i]]);
-            }
+            if (!use[a]) continue;
             float la[NB]; uint32_t lc[NB];
             Box3 acc = { mk3(FMAXV), mk3(-FMAXV) };
             uint32_t c = 0;
-            for (int b = 0; b < NB - 1; ++b) { grow(acc, bbx[b]); c += cnt[b]; la[b] = c ? half_area(acc) : 0; lc[b] = c; }
+            for (int b = 0; b < NB - 1; ++b) { grow(acc, bins.box[a][b]); c += bins.cnt[a][b]; la[b] = c ? half_area(acc) : 0; lc[b] = c; }
             acc.lo = mk3(FMAXV); acc.hi = mk3(-FMAXV); c = 0;
             for (int b = NB - 1; b > 0; --b) {
-                grow(acc, bbx[b]); c += cnt[b];
+                grow(acc, bins.box[a][b]); c += bins.cnt[a][b];
                 if (lc[b - 1] == 0 || c == 0) continue;
                 float cost = la[b - 1] * lc[b - 1] + half_area(acc) * c;
                 if (cost < best_cost) { best_cost = cost; best_axis = a; best_split = b; }
@@ -74,75 +146,122 @@ struct Builder {
 
         uint32_t mid;
         if (best_axis < 0) {
-            mid = first + count / 2;                       /* coincident centroids: split by index */
-        } else if (depth > 40) {                           /* failsafe against degenerate SAH chains */
+            mid = count / 2;                               /* coincident centroids: split by index */
+        } else if (w.depth > 40) {                         /* failsafe against degenerate SAH chains */
             V3 e = cb.hi - cb.lo;
             int a = (e.x >= e.y && e.x >= e.z) ? 0 : (e.y >= e.z ? 1 : 2);
-            const V3 *cen = pcen;
-            mid = first + count / 2;
-            std::nth_element(idx + first, idx + mid, idx + first + count,
-                             [=](uint32_t p, uint32_t q) { return axis_of(cen[p], a) < axis_of(cen[q], a); });
+            mid = count / 2;
+            std::nth_element(P, P + mid, P + count, [=](const Prim &p, const Prim &q) { return axis_of(centroid(p), a) < axis_of(centroid(q), a); });
         } else {
-            float lo = axis_of(cb.lo, best_axis), scale = NB / (axis_of(cb.hi, best_axis) - lo);
-            const V3 *cen = pcen; int a = best_axis, sp = best_split;
-            uint32_t *m = std::partition(idx + first, idx + first + count, [=](uint32_t t) {
-                int b = (int)((axis_of(cen[t], a) - lo) * scale);
-                b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
-                return b < sp;
-            });
-            mid = (uint32_t)(m - idx);
-            if (mid == first || mid == first + count) mid = first + count / 2;
+            const int a = best_axis, sp = best_split;
+            const float lo = lo3[a], sc = scale[a];
+            auto is_left = [=](const Prim &t) { return bin_of(axis_of(centroid(t), a), lo, sc) < sp; };
+            if (T > 1) {
+                /* stable partition through the scratch array: count per chunk, scan, scatter, copy back */
+                std::vector<uint32_t> nl(T + 1, 0);
+                Prim *S = scratch + w.first;
+                parallel_chunks(T, count, [&](int t, size_t b, size_t e) { uint32_t c = 0; for (size_t i = b; i < e; ++i) c += is_left(P[i]); nl[t + 1] = c; });
+                for (int t = 0; t < T; ++t) nl[t + 1] += nl[t];
+                const uint32_t total_left = nl[T];
+                const size_t per = ((size_t)count + T - 1) / T;
+                parallel_chunks(T, count, [&](int t, size_t b, size_t e) {
+                    size_t lpos = nl[t], rpos = total_left + (std::min((size_t)count, per * t) - nl[t]);
+                    for (size_t i = b; i < e; ++i) { if (is_left(P[i])) S[lpos++] = P[i]; else S[rpos++] = P[i]; }
+                });
+                parallel_chunks(T, count, [&](int, size_t b, size_t e) { if (e > b) memcpy(P + b, S + b, (e - b) * sizeof(Prim)); });
+                mid = total_left;
+            } else if (count > COOP_MIN) {                 /* same (stable) order as the cooperative path: the tree does not depend on the thread count */
+                mid = (uint32_t)(std::stable_partition(P, P + count, is_left) - P);
+            } else {
+                mid = (uint32_t)(std::partition(P, P + count, is_left) - P);
+            }
+            if (mid == 0 || mid == count) mid = count / 2;
         }
-        int32_t l = alloc(), r = alloc();
-        tmp[me].left = l; tmp[me].right = r;
-        uint32_t lc = mid - first, rc = count - lc;
-        if (lc > 16384 && rc > 16384 && free_threads.fetch_sub(1) > 0) {
-            std::thread th([=]() { build(l, first, lc, depth + 1); });
-            build(r, mid, rc, depth + 1);
-            th.join();
-            free_threads.fetch_add(1);
-        } else {
-            if (lc > 16384 && rc > 16384) free_threads.fetch_add(1);   /* undo the failed reservation */
-            build(l, first, lc, depth + 1);
-            build(r, mid, rc, depth + 1);
-        }
+        l.node = alloc(); r.node = alloc();
+        tmp[w.node].left = l.node; tmp[w.node].right = r.node;
+        l.first = w.first; l.count = mid; r.first = w.first + mid; r.count = count - mid;
+        l.depth = r.depth = w.depth + 1;
+        return true;
     }
+
+    void build_serial(const Work &w)
+    {
+        Work l, r;
+        if (!split(w, false, l, r)) return;
+        build_serial(l);
+        build_serial(r);
+        tmp[w.node].inner = 1 + tmp[l.node].inner + tmp[r.node].inner;
+        tmp[w.node].height = 1 + std::max(tmp[l.node].height, tmp[r.node].height);
+    }
+
+    /* sub-tree sizes of the nodes built cooperatively (their descendants built in phase B are known) */
+    void finish_sizes(int32_t t)
+    {
+        Tmp &N = tmp[t];
+        if (N.inner >= 0) return;
+        finish_sizes(N.left); finish_sizes(N.right);
+        N.inner = 1 + tmp[N.left].inner + tmp[N.right].inner;
+        N.height = 1 + std::max(tmp[N.left].height, tmp[N.right].height);
+    }
+
+    void run(uint32_t count)
+    {
+        Work root = { alloc(), 0, count, 0 };
+        /* phase A: the few nodes big enough to be worth every thread, one after the other */
+        std::vector<Work> big{ root }, small;
+        while (!big.empty()) {
+            Work w = big.back(); big.pop_back();
+            if (w.count <= COOP_MIN || threads <= 1) { small.push_back(w); continue; }
+            Work l, r;
+            if (split(w, true, l, r)) { big.push_back(l); big.push_back(r); }
+        }
+        /* phase B: independent sub-trees, largest first, pulled by the threads from a shared cursor */
+        std::sort(small.begin(), small.end(), [](const Work &a, const Work &b) { return a.count != b.count ? a.count > b.count : a.first < b.first; });
+        std::atomic<size_t> cursor{0};
+        auto worker = [&]() { for (size_t i; (i = cursor.fetch_add(1)) < small.size();) build_serial(small[i]); };
+        std::vector<std::thread> pool;
+        const int T = (int)std::min<size_t>((size_t)std::max(1, threads), small.size());
+        for (int t = 1; t < T; ++t) pool.emplace_back(worker);
+        worker();
+        for (auto &th : pool) th.join();
+        finish_sizes(root.node);
+        subtrees.swap(small);
+    }
+    std::vector<Work> subtrees;                   /* the phase-B roots: units of the parallel flatten as well */
 };
 
 inline int32_t leaf_code(uint32_t first, uint32_t count) { return ~(int32_t)((first << 3) | count); }
 
+/* Pre-order layout: an inner node's first child (if inner) is the next slot, the second child follows the
+ * first child's whole sub-tree.  With the sub-tree sizes known, every slot is a pure function of the path
+ * from the root, so the phase-B sub-trees are emitted by the threads independently. */
 struct Flattener {
-    const std::vector<Tmp> &tmp;
-    std::vector<BvhNode> &out;
-    int maxdepth = 0;
+    const Tmp *tmp;
+    BvhNode *out;
 
     static void set_child(BvhNode &n, int which, const Box3 &b, int32_t code)
     {
         if (which == 0) { n.lo0x = b.lo.x; n.lo0y = b.lo.y; n.lo0z = b.lo.z; n.hi0x = b.hi.x; n.hi0y = b.hi.y; n.hi0z = b.hi.z; n.c0 = code; }
         else            { n.lo1x = b.lo.x; n.lo1y = b.lo.y; n.lo1z = b.lo.z; n.hi1x = b.hi.x; n.hi1y = b.hi.y; n.hi1z = b.hi.z; n.c1 = code; }
     }
-    /* iterative DFS: (tmp index of an INNER node, slot in out) */
-    void run(int32_t root)
+    /* emits the sub-tree of INNER node t at `slot`; stops (and records) at the nodes listed in `cut` when given */
+    void emit(int32_t t, int32_t slot, const std::vector<uint8_t> *is_cut, std::vector<std::pair<int32_t, int32_t>> *cut_out) const
     {
-        struct Item { int32_t t, slot, depth; };
+        struct Item { int32_t t, slot; };
         std::vector<Item> st;
-        out.push_back(BvhNode());
-        st.push_back({ root, 0, 1 });
+        st.push_back({ t, slot });
         while (!st.empty()) {
-            Item it = st.back(); st.pop_back();
-            if (it.depth > maxdepth) maxdepth = it.depth;
+            const Item it = st.back(); st.pop_back();
+            if (is_cut && (*is_cut)[it.t]) { cut_out->push_back({ it.t, it.slot }); continue; }
             const Tmp &N = tmp[it.t];
-            int32_t kids[2] = { N.left, N.right };
-            int32_t slots[2] = { -1, -1 };
-            for (int k = 0; k < 2; ++k) {
-                const Tmp &C = tmp[kids[k]];
-                if (C.left < 0) set_child(out[it.slot], k, C.box, leaf_code(C.first, C.count));
-                else { slots[k] = (int32_t)out.size(); out.push_back(BvhNode()); set_child(out[it.slot], k, C.box, slots[k]); }
-            }
-            out[it.slot].pad0 = out[it.slot].pad1 = 0;
-            /* push second child first so the first child is processed (and laid out) next */
-            if (slots[1] >= 0) st.push_back({ kids[1], slots[1], it.depth + 1 });
-            if (slots[0] >= 0) st.push_back({ kids[0], slots[0], it.depth + 1 });
+            const Tmp &L = tmp[N.left], &R = tmp[N.right];
+            BvhNode &o = out[it.slot];
+            const int32_t ls = it.slot + 1, rs = it.slot + 1 + L.inner;
+            set_child(o, 0, L.box, L.left < 0 ? leaf_code(L.first, L.count) : ls);
+            set_child(o, 1, R.box, R.left < 0 ? leaf_code(R.first, R.count) : rs);
+            o.pad0 = o.pad1 = 0;
+            if (R.left >= 0) st.push_back({ N.right, rs });
+            if (L.left >= 0) st.push_back({ N.left, ls });
         }
     }
 };
@@ -168,38 +287,76 @@ void build_scene_bvh(const float *tris9, size_t count, SceneBvh &out, int leaf_m
         return;
     }
 
-    std::vector<Box3> pbox(count);
-    std::vector<V3> pcen(count);
-    for (size_t i = 0; i < count; ++i) {
-        const float *t = tris9 + 9 * i;
-        V3 a = mk3(t[0], t[1], t[2]), b = mk3(t[3], t[4], t[5]), c = mk3(t[6], t[7], t[8]);
-        pbox[i].lo = min3(a, min3(b, c));
-        pbox[i].hi = max3(a, max3(b, c));
-        pcen[i] = (pbox[i].lo + pbox[i].hi) * 0.5f;
-        out.order[i] = (uint32_t)i;
-        grow(out.bounds, pbox[i]);
+    const bool trace = getenv("LTR_TRACE_BVH") != nullptr;
+    auto tnow = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tt = tnow();
+    auto lap = [&](const char *w) { if (trace) { double t = tnow(); fprintf(stderr, "[bvh] %-12s %7.1f ms\n", w, t - tt); tt = t; } };
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    /* uninitialised working arrays: zero-filling ~140 MB on one thread costs more than the top of the build */
+    std::unique_ptr<Prim[]> prim(new Prim[count]), scratch(threads > 1 && count > COOP_MIN ? new Prim[count] : nullptr);
+    {
+        std::vector<Box3> part(threads, Box3{ mk3(FMAXV), mk3(-FMAXV) });
+        Prim *pp = prim.get();
+        parallel_chunks(count > COOP_MIN ? threads : 1, count, [&](int t, size_t b, size_t e) {
+            Box3 acc = { mk3(FMAXV), mk3(-FMAXV) };
+            for (size_t i = b; i < e; ++i) {
+                const float *q = tris9 + 9 * i;
+                V3 a = mk3(q[0], q[1], q[2]), bb = mk3(q[3], q[4], q[5]), c = mk3(q[6], q[7], q[8]);
+                pp[i].b.lo = min3(a, min3(bb, c));
+                pp[i].b.hi = max3(a, max3(bb, c));
+                pp[i].id = (uint32_t)i;
+                grow(acc, pp[i].b);
+            }
+            part[t] = acc;
+        });
+        for (int t = 0; t < threads; ++t) grow(out.bounds, part[t]);
     }
 
+    lap("prims");
     Builder B;
-    B.pbox = pbox.data(); B.pcen = pcen.data(); B.idx = out.order.data();
-    B.tmp.resize(2 * count + 1);
+    std::unique_ptr<Tmp[]> tmp(new Tmp[2 * count + 1]);
+    B.prim = prim.get(); B.scratch = scratch.get(); B.tmp = tmp.get();
     B.leaf_max = leaf_max;
-    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
-    B.free_threads.store(threads > 1 ? threads - 1 : 0);
-    int32_t root = B.alloc();
-    B.build(root, 0, (uint32_t)count, 0);
+    B.threads = threads;
+    B.run((uint32_t)count);
+    lap("build");
+    const int32_t root = 0;
+    {
+        const Prim *pp = prim.get();
+        uint32_t *oo = out.order.data();
+        parallel_chunks(count > COOP_MIN ? threads : 1, count, [=](int, size_t b, size_t e) { for (size_t i = b; i < e; ++i) oo[i] = pp[i].id; });
+    }
 
-    if (B.tmp[root].left < 0) {                 /* whole scene fits one leaf: wrap it */
+    if (tmp[root].left < 0) {                   /* whole scene fits one leaf: wrap it */
         BvhNode n;
-        Flattener::set_child(n, 0, B.tmp[root].box, leaf_code(0, (uint32_t)count));
+        Flattener::set_child(n, 0, tmp[root].box, leaf_code(0, (uint32_t)count));
         Flattener::set_child(n, 1, empty, leaf_code(0, 0));
         n.pad0 = n.pad1 = 0;
         out.nodes.push_back(n);
         out.depth = 1;
         return;
     }
-    Flattener F{ B.tmp, out.nodes };
-    out.nodes.reserve(count);
-    F.run(root);
-    out.depth = F.maxdepth;
+    out.nodes.resize((size_t)tmp[root].inner);
+    out.depth = tmp[root].height;
+    Flattener F{ tmp.get(), out.nodes.data() };
+    /* the cooperative top of the tree serially (a few dozen nodes), cutting at the phase-B roots; those in parallel */
+    std::vector<uint8_t> is_cut;
+    std::vector<std::pair<int32_t, int32_t>> cuts;
+    if (B.subtrees.size() > 1) {
+        is_cut.assign((size_t)B.next.load(), 0);
+        for (const Work &w : B.subtrees) if (tmp[w.node].left >= 0) is_cut[w.node] = 1;
+        F.emit(root, 0, &is_cut, &cuts);
+        std::atomic<size_t> cursor{0};
+        auto worker = [&]() { for (size_t i; (i = cursor.fetch_add(1)) < cuts.size();) F.emit(cuts[i].first, cuts[i].second, nullptr, nullptr); };
+        std::vector<std::thread> pool;
+        const int T = (int)std::min<size_t>((size_t)threads, cuts.size());
+        for (int t = 1; t < T; ++t) pool.emplace_back(worker);
+        worker();
+        for (auto &th : pool) th.join();
+    } else {
+        F.emit(root, 0, nullptr, nullptr);
+    }
+    lap("flatten");
 }

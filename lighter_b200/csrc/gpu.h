@@ -126,6 +126,15 @@ int ltrgpu_finalize(ltrgpu_Ctx *ctx);
 int ltrgpu_output_size(ltrgpu_Ctx *ctx, uint32_t inst, uint32_t *w, uint32_t *h);
 int ltrgpu_download_output(ltrgpu_Ctx *ctx, uint32_t inst, float *rgb, float *normals_xyzf /* may be NULL */);
 int ltrgpu_download_probe_colors(ltrgpu_Ctx *ctx, float *rgb3);
+/* all lightmaps in one copy: rgb_all receives the concatenated output images (instance i at float offset
+ * 3*out_off[i], out_off = n_inst+1 prefix offsets in texels); total texel count returned in *texels */
+int ltrgpu_output_layout(ltrgpu_Ctx *ctx, uint64_t *out_off /* n_inst+1 */);
+int ltrgpu_download_outputs_all(ltrgpu_Ctx *ctx, float *rgb_all);
+
+/* Page-locked host memory from a process-wide cache (a bake moves ~200 MB each way; pinning costs more than
+ * the copy, so blocks are kept and reused across bakes).  Falls back to malloc without a CUDA device. */
+void *ltrgpu_host_alloc(size_t bytes);
+void ltrgpu_host_free(void *p);
 
 int ltrgpu_sync(ltrgpu_Ctx *ctx);
 int ltrgpu_get_counters(ltrgpu_Ctx *ctx, ltrgpu_Counters *out);

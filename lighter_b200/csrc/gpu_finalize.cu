@@ -276,6 +276,27 @@ extern "C" int ltrgpu_output_size(ltrgpu_Ctx *ctx, uint32_t inst, uint32_t *w, u
     return 0;
 }
 
+extern "C" int ltrgpu_output_layout(ltrgpu_Ctx *ctx, uint64_t *out_off)
+{
+    if (!ctx->h_out_off) { snprintf(ctx->err, sizeof(ctx->err), "no outputs yet"); return 1; }
+    memcpy(out_off, ctx->h_out_off, sizeof(uint64_t) * ((size_t)ctx->n_inst + 1));
+    return 0;
+}
+
+extern "C" int ltrgpu_download_outputs_all(ltrgpu_Ctx *ctx, float *rgb_all)
+{
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->h_out_off) { snprintf(ctx->err, sizeof(ctx->err), "no outputs yet"); return 1; }
+    const uint64_t texels = ctx->h_out_off[ctx->n_inst];
+    const float *src = ctx->params.ds2x ? ctx->d_out : ctx->d_image;
+    if (texels) {
+        CU_TRY(ctx, cudaMemcpyAsync(rgb_all, src, texels * 12, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->host_counters.d2h_bytes += texels * 12;
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 extern "C" int ltrgpu_download_output(ltrgpu_Ctx *ctx, uint32_t inst, float *rgb, float *normals_xyzf)
 {
     CU_TRY(ctx, cudaSetDevice(ctx->device));

@@ -23,6 +23,8 @@ struct ltrgpu_Ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_span0 = nullptr, ev_span1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     char err[512] = {0};
+    void *stage_buf[2] = { nullptr, nullptr };    /* pinned staging for pageable uploads (lb_upload_staged) */
+    cudaEvent_t stage_ev[2] = { nullptr, nullptr };
 
     ltrgpu_Params params;
     /* ---- uploaded scene ---- */
@@ -123,11 +125,12 @@ template <class T> static inline int dev_alloc(ltrgpu_Ctx *ctx, T **p, size_t co
     CU_TRY(ctx, lb_malloc((void **)p, count * sizeof(T)));
     return 0;
 }
+int lb_upload_staged(ltrgpu_Ctx *ctx, void *dst, const void *src, size_t bytes);      /* gpu_scene.cu */
 template <class T> static inline int dev_upload(ltrgpu_Ctx *ctx, T **p, const void *src, size_t count)
 {
     if (dev_alloc(ctx, p, count)) return 1;
     if (count && src) {
-        CU_TRY(ctx, cudaMemcpyAsync(*p, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        if (lb_upload_staged(ctx, *p, src, count * sizeof(T))) return 1;
         ctx->host_counters.h2d_bytes += count * sizeof(T);
     }
     return 0;

@@ -77,6 +77,78 @@ void lb_trim(void)
     cudaSetDevice(cur);
 }
 
+/* ---- caching page-locked host allocator --------------------------------------------------------- */
+namespace {
+struct HostPool {
+    std::mutex mu;
+    std::unordered_map<void *, std::pair<size_t, bool>> live;      /* ptr -> (bytes, pinned) */
+    std::multimap<size_t, void *> idle;                            /* pinned blocks only */
+};
+HostPool &host_pool() { static HostPool p; return p; }
+} // namespace
+
+extern "C" void *ltrgpu_host_alloc(size_t bytes)
+{
+    HostPool &P = host_pool();
+    const size_t cls = size_class(bytes ? bytes : 1);
+    {
+        std::lock_guard<std::mutex> g(P.mu);
+        auto it = P.idle.find(cls);
+        if (it != P.idle.end()) {
+            void *p = it->second;
+            P.idle.erase(it);
+            P.live[p] = { cls, true };
+            return p;
+        }
+    }
+    void *p = nullptr;
+    bool pinned = cudaHostAlloc(&p, cls, cudaHostAllocPortable) == cudaSuccess;
+    if (!pinned) { cudaGetLastError(); p = malloc(cls); }
+    if (!p) return nullptr;
+    std::lock_guard<std::mutex> g(P.mu);
+    P.live[p] = { cls, pinned };
+    return p;
+}
+
+extern "C" void ltrgpu_host_free(void *p)
+{
+    if (!p) return;
+    HostPool &P = host_pool();
+    std::lock_guard<std::mutex> g(P.mu);
+    auto it = P.live.find(p);
+    if (it == P.live.end()) { free(p); return; }
+    if (it->second.second) P.idle.insert({ it->second.first, p }); else free(p);
+    P.live.erase(it);
+}
+
+/* Host -> device copy of a pageable array through two pinned staging buffers: the CPU copies chunk k+1
+ * into one buffer while the DMA engine drains the other.  (cudaMemcpyAsync from pageable memory stages
+ * internally too, but synchronously and in small pieces: measured ~1.7 GB/s on the scene upload.) */
+int lb_upload_staged(ltrgpu_Ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    const size_t CHUNK = (size_t)8 << 20;
+    if (bytes < ((size_t)1 << 20)) {
+        CU_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return 0;
+    }
+    if (!ctx->stage_buf[0]) {
+        for (int b = 0; b < 2; ++b) {
+            ctx->stage_buf[b] = ltrgpu_host_alloc(CHUNK);
+            if (!ctx->stage_buf[b]) { snprintf(ctx->err, sizeof(ctx->err), "out of host memory for the upload staging buffers"); return 1; }
+            CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[b], cudaEventDisableTiming));
+        }
+    }
+    int b = 0;
+    for (size_t off = 0; off < bytes; off += CHUNK, b ^= 1) {
+        const size_t n = bytes - off < CHUNK ? bytes - off : CHUNK;
+        CU_TRY(ctx, cudaEventSynchronize(ctx->stage_ev[b]));          /* previous DMA out of this buffer finished */
+        memcpy(ctx->stage_buf[b], (const char *)src + off, n);
+        CU_TRY(ctx, cudaMemcpyAsync((char *)dst + off, ctx->stage_buf[b], n, cudaMemcpyHostToDevice, ctx->stream));
+        CU_TRY(ctx, cudaEventRecord(ctx->stage_ev[b], ctx->stream));
+    }
+    return 0;
+}
+
 /* one thread per BVH-order triangle: expand the 9 floats into the two prepared records
  * (geom.h) with the reference's exact expressions. */
 __global__ void prepare_tris_kernel(const float *__restrict__ tris9, uint32_t n, PreparedTri *__restrict__ pt, RayTri *__restrict__ rt)
@@ -155,12 +227,20 @@ extern "C" void ltrgpu_destroy(ltrgpu_Ctx *ctx)
     if (ctx->ev_span1) cudaEventDestroy(ctx->ev_span1);
     if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
     if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
+    for (int b = 0; b < 2; ++b) { ltrgpu_host_free(ctx->stage_buf[b]); if (ctx->stage_ev[b]) cudaEventDestroy(ctx->stage_ev[b]); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     /* cached device blocks stay in the pool for the next bake of this process (ltrgpu_release_memory drops them) */
     delete ctx;
 }
 
-extern "C" void ltrgpu_release_memory(void) { lb_trim(); }
+extern "C" void ltrgpu_release_memory(void)
+{
+    lb_trim();
+    HostPool &P = host_pool();
+    std::lock_guard<std::mutex> g(P.mu);
+    for (auto &kv : P.idle) cudaFreeHost(kv.second);
+    P.idle.clear();
+}
 extern "C" const char *ltrgpu_last_error(ltrgpu_Ctx *ctx) { return ctx ? ctx->err : "no GPU context"; }
 extern "C" void *ltrgpu_stream(ltrgpu_Ctx *ctx) { return (void *)ctx->stream; }
 

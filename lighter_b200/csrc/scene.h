@@ -58,6 +58,7 @@ struct ltr_Scene {
     std::vector<Light> lights;
     std::vector<ltr_SampleInfo> probes;
     std::vector<ltr_WorkOutput> outputs;
+    float *output_arena = nullptr;             /* page-locked block all lightmap_rgb pointers point into (one D2H copy) */
 
     /* status (ref: lighter_int.hpp:1045-1046, lighter.cpp:1159-1164) */
     std::atomic<const char *> stage;
