@@ -211,11 +211,14 @@ def main():
         traffic = json.load(open(tpath)).get(args.workload, {})
 
     def roof(kernel, nbytes, ms, launches, note, extra=None):
+        """achieved = algorithmic bytes per launch / average launch duration (CUDA events on the bake stream)."""
         if not ms or ms <= 0:
             return None
+        launches = max(int(launches or 1), 1)
         ach = nbytes / (ms * 1e-3) / 1e9
         r = {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
              "traffic": traffic.get(kernel), "peak_source": peak_src, "launches_per_step": launches,
+             "algorithmic_bytes_per_launch": nbytes / launches, "kernel_ms_per_launch": ms / launches,
              "algorithmic_bytes_per_step": nbytes, "kernel_ms_per_step": ms, "note": note}
         if extra:
             r.update(extra)
@@ -223,24 +226,29 @@ def main():
 
     # SURVEY 8d unit costs: 64 B per BVH node visit, 160 B per point/triangle test (PreparedTri), 64 B per
     # segment/triangle test (RayTri), 36 B per march (lumel in, factor out), 32 B per segment.
+    batches = max(int(stats.get("n_rad_batches", 1)), 1)
+    rad_share = stats["n_rad_segments"] / max(stats["n_rad_segments"] + stats["n_ao_segments"], 1)
     roofs = {
-        "rad_candidates_kernel": roof(
-            "rad_candidates_kernel",
-            stats["n_rad_tile_loads"] * 4096.0 + stats["n_rad_segments"] * 12.0 + stats["n_lumels_local"] * 32.0,
-            stats["gpu_ms_rad_pairs"], None,
-            "compulsory HBM bytes = 4 KiB per staged column tile + 12 B per candidate written + 32 B per row lumel; the kernel is "
-            "FP32-issue/LDS bound (no FMA by design, ncu: FMA pipe 40 % active), so the HBM fraction is small by construction",
-            {"pair_tests_per_s": stats["n_rad_pairs"] / (stats["gpu_ms_rad_pairs"] * 1e-3) if stats["gpu_ms_rad_pairs"] else None}),
         "rad_visibility_kernel": roof(
             "rad_visibility_kernel",
-            (stats["n_ray_node_visits"] - 0) * 64.0 + stats["n_ray_tri_tests"] * 64.0 + (stats["n_rad_segments"] + stats["n_ao_segments"]) * 32.0,
-            stats["gpu_ms_rad_vis"] + stats["gpu_ms_ao"], None,
-            "segment traversal (radiosity visibility + AO): 64 B/node + 64 B/triangle test + 32 B/segment; bytes are served by L1/L2 "
-            "(scene is cache resident), so this is cache bandwidth, not HBM utilisation"),
+            (stats["n_ray_node_visits"] * 64.0 + stats["n_ray_tri_tests"] * 64.0) * rad_share + stats["n_rad_segments"] * (12.0 + 32.0),
+            stats["gpu_ms_rad_vis"], batches,
+            "any-hit segment traversal of the radiosity candidates: 64 B/node visit + 64 B/triangle test (the node/triangle counters are shared "
+            "with the AO pass and apportioned by segment count) + 12 B candidate + 32 B endpoints per segment; the bytes are served by L1/L2 "
+            "(the scene is cache resident, ncu: DRAM traffic is ~1 % of them), so this is CACHE bandwidth and the fraction of the HBM peak can "
+            "exceed 1; the kernel is instruction-issue bound (ncu: IPC 3.1 of 4, 23 of 32 lanes active)",
+            {"segments_per_s": stats["n_rad_segments"] / (stats["gpu_ms_rad_vis"] * 1e-3) if stats["gpu_ms_rad_vis"] else None}),
+        "rad_candidates_kernel": roof(
+            "rad_candidates_kernel",
+            stats["n_rad_tile_loads"] * 5120.0 + stats["n_rad_segments"] * 12.0,
+            stats["gpu_ms_rad_pairs"], batches,
+            "pair sweep: 5 KiB per column tile staged by TMA bulk copy (positions, normals, group bounds) + 12 B per candidate written; "
+            "FP32-issue bound (22 instructions per lumel pair per lane), the HBM fraction is small by construction",
+            {"pair_tests_per_s": stats["n_rad_pairs"] / (stats["gpu_ms_rad_pairs"] * 1e-3) if stats["gpu_ms_rad_pairs"] else None}),
         "direct_march_kernel": roof(
             "direct_march_kernel",
             stats["n_node_visits"] * 64.0 + stats["n_tri_tests"] * 160.0 + stats["n_marches"] * 36.0,
-            stats["gpu_ms_march"], None,
+            stats["gpu_ms_march"], 1,
             "distance-query traversal: 64 B/node + 160 B/point-triangle test + 36 B/march; L1/L2 served"),
     }
     roofs = {k: v for k, v in roofs.items() if v}
@@ -273,7 +281,7 @@ def main():
         "rays_per_step": rays_step,
         "stage_ms": stage_ms,
         "counters": {k: int(stats[k]) for k in ("n_marches", "n_distance_queries", "n_ao_segments", "n_rad_pairs", "n_rad_segments", "n_rad_links",
-                                                 "n_node_visits", "n_tri_tests", "n_ray_node_visits", "n_ray_tri_tests", "n_rad_tile_loads")},
+                                                 "n_node_visits", "n_tri_tests", "n_ray_node_visits", "n_ray_tri_tests", "n_rad_tile_loads", "n_rad_batches")},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": int(e2e_stats["h2d_bytes"]), "d2h_bytes_per_step": int(e2e_stats["d2h_bytes"]),
                 "bake_wall_s": sum(e2e_walls) / len(e2e_walls), "steps": len(e2e_walls),

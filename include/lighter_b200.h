@@ -42,6 +42,7 @@ typedef struct ltrx_Stats {
     uint64_t n_ray_node_visits, n_ray_tri_tests; /* segment traversal (AO + radiosity visibility) */
     uint64_t n_rad_tile_loads;                /* 4 KiB column tiles staged by the radiosity pair sweep */
     uint64_t kernel_launches, h2d_bytes, d2h_bytes;
+    uint64_t n_rad_batches;                   /* launches of the pair-sweep / visibility kernel pair (candidate buffer refills) */
 } ltrx_Stats;
 
 typedef struct ltrx_Lumels {

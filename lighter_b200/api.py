@@ -96,7 +96,7 @@ class Stats(C.Structure):
                                            "n_distance_queries", "n_ao_segments", "n_correction_rays", "n_rad_pairs",
                                            "n_rad_segments", "n_rad_links", "n_node_visits", "n_tri_tests",
                                            "n_ray_node_visits", "n_ray_tri_tests", "n_rad_tile_loads",
-                                           "kernel_launches", "h2d_bytes", "d2h_bytes")])
+                                           "kernel_launches", "h2d_bytes", "d2h_bytes", "n_rad_batches")])
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -599,7 +599,7 @@ void readback(ltr_Scene *S)
         st.n_correction_rays = c.correction_rays; st.n_rad_pairs = c.rad_pairs; st.n_rad_segments = c.rad_segments;
         st.n_rad_links = c.rad_links; st.n_node_visits = c.node_visits; st.n_tri_tests = c.tri_tests;
         st.n_ray_node_visits = c.ray_node_visits; st.n_ray_tri_tests = c.ray_tri_tests; st.n_rad_tile_loads = c.rad_tile_loads;
-        st.kernel_launches = c.kernel_launches; st.h2d_bytes = c.h2d_bytes; st.d2h_bytes = c.d2h_bytes;
+        st.kernel_launches = c.kernel_launches; st.h2d_bytes = c.h2d_bytes; st.d2h_bytes = c.d2h_bytes; st.n_rad_batches = c.rad_batches;
         st.gpu_ms_samples = c.ms_samples; st.gpu_ms_direct = c.ms_direct; st.gpu_ms_march = c.ms_march;
         st.gpu_ms_radiosity = c.ms_radiosity; st.gpu_ms_ao = c.ms_ao; st.gpu_ms_finalize = c.ms_finalize;
         st.gpu_ms_total = c.ms_samples + c.ms_direct + c.ms_radiosity + c.ms_ao + c.ms_finalize;
@@ -616,7 +616,7 @@ void collect_counters(ltr_Scene *S)
     st.n_correction_rays = c.correction_rays; st.n_rad_pairs = c.rad_pairs; st.n_rad_segments = c.rad_segments;
     st.n_rad_links = c.rad_links; st.n_node_visits = c.node_visits; st.n_tri_tests = c.tri_tests;
         st.n_ray_node_visits = c.ray_node_visits; st.n_ray_tri_tests = c.ray_tri_tests; st.n_rad_tile_loads = c.rad_tile_loads;
-    st.kernel_launches = c.kernel_launches; st.h2d_bytes = c.h2d_bytes; st.d2h_bytes = c.d2h_bytes;
+    st.kernel_launches = c.kernel_launches; st.h2d_bytes = c.h2d_bytes; st.d2h_bytes = c.d2h_bytes; st.n_rad_batches = c.rad_batches;
     st.gpu_ms_samples = c.ms_samples; st.gpu_ms_direct = c.ms_direct; st.gpu_ms_march = c.ms_march;
     st.gpu_ms_radiosity = c.ms_radiosity; st.gpu_ms_ao = c.ms_ao; st.gpu_ms_finalize = c.ms_finalize;
     st.gpu_ms_total = c.ms_samples + c.ms_direct + c.ms_radiosity + c.ms_ao + c.ms_finalize;

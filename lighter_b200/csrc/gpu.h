@@ -83,6 +83,7 @@ typedef struct ltrgpu_Counters {
     uint64_t ray_node_visits, ray_tri_tests;   /* segment queries (AO, radiosity): 64 B nodes, 64 B ray triangles */
     uint64_t rad_tile_loads;                   /* 128-lumel column tiles (4 KiB) staged into shared memory by the pair sweep */
     uint64_t kernel_launches, h2d_bytes, d2h_bytes;
+    uint64_t rad_batches;                      /* pair-sweep + visibility launch pairs */
     float ms_samples, ms_direct, ms_march, ms_radiosity, ms_ao, ms_finalize, ms_rad_pairs, ms_rad_vis, ms_span;
 } ltrgpu_Counters;
 

@@ -879,6 +879,7 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
                 { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1); ms_vis += ms; }
                 link_used += h_cnt[1];
                 mirror_used += h_cnt[2];
+                ctx->host_counters.rad_batches++;
             }
             {
                 const double per_item = (double)(nc ? nc : 1) / (double)(i1 - i0);
