@@ -250,7 +250,7 @@ __global__ void probe_emit_kernel(const V3 *pos, const V3 *nrm, uint32_t n, floa
 /* ---------------------------------------------------------------------------------------------
  * reference-order tree walks (used only here; see reftree.h for why order matters)
  * ------------------------------------------------------------------------------------------- */
-struct RefView { const RefNode *nodes; const int32_t *items; const float *tris9; };
+struct RefView { const RefNode *nodes; const int32_t *items; const float *tris9; const PreparedTri *ptris; };
 
 __device__ __forceinline__ void ld_tri9(const float *t, V3 &a, V3 &b, V3 &c)
 {
@@ -286,44 +286,67 @@ __device__ float reftree_closest(const RefView &v, V3 from, V3 to, int *tid)
     return closest;
 }
 
-/* concave-edge offset against one instance (ref: lighter_math.cpp:991-1044) */
-__device__ void reftree_offset_sample(const RefView &v, V3 &P, V3 N, float dist)
+/* One candidate triangle of the concave-edge offset, evaluated with the CURRENT (possibly already moved)
+ * sample position -- the reference mutates P while it walks (lighter_math.cpp:991-1038). */
+__device__ __forceinline__ void offset_one_tri(const RefView &v, int id, V3 &P, V3 N, float dist)
+{
+    PreparedTri PT;
+    load_prepared(v.ptris + id, PT);
+    float ndst = point_tri_distance_prepared(P, PT);
+    if (!(ndst < dist)) return;
+    V3 TPN = -tri_back_normal(PT.t0, PT.t1, PT.t2);
+    float TPD = dot3(TPN, PT.t0);
+    float sigdst = dot3(TPN, P) - TPD;
+    if (!(sigdst <= LB_SMALL)) return;
+    V3 Pextr = P + norm3(TPN + N) * -sigdst * 1.41f;
+    if (!point_proj_on_tri(Pextr, PT)) return;
+    float projDot = dot3(TPN, N);
+    if (!(fabsf(projDot) < 0.95f)) return;
+    V3 projTPN = norm3(TPN - N * projDot);
+    float dotFactor = 1.0f - fabsf(projDot);
+    V3 Pnew = P + projTPN * (-sigdst / dotFactor + LB_SMALL);
+    int tid = -1;
+    float d = reftree_closest(v, P + (N + projTPN) * LB_SMALL, Pnew, &tid);
+    if (d >= 0.9f || tid == id) P = Pnew;
+}
+
+/* Concave-edge offset against one instance (ref: lighter_math.cpp:991-1044).  The node culling uses the box
+ * around the INITIAL position (the reference builds its query box once), so the walk only has to list the
+ * triangles of the overlapped nodes in reference order; they are then evaluated in that order, in batches,
+ * with every lane of the warp inside the same loop -- the evaluation is where the time goes, and a lane-
+ * private walk-and-evaluate loop ran with 6 of 32 lanes active (ncu). */
+#define OFFSET_BATCH 24
+__device__ void reftree_offset_sample(const RefView &v, V3 &P, V3 N, float dist, bool active)
 {
     const V3 qlo = P - mk3(dist), qhi = P + mk3(dist);
-    int stack[24];
-    int sp = 0;
-    stack[sp++] = 0;
-    while (sp) {
-        int node = stack[--sp];
-        RefNode Nd = v.nodes[node];
-        if (qlo.x > Nd.hi.x || qhi.x < Nd.lo.x || qlo.y > Nd.hi.y || qhi.y < Nd.lo.y || qlo.z > Nd.hi.z || qhi.z < Nd.lo.z) continue;
-        if (Nd.ido != -1) {
-            int cnt = v.items[Nd.ido];
-            for (int k = 0; k < cnt; ++k) {
-                int id = v.items[Nd.ido + 1 + k];
-                V3 a, b, c;
-                ld_tri9(v.tris9 + 9ull * id, a, b, c);
-                PreparedTri PT;
-                prepare_tri(a, b, c, PT);
-                float ndst = point_tri_distance_prepared(P, PT);
-                if (!(ndst < dist)) continue;
-                V3 TPN = -tri_back_normal(a, b, c);
-                float TPD = dot3(TPN, a);
-                float sigdst = dot3(TPN, P) - TPD;
-                if (!(sigdst <= LB_SMALL)) continue;
-                V3 Pextr = P + norm3(TPN + N) * -sigdst * 1.41f;
-                if (!point_proj_on_tri(Pextr, PT)) continue;
-                float projDot = dot3(TPN, N);
-                if (!(fabsf(projDot) < 0.95f)) continue;
-                V3 projTPN = norm3(TPN - N * projDot);
-                float dotFactor = 1.0f - fabsf(projDot);
-                V3 Pnew = P + projTPN * (-sigdst / dotFactor + LB_SMALL);
-                int tid = -1;
-                float d = reftree_closest(v, P + (N + projTPN) * LB_SMALL, Pnew, &tid);
-                if (d >= 0.9f || tid == id) P = Pnew;
+    int stack[32];                                        /* reference trees are at most 16 deep: never fills */
+    int list[OFFSET_BATCH];
+    int sp = 0, ln = 0;
+    if (active) stack[sp++] = 0;
+    for (;;) {
+        /* walk until the batch is full or the tree is exhausted */
+        int pend_ido = -1, pend_k = 0, pend_cnt = 0;
+        while (sp && ln < OFFSET_BATCH) {
+            int node = stack[--sp];
+            if (node < 0) {                               /* resume marker: remaining items of a node that did not fit the last batch */
+                pend_ido = stack[--sp]; pend_k = -node - 1; pend_cnt = v.items[pend_ido];
+            } else {
+                RefNode Nd = v.nodes[node];
+                if (qlo.x > Nd.hi.x || qhi.x < Nd.lo.x || qlo.y > Nd.hi.y || qhi.y < Nd.lo.y || qlo.z > Nd.hi.z || qhi.z < Nd.lo.z) continue;
+                if (Nd.ch != -1 && sp + 2 <= 28) { stack[sp++] = Nd.ch; stack[sp++] = node + 1; }
+                if (Nd.ido == -1) continue;
+                pend_ido = Nd.ido; pend_k = 0; pend_cnt = v.items[Nd.ido];
             }
+            while (pend_k < pend_cnt && ln < OFFSET_BATCH) list[ln++] = v.items[pend_ido + 1 + pend_k++];
+            if (pend_k < pend_cnt) { stack[sp++] = pend_ido; stack[sp++] = -pend_k - 1; }     /* continue this node first next time */
         }
-        if (Nd.ch != -1 && sp + 2 <= 24) { stack[sp++] = Nd.ch; stack[sp++] = node + 1; }
+        const unsigned any = __ballot_sync(0xffffffffu, ln > 0);
+        if (!any) break;
+        int maxn = ln;
+        for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, o));
+        for (int k = 0; k < maxn; ++k)
+            if (k < ln) offset_one_tri(v, list[k], P, N, dist);
+        ln = 0;
     }
 }
 
@@ -335,14 +358,36 @@ lumel_fix_kernel(const ltrgpu_Inst *__restrict__ inst, uint32_t n_inst, RefView 
 {
     uint64_t i = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned rays = 0;
-    if (i < n_lumels) {
-        V3 P = ld3(lpos[i]), N = ld3(lnrm[i]);
-        float dist = sqrtf(lrad[i].w);
-        for (uint32_t m = 0; m < n_inst; ++m) {
-            const ltrgpu_Inst I = inst[m];
-            RefView v = { all.nodes + I.node_off, all.items + I.item_off, all.tris9 + 9ull * I.tri_off };
-            reftree_offset_sample(v, P, N, dist);
+    const bool active = i < n_lumels;
+    const unsigned lane = threadIdx.x & 31u;
+    V3 P = mk3(0.f), N = mk3(0.f);
+    float dist = 0.f;
+    if (active) { P = ld3(lpos[i]); N = ld3(lnrm[i]); dist = sqrtf(lrad[i].w); }
+    {
+        /* instances whose tree can matter to ANY lumel of this warp: one instance root box per lane against the
+         * union of the warp's query boxes, then the survivors in ascending order (the reference's order) */
+        float ul[3] = { active ? P.x - dist : INFINITY, active ? P.y - dist : INFINITY, active ? P.z - dist : INFINITY };
+        float uh[3] = { active ? P.x + dist : -INFINITY, active ? P.y + dist : -INFINITY, active ? P.z + dist : -INFINITY };
+        for (int o = 16; o > 0; o >>= 1)
+            for (int a = 0; a < 3; ++a) { ul[a] = fminf(ul[a], __shfl_xor_sync(0xffffffffu, ul[a], o)); uh[a] = fmaxf(uh[a], __shfl_xor_sync(0xffffffffu, uh[a], o)); }
+        for (uint32_t base = 0; base < n_inst; base += 32) {
+            const uint32_t m = base + lane;
+            bool ok = false;
+            if (m < n_inst) {
+                const RefNode R = all.nodes[inst[m].node_off];
+                ok = !(ul[0] > R.hi.x || uh[0] < R.lo.x || ul[1] > R.hi.y || uh[1] < R.lo.y || ul[2] > R.hi.z || uh[2] < R.lo.z);
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, ok);
+            while (mask) {
+                const uint32_t mm = base + (uint32_t)__ffs(mask) - 1u;
+                mask &= mask - 1u;
+                const ltrgpu_Inst I = inst[mm];
+                RefView v = { all.nodes + I.node_off, all.items + I.item_off, all.tris9 + 9ull * I.tri_off, all.ptris + I.tri_off };
+                reftree_offset_sample(v, P, N, dist, active);
+            }
         }
+    }
+    if (active) {
         if (max_correct_dist) {
             int itsleft = 100;
             float md = max_correct_dist;
@@ -458,7 +503,7 @@ extern "C" int ltrgpu_generate_lumels(ltrgpu_Ctx *ctx, uint64_t *inst_lumel_off)
         if (b > n) b = n;
         if (e > n) e = n;
         if (b < ctx->n_probes) b = ctx->n_probes;
-        RefView all = { ctx->d_rnodes, ctx->d_ritems, ctx->d_rtree_tris };
+        RefView all = { ctx->d_rnodes, ctx->d_ritems, ctx->d_rtree_tris, ctx->d_rtree_ptris };
         if (e > b) {
             lumel_fix_kernel<<<grid_for(e - b, LB_BLOCK), LB_BLOCK, 0, st>>>(
                 ctx->d_inst, ctx->n_inst, all, ctx->d_bvh, ctx->d_raytris, ctx->d_ptris, ctx->d_tri_orig, b, e,

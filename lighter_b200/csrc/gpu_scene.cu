@@ -160,9 +160,11 @@ __global__ void prepare_tris_kernel(const float *__restrict__ tris9, uint32_t n,
     PreparedTri P;
     prepare_tri(a, b, c, P);
     pt[i] = P;
-    RayTri R;
-    prepare_raytri(a, b, c, R);
-    rt[i] = R;
+    if (rt) {
+        RayTri R;
+        prepare_raytri(a, b, c, R);
+        rt[i] = R;
+    }
 }
 
 extern "C" int ltrgpu_create(ltrgpu_Ctx **out, int device)
@@ -215,7 +217,7 @@ extern "C" void ltrgpu_destroy(ltrgpu_Ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_bake_state(ctx);
     dev_free(&ctx->d_inst); dev_free(&ctx->d_wpos); dev_free(&ctx->d_wnrm); dev_free(&ctx->d_vtex); dev_free(&ctx->d_ltex);
-    dev_free(&ctx->d_rtris); dev_free(&ctx->d_rnodes); dev_free(&ctx->d_ritems); dev_free(&ctx->d_rtree_tris);
+    dev_free(&ctx->d_rtris); dev_free(&ctx->d_rnodes); dev_free(&ctx->d_ritems); dev_free(&ctx->d_rtree_tris); dev_free(&ctx->d_rtree_ptris);
     dev_free(&ctx->d_bvh); dev_free(&ctx->d_ptris); dev_free(&ctx->d_raytris); dev_free(&ctx->d_tri_orig);
     dev_free(&ctx->d_lights); dev_free(&ctx->d_light_inst); dev_free(&ctx->d_probe_pos); dev_free(&ctx->d_probe_nrm);
     dev_free(&ctx->d_ao_cos); dev_free(&ctx->d_ao_sin); dev_free(&ctx->d_blur_kernel); dev_free(&ctx->d_counters);
@@ -325,6 +327,12 @@ extern "C" int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *d)
     if (dev_alloc(ctx, &ctx->d_raytris, d->n_tris)) return 1;
     if (d->n_tris) {
         prepare_tris_kernel<<<grid_for(d->n_tris, 256), 256, 0, ctx->stream>>>(d_raw, d->n_tris, ctx->d_ptris, ctx->d_raytris);
+        CU_LAUNCH_CHECK(ctx);
+    }
+    /* reference-order triangles (lumel generation): point-query terms precomputed once instead of per query */
+    if (dev_alloc(ctx, &ctx->d_rtree_ptris, d->n_rtree_tris)) return 1;
+    if (d->n_rtree_tris) {
+        prepare_tris_kernel<<<grid_for(d->n_rtree_tris, 256), 256, 0, ctx->stream>>>(ctx->d_rtree_tris, d->n_rtree_tris, ctx->d_rtree_ptris, nullptr);
         CU_LAUNCH_CHECK(ctx);
     }
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
