@@ -43,6 +43,7 @@ typedef struct ltrx_Stats {
     uint64_t n_rad_tile_loads;                /* 4 KiB column tiles staged by the radiosity pair sweep */
     uint64_t kernel_launches, h2d_bytes, d2h_bytes;
     uint64_t n_rad_batches;                   /* launches of the pair-sweep / visibility kernel pair (candidate buffer refills) */
+    uint64_t n_shadow_rays;                   /* sampled-shadow extension: any-hit rays, lumel x light x sample */
 } ltrx_Stats;
 
 typedef struct ltrx_Lumels {
@@ -68,6 +69,21 @@ LTRAPI int  ltrx_SetDevice(ltr_Scene *scene, int cuda_device);
 LTRAPI int  ltrx_NcclUniqueId(unsigned char out_id[LTRX_NCCL_ID_BYTES]);
 LTRAPI int  ltrx_SetShard(ltr_Scene *scene, int rank, int world, const unsigned char *nccl_id /* NULL iff world==1 */);
 LTRAPI void ltrx_ShardRange(uint64_t n, int rank, int world, uint64_t *begin, uint64_t *end);
+
+/* direct-light shadow term ----------------------------------------------------------------------
+ * LTRX_SHADOW_MARCH (default) is the reference's behaviour: the distance-field penumbra march of
+ * CalcInvShadowFactor (lighter.cpp:190-207); shadow_sample_count is ignored, as in the reference.
+ * LTRX_SHADOW_SAMPLED is an EXTENSION (the reference has only a disabled sketch, lighter.cpp:566-584):
+ * shadow_sample_count (1..64) any-hit rays per lumel and light towards a golden-angle disk of
+ * light_radius, VisibilityTest semantics (lighter.cpp:138-147); f_vis = 1 - blocked/samples. */
+#define LTRX_SHADOW_MARCH   0
+#define LTRX_SHADOW_SAMPLED 1
+LTRAPI int ltrx_SetShadowMode(ltr_Scene *scene, int mode);
+/* after a bake with ltrx_SetDebug(scene,1) in sampled mode: per local lumel, bit s set = sample s blocked */
+LTRAPI int ltrx_GetShadowMasks(ltr_Scene *scene, u32 light, const uint64_t **out, uint64_t *count);
+/* the segment sample `sample` of `light` casts from a lumel (host evaluation of the kernel's own function) */
+LTRAPI int ltrx_ShadowSampleSegment(ltr_Scene *scene, u32 light, u32 sample, const float pos[3], const float nrm[3],
+                                    float from_out[3], float to_out[3]);
 
 /* measurement ------------------------------------------------------------------------------ */
 LTRAPI int         ltrx_GetStats(ltr_Scene *scene, ltrx_Stats *out);

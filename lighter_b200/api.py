@@ -96,7 +96,7 @@ class Stats(C.Structure):
                                            "n_distance_queries", "n_ao_segments", "n_correction_rays", "n_rad_pairs",
                                            "n_rad_segments", "n_rad_links", "n_node_visits", "n_tri_tests",
                                            "n_ray_node_visits", "n_ray_tri_tests", "n_rad_tile_loads",
-                                           "kernel_launches", "h2d_bytes", "d2h_bytes", "n_rad_batches")])
+                                           "kernel_launches", "h2d_bytes", "d2h_bytes", "n_rad_batches", "n_shadow_rays")])
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -119,7 +119,8 @@ LTR_SYMBOLS = ["ltr_DefaultSizeFunc", "ltr_CreateScene", "ltr_DestroyScene", "lt
                "ltr_LightAdd", "ltr_SampleAdd", "ltr_GetWorkOutputInfo", "ltr_GetWorkOutput", "ltr_NextPowerOfTwo"]
 LTRX_SYMBOLS = ["ltrx_Version", "ltrx_SetDevice", "ltrx_NcclUniqueId", "ltrx_SetShard", "ltrx_ShardRange", "ltrx_GetStats",
                 "ltrx_GetError", "ltrx_Prepare", "ltrx_BakeResident", "ltrx_Finish", "ltrx_SetDebug", "ltrx_GetLumels",
-                "ltrx_GetLinks", "ltrx_GetShadowFactors", "ltrx_test_point_tri_distance", "ltrx_test_seg_tri",
+                "ltrx_GetLinks", "ltrx_GetShadowFactors", "ltrx_SetShadowMode", "ltrx_GetShadowMasks", "ltrx_ShadowSampleSegment",
+                "ltrx_test_point_tri_distance", "ltrx_test_seg_tri",
                 "ltrx_test_scene_queries", "ltrx_test_march", "ltrx_test_spiral_dirs", "ltrx_test_reftree", "ltrx_test_bvh"]
 
 _lib = None
@@ -172,6 +173,9 @@ def lib() -> C.CDLL:
     L.ltrx_GetLinks.argtypes = [vp, C.POINTER(Links)]
     L.ltrx_GetShadowFactors.argtypes = [vp, u32, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_uint64)]
     fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
+    L.ltrx_SetShadowMode.argtypes = [vp, C.c_int]
+    L.ltrx_GetShadowMasks.argtypes = [vp, u32, C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64)]
+    L.ltrx_ShadowSampleSegment.argtypes = [vp, u32, u32, fp, fp, fp, fp]
     L.ltrx_test_point_tri_distance.argtypes = [fp, fp, u32, fp]
     L.ltrx_test_seg_tri.argtypes = [fp, fp, fp, u32, fp]
     L.ltrx_test_scene_queries.argtypes = [fp, u32, fp, fp, u32, fp, ip, fp, ip]
@@ -215,7 +219,7 @@ class BakeHandle:
     """A scene fed through the C API, kept alive so outputs (owned by the scene) stay valid."""
 
     def __init__(self, scene: _scenes.Scene, debug: bool = False, device: int | None = None, shard: tuple | None = None,
-                 reset_rand: bool = True):
+                 reset_rand: bool = True, shadow_mode: int = 0):
         L = lib()
         self.L = L
         self.scene_desc = scene
@@ -252,6 +256,8 @@ class BakeHandle:
             L.ltrx_SetDevice(self.h, device)
         if debug:
             L.ltrx_SetDebug(self.h, 1)
+        if shadow_mode and not L.ltrx_SetShadowMode(self.h, shadow_mode):
+            raise RuntimeError("ltrx_SetShadowMode rejected the mode")
         if shard is not None:
             rank, world, nccl_id = shard
             if not L.ltrx_SetShard(self.h, rank, world, nccl_id):
@@ -373,6 +379,21 @@ class BakeHandle:
         if not self.L.ltrx_GetShadowFactors(self.h, light, C.byref(p), C.byref(n)):
             raise RuntimeError("no shadow factors kept (bake with debug=True)")
         return np.ctypeslib.as_array(p, (n.value,)).copy()
+
+    def shadow_masks(self, light: int) -> np.ndarray:
+        """Sampled-shadow mode, debug bakes: per local lumel, bit s set = sample s of `light` is blocked."""
+        p, n = C.POINTER(C.c_uint64)(), C.c_uint64()
+        if not self.L.ltrx_GetShadowMasks(self.h, light, C.byref(p), C.byref(n)):
+            raise RuntimeError("no shadow masks kept (bake with debug=True, shadow_mode=1)")
+        return np.ctypeslib.as_array(p, (n.value,)).copy()
+
+    def shadow_segment(self, light: int, sample: int, pos, nrm):
+        """Host evaluation of the kernel's own segment function for one lumel (bit-identical end points)."""
+        pos = np.ascontiguousarray(pos, np.float32); nrm = np.ascontiguousarray(nrm, np.float32)
+        a, b = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        if not self.L.ltrx_ShadowSampleSegment(self.h, light, sample, _fp(pos), _fp(nrm), _fp(a), _fp(b)):
+            raise RuntimeError("ltrx_ShadowSampleSegment: bad light/sample or scene not baked")
+        return a, b
 
     def close(self):
         if self.h:

@@ -166,8 +166,9 @@ void ltr_LightAdd(ltr_Scene *scene, ltr_LightInfo *li)
     L.spot_angle_in = li->spot_angle_in;
     L.spot_curve = li->spot_curve;
     /* The reference draws one randf() here for its (unread) per-light sample table
-     * (lighter.cpp:1300).  Consume it so the AO random offsets that follow line up. */
-    (void)rand();
+     * (lighter.cpp:1300).  Consume it so the AO random offsets that follow line up; the value
+     * rotates the sample spiral of the sampled-shadow extension mode. */
+    L.randoff = (float)rand() / (float)RAND_MAX;
     scene->lights.push_back(L);
 }
 

@@ -107,6 +107,7 @@ struct Bake {
     SceneBvh bvh;
     std::vector<float> bvh_tris;
     std::vector<ltrgpu_Light> lights;
+    std::vector<float> light_samples;         /* float4 per (light, sample): sampled-shadow extension table (host libm) */
     std::vector<uint8_t> light_inst;
     std::vector<float> ao_cos, ao_sin, blur_kernel;
     int blur_ext = 0;
@@ -117,7 +118,7 @@ struct Bake {
     /* debug copies */
     std::vector<float> d_pos, d_nrm, d_rad, d_rgb, d_fvis, d_lfac;
     std::vector<uint32_t> d_loc, d_lother;
-    std::vector<uint64_t> d_lrow;
+    std::vector<uint64_t> d_lrow, d_smask;
 };
 
 namespace {
@@ -315,6 +316,7 @@ void host_prepare(ltr_Scene *S)
     /* lights and the light -> instance table */
     const size_t nl = S->lights.size();
     B.lights.resize(nl);
+    B.light_samples.clear();
     B.light_inst.assign(nl * ni, 0);
     for (size_t l = 0; l < nl; ++l) {
         const Light &L = S->lights[l];
@@ -324,6 +326,27 @@ void host_prepare(ltr_Scene *S)
         float out_rad = L.spot_angle_out / 180.0f * (float)M_PI, in_rad = L.spot_angle_in / 180.0f * (float)M_PI;
         if (in_rad == out_rad) in_rad -= LB_SMALL;
         G.angle_out_rad = out_rad; G.angle_diff = in_rad - out_rad;
+        /* sampled-shadow extension: golden-angle disk of light_radius, see geom.h shadow_sample_segment.
+         * cos/sin come from the host libm, like every configuration-only transcendental. */
+        G.n_samples = (uint32_t)std::min(std::max(L.shadow_sample_count, 1), 64);
+        G.sample_off = (uint32_t)(B.light_samples.size() / 4);
+        G.pad0 = G.pad1 = 0;
+        for (uint32_t s = 0; s < G.n_samples; ++s) {
+            const float q = (s + 0.5f) / (float)G.n_samples;
+            const float rho = L.light_radius * sqrtf(q);
+            const float angle = (s + L.randoff) * (137.508f / 180.0f * (float)M_PI);
+            const float dx = cosf(angle) * rho, dy = sinf(angle) * rho;
+            if (L.type == LTR_LT_DIRECT) {
+                const V3 d = L.direction;
+                const V3 up = norm3(cross3(d, mk3(d.y, -d.z, d.x))), rt = cross3(d, up);
+                const V3 a = norm3(d + rt * dx + up * dy);
+                const float v[4] = { a.x, a.y, a.z, 0.f };
+                B.light_samples.insert(B.light_samples.end(), v, v + 4);
+            } else {
+                const float v[4] = { dx, dy, 0.f, 0.f };
+                B.light_samples.insert(B.light_samples.end(), v, v + 4);
+            }
+        }
         uint8_t *row = &B.light_inst[l * ni];
         row[0] = 1;
         auto mark = [&](const int32_t *ids, int32_t n) { for (int32_t k = 0; k < n; ++k) row[ids[k]] = 1; };
@@ -380,6 +403,7 @@ void upload(ltr_Scene *S)
     memcpy(P.ao_color, cfg.ao_color_rgb, 12);
     P.ao_num_samples = cfg.ao_num_samples; P.blur_size = cfg.blur_size; P.ds2x = cfg.ds2x; P.normalmap = cfg.generate_normalmap_data;
     P.amb_brightness = (cfg.ambient_color[0] + cfg.ambient_color[1] + cfg.ambient_color[2]) * (1.0f / 3.0f);
+    P.shadow_mode = S->shadow_mode;
     d.n_inst = (uint32_t)B.inst.size(); d.inst = B.inst.data();
     d.n_verts = (uint32_t)B.wpos.size(); d.wpos = B.wpos.data(); d.wnrm = B.wnrm.data(); d.vtex2 = B.vtex.data(); d.ltex2 = B.ltex.data();
     d.n_rtris = (uint32_t)B.rtris.size(); d.rtris = B.rtris.data();
@@ -389,6 +413,7 @@ void upload(ltr_Scene *S)
     d.n_bvh_nodes = (uint32_t)B.bvh.nodes.size(); d.bvh = B.bvh.nodes.data();
     d.n_tris = (uint32_t)(B.bvh_tris.size() / 9); d.tris9 = B.bvh_tris.data(); d.tri_orig = B.bvh.order.data();
     d.n_lights = (uint32_t)B.lights.size(); d.lights = B.lights.data(); d.light_inst = B.light_inst.data();
+    d.n_light_samples = (uint32_t)(B.light_samples.size() / 4); d.light_samples4 = B.light_samples.data();
     d.n_probes = (uint32_t)ppos.size(); d.probe_pos = ppos.data(); d.probe_nrm = pnrm.data();
     d.ao_cos_side = B.ao_cos.data(); d.ao_sin_side = B.ao_sin.data();
     d.blur_ext = B.blur_ext; d.blur_kernel = B.blur_kernel.empty() ? nullptr : B.blur_kernel.data();
@@ -475,6 +500,12 @@ void gpu_stages(ltr_Scene *S)
             B.d_fvis.assign(S->lights.size() * nl, 0.f);
             for (size_t l = 0; l < S->lights.size(); ++l)
                 if (ltrgpu_download_shadow_factors(B.gpu, (uint32_t)l, B.d_fvis.data() + l * nl)) break;   /* only the last light chunk is resident */
+            B.d_smask.clear();
+            if (S->shadow_mode == 1) {
+                B.d_smask.assign(S->lights.size() * nl, 0);
+                for (size_t l = 0; l < S->lights.size(); ++l)
+                    if (ltrgpu_download_shadow_masks(B.gpu, (uint32_t)l, B.d_smask.data() + l * nl)) break;
+            }
         }
     }
     S->stats.t_direct = now_s() - t0;
@@ -599,7 +630,7 @@ void readback(ltr_Scene *S)
         st.n_correction_rays = c.correction_rays; st.n_rad_pairs = c.rad_pairs; st.n_rad_segments = c.rad_segments;
         st.n_rad_links = c.rad_links; st.n_node_visits = c.node_visits; st.n_tri_tests = c.tri_tests;
         st.n_ray_node_visits = c.ray_node_visits; st.n_ray_tri_tests = c.ray_tri_tests; st.n_rad_tile_loads = c.rad_tile_loads;
-        st.kernel_launches = c.kernel_launches; st.h2d_bytes = c.h2d_bytes; st.d2h_bytes = c.d2h_bytes; st.n_rad_batches = c.rad_batches;
+        st.kernel_launches = c.kernel_launches; st.h2d_bytes = c.h2d_bytes; st.d2h_bytes = c.d2h_bytes; st.n_rad_batches = c.rad_batches; st.n_shadow_rays = c.shadow_rays;
         st.gpu_ms_samples = c.ms_samples; st.gpu_ms_direct = c.ms_direct; st.gpu_ms_march = c.ms_march;
         st.gpu_ms_radiosity = c.ms_radiosity; st.gpu_ms_ao = c.ms_ao; st.gpu_ms_finalize = c.ms_finalize;
         st.gpu_ms_total = c.ms_samples + c.ms_direct + c.ms_radiosity + c.ms_ao + c.ms_finalize;
@@ -616,7 +647,7 @@ void collect_counters(ltr_Scene *S)
     st.n_correction_rays = c.correction_rays; st.n_rad_pairs = c.rad_pairs; st.n_rad_segments = c.rad_segments;
     st.n_rad_links = c.rad_links; st.n_node_visits = c.node_visits; st.n_tri_tests = c.tri_tests;
         st.n_ray_node_visits = c.ray_node_visits; st.n_ray_tri_tests = c.ray_tri_tests; st.n_rad_tile_loads = c.rad_tile_loads;
-    st.kernel_launches = c.kernel_launches; st.h2d_bytes = c.h2d_bytes; st.d2h_bytes = c.d2h_bytes; st.n_rad_batches = c.rad_batches;
+    st.kernel_launches = c.kernel_launches; st.h2d_bytes = c.h2d_bytes; st.d2h_bytes = c.d2h_bytes; st.n_rad_batches = c.rad_batches; st.n_shadow_rays = c.shadow_rays;
     st.gpu_ms_samples = c.ms_samples; st.gpu_ms_direct = c.ms_direct; st.gpu_ms_march = c.ms_march;
     st.gpu_ms_radiosity = c.ms_radiosity; st.gpu_ms_ao = c.ms_ao; st.gpu_ms_finalize = c.ms_finalize;
     st.gpu_ms_total = c.ms_samples + c.ms_direct + c.ms_radiosity + c.ms_ao + c.ms_finalize;
@@ -806,6 +837,38 @@ int ltrx_test_bvh(const float *tris9, u32 ntris, int leaf_max, u32 *n_nodes, u32
         }
     }
     for (u32 t = 0; t < ntris; ++t) if (seen[t] != 1) return 0;
+    return 1;
+}
+
+int ltrx_SetShadowMode(ltr_Scene *scene, int mode)
+{
+    if (mode != LTRX_SHADOW_MARCH && mode != LTRX_SHADOW_SAMPLED) return 0;
+    scene->shadow_mode = mode;
+    return 1;
+}
+
+int ltrx_GetShadowMasks(ltr_Scene *scene, u32 light, const uint64_t **out, uint64_t *count)
+{
+    Bake *B = scene->bake;
+    if (!B || B->d_smask.empty() || light >= scene->lights.size()) return 0;
+    const uint64_t nl = scene->stats.n_lumels_local;
+    *out = B->d_smask.data() + (size_t)light * nl; *count = nl;
+    return 1;
+}
+
+/* host evaluation of the shadow segment of (light, sample) for a lumel: the SAME inline function the kernel
+ * uses (geom.h), compiled for the host with contraction off -- bit-identical end points */
+int ltrx_ShadowSampleSegment(ltr_Scene *scene, u32 light, u32 sample, const float pos[3], const float nrm[3], float from_out[3], float to_out[3])
+{
+    Bake *B = scene->bake;
+    if (!B || light >= B->lights.size()) return 0;
+    const ltrgpu_Light &L = B->lights[light];
+    if (sample >= L.n_samples) return 0;
+    const float *sm = &B->light_samples[(size_t)(L.sample_off + sample) * 4];
+    V3 from, to;
+    shadow_sample_segment(L.type, L.pos, L.range, mk3(sm[0], sm[1], sm[2]), mk3(pos[0], pos[1], pos[2]), mk3(nrm[0], nrm[1], nrm[2]), from, to);
+    from_out[0] = from.x; from_out[1] = from.y; from_out[2] = from.z;
+    to_out[0] = to.x; to_out[1] = to.y; to_out[2] = to.z;
     return 1;
 }
 

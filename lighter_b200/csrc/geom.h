@@ -110,6 +110,34 @@ LB_HD void prepare_raytri(V3 p1, V3 p2, V3 p3, RayTri &o)
 
 #define LB_NO_HIT 2.0f
 
+/* ------------------------------------------------------------------------------------------
+ * Sampled soft shadows (EXTENSION mode; the reference only has a disabled directional-light
+ * sketch of it, lighter.cpp:566-584, and "TODO" for point/spot lights, lighter.cpp:1311-1314).
+ *
+ * Every light is an area source sampled on a golden-angle disk: sample s of n sits at radius
+ * light_radius*sqrt((s+.5)/n), angle (s+randoff)*137.508 deg (randoff = the rand() the reference
+ * draws per ltr_LightAdd, lighter.cpp:1300).  Point/spot: the disk is centred on the light and
+ * faces the lumel.  Directional: the disk sits at unit distance along the light direction, i.e.
+ * the direction is jittered within atan(light_radius).  The shadow ray starts at the reference's
+ * shadow offset SP + SN*0.005 (lighter_int.hpp:966) and is tested with VisibilityTest semantics
+ * (any hit, both ends pulled in by 0.001, lighter.cpp:138-147).
+ *
+ * `smp` is the host-libm table entry of (light, s): directional = the unit sample direction;
+ * point/spot = (disk x, disk y, 0).  Only exact IEEE operations below: host and device agree bit
+ * for bit, which is what lets the tests check hit/miss against the oracle.
+ * ------------------------------------------------------------------------------------------ */
+#define LB_SHADOW_OFFSET 0.005f
+LB_HD void shadow_sample_segment(unsigned type, V3 Lpos, float range, V3 smp, V3 SP, V3 SN, V3 &from, V3 &to)
+{
+    from = SP + SN * LB_SHADOW_OFFSET;
+    if (type == 3u) { to = from + smp * range; return; }
+    const V3 d = norm3(Lpos - from);
+    const V3 diffvec = mk3(d.y, -d.z, d.x);
+    const V3 up = norm3(cross3(d, diffvec));
+    const V3 rt = cross3(d, up);
+    to = Lpos + rt * smp.x + up * smp.y;
+}
+
 LB_HD float seg_tri_prepared(V3 l1, V3 dir /* = l2 - l1 */, const RayTri &T)
 {
     if (near_zero3(T.n)) return LB_NO_HIT;

@@ -22,11 +22,12 @@ extern "C" {
 
 typedef struct ltrgpu_Ctx ltrgpu_Ctx;
 
-typedef struct ltrgpu_Light {          /* 64 bytes; ref: ltr_Light lighter_int.hpp:906-925 */
+typedef struct ltrgpu_Light {          /* 80 bytes; ref: ltr_Light lighter_int.hpp:906-925 */
     V3 pos;    uint32_t type;
     V3 dir;    float range;
     V3 color;  float power;
     float radius, angle_out_rad, angle_diff, curve;
+    uint32_t n_samples, sample_off, pad0, pad1;   /* sampled-shadow extension: slice of the sample table */
 } ltrgpu_Light;
 
 typedef struct ltrgpu_Inst {           /* 48 bytes */
@@ -50,6 +51,7 @@ typedef struct ltrgpu_Params {         /* the slice of ltr_Config the device nee
     float blur_size;
     int   ds2x, normalmap;
     float amb_brightness;
+    int   shadow_mode;                 /* 0 = the reference's distance march, 1 = sampled any-hit shadow rays (extension) */
 } ltrgpu_Params;
 
 typedef struct ltrgpu_SceneDesc {
@@ -68,6 +70,7 @@ typedef struct ltrgpu_SceneDesc {
     uint32_t n_tris;          const float *tris9; const uint32_t *tri_orig;
     /* lights + light->instance visibility table [n_lights][n_inst] */
     uint32_t n_lights;        const ltrgpu_Light *lights; const uint8_t *light_inst;
+    uint32_t n_light_samples; const float *light_samples4;     /* sampled-shadow extension: float4 per (light, sample) */
     /* probes */
     uint32_t n_probes;        const V3 *probe_pos; const V3 *probe_nrm;
     /* AO hemisphere table: cos_side[s], sin_side[s] for s < ao_num_samples (host libm) */
@@ -84,6 +87,7 @@ typedef struct ltrgpu_Counters {
     uint64_t rad_tile_loads;                   /* 128-lumel column tiles (4 KiB) staged into shared memory by the pair sweep */
     uint64_t kernel_launches, h2d_bytes, d2h_bytes;
     uint64_t rad_batches;                      /* pair-sweep + visibility launch pairs */
+    uint64_t shadow_rays;                      /* sampled-shadow extension: any-hit rays lumel x light x sample */
     float ms_samples, ms_direct, ms_march, ms_radiosity, ms_ao, ms_finalize, ms_rad_pairs, ms_rad_vis, ms_span;
 } ltrgpu_Counters;
 
@@ -145,6 +149,7 @@ int ltrgpu_span_end(ltrgpu_Ctx *ctx);
 
 /* debug dumps */
 int ltrgpu_download_shadow_factors(ltrgpu_Ctx *ctx, uint32_t light, float *out /* local lumels */);
+int ltrgpu_download_shadow_masks(ltrgpu_Ctx *ctx, uint32_t light, uint64_t *out /* local lumels; bit s = sample s blocked */);
 int ltrgpu_download_links(ltrgpu_Ctx *ctx, uint64_t *row_offset, uint32_t *other, float *factor, uint64_t *rows, uint64_t *count);
 
 #ifdef __cplusplus

@@ -144,6 +144,67 @@ direct_march_kernel(const ltrgpu_Light *__restrict__ lights, const BvhNode *__re
     count_add(counters, CNT_TRI_TESTS, ts.tris);
 }
 
+/*
+ * Sampled soft shadows (extension mode, see geom.h shadow_sample_segment): one thread per
+ * (work-list entry, sample) = lumel x light x soft-shadow sample.  Consecutive lanes are the samples of
+ * one lumel/light pair (same origin, targets on one small disk) and neighbouring pairs are neighbouring
+ * lumels, so a warp's rays walk the same BVH nodes; node and triangle records are fetched as float4
+ * through the read-only path (bvh_anyhit).  A blocked sample sets its bit in the pair's 64-bit mask:
+ * bits are OR-reduced over the lanes of the pair first (match_any), one atomic per pair and warp.
+ */
+__global__ void __launch_bounds__(LB_BLOCK)
+direct_sampled_kernel(const ltrgpu_Light *__restrict__ lights, const float4 *__restrict__ samples, const BvhNode *__restrict__ bvh,
+                      const RayTri *__restrict__ raytris, const float4 *__restrict__ lpos, const float4 *__restrict__ lnrm,
+                      uint64_t sh_begin, uint32_t n_local, const uint2 *__restrict__ active, const uint32_t *__restrict__ active_count,
+                      uint32_t spp /* samples per pair slot = max over the lights of this chunk */, uint32_t l0,
+                      unsigned long long *__restrict__ smask, unsigned long long *counters)
+{
+    const unsigned long long total = (unsigned long long)(*active_count) * spp;
+    const unsigned long long total_pad = (total + 31ull) & ~31ull;
+    unsigned rays = 0;
+    TravStats ts = { 0, 0 };
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total_pad; t += (unsigned long long)gridDim.x * blockDim.x) {
+        bool blocked = false, live = false;
+        uint32_t e = 0xffffffffu, s = 0;
+        uint2 a = make_uint2(0, 0);
+        if (t < total) {
+            e = (uint32_t)(t / spp); s = (uint32_t)(t % spp);
+            a = active[e];
+            const ltrgpu_Light L = lights[a.y];
+            if (s < L.n_samples) {
+                live = true;
+                const uint64_t g = sh_begin + a.x;
+                const float4 sm = samples[L.sample_off + s];
+                V3 from, to;
+                shadow_sample_segment(L.type, L.pos, L.range, mk3(sm.x, sm.y, sm.z), ld3(lpos[g]), ld3(lnrm[g]), from, to);
+                const V3 dn = norm3(to - from);                       /* VisibilityTest: both ends pulled in (lighter.cpp:138-147) */
+                blocked = bvh_anyhit(bvh, raytris, from + dn * LB_SMALL, to - dn * LB_SMALL, ts);
+                ++rays;
+            }
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, e);
+        const unsigned lo = __reduce_or_sync(peers, (blocked && s < 32u) ? 1u << s : 0u);
+        const unsigned hi = __reduce_or_sync(peers, (blocked && s >= 32u) ? 1u << (s - 32u) : 0u);
+        if (live && (lo | hi) && (threadIdx.x & 31u) == (unsigned)__ffs(peers) - 1u)
+            atomicOr(smask + (size_t)(a.y - l0) * n_local + a.x, ((unsigned long long)hi << 32) | lo);
+    }
+    count_add(counters, CNT_SHADOW_RAYS, rays);
+    count_add(counters, CNT_RAY_NODE_VISITS, ts.nodes);
+    count_add(counters, CNT_RAY_TRI_TESTS, ts.tris);
+}
+
+/* blocked-sample masks -> shadow factor of every work-list pair: f_vis = 1 - blocked / n */
+__global__ void sampled_resolve_kernel(const ltrgpu_Light *__restrict__ lights, const uint2 *__restrict__ active, const uint32_t *__restrict__ active_count,
+                                       uint32_t n_local, uint32_t l0, const unsigned long long *__restrict__ smask, float *__restrict__ fvis)
+{
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= *active_count) return;
+    const uint2 a = active[e];
+    const size_t at = (size_t)(a.y - l0) * n_local + a.x;
+    const float n = (float)lights[a.y].n_samples;
+    fvis[at] = 1.0f - (float)__popcll(smask[at]) / n;
+}
+
 __global__ void direct_accumulate_kernel(const ltrgpu_Light *__restrict__ lights, uint32_t l0, uint32_t l1,
                                          const uint8_t *__restrict__ light_inst, uint32_t n_inst,
                                          const float4 *__restrict__ lpos, const float4 *__restrict__ lnrm, const uint32_t *__restrict__ linst,
@@ -239,8 +300,9 @@ extern "C" int ltrgpu_direct_light(ltrgpu_Ctx *ctx)
 
     /* lights are processed in chunks so that the factor table stays within a fixed budget;
      * accumulation order over chunks is still the light order */
+    const bool sampled = ctx->params.shadow_mode == 1;
     const size_t budget = (size_t)8 << 30;
-    uint32_t chunk = (uint32_t)(budget / ((size_t)n_local * 12));
+    uint32_t chunk = (uint32_t)(budget / ((size_t)n_local * (sampled ? 20 : 12)));
     if (chunk < 1) chunk = 1;
     if (chunk > ctx->n_lights) chunk = ctx->n_lights;
     if (ctx->params.normalmap) chunk = ctx->n_lights;           /* the normal map needs every factor resident */
@@ -248,6 +310,7 @@ extern "C" int ltrgpu_direct_light(ltrgpu_Ctx *ctx)
     if (dev_alloc(ctx, &ctx->d_fvis, (size_t)chunk * n_local)) return 1;
     if (dev_alloc(ctx, &ctx->d_active, (size_t)chunk * n_local)) return 1;
     if (dev_alloc(ctx, &ctx->d_active_count, 2)) return 1;
+    if (sampled && dev_alloc(ctx, &ctx->d_smask, (size_t)chunk * n_local)) return 1;
 
     cudaEvent_t m0, m1;
     CU_TRY(ctx, cudaEventCreate(&m0));
@@ -264,9 +327,22 @@ extern "C" int ltrgpu_direct_light(ltrgpu_Ctx *ctx)
         CU_LAUNCH_CHECK(ctx);
         CU_TRY(ctx, cudaEventRecord(m0, st));
         unsigned blocks = (unsigned)ctx->num_sms * 16;
-        direct_march_kernel<<<blocks, LB_BLOCK, 0, st>>>(ctx->d_lights, ctx->d_bvh, ctx->d_ptris, ctx->d_lpos, ctx->d_lnrm, ctx->sh_begin,
-                                                         n_local, ctx->d_active, ctx->d_active_count, ctx->d_active_count + 1, l0, ctx->d_fvis, ctx->d_counters);
-        CU_LAUNCH_CHECK(ctx);
+        if (!sampled) {
+            direct_march_kernel<<<blocks, LB_BLOCK, 0, st>>>(ctx->d_lights, ctx->d_bvh, ctx->d_ptris, ctx->d_lpos, ctx->d_lnrm, ctx->sh_begin,
+                                                             n_local, ctx->d_active, ctx->d_active_count, ctx->d_active_count + 1, l0, ctx->d_fvis, ctx->d_counters);
+            CU_LAUNCH_CHECK(ctx);
+        } else {
+            uint32_t spp = 1;
+            for (uint32_t l = l0; l < l1; ++l) if (ctx->h_lights[l].n_samples > spp) spp = ctx->h_lights[l].n_samples;
+            CU_TRY(ctx, cudaMemsetAsync(ctx->d_smask, 0, (size_t)(l1 - l0) * n_local * 8, st));
+            direct_sampled_kernel<<<(unsigned)ctx->num_sms * 32, LB_BLOCK, 0, st>>>(ctx->d_lights, ctx->d_light_samples, ctx->d_bvh, ctx->d_raytris, ctx->d_lpos,
+                                                                                   ctx->d_lnrm, ctx->sh_begin, n_local, ctx->d_active, ctx->d_active_count, spp, l0,
+                                                                                   ctx->d_smask, ctx->d_counters);
+            CU_LAUNCH_CHECK(ctx);
+            sampled_resolve_kernel<<<grid_for((uint64_t)(l1 - l0) * n_local, 256), 256, 0, st>>>(ctx->d_lights, ctx->d_active, ctx->d_active_count, n_local, l0,
+                                                                                               ctx->d_smask, ctx->d_fvis);
+            CU_LAUNCH_CHECK(ctx);
+        }
         CU_TRY(ctx, cudaEventRecord(m1, st));
         direct_accumulate_kernel<<<grid_for(n_local, 256), 256, 0, st>>>(ctx->d_lights, l0, l1, ctx->d_light_inst, ctx->n_inst, ctx->d_lpos,
                                                                         ctx->d_lnrm, ctx->d_linst, ctx->sh_begin, n_local, ctx->d_fvis, ctx->d_lrgb);
@@ -299,6 +375,16 @@ extern "C" int ltrgpu_download_shadow_factors(ltrgpu_Ctx *ctx, uint32_t light, f
     const uint64_t n_local = ctx->sh_end - ctx->sh_begin;
     if (!ctx->d_fvis || light >= ctx->n_lights) { snprintf(ctx->err, sizeof(ctx->err), "no shadow factors"); return 1; }
     CU_TRY(ctx, cudaMemcpyAsync(out, ctx->d_fvis + (size_t)light * n_local, n_local * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int ltrgpu_download_shadow_masks(ltrgpu_Ctx *ctx, uint32_t light, uint64_t *out)
+{
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint64_t n_local = ctx->sh_end - ctx->sh_begin;
+    if (!ctx->d_smask || light >= ctx->n_lights) { snprintf(ctx->err, sizeof(ctx->err), "no shadow masks (sampled mode only)"); return 1; }
+    CU_TRY(ctx, cudaMemcpyAsync(out, ctx->d_smask + (size_t)light * n_local, n_local * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }

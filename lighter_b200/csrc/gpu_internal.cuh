@@ -69,6 +69,8 @@ struct ltrgpu_Ctx {
 
     /* ---- direct light ---- */
     float *d_fvis = nullptr;                  /* [n_lights][local lumels] shadow factors */
+    unsigned long long *d_smask = nullptr;    /* sampled mode: [n_lights][local lumels] blocked-sample bit masks */
+    float4 *d_light_samples = nullptr;        /* sampled mode: per (light, sample) table */
     uint2 *d_active = nullptr;                /* (local lumel, light) pairs to march */
     uint32_t *d_active_count = nullptr;
 
@@ -93,7 +95,7 @@ struct ltrgpu_Ctx {
 };
 
 enum { CNT_MARCHES = 0, CNT_DIST_QUERIES, CNT_AO_SEGMENTS, CNT_CORR_RAYS, CNT_RAD_PAIRS, CNT_RAD_SEGMENTS,
-       CNT_RAD_LINKS, CNT_NODE_VISITS, CNT_TRI_TESTS, CNT_RAY_NODE_VISITS, CNT_RAY_TRI_TESTS, CNT_RAD_TILE_LOADS, CNT_COUNT };
+       CNT_RAD_LINKS, CNT_NODE_VISITS, CNT_TRI_TESTS, CNT_RAY_NODE_VISITS, CNT_RAY_TRI_TESTS, CNT_RAD_TILE_LOADS, CNT_SHADOW_RAYS, CNT_COUNT };
 
 #define CU_TRY(ctx, call)                                                                          \
     do {                                                                                           \

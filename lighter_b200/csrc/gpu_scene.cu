@@ -203,7 +203,7 @@ static void free_bake_state(ltrgpu_Ctx *ctx)
     dev_free(&ctx->d_texkey); dev_free(&ctx->d_texidx);
     dev_free(&ctx->d_lpos); dev_free(&ctx->d_lnrm); dev_free(&ctx->d_lrad); dev_free(&ctx->d_lrgb);
     dev_free(&ctx->d_lloc); dev_free(&ctx->d_linst); dev_free(&ctx->d_lnmap);
-    dev_free(&ctx->d_fvis); dev_free(&ctx->d_active); dev_free(&ctx->d_active_count);
+    dev_free(&ctx->d_fvis); dev_free(&ctx->d_smask); dev_free(&ctx->d_active); dev_free(&ctx->d_active_count);
     dev_free(&ctx->d_rad_rowoff); dev_free(&ctx->d_rad_other); dev_free(&ctx->d_rad_factor); dev_free(&ctx->d_rad_sidx);
     dev_free(&ctx->d_image); dev_free(&ctx->d_image_tmp); dev_free(&ctx->d_mask); dev_free(&ctx->d_mask_tmp);
     dev_free(&ctx->d_normals); dev_free(&ctx->d_out);
@@ -219,7 +219,7 @@ extern "C" void ltrgpu_destroy(ltrgpu_Ctx *ctx)
     dev_free(&ctx->d_inst); dev_free(&ctx->d_wpos); dev_free(&ctx->d_wnrm); dev_free(&ctx->d_vtex); dev_free(&ctx->d_ltex);
     dev_free(&ctx->d_rtris); dev_free(&ctx->d_rnodes); dev_free(&ctx->d_ritems); dev_free(&ctx->d_rtree_tris); dev_free(&ctx->d_rtree_ptris);
     dev_free(&ctx->d_bvh); dev_free(&ctx->d_ptris); dev_free(&ctx->d_raytris); dev_free(&ctx->d_tri_orig);
-    dev_free(&ctx->d_lights); dev_free(&ctx->d_light_inst); dev_free(&ctx->d_probe_pos); dev_free(&ctx->d_probe_nrm);
+    dev_free(&ctx->d_lights); dev_free(&ctx->d_light_inst); dev_free(&ctx->d_light_samples); dev_free(&ctx->d_probe_pos); dev_free(&ctx->d_probe_nrm);
     dev_free(&ctx->d_ao_cos); dev_free(&ctx->d_ao_sin); dev_free(&ctx->d_blur_kernel); dev_free(&ctx->d_counters);
     free(ctx->h_inst); free(ctx->h_lights); free(ctx->h_inst_lumel_off);
     free(ctx->h_out_off); free(ctx->h_out_w); free(ctx->h_out_h);
@@ -313,6 +313,7 @@ extern "C" int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *d)
     if (dev_upload(ctx, &ctx->d_tri_orig, d->tri_orig, d->n_tris)) return 1;
     if (dev_upload(ctx, &ctx->d_lights, d->lights, d->n_lights)) return 1;
     if (dev_upload(ctx, &ctx->d_light_inst, d->light_inst, (size_t)d->n_lights * d->n_inst)) return 1;
+    if (dev_upload(ctx, &ctx->d_light_samples, d->light_samples4, d->n_light_samples)) return 1;
     if (dev_upload(ctx, &ctx->d_probe_pos, d->probe_pos, d->n_probes)) return 1;
     if (dev_upload(ctx, &ctx->d_probe_nrm, d->probe_nrm, d->n_probes)) return 1;
     int ns = d->params.ao_num_samples > 0 ? d->params.ao_num_samples : 0;
@@ -365,7 +366,7 @@ extern "C" int ltrgpu_get_counters(ltrgpu_Ctx *ctx, ltrgpu_Counters *out)
     h.marches = c[CNT_MARCHES]; h.distance_queries = c[CNT_DIST_QUERIES]; h.ao_segments = c[CNT_AO_SEGMENTS];
     h.correction_rays = c[CNT_CORR_RAYS]; h.rad_pairs = c[CNT_RAD_PAIRS]; h.rad_segments = c[CNT_RAD_SEGMENTS];
     h.rad_links = c[CNT_RAD_LINKS]; h.node_visits = c[CNT_NODE_VISITS]; h.tri_tests = c[CNT_TRI_TESTS];
-    h.ray_node_visits = c[CNT_RAY_NODE_VISITS]; h.ray_tri_tests = c[CNT_RAY_TRI_TESTS]; h.rad_tile_loads = c[CNT_RAD_TILE_LOADS];
+    h.ray_node_visits = c[CNT_RAY_NODE_VISITS]; h.ray_tri_tests = c[CNT_RAY_TRI_TESTS]; h.rad_tile_loads = c[CNT_RAD_TILE_LOADS]; h.shadow_rays = c[CNT_SHADOW_RAYS];
     *out = h;
     return 0;
 }

@@ -46,6 +46,7 @@ struct Light {
     float range, power, light_radius;
     int shadow_sample_count;
     float spot_angle_out, spot_angle_in, spot_curve;
+    float randoff;             /* the randf() the reference draws per ltr_LightAdd (lighter.cpp:1300) */
 };
 
 struct ltr_Scene {
@@ -75,6 +76,7 @@ struct ltr_Scene {
     /* diagnostics */
     ltrx_Stats stats;
     std::string error;                        /* first fatal error of the bake, "" if none */
+    int shadow_mode = 0;                      /* 0 = reference distance march, 1 = sampled any-hit shadow rays (ltrx_SetShadowMode) */
     int keep_debug = 0;                       /* keep stage arrays for ltrx_Get* */
     struct Bake *bake = nullptr;              /* pipeline state incl. device buffers (bake.cpp) */
 };

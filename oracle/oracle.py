@@ -71,6 +71,11 @@ class Oracle:
         tris, pts = _c(tris), _c(pts)
         return np.array([self.L.o_scene_distance(_f(tris), len(tris), _f(pts[i])) for i in range(len(pts))], np.float32)
 
+    def visibility_test(self, tris, a, b):
+        """ltr_Scene::VisibilityTest (lighter.cpp:138-147): 1 = the segment, pulled in 0.001 at both ends, is BLOCKED."""
+        tris, a, b = _c(tris), _c(a), _c(b)
+        return np.array([self.L.o_visibility_test(_f(tris), len(tris), _f(a[i]), _f(b[i])) for i in range(len(a))], np.int32)
+
     def anyhit_raw(self, tris, a, b):
         tris, a, b = _c(tris), _c(a), _c(b)
         return np.array([self.L.o_anyhit_raw(_f(tris), len(tris), _f(a[i]), _f(b[i])) for i in range(len(a))], np.int32)

@@ -286,3 +286,60 @@ def test_rebake_on_resident_scene_is_idempotent():
     assert bits_equal(first, second)
     ref = api.bake(sc)["lightmaps"][0]["rgb"]
     assert bits_equal(first, ref)
+
+
+# ---- sampled soft shadows (extension mode): lumel x light x sample any-hit rays --------------------
+@pytest.mark.parametrize("name", ["mesh1", "mesh2"])
+def test_sampled_shadow_rays_hit_miss_equals_oracle(name, oracle):
+    """north_star (3): one any-hit ray per lumel x light x soft-shadow sample.  Hit/miss of every sampled
+    ray is compared with the oracle's VisibilityTest (brute force over the scene triangles) on the segment
+    the host evaluation of the kernel's own segment function returns; bar: bit-exact, no grazing exemptions
+    needed because both sides see identical end points."""
+    sc = scenes.NAMED[name]()
+    for lt in sc.lights:
+        lt.shadow_sample_count = 8
+    tris = scene_tris(sc)
+    rng = np.random.default_rng(11)
+    with api.BakeHandle(sc, debug=True, shadow_mode=1) as b:
+        b.run()
+        st = b.stats()
+        assert st["n_shadow_rays"] > 0 and st["n_marches"] == 0 and st["n_distance_queries"] == 0
+        insts = [b.lumels(i) for i in range(len(sc.instances) + 1)]
+        pos = np.concatenate([i["pos"] for i in insts]); nrm = np.concatenate([i["nrm"] for i in insts])
+        checked = blocked_seen = open_seen = rays = 0
+        for l, lt in enumerate(sc.lights):
+            masks, fv = b.shadow_masks(l), b.shadow_factors(l)
+            assert len(masks) == len(pos)
+            active = np.nonzero((fv != 0) | (masks != 0))[0]
+            rays += 8 * len(active)
+            assert np.array_equal(fv[active], (np.float32(1.0) - np.array([bin(int(m)).count("1") for m in masks[active]], np.float32) / np.float32(8)))
+            for g in rng.choice(active, size=min(60, len(active)), replace=False):
+                for s in range(8):
+                    a, c = b.shadow_segment(l, s, pos[g], nrm[g])
+                    want = oracle.visibility_test(tris, a[None], c[None])[0]
+                    got = (int(masks[g]) >> s) & 1
+                    assert want == got, (name, l, int(g), s)
+                    checked += 1; blocked_seen += got; open_seen += 1 - got
+        assert rays == st["n_shadow_rays"]
+        assert checked > 500 and blocked_seen > 20 and open_seen > 20
+
+
+def test_sampled_shadow_single_centre_sample_is_a_hard_shadow(oracle):
+    """radius 0, one sample: the ray goes to the light centre; f_vis is 0 or 1 and equals the oracle's
+    VisibilityTest from the offset lumel to the light."""
+    sc = scenes.scene_mesh1()
+    for lt in sc.lights:
+        lt.shadow_sample_count = 1; lt.light_radius = 0.0
+    tris = scene_tris(sc)
+    with api.BakeHandle(sc, debug=True, shadow_mode=1) as b:
+        b.run()
+        insts = [b.lumels(i) for i in range(len(sc.instances) + 1)]
+        pos = np.concatenate([i["pos"] for i in insts]); nrm = np.concatenate([i["nrm"] for i in insts])
+        fv, masks = b.shadow_factors(0), b.shadow_masks(0)
+        active = np.nonzero((fv != 0) | (masks != 0))[0]
+        assert set(np.unique(fv[active]).tolist()) <= {0.0, 1.0} and len(active) > 1000
+        sel = active[:: max(1, len(active) // 300)]
+        frm = pos[sel] + nrm[sel] * np.float32(0.005)
+        to = np.tile(np.asarray(sc.lights[0].position, np.float32), (len(sel), 1))
+        want = oracle.visibility_test(tris, frm, to)
+        assert np.array_equal(want, (masks[sel] & 1).astype(want.dtype))
