@@ -39,6 +39,7 @@ struct ltrgpu_Ctx {
     RefNode *d_rnodes = nullptr;
     int32_t *d_ritems = nullptr;
     float *d_rtree_tris = nullptr;
+    float4 *d_rtree_boxes = nullptr;          /* 2 float4 per reference-order triangle: its box (conservative pre-test) */
     PreparedTri *d_rtree_ptris = nullptr;     /* the same triangles with the point-query terms precomputed (lumel_fix_kernel) */
     BvhNode *d_bvh = nullptr;
     PreparedTri *d_ptris = nullptr;

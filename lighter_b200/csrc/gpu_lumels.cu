@@ -250,11 +250,20 @@ __global__ void probe_emit_kernel(const V3 *pos, const V3 *nrm, uint32_t n, floa
 /* ---------------------------------------------------------------------------------------------
  * reference-order tree walks (used only here; see reftree.h for why order matters)
  * ------------------------------------------------------------------------------------------- */
-struct RefView { const RefNode *nodes; const int32_t *items; const float *tris9; const PreparedTri *ptris; };
+struct RefView { const RefNode *nodes; const int32_t *items; const float *tris9; const PreparedTri *ptris; const float4 *boxes; };
 
 __device__ __forceinline__ void ld_tri9(const float *t, V3 &a, V3 &b, V3 &c)
 {
     a = mk3(t[0], t[1], t[2]); b = mk3(t[3], t[4], t[5]); c = mk3(t[6], t[7], t[8]);
+}
+
+/* does the segment's own box overlap the triangle box widened by 1e-4 relative + absolute?  (necessary for a hit) */
+__device__ __forceinline__ bool seg_box_overlap(V3 a, V3 b, float4 lo, float4 hi)
+{
+    const float e = 1e-4f;
+    const float ex = e * (1.0f + fmaxf(fabsf(lo.x), fabsf(hi.x))), ey = e * (1.0f + fmaxf(fabsf(lo.y), fabsf(hi.y))), ez = e * (1.0f + fmaxf(fabsf(lo.z), fabsf(hi.z)));
+    return !(fminf(a.x, b.x) > hi.x + ex || fmaxf(a.x, b.x) < lo.x - ex || fminf(a.y, b.y) > hi.y + ey || fmaxf(a.y, b.y) < lo.y - ey ||
+             fminf(a.z, b.z) > hi.z + ez || fmaxf(a.z, b.z) < lo.z - ez);
 }
 
 /* closest hit inside one instance tree, first-met wins ties (ref: lighter_math.cpp:835-871) */
@@ -274,6 +283,12 @@ __device__ float reftree_closest(const RefView &v, V3 from, V3 to, int *tid)
             int cnt = v.items[N.ido];
             for (int k = 0; k < cnt; ++k) {
                 int id = v.items[N.ido + 1 + k];
+                {   /* conservative pre-test: a segment that misses the triangle's box (widened) cannot hit the triangle.
+                     * Degenerate reference trees put thousands of triangles in one leaf (a flat 40x40 ceiling ends up
+                     * as ONE leaf of 7848), and the reference tests them all. */
+                    const float4 bl = __ldg(v.boxes + 2ull * id), bh = __ldg(v.boxes + 2ull * id + 1);
+                    if (!seg_box_overlap(from, to, bl, bh)) continue;
+                }
                 V3 a, b, c;
                 ld_tri9(v.tris9 + 9ull * id, a, b, c);
                 float d = seg_tri(from, to, a, b, c);
@@ -290,6 +305,16 @@ __device__ float reftree_closest(const RefView &v, V3 from, V3 to, int *tid)
  * sample position -- the reference mutates P while it walks (lighter_math.cpp:991-1038). */
 __device__ __forceinline__ void offset_one_tri(const RefView &v, int id, V3 &P, V3 N, float dist)
 {
+    {   /* conservative pre-test with the CURRENT position: the distance to a triangle is at least the distance to
+         * its box, so a box farther than dist (with slack for rounding) cannot pass `ndst < dist` */
+        const float4 bl = __ldg(v.boxes + 2ull * id), bh = __ldg(v.boxes + 2ull * id + 1);
+        const float dx = fmaxf(fmaxf(bl.x - P.x, P.x - bh.x), 0.f), dy = fmaxf(fmaxf(bl.y - P.y, P.y - bh.y), 0.f), dz = fmaxf(fmaxf(bl.z - P.z, P.z - bh.z), 0.f);
+        /* slack: 1 % of dist plus the worst rounding error of the reference's float evaluation at these coordinate
+         * magnitudes (dot products of ~|P|-sized terms: a few ulps of |P|), so the pre-test can never reject a triangle
+         * the exact test would accept */
+        const float lim = dist * 1.01f + 2e-6f * (1.0f + fabsf(P.x) + fabsf(P.y) + fabsf(P.z));
+        if (dx * dx + dy * dy + dz * dz > lim * lim) return;
+    }
     PreparedTri PT;
     load_prepared(v.ptris + id, PT);
     float ndst = point_tri_distance_prepared(P, PT);
@@ -382,7 +407,7 @@ lumel_fix_kernel(const ltrgpu_Inst *__restrict__ inst, uint32_t n_inst, RefView 
                 const uint32_t mm = base + (uint32_t)__ffs(mask) - 1u;
                 mask &= mask - 1u;
                 const ltrgpu_Inst I = inst[mm];
-                RefView v = { all.nodes + I.node_off, all.items + I.item_off, all.tris9 + 9ull * I.tri_off, all.ptris + I.tri_off };
+                RefView v = { all.nodes + I.node_off, all.items + I.item_off, all.tris9 + 9ull * I.tri_off, all.ptris + I.tri_off, all.boxes + 2ull * I.tri_off };
                 reftree_offset_sample(v, P, N, dist, active);
             }
         }
@@ -503,7 +528,7 @@ extern "C" int ltrgpu_generate_lumels(ltrgpu_Ctx *ctx, uint64_t *inst_lumel_off)
         if (b > n) b = n;
         if (e > n) e = n;
         if (b < ctx->n_probes) b = ctx->n_probes;
-        RefView all = { ctx->d_rnodes, ctx->d_ritems, ctx->d_rtree_tris, ctx->d_rtree_ptris };
+        RefView all = { ctx->d_rnodes, ctx->d_ritems, ctx->d_rtree_tris, ctx->d_rtree_ptris, ctx->d_rtree_boxes };
         if (e > b) {
             lumel_fix_kernel<<<grid_for(e - b, LB_BLOCK), LB_BLOCK, 0, st>>>(
                 ctx->d_inst, ctx->n_inst, all, ctx->d_bvh, ctx->d_raytris, ctx->d_ptris, ctx->d_tri_orig, b, e,

@@ -2,6 +2,7 @@
 #include "gpu_internal.cuh"
 
 #include <stdlib.h>
+#include <time.h>
 
 #include <map>
 #include <mutex>
@@ -167,9 +168,28 @@ __global__ void prepare_tris_kernel(const float *__restrict__ tris9, uint32_t n,
     }
 }
 
+__global__ void tri_boxes_kernel(const float *__restrict__ tris9, uint32_t n, float4 *__restrict__ boxes)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *t = tris9 + 9ull * i;
+    V3 a = mk3(t[0], t[1], t[2]), b = mk3(t[3], t[4], t[5]), c = mk3(t[6], t[7], t[8]);
+    V3 lo = min3(a, min3(b, c)), hi = max3(a, max3(b, c));
+    boxes[2ull * i] = make_float4(lo.x, lo.y, lo.z, 0.f);
+    boxes[2ull * i + 1] = make_float4(hi.x, hi.y, hi.z, 0.f);
+}
+
 extern "C" int ltrgpu_create(ltrgpu_Ctx **out, int device)
 {
     *out = nullptr;
+    const bool trace = getenv("LTR_TRACE") != nullptr;
+    struct timespec t0; clock_gettime(CLOCK_MONOTONIC, &t0);
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t);
+        fprintf(stderr, "[ltr gpu] create %-24s %8.2f ms\n", what, (t.tv_sec - t0.tv_sec) * 1e3 + (t.tv_nsec - t0.tv_nsec) * 1e-6);
+        t0 = t;
+    };
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -183,9 +203,10 @@ extern "C" int ltrgpu_create(ltrgpu_Ctx **out, int device)
     ctx->device = device;
     *out = ctx;
     CU_TRY(ctx, cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CU_TRY(ctx, cudaGetDeviceProperties(&prop, device));
-    ctx->num_sms = prop.multiProcessorCount;
+    lap("device count + set");
+    /* the SM count only (cudaGetDeviceProperties fills ~100 fields and costs tens of milliseconds per call) */
+    CU_TRY(ctx, cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device));
+    lap("attributes");
     CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU_TRY(ctx, cudaEventCreate(&ctx->ev0));
     CU_TRY(ctx, cudaEventCreate(&ctx->ev1));
@@ -193,8 +214,10 @@ extern "C" int ltrgpu_create(ltrgpu_Ctx **out, int device)
     CU_TRY(ctx, cudaEventCreate(&ctx->ev_span1));
     CU_TRY(ctx, cudaEventCreate(&ctx->ev_k0));
     CU_TRY(ctx, cudaEventCreate(&ctx->ev_k1));
+    lap("stream + events");
     if (dev_alloc(ctx, &ctx->d_counters, CNT_COUNT)) return 1;
     CU_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, CNT_COUNT * sizeof(unsigned long long), ctx->stream));
+    lap("counters");
     return 0;
 }
 
@@ -217,7 +240,7 @@ extern "C" void ltrgpu_destroy(ltrgpu_Ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_bake_state(ctx);
     dev_free(&ctx->d_inst); dev_free(&ctx->d_wpos); dev_free(&ctx->d_wnrm); dev_free(&ctx->d_vtex); dev_free(&ctx->d_ltex);
-    dev_free(&ctx->d_rtris); dev_free(&ctx->d_rnodes); dev_free(&ctx->d_ritems); dev_free(&ctx->d_rtree_tris); dev_free(&ctx->d_rtree_ptris);
+    dev_free(&ctx->d_rtris); dev_free(&ctx->d_rnodes); dev_free(&ctx->d_ritems); dev_free(&ctx->d_rtree_tris); dev_free(&ctx->d_rtree_ptris); dev_free(&ctx->d_rtree_boxes);
     dev_free(&ctx->d_bvh); dev_free(&ctx->d_ptris); dev_free(&ctx->d_raytris); dev_free(&ctx->d_tri_orig);
     dev_free(&ctx->d_lights); dev_free(&ctx->d_light_inst); dev_free(&ctx->d_light_samples); dev_free(&ctx->d_probe_pos); dev_free(&ctx->d_probe_nrm);
     dev_free(&ctx->d_ao_cos); dev_free(&ctx->d_ao_sin); dev_free(&ctx->d_blur_kernel); dev_free(&ctx->d_counters);
@@ -332,7 +355,10 @@ extern "C" int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *d)
     }
     /* reference-order triangles (lumel generation): point-query terms precomputed once instead of per query */
     if (dev_alloc(ctx, &ctx->d_rtree_ptris, d->n_rtree_tris)) return 1;
+    if (dev_alloc(ctx, &ctx->d_rtree_boxes, (size_t)d->n_rtree_tris * 2)) return 1;
     if (d->n_rtree_tris) {
+        tri_boxes_kernel<<<grid_for(d->n_rtree_tris, 256), 256, 0, ctx->stream>>>(ctx->d_rtree_tris, d->n_rtree_tris, ctx->d_rtree_boxes);
+        CU_LAUNCH_CHECK(ctx);
         prepare_tris_kernel<<<grid_for(d->n_rtree_tris, 256), 256, 0, ctx->stream>>>(ctx->d_rtree_tris, d->n_rtree_tris, ctx->d_rtree_ptris, nullptr);
         CU_LAUNCH_CHECK(ctx);
     }

@@ -519,6 +519,7 @@ WORKLOADS = {
     "config4": (scene_config4, {}),
     "config4_sibling": (scene_config4, dict(tiles=2, lm_size=64, target_tris=1_000_000 // 64)),
     "config4_quarter": (scene_config4, dict(tiles=8, lm_size=256, target_tris=250_000)),
+    "config5": (scene_config5, dict(n_lights=64, samples=16)),
     "mesh1": (scene_mesh1, {}),
     "mesh2": (scene_mesh2, {}),
 }
