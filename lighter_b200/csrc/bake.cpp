@@ -18,6 +18,8 @@
 #include <time.h>
 
 #include <algorithm>
+#include <atomic>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -207,16 +209,29 @@ void host_prepare(ltr_Scene *S)
     const bool trace = getenv("LTR_TRACE") != nullptr;          /* host-side phase timings on stderr */
     double tt = now_s();
     auto lap = [&](const char *what) { if (trace) { double t = now_s(); fprintf(stderr, "[ltr host] accel %-28s %8.2f ms\n", what, (t - tt) * 1e3); tt = t; } };
-    /* per instance: useful triangles of shadow-casting parts, and their reference-order tree */
+    /* per instance: useful triangles of shadow-casting parts (phase 1), then -- concurrently -- the flat scene BVH
+     * over all of them on a background thread and the per-instance reference-order trees on this one */
     std::vector<std::vector<float>> itris(ni);
+    std::vector<std::vector<Box3>> iboxes(ni);
     std::vector<RefTree> itree(ni);
-    auto build_one = [&](size_t i) {
-        if (i == 0) { itree[0].build(nullptr, 0); return; }
+    auto parallel_instances = [&](const std::function<void(size_t)> &fn) {
+        unsigned nthreads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)ni));
+        std::atomic<size_t> next{0};
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nthreads; ++t)
+            pool.emplace_back([&]() { for (size_t i; (i = next.fetch_add(1)) < ni;) fn(i); });
+        for (auto &th : pool) th.join();
+    };
+    parallel_instances([&](size_t i) {
+        if (i == 0) return;
         MeshInstance *mi = S->instances[i];
         ltr_Mesh *mesh = mi->mesh;
         std::vector<float> &T = itris[i];
-        std::vector<Box3> boxes;
+        std::vector<Box3> &boxes = iboxes[i];
         const V3 *wp = B.wpos.data() + vbase[i];
+        size_t cap = 0;
+        for (const MeshPart &mp : mesh->parts) if (mp.shadow) cap += mp.index_count / 3;
+        T.reserve(cap * 9); boxes.reserve(cap);
         for (const MeshPart &mp : mesh->parts) {
             if (!mp.shadow) continue;
             const V3 *vb = wp + mp.vertex_offset;
@@ -230,16 +245,31 @@ void host_prepare(ltr_Scene *S)
                 boxes.push_back(b);
             }
         }
-        itree[i].build(boxes.data(), boxes.size());
-    };
-    {
-        unsigned nthreads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)ni));
-        std::atomic<size_t> next{0};
+    });
+    std::vector<size_t> o_stri(ni + 1, 0);
+    for (size_t i = 0; i < ni; ++i) o_stri[i + 1] = o_stri[i] + ((i && S->instances[i]->shadow) ? itris[i].size() / 9 : 0);
+    std::vector<float> scene_tris(o_stri[ni] * 9);
+    parallel_instances([&](size_t i) {
+        if (i && S->instances[i]->shadow && !itris[i].empty()) memcpy(&scene_tris[o_stri[i] * 9], itris[i].data(), itris[i].size() * 4);
+    });
+    lap("world triangles");
+    int leaf_max = BVH_LEAF_MAX;
+    if (const char *e = getenv("LTR_BVH_LEAF")) leaf_max = atoi(e);
+    const size_t nst = scene_tris.size() / 9;
+    std::thread bvh_thread([&]() {
+        build_scene_bvh(scene_tris.data(), nst, B.bvh, leaf_max, 0);
+        /* triangles in BVH order */
+        B.bvh_tris.resize(nst * 9);
+        const unsigned T = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
         std::vector<std::thread> pool;
-        for (unsigned t = 0; t < nthreads; ++t)
-            pool.emplace_back([&]() { for (size_t i; (i = next.fetch_add(1)) < ni;) build_one(i); });
+        for (unsigned t = 0; t < T; ++t)
+            pool.emplace_back([&, t]() {
+                for (size_t k = nst * t / T; k < nst * (t + 1) / T; ++k) memcpy(&B.bvh_tris[k * 9], &scene_tris[(size_t)B.bvh.order[k] * 9], 36);
+            });
         for (auto &th : pool) th.join();
-    }
+    });
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } bvh_joiner{ bvh_thread };
+    parallel_instances([&](size_t i) { itree[i].build(i ? iboxes[i].data() : nullptr, i ? iboxes[i].size() : 0); });
     lap("instance trees (threads)");
     S->completion.store(0.99f);
     /* instance tree over the root boxes (invalid boxes are dropped by the builder) */
@@ -251,9 +281,8 @@ void host_prepare(ltr_Scene *S)
     /* concatenate trees, lay out the texel space, list raster triangles: offsets first, then every
      * instance copies its own slices (threads) -- at 1M triangles this is ~130 MB of host memory */
     uint64_t texel_off = 0;
-    std::vector<float> scene_tris;
     {
-        std::vector<size_t> o_node(ni + 1, 0), o_item(ni + 1, 0), o_tri(ni + 1, 0), o_stri(ni + 1, 0), o_rtri(ni + 1, 0);
+        std::vector<size_t> o_node(ni + 1, 0), o_item(ni + 1, 0), o_tri(ni + 1, 0), o_rtri(ni + 1, 0);
         for (size_t i = 0; i < ni; ++i) {
             ltrgpu_Inst &I = B.inst[i];
             MeshInstance *mi = S->instances[i];
@@ -268,19 +297,13 @@ void host_prepare(ltr_Scene *S)
             o_node[i + 1] = o_node[i] + itree[i].nodes.size();
             o_item[i + 1] = o_item[i] + itree[i].items.size();
             o_tri[i + 1] = o_tri[i] + itris[i].size() / 9;
-            o_stri[i + 1] = o_stri[i] + (I.shadow ? itris[i].size() / 9 : 0);
             o_rtri[i + 1] = o_rtri[i] + nrt;
         }
         B.rnodes.resize(o_node[ni]); B.ritems.resize(o_item[ni]); B.rtree_tris.resize(o_tri[ni] * 9); B.rtris.resize(o_rtri[ni]);
-        scene_tris.resize(o_stri[ni] * 9);
         auto copy_one = [&](size_t i) {
-            const ltrgpu_Inst &I = B.inst[i];
             if (!itree[i].nodes.empty()) memcpy(&B.rnodes[o_node[i]], itree[i].nodes.data(), itree[i].nodes.size() * sizeof(itree[i].nodes[0]));
             if (!itree[i].items.empty()) memcpy(&B.ritems[o_item[i]], itree[i].items.data(), itree[i].items.size() * sizeof(itree[i].items[0]));
-            if (!itris[i].empty()) {
-                memcpy(&B.rtree_tris[o_tri[i] * 9], itris[i].data(), itris[i].size() * 4);
-                if (I.shadow) memcpy(&scene_tris[o_stri[i] * 9], itris[i].data(), itris[i].size() * 4);
-            }
+            if (!itris[i].empty()) memcpy(&B.rtree_tris[o_tri[i] * 9], itris[i].data(), itris[i].size() * 4);
             if (!i) return;
             MeshInstance *mi = S->instances[i];
             ltr_Mesh *mesh = mi->mesh;
@@ -303,16 +326,9 @@ void host_prepare(ltr_Scene *S)
         for (auto &th : pool) th.join();
     }
     lap("concatenate + raster list");
-    /* flat scene BVH over the shadow-casting triangles */
-    int leaf_max = BVH_LEAF_MAX;
-    if (const char *e = getenv("LTR_BVH_LEAF")) leaf_max = atoi(e);
-    const size_t nst = scene_tris.size() / 9;
-    build_scene_bvh(scene_tris.data(), nst, B.bvh, leaf_max, 0);
-    lap("scene BVH");
-    B.bvh_tris.resize(nst * 9);
-    for (size_t k = 0; k < nst; ++k) memcpy(&B.bvh_tris[k * 9], &scene_tris[(size_t)B.bvh.order[k] * 9], 36);
-
-    lap("reorder triangles");
+    /* flat scene BVH over the shadow-casting triangles: built in the background since the world triangles were ready */
+    bvh_thread.join();
+    lap("scene BVH (overlapped) + reorder");
     /* lights and the light -> instance table */
     const size_t nl = S->lights.size();
     B.lights.resize(nl);
