@@ -114,6 +114,9 @@ LTRAPI int ltrx_test_spiral_dirs(const float *nrm3, const float *randoff, u32 n,
  * "<count> ids...") and the flat scene BVH with a structural self-check (returns 0 when it fails) */
 LTRAPI int ltrx_test_reftree(const float *tris9, u32 ntris, void *nodes_out, u32 nodes_cap, int32_t *items_out, u32 items_cap,
                              u32 *n_nodes, u32 *n_items);
+/* n draws of the process's libc rand() stream as randf() = rand()/RAND_MAX (the AO pass's per-lumel offsets); returns 1
+ * when the lock-free table-level path was used, 0 for the plain rand() loop -- same values, same libc state afterwards */
+LTRAPI int ltrx_test_rand_fill(float *out, uint64_t n);
 LTRAPI int ltrx_test_bvh(const float *tris9, u32 ntris, int leaf_max, u32 *n_nodes, u32 *depth, u32 *order_out, float *bounds6);
 
 #ifdef __cplusplus

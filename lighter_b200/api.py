@@ -121,7 +121,8 @@ LTRX_SYMBOLS = ["ltrx_Version", "ltrx_SetDevice", "ltrx_NcclUniqueId", "ltrx_Set
                 "ltrx_GetError", "ltrx_Prepare", "ltrx_BakeResident", "ltrx_Finish", "ltrx_SetDebug", "ltrx_GetLumels",
                 "ltrx_GetLinks", "ltrx_GetShadowFactors", "ltrx_SetShadowMode", "ltrx_GetShadowMasks", "ltrx_ShadowSampleSegment",
                 "ltrx_test_point_tri_distance", "ltrx_test_seg_tri",
-                "ltrx_test_scene_queries", "ltrx_test_march", "ltrx_test_spiral_dirs", "ltrx_test_reftree", "ltrx_test_bvh"]
+                "ltrx_test_scene_queries", "ltrx_test_march", "ltrx_test_spiral_dirs", "ltrx_test_reftree", "ltrx_test_bvh",
+                "ltrx_test_rand_fill"]
 
 _lib = None
 
@@ -182,6 +183,7 @@ def lib() -> C.CDLL:
     L.ltrx_test_march.argtypes = [fp, u32, fp, fp, fp, u32, fp, C.POINTER(u32)]
     L.ltrx_test_spiral_dirs.argtypes = [fp, fp, u32, C.c_int, fp]
     L.ltrx_test_reftree.argtypes = [fp, u32, C.c_void_p, u32, C.c_void_p, u32, C.POINTER(u32), C.POINTER(u32)]
+    L.ltrx_test_rand_fill.argtypes = [fp, C.c_uint64]
     L.ltrx_test_bvh.argtypes = [fp, u32, C.c_int, C.POINTER(u32), C.POINTER(u32), C.c_void_p, fp]
     _lib = L
     return L
@@ -194,6 +196,17 @@ def srand(seed: int = 1) -> None:
     """Reset the process's libc rand() stream.  The bake consumes rand() exactly as the reference does
     (one draw per light added, one per lumel in the AO pass); srand(1) is the state of a fresh process."""
     _libc.srand(C.c_uint(seed))
+
+
+def libc_rand() -> int:
+    return _libc.rand()
+
+
+def test_rand_fill(n: int):
+    """(values, fast) -- n randf() draws of the libc stream through the library's replay routine."""
+    out = np.zeros(max(n, 1), np.float32)
+    fast = lib().ltrx_test_rand_fill(_fp(out), n)
+    return out[:n], bool(fast)
 
 
 def shard_range(n: int, rank: int, world: int) -> tuple:

@@ -26,6 +26,7 @@
 
 #include "gpu.h"
 #include "nccl_dl.h"
+#include "randfill.h"
 #include "scene.h"
 
 namespace {
@@ -502,7 +503,7 @@ void gpu_stages(ltr_Scene *S)
     const bool user_code_before_ao = cfg.bounce_count && cfg.sample_fn;   /* a material callback might itself call rand(): keep the reference's order */
     if (cfg.ao_distance) randjob.v.resize(n ? n : 1);
     if (cfg.ao_distance && !user_code_before_ao) {
-        randjob.th = std::thread([&randjob, n]() { for (uint64_t i = 0; i < n; ++i) randjob.v[i] = (float)rand() / (float)RAND_MAX; });
+        randjob.th = std::thread([&randjob, n]() { rand_fill(randjob.v.data(), n); });
     }
 
     t0 = now_s();
@@ -575,8 +576,8 @@ void gpu_stages(ltr_Scene *S)
         /* replay of the reference's rand() consumption: one randf() per lumel, instance by
          * instance (probe container first), lumel index ascending (lighter.cpp:819,1130-1135) */
         if (randjob.th.joinable()) randjob.th.join();
-        else for (uint64_t i = 0; i < n; ++i) randjob.v[i] = (float)rand() / (float)RAND_MAX;
-        gpu_check(S, ltrgpu_ambient_occlusion(B.gpu, randjob.v.data()), "ambient occlusion");
+        else rand_fill(randjob.v.data(), n);
+        gpu_check(S, ltrgpu_ambient_occlusion(B.gpu, randjob.v.data() + sb), "ambient occlusion");
         S->completion.store(1.f);
     }
     S->stats.t_ao = now_s() - t0;
@@ -855,6 +856,8 @@ int ltrx_test_bvh(const float *tris9, u32 ntris, int leaf_max, u32 *n_nodes, u32
     for (u32 t = 0; t < ntris; ++t) if (seen[t] != 1) return 0;
     return 1;
 }
+
+int ltrx_test_rand_fill(float *out, uint64_t n) { return rand_fill(out, n) ? 1 : 0; }
 
 int ltrx_SetShadowMode(ltr_Scene *scene, int mode)
 {

@@ -123,7 +123,7 @@ int ltrgpu_download_lumels(ltrgpu_Ctx *ctx, float *pos3, float *nrm3, uint32_t *
  * NULL for (1,1,1) / no extra emission on mesh lumels (probes always diffuse 0, area 0). */
 int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const float *emissive3, int bounces);
 
-/* stage: ambient occlusion; randoff has one value per global lumel (host rand() replay) */
+/* stage: ambient occlusion; randoff has one value per lumel OF THIS SHARD (host rand() replay, sliced by the caller) */
 int ltrgpu_ambient_occlusion(ltrgpu_Ctx *ctx, const float *randoff);
 
 /* stage: finalize (gather shards, scatter, 3x dilation, blur, ds2x, normal map) */

@@ -46,7 +46,7 @@ ao_trace_kernel(const BvhNode *__restrict__ bvh, const RayTri *__restrict__ rayt
         const uint64_t g = sh_begin + li;
         const V3 SP = ld3(lpos[g]), SN = ld3(lnrm[g]);
         const V3 origin = SP + SN * (LB_SMALL * 2);
-        const V3 ray = spiral_dir(SN, randoff[g], s, cos_side[s], sin_side[s]) * ao_distance;
+        const V3 ray = spiral_dir(SN, randoff[li], s, cos_side[s], sin_side[s]) * ao_distance;
         const V3 B = origin + ray;
         const V3 dn = norm3(B - origin);
         const V3 mA = origin + dn * LB_SMALL, mB = B - dn * LB_SMALL;
@@ -94,7 +94,7 @@ extern "C" int ltrgpu_ambient_occlusion(ltrgpu_Ctx *ctx, const float *randoff_ho
     if (n_local64 == 0) return 0;
     const uint32_t n_local = (uint32_t)n_local64;
     float *d_rand = nullptr, *d_hits = nullptr;
-    if (dev_upload(ctx, &d_rand, randoff_host, ctx->n_lumels)) return 1;
+    if (dev_upload(ctx, &d_rand, randoff_host, n_local)) return 1;       /* this shard's offsets only */
     if (dev_alloc(ctx, &d_hits, (size_t)n_local * (ns > 0 ? ns : 1))) return 1;
     CU_TRY(ctx, cudaEventRecord(ctx->ev0, st));
     if (ns > 0) {

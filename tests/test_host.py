@@ -115,3 +115,20 @@ def test_flat_bvh_invariants():
     tris = np.tile(np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32), (4000, 1))
     b = api.test_bvh(tris, 4)
     assert b["ok"] and b["depth"] <= 20
+
+
+def test_rand_replay_equals_libc_stream_and_leaves_libc_in_step():
+    """The AO pass consumes one libc rand() per lumel (lighter.cpp:819).  The library's fast replay must give
+    exactly rand()/RAND_MAX, and the libc generator must afterwards stand where that many rand() calls leave
+    it (a caller's own rand() use, and the next bake, continue the same stream)."""
+    RAND_MAX = 2147483647
+    for seed, n in ((1, 5), (1, 1000), (20261017, 100_003), (7, 0)):
+        api.srand(seed)
+        want = np.array([api.libc_rand() for _ in range(n)], np.float64)
+        tail_want = [api.libc_rand() for _ in range(40)]
+        api.srand(seed)
+        got, fast = api.test_rand_fill(n)
+        tail_got = [api.libc_rand() for _ in range(40)]
+        assert fast, "glibc table-level path expected in this image"
+        assert np.array_equal(got, (want.astype(np.float32) / np.float32(RAND_MAX)))
+        assert tail_got == tail_want
