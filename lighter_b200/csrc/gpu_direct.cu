@@ -63,7 +63,8 @@ __device__ __forceinline__ bool light_is_supported(unsigned type) { return type 
 __global__ void direct_classify_kernel(const ltrgpu_Light *__restrict__ lights, uint32_t l0, uint32_t l1,
                                        const uint8_t *__restrict__ light_inst, uint32_t n_inst,
                                        const float4 *__restrict__ lpos, const float4 *__restrict__ lnrm, const uint32_t *__restrict__ linst,
-                                       uint64_t sh_begin, uint32_t n_local, uint2 *__restrict__ active, uint32_t *active_count)
+                                       uint64_t sh_begin, uint32_t n_local, uint2 *__restrict__ active, uint32_t *active_count,
+                                       unsigned long long *__restrict__ smask /* sampled mode: cleared for every listed pair */)
 {
     const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t l = l0 + blockIdx.y;
@@ -83,7 +84,10 @@ __global__ void direct_classify_kernel(const ltrgpu_Light *__restrict__ lights, 
         unsigned base = 0;
         if (lane == 0) base = atomicAdd(active_count, (unsigned)__popc(mask));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (want) active[base + __popc(mask & ((1u << lane) - 1u))] = make_uint2(li, l);
+        if (want) {
+            active[base + __popc(mask & ((1u << lane) - 1u))] = make_uint2(li, l);
+            if (smask) smask[(size_t)(l - l0) * n_local + li] = 0ull;
+        }
     }
 }
 
@@ -159,6 +163,7 @@ direct_sampled_kernel(const ltrgpu_Light *__restrict__ lights, const float4 *__r
                       uint32_t spp /* samples per pair slot = max over the lights of this chunk */, uint32_t l0,
                       unsigned long long *__restrict__ smask, unsigned long long *counters)
 {
+    const bool spp_pow2 = (spp & (spp - 1u)) == 0u;
     const unsigned long long total = (unsigned long long)(*active_count) * spp;
     const unsigned long long total_pad = (total + 31ull) & ~31ull;
     unsigned rays = 0;
@@ -182,11 +187,24 @@ direct_sampled_kernel(const ltrgpu_Light *__restrict__ lights, const float4 *__r
                 ++rays;
             }
         }
-        const unsigned peers = __match_any_sync(0xffffffffu, e);
-        const unsigned lo = __reduce_or_sync(peers, (blocked && s < 32u) ? 1u << s : 0u);
-        const unsigned hi = __reduce_or_sync(peers, (blocked && s >= 32u) ? 1u << (s - 32u) : 0u);
-        if (live && (lo | hi) && (threadIdx.x & 31u) == (unsigned)__ffs(peers) - 1u)
-            atomicOr(smask + (size_t)(a.y - l0) * n_local + a.x, ((unsigned long long)hi << 32) | lo);
+        unsigned lo = (blocked && s < 32u) ? 1u << s : 0u, hi = (blocked && s >= 32u) ? 1u << (s - 32u) : 0u;
+        bool leader;
+        if (spp_pow2) {
+            /* the lanes of a pair are an aligned group of min(spp,32) lanes (t is lane-aligned): butterfly OR */
+            const unsigned gw = spp < 32u ? spp : 32u;
+            for (unsigned o = 1; o < gw; o <<= 1) { lo |= __shfl_xor_sync(0xffffffffu, lo, o); hi |= __shfl_xor_sync(0xffffffffu, hi, o); }
+            leader = ((threadIdx.x & 31u) & (gw - 1u)) == 0u;
+        } else {
+            const unsigned peers = __match_any_sync(0xffffffffu, e);
+            lo = __reduce_or_sync(peers, lo); hi = __reduce_or_sync(peers, hi);
+            leader = (threadIdx.x & 31u) == (unsigned)__ffs(peers) - 1u;
+        }
+        if (live && (lo | hi) && leader) {
+            unsigned long long *dst = smask + (size_t)(a.y - l0) * n_local + a.x;
+            const unsigned long long bits = ((unsigned long long)hi << 32) | lo;
+            if (spp <= 32u) *dst = bits;                                  /* one warp owns the whole pair */
+            else atomicOr(dst, bits);
+        }
     }
     count_add(counters, CNT_SHADOW_RAYS, rays);
     count_add(counters, CNT_RAY_NODE_VISITS, ts.nodes);
@@ -197,12 +215,13 @@ direct_sampled_kernel(const ltrgpu_Light *__restrict__ lights, const float4 *__r
 __global__ void sampled_resolve_kernel(const ltrgpu_Light *__restrict__ lights, const uint2 *__restrict__ active, const uint32_t *__restrict__ active_count,
                                        uint32_t n_local, uint32_t l0, const unsigned long long *__restrict__ smask, float *__restrict__ fvis)
 {
-    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= *active_count) return;
-    const uint2 a = active[e];
-    const size_t at = (size_t)(a.y - l0) * n_local + a.x;
-    const float n = (float)lights[a.y].n_samples;
-    fvis[at] = 1.0f - (float)__popcll(smask[at]) / n;
+    const uint32_t n_active = *active_count;
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_active; e += gridDim.x * blockDim.x) {
+        const uint2 a = active[e];
+        const size_t at = (size_t)(a.y - l0) * n_local + a.x;
+        const float n = (float)lights[a.y].n_samples;
+        fvis[at] = 1.0f - (float)__popcll(smask[at]) / n;
+    }
 }
 
 __global__ void direct_accumulate_kernel(const ltrgpu_Light *__restrict__ lights, uint32_t l0, uint32_t l1,
@@ -323,7 +342,7 @@ extern "C" int ltrgpu_direct_light(ltrgpu_Ctx *ctx)
         CU_TRY(ctx, cudaMemsetAsync(ctx->d_fvis, 0, (size_t)(l1 - l0) * n_local * 4, st));
         dim3 grid(grid_for(n_local, 256), l1 - l0);
         direct_classify_kernel<<<grid, 256, 0, st>>>(ctx->d_lights, l0, l1, ctx->d_light_inst, ctx->n_inst, ctx->d_lpos, ctx->d_lnrm,
-                                                     ctx->d_linst, ctx->sh_begin, n_local, ctx->d_active, ctx->d_active_count);
+                                                     ctx->d_linst, ctx->sh_begin, n_local, ctx->d_active, ctx->d_active_count, sampled ? ctx->d_smask : nullptr);
         CU_LAUNCH_CHECK(ctx);
         CU_TRY(ctx, cudaEventRecord(m0, st));
         unsigned blocks = (unsigned)ctx->num_sms * 16;
@@ -334,12 +353,11 @@ extern "C" int ltrgpu_direct_light(ltrgpu_Ctx *ctx)
         } else {
             uint32_t spp = 1;
             for (uint32_t l = l0; l < l1; ++l) if (ctx->h_lights[l].n_samples > spp) spp = ctx->h_lights[l].n_samples;
-            CU_TRY(ctx, cudaMemsetAsync(ctx->d_smask, 0, (size_t)(l1 - l0) * n_local * 8, st));
             direct_sampled_kernel<<<(unsigned)ctx->num_sms * 32, LB_BLOCK, 0, st>>>(ctx->d_lights, ctx->d_light_samples, ctx->d_bvh, ctx->d_raytris, ctx->d_lpos,
                                                                                    ctx->d_lnrm, ctx->sh_begin, n_local, ctx->d_active, ctx->d_active_count, spp, l0,
                                                                                    ctx->d_smask, ctx->d_counters);
             CU_LAUNCH_CHECK(ctx);
-            sampled_resolve_kernel<<<grid_for((uint64_t)(l1 - l0) * n_local, 256), 256, 0, st>>>(ctx->d_lights, ctx->d_active, ctx->d_active_count, n_local, l0,
+            sampled_resolve_kernel<<<(unsigned)ctx->num_sms * 16, 256, 0, st>>>(ctx->d_lights, ctx->d_active, ctx->d_active_count, n_local, l0,
                                                                                                ctx->d_smask, ctx->d_fvis);
             CU_LAUNCH_CHECK(ctx);
         }
