@@ -63,8 +63,7 @@ __device__ __forceinline__ bool light_is_supported(unsigned type) { return type 
 __global__ void direct_classify_kernel(const ltrgpu_Light *__restrict__ lights, uint32_t l0, uint32_t l1,
                                        const uint8_t *__restrict__ light_inst, uint32_t n_inst,
                                        const float4 *__restrict__ lpos, const float4 *__restrict__ lnrm, const uint32_t *__restrict__ linst,
-                                       uint64_t sh_begin, uint32_t n_local, uint2 *__restrict__ active, uint32_t *active_count,
-                                       unsigned long long *__restrict__ smask /* sampled mode: cleared for every listed pair */)
+                                       uint64_t sh_begin, uint32_t n_local, uint2 *__restrict__ active, uint32_t *active_count)
 {
     const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t l = l0 + blockIdx.y;
@@ -86,7 +85,6 @@ __global__ void direct_classify_kernel(const ltrgpu_Light *__restrict__ lights, 
         base = __shfl_sync(0xffffffffu, base, 0);
         if (want) {
             active[base + __popc(mask & ((1u << lane) - 1u))] = make_uint2(li, l);
-            if (smask) smask[(size_t)(l - l0) * n_local + li] = 0ull;
         }
     }
 }
@@ -183,7 +181,7 @@ direct_sampled_kernel(const ltrgpu_Light *__restrict__ lights, const float4 *__r
                 V3 from, to;
                 shadow_sample_segment(L.type, L.pos, L.range, mk3(sm.x, sm.y, sm.z), ld3(lpos[g]), ld3(lnrm[g]), from, to);
                 const V3 dn = norm3(to - from);                       /* VisibilityTest: both ends pulled in (lighter.cpp:138-147) */
-                blocked = bvh_anyhit(bvh, raytris, from + dn * LB_SMALL, to - dn * LB_SMALL, ts);
+                blocked = bvh_anyhit<2>(bvh, raytris, from + dn * LB_SMALL, to - dn * LB_SMALL, ts);   /* shadow rays are often blocked: test early */
                 ++rays;
             }
         }
@@ -342,7 +340,7 @@ extern "C" int ltrgpu_direct_light(ltrgpu_Ctx *ctx)
         CU_TRY(ctx, cudaMemsetAsync(ctx->d_fvis, 0, (size_t)(l1 - l0) * n_local * 4, st));
         dim3 grid(grid_for(n_local, 256), l1 - l0);
         direct_classify_kernel<<<grid, 256, 0, st>>>(ctx->d_lights, l0, l1, ctx->d_light_inst, ctx->n_inst, ctx->d_lpos, ctx->d_lnrm,
-                                                     ctx->d_linst, ctx->sh_begin, n_local, ctx->d_active, ctx->d_active_count, sampled ? ctx->d_smask : nullptr);
+                                                     ctx->d_linst, ctx->sh_begin, n_local, ctx->d_active, ctx->d_active_count);
         CU_LAUNCH_CHECK(ctx);
         CU_TRY(ctx, cudaEventRecord(m0, st));
         unsigned blocks = (unsigned)ctx->num_sms * 16;
@@ -353,6 +351,7 @@ extern "C" int ltrgpu_direct_light(ltrgpu_Ctx *ctx)
         } else {
             uint32_t spp = 1;
             for (uint32_t l = l0; l < l1; ++l) if (ctx->h_lights[l].n_samples > spp) spp = ctx->h_lights[l].n_samples;
+            CU_TRY(ctx, cudaMemsetAsync(ctx->d_smask, 0, (size_t)(l1 - l0) * n_local * 8, st));     /* pairs that are not listed keep mask 0 */
             direct_sampled_kernel<<<(unsigned)ctx->num_sms * 32, LB_BLOCK, 0, st>>>(ctx->d_lights, ctx->d_light_samples, ctx->d_bvh, ctx->d_raytris, ctx->d_lpos,
                                                                                    ctx->d_lnrm, ctx->sh_begin, n_local, ctx->d_active, ctx->d_active_count, spp, l0,
                                                                                    ctx->d_smask, ctx->d_counters);

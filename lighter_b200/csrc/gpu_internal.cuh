@@ -349,6 +349,7 @@ __device__ __forceinline__ float bvh_segment(const BvhNode *__restrict__ nodes, 
  * the boundary and never NaN), absolute slack on the slab comparison.  Box tests may use any
  * conservative arithmetic; the triangle test keeps the reference's exact operand order.
  */
+template <int FLUSH = 10>  /* postponed triangles that trigger the test phase: high for rays that mostly miss, low for rays that are often blocked */
 __device__ __forceinline__ bool bvh_anyhit(const BvhNode *__restrict__ nodes, const RayTri *__restrict__ tris, V3 l1, V3 l2, TravStats &ts)
 {
     /* Two-phase ("while-while") walk: the node loop only COLLECTS the triangles of the leaves it meets; they are
@@ -356,7 +357,7 @@ __device__ __forceinline__ bool bvh_anyhit(const BvhNode *__restrict__ nodes, co
      * ncu on the one-phase version: node tests ran with 28 of 32 lanes, but the triangle tests -- a quarter of the
      * instructions -- with 9, because lanes reach their leaves at different iterations.  A miss (98 % of the
      * radiosity rays) costs exactly the same work either way; a hit is found a little later. */
-    constexpr int TQ = 24;
+    constexpr int TQ = FLUSH + 14;                   /* FLUSH - 1 pending + two leaves of up to 7 triangles */
     int stack_n[BVH_STACK];
     int tq[TQ];
     int sp = 0, nq = 0;
@@ -393,7 +394,7 @@ __device__ __forceinline__ bool bvh_anyhit(const BvhNode *__restrict__ nodes, co
                 else stack_n[sp++] = k.y;
             }
             node = next >= 0 ? next : (sp ? stack_n[--sp] : -1);
-            if (nq > TQ - 14) break;                     /* room for two more leaves of up to 7 triangles each */
+            if (nq >= FLUSH) break;                      /* enough postponed work: test it (a blocked ray stops here) */
         }
         while (nq) {
             RayTri T;
