@@ -259,7 +259,7 @@ void host_prepare(ltr_Scene *S)
     const size_t nst = scene_tris.size() / 9;
     std::thread bvh_thread([&]() {
         build_scene_bvh(scene_tris.data(), nst, B.bvh, leaf_max, 0);
-        /* triangles in BVH order */
+        /* triangles in BVH order (threads), while this thread collapses the tree into its 4-wide form */
         B.bvh_tris.resize(nst * 9);
         const unsigned T = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
         std::vector<std::thread> pool;
@@ -267,6 +267,7 @@ void host_prepare(ltr_Scene *S)
             pool.emplace_back([&, t]() {
                 for (size_t k = nst * t / T; k < nst * (t + 1) / T; ++k) memcpy(&B.bvh_tris[k * 9], &scene_tris[(size_t)B.bvh.order[k] * 9], 36);
             });
+        build_bvh4(B.bvh);
         for (auto &th : pool) th.join();
     });
     struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } bvh_joiner{ bvh_thread };
@@ -428,6 +429,7 @@ void upload(ltr_Scene *S)
     d.n_ritems = (uint32_t)B.ritems.size(); d.ritems = B.ritems.data();
     d.n_rtree_tris = (uint32_t)(B.rtree_tris.size() / 9); d.rtree_tris9 = B.rtree_tris.data();
     d.n_bvh_nodes = (uint32_t)B.bvh.nodes.size(); d.bvh = B.bvh.nodes.data();
+    d.n_bvh4_nodes = (uint32_t)B.bvh.nodes4.size(); d.bvh4 = B.bvh.nodes4.data();
     d.n_tris = (uint32_t)(B.bvh_tris.size() / 9); d.tris9 = B.bvh_tris.data(); d.tri_orig = B.bvh.order.data();
     d.n_lights = (uint32_t)B.lights.size(); d.lights = B.lights.data(); d.light_inst = B.light_inst.data();
     d.n_light_samples = (uint32_t)(B.light_samples.size() / 4); d.light_samples4 = B.light_samples.data();
@@ -854,6 +856,42 @@ int ltrx_test_bvh(const float *tris9, u32 ntris, int leaf_max, u32 *n_nodes, u32
         }
     }
     for (u32 t = 0; t < ntris; ++t) if (seen[t] != 1) return 0;
+    /* the 4-wide collapse: reachable from its root, every triangle in exactly one leaf slot and inside that slot's box,
+     * every inner slot's box containing the boxes of the node it points to */
+    build_bvh4(bvh);
+    if (bvh.nodes4.empty()) return 0;
+    std::vector<int> seen4(ntris, 0);
+    std::vector<char> visited(bvh.nodes4.size(), 0);
+    std::vector<int32_t> st{ 0 };
+    while (!st.empty()) {
+        const int32_t i = st.back(); st.pop_back();
+        if (i < 0 || (size_t)i >= bvh.nodes4.size() || visited[i]) return 0;
+        visited[i] = 1;
+        const Bvh4Node &n = bvh.nodes4[i];
+        for (int j = 0; j < 4; ++j) {
+            if (n.c[j] == BVH4_EMPTY) continue;
+            const float lo[3] = { n.lox[j], n.loy[j], n.loz[j] }, hi[3] = { n.hix[j], n.hiy[j], n.hiz[j] };
+            if (n.c[j] >= 0) {
+                if ((size_t)n.c[j] >= bvh.nodes4.size()) return 0;
+                const Bvh4Node &c = bvh.nodes4[n.c[j]];
+                for (int q = 0; q < 4; ++q) {
+                    if (c.c[q] == BVH4_EMPTY) continue;
+                    if (c.lox[q] < lo[0] || c.loy[q] < lo[1] || c.loz[q] < lo[2] || c.hix[q] > hi[0] || c.hiy[q] > hi[1] || c.hiz[q] > hi[2]) return 0;
+                }
+                st.push_back(n.c[j]);
+            } else {
+                uint32_t code = ~n.c[j], first = code >> 3, cnt = code & 7u;
+                for (uint32_t t = first; t < first + cnt; ++t) {
+                    if (t >= ntris) return 0;
+                    seen4[t]++;
+                    const float *v = tris9 + 9 * (size_t)bvh.order[t];
+                    for (int c = 0; c < 9; ++c) if (v[c] < lo[c % 3] || v[c] > hi[c % 3]) return 0;
+                }
+            }
+        }
+    }
+    for (u32 t = 0; t < ntris; ++t) if (seen4[t] != 1) return 0;
+    for (char v : visited) if (!v) return 0;
     return 1;
 }
 

@@ -360,3 +360,60 @@ void build_scene_bvh(const float *tris9, size_t count, SceneBvh &out, int leaf_m
     }
     lap("flatten");
 }
+
+
+void build_bvh4(SceneBvh &bvh)
+{
+    const std::vector<BvhNode> &n2 = bvh.nodes;
+    std::vector<Bvh4Node> &n4 = bvh.nodes4;
+    n4.clear();
+    if (n2.empty()) return;
+    n4.reserve(n2.size() / 2 + 1);
+    struct Slot { Box3 b; int32_t code; };                 /* code: binary-tree child code (>=0 inner index in n2, <0 leaf) */
+    auto child = [&](const BvhNode &n, int k) {
+        Slot s;
+        if (k == 0) { s.b.lo = mk3(n.lo0x, n.lo0y, n.lo0z); s.b.hi = mk3(n.hi0x, n.hi0y, n.hi0z); s.code = n.c0; }
+        else        { s.b.lo = mk3(n.lo1x, n.lo1y, n.lo1z); s.b.hi = mk3(n.hi1x, n.hi1y, n.hi1z); s.code = n.c1; }
+        return s;
+    };
+    /* iterative pre-order: (binary node to expand, slot in n4) */
+    struct Item { int32_t n2i, n4i; };
+    std::vector<Item> st;
+    n4.push_back(Bvh4Node());
+    st.push_back({ 0, 0 });
+    while (!st.empty()) {
+        const Item it = st.back(); st.pop_back();
+        /* start from the two binary children; while there is room, open the inner slot with the largest box
+         * (the one a ray is most likely to enter) -- nodes end up full even where the binary tree is lopsided */
+        Slot slots[4];
+        int ns = 0;
+        slots[ns++] = child(n2[it.n2i], 0);
+        slots[ns++] = child(n2[it.n2i], 1);
+        while (ns < 4) {
+            int best = -1;
+            float best_area = -1.f;
+            for (int j = 0; j < ns; ++j)
+                if (slots[j].code >= 0) { const float a = half_area(slots[j].b); if (a > best_area) { best_area = a; best = j; } }
+            if (best < 0) break;
+            const int32_t open = slots[best].code;
+            slots[best] = child(n2[open], 0);
+            slots[ns++] = child(n2[open], 1);
+        }
+        Bvh4Node node;
+        int32_t kids[4] = { -1, -1, -1, -1 };
+        for (int j = 0; j < 4; ++j) {
+            if (j < ns && !(slots[j].code < 0 && ((~slots[j].code) & 7) == 0)) {
+                node.lox[j] = slots[j].b.lo.x; node.loy[j] = slots[j].b.lo.y; node.loz[j] = slots[j].b.lo.z;
+                node.hix[j] = slots[j].b.hi.x; node.hiy[j] = slots[j].b.hi.y; node.hiz[j] = slots[j].b.hi.z;
+                if (slots[j].code >= 0) { kids[j] = slots[j].code; node.c[j] = (int32_t)n4.size(); n4.push_back(Bvh4Node()); }
+                else node.c[j] = slots[j].code;
+            } else {
+                node.lox[j] = node.loy[j] = node.loz[j] = FMAXV; node.hix[j] = node.hiy[j] = node.hiz[j] = -FMAXV;
+                node.c[j] = BVH4_EMPTY;
+            }
+            node.pad[j] = 0;
+        }
+        n4[it.n4i] = node;
+        for (int j = 3; j >= 0; --j) if (kids[j] >= 0) st.push_back({ kids[j], node.c[j] });
+    }
+}

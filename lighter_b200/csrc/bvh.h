@@ -25,8 +25,19 @@ struct BvhNode {                 /* 64 bytes */
 #define BVH_LEAF_MAX 2      /* measured on B200 (configs 3, 4): leaves of <=2 beat 4 by 10-12 % and 7 by 25-30 % on the traversal kernels */
 #define BVH_STACK 64
 
+/* The same tree with every other level removed: a node holds the boxes of up to four grand-children (SoA, so each
+ * coordinate of the four boxes is one float4 load).  Used by the any-hit walks, which visit every overlapped node anyway:
+ * half the iterations, half the loop/stack overhead per box test (the walks are instruction-issue bound). */
+#define BVH4_EMPTY 0x7fffffff
+struct Bvh4Node {                /* 128 bytes */
+    float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
+    int32_t c[4];                /* >=0 inner Bvh4Node index; <0 leaf (same code as BvhNode); BVH4_EMPTY unused slot */
+    int32_t pad[4];
+};
+
 struct SceneBvh {
     std::vector<BvhNode> nodes;          /* nodes[0] = root */
+    std::vector<Bvh4Node> nodes4;        /* nodes4[0] = root of the collapsed tree (build_bvh4) */
     std::vector<uint32_t> order;         /* order[k] = original triangle index stored at slot k */
     Box3 bounds;
     int depth = 0;
@@ -34,3 +45,5 @@ struct SceneBvh {
 
 /* tris: 9 floats per triangle (world space).  threads <= 0: hardware concurrency. */
 void build_scene_bvh(const float *tris9, size_t count, SceneBvh &out, int leaf_max, int threads);
+/* collapse out.nodes (binary) into out.nodes4 (4-wide): the largest inner child is opened until the node has four slots */
+void build_bvh4(SceneBvh &bvh);

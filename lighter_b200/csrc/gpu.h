@@ -67,6 +67,7 @@ typedef struct ltrgpu_SceneDesc {
     uint32_t n_rtree_tris;    const float *rtree_tris9;
     /* flat scene BVH over shadow-casting triangles, triangles already in BVH order */
     uint32_t n_bvh_nodes;     const BvhNode *bvh;
+    uint32_t n_bvh4_nodes;    const Bvh4Node *bvh4;            /* 4-wide collapse of the same tree (any-hit walks) */
     uint32_t n_tris;          const float *tris9; const uint32_t *tri_orig;
     /* lights + light->instance visibility table [n_lights][n_inst] */
     uint32_t n_lights;        const ltrgpu_Light *lights; const uint8_t *light_inst;

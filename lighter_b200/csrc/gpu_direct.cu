@@ -155,7 +155,7 @@ direct_march_kernel(const ltrgpu_Light *__restrict__ lights, const BvhNode *__re
  * bits are OR-reduced over the lanes of the pair first (match_any), one atomic per pair and warp.
  */
 __global__ void __launch_bounds__(LB_BLOCK)
-direct_sampled_kernel(const ltrgpu_Light *__restrict__ lights, const float4 *__restrict__ samples, const BvhNode *__restrict__ bvh,
+direct_sampled_kernel(const ltrgpu_Light *__restrict__ lights, const float4 *__restrict__ samples, const Bvh4Node *__restrict__ bvh,
                       const RayTri *__restrict__ raytris, const float4 *__restrict__ lpos, const float4 *__restrict__ lnrm,
                       uint64_t sh_begin, uint32_t n_local, const uint2 *__restrict__ active, const uint32_t *__restrict__ active_count,
                       uint32_t spp /* samples per pair slot = max over the lights of this chunk */, uint32_t l0,
@@ -181,7 +181,7 @@ direct_sampled_kernel(const ltrgpu_Light *__restrict__ lights, const float4 *__r
                 V3 from, to;
                 shadow_sample_segment(L.type, L.pos, L.range, mk3(sm.x, sm.y, sm.z), ld3(lpos[g]), ld3(lnrm[g]), from, to);
                 const V3 dn = norm3(to - from);                       /* VisibilityTest: both ends pulled in (lighter.cpp:138-147) */
-                blocked = bvh_anyhit<2>(bvh, raytris, from + dn * LB_SMALL, to - dn * LB_SMALL, ts);   /* shadow rays are often blocked: test early */
+                blocked = bvh4_anyhit<2>(bvh, raytris, from + dn * LB_SMALL, to - dn * LB_SMALL, ts);   /* shadow rays are often blocked: test early */
                 ++rays;
             }
         }
@@ -352,7 +352,7 @@ extern "C" int ltrgpu_direct_light(ltrgpu_Ctx *ctx)
             uint32_t spp = 1;
             for (uint32_t l = l0; l < l1; ++l) if (ctx->h_lights[l].n_samples > spp) spp = ctx->h_lights[l].n_samples;
             CU_TRY(ctx, cudaMemsetAsync(ctx->d_smask, 0, (size_t)(l1 - l0) * n_local * 8, st));     /* pairs that are not listed keep mask 0 */
-            direct_sampled_kernel<<<(unsigned)ctx->num_sms * 32, LB_BLOCK, 0, st>>>(ctx->d_lights, ctx->d_light_samples, ctx->d_bvh, ctx->d_raytris, ctx->d_lpos,
+            direct_sampled_kernel<<<(unsigned)ctx->num_sms * 32, LB_BLOCK, 0, st>>>(ctx->d_lights, ctx->d_light_samples, ctx->d_bvh4, ctx->d_raytris, ctx->d_lpos,
                                                                                    ctx->d_lnrm, ctx->sh_begin, n_local, ctx->d_active, ctx->d_active_count, spp, l0,
                                                                                    ctx->d_smask, ctx->d_counters);
             CU_LAUNCH_CHECK(ctx);

@@ -42,6 +42,7 @@ struct ltrgpu_Ctx {
     float4 *d_rtree_boxes = nullptr;          /* 2 float4 per reference-order triangle: its box (conservative pre-test) */
     PreparedTri *d_rtree_ptris = nullptr;     /* the same triangles with the point-query terms precomputed (lumel_fix_kernel) */
     BvhNode *d_bvh = nullptr;
+    Bvh4Node *d_bvh4 = nullptr;               /* 4-wide collapse of d_bvh for the any-hit walks */
     PreparedTri *d_ptris = nullptr;
     RayTri *d_raytris = nullptr;
     uint32_t *d_tri_orig = nullptr;
@@ -395,6 +396,57 @@ __device__ __forceinline__ bool bvh_anyhit(const BvhNode *__restrict__ nodes, co
             }
             node = next >= 0 ? next : (sp ? stack_n[--sp] : -1);
             if (nq >= FLUSH) break;                      /* enough postponed work: test it (a blocked ray stops here) */
+        }
+        while (nq) {
+            RayTri T;
+            load_raytri(tris + tq[--nq], T);
+            ts.tris++;
+            if (seg_tri_prepared(l1, d, T) < 1.0f) return true;
+        }
+        if (node < 0) return false;
+    }
+}
+
+/*
+ * The same any-hit walk on the 4-wide tree (bvh.h Bvh4Node): one iteration tests four boxes (six float4 loads for the
+ * boxes, one for the child codes).  A visit is counted as two node units (128 bytes = two 64-byte binary nodes).
+ */
+template <int FLUSH = 10>
+__device__ __forceinline__ bool bvh4_anyhit(const Bvh4Node *__restrict__ nodes, const RayTri *__restrict__ tris, V3 l1, V3 l2, TravStats &ts)
+{
+    constexpr int TQ = FLUSH + 28;                   /* FLUSH - 1 pending + four leaves of up to 7 triangles */
+    int stack_n[BVH_STACK];
+    int tq[TQ];
+    int sp = 0, nq = 0;
+    const V3 d = l2 - l1;
+    const float ix = d.x != 0 ? 1.0f / d.x : 1e30f, iy = d.y != 0 ? 1.0f / d.y : 1e30f, iz = d.z != 0 ? 1.0f / d.z : 1e30f;
+    int node = 0;
+    for (;;) {
+        while (node >= 0) {
+            const float4 *n4 = reinterpret_cast<const float4 *>(nodes + node);
+            const float4 lx = __ldg(n4), ly = __ldg(n4 + 1), lz = __ldg(n4 + 2), hx = __ldg(n4 + 3), hy = __ldg(n4 + 4), hz = __ldg(n4 + 5);
+            const int4 k = __ldg(reinterpret_cast<const int4 *>(n4 + 6));
+            ts.nodes += 2;
+            int next = -1;
+#define LB_BVH4_CHILD(LX, LY, LZ, HX, HY, HZ, C)                                                                        \
+            {                                                                                                           \
+                const float x0 = ((LX) - l1.x) * ix, x1 = ((HX) - l1.x) * ix, y0 = ((LY) - l1.y) * iy, y1 = ((HY) - l1.y) * iy; \
+                const float z0 = ((LZ) - l1.z) * iz, z1 = ((HZ) - l1.z) * iz;                                           \
+                const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));                 \
+                const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));                 \
+                if (t0 <= t1 + 2e-6f && (C) != BVH4_EMPTY) {                                                            \
+                    if ((C) < 0) { const unsigned code = ~(C); for (unsigned t = 0, first = code >> 3; t < (code & 7u); ++t) tq[nq++] = (int)(first + t); } \
+                    else if (next < 0) next = (C);                                                                      \
+                    else stack_n[sp++] = (C);                                                                           \
+                }                                                                                                       \
+            }
+            LB_BVH4_CHILD(lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, k.x)
+            LB_BVH4_CHILD(lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, k.y)
+            LB_BVH4_CHILD(lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, k.z)
+            LB_BVH4_CHILD(lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, k.w)
+#undef LB_BVH4_CHILD
+            node = next >= 0 ? next : (sp ? stack_n[--sp] : -1);
+            if (nq >= FLUSH) break;
         }
         while (nq) {
             RayTri T;

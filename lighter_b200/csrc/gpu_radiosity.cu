@@ -483,7 +483,7 @@ template <int G> static size_t rad_sweep_smem() { return sizeof(RadColBuf<G>) * 
 
 /* one thread per candidate: blocked segment -> directed link(s) keyed (row sorted position, partner original index) */
 __global__ void __launch_bounds__(LB_BLOCK)
-rad_visibility_kernel(const BvhNode *__restrict__ bvh, const RayTri *__restrict__ raytris, const float4 *__restrict__ spos,
+rad_visibility_kernel(const Bvh4Node *__restrict__ bvh, const RayTri *__restrict__ raytris, const float4 *__restrict__ spos,
                       const uint32_t *__restrict__ sidx, const RadCand *__restrict__ cand, unsigned long long n_cand,
                       uint32_t my_k0, uint32_t my_k1, unsigned long long *__restrict__ keys, float *__restrict__ factors,
                       unsigned long long *link_count, uint4 *__restrict__ mirror, unsigned long long mirror_cap, unsigned long long *mirror_count,
@@ -507,7 +507,7 @@ rad_visibility_kernel(const BvhNode *__restrict__ bvh, const RayTri *__restrict_
             const V3 dn = norm3(B - A);
             const V3 mA = A + dn * LB_SMALL, mB = B - dn * LB_SMALL;
             ++segs;
-            if (bvh_anyhit(bvh, raytris, mA, mB, ts))
+            if (bvh4_anyhit(bvh, raytris, mA, mB, ts))
                 emit = 1u | ((c.b >= my_k0 && c.b < my_k1) ? 2u : 4u);
         }
         const unsigned cnt = __popc(emit & 3u);
@@ -868,7 +868,7 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
                 unsigned cap = (unsigned)ctx->num_sms * 32;
                 unsigned blocks = want > cap ? cap : (unsigned)want;
                 RAD_CU(cudaEventRecord(ctx->ev_k0, st));
-                rad_visibility_kernel<<<blocks, LB_BLOCK, 0, st>>>(ctx->d_bvh, ctx->d_raytris, spos, sidx, cand, nc, (uint32_t)k0, (uint32_t)k1,
+                rad_visibility_kernel<<<blocks, LB_BLOCK, 0, st>>>(ctx->d_bvh4, ctx->d_raytris, spos, sidx, cand, nc, (uint32_t)k0, (uint32_t)k1,
                                                                   keys + link_used, fac + link_used, d_cnt + 1,
                                                                   mirror ? mirror + mirror_used : nullptr, mirror ? mirror_cap - mirror_used : 0, d_cnt + 2,
                                                                   ctx->d_counters);

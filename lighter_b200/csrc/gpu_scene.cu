@@ -241,7 +241,7 @@ extern "C" void ltrgpu_destroy(ltrgpu_Ctx *ctx)
     free_bake_state(ctx);
     dev_free(&ctx->d_inst); dev_free(&ctx->d_wpos); dev_free(&ctx->d_wnrm); dev_free(&ctx->d_vtex); dev_free(&ctx->d_ltex);
     dev_free(&ctx->d_rtris); dev_free(&ctx->d_rnodes); dev_free(&ctx->d_ritems); dev_free(&ctx->d_rtree_tris); dev_free(&ctx->d_rtree_ptris); dev_free(&ctx->d_rtree_boxes);
-    dev_free(&ctx->d_bvh); dev_free(&ctx->d_ptris); dev_free(&ctx->d_raytris); dev_free(&ctx->d_tri_orig);
+    dev_free(&ctx->d_bvh); dev_free(&ctx->d_bvh4); dev_free(&ctx->d_ptris); dev_free(&ctx->d_raytris); dev_free(&ctx->d_tri_orig);
     dev_free(&ctx->d_lights); dev_free(&ctx->d_light_inst); dev_free(&ctx->d_light_samples); dev_free(&ctx->d_probe_pos); dev_free(&ctx->d_probe_nrm);
     dev_free(&ctx->d_ao_cos); dev_free(&ctx->d_ao_sin); dev_free(&ctx->d_blur_kernel); dev_free(&ctx->d_counters);
     free(ctx->h_inst); free(ctx->h_lights); free(ctx->h_inst_lumel_off);
@@ -333,6 +333,7 @@ extern "C" int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *d)
     if (dev_upload(ctx, &ctx->d_ritems, d->ritems, d->n_ritems)) return 1;
     if (dev_upload(ctx, &ctx->d_rtree_tris, d->rtree_tris9, (size_t)d->n_rtree_tris * 9)) return 1;
     if (dev_upload(ctx, &ctx->d_bvh, d->bvh, d->n_bvh_nodes)) return 1;
+    if (dev_upload(ctx, &ctx->d_bvh4, d->bvh4, d->n_bvh4_nodes)) return 1;
     if (dev_upload(ctx, &ctx->d_tri_orig, d->tri_orig, d->n_tris)) return 1;
     if (dev_upload(ctx, &ctx->d_lights, d->lights, d->n_lights)) return 1;
     if (dev_upload(ctx, &ctx->d_light_inst, d->light_inst, (size_t)d->n_lights * d->n_inst)) return 1;

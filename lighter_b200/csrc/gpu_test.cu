@@ -43,7 +43,7 @@ __global__ void t_segtri_kernel(const float *a, const float *b, const float *tri
                      mk3(t[3], t[4], t[5]), mk3(t[6], t[7], t[8]));
 }
 
-__global__ void t_queries_kernel(const BvhNode *bvh, const PreparedTri *pt, const RayTri *rt, const uint32_t *orig, const float *a, const float *b,
+__global__ void t_queries_kernel(const BvhNode *bvh, const Bvh4Node *bvh4, const PreparedTri *pt, const RayTri *rt, const uint32_t *orig, const float *a, const float *b,
                                  uint32_t n, float *dist, int *anyhit, float *closest, int *closest_tri)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -51,7 +51,13 @@ __global__ void t_queries_kernel(const BvhNode *bvh, const PreparedTri *pt, cons
     TravStats ts = { 0, 0 };
     V3 A = mk3(a[3 * i], a[3 * i + 1], a[3 * i + 2]), B = mk3(b[3 * i], b[3 * i + 1], b[3 * i + 2]);
     if (dist) dist[i] = bvh_distance(bvh, pt, A, 2.0f, -1.0f, ts);
-    if (anyhit) anyhit[i] = bvh_segment<true>(bvh, rt, orig, A, B, nullptr, ts) < 1.0f ? 1 : 0;
+    if (anyhit) {
+        /* three implementations of the same predicate: ordered segment walk, two-phase binary walk, two-phase 4-wide walk
+         * (the one the radiosity and sampled-shadow kernels use); a disagreement is reported as 2 + bits */
+        const int h0 = bvh_segment<true>(bvh, rt, orig, A, B, nullptr, ts) < 1.0f ? 1 : 0;
+        const int h1 = bvh_anyhit(bvh, rt, A, B, ts) ? 1 : 0, h2 = bvh4_anyhit(bvh4, rt, A, B, ts) ? 1 : 0, h3 = bvh4_anyhit<2>(bvh4, rt, A, B, ts) ? 1 : 0;
+        anyhit[i] = (h0 == h1 && h1 == h2 && h2 == h3) ? h0 : 2 + h0 + 2 * h1 + 4 * h2 + 8 * h3;
+    }
     if (closest) {
         int slot = -1;
         closest[i] = bvh_segment<false>(bvh, rt, orig, A, B, &slot, ts);
@@ -115,7 +121,7 @@ bool have_device()
 }
 
 struct SceneOnDevice {
-    BvhNode *bvh; PreparedTri *pt; RayTri *rt; uint32_t *orig;
+    BvhNode *bvh; Bvh4Node *bvh4; PreparedTri *pt; RayTri *rt; uint32_t *orig;
 };
 
 __global__ void t_prepare_kernel(const float *tris9, uint32_t n, PreparedTri *pt, RayTri *rt)
@@ -134,10 +140,12 @@ bool scene_to_device(Dev &D, const float *tris9, uint32_t ntris, SceneOnDevice &
     int leaf_max = BVH_LEAF_MAX;
     if (const char *e = getenv("LTR_BVH_LEAF")) leaf_max = atoi(e);
     build_scene_bvh(tris9, ntris, bvh, leaf_max, 0);
+    build_bvh4(bvh);
     std::vector<float> ordered((size_t)ntris * 9);
     for (uint32_t k = 0; k < ntris; ++k) memcpy(&ordered[(size_t)k * 9], tris9 + (size_t)bvh.order[k] * 9, 36);
     float *d_raw = D.up(ordered.data(), ordered.size());
     S.bvh = D.up(bvh.nodes.data(), bvh.nodes.size());
+    S.bvh4 = D.up(bvh.nodes4.data(), bvh.nodes4.size());
     S.orig = D.up(bvh.order.data(), bvh.order.size());
     S.pt = D.alloc<PreparedTri>(ntris);
     S.rt = D.alloc<RayTri>(ntris);
@@ -185,7 +193,7 @@ int ltrx_test_scene_queries(const float *tris9, u32 ntris, const float *a3, cons
     float *dd = dist_out ? D.alloc<float>(n) : nullptr, *dc = closest_out ? D.alloc<float>(n) : nullptr;
     int *dh = anyhit_out ? D.alloc<int>(n) : nullptr, *dct = closest_tri_out ? D.alloc<int>(n) : nullptr;
     if (!D.ok) return 0;
-    if (n) t_queries_kernel<<<(n + 127) / 128, 128>>>(S.bvh, S.pt, S.rt, S.orig, da, db, n, dd, dh, dc, dct);
+    if (n) t_queries_kernel<<<(n + 127) / 128, 128>>>(S.bvh, S.bvh4, S.pt, S.rt, S.orig, da, db, n, dd, dh, dc, dct);
     if (cudaDeviceSynchronize() != cudaSuccess) { fprintf(stderr, "ltrx_test_scene_queries: %s\n", cudaGetErrorString(cudaGetLastError())); return 0; }
     D.down(dist_out, dd, n); D.down(anyhit_out, dh, n); D.down(closest_out, dc, n); D.down(closest_tri_out, dct, n);
     return D.ok;
