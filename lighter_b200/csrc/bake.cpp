@@ -259,7 +259,7 @@ void host_prepare(ltr_Scene *S)
     const size_t nst = scene_tris.size() / 9;
     std::thread bvh_thread([&]() {
         build_scene_bvh(scene_tris.data(), nst, B.bvh, leaf_max, 0);
-        /* triangles in BVH order (threads), while this thread collapses the tree into its 4-wide form */
+        /* triangles in BVH order */
         B.bvh_tris.resize(nst * 9);
         const unsigned T = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
         std::vector<std::thread> pool;
@@ -267,7 +267,6 @@ void host_prepare(ltr_Scene *S)
             pool.emplace_back([&, t]() {
                 for (size_t k = nst * t / T; k < nst * (t + 1) / T; ++k) memcpy(&B.bvh_tris[k * 9], &scene_tris[(size_t)B.bvh.order[k] * 9], 36);
             });
-        build_bvh4(B.bvh);
         for (auto &th : pool) th.join();
     });
     struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } bvh_joiner{ bvh_thread };
@@ -858,7 +857,6 @@ int ltrx_test_bvh(const float *tris9, u32 ntris, int leaf_max, u32 *n_nodes, u32
     for (u32 t = 0; t < ntris; ++t) if (seen[t] != 1) return 0;
     /* the 4-wide collapse: reachable from its root, every triangle in exactly one leaf slot and inside that slot's box,
      * every inner slot's box containing the boxes of the node it points to */
-    build_bvh4(bvh);
     if (bvh.nodes4.empty()) return 0;
     std::vector<int> seen4(ntris, 0);
     std::vector<char> visited(bvh.nodes4.size(), 0);

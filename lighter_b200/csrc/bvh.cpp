@@ -21,6 +21,7 @@ struct Tmp {
     int32_t left, right;       /* -1 for a leaf */
     uint32_t first, count;
     int32_t inner;             /* inner nodes in this sub-tree (0 for a leaf); -1 = not known yet */
+    int32_t inner_even;        /* ... of which at even depth below this node (itself included): the 4-wide nodes of the sub-tree */
     int32_t height;            /* levels of inner nodes below and including this one */
 };
 
@@ -112,7 +113,7 @@ struct Builder {
             for (int t = 1; t < T; ++t) { grow(nb.bb, part[t].bb); grow(nb.cb, part[t].cb); }
         } else bounds_of(P, count, nb);
         Tmp &N = tmp[w.node];
-        N.box = nb.bb; N.first = w.first; N.count = count; N.left = N.right = -1; N.inner = 0; N.height = 0;
+        N.box = nb.bb; N.first = w.first; N.count = count; N.left = N.right = -1; N.inner = 0; N.inner_even = 0; N.height = 0;
         if ((int)count <= leaf_max) return false;
         N.inner = -1;
 
@@ -191,6 +192,7 @@ struct Builder {
         build_serial(l);
         build_serial(r);
         tmp[w.node].inner = 1 + tmp[l.node].inner + tmp[r.node].inner;
+        tmp[w.node].inner_even = 1 + (tmp[l.node].inner - tmp[l.node].inner_even) + (tmp[r.node].inner - tmp[r.node].inner_even);
         tmp[w.node].height = 1 + std::max(tmp[l.node].height, tmp[r.node].height);
     }
 
@@ -201,6 +203,7 @@ struct Builder {
         if (N.inner >= 0) return;
         finish_sizes(N.left); finish_sizes(N.right);
         N.inner = 1 + tmp[N.left].inner + tmp[N.right].inner;
+        N.inner_even = 1 + (tmp[N.left].inner - tmp[N.left].inner_even) + (tmp[N.right].inner - tmp[N.right].inner_even);
         N.height = 1 + std::max(tmp[N.left].height, tmp[N.right].height);
     }
 
@@ -266,6 +269,52 @@ struct Flattener {
     }
 };
 
+/* The 4-wide tree straight from the build tree: a 4-wide node stands for an inner node at EVEN depth, its slots are
+ * that node's grand-children (a leaf child stays a slot).  Pre-order layout again: with inner_even known per sub-tree
+ * every index is a function of the path, so sub-trees are emitted independently by the threads. */
+struct Flattener4 {
+    const Tmp *tmp;
+    Bvh4Node *out;
+    struct Item { int32_t t, slot; };
+
+    /* emits the 4-wide sub-tree of even-depth inner node t at `slot`; sub-trees of at most `defer_below` 4-wide nodes are
+     * recorded in `deferred` instead of being emitted (0 = emit everything) */
+    void emit(int32_t t, int32_t slot, int32_t defer_below, std::vector<Item> *deferred) const
+    {
+        std::vector<Item> st;
+        st.push_back({ t, slot });
+        while (!st.empty()) {
+            const Item it = st.back(); st.pop_back();
+            if (deferred && tmp[it.t].inner_even <= defer_below) { deferred->push_back(it); continue; }
+            const Tmp &N = tmp[it.t];
+            int32_t g[4]; int ng = 0;
+            const int32_t kids[2] = { N.left, N.right };
+            for (int k = 0; k < 2; ++k) {
+                const Tmp &C = tmp[kids[k]];
+                if (C.left >= 0) { g[ng++] = C.left; g[ng++] = C.right; } else g[ng++] = kids[k];
+            }
+            Bvh4Node node;
+            int32_t next = it.slot + 1;
+            Item push[4]; int np = 0;
+            for (int j = 0; j < 4; ++j) {
+                node.pad[j] = 0;
+                if (j >= ng) {
+                    node.lox[j] = node.loy[j] = node.loz[j] = FMAXV; node.hix[j] = node.hiy[j] = node.hiz[j] = -FMAXV;
+                    node.c[j] = BVH4_EMPTY;
+                    continue;
+                }
+                const Tmp &G = tmp[g[j]];
+                node.lox[j] = G.box.lo.x; node.loy[j] = G.box.lo.y; node.loz[j] = G.box.lo.z;
+                node.hix[j] = G.box.hi.x; node.hiy[j] = G.box.hi.y; node.hiz[j] = G.box.hi.z;
+                if (G.left >= 0) { node.c[j] = next; push[np++] = { g[j], next }; next += G.inner_even; }
+                else node.c[j] = leaf_code(G.first, G.count);
+            }
+            out[it.slot] = node;
+            for (int j = np - 1; j >= 0; --j) st.push_back(push[j]);
+        }
+    }
+};
+
 } // namespace
 
 void build_scene_bvh(const float *tris9, size_t count, SceneBvh &out, int leaf_max, int threads)
@@ -284,6 +333,7 @@ void build_scene_bvh(const float *tris9, size_t count, SceneBvh &out, int leaf_m
         n.pad0 = n.pad1 = 0;
         out.nodes.push_back(n);
         out.depth = 1;
+        build_bvh4(out);
         return;
     }
 
@@ -336,6 +386,7 @@ void build_scene_bvh(const float *tris9, size_t count, SceneBvh &out, int leaf_m
         n.pad0 = n.pad1 = 0;
         out.nodes.push_back(n);
         out.depth = 1;
+        build_bvh4(out);
         return;
     }
     out.nodes.resize((size_t)tmp[root].inner);
@@ -359,6 +410,24 @@ void build_scene_bvh(const float *tris9, size_t count, SceneBvh &out, int leaf_m
         F.emit(root, 0, nullptr, nullptr);
     }
     lap("flatten");
+    {
+        out.nodes4.resize((size_t)tmp[root].inner_even);
+        Flattener4 F4{ tmp.get(), out.nodes4.data() };
+        std::vector<Flattener4::Item> tasks;
+        if (threads > 1 && tmp[root].inner_even > 8192) {
+            F4.emit(root, 0, tmp[root].inner_even / (threads * 8) + 64, &tasks);
+            std::atomic<size_t> cursor{0};
+            auto worker = [&]() { for (size_t i; (i = cursor.fetch_add(1)) < tasks.size();) F4.emit(tasks[i].t, tasks[i].slot, 0, nullptr); };
+            std::vector<std::thread> pool;
+            const int T = (int)std::min<size_t>((size_t)threads, tasks.size());
+            for (int t = 1; t < T; ++t) pool.emplace_back(worker);
+            worker();
+            for (auto &th : pool) th.join();
+        } else {
+            F4.emit(root, 0, 0, nullptr);
+        }
+    }
+    lap("flatten4");
 }
 
 
@@ -383,21 +452,12 @@ void build_bvh4(SceneBvh &bvh)
     st.push_back({ 0, 0 });
     while (!st.empty()) {
         const Item it = st.back(); st.pop_back();
-        /* start from the two binary children; while there is room, open the inner slot with the largest box
-         * (the one a ray is most likely to enter) -- nodes end up full even where the binary tree is lopsided */
         Slot slots[4];
         int ns = 0;
-        slots[ns++] = child(n2[it.n2i], 0);
-        slots[ns++] = child(n2[it.n2i], 1);
-        while (ns < 4) {
-            int best = -1;
-            float best_area = -1.f;
-            for (int j = 0; j < ns; ++j)
-                if (slots[j].code >= 0) { const float a = half_area(slots[j].b); if (a > best_area) { best_area = a; best = j; } }
-            if (best < 0) break;
-            const int32_t open = slots[best].code;
-            slots[best] = child(n2[open], 0);
-            slots[ns++] = child(n2[open], 1);
+        for (int k = 0; k < 2; ++k) {
+            const Slot c = child(n2[it.n2i], k);
+            if (c.code >= 0) { slots[ns++] = child(n2[c.code], 0); slots[ns++] = child(n2[c.code], 1); }
+            else slots[ns++] = c;
         }
         Bvh4Node node;
         int32_t kids[4] = { -1, -1, -1, -1 };

@@ -45,5 +45,6 @@ struct SceneBvh {
 
 /* tris: 9 floats per triangle (world space).  threads <= 0: hardware concurrency. */
 void build_scene_bvh(const float *tris9, size_t count, SceneBvh &out, int leaf_max, int threads);
-/* collapse out.nodes (binary) into out.nodes4 (4-wide): the largest inner child is opened until the node has four slots */
+/* out.nodes4 from out.nodes by serial collapse (slots = grand-children; a leaf child stays a slot).  build_scene_bvh already
+ * fills nodes4 (in parallel, straight from its build tree); this is the reference implementation used for degenerate trees. */
 void build_bvh4(SceneBvh &bvh);

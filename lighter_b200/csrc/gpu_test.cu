@@ -140,7 +140,6 @@ bool scene_to_device(Dev &D, const float *tris9, uint32_t ntris, SceneOnDevice &
     int leaf_max = BVH_LEAF_MAX;
     if (const char *e = getenv("LTR_BVH_LEAF")) leaf_max = atoi(e);
     build_scene_bvh(tris9, ntris, bvh, leaf_max, 0);
-    build_bvh4(bvh);
     std::vector<float> ordered((size_t)ntris * 9);
     for (uint32_t k = 0; k < ntris; ++k) memcpy(&ordered[(size_t)k * 9], tris9 + (size_t)bvh.order[k] * 9, 36);
     float *d_raw = D.up(ordered.data(), ordered.size());
