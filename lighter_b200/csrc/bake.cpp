@@ -135,6 +135,15 @@ int nccl_allgather_cb(void *user, const void *send, void *recv, size_t bytes, vo
     return rc;
 }
 
+int nccl_allreduce_cb(void *user, float *buf, size_t n, void *stream)
+{
+    Bake *B = (Bake *)user;
+    if (!B->nccl || !B->comm) return 1;
+    int rc = B->nccl->AllReduce(buf, buf, n, /*ncclFloat32*/ 7, /*ncclSum*/ 0, B->comm, stream);
+    if (rc != 0) fprintf(stderr, "lighter_b200: ncclAllReduce failed: %s\n", B->nccl->GetErrorString(rc));
+    return rc;
+}
+
 struct Fail { std::string msg; };
 
 void gpu_check(ltr_Scene *S, int rc, const char *what)
@@ -482,6 +491,7 @@ void gpu_stages(ltr_Scene *S)
     S->completion.store(0.f);
     B.lumel_off.assign(ni + 1, 0);
     gpu_check(S, ltrgpu_set_world(B.gpu, S->rank, S->world, S->world > 1 ? nccl_allgather_cb : nullptr, &B), "world");
+    gpu_check(S, ltrgpu_set_allreduce(B.gpu, S->world > 1 ? nccl_allreduce_cb : nullptr), "world");
     gpu_check(S, ltrgpu_generate_lumels(B.gpu, B.lumel_off.data()), "lumel generation");
     const uint64_t n = B.lumel_off[ni];
     uint64_t sb = 0, se = n;

@@ -95,6 +95,9 @@ typedef struct ltrgpu_Counters {
 /* all-gather hook for the multi-GPU radiance exchange: gathers `bytes_per_rank` bytes from
  * `send` (device) of every rank into `recv` (device, world*bytes_per_rank) on `stream`. */
 typedef int (*ltrgpu_allgather_fn)(void *user, const void *send, void *recv, size_t bytes_per_rank, void *cuda_stream);
+/* in-place float sum over the ranks (the direct-light factor table: every entry is written by exactly one rank, the
+ * others hold 0, so the sum is exact) */
+typedef int (*ltrgpu_allreduce_fn)(void *user, float *buf, size_t n_floats, void *cuda_stream);
 
 int  ltrgpu_create(ltrgpu_Ctx **out, int device);
 void ltrgpu_destroy(ltrgpu_Ctx *ctx);
@@ -110,6 +113,7 @@ int ltrgpu_generate_lumels(ltrgpu_Ctx *ctx, uint64_t *inst_lumel_off);
 
 /* multi-GPU identity of this context and the all-gather hook; call before ltrgpu_generate_lumels */
 int ltrgpu_set_world(ltrgpu_Ctx *ctx, int rank, int world, ltrgpu_allgather_fn allgather, void *allgather_user);
+int ltrgpu_set_allreduce(ltrgpu_Ctx *ctx, ltrgpu_allreduce_fn allreduce);      /* same user pointer as the all-gather hook */
 
 /* restrict the per-lumel stages to global lumels [begin,end) (multi-GPU shard); default = all */
 int ltrgpu_set_shard(ltrgpu_Ctx *ctx, uint64_t begin, uint64_t end, int rank, int world,

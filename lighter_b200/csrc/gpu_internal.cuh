@@ -67,9 +67,11 @@ struct ltrgpu_Ctx {
     uint64_t sh_begin = 0, sh_end = 0;
     int rank = 0, world = 1;
     ltrgpu_allgather_fn allgather = nullptr;
+    ltrgpu_allreduce_fn allreduce = nullptr;
     void *allgather_user = nullptr;
 
     /* ---- direct light ---- */
+    uint64_t fvis_tab_base = 0; uint32_t fvis_tab_n = 0;   /* the factor table covers lumels [base, base + n) */
     float *d_fvis = nullptr;                  /* [n_lights][local lumels] shadow factors */
     unsigned long long *d_smask = nullptr;    /* sampled mode: [n_lights][local lumels] blocked-sample bit masks */
     float4 *d_light_samples = nullptr;        /* sampled mode: per (light, sample) table */

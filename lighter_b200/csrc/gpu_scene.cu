@@ -375,6 +375,8 @@ extern "C" int ltrgpu_set_world(ltrgpu_Ctx *ctx, int rank, int world, ltrgpu_all
     return 0;
 }
 
+extern "C" int ltrgpu_set_allreduce(ltrgpu_Ctx *ctx, ltrgpu_allreduce_fn allreduce) { ctx->allreduce = allreduce; return 0; }
+
 extern "C" int ltrgpu_set_shard(ltrgpu_Ctx *ctx, uint64_t begin, uint64_t end, int rank, int world,
                                 ltrgpu_allgather_fn allgather, void *allgather_user)
 {

@@ -15,6 +15,7 @@ struct NcclApi {
     int (*CommInitRank)(void **comm, int nranks, NcclId id, int rank);
     int (*CommDestroy)(void *comm);
     int (*AllGather)(const void *send, void *recv, size_t count, int dtype, void *comm, void *stream);
+    int (*AllReduce)(const void *send, void *recv, size_t count, int dtype, int op, void *comm, void *stream);
     const char *(*GetErrorString)(int);
 };
 

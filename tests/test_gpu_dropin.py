@@ -43,10 +43,10 @@ def test_sharded_bake_equals_single_gpu():
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", str(port), os.path.join(ROOT, "tools", "multi_gpu_check.py"), "config4_sibling", "rad1", "mesh2"],
+                        "--master-port", str(port), os.path.join(ROOT, "tools", "multi_gpu_check.py"), "config4_sibling", "rad1", "mesh2", "mesh2:sampled"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("bit-identical: True, normals: True") == 3, r.stdout
+    assert r.stdout.count("bit-identical: True, normals: True") == 4, r.stdout
 
 
 def test_properties_at_config3_size():

@@ -22,7 +22,7 @@ from lighter_b200 import api, scenes  # noqa: E402
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-names = sys.argv[1:] or ["config4_sibling", "rad1", "mesh2"]
+names = sys.argv[1:] or ["config4_sibling", "rad1", "mesh2", "mesh2:sampled"]
 ok = True
 for name in names:
     idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -32,13 +32,18 @@ for name in names:
         idt = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
     dist.broadcast(idt, 0)
     nccl_id = bytes(idt.cpu().tolist())
-    sc = scenes.NAMED[name]() if name in scenes.NAMED else scenes.workload(name)
+    mode = 1 if name.endswith(":sampled") else 0            # "<scene>:sampled" = sampled soft-shadow extension mode
+    base = name.split(":")[0]
+    sc = scenes.NAMED[base]() if base in scenes.NAMED else scenes.workload(base)
+    if mode:
+        for lt in sc.lights:
+            lt.shadow_sample_count = 8
     api.srand(1)
-    out = api.bake(sc, device=local, shard=(rank, world, nccl_id), reset_rand=False)
+    out = api.bake(sc, device=local, shard=(rank, world, nccl_id), reset_rand=False, shadow_mode=mode)
     dist.barrier()
     if rank == 0:
         api.srand(1)
-        solo = api.bake(sc, device=local, reset_rand=False)
+        solo = api.bake(sc, device=local, reset_rand=False, shadow_mode=mode)
         same = all(np.array_equal(a["rgb"].view(np.uint32), b["rgb"].view(np.uint32)) for a, b in zip(out["lightmaps"], solo["lightmaps"]))
         nsame = all((a["normals"] is None and b["normals"] is None) or np.array_equal(a["normals"].view(np.uint32), b["normals"].view(np.uint32))
                     for a, b in zip(out["lightmaps"], solo["lightmaps"]))
