@@ -58,29 +58,58 @@ __device__ __forceinline__ ShadeTerms shade_terms(const ltrgpu_Light &L, V3 SP, 
     return o;
 }
 
+/* cut the blocks into `world` contiguous runs of (nearly) equal weight; cuts[r] = first block of rank r, cuts[world] = nb */
+__global__ void direct_cuts_kernel(const uint32_t *__restrict__ block_w, uint32_t nb, uint32_t world, uint32_t *__restrict__ cuts)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    unsigned long long total = 0;
+    for (uint32_t b = 0; b < nb; ++b) total += block_w[b];
+    unsigned long long acc = 0;
+    uint32_t r = 1;
+    cuts[0] = 0;
+    for (uint32_t b = 0; b < nb && r < world; ++b) {
+        acc += block_w[b];
+        while (r < world && acc * world >= total * r) cuts[r++] = b + 1;
+    }
+    while (r <= world) cuts[r++] = nb;
+    cuts[world] = nb;
+}
+
 __device__ __forceinline__ bool light_is_supported(unsigned type) { return type == 1u || type == 2u || type == 3u; }
 
 __global__ void direct_classify_kernel(const ltrgpu_Light *__restrict__ lights, uint32_t l0, uint32_t l1,
                                        const uint8_t *__restrict__ light_inst, uint32_t n_inst,
                                        const float4 *__restrict__ lpos, const float4 *__restrict__ lnrm, const uint32_t *__restrict__ linst,
-                                       uint64_t sh_begin, uint32_t n_local, uint32_t rank, uint32_t world,
+                                       uint64_t sh_begin, uint32_t n_local, const uint32_t *__restrict__ cuts /* [2]: my first / end block, or NULL */,
+                                       uint32_t *__restrict__ block_w /* weight pass: per 1024-lumel block, or NULL */,
                                        uint2 *__restrict__ active, uint32_t *active_count)
 {
-    /* (sh_begin, n_local) is the range the factor table covers.  With several GPUs that is the WHOLE lumel array, and a
-     * rank lists the pairs of the 1024-lumel blocks dealt to it round-robin: shadow-march cost is concentrated around
-     * the lights, contiguous ranges measured 17 ms on the slowest of 8 ranks against a 6 ms mean. */
+    /* (sh_begin, n_local) is the range the factor table covers.  With several GPUs that is the WHOLE lumel array: a first
+     * pass (block_w != NULL) sums an integer cost estimate of the marches per 1024-lumel block -- identical on every rank --
+     * the blocks are cut into `world` contiguous runs of equal cost, and the second pass lists the pairs of this rank's
+     * run.  Contiguous = each rank's marches stay in one part of the BVH (an interleaved deal was measured 30 % slower
+     * per march: every rank then streams the whole 200 MB scene through its L2); equal cost, because march work is
+     * concentrated around the lights (equal lumel counts: 17 ms on the slowest of 8 ranks against a 6 ms mean). */
     const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t l = l0 + blockIdx.y;
     bool want = false;
-    if (li < n_local && l < l1 && ((sh_begin + li) >> 10) % world == rank) {
+    const uint32_t blk = (uint32_t)((sh_begin + li) >> 10);
+    if (li < n_local && l < l1 && (!cuts || (blk >= cuts[0] && blk < cuts[1]))) {
         const ltrgpu_Light L = lights[l];
         const uint64_t g = sh_begin + li;
         if (light_is_supported(L.type) && light_inst[(size_t)l * n_inst + linst[g]]) {
             ShadeTerms t = shade_terms(L, ld3(lpos[g]), ld3(lnrm[g]));
             /* a directional light facing away adds colour * 0: the march result cannot matter, skip it */
             want = (L.type == 3u) ? (t.f_ndotl > 0) : (t.pre > 0);
+            if (want && block_w) {
+                /* cost ~ distance queries of the march ~ its length (steps are <= 1 and ~1 in open space); integer, so the sum
+                 * does not depend on the order of the atomics and every rank computes the same cuts */
+                const float len = len3(t.to - (ld3(lpos[g]) + ld3(lnrm[g]) * 0.005f));
+                atomicAdd(block_w + blk, 4u + (uint32_t)fminf(len * 4.0f, 4000.0f));
+            }
         }
     }
+    if (block_w) return;
     const unsigned mask = __ballot_sync(0xffffffffu, want);
     if (mask) {
         const unsigned lane = threadIdx.x & 31u;
@@ -122,18 +151,19 @@ direct_march_kernel(const ltrgpu_Light *__restrict__ lights, const BvhNode *__re
      * part of the BVH.  (A persistent-lane variant that refilled finished lanes from a global cursor
      * was measured 40-60 % SLOWER on configs 3 and 4: it trades this coherence for lane occupancy,
      * and the divergence that matters is inside the BVH walk, not in the march length.)
-     * `cursor` is kept for dynamic CTA-level scheduling of the work list in 1024-entry chunks. */
+     * Warps pull 32 entries at a time from `cursor`: with 1024-entry CTA chunks a rank of an 8-GPU bake
+     * (1.1 M pairs) had one chunk per CTA and ran at a third of the single-GPU throughput. */
     const uint32_t n = *active_count;
+    const unsigned lane = threadIdx.x & 31u;
     unsigned queries = 0, marches = 0;
     TravStats ts = { 0, 0 };
-    __shared__ uint32_t chunk_base;
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) chunk_base = atomicAdd(cursor, 1024u);
-        __syncthreads();
-        const uint32_t base = chunk_base;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(cursor, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
-        for (uint32_t e = base + threadIdx.x; e < base + 1024u && e < n; e += LB_BLOCK) {
+        const uint32_t e = base + lane;
+        if (e < n) {
             const uint2 a = active[e];
             const ltrgpu_Light L = lights[a.y];
             const uint64_t g = sh_begin + a.x;
@@ -324,10 +354,15 @@ extern "C" int ltrgpu_direct_light(ltrgpu_Ctx *ctx)
     /* The factor table f_vis[light][lumel].  One GPU: columns = this shard.  Several GPUs: columns = ALL lumels; each
      * rank marches the pairs of the lumel blocks dealt to it round-robin (balanced), the tables are summed over the
      * ranks (every entry is non-zero on one rank at most: exact), then each rank shades its own contiguous range. */
-    const bool spread = ctx->world > 1 && ctx->allreduce;
+    const bool spread = ctx->world > 1 && ctx->allreduce && !getenv("LTR_DIRECT_CONTIGUOUS");     /* env: A/B switch back to contiguous ranges */
     const uint64_t tab_base = spread ? 0 : ctx->sh_begin;
     const uint32_t tab_n = spread ? (uint32_t)ctx->n_lumels : n_local;
-    const uint32_t own_rank = spread ? (uint32_t)ctx->rank : 0u, own_world = spread ? (uint32_t)ctx->world : 1u;
+    const uint32_t n_blocks = (uint32_t)((ctx->n_lumels + 1023) >> 10);
+    uint32_t *d_block_w = nullptr, *d_cuts = nullptr;
+    if (spread) {
+        if (dev_alloc(ctx, &d_block_w, n_blocks)) return 1;
+        if (dev_alloc(ctx, &d_cuts, (size_t)ctx->world + 1)) return 1;
+    }
 
     /* lights are processed in chunks so that the factor table stays within a fixed budget;
      * accumulation order over chunks is still the light order */
@@ -354,8 +389,17 @@ extern "C" int ltrgpu_direct_light(ltrgpu_Ctx *ctx)
         CU_TRY(ctx, cudaMemsetAsync(ctx->d_active_count, 0, 8, st));
         CU_TRY(ctx, cudaMemsetAsync(ctx->d_fvis, 0, (size_t)(l1 - l0) * tab_n * 4, st));
         dim3 grid(grid_for(tab_n, 256), l1 - l0);
+        if (spread) {
+            CU_TRY(ctx, cudaMemsetAsync(d_block_w, 0, (size_t)n_blocks * 4, st));
+            direct_classify_kernel<<<grid, 256, 0, st>>>(ctx->d_lights, l0, l1, ctx->d_light_inst, ctx->n_inst, ctx->d_lpos, ctx->d_lnrm,
+                                                         ctx->d_linst, tab_base, tab_n, nullptr, d_block_w, nullptr, nullptr);
+            CU_LAUNCH_CHECK(ctx);
+            direct_cuts_kernel<<<1, 32, 0, st>>>(d_block_w, n_blocks, (uint32_t)ctx->world, d_cuts);
+            CU_LAUNCH_CHECK(ctx);
+        }
         direct_classify_kernel<<<grid, 256, 0, st>>>(ctx->d_lights, l0, l1, ctx->d_light_inst, ctx->n_inst, ctx->d_lpos, ctx->d_lnrm,
-                                                     ctx->d_linst, tab_base, tab_n, own_rank, own_world, ctx->d_active, ctx->d_active_count);
+                                                     ctx->d_linst, tab_base, tab_n, spread ? d_cuts + ctx->rank : nullptr, nullptr,
+                                                     ctx->d_active, ctx->d_active_count);
         CU_LAUNCH_CHECK(ctx);
         CU_TRY(ctx, cudaEventRecord(m0, st));
         unsigned blocks = (unsigned)ctx->num_sms * 16;
@@ -402,6 +446,7 @@ extern "C" int ltrgpu_direct_light(ltrgpu_Ctx *ctx)
     ctx->host_counters.ms_direct += ms;
     ctx->host_counters.ms_march += march_ms;
     cudaEventDestroy(m0); cudaEventDestroy(m1);
+    lb_free(d_block_w); lb_free(d_cuts);
     return 0;
 }
 
