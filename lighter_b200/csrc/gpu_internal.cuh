@@ -188,55 +188,72 @@ __device__ __forceinline__ void load_prepared(const PreparedTri *src, PreparedTr
  * that h < 0.001, lighter.cpp:200-201).  Pruning is conservative: a sub-tree is skipped only when
  * its box is farther than the best distance so far.
  */
+template <int FLUSH = 3>
 __device__ __forceinline__ float bvh_distance(const BvhNode *__restrict__ nodes, const PreparedTri *__restrict__ tris,
                                               V3 p, float radius, float stop_below, TravStats &ts)
 {
+    /* Two-phase walk: the node loop (nearer child first, sub-trees farther than the best distance so far pruned) only
+     * QUEUES the triangles of the leaves it reaches; once FLUSH are pending, or the walk is over, they are evaluated
+     * together.  ncu on the test-as-you-go version: half of the warp instructions were point/triangle evaluations
+     * running with 5 of 32 lanes, because lanes reach their leaves at different iterations; evaluated in a batch the
+     * lanes of a warp (neighbouring lumels at the same march step) do it side by side.  Pruning lags by at most
+     * FLUSH triangles. */
+    constexpr int TQ = FLUSH + 14;                   /* FLUSH - 1 pending + two leaves of up to 7 triangles */
     int   stack_n[BVH_STACK];
     float stack_d[BVH_STACK];
-    int sp = 0;
+    int   tq[TQ];
+    float tqd[TQ];
+    int sp = 0, nq = 0;
     float best = radius;
     float best2 = best * best * 1.000001f;
     int node = 0;
     for (;;) {
-        const float4 *n4 = reinterpret_cast<const float4 *>(nodes + node);
-        float4 a = __ldg(n4), b = __ldg(n4 + 1), c = __ldg(n4 + 2);
-        int4 k = __ldg(reinterpret_cast<const int4 *>(n4 + 3));
-        ts.nodes++;
-        float d0 = box_dist2(p, a.x, a.y, a.z, a.w, b.x, b.y);
-        float d1 = box_dist2(p, b.z, b.w, c.x, c.y, c.z, c.w);
-        int c0 = k.x, c1 = k.y;
-        if (d1 < d0) { float td = d0; d0 = d1; d1 = td; int tc = c0; c0 = c1; c1 = tc; }   /* c0 = nearer */
-        int next = -1;
+        while (node >= 0) {
+            const float4 *n4 = reinterpret_cast<const float4 *>(nodes + node);
+            float4 a = __ldg(n4), b = __ldg(n4 + 1), c = __ldg(n4 + 2);
+            int4 k = __ldg(reinterpret_cast<const int4 *>(n4 + 3));
+            ts.nodes++;
+            float d0 = box_dist2(p, a.x, a.y, a.z, a.w, b.x, b.y);
+            float d1 = box_dist2(p, b.z, b.w, c.x, c.y, c.z, c.w);
+            int c0 = k.x, c1 = k.y;
+            if (d1 < d0) { float td = d0; d0 = d1; d1 = td; int tc = c0; c0 = c1; c1 = tc; }   /* c0 = nearer */
+            int next = -1;
 #pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            int cc = side ? c1 : c0;
-            float dd = side ? d1 : d0;
-            if (dd > best2) continue;
-            if (cc < 0) {
-                unsigned code = ~cc;
-                unsigned first = code >> 3, cnt = code & 7u;
-                for (unsigned t = 0; t < cnt; ++t) {
-                    PreparedTri T;
-                    load_prepared(tris + first + t, T);
-                    ts.tris++;
-                    float d = point_tri_distance_prepared(p, T);
-                    if (d < best) {
-                        best = d;
-                        best2 = best * best * 1.000001f;
-                        if (best < stop_below) return best;
-                    }
+            for (int side = 0; side < 2; ++side) {
+                int cc = side ? c1 : c0;
+                float dd = side ? d1 : d0;
+                if (dd > best2) continue;
+                if (cc < 0) {
+                    unsigned code = ~cc;
+                    unsigned first = code >> 3, cnt = code & 7u;
+                    for (unsigned t = 0; t < cnt; ++t) { tq[nq] = (int)(first + t); tqd[nq] = dd; ++nq; }
+                } else if (next < 0) {
+                    next = cc;
+                } else {
+                    stack_n[sp] = cc; stack_d[sp] = dd; ++sp;
                 }
-            } else if (next < 0) {
-                next = cc;
-            } else {
-                stack_n[sp] = cc; stack_d[sp] = dd; ++sp;
+            }
+            node = next;
+            while (node < 0 && sp > 0) { --sp; if (stack_d[sp] <= best2) node = stack_n[sp]; }
+            if (nq >= FLUSH) break;
+        }
+        while (nq > 0) {
+            --nq;
+            if (tqd[nq] > best2) continue;               /* the best distance has improved since this leaf was queued */
+            PreparedTri T;
+            load_prepared(tris + tq[nq], T);
+            ts.tris++;
+            float d = point_tri_distance_prepared(p, T);
+            if (d < best) {
+                best = d;
+                best2 = best * best * 1.000001f;
+                if (best < stop_below) return best;
             }
         }
-        if (next >= 0) { node = next; continue; }
-        for (;;) {
-            if (sp == 0) return best;
-            --sp;
-            if (stack_d[sp] <= best2) { node = stack_n[sp]; break; }
+        if (node < 0) {
+            /* the stack may still hold sub-trees that were skipped at pop time with an older bound: they stay skipped
+             * (the bound only shrinks), so an empty `node` with nothing pending means the walk is complete */
+            return best;
         }
     }
 }
