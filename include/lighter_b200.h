@@ -44,6 +44,7 @@ typedef struct ltrx_Stats {
     uint64_t kernel_launches, h2d_bytes, d2h_bytes;
     uint64_t n_rad_batches;                   /* launches of the pair-sweep / visibility kernel pair (candidate buffer refills) */
     uint64_t n_shadow_rays;                   /* sampled-shadow extension: any-hit rays, lumel x light x sample */
+    uint64_t n_ray_entry_tests;               /* entry boxes tested by rays that start at a bundle's entry set instead of the root */
 } ltrx_Stats;
 
 typedef struct ltrx_Lumels {
@@ -118,6 +119,9 @@ LTRAPI int ltrx_test_reftree(const float *tris9, u32 ntris, void *nodes_out, u32
  * when the lock-free table-level path was used, 0 for the plain rand() loop -- same values, same libc state afterwards */
 LTRAPI int ltrx_test_rand_fill(float *out, uint64_t n);
 LTRAPI int ltrx_test_bvh(const float *tris9, u32 ntris, int leaf_max, u32 *n_nodes, u32 *depth, u32 *order_out, float *bounds6);
+/* host-only: entry sets of segment bundles (csrc/bvh_entry.h) -- reachability self-check, root walk vs entry walk */
+LTRAPI int ltrx_test_bvh_entry(const float *tris9, u32 ntris, int leaf_max, const float *segs6, const u32 *bundle_off, u32 n_bundles,
+                               u32 *entries_out, uint64_t *visits_root, uint64_t *visits_entry, uint64_t *entry_tests, u32 *mismatches);
 
 #ifdef __cplusplus
 }

@@ -96,7 +96,7 @@ class Stats(C.Structure):
                                            "n_distance_queries", "n_ao_segments", "n_correction_rays", "n_rad_pairs",
                                            "n_rad_segments", "n_rad_links", "n_node_visits", "n_tri_tests",
                                            "n_ray_node_visits", "n_ray_tri_tests", "n_rad_tile_loads",
-                                           "kernel_launches", "h2d_bytes", "d2h_bytes", "n_rad_batches", "n_shadow_rays")])
+                                           "kernel_launches", "h2d_bytes", "d2h_bytes", "n_rad_batches", "n_shadow_rays", "n_ray_entry_tests")])
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -106,6 +106,21 @@ class Lumels(C.Structure):
     _fields_ = [("count", u32), ("width", u32), ("height", u32), ("pos_xyz", C.POINTER(C.c_float)),
                 ("nrm_xyz", C.POINTER(C.c_float)), ("loc", C.POINTER(u32)), ("radinfo_xyzw", C.POINTER(C.c_float)),
                 ("rgb", C.POINTER(C.c_float))]
+
+
+def test_bvh_entry(tris: np.ndarray, segs: np.ndarray, bundle_off: np.ndarray, leaf_max: int = 2) -> dict:
+    """Host-only: entry sets (csrc/bvh_entry.h) of bundles of segments -- segs (n,6), bundle_off (nb+1) -- with the
+    reachability self-check and the any-hit walk from the root vs from the entry set (4-wide node reads summed)."""
+    tris = np.ascontiguousarray(tris, np.float32)
+    segs = np.ascontiguousarray(segs, np.float32).reshape(-1, 6)
+    off = np.ascontiguousarray(bundle_off, np.uint32)
+    nb = len(off) - 1
+    entries = np.zeros(max(nb, 1), np.uint32)
+    vr, ve, et, mm = C.c_uint64(), C.c_uint64(), C.c_uint64(), u32()
+    ok = lib().ltrx_test_bvh_entry(_fp(tris), len(tris), leaf_max, _fp(segs), off.ctypes.data, nb, entries.ctypes.data,
+                                   C.byref(vr), C.byref(ve), C.byref(et), C.byref(mm))
+    return dict(ok=bool(ok), entries=entries[:nb], visits_root=vr.value, visits_entry=ve.value, entry_tests=et.value,
+                mismatches=mm.value)
 
 
 class Links(C.Structure):
@@ -121,7 +136,7 @@ LTRX_SYMBOLS = ["ltrx_Version", "ltrx_SetDevice", "ltrx_NcclUniqueId", "ltrx_Set
                 "ltrx_GetError", "ltrx_Prepare", "ltrx_BakeResident", "ltrx_Finish", "ltrx_SetDebug", "ltrx_GetLumels",
                 "ltrx_GetLinks", "ltrx_GetShadowFactors", "ltrx_SetShadowMode", "ltrx_GetShadowMasks", "ltrx_ShadowSampleSegment",
                 "ltrx_test_point_tri_distance", "ltrx_test_seg_tri",
-                "ltrx_test_scene_queries", "ltrx_test_march", "ltrx_test_spiral_dirs", "ltrx_test_reftree", "ltrx_test_bvh",
+                "ltrx_test_scene_queries", "ltrx_test_march", "ltrx_test_spiral_dirs", "ltrx_test_reftree", "ltrx_test_bvh", "ltrx_test_bvh_entry",
                 "ltrx_test_rand_fill"]
 
 _lib = None
@@ -185,6 +200,8 @@ def lib() -> C.CDLL:
     L.ltrx_test_reftree.argtypes = [fp, u32, C.c_void_p, u32, C.c_void_p, u32, C.POINTER(u32), C.POINTER(u32)]
     L.ltrx_test_rand_fill.argtypes = [fp, C.c_uint64]
     L.ltrx_test_bvh.argtypes = [fp, u32, C.c_int, C.POINTER(u32), C.POINTER(u32), C.c_void_p, fp]
+    L.ltrx_test_bvh_entry.argtypes = [fp, u32, C.c_int, fp, C.c_void_p, u32, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                      C.POINTER(C.c_uint64), C.POINTER(u32)]
     _lib = L
     return L
 

@@ -25,6 +25,7 @@
 #include <thread>
 
 #include "gpu.h"
+#include "bvh_entry.h"
 #include "nccl_dl.h"
 #include "randfill.h"
 #include "scene.h"
@@ -658,7 +659,7 @@ void readback(ltr_Scene *S)
         st.n_correction_rays = c.correction_rays; st.n_rad_pairs = c.rad_pairs; st.n_rad_segments = c.rad_segments;
         st.n_rad_links = c.rad_links; st.n_node_visits = c.node_visits; st.n_tri_tests = c.tri_tests;
         st.n_ray_node_visits = c.ray_node_visits; st.n_ray_tri_tests = c.ray_tri_tests; st.n_rad_tile_loads = c.rad_tile_loads;
-        st.kernel_launches = c.kernel_launches; st.h2d_bytes = c.h2d_bytes; st.d2h_bytes = c.d2h_bytes; st.n_rad_batches = c.rad_batches; st.n_shadow_rays = c.shadow_rays;
+        st.kernel_launches = c.kernel_launches; st.h2d_bytes = c.h2d_bytes; st.d2h_bytes = c.d2h_bytes; st.n_rad_batches = c.rad_batches; st.n_shadow_rays = c.shadow_rays; st.n_ray_entry_tests = c.ray_entry_tests;
         st.gpu_ms_samples = c.ms_samples; st.gpu_ms_direct = c.ms_direct; st.gpu_ms_march = c.ms_march;
         st.gpu_ms_radiosity = c.ms_radiosity; st.gpu_ms_ao = c.ms_ao; st.gpu_ms_finalize = c.ms_finalize;
         st.gpu_ms_total = c.ms_samples + c.ms_direct + c.ms_radiosity + c.ms_ao + c.ms_finalize;
@@ -675,7 +676,7 @@ void collect_counters(ltr_Scene *S)
     st.n_correction_rays = c.correction_rays; st.n_rad_pairs = c.rad_pairs; st.n_rad_segments = c.rad_segments;
     st.n_rad_links = c.rad_links; st.n_node_visits = c.node_visits; st.n_tri_tests = c.tri_tests;
         st.n_ray_node_visits = c.ray_node_visits; st.n_ray_tri_tests = c.ray_tri_tests; st.n_rad_tile_loads = c.rad_tile_loads;
-    st.kernel_launches = c.kernel_launches; st.h2d_bytes = c.h2d_bytes; st.d2h_bytes = c.d2h_bytes; st.n_rad_batches = c.rad_batches; st.n_shadow_rays = c.shadow_rays;
+    st.kernel_launches = c.kernel_launches; st.h2d_bytes = c.h2d_bytes; st.d2h_bytes = c.d2h_bytes; st.n_rad_batches = c.rad_batches; st.n_shadow_rays = c.shadow_rays; st.n_ray_entry_tests = c.ray_entry_tests;
     st.gpu_ms_samples = c.ms_samples; st.gpu_ms_direct = c.ms_direct; st.gpu_ms_march = c.ms_march;
     st.gpu_ms_radiosity = c.ms_radiosity; st.gpu_ms_ao = c.ms_ao; st.gpu_ms_finalize = c.ms_finalize;
     st.gpu_ms_total = c.ms_samples + c.ms_direct + c.ms_radiosity + c.ms_ao + c.ms_finalize;
@@ -839,6 +840,113 @@ int ltrx_test_reftree(const float *tris9, u32 ntris, void *nodes_out, u32 nodes_
     memcpy(nodes_out, T.nodes.data(), T.nodes.size() * sizeof(RefNode));
     if (!T.items.empty()) memcpy(items_out, T.items.data(), T.items.size() * 4);
     return 1;
+}
+
+/* host model of the device any-hit walk on the 4-wide tree (gpu_internal.cuh: bvh4_anyhit_core), from a given start stack;
+ * returns hit/miss and adds the nodes read to *visits */
+static bool host_bvh4_anyhit(const SceneBvh &bvh, const std::vector<RayTri> &rt, V3 l1, V3 l2, std::vector<int32_t> &stack, uint64_t *visits)
+{
+    const V3 d = l2 - l1;
+    const float ix = d.x != 0 ? 1.0f / d.x : 1e30f, iy = d.y != 0 ? 1.0f / d.y : 1e30f, iz = d.z != 0 ? 1.0f / d.z : 1e30f;
+    bool hit = false;
+    while (!stack.empty()) {
+        const int32_t ni = stack.back(); stack.pop_back();
+        const Bvh4Node &n = bvh.nodes4[ni];
+        ++*visits;
+        for (int c = 0; c < 4; ++c) {
+            if (n.c[c] == BVH4_EMPTY) continue;
+            const float x0 = (n.lox[c] - l1.x) * ix, x1 = (n.hix[c] - l1.x) * ix, y0 = (n.loy[c] - l1.y) * iy, y1 = (n.hiy[c] - l1.y) * iy;
+            const float z0 = (n.loz[c] - l1.z) * iz, z1 = (n.hiz[c] - l1.z) * iz;
+            const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
+            const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));
+            if (!(t0 <= t1 + 2e-6f)) continue;
+            if (n.c[c] < 0) {
+                const uint32_t code = ~n.c[c];
+                for (uint32_t t = code >> 3; t < (code >> 3) + (code & 7u); ++t)
+                    if (seg_tri_prepared(l1, d, rt[t]) < 1.0f) hit = true;       /* keep walking: the visit count is that of a miss */
+            } else stack.push_back(n.c[c]);
+        }
+    }
+    return hit;
+}
+
+/* host-only check of the entry sets (bvh_entry.h) on bundles of segments: per bundle the box of its segments is padded,
+ * the entry set searched, and every segment walked twice -- from the root and from the entry set.  Returns 0 if any
+ * triangle whose box overlaps a bundle box is unreachable from that bundle's entry set; *mismatches counts segments
+ * whose two walks disagree (must be 0).  visits are 4-wide node reads summed over all segments. */
+int ltrx_test_bvh_entry(const float *tris9, u32 ntris, int leaf_max, const float *segs6, const u32 *bundle_off, u32 n_bundles,
+                        u32 *entries_out, uint64_t *visits_root, uint64_t *visits_entry, uint64_t *entry_tests, u32 *mismatches)
+{
+    SceneBvh bvh;
+    build_scene_bvh(tris9, ntris, bvh, leaf_max, 0);
+    if (bvh.nodes4.empty()) return 0;
+    int max_entries = BVH_ENTRY_MAX;
+    if (const char *e = getenv("LTR_TEST_ENTRY_MAX")) { max_entries = atoi(e); if (max_entries < 1 || max_entries > BVH_ENTRY_MAX) max_entries = BVH_ENTRY_MAX; }
+    std::vector<RayTri> rt(ntris);
+    for (u32 t = 0; t < ntris; ++t) {
+        const float *v = tris9 + 9 * (size_t)bvh.order[t];
+        prepare_raytri(mk3(v[0], v[1], v[2]), mk3(v[3], v[4], v[5]), mk3(v[6], v[7], v[8]), rt[t]);
+    }
+    *visits_root = *visits_entry = *entry_tests = 0; *mismatches = 0;
+    std::vector<int32_t> stack;
+    std::vector<char> reach(ntris);
+    int ok = 1;
+    for (u32 b = 0; b < n_bundles; ++b) {
+        float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
+        for (u32 s = bundle_off[b]; s < bundle_off[b + 1]; ++s)
+            for (int e = 0; e < 2; ++e) {
+                const float *p = segs6 + 6 * (size_t)s + 3 * e;
+                lx = fminf(lx, p[0]); ly = fminf(ly, p[1]); lz = fminf(lz, p[2]); hx = fmaxf(hx, p[0]); hy = fmaxf(hy, p[1]); hz = fmaxf(hz, p[2]);
+            }
+        BvhEntrySet E;
+        E.n = 0;
+        if (lx <= hx) {
+            bvh_entry_pad(lx, ly, lz, hx, hy, hz);
+            bvh4_entry_search(bvh.nodes4.data(), lx, ly, lz, hx, hy, hz, E, max_entries);
+        }
+        if (entries_out) entries_out[b] = (u32)E.n;
+        /* reachability: every triangle whose own box overlaps the padded bundle box */
+        std::fill(reach.begin(), reach.end(), 0);
+        for (int i = 0; i < E.n; ++i) stack.push_back(E.node[i]);
+        while (!stack.empty()) {
+            const Bvh4Node &n = bvh.nodes4[stack.back()]; stack.pop_back();
+            for (int c = 0; c < 4; ++c) {
+                if (n.c[c] == BVH4_EMPTY) continue;
+                if (n.c[c] >= 0) { stack.push_back(n.c[c]); continue; }
+                const uint32_t code = ~n.c[c];
+                for (uint32_t t = code >> 3; t < (code >> 3) + (code & 7u); ++t) reach[t] = 1;
+            }
+        }
+        if (lx <= hx)
+            for (u32 t = 0; t < ntris; ++t) {
+                const float *v = tris9 + 9 * (size_t)bvh.order[t];
+                const float tlx = fminf(v[0], fminf(v[3], v[6])), thx = fmaxf(v[0], fmaxf(v[3], v[6]));
+                const float tly = fminf(v[1], fminf(v[4], v[7])), thy = fmaxf(v[1], fmaxf(v[4], v[7]));
+                const float tlz = fminf(v[2], fminf(v[5], v[8])), thz = fmaxf(v[2], fmaxf(v[5], v[8]));
+                if (tlx <= hx && thx >= lx && tly <= hy && thy >= ly && tlz <= hz && thz >= lz && !reach[t]) ok = 0;
+            }
+        for (u32 s = bundle_off[b]; s < bundle_off[b + 1]; ++s) {
+            const float *p = segs6 + 6 * (size_t)s;
+            const V3 A = mk3(p[0], p[1], p[2]), B = mk3(p[3], p[4], p[5]);
+            stack.assign(1, 0);
+            const bool h_root = host_bvh4_anyhit(bvh, rt, A, B, stack, visits_root);
+            /* the entry tests of the device walk (gpu_internal.cuh: bvh4_anyhit_entries) */
+            const V3 d = B - A;
+            const float ix = d.x != 0 ? 1.0f / d.x : 1e30f, iy = d.y != 0 ? 1.0f / d.y : 1e30f, iz = d.z != 0 ? 1.0f / d.z : 1e30f;
+            stack.clear();
+            for (int i = 0; i < E.n; ++i) {
+                const float x0 = (E.lox[i] - A.x) * ix, x1 = (E.hix[i] - A.x) * ix, y0 = (E.loy[i] - A.y) * iy, y1 = (E.hiy[i] - A.y) * iy;
+                const float z0 = (E.loz[i] - A.z) * iz, z1 = (E.hiz[i] - A.z) * iz;
+                const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
+                const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));
+                if (t0 <= t1 + 2e-6f) stack.push_back(E.node[i]);
+            }
+            *entry_tests += (uint64_t)E.n;
+            const bool h_entry = host_bvh4_anyhit(bvh, rt, A, B, stack, visits_entry);
+            if (h_root != h_entry) ++*mismatches;
+        }
+    }
+    return ok;
 }
 
 int ltrx_test_bvh(const float *tris9, u32 ntris, int leaf_max, u32 *n_nodes, u32 *depth, u32 *order_out, float *bounds6)

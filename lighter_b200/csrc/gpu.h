@@ -89,6 +89,7 @@ typedef struct ltrgpu_Counters {
     uint64_t kernel_launches, h2d_bytes, d2h_bytes;
     uint64_t rad_batches;                      /* pair-sweep + visibility launch pairs */
     uint64_t shadow_rays;                      /* sampled-shadow extension: any-hit rays lumel x light x sample */
+    uint64_t ray_entry_tests;                  /* entry boxes tested by rays started from a bundle's entry set (bvh_entry.h) */
     float ms_samples, ms_direct, ms_march, ms_radiosity, ms_ao, ms_finalize, ms_rad_pairs, ms_rad_vis, ms_span;
 } ltrgpu_Counters;
 

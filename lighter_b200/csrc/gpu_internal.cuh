@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include "gpu.h"
+#include "bvh_entry.h"
 
 #define LB_BLOCK 128                      /* traversal kernels: 4 warps per CTA, many CTAs per SM */
 #define LB_PAD 1024                       /* slack elements on per-lumel arrays so shards can be padded to equal size */
@@ -99,7 +100,7 @@ struct ltrgpu_Ctx {
 };
 
 enum { CNT_MARCHES = 0, CNT_DIST_QUERIES, CNT_AO_SEGMENTS, CNT_CORR_RAYS, CNT_RAD_PAIRS, CNT_RAD_SEGMENTS,
-       CNT_RAD_LINKS, CNT_NODE_VISITS, CNT_TRI_TESTS, CNT_RAY_NODE_VISITS, CNT_RAY_TRI_TESTS, CNT_RAD_TILE_LOADS, CNT_SHADOW_RAYS, CNT_COUNT };
+       CNT_RAD_LINKS, CNT_NODE_VISITS, CNT_TRI_TESTS, CNT_RAY_NODE_VISITS, CNT_RAY_TRI_TESTS, CNT_RAD_TILE_LOADS, CNT_SHADOW_RAYS, CNT_RAY_ENTRY_TESTS, CNT_COUNT };
 
 #define CU_TRY(ctx, call)                                                                          \
     do {                                                                                           \
@@ -163,7 +164,7 @@ __device__ __forceinline__ float ref_acosf(float x) { return (float)acos((double
 __device__ __forceinline__ float ref_sinf(float x) { return (float)sin((double)x); }
 __device__ __forceinline__ float ref_cosf(float x) { return (float)cos((double)x); }
 
-struct TravStats { unsigned nodes, tris; };
+struct TravStats { unsigned nodes, tris, entries; };
 
 __device__ __forceinline__ float box_dist2(V3 p, float lx, float ly, float lz, float hx, float hy, float hz)
 {
@@ -430,16 +431,13 @@ __device__ __forceinline__ bool bvh_anyhit(const BvhNode *__restrict__ nodes, co
  * The same any-hit walk on the 4-wide tree (bvh.h Bvh4Node): one iteration tests four boxes (six float4 loads for the
  * boxes, one for the child codes).  A visit is counted as two node units (128 bytes = two 64-byte binary nodes).
  */
-template <int FLUSH = 10>
-__device__ __forceinline__ bool bvh4_anyhit(const Bvh4Node *__restrict__ nodes, const RayTri *__restrict__ tris, V3 l1, V3 l2, TravStats &ts)
+template <int FLUSH>
+__device__ __forceinline__ bool bvh4_anyhit_core(const Bvh4Node *__restrict__ nodes, const RayTri *__restrict__ tris, const V3 l1, const V3 d,
+                                                 const float ix, const float iy, const float iz, int (&stack_n)[BVH_STACK], int sp, int node, TravStats &ts)
 {
     constexpr int TQ = FLUSH + 28;                   /* FLUSH - 1 pending + four leaves of up to 7 triangles */
-    int stack_n[BVH_STACK];
     int tq[TQ];
-    int sp = 0, nq = 0;
-    const V3 d = l2 - l1;
-    const float ix = d.x != 0 ? 1.0f / d.x : 1e30f, iy = d.y != 0 ? 1.0f / d.y : 1e30f, iz = d.z != 0 ? 1.0f / d.z : 1e30f;
-    int node = 0;
+    int nq = 0;
     for (;;) {
         while (node >= 0) {
             const float4 *n4 = reinterpret_cast<const float4 *>(nodes + node);
@@ -475,6 +473,42 @@ __device__ __forceinline__ bool bvh4_anyhit(const Bvh4Node *__restrict__ nodes, 
         }
         if (node < 0) return false;
     }
+}
+
+template <int FLUSH = 10>
+__device__ __forceinline__ bool bvh4_anyhit(const Bvh4Node *__restrict__ nodes, const RayTri *__restrict__ tris, V3 l1, V3 l2, TravStats &ts)
+{
+    int stack_n[BVH_STACK];
+    const V3 d = l2 - l1;
+    const float ix = d.x != 0 ? 1.0f / d.x : 1e30f, iy = d.y != 0 ? 1.0f / d.y : 1e30f, iz = d.z != 0 ? 1.0f / d.z : 1e30f;
+    return bvh4_anyhit_core<FLUSH>(nodes, tris, l1, d, ix, iy, iz, stack_n, 0, 0, ts);
+}
+
+/*
+ * The same walk started from the entry set of the ray's bundle (bvh_entry.h) instead of the root: the ray tests the
+ * entry boxes (one box each; the set lives in shared memory, every lane reads the same words) and walks the sub-trees it
+ * touches.  ts.entries counts the entry boxes tested.
+ */
+template <int FLUSH = 10>
+__device__ __forceinline__ bool bvh4_anyhit_entries(const Bvh4Node *__restrict__ nodes, const RayTri *__restrict__ tris, const BvhEntrySet &E,
+                                                    V3 l1, V3 l2, TravStats &ts)
+{
+    int stack_n[BVH_STACK];
+    int sp = 0;
+    const V3 d = l2 - l1;
+    const float ix = d.x != 0 ? 1.0f / d.x : 1e30f, iy = d.y != 0 ? 1.0f / d.y : 1e30f, iz = d.z != 0 ? 1.0f / d.z : 1e30f;
+    const int n = E.n;
+    for (int i = 0; i < n; ++i) {
+        const float x0 = (E.lox[i] - l1.x) * ix, x1 = (E.hix[i] - l1.x) * ix, y0 = (E.loy[i] - l1.y) * iy, y1 = (E.hiy[i] - l1.y) * iy;
+        const float z0 = (E.loz[i] - l1.z) * iz, z1 = (E.hiz[i] - l1.z) * iz;
+        const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
+        const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));
+        if (t0 <= t1 + 2e-6f) stack_n[sp++] = E.node[i];
+    }
+    ts.entries += (unsigned)n;
+    if (sp == 0) return false;
+    const int node = stack_n[--sp];
+    return bvh4_anyhit_core<FLUSH>(nodes, tris, l1, d, ix, iy, iz, stack_n, sp, node, ts);
 }
 
 /* warp-aggregated counter add */

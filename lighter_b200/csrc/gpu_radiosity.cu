@@ -481,63 +481,108 @@ __global__ void rad_items_kernel(const TileBounds *__restrict__ tb32, const Tile
 
 template <int G> static size_t rad_sweep_smem() { return sizeof(RadColBuf<G>) * 2 * RAD_WARPS + sizeof(TileBounds) * RAD_WARPS + 16 * RAD_WARPS + 2 * RAD_STAGE * RAD_WARPS; }
 
-/* one thread per candidate: blocked segment -> directed link(s) keyed (row sorted position, partner original index) */
+/*
+ * Visibility of the candidates: blocked segment -> directed link(s) keyed (row sorted position, partner original index).
+ *
+ * The candidate array is a sequence of RAD_CHUNK-slot chunks, each written by ONE sweep warp: the candidates of one row
+ * warp (32 neighbouring lumels) against a few Morton-consecutive column tiles, i.e. a spatially compact bundle of
+ * segments.  A warp takes whole chunks.  ENTRY = true: it first reduces the chunk's bounding box (one extra pass over the
+ * 12-byte candidates; the positions come out of L1/L2 again in the second pass), lane 0 descends the scene tree once for
+ * the whole chunk (bvh_entry.h) and leaves the entry set in shared memory; the 1024 segments then start at the entry set
+ * instead of the root.  ENTRY = false is the plain walk from the root (kept for A/B measurement: LTR_RAD_ENTRY=0).
+ */
+template <bool ENTRY>
 __global__ void __launch_bounds__(LB_BLOCK)
 rad_visibility_kernel(const Bvh4Node *__restrict__ bvh, const RayTri *__restrict__ raytris, const float4 *__restrict__ spos,
                       const uint32_t *__restrict__ sidx, const RadCand *__restrict__ cand, unsigned long long n_cand,
                       uint32_t my_k0, uint32_t my_k1, unsigned long long *__restrict__ keys, float *__restrict__ factors,
                       unsigned long long *link_count, uint4 *__restrict__ mirror, unsigned long long mirror_cap, unsigned long long *mirror_count,
-                      unsigned long long *counters)
+                      uint32_t *chunk_cursor, unsigned long long *counters)
 {
+    __shared__ BvhEntrySet s_entry[LB_BLOCK / 32];
     unsigned segs = 0;
     TravStats ts = { 0, 0 };
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned long long n_pad = (n_cand + 31ull) & ~31ull;
-    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_pad; e += (unsigned long long)gridDim.x * blockDim.x) {
-        unsigned emit = 0;                        /* bit 0: link for row a (always mine), bit 1: row b is mine too, bit 2: row b lives on another rank */
-        RadCand c = { 0, 0, 0.f };
-        uint32_t oa = 0, ob = 0;
-        if (e < n_cand) {
-            c = cand[e];
+    BvhEntrySet &E = s_entry[threadIdx.x >> 5];
+    const unsigned long long n_chunks = (n_cand + RAD_CHUNK - 1ull) / RAD_CHUNK;
+    for (;;) {                                        /* persistent warps: chunks differ a lot in cost, so they are pulled from a cursor */
+        uint32_t ch = 0;
+        if (lane == 0) ch = atomicAdd(chunk_cursor, 1u);
+        ch = __shfl_sync(0xffffffffu, ch, 0);
+        if (ch >= n_chunks) break;
+        const unsigned long long e0 = (unsigned long long)ch * RAD_CHUNK;
+        if (ENTRY) {
+            float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
+            for (unsigned i = 0; i < RAD_CHUNK; i += 32u) {
+                const unsigned long long e = e0 + i + lane;
+                if (e >= n_cand) break;
+                const RadCand c = cand[e];
+                if (c.a == RAD_PAD) continue;
+                const float4 A = spos[c.a], B = spos[c.b];
+                lx = fminf(lx, fminf(A.x, B.x)); ly = fminf(ly, fminf(A.y, B.y)); lz = fminf(lz, fminf(A.z, B.z));
+                hx = fmaxf(hx, fmaxf(A.x, B.x)); hy = fmaxf(hy, fmaxf(A.y, B.y)); hz = fmaxf(hz, fmaxf(A.z, B.z));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)); ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o)); lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o));
+                hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o)); hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+            }
+            if (!(lx <= hx)) continue;                /* warp-uniform: the chunk holds only unused slots */
+            __syncwarp();                             /* every lane is done with the previous chunk's set */
+            if (lane == 0) {
+                bvh_entry_pad(lx, ly, lz, hx, hy, hz);
+                bvh4_entry_search(bvh, lx, ly, lz, hx, hy, hz, E);
+            }
+            __syncwarp();
         }
-        if (e < n_cand && c.a != RAD_PAD) {           /* RAD_PAD: unused slot of a warp's output chunk */
-            oa = sidx[c.a]; ob = sidx[c.b];
-            const bool a_first = oa < ob;         /* the reference traces from the lower lumel index */
-            const V3 A = ld3(spos[a_first ? c.a : c.b]), B = ld3(spos[a_first ? c.b : c.a]);
-            const V3 dn = norm3(B - A);
-            const V3 mA = A + dn * LB_SMALL, mB = B - dn * LB_SMALL;
-            ++segs;
-            if (bvh4_anyhit(bvh, raytris, mA, mB, ts))
-                emit = 1u | ((c.b >= my_k0 && c.b < my_k1) ? 2u : 4u);
-        }
-        const unsigned cnt = __popc(emit & 3u);
-        /* warp-aggregated append: exclusive prefix of cnt over the warp */
-        unsigned pre = cnt;
-        for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= (unsigned)o) pre += t; }
-        const unsigned total = __shfl_sync(0xffffffffu, pre, 31);
-        if (total) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(link_count, (unsigned long long)total);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            unsigned long long at = base + (pre - cnt);
-            if (emit & 1u) { keys[at] = ((unsigned long long)c.a << 32) | ob; factors[at] = c.factor; ++at; }
-            if (emit & 2u) { keys[at] = ((unsigned long long)c.b << 32) | oa; factors[at] = c.factor; }
-        }
-        /* mirrored link for a row owned by another rank: queued for the exchange */
-        const unsigned mm = __ballot_sync(0xffffffffu, (emit & 4u) != 0);
-        if (mm) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(mirror_count, (unsigned long long)__popc(mm));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (emit & 4u) {
-                const unsigned long long at = base + __popc(mm & ((1u << lane) - 1u));
-                if (at < mirror_cap) mirror[at] = make_uint4(c.b, oa, __float_as_uint(c.factor), 0u);
+        for (unsigned i = 0; i < RAD_CHUNK; i += 32u) {
+            const unsigned long long e = e0 + i + lane;
+            if (e0 + i >= n_cand) break;              /* warp-uniform */
+            unsigned emit = 0;                        /* bit 0: link for row a (always mine), bit 1: row b is mine too, bit 2: row b lives on another rank */
+            RadCand c = { RAD_PAD, 0, 0.f };
+            uint32_t oa = 0, ob = 0;
+            if (e < n_cand) c = cand[e];
+            if (!__any_sync(0xffffffffu, c.a != RAD_PAD)) continue;
+            if (c.a != RAD_PAD) {                     /* RAD_PAD: unused slot of a warp's output chunk */
+                oa = sidx[c.a]; ob = sidx[c.b];
+                const bool a_first = oa < ob;         /* the reference traces from the lower lumel index */
+                const V3 A = ld3(spos[a_first ? c.a : c.b]), B = ld3(spos[a_first ? c.b : c.a]);
+                const V3 dn = norm3(B - A);
+                const V3 mA = A + dn * LB_SMALL, mB = B - dn * LB_SMALL;
+                ++segs;
+                const bool blocked = ENTRY ? bvh4_anyhit_entries(bvh, raytris, E, mA, mB, ts) : bvh4_anyhit(bvh, raytris, mA, mB, ts);
+                if (blocked) emit = 1u | ((c.b >= my_k0 && c.b < my_k1) ? 2u : 4u);
+            }
+            const unsigned cnt = __popc(emit & 3u);
+            /* warp-aggregated append: exclusive prefix of cnt over the warp */
+            unsigned pre = cnt;
+            for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= (unsigned)o) pre += t; }
+            const unsigned total = __shfl_sync(0xffffffffu, pre, 31);
+            if (total) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(link_count, (unsigned long long)total);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                unsigned long long at = base + (pre - cnt);
+                if (emit & 1u) { keys[at] = ((unsigned long long)c.a << 32) | ob; factors[at] = c.factor; ++at; }
+                if (emit & 2u) { keys[at] = ((unsigned long long)c.b << 32) | oa; factors[at] = c.factor; }
+            }
+            /* mirrored link for a row owned by another rank: queued for the exchange */
+            const unsigned mm = __ballot_sync(0xffffffffu, (emit & 4u) != 0);
+            if (mm) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(mirror_count, (unsigned long long)__popc(mm));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (emit & 4u) {
+                    const unsigned long long at = base + __popc(mm & ((1u << lane) - 1u));
+                    if (at < mirror_cap) mirror[at] = make_uint4(c.b, oa, __float_as_uint(c.factor), 0u);
+                }
             }
         }
     }
     count_add(counters, CNT_RAD_SEGMENTS, segs);
     count_add(counters, CNT_RAY_NODE_VISITS, ts.nodes);
     count_add(counters, CNT_RAY_TRI_TESTS, ts.tris);
+    count_add(counters, CNT_RAY_ENTRY_TESTS, ts.entries);
 }
 
 /* after the exchange: keep the mirrored links whose row is mine */
@@ -709,6 +754,8 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
     const bool trace = getenv("LTR_TRACE") != nullptr;
     /* column group size of the warp-level culling (4, 8, 16 or 32 lumels); LTR_RAD_GROUP overrides for experiments */
     int group = RAD_GROUP_DEFAULT;
+    bool rad_entry = true;                         /* visibility rays start at their chunk's entry set; LTR_RAD_ENTRY=0: at the root (A/B) */
+    if (const char *e = getenv("LTR_RAD_ENTRY")) rad_entry = atoi(e) != 0;
     if (const char *e = getenv("LTR_RAD_GROUP")) { const int g = atoi(e); if (g == 4 || g == 8 || g == 16 || g == 32) group = g; }
     struct timespec tr0; clock_gettime(CLOCK_MONOTONIC, &tr0);
 #define RAD_TRACE(label) do { if (trace) { cudaStreamSynchronize(st); struct timespec t_; clock_gettime(CLOCK_MONOTONIC, &t_); \
@@ -864,14 +911,17 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
                 RAD_TRY(grow_buf(ctx, &keys, &link_cap, link_used, link_used + 2 * nc));
                 RAD_TRY(grow_buf(ctx, &fac, &link_cap_f, link_used, link_used + 2 * nc));
                 if (world > 1) RAD_TRY(grow_buf(ctx, &mirror, &mirror_cap, mirror_used, mirror_used + nc));
-                unsigned long long want = (nc + LB_BLOCK - 1) / LB_BLOCK;
-                unsigned cap = (unsigned)ctx->num_sms * 32;
+                /* one warp per RAD_CHUNK candidates at a time, pulled from a cursor (the upper half of d_cnt[3], zero since the memset above) */
+                unsigned long long want = ((nc + RAD_CHUNK - 1) / RAD_CHUNK + LB_BLOCK / 32 - 1) / (LB_BLOCK / 32);
+                unsigned cap = (unsigned)ctx->num_sms * 16;
                 unsigned blocks = want > cap ? cap : (unsigned)want;
                 RAD_CU(cudaEventRecord(ctx->ev_k0, st));
-                rad_visibility_kernel<<<blocks, LB_BLOCK, 0, st>>>(ctx->d_bvh4, ctx->d_raytris, spos, sidx, cand, nc, (uint32_t)k0, (uint32_t)k1,
-                                                                  keys + link_used, fac + link_used, d_cnt + 1,
-                                                                  mirror ? mirror + mirror_used : nullptr, mirror ? mirror_cap - mirror_used : 0, d_cnt + 2,
-                                                                  ctx->d_counters);
+#define RAD_VIS(ENTRY) rad_visibility_kernel<ENTRY><<<blocks, LB_BLOCK, 0, st>>>(ctx->d_bvh4, ctx->d_raytris, spos, sidx, cand, nc, (uint32_t)k0, (uint32_t)k1, \
+                                                                  keys + link_used, fac + link_used, d_cnt + 1,                                                \
+                                                                  mirror ? mirror + mirror_used : nullptr, mirror ? mirror_cap - mirror_used : 0, d_cnt + 2,  \
+                                                                  (uint32_t *)(d_cnt + 3) + 1, ctx->d_counters)
+                if (rad_entry) RAD_VIS(true); else RAD_VIS(false);
+#undef RAD_VIS
                 RAD_LAUNCHED();
                 RAD_CU(cudaEventRecord(ctx->ev_k1, st));
                 RAD_CU(cudaMemcpyAsync(h_cnt, d_cnt, 32, cudaMemcpyDeviceToHost, st));

@@ -395,7 +395,7 @@ extern "C" int ltrgpu_get_counters(ltrgpu_Ctx *ctx, ltrgpu_Counters *out)
     h.marches = c[CNT_MARCHES]; h.distance_queries = c[CNT_DIST_QUERIES]; h.ao_segments = c[CNT_AO_SEGMENTS];
     h.correction_rays = c[CNT_CORR_RAYS]; h.rad_pairs = c[CNT_RAD_PAIRS]; h.rad_segments = c[CNT_RAD_SEGMENTS];
     h.rad_links = c[CNT_RAD_LINKS]; h.node_visits = c[CNT_NODE_VISITS]; h.tri_tests = c[CNT_TRI_TESTS];
-    h.ray_node_visits = c[CNT_RAY_NODE_VISITS]; h.ray_tri_tests = c[CNT_RAY_TRI_TESTS]; h.rad_tile_loads = c[CNT_RAD_TILE_LOADS]; h.shadow_rays = c[CNT_SHADOW_RAYS];
+    h.ray_node_visits = c[CNT_RAY_NODE_VISITS]; h.ray_tri_tests = c[CNT_RAY_TRI_TESTS]; h.rad_tile_loads = c[CNT_RAD_TILE_LOADS]; h.shadow_rays = c[CNT_SHADOW_RAYS]; h.ray_entry_tests = c[CNT_RAY_ENTRY_TESTS];
     *out = h;
     return 0;
 }

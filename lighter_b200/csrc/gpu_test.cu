@@ -46,19 +46,34 @@ __global__ void t_segtri_kernel(const float *a, const float *b, const float *tri
 __global__ void t_queries_kernel(const BvhNode *bvh, const Bvh4Node *bvh4, const PreparedTri *pt, const RayTri *rt, const uint32_t *orig, const float *a, const float *b,
                                  uint32_t n, float *dist, int *anyhit, float *closest, int *closest_tri)
 {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    __shared__ BvhEntrySet s_entry[4];               /* launched with 128 threads */
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    const uint32_t q = valid ? i : 0;                /* idle lanes of the last warp stay for the warp-wide reduction below */
     TravStats ts = { 0, 0 };
-    V3 A = mk3(a[3 * i], a[3 * i + 1], a[3 * i + 2]), B = mk3(b[3 * i], b[3 * i + 1], b[3 * i + 2]);
-    if (dist) dist[i] = bvh_distance(bvh, pt, A, 2.0f, -1.0f, ts);
+    V3 A = mk3(a[3 * q], a[3 * q + 1], a[3 * q + 2]), B = mk3(b[3 * q], b[3 * q + 1], b[3 * q + 2]);
+    if (dist && valid) dist[i] = bvh_distance(bvh, pt, A, 2.0f, -1.0f, ts);
     if (anyhit) {
-        /* three implementations of the same predicate: ordered segment walk, two-phase binary walk, two-phase 4-wide walk
-         * (the one the radiosity and sampled-shadow kernels use); a disagreement is reported as 2 + bits */
+        /* the bundle of this warp's 32 segments: box, entry set (bvh_entry.h), walk from the entry set */
+        float lx = fminf(A.x, B.x), ly = fminf(A.y, B.y), lz = fminf(A.z, B.z), hx = fmaxf(A.x, B.x), hy = fmaxf(A.y, B.y), hz = fmaxf(A.z, B.z);
+        for (int o = 16; o > 0; o >>= 1) {
+            lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)); ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o)); lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o));
+            hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o)); hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+        }
+        BvhEntrySet &E = s_entry[threadIdx.x >> 5];
+        if ((threadIdx.x & 31u) == 0) {
+            bvh_entry_pad(lx, ly, lz, hx, hy, hz);
+            bvh4_entry_search(bvh4, lx, ly, lz, hx, hy, hz, E);
+        }
+        __syncwarp();
+        /* four implementations of the same predicate: ordered segment walk, two-phase binary walk, two-phase 4-wide walk
+         * from the root and from the bundle's entry set (the one the radiosity kernel uses); a disagreement is reported as 2 + bits */
         const int h0 = bvh_segment<true>(bvh, rt, orig, A, B, nullptr, ts) < 1.0f ? 1 : 0;
         const int h1 = bvh_anyhit(bvh, rt, A, B, ts) ? 1 : 0, h2 = bvh4_anyhit(bvh4, rt, A, B, ts) ? 1 : 0, h3 = bvh4_anyhit<2>(bvh4, rt, A, B, ts) ? 1 : 0;
-        anyhit[i] = (h0 == h1 && h1 == h2 && h2 == h3) ? h0 : 2 + h0 + 2 * h1 + 4 * h2 + 8 * h3;
+        const int h4 = bvh4_anyhit_entries(bvh4, rt, E, A, B, ts) ? 1 : 0;
+        if (valid) anyhit[i] = (h0 == h1 && h1 == h2 && h2 == h3 && h3 == h4) ? h0 : 2 + h0 + 2 * h1 + 4 * h2 + 8 * h3 + 16 * h4;
     }
-    if (closest) {
+    if (closest && valid) {
         int slot = -1;
         closest[i] = bvh_segment<false>(bvh, rt, orig, A, B, &slot, ts);
         if (closest_tri) closest_tri[i] = slot >= 0 ? (int)orig[slot] : -1;

@@ -117,6 +117,37 @@ def test_flat_bvh_invariants():
     assert b["ok"] and b["depth"] <= 20
 
 
+def test_bvh_entry_set_keeps_every_triangle_in_range_reachable():
+    """csrc/bvh_entry.h: for bundles of segments (compact, scene-wide, degenerate, empty) the entry set must keep every
+    triangle whose box overlaps the bundle box reachable, and the any-hit walk from the entry set must agree with the walk
+    from the root on every segment -- while reading fewer nodes on compact bundles."""
+    rng = np.random.default_rng(11)
+    for n, leaf in ((0, 2), (1, 2), (3, 2), (400, 2), (20000, 2), (20000, 7)):
+        tris = (rng.uniform(-20, 20, (n, 1, 3)) * np.array([1, 1, 0.1]) + rng.uniform(-0.4, 0.4, (n, 3, 3))).astype(np.float32).reshape(n, 9)
+        segs, off = [], [0]
+        for b in range(40):
+            k = int(rng.integers(1, 200))
+            if b % 4 == 3:                           # scene-wide bundle: the entry set has to stay near the root
+                a, e = rng.uniform(-22, 22, (k, 3)), rng.uniform(-22, 22, (k, 3))
+            else:                                    # compact bundle
+                c = rng.uniform(-18, 18, 3) * np.array([1, 1, 0.1])
+                a, e = c + rng.uniform(-1, 1, (k, 3)), c + rng.uniform(-3, 3, (k, 3))
+            if b == 5:
+                e = a.copy()                         # zero-length segments
+            if b == 6:
+                a[:, 0] = e[:, 0] = 1.5              # axis-parallel: zero direction components
+            segs.append(np.c_[a, e]); off.append(off[-1] + k)
+        off.append(off[-1])                          # an empty bundle
+        r = api.test_bvh_entry(tris, np.concatenate(segs), np.array(off, np.uint32), leaf)
+        if n == 0:
+            continue
+        assert r["ok"], (n, leaf)
+        assert r["mismatches"] == 0, (n, leaf, r["mismatches"])
+        assert r["entries"].max() <= 8 and r["entries"][-1] == 0
+        if n >= 20000:
+            assert r["visits_entry"] < 0.8 * r["visits_root"], r
+
+
 def test_rand_replay_equals_libc_stream_and_leaves_libc_in_step():
     """The AO pass consumes one libc rand() per lumel (lighter.cpp:819).  The library's fast replay must give
     exactly rand()/RAND_MAX, and the libc generator must afterwards stand where that many rand() calls leave
