@@ -925,6 +925,29 @@ int ltrx_test_bvh_entry(const float *tris9, u32 ntris, int leaf_max, const float
                 const float tlz = fminf(v[2], fminf(v[5], v[8])), thz = fmaxf(v[2], fmaxf(v[5], v[8]));
                 if (tlx <= hx && thx >= lx && tly <= hy && thy >= ly && tlz <= hz && thz >= lz && !reach[t]) ok = 0;
             }
+        /* the same on the binary tree (closest-hit walks: ambient occlusion) */
+        if (lx <= hx) {
+            BvhEntrySet E2;
+            bvh2_entry_search(bvh.nodes.data(), lx, ly, lz, hx, hy, hz, E2, max_entries);
+            std::fill(reach.begin(), reach.end(), 0);
+            for (int i = 0; i < E2.n; ++i) stack.push_back(E2.node[i]);
+            while (!stack.empty()) {
+                const BvhNode &n = bvh.nodes[stack.back()]; stack.pop_back();
+                const int32_t cs[2] = { n.c0, n.c1 };
+                for (int c = 0; c < 2; ++c) {
+                    if (cs[c] >= 0) { stack.push_back(cs[c]); continue; }
+                    const uint32_t code = ~cs[c];
+                    for (uint32_t t = code >> 3; t < (code >> 3) + (code & 7u); ++t) reach[t] = 1;
+                }
+            }
+            for (u32 t = 0; t < ntris; ++t) {
+                const float *v = tris9 + 9 * (size_t)bvh.order[t];
+                const float tlx = fminf(v[0], fminf(v[3], v[6])), thx = fmaxf(v[0], fmaxf(v[3], v[6]));
+                const float tly = fminf(v[1], fminf(v[4], v[7])), thy = fmaxf(v[1], fmaxf(v[4], v[7]));
+                const float tlz = fminf(v[2], fminf(v[5], v[8])), thz = fmaxf(v[2], fmaxf(v[5], v[8]));
+                if (tlx <= hx && thx >= lx && tly <= hy && thy >= ly && tlz <= hz && thz >= lz && !reach[t]) ok = 0;
+            }
+        }
         for (u32 s = bundle_off[b]; s < bundle_off[b + 1]; ++s) {
             const float *p = segs6 + 6 * (size_t)s;
             const V3 A = mk3(p[0], p[1], p[2]), B = mk3(p[3], p[4], p[5]);

@@ -24,7 +24,7 @@
 
 struct BvhEntrySet {
     int n;
-    int node[BVH_ENTRY_MAX];                      /* Bvh4Node indices */
+    int node[BVH_ENTRY_MAX];                      /* node indices of the tree searched (Bvh4Node or BvhNode) */
     float lox[BVH_ENTRY_MAX], loy[BVH_ENTRY_MAX], loz[BVH_ENTRY_MAX];
     float hix[BVH_ENTRY_MAX], hiy[BVH_ENTRY_MAX], hiz[BVH_ENTRY_MAX];
 };
@@ -39,9 +39,31 @@ LB_HD void bvh_entry_pad(float &lx, float &ly, float &lz, float &hx, float &hy, 
     lx -= pad; ly -= pad; lz -= pad; hx += pad; hy += pad; hz += pad;
 }
 
+/* node accessors: the search is the same on the binary tree (closest-hit walks) and on its 4-wide collapse (any-hit walks) */
+struct Bvh4Access {
+    typedef Bvh4Node Node;
+    static constexpr int W = 4;
+    static LB_HD int code(const Node &n, int c) { return n.c[c]; }
+    static LB_HD bool empty(int code) { return code == BVH4_EMPTY; }
+    static LB_HD void box(const Node &n, int c, float &lx, float &ly, float &lz, float &hx, float &hy, float &hz)
+    { lx = n.lox[c]; ly = n.loy[c]; lz = n.loz[c]; hx = n.hix[c]; hy = n.hiy[c]; hz = n.hiz[c]; }
+};
+struct Bvh2Access {
+    typedef BvhNode Node;
+    static constexpr int W = 2;
+    static LB_HD int code(const Node &n, int c) { return c ? n.c1 : n.c0; }
+    static LB_HD bool empty(int) { return false; }
+    static LB_HD void box(const Node &n, int c, float &lx, float &ly, float &lz, float &hx, float &hy, float &hz)
+    {
+        if (c) { lx = n.lo1x; ly = n.lo1y; lz = n.lo1z; hx = n.hi1x; hy = n.hi1y; hz = n.hi1z; }
+        else   { lx = n.lo0x; ly = n.lo0y; lz = n.lo0z; hx = n.hi0x; hy = n.hi0y; hz = n.hi0z; }
+    }
+};
+
 /* Scalar, executed by one thread per bundle.  `iters` (optional) receives the number of nodes read. */
-LB_HD void bvh4_entry_search(const Bvh4Node *nodes, float qlx, float qly, float qlz, float qhx, float qhy, float qhz,
-                             BvhEntrySet &E, int max_entries = BVH_ENTRY_MAX, int *iters = nullptr)
+template <class A>
+LB_HD void bvh_entry_search_t(const typename A::Node *nodes, float qlx, float qly, float qlz, float qhx, float qhy, float qhz,
+                              BvhEntrySet &E, int max_entries = BVH_ENTRY_MAX, int *iters = nullptr)
 {
     E.n = 1;
     E.node[0] = 0;
@@ -58,15 +80,20 @@ LB_HD void bvh4_entry_search(const Bvh4Node *nodes, float qlx, float qly, float 
             if (s > best) { best = s; pick = i; }
         }
         if (pick < 0) break;
-        const Bvh4Node *N = nodes + E.node[pick];
-        int nh = 0, hc[4];
+        const typename A::Node &N = nodes[E.node[pick]];
+        int nh = 0, hcode[A::W];
+        float hb[A::W][6];
         bool leaf = false;
-        for (int c = 0; c < 4; ++c) {
-            const int code = N->c[c];
-            if (code == BVH4_EMPTY) continue;
-            if (N->lox[c] <= qhx && N->hix[c] >= qlx && N->loy[c] <= qhy && N->hiy[c] >= qly && N->loz[c] <= qhz && N->hiz[c] >= qlz) {
+        for (int c = 0; c < A::W; ++c) {
+            const int code = A::code(N, c);
+            if (A::empty(code)) continue;
+            float lx, ly, lz, hx, hy, hz;
+            A::box(N, c, lx, ly, lz, hx, hy, hz);
+            if (lx <= qhx && hx >= qlx && ly <= qhy && hy >= qly && lz <= qhz && hz >= qlz) {
                 if (code < 0) leaf = true;
-                hc[nh++] = c;
+                hcode[nh] = code;
+                hb[nh][0] = lx; hb[nh][1] = ly; hb[nh][2] = lz; hb[nh][3] = hx; hb[nh][4] = hy; hb[nh][5] = hz;
+                ++nh;
             }
         }
         if (leaf || E.n - 1 + nh > max_entries) { fin |= 1u << pick; continue; }
@@ -83,12 +110,22 @@ LB_HD void bvh4_entry_search(const Bvh4Node *nodes, float qlx, float qly, float 
             continue;
         }
         for (int k = 0; k < nh; ++k) {            /* first child in place, the others appended (their final bits are clear) */
-            const int c = hc[k];
             const int at = k == 0 ? pick : E.n++;
-            E.node[at] = N->c[c];
-            E.lox[at] = N->lox[c]; E.loy[at] = N->loy[c]; E.loz[at] = N->loz[c];
-            E.hix[at] = N->hix[c]; E.hiy[at] = N->hiy[c]; E.hiz[at] = N->hiz[c];
+            E.node[at] = hcode[k];
+            E.lox[at] = hb[k][0]; E.loy[at] = hb[k][1]; E.loz[at] = hb[k][2];
+            E.hix[at] = hb[k][3]; E.hiy[at] = hb[k][4]; E.hiz[at] = hb[k][5];
         }
     }
     if (iters) *iters = it;
+}
+
+LB_HD void bvh4_entry_search(const Bvh4Node *nodes, float qlx, float qly, float qlz, float qhx, float qhy, float qhz,
+                             BvhEntrySet &E, int max_entries = BVH_ENTRY_MAX, int *iters = nullptr)
+{
+    bvh_entry_search_t<Bvh4Access>(nodes, qlx, qly, qlz, qhx, qhy, qhz, E, max_entries, iters);
+}
+LB_HD void bvh2_entry_search(const BvhNode *nodes, float qlx, float qly, float qlz, float qhx, float qhy, float qhz,
+                             BvhEntrySet &E, int max_entries = BVH_ENTRY_MAX, int *iters = nullptr)
+{
+    bvh_entry_search_t<Bvh2Access>(nodes, qlx, qly, qlz, qhx, qhy, qhz, E, max_entries, iters);
 }

@@ -6,8 +6,8 @@
  * offset per lumel; blend into the lumel colour), lighter_int.hpp:456-471 (spiral direction),
  * lighter.cpp:254-289 (closest hit over shadow-casting instances, end points pulled in by 0.001).
  *
- * GPU formulation: one thread per (lumel, sample) traces the segment on the flat BVH and stores
- * the hit parameter; a second kernel, one thread per lumel, sums the samples in index order (the
+ * GPU formulation: one warp per 32 neighbouring lumels traces their samples on the flat BVH, starting
+ * at the group's entry set, and stores the hit parameters; a second kernel, one thread per lumel, sums the samples in index order (the
  * reference's float summation order) and applies the blend.  The per-lumel random offset is the
  * host's libc rand() stream replayed in the reference's order (bake.cpp), uploaded per lumel.
  */
@@ -25,6 +25,14 @@ __device__ __forceinline__ V3 spiral_dir(V3 dir, float randoff, int i, float cos
     return cos_around * sin_side * rt + sin_around * sin_side * up + cos_side * dir;
 }
 
+/*
+ * One warp per group of 32 consecutive lumels (neighbouring texels of one lightmap row), one lumel per lane, the samples
+ * in a loop: a warp traces the same sample index for 32 neighbouring lumels, i.e. nearly parallel segments from nearby
+ * origins.  Every segment of the group lies within ao_distance of the group's origins, so the scene tree is descended
+ * ONCE per group (bvh_entry.h; lane 0, entry set in shared memory) and the 32 x num_samples segments start there
+ * instead of at the root -- for 2-unit segments in a 400-unit scene most of a root walk is that descent.
+ */
+template <bool ENTRY>
 __global__ void __launch_bounds__(LB_BLOCK)
 ao_trace_kernel(const BvhNode *__restrict__ bvh, const RayTri *__restrict__ raytris, const uint32_t *__restrict__ tri_orig,
                 const float4 *__restrict__ lpos, const float4 *__restrict__ lnrm, const float *__restrict__ randoff,
@@ -32,31 +40,52 @@ ao_trace_kernel(const BvhNode *__restrict__ bvh, const RayTri *__restrict__ rayt
                 uint64_t sh_begin, uint32_t n_local, int num_samples, float ao_distance,
                 float *__restrict__ hits, unsigned long long *counters)
 {
-    const uint64_t total = (uint64_t)((n_local + 31u) / 32u) * 32ull * num_samples;   /* padded to whole groups */
+    __shared__ BvhEntrySet s_entry[LB_BLOCK / 32];
+    BvhEntrySet &E = s_entry[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t n_groups = (n_local + 31u) / 32u;
+    const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     unsigned segs = 0;
     TravStats ts = { 0, 0 };
-    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
-        /* sample-major inside a group of 32 lumels: a warp traces the same sample index for 32
-         * neighbouring lumels, i.e. nearly parallel segments from nearby origins */
-        const uint64_t grp = e / (32ull * num_samples);
-        const uint32_t rem = (uint32_t)(e % (32ull * num_samples));
-        const int s = (int)(rem / 32u);
-        const uint64_t li = grp * 32ull + (rem & 31u);
-        if (li >= n_local) continue;
-        const uint64_t g = sh_begin + li;
+    for (uint32_t grp = warp0; grp < n_groups; grp += n_warps) {
+        const uint32_t li = grp * 32u + lane;
+        const bool valid = li < n_local;
+        const uint64_t g = sh_begin + (valid ? li : n_local - 1u);
         const V3 SP = ld3(lpos[g]), SN = ld3(lnrm[g]);
         const V3 origin = SP + SN * (LB_SMALL * 2);
-        const V3 ray = spiral_dir(SN, randoff[li], s, cos_side[s], sin_side[s]) * ao_distance;
-        const V3 B = origin + ray;
-        const V3 dn = norm3(B - origin);
-        const V3 mA = origin + dn * LB_SMALL, mB = B - dn * LB_SMALL;
-        float hit = bvh_segment<false>(bvh, raytris, tri_orig, mA, mB, nullptr, ts);
-        hits[li * num_samples + s] = hit;
-        ++segs;
+        const float ro = valid ? randoff[li] : 0.f;
+        if (ENTRY) {
+            /* |spiral_dir| = 1 up to rounding, so every end point is within ao_distance (1 + 1e-3) of its origin */
+            const float reach = ao_distance * 1.001f;
+            float lx = origin.x - reach, ly = origin.y - reach, lz = origin.z - reach, hx = origin.x + reach, hy = origin.y + reach, hz = origin.z + reach;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)); ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o)); lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o));
+                hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o)); hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+            }
+            __syncwarp();                             /* every lane is done with the previous group's set */
+            if (lane == 0) {
+                bvh_entry_pad(lx, ly, lz, hx, hy, hz);
+                bvh2_entry_search(bvh, lx, ly, lz, hx, hy, hz, E);
+            }
+            __syncwarp();
+        }
+        if (!valid) continue;                         /* no warp-wide operation below */
+        for (int s = 0; s < num_samples; ++s) {
+            const V3 ray = spiral_dir(SN, ro, s, cos_side[s], sin_side[s]) * ao_distance;
+            const V3 B = origin + ray;
+            const V3 dn = norm3(B - origin);
+            const V3 mA = origin + dn * LB_SMALL, mB = B - dn * LB_SMALL;
+            const float hit = ENTRY ? bvh_segment_entries<false>(bvh, raytris, tri_orig, E, mA, mB, nullptr, ts)
+                                    : bvh_segment<false>(bvh, raytris, tri_orig, mA, mB, nullptr, ts);
+            hits[(uint64_t)li * num_samples + s] = hit;
+            ++segs;
+        }
     }
     count_add(counters, CNT_AO_SEGMENTS, segs);
     count_add(counters, CNT_RAY_NODE_VISITS, ts.nodes);
     count_add(counters, CNT_RAY_TRI_TESTS, ts.tris);
+    count_add(counters, CNT_RAY_ENTRY_TESTS, ts.entries);
 }
 
 __global__ void ao_apply_kernel(const float *__restrict__ hits, uint64_t sh_begin, uint32_t n_local, ltrgpu_Params P, float4 *__restrict__ lrgb)
@@ -98,12 +127,17 @@ extern "C" int ltrgpu_ambient_occlusion(ltrgpu_Ctx *ctx, const float *randoff_ho
     if (dev_alloc(ctx, &d_hits, (size_t)n_local * (ns > 0 ? ns : 1))) return 1;
     CU_TRY(ctx, cudaEventRecord(ctx->ev0, st));
     if (ns > 0) {
-        const uint64_t total = (uint64_t)((n_local + 31u) / 32u) * 32ull * ns;
-        uint64_t want = (total + LB_BLOCK - 1) / LB_BLOCK;
+        const uint64_t n_groups = (n_local + 31u) / 32u;                 /* one warp per group of 32 lumels at a time */
+        uint64_t want = (n_groups + LB_BLOCK / 32 - 1) / (LB_BLOCK / 32);
         unsigned cap = (unsigned)ctx->num_sms * 64;
         unsigned blocks = want > cap ? cap : (unsigned)want;
-        ao_trace_kernel<<<blocks, LB_BLOCK, 0, st>>>(ctx->d_bvh, ctx->d_raytris, ctx->d_tri_orig, ctx->d_lpos, ctx->d_lnrm, d_rand, ctx->d_ao_cos,
-                                                     ctx->d_ao_sin, ctx->sh_begin, n_local, ns, ctx->params.ao_distance, d_hits, ctx->d_counters);
+        const char *e = getenv("LTR_AO_ENTRY");                           /* A/B switch: 0 = every segment starts at the root */
+        if (!e || atoi(e) != 0)
+            ao_trace_kernel<true><<<blocks, LB_BLOCK, 0, st>>>(ctx->d_bvh, ctx->d_raytris, ctx->d_tri_orig, ctx->d_lpos, ctx->d_lnrm, d_rand, ctx->d_ao_cos,
+                                                               ctx->d_ao_sin, ctx->sh_begin, n_local, ns, ctx->params.ao_distance, d_hits, ctx->d_counters);
+        else
+            ao_trace_kernel<false><<<blocks, LB_BLOCK, 0, st>>>(ctx->d_bvh, ctx->d_raytris, ctx->d_tri_orig, ctx->d_lpos, ctx->d_lnrm, d_rand, ctx->d_ao_cos,
+                                                                ctx->d_ao_sin, ctx->sh_begin, n_local, ns, ctx->params.ao_distance, d_hits, ctx->d_counters);
         CU_LAUNCH_CHECK(ctx);
     }
     ao_apply_kernel<<<grid_for(n_local, 256), 256, 0, st>>>(d_hits, ctx->sh_begin, n_local, ctx->params, ctx->d_lrgb);

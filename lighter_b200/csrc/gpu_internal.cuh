@@ -302,19 +302,22 @@ __device__ __forceinline__ void load_raytri(const RayTri *src, RayTri &T)
  * The caller shortens the segment (SMALL_FLOAT at both ends) exactly as the reference does.
  */
 template <bool ANY>
-__device__ __forceinline__ float bvh_segment(const BvhNode *__restrict__ nodes, const RayTri *__restrict__ tris,
-                                             const uint32_t *__restrict__ tri_orig, V3 l1, V3 l2, int *hit_slot, TravStats &ts)
+__device__ __forceinline__ float bvh_segment_core(const BvhNode *__restrict__ nodes, const RayTri *__restrict__ tris, const uint32_t *__restrict__ tri_orig,
+                                                  const SegRay &r, int (&stack_n)[BVH_STACK], float (&stack_t)[BVH_STACK], int sp, int node,
+                                                  int *hit_slot, TravStats &ts)
 {
-    int stack_n[BVH_STACK];
-    float stack_t[BVH_STACK];
-    int sp = 0;
-    SegRay r = make_seg(l1, l2);
     float best = LB_NO_HIT;
     float tmax = 1.0f;
     int best_slot = -1;
     unsigned best_orig = 0xffffffffu;
-    int node = 0;
     for (;;) {
+        if (node < 0) {                                      /* next postponed node that can still hold a closer hit */
+            for (;;) {
+                if (sp == 0) { if (hit_slot) *hit_slot = best_slot; return best; }
+                --sp;
+                if (stack_t[sp] <= tmax) { node = stack_n[sp]; break; }
+            }
+        }
         const float4 *n4 = reinterpret_cast<const float4 *>(nodes + node);
         float4 a = __ldg(n4), b = __ldg(n4 + 1), c = __ldg(n4 + 2);
         int4 k = __ldg(reinterpret_cast<const int4 *>(n4 + 3));
@@ -353,13 +356,38 @@ __device__ __forceinline__ float bvh_segment(const BvhNode *__restrict__ nodes, 
                 stack_n[sp] = cc; stack_t[sp] = ee; ++sp;
             }
         }
-        if (next >= 0) { node = next; continue; }
-        for (;;) {
-            if (sp == 0) { if (hit_slot) *hit_slot = best_slot; return best; }
-            --sp;
-            if (stack_t[sp] <= tmax) { node = stack_n[sp]; break; }
-        }
+        node = next;
     }
+}
+
+template <bool ANY>
+__device__ __forceinline__ float bvh_segment(const BvhNode *__restrict__ nodes, const RayTri *__restrict__ tris,
+                                             const uint32_t *__restrict__ tri_orig, V3 l1, V3 l2, int *hit_slot, TravStats &ts)
+{
+    int stack_n[BVH_STACK];
+    float stack_t[BVH_STACK];
+    const SegRay r = make_seg(l1, l2);
+    return bvh_segment_core<ANY>(nodes, tris, tri_orig, r, stack_n, stack_t, 0, 0, hit_slot, ts);
+}
+
+/* The same query started from the entry set of the segment's bundle (bvh_entry.h, searched on the BINARY tree): entry
+ * boxes the segment misses are skipped, the others are walked nearest-box-last-pushed; the result does not depend on the
+ * order (closest hit, ties -> lowest original triangle index). */
+template <bool ANY>
+__device__ __forceinline__ float bvh_segment_entries(const BvhNode *__restrict__ nodes, const RayTri *__restrict__ tris, const uint32_t *__restrict__ tri_orig,
+                                                     const BvhEntrySet &E, V3 l1, V3 l2, int *hit_slot, TravStats &ts)
+{
+    int stack_n[BVH_STACK];
+    float stack_t[BVH_STACK];
+    int sp = 0;
+    const SegRay r = make_seg(l1, l2);
+    const int n = E.n;
+    for (int i = 0; i < n; ++i) {
+        const float e = seg_box(r, E.lox[i], E.loy[i], E.loz[i], E.hix[i], E.hiy[i], E.hiz[i], 1.0f);
+        if (e <= 1.0f) { stack_n[sp] = E.node[i]; stack_t[sp] = e; ++sp; }
+    }
+    ts.entries += (unsigned)n;
+    return bvh_segment_core<ANY>(nodes, tris, tri_orig, r, stack_n, stack_t, sp, -1, hit_slot, ts);
 }
 
 /*
