@@ -63,12 +63,8 @@ ao_trace_kernel(const BvhNode *__restrict__ bvh, const RayTri *__restrict__ rayt
                 lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)); ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o)); lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o));
                 hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o)); hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
             }
-            __syncwarp();                             /* every lane is done with the previous group's set */
-            if (lane == 0) {
-                bvh_entry_pad(lx, ly, lz, hx, hy, hz);
-                bvh2_entry_search(bvh, lx, ly, lz, hx, hy, hz, E);
-            }
-            __syncwarp();
+            bvh_entry_pad(lx, ly, lz, hx, hy, hz);
+            bvh_entry_search_warp<Bvh2Access>(bvh, lx, ly, lz, hx, hy, hz, E, lane);   /* syncs the warp before it overwrites the previous group's set */
         }
         if (!valid) continue;                         /* no warp-wide operation below */
         for (int s = 0; s < num_samples; ++s) {

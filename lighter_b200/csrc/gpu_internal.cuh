@@ -463,6 +463,10 @@ template <int FLUSH>
 __device__ __forceinline__ bool bvh4_anyhit_core(const Bvh4Node *__restrict__ nodes, const RayTri *__restrict__ tris, const V3 l1, const V3 d,
                                                  const float ix, const float iy, const float iz, int (&stack_n)[BVH_STACK], int sp, int node, TravStats &ts)
 {
+    /* Measured and NOT adopted (B200, config 4): picking the near / far plane of every slab by the sign of the direction
+     * (bit-identical to min/max, 4 three-way min/max per child instead of 10 two-way) needs a separate address per
+     * float4 of the node; the extra pointers cost 16-24 registers and the kernel is more sensitive to occupancy than to
+     * those instructions: 265 ms vs 236 ms for this form at 56 registers. */
     constexpr int TQ = FLUSH + 28;                   /* FLUSH - 1 pending + four leaves of up to 7 triangles */
     int tq[TQ];
     int nq = 0;
@@ -537,6 +541,80 @@ __device__ __forceinline__ bool bvh4_anyhit_entries(const Bvh4Node *__restrict__
     if (sp == 0) return false;
     const int node = stack_n[--sp];
     return bvh4_anyhit_core<FLUSH>(nodes, tris, l1, d, ix, iy, iz, stack_n, sp, node, ts);
+}
+
+/*
+ * Warp-cooperative form of bvh_entry_search_t (bvh_entry.h): the same frontier, the same picks and the same slot
+ * assignment -- hence the same entry set as the scalar host model -- but entry i lives in the registers of lane i and the
+ * children of the picked node are tested one per lane, so an iteration is a few dozen warp instructions instead of a
+ * one-lane loop (ncu on the scalar version: 10 % of the visibility kernel's time went into lane 0's search).
+ * All 32 lanes must call it; the bundle box must already be padded and identical on every lane.  The result is written
+ * to E (shared memory) and is visible to the warp on return.
+ */
+template <class A>
+__device__ __forceinline__ void bvh_entry_search_warp(const typename A::Node *__restrict__ nodes, float qlx, float qly, float qlz, float qhx, float qhy, float qhz,
+                                                      BvhEntrySet &E, const unsigned lane)
+{
+    const unsigned FULL = 0xffffffffu;
+    int e_node = 0;
+    float e_lx = -INFINITY, e_ly = -INFINITY, e_lz = -INFINITY, e_hx = INFINITY, e_hy = INFINITY, e_hz = INFINITY;
+    bool e_fin = false;
+    int n = 1;
+    for (int it = 0; it < 64; ++it) {
+        /* pick: the first non-final entry of largest extent */
+        float key = ((int)lane < n && !e_fin) ? (e_hx - e_lx) + (e_hy - e_ly) + (e_hz - e_lz) : -1.f;
+        int who = (int)lane;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {                /* entries live in lanes 0..7 */
+            const float k2 = __shfl_xor_sync(FULL, key, o);
+            const int w2 = __shfl_xor_sync(FULL, who, o);
+            if (k2 > key || (k2 == key && w2 < who)) { key = k2; who = w2; }
+        }
+        key = __shfl_sync(FULL, key, 0); who = __shfl_sync(FULL, who, 0);
+        if (!(key >= 0.f)) break;
+        const int pick = who;
+        const int pnode = __shfl_sync(FULL, e_node, pick);
+        /* children of the picked node, one per lane */
+        const int c = (int)(lane % (unsigned)A::W);
+        const typename A::Node &N = nodes[pnode];
+        const int code = A::code(N, c);
+        float lx, ly, lz, hx, hy, hz;
+        A::box(N, c, lx, ly, lz, hx, hy, hz);
+        const bool in = lane < (unsigned)A::W && !A::empty(code) && lx <= qhx && hx >= qlx && ly <= qhy && hy >= qly && lz <= qhz && hz >= qlz;
+        const unsigned hm = __ballot_sync(FULL, in);
+        const unsigned leafm = __ballot_sync(FULL, in && code < 0);
+        const int nh = __popc(hm);
+        if (leafm || n - 1 + nh > BVH_ENTRY_MAX) { if ((int)lane == pick) e_fin = true; continue; }
+        if (nh == 0) {                                   /* drop the entry: the last one takes its slot */
+            const int last = n - 1;
+            const int t_node = __shfl_sync(FULL, e_node, last);
+            const float t_lx = __shfl_sync(FULL, e_lx, last), t_ly = __shfl_sync(FULL, e_ly, last), t_lz = __shfl_sync(FULL, e_lz, last);
+            const float t_hx = __shfl_sync(FULL, e_hx, last), t_hy = __shfl_sync(FULL, e_hy, last), t_hz = __shfl_sync(FULL, e_hz, last);
+            const int t_fin = __shfl_sync(FULL, (int)e_fin, last);
+            if ((int)lane == pick && pick != last) { e_node = t_node; e_lx = t_lx; e_ly = t_ly; e_lz = t_lz; e_hx = t_hx; e_hy = t_hy; e_hz = t_hz; e_fin = t_fin != 0; }
+            if ((int)lane == last) e_fin = false;
+            n = last;
+            continue;
+        }
+        /* the k-th child in range goes to slot pick (k = 0) or n + k - 1; seen from the destination lane: */
+        int k = -1;
+        if ((int)lane == pick) k = 0;
+        else if ((int)lane >= n && (int)lane < n + nh - 1) k = (int)lane - n + 1;
+        const int src = k >= 0 ? (int)__fns(hm, 0, k + 1) : 0;
+        const int t_node = __shfl_sync(FULL, code, src);
+        const float t_lx = __shfl_sync(FULL, lx, src), t_ly = __shfl_sync(FULL, ly, src), t_lz = __shfl_sync(FULL, lz, src);
+        const float t_hx = __shfl_sync(FULL, hx, src), t_hy = __shfl_sync(FULL, hy, src), t_hz = __shfl_sync(FULL, hz, src);
+        if (k >= 0) { e_node = t_node; e_lx = t_lx; e_ly = t_ly; e_lz = t_lz; e_hx = t_hx; e_hy = t_hy; e_hz = t_hz; e_fin = false; }
+        n += nh - 1;
+    }
+    __syncwarp();
+    if ((int)lane < n) {
+        E.node[lane] = e_node;
+        E.lox[lane] = e_lx; E.loy[lane] = e_ly; E.loz[lane] = e_lz;
+        E.hix[lane] = e_hx; E.hiy[lane] = e_hy; E.hiz[lane] = e_hz;
+    }
+    if (lane == 0) E.n = n;
+    __syncwarp();
 }
 
 /* warp-aggregated counter add */

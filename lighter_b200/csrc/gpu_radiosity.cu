@@ -491,8 +491,11 @@ template <int G> static size_t rad_sweep_smem() { return sizeof(RadColBuf<G>) * 
  * the whole chunk (bvh_entry.h) and leaves the entry set in shared memory; the 1024 segments then start at the entry set
  * instead of the root.  ENTRY = false is the plain walk from the root (kept for A/B measurement: LTR_RAD_ENTRY=0).
  */
+#ifndef LB_VIS_MINBLOCKS
+#define LB_VIS_MINBLOCKS 9      /* 56 registers: measured optimum on B200 (48 regs: +2 %, 40: +10 %, 72-80 uncapped: +12 %) */
+#endif
 template <bool ENTRY>
-__global__ void __launch_bounds__(LB_BLOCK)
+__global__ void __launch_bounds__(LB_BLOCK, LB_VIS_MINBLOCKS)
 rad_visibility_kernel(const Bvh4Node *__restrict__ bvh, const RayTri *__restrict__ raytris, const float4 *__restrict__ spos,
                       const uint32_t *__restrict__ sidx, const RadCand *__restrict__ cand, unsigned long long n_cand,
                       uint32_t my_k0, uint32_t my_k1, unsigned long long *__restrict__ keys, float *__restrict__ factors,
@@ -513,14 +516,23 @@ rad_visibility_kernel(const Bvh4Node *__restrict__ bvh, const RayTri *__restrict
         const unsigned long long e0 = (unsigned long long)ch * RAD_CHUNK;
         if (ENTRY) {
             float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
-            for (unsigned i = 0; i < RAD_CHUNK; i += 32u) {
-                const unsigned long long e = e0 + i + lane;
-                if (e >= n_cand) break;
-                const RadCand c = cand[e];
-                if (c.a == RAD_PAD) continue;
-                const float4 A = spos[c.a], B = spos[c.b];
-                lx = fminf(lx, fminf(A.x, B.x)); ly = fminf(ly, fminf(A.y, B.y)); lz = fminf(lz, fminf(A.z, B.z));
-                hx = fmaxf(hx, fmaxf(A.x, B.x)); hy = fmaxf(hy, fmaxf(A.y, B.y)); hz = fmaxf(hz, fmaxf(A.z, B.z));
+            for (unsigned i = 0; i < RAD_CHUNK; i += 128u) {          /* four independent candidate -> position load chains in flight */
+                RadCand c4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned long long e = e0 + i + 32u * u + lane;
+                    c4[u].a = RAD_PAD;
+                    if (e < n_cand) c4[u] = cand[e];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const bool used = c4[u].a != RAD_PAD;
+                    const float4 A = spos[used ? c4[u].a : 0u], B = spos[used ? c4[u].b : 0u];
+                    if (used) {
+                        lx = fminf(lx, fminf(A.x, B.x)); ly = fminf(ly, fminf(A.y, B.y)); lz = fminf(lz, fminf(A.z, B.z));
+                        hx = fmaxf(hx, fmaxf(A.x, B.x)); hy = fmaxf(hy, fmaxf(A.y, B.y)); hz = fmaxf(hz, fmaxf(A.z, B.z));
+                    }
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -528,20 +540,32 @@ rad_visibility_kernel(const Bvh4Node *__restrict__ bvh, const RayTri *__restrict
                 hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o)); hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
             }
             if (!(lx <= hx)) continue;                /* warp-uniform: the chunk holds only unused slots */
-            __syncwarp();                             /* every lane is done with the previous chunk's set */
-            if (lane == 0) {
-                bvh_entry_pad(lx, ly, lz, hx, hy, hz);
-                bvh4_entry_search(bvh, lx, ly, lz, hx, hy, hz, E);
-            }
-            __syncwarp();
+            bvh_entry_pad(lx, ly, lz, hx, hy, hz);
+            bvh_entry_search_warp<Bvh4Access>(bvh, lx, ly, lz, hx, hy, hz, E, lane);   /* syncs the warp before it overwrites the previous chunk's set */
         }
+        /* software pipeline over the chunk's 32 batches: the candidate records are loaded two batches ahead, the lumels of
+         * the next batch's candidates are prefetched into L1 while this batch is traced (ncu: a fifth of the kernel's stall
+         * samples sat on the candidate -> position load chain) */
+        RadCand cn1 = { RAD_PAD, 0, 0.f }, cn2 = { RAD_PAD, 0, 0.f };
+        if (e0 + lane < n_cand) cn1 = cand[e0 + lane];
+        if (e0 + 32u + lane < n_cand) cn2 = cand[e0 + 32u + lane];
         for (unsigned i = 0; i < RAD_CHUNK; i += 32u) {
-            const unsigned long long e = e0 + i + lane;
             if (e0 + i >= n_cand) break;              /* warp-uniform */
             unsigned emit = 0;                        /* bit 0: link for row a (always mine), bit 1: row b is mine too, bit 2: row b lives on another rank */
-            RadCand c = { RAD_PAD, 0, 0.f };
+            const RadCand c = cn1;
             uint32_t oa = 0, ob = 0;
-            if (e < n_cand) c = cand[e];
+            cn1 = cn2;
+            {
+                const unsigned long long e2 = e0 + i + 64u + lane;
+                cn2.a = RAD_PAD;
+                if (i + 64u < RAD_CHUNK && e2 < n_cand) cn2 = cand[e2];
+            }
+            if (cn1.a != RAD_PAD) {
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(spos + cn1.a));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(spos + cn1.b));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(sidx + cn1.a));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(sidx + cn1.b));
+            }
             if (!__any_sync(0xffffffffu, c.a != RAD_PAD)) continue;
             if (c.a != RAD_PAD) {                     /* RAD_PAD: unused slot of a warp's output chunk */
                 oa = sidx[c.a]; ob = sidx[c.b];

@@ -46,7 +46,7 @@ __global__ void t_segtri_kernel(const float *a, const float *b, const float *tri
 __global__ void t_queries_kernel(const BvhNode *bvh, const Bvh4Node *bvh4, const PreparedTri *pt, const RayTri *rt, const uint32_t *orig, const float *a, const float *b,
                                  uint32_t n, float *dist, int *anyhit, float *closest, int *closest_tri)
 {
-    __shared__ BvhEntrySet s_entry[4];               /* launched with 128 threads */
+    __shared__ BvhEntrySet s_entry[4], s_entry1[4];  /* launched with 128 threads */
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
     const uint32_t q = valid ? i : 0;                /* idle lanes of the last warp stay for the warp-wide reduction below */
@@ -60,18 +60,19 @@ __global__ void t_queries_kernel(const BvhNode *bvh, const Bvh4Node *bvh4, const
             lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)); ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o)); lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o));
             hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o)); hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
         }
-        BvhEntrySet &E = s_entry[threadIdx.x >> 5];
-        if ((threadIdx.x & 31u) == 0) {
-            bvh_entry_pad(lx, ly, lz, hx, hy, hz);
-            bvh4_entry_search(bvh4, lx, ly, lz, hx, hy, hz, E);
-        }
-        __syncwarp();
+        BvhEntrySet &E = s_entry[threadIdx.x >> 5], &E1 = s_entry1[threadIdx.x >> 5];
+        bvh_entry_pad(lx, ly, lz, hx, hy, hz);
+        if ((threadIdx.x & 31u) == 0) bvh4_entry_search(bvh4, lx, ly, lz, hx, hy, hz, E1);       /* the scalar model (also run on the host) */
+        bvh_entry_search_warp<Bvh4Access>(bvh4, lx, ly, lz, hx, hy, hz, E, threadIdx.x & 31u);   /* the form the kernels use */
+        bool same = E.n == E1.n;
+        for (int e = 0; same && e < E.n; ++e)
+            same = E.node[e] == E1.node[e] && E.lox[e] == E1.lox[e] && E.loy[e] == E1.loy[e] && E.loz[e] == E1.loz[e] && E.hix[e] == E1.hix[e] && E.hiy[e] == E1.hiy[e] && E.hiz[e] == E1.hiz[e];
         /* four implementations of the same predicate: ordered segment walk, two-phase binary walk, two-phase 4-wide walk
          * from the root and from the bundle's entry set (the one the radiosity kernel uses); a disagreement is reported as 2 + bits */
         const int h0 = bvh_segment<true>(bvh, rt, orig, A, B, nullptr, ts) < 1.0f ? 1 : 0;
         const int h1 = bvh_anyhit(bvh, rt, A, B, ts) ? 1 : 0, h2 = bvh4_anyhit(bvh4, rt, A, B, ts) ? 1 : 0, h3 = bvh4_anyhit<2>(bvh4, rt, A, B, ts) ? 1 : 0;
         const int h4 = bvh4_anyhit_entries(bvh4, rt, E, A, B, ts) ? 1 : 0;
-        if (valid) anyhit[i] = (h0 == h1 && h1 == h2 && h2 == h3 && h3 == h4) ? h0 : 2 + h0 + 2 * h1 + 4 * h2 + 8 * h3 + 16 * h4;
+        if (valid) anyhit[i] = (h0 == h1 && h1 == h2 && h2 == h3 && h3 == h4 && same) ? h0 : 2 + h0 + 2 * h1 + 4 * h2 + 8 * h3 + 16 * h4 + (same ? 0 : 32);
     }
     if (closest && valid) {
         int slot = -1;
