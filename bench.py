@@ -231,12 +231,14 @@ def main():
     roofs = {
         "rad_visibility_kernel": roof(
             "rad_visibility_kernel",
-            (stats["n_ray_node_visits"] * 64.0 + stats["n_ray_tri_tests"] * 64.0) * rad_share + stats["n_rad_segments"] * (12.0 + 32.0),
+            (stats["n_ray_node_visits"] * 64.0 + stats["n_ray_tri_tests"] * 64.0 + stats.get("n_ray_entry_tests", 0) * 28.0) * rad_share
+            + stats["n_rad_segments"] * (12.0 + 32.0),
             stats["gpu_ms_rad_vis"], batches,
-            "any-hit segment traversal of the radiosity candidates: 64 B/node visit + 64 B/triangle test (the node/triangle counters are shared "
-            "with the AO pass and apportioned by segment count) + 12 B candidate + 32 B endpoints per segment; the bytes are served by L1/L2 "
-            "(the scene is cache resident, ncu: DRAM traffic is ~1 % of them), so this is CACHE bandwidth and the fraction of the HBM peak can "
-            "exceed 1; the kernel is instruction-issue bound (ncu: IPC 3.1 of 4, 23 of 32 lanes active)",
+            "any-hit segment traversal of the radiosity candidates, started at the entry set of each 1024-candidate chunk: 64 B/node visit + "
+            "64 B/triangle test + 28 B/entry box (the counters are shared with the AO pass and apportioned by segment count) + 12 B candidate + "
+            "32 B endpoints per segment; the bytes are served by L1/L2 (the scene is cache resident, ncu: DRAM traffic is a few % of them), so "
+            "this is CACHE bandwidth and the fraction of the HBM peak can exceed 1; ncu: issue slots 81 % busy, L1 data-pipe wavefronts 76 % of "
+            "peak, 24 of 32 lanes active -- the kernel is co-limited by instruction issue and L1 wavefronts, not by HBM",
             {"segments_per_s": stats["n_rad_segments"] / (stats["gpu_ms_rad_vis"] * 1e-3) if stats["gpu_ms_rad_vis"] else None}),
         "rad_candidates_kernel": roof(
             "rad_candidates_kernel",
@@ -281,7 +283,7 @@ def main():
         "rays_per_step": rays_step,
         "stage_ms": stage_ms,
         "counters": {k: int(stats[k]) for k in ("n_marches", "n_distance_queries", "n_ao_segments", "n_rad_pairs", "n_rad_segments", "n_rad_links",
-                                                 "n_node_visits", "n_tri_tests", "n_ray_node_visits", "n_ray_tri_tests", "n_rad_tile_loads", "n_rad_batches")},
+                                                 "n_node_visits", "n_tri_tests", "n_ray_node_visits", "n_ray_tri_tests", "n_ray_entry_tests", "n_rad_tile_loads", "n_rad_batches")},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": int(e2e_stats["h2d_bytes"]), "d2h_bytes_per_step": int(e2e_stats["d2h_bytes"]),
                 "bake_wall_s": sum(e2e_walls) / len(e2e_walls), "steps": len(e2e_walls),

@@ -41,6 +41,7 @@ struct Prim { Box3 b; uint32_t id; };
 inline V3 centroid(const Prim &p) { return (p.b.lo + p.b.hi) * 0.5f; }
 
 const int NB = 16;                                /* SAH bins per axis */
+const uint32_t FINE_MIN = 4096;                   /* unit of the dynamically scheduled part of the build */
 const uint32_t COOP_MIN = 65536;                  /* nodes above this size are built by all threads together */
 
 struct Bounds { Box3 bb, cb; };
@@ -196,6 +197,16 @@ struct Builder {
         tmp[w.node].height = 1 + std::max(tmp[l.node].height, tmp[r.node].height);
     }
 
+    /* serial splits down to FINE_MIN triangles; the nodes at that size are left for phase B2 */
+    void expand(const Work &w, std::vector<Work> &out)
+    {
+        if (w.count <= FINE_MIN) { out.push_back(w); return; }
+        Work l, r;
+        if (!split(w, false, l, r)) return;
+        expand(l, out);
+        expand(r, out);
+    }
+
     /* sub-tree sizes of the nodes built cooperatively (their descendants built in phase B are known) */
     void finish_sizes(int32_t t)
     {
@@ -210,6 +221,7 @@ struct Builder {
     void run(uint32_t count)
     {
         Work root = { alloc(), 0, count, 0 };
+        const double t_0 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
         /* phase A: the few nodes big enough to be worth every thread, one after the other */
         std::vector<Work> big{ root }, small;
         while (!big.empty()) {
@@ -218,7 +230,28 @@ struct Builder {
             Work l, r;
             if (split(w, true, l, r)) { big.push_back(l); big.push_back(r); }
         }
-        /* phase B: independent sub-trees, largest first, pulled by the threads from a shared cursor */
+        /* phase B1: every medium sub-tree (<= COOP_MIN triangles; only ~16 of them at 1 M triangles -- one per thread of a
+         * 16-core host, i.e. no slack for their uneven sizes) is split further by ONE thread down to FINE_MIN triangles;
+         * phase B2: the resulting few hundred small sub-trees, largest first, are pulled from a shared cursor.  The tree is
+         * the same as before: split() does not depend on who calls it. */
+        const bool trace_b = getenv("LTR_TRACE_BVH") != nullptr;
+        if (trace_b) fprintf(stderr, "[bvh] phase A %.1f ms: %zu sub-trees\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() - t_0, small.size());
+        auto tnow = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t_a = tnow();
+        std::vector<Work> fine;
+        {
+            std::vector<std::vector<Work>> part(small.size());
+            std::atomic<size_t> cursor{0};
+            auto worker = [&]() { for (size_t i; (i = cursor.fetch_add(1)) < small.size();) expand(small[i], part[i]); };
+            std::vector<std::thread> pool;
+            const int T = (int)std::min<size_t>((size_t)std::max(1, threads), small.size());
+            for (int t = 1; t < T; ++t) pool.emplace_back(worker);
+            worker();
+            for (auto &th : pool) th.join();
+            for (auto &v : part) fine.insert(fine.end(), v.begin(), v.end());
+        }
+        small.swap(fine);
+        if (trace_b) fprintf(stderr, "[bvh] phase B1 %.1f ms: %zu sub-trees\n", tnow() - t_a, small.size());
         std::sort(small.begin(), small.end(), [](const Work &a, const Work &b) { return a.count != b.count ? a.count > b.count : a.first < b.first; });
         std::atomic<size_t> cursor{0};
         auto worker = [&]() { for (size_t i; (i = cursor.fetch_add(1)) < small.size();) build_serial(small[i]); };

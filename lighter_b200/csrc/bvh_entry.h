@@ -20,7 +20,9 @@
 #pragma once
 #include "bvh.h"
 
-#define BVH_ENTRY_MAX 8
+#ifndef BVH_ENTRY_MAX
+#define BVH_ENTRY_MAX 8       /* warp-cooperative search: entry i lives in lane i of an 8-lane group, so <= 8 */
+#endif
 
 struct BvhEntrySet {
     int n;

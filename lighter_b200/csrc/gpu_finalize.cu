@@ -94,6 +94,68 @@ __global__ void dilate_kernel(ImgTable tab, uint64_t n_texels, float *__restrict
     }
 }
 
+/*
+ * Separable gaussian blur as ONE shared-memory-tiled kernel (north_star item 5).  The reference runs Convolve_Transpose
+ * twice through a transposed intermediate image (lighter_math.cpp:367-398); here a CTA stages a (32+2e) x (32+2e) source
+ * tile with clamped coordinates (coalesced row segments), runs the horizontal pass into a second shared array, the
+ * vertical pass out of it, and writes 32 x 32 texels as coalesced rows -- the intermediate never touches HBM and no
+ * access is strided.  Per texel: 12 B read (+ halo) and 12 B written instead of 48 B with two strided passes.
+ * Arithmetic is the reference's: per pass, taps accumulated from -ext to +ext, multiply then add, intermediate rounded
+ * to float; clamp-to-edge per instance image.  Tiles of all instance images are enumerated back to back (tile_off).
+ */
+#define BLUR_T 32
+#define BLUR_MAX_EXT 8
+__global__ void __launch_bounds__(256)
+blur_tiled_kernel(ImgTable tab, const uint32_t *__restrict__ tile_off, const float *__restrict__ src, float *__restrict__ dst,
+                  const float *__restrict__ kern, int ext)
+{
+    extern __shared__ float blur_smem[];
+    const int S = BLUR_T + 2 * ext;
+    float *tile = blur_smem;                         /* [S rows][S][3] */
+    float *tmp = blur_smem + (size_t)S * S * 3;      /* [S rows][BLUR_T][3] horizontal pass */
+    /* which image, which tile */
+    uint32_t lo = 0, hi = tab.n_img;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (tile_off[mid] <= blockIdx.x) lo = mid; else hi = mid; }
+    const uint32_t im = lo;
+    const int w = (int)tab.w[im], h = (int)tab.h[im];
+    const uint64_t base = tab.off[im];
+    const uint32_t lt = blockIdx.x - tile_off[im], tiles_x = (uint32_t)(w + BLUR_T - 1) / BLUR_T;
+    const int x0 = (int)(lt % tiles_x) * BLUR_T, y0 = (int)(lt / tiles_x) * BLUR_T;
+    for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
+        const int sx = i % S, sy = i / S;
+        int gx = x0 - ext + sx, gy = y0 - ext + sy;
+        gx = gx < 0 ? 0 : (gx >= w ? w - 1 : gx);
+        gy = gy < 0 ? 0 : (gy >= h ? h - 1 : gy);
+        const float *p = src + (base + (uint64_t)gy * w + gx) * 3;
+        tile[i * 3] = p[0]; tile[i * 3 + 1] = p[1]; tile[i * 3 + 2] = p[2];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < S * BLUR_T; i += blockDim.x) {
+        const int ox = i % BLUR_T, sy = i / BLUR_T;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        const float *row = tile + ((size_t)sy * S + ox) * 3;
+        for (int k = 0; k <= 2 * ext; ++k) {
+            const float kv = kern[k];
+            s0 += row[k * 3] * kv; s1 += row[k * 3 + 1] * kv; s2 += row[k * 3 + 2] * kv;
+        }
+        tmp[i * 3] = s0; tmp[i * 3 + 1] = s1; tmp[i * 3 + 2] = s2;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < BLUR_T * BLUR_T; i += blockDim.x) {
+        const int ox = i % BLUR_T, oy = i / BLUR_T;
+        const int x = x0 + ox, y = y0 + oy;
+        if (x >= w || y >= h) continue;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        for (int k = 0; k <= 2 * ext; ++k) {
+            const float kv = kern[k];
+            const float *q = tmp + ((size_t)(oy + k) * BLUR_T + ox) * 3;
+            s0 += q[0] * kv; s1 += q[1] * kv; s2 += q[2] * kv;
+        }
+        float *o = dst + (base + (uint64_t)y * w + x) * 3;
+        o[0] = s0; o[1] = s1; o[2] = s2;
+    }
+}
+
 /* horizontal pass: dst is the transposed image (x-major), as the reference's first Convolve_Transpose */
 __global__ void blur_h_kernel(ImgTable tab, uint64_t n_texels, const float *__restrict__ src, float *__restrict__ dst,
                               const float *__restrict__ kern, int ext)
@@ -203,7 +265,7 @@ extern "C" int ltrgpu_finalize(ltrgpu_Ctx *ctx)
     }
     h_off[ni] = acc; ctx->h_out_off[ni] = oacc;
     uint64_t *d_off = nullptr, *d_ooff = nullptr;
-    uint32_t *d_w = nullptr, *d_h = nullptr, *d_ow = nullptr, *d_oh = nullptr;
+    uint32_t *d_w = nullptr, *d_h = nullptr, *d_ow = nullptr, *d_oh = nullptr, *d_toff = nullptr;
     int rc = 0;
     rc |= dev_upload(ctx, &d_off, h_off, ni + 1); rc |= dev_upload(ctx, &d_w, h_w, ni); rc |= dev_upload(ctx, &d_h, h_h, ni);
     rc |= dev_upload(ctx, &d_ooff, ctx->h_out_off, ni + 1); rc |= dev_upload(ctx, &d_ow, ctx->h_out_w, ni); rc |= dev_upload(ctx, &d_oh, ctx->h_out_h, ni);
@@ -234,10 +296,32 @@ extern "C" int ltrgpu_finalize(ltrgpu_Ctx *ctx)
             unsigned char *t = m_in; m_in = m_out; m_out = t;
         }
         if (ctx->params.blur_size && ctx->d_blur_kernel) {
-            blur_h_kernel<<<grid_for(nt, 256), 256, 0, st>>>(tab, nt, img, ctx->d_image_tmp, ctx->d_blur_kernel, ctx->blur_ext);
-            CU_LAUNCH_CHECK(ctx);
-            blur_v_kernel<<<grid_for(nt, 256), 256, 0, st>>>(tab, nt, ctx->d_image_tmp, img, ctx->d_blur_kernel, ctx->blur_ext);
-            CU_LAUNCH_CHECK(ctx);
+            if (ctx->blur_ext <= BLUR_MAX_EXT && !getenv("LTR_BLUR_TWO_PASS")) {
+                /* tiles of every image, back to back */
+                uint32_t *h_toff = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)ni + 1));
+                uint32_t tacc = 0;
+                for (uint32_t i = 0; i < ni; ++i) {
+                    h_toff[i] = tacc;
+                    tacc += ((ctx->h_inst[i].lm_w + BLUR_T - 1) / BLUR_T) * ((ctx->h_inst[i].lm_h + BLUR_T - 1) / BLUR_T);
+                }
+                h_toff[ni] = tacc;
+                const int up = dev_upload(ctx, &d_toff, h_toff, (size_t)ni + 1);
+                free(h_toff);
+                if (up) return 1;
+                const int S = BLUR_T + 2 * ctx->blur_ext;
+                const size_t smem = ((size_t)S * S + (size_t)S * BLUR_T) * 3 * sizeof(float);
+                if (tacc) {
+                    blur_tiled_kernel<<<tacc, 256, smem, st>>>(tab, d_toff, img, ctx->d_image_tmp, ctx->d_blur_kernel, ctx->blur_ext);
+                    CU_LAUNCH_CHECK(ctx);
+                }
+                float *t = ctx->d_image; ctx->d_image = ctx->d_image_tmp; ctx->d_image_tmp = t;
+                img = ctx->d_image;
+            } else {                                     /* very wide kernels: two passes through a transposed intermediate */
+                blur_h_kernel<<<grid_for(nt, 256), 256, 0, st>>>(tab, nt, img, ctx->d_image_tmp, ctx->d_blur_kernel, ctx->blur_ext);
+                CU_LAUNCH_CHECK(ctx);
+                blur_v_kernel<<<grid_for(nt, 256), 256, 0, st>>>(tab, nt, ctx->d_image_tmp, img, ctx->d_blur_kernel, ctx->blur_ext);
+                CU_LAUNCH_CHECK(ctx);
+            }
         }
     }
     /* output buffer */
@@ -266,6 +350,7 @@ extern "C" int ltrgpu_finalize(ltrgpu_Ctx *ctx)
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->host_counters.ms_finalize += ms;
     lb_free(d_off); lb_free(d_w); lb_free(d_h); lb_free(d_ooff); lb_free(d_ow); lb_free(d_oh);
+    if (d_toff) lb_free(d_toff);
     return 0;
 }
 

@@ -491,6 +491,9 @@ template <int G> static size_t rad_sweep_smem() { return sizeof(RadColBuf<G>) * 
  * the whole chunk (bvh_entry.h) and leaves the entry set in shared memory; the 1024 segments then start at the entry set
  * instead of the root.  ENTRY = false is the plain walk from the root (kept for A/B measurement: LTR_RAD_ENTRY=0).
  */
+#ifndef LB_VIS_FLUSH
+#define LB_VIS_FLUSH 10
+#endif
 #ifndef LB_VIS_MINBLOCKS
 #define LB_VIS_MINBLOCKS 9      /* 56 registers: measured optimum on B200 (48 regs: +2 %, 40: +10 %, 72-80 uncapped: +12 %) */
 #endif
@@ -574,7 +577,7 @@ rad_visibility_kernel(const Bvh4Node *__restrict__ bvh, const RayTri *__restrict
                 const V3 dn = norm3(B - A);
                 const V3 mA = A + dn * LB_SMALL, mB = B - dn * LB_SMALL;
                 ++segs;
-                const bool blocked = ENTRY ? bvh4_anyhit_entries(bvh, raytris, E, mA, mB, ts) : bvh4_anyhit(bvh, raytris, mA, mB, ts);
+                const bool blocked = ENTRY ? bvh4_anyhit_entries<LB_VIS_FLUSH>(bvh, raytris, E, mA, mB, ts) : bvh4_anyhit<LB_VIS_FLUSH>(bvh, raytris, mA, mB, ts);
                 if (blocked) emit = 1u | ((c.b >= my_k0 && c.b < my_k1) ? 2u : 4u);
             }
             const unsigned cnt = __popc(emit & 3u);

@@ -8,7 +8,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --
     python bench.py --workload $W --steps 1 --warmup 1 --e2e-steps 1 --no-cpu-baseline > gpurun_out/${T}_bench_under_ncu_$W.log 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${T}_launches_step_$W.csv \
     python tools/profile_step.py $W > gpurun_out/${T}_step_$W.log 2>&1
-timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"rad_candidates|rad_visibility|direct_march|lumel_fix|ao_trace" -c 12 \
+timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"rad_candidates|rad_visibility|direct_march|lumel_fix|ao_trace" -c 16 \
     -o gpurun_out/${T}_full_$W python tools/profile_step.py $W > gpurun_out/${T}_full_$W.log 2>&1
 python bench.py --workload $W > gpurun_out/${T}_bench_$W.json 2> gpurun_out/${T}_bench_$W.err
 tail -c 1500 gpurun_out/${T}_bench_$W.json
