@@ -189,6 +189,21 @@ __device__ __forceinline__ bool tile_pair_may_link(const TileBounds &R, const Ti
     return true;
 }
 
+/* can row lumel (P, N) link with any lumel of the group bounded by C?  Conservative, like tile_pair_may_link: the maximum of
+ * the row's linear form N.(c - P) over the group's position box is exact; the group's side uses interval products. */
+__device__ __forceinline__ bool row_group_may_link(const V3 &P, const V3 &N, const TileBounds &C)
+{
+    const float lx = C.plo.x - P.x, hx = C.phi.x - P.x, ly = C.plo.y - P.y, hy = C.phi.y - P.y, lz = C.plo.z - P.z, hz = C.phi.z - P.z;   /* d = c - P per axis */
+    const float gx = fmaxf(fmaxf(lx, -hx), 0.f), gy = fmaxf(fmaxf(ly, -hy), 0.f), gz = fmaxf(fmaxf(lz, -hz), 0.f);
+    const float min_len2 = gx * gx + gy * gy + gz * gz;
+    if (!(min_len2 <= RAD_CUTOFF * RAD_CUTOFF)) return false;
+    const float maxA = fmaxf(N.x * lx, N.x * hx) + fmaxf(N.y * ly, N.y * hy) + fmaxf(N.z * lz, N.z * hz);
+    const float maxB = imax_prod(C.nlo.x, C.nhi.x, -hx, -lx) + imax_prod(C.nlo.y, C.nhi.y, -hy, -ly) + imax_prod(C.nlo.z, C.nhi.z, -hz, -lz);
+    if (maxA < RAD_SKIP_BELOW || maxB < RAD_SKIP_BELOW) return false;
+    if (min_len2 > 0.f && maxA * maxB < RAD_SKIP_BELOW * 3.14159265f * min_len2 * min_len2) return false;
+    return true;
+}
+
 /* ---- mbarrier / bulk-copy (TMA 1-D) primitives: one lane stages a column tile, the warp waits on the barrier ---- */
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
@@ -271,11 +286,15 @@ __device__ __forceinline__ void rad_sweep_tile(const RadColBuf<G> &B, const Tile
     constexpr int CH = G < 8 ? G : 8;                      /* pairs per lane between two drain checks */
     /* warp x group culling, one group per lane */
     unsigned gm = __ballot_sync(0xffffffffu, lane < (unsigned)NG && tile_pair_may_link(Rw, B.gb[lane < (unsigned)NG ? lane : 0]));
-    tested += (unsigned)__popc(gm) * G;                    /* per lane: pairs this lane goes on to test */
     unsigned wcount = 0;                                   /* staged survivors (warp-uniform) */
     while (gm) {
         const unsigned g = (unsigned)__ffs(gm) - 1u;
         gm &= gm - 1u;
+        /* lumel x group: every lane tests ITS row lumel (exact position and normal) against the group's bounds; the group
+         * is swept only if some lane can link.  The warp-level interval test above loses the correlation between a row's
+         * position and its normal; this one keeps it and rejects about half of the groups that pass it (config 4). */
+        if (!__any_sync(0xffffffffu, row_group_may_link(Pr, Nr, B.gb[g]))) continue;
+        tested += G;                                       /* per lane: pairs this lane goes on to test */
 #pragma unroll 1
         for (unsigned q0 = 0; q0 < (unsigned)G; q0 += CH) {
             const unsigned kb = g * G + q0;
