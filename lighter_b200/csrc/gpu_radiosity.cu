@@ -921,6 +921,7 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
         RAD_TRY(dev_alloc(ctx, &cand, cand_cap));
         /* batch of items: probe with a small one, then size each batch from the measured yield */
         uint32_t batch = (uint32_t)ctx->num_sms * (uint32_t)sweep_ctas * RAD_WARPS * 8u;
+        RAD_TRACE("candidate buffer");
         for (uint32_t i0 = 0; i0 < n_items;) {
             const uint32_t i1 = batch < n_items - i0 ? i0 + batch : n_items;
             RAD_CU(cudaMemsetAsync(d_cnt, 0, 32, st));
@@ -954,9 +955,16 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
             }
             const unsigned long long nc = h_cnt[0];
             if (nc) {
+                struct timespec tg0, tg1;
+                if (trace) clock_gettime(CLOCK_MONOTONIC, &tg0);
                 RAD_TRY(grow_buf(ctx, &keys, &link_cap, link_used, link_used + 2 * nc));
                 RAD_TRY(grow_buf(ctx, &fac, &link_cap_f, link_used, link_used + 2 * nc));
                 if (world > 1) RAD_TRY(grow_buf(ctx, &mirror, &mirror_cap, mirror_used, mirror_used + nc));
+                if (trace) {
+                    clock_gettime(CLOCK_MONOTONIC, &tg1);
+                    fprintf(stderr, "[ltr rank %d] radiosity batch %u items, %llu candidates, link buffers grown in %.2f ms (capacity %zu)\n", ctx->rank, i1 - i0, nc,
+                            (tg1.tv_sec - tg0.tv_sec) * 1e3 + (tg1.tv_nsec - tg0.tv_nsec) * 1e-6, link_cap);
+                }
                 /* one warp per RAD_CHUNK candidates at a time, pulled from a cursor (the upper half of d_cnt[3], zero since the memset above) */
                 unsigned long long want = ((nc + RAD_CHUNK - 1) / RAD_CHUNK + LB_BLOCK / 32 - 1) / (LB_BLOCK / 32);
                 unsigned cap = (unsigned)ctx->num_sms * 16;
@@ -1035,9 +1043,11 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
             RAD_TRY(dev_alloc(ctx, &keys_alt, link_used)); RAD_TRY(dev_alloc(ctx, &fac_alt, link_used));
             cub::DoubleBuffer<unsigned long long> kb(keys, keys_alt);
             cub::DoubleBuffer<float> vb(fac, fac_alt);
-            RAD_CU(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, kb, vb, (int64_t)link_used, 0, 64, st));
+            int end_bit = 33;                             /* key = row position << 32 | partner index: the bits above the row field are zero */
+            while (end_bit < 64 && (n_pad >> (end_bit - 32)) != 0) ++end_bit;
+            RAD_CU(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, kb, vb, (int64_t)link_used, 0, end_bit, st));
             RAD_CU(lb_malloc(&sort_tmp, sort_tmp_bytes ? sort_tmp_bytes : 16));
-            RAD_CU(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_tmp_bytes, kb, vb, (int64_t)link_used, 0, 64, st));
+            RAD_CU(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_tmp_bytes, kb, vb, (int64_t)link_used, 0, end_bit, st));
             ctx->host_counters.kernel_launches += 8;
             RAD_CU(cudaStreamSynchronize(st));
             if (kb.Current() != keys) { unsigned long long *t = keys; keys = keys_alt; keys_alt = t; }
