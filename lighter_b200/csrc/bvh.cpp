@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <chrono>
+#include <emmintrin.h>
 
 namespace {
 
@@ -41,36 +42,95 @@ struct Prim { Box3 b; uint32_t id; };
 inline V3 centroid(const Prim &p) { return (p.b.lo + p.b.hi) * 0.5f; }
 
 const int NB = 16;                                /* SAH bins per axis */
+const uint32_t SPARSE_MAX = 96;                   /* nodes up to this size bin without clearing (bin_range_sparse) */
 const uint32_t FINE_MIN = 4096;                   /* unit of the dynamically scheduled part of the build */
 const uint32_t COOP_MIN = 65536;                  /* nodes above this size are built by all threads together */
 
 struct Bounds { Box3 bb, cb; };
-struct Bins {
-    Box3 box[3][NB];
+
+/* SSE2 (baseline x86-64) forms of the two per-triangle passes.  A Prim is 7 floats: lo.xyz, hi.xyz, id -- an unaligned
+ * 4-float load at float 0 gives lo in lanes 0-2, one at float 3 gives hi in lanes 0-2 (lane 3 holds a neighbouring field and
+ * is never read back: min/max/add/mul are lane-wise).  min/max of floats is exact, and the centroid / bin arithmetic is the
+ * same IEEE single-precision sequence as the scalar code, so the tree is the one the scalar builder produces. */
+inline __m128 ld_lo(const Prim &p) { return _mm_loadu_ps(&p.b.lo.x); }
+inline __m128 ld_hi(const Prim &p) { return _mm_loadu_ps(&p.b.lo.x + 3); }
+inline V3 v3_of(__m128 v) { alignas(16) float f[4]; _mm_store_ps(f, v); return mk3(f[0], f[1], f[2]); }
+
+struct alignas(16) Bins {
+    __m128 lo[3][NB], hi[3][NB];
     uint32_t cnt[3][NB];
-    void clear() { for (int a = 0; a < 3; ++a) for (int b = 0; b < NB; ++b) { box[a][b].lo = mk3(FMAXV); box[a][b].hi = mk3(-FMAXV); cnt[a][b] = 0; } }
-    void merge(const Bins &o) { for (int a = 0; a < 3; ++a) for (int b = 0; b < NB; ++b) { grow(box[a][b], o.box[a][b]); cnt[a][b] += o.cnt[a][b]; } }
+    uint32_t mask[3];                             /* bit b: bin b of that axis holds something (the only valid bins) */
+    void clear()                                  /* dense use: every bin initialised, masks derived afterwards (set_masks) */
+    {
+        const __m128 big = _mm_set1_ps(FMAXV), small = _mm_set1_ps(-FMAXV);
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < NB; ++b) { lo[a][b] = big; hi[a][b] = small; cnt[a][b] = 0; }
+    }
+    void merge(const Bins &o)
+    {
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < NB; ++b) { lo[a][b] = _mm_min_ps(lo[a][b], o.lo[a][b]); hi[a][b] = _mm_max_ps(hi[a][b], o.hi[a][b]); cnt[a][b] += o.cnt[a][b]; }
+    }
+    void set_masks()
+    {
+        for (int a = 0; a < 3; ++a) { uint32_t m = 0; for (int b = 0; b < NB; ++b) m |= (cnt[a][b] ? 1u : 0u) << b; mask[a] = m; }
+    }
 };
 
 inline void bounds_of(const Prim *p, size_t n, Bounds &o)
 {
-    o.bb.lo = o.cb.lo = mk3(FMAXV); o.bb.hi = o.cb.hi = mk3(-FMAXV);
-    for (size_t i = 0; i < n; ++i) { grow(o.bb, p[i].b); grow(o.cb, centroid(p[i])); }
+    const __m128 half = _mm_set1_ps(0.5f);
+    __m128 blo = _mm_set1_ps(FMAXV), bhi = _mm_set1_ps(-FMAXV), clo = blo, chi = bhi;
+    for (size_t i = 0; i < n; ++i) {
+        const __m128 l = ld_lo(p[i]), h = ld_hi(p[i]);
+        const __m128 c = _mm_mul_ps(_mm_add_ps(l, h), half);
+        blo = _mm_min_ps(blo, l); bhi = _mm_max_ps(bhi, h);
+        clo = _mm_min_ps(clo, c); chi = _mm_max_ps(chi, c);
+    }
+    o.bb.lo = v3_of(blo); o.bb.hi = v3_of(bhi); o.cb.lo = v3_of(clo); o.cb.hi = v3_of(chi);
 }
 inline int bin_of(float c, float lo, float scale)
 {
     int b = (int)((c - lo) * scale);
     return b < 0 ? 0 : (b >= NB ? NB - 1 : b);
 }
-/* all three axes in one pass over the primitives */
+inline int clamp_bin(int b) { return b < 0 ? 0 : (b >= NB ? NB - 1 : b); }
+/* all three axes in one pass over the primitives (an unused axis has scale 0: everything lands in its bin 0, which nobody reads) */
 inline void bin_range(const Prim *p, size_t n, const Box3 &cb, const bool use[3], const float scale[3], Bins &o)
 {
+    (void)use;
+    const __m128 half = _mm_set1_ps(0.5f), cblo = _mm_set_ps(0.f, cb.lo.z, cb.lo.y, cb.lo.x), sc = _mm_set_ps(0.f, scale[2], scale[1], scale[0]);
     for (size_t i = 0; i < n; ++i) {
-        const V3 c = centroid(p[i]);
-        if (use[0]) { int b = bin_of(c.x, cb.lo.x, scale[0]); o.cnt[0][b]++; grow(o.box[0][b], p[i].b); }
-        if (use[1]) { int b = bin_of(c.y, cb.lo.y, scale[1]); o.cnt[1][b]++; grow(o.box[1][b], p[i].b); }
-        if (use[2]) { int b = bin_of(c.z, cb.lo.z, scale[2]); o.cnt[2][b]++; grow(o.box[2][b], p[i].b); }
+        const __m128 l = ld_lo(p[i]), h = ld_hi(p[i]);
+        const __m128 c = _mm_mul_ps(_mm_add_ps(l, h), half);
+        const __m128i bi = _mm_cvttps_epi32(_mm_mul_ps(_mm_sub_ps(c, cblo), sc));
+        const int bx = clamp_bin(_mm_cvtsi128_si32(bi)), by = clamp_bin(_mm_cvtsi128_si32(_mm_shuffle_epi32(bi, 1))), bz = clamp_bin(_mm_cvtsi128_si32(_mm_shuffle_epi32(bi, 2)));
+        o.cnt[0][bx]++; o.lo[0][bx] = _mm_min_ps(o.lo[0][bx], l); o.hi[0][bx] = _mm_max_ps(o.hi[0][bx], h);
+        o.cnt[1][by]++; o.lo[1][by] = _mm_min_ps(o.lo[1][by], l); o.hi[1][by] = _mm_max_ps(o.hi[1][by], h);
+        o.cnt[2][bz]++; o.lo[2][bz] = _mm_min_ps(o.lo[2][bz], l); o.hi[2][bz] = _mm_max_ps(o.hi[2][bz], h);
     }
+}
+/* The same for a SMALL node (most nodes are: half a million of them hold < 16 triangles): nothing is cleared, a bin is
+ * initialised by the first triangle that lands in it (mask bit), so the cost is per triangle, not per bin. */
+inline void bin_range_sparse(const Prim *p, size_t n, const Box3 &cb, const float scale[3], Bins &o)
+{
+    o.mask[0] = o.mask[1] = o.mask[2] = 0;
+    const __m128 half = _mm_set1_ps(0.5f), cblo = _mm_set_ps(0.f, cb.lo.z, cb.lo.y, cb.lo.x), sc = _mm_set_ps(0.f, scale[2], scale[1], scale[0]);
+    for (size_t i = 0; i < n; ++i) {
+        const __m128 l = ld_lo(p[i]), h = ld_hi(p[i]);
+        const __m128 c = _mm_mul_ps(_mm_add_ps(l, h), half);
+        const __m128i bi = _mm_cvttps_epi32(_mm_mul_ps(_mm_sub_ps(c, cblo), sc));
+        const int bin[3] = { clamp_bin(_mm_cvtsi128_si32(bi)), clamp_bin(_mm_cvtsi128_si32(_mm_shuffle_epi32(bi, 1))), clamp_bin(_mm_cvtsi128_si32(_mm_shuffle_epi32(bi, 2))) };
+        for (int a = 0; a < 3; ++a) {
+            const int b = bin[a];
+            if (o.mask[a] & (1u << b)) { o.cnt[a][b]++; o.lo[a][b] = _mm_min_ps(o.lo[a][b], l); o.hi[a][b] = _mm_max_ps(o.hi[a][b], h); }
+            else { o.mask[a] |= 1u << b; o.cnt[a][b] = 1; o.lo[a][b] = l; o.hi[a][b] = h; }
+        }
+    }
+}
+inline float half_area_v(__m128 lo, __m128 hi)
+{
+    alignas(16) float e[4];
+    _mm_store_ps(e, _mm_sub_ps(hi, lo));
+    return e[0] * e[1] + e[1] * e[2] + e[2] * e[0];
 }
 
 template <class F> void parallel_chunks(int threads, size_t n, F fn)      /* fn(chunk index, begin, end), chunk count == threads */
@@ -85,7 +145,57 @@ template <class F> void parallel_chunks(int threads, size_t n, F fn)      /* fn(
     for (auto &th : pool) th.join();
 }
 
-struct Work { int32_t node; uint32_t first, count; int depth; };
+struct Work {
+    int32_t node; uint32_t first, count; int depth;
+    bool has_nb = false;          /* nb = bounds of the range, accumulated by the parent's partition pass (saves a pass over the range) */
+    Bounds nb;
+};
+
+/* bounds of one side of a partition, accumulated while the triangles are being moved */
+struct SideAcc {
+    __m128 blo, bhi, clo, chi;
+    void clear() { blo = clo = _mm_set1_ps(FMAXV); bhi = chi = _mm_set1_ps(-FMAXV); }
+    void add(__m128 l, __m128 h, __m128 c) { blo = _mm_min_ps(blo, l); bhi = _mm_max_ps(bhi, h); clo = _mm_min_ps(clo, c); chi = _mm_max_ps(chi, c); }
+    void merge(const SideAcc &o) { blo = _mm_min_ps(blo, o.blo); bhi = _mm_max_ps(bhi, o.bhi); clo = _mm_min_ps(clo, o.clo); chi = _mm_max_ps(chi, o.chi); }
+    Bounds get() const { Bounds b; b.bb.lo = v3_of(blo); b.bb.hi = v3_of(bhi); b.cb.lo = v3_of(clo); b.cb.hi = v3_of(chi); return b; }
+};
+
+/* bin (unclamped) of a centroid on axis A: the arithmetic of bin_range */
+template <int A> inline int axis_bin(__m128 c, __m128 cblo, __m128 sc4)
+{
+    const __m128i bi = _mm_cvttps_epi32(_mm_mul_ps(_mm_sub_ps(c, cblo), sc4));
+    return A == 0 ? _mm_cvtsi128_si32(bi) : _mm_cvtsi128_si32(_mm_shuffle_epi32(bi, A));
+}
+
+/* std::partition's two-pointer scheme written out (same swaps, same resulting order) with "left = centroid bin on axis A
+ * below sp" as the predicate; every triangle is looked at exactly once, and while it is in registers its box and centroid
+ * are added to the bounds of the side it lands on (the accumulators stay in registers: no call, no captures). */
+template <int A> uint32_t partition_acc(Prim *P, uint32_t count, int sp, __m128 cblo, __m128 sc4, SideAcc &AL, SideAcc &AR)
+{
+    const __m128 half = _mm_set1_ps(0.5f);
+    __m128 lbl = AL.blo, lbh = AL.bhi, lcl = AL.clo, lch = AL.chi, rbl = AR.blo, rbh = AR.bhi, rcl = AR.clo, rch = AR.chi;
+#define LB_SIDE(PRIM, LEFT)                                                                                   \
+    {                                                                                                         \
+        const __m128 l_ = ld_lo(PRIM), h_ = ld_hi(PRIM);                                                      \
+        const __m128 c_ = _mm_mul_ps(_mm_add_ps(l_, h_), half);                                               \
+        LEFT = clamp_bin(axis_bin<A>(c_, cblo, sc4)) < sp;                                                    \
+        if (LEFT) { lbl = _mm_min_ps(lbl, l_); lbh = _mm_max_ps(lbh, h_); lcl = _mm_min_ps(lcl, c_); lch = _mm_max_ps(lch, c_); } \
+        else      { rbl = _mm_min_ps(rbl, l_); rbh = _mm_max_ps(rbh, h_); rcl = _mm_min_ps(rcl, c_); rch = _mm_max_ps(rch, c_); } \
+    }
+    Prim *first = P, *last = P + count;
+    for (;;) {
+        bool left;
+        for (;;) { if (first == last) goto done; LB_SIDE(*first, left) if (left) ++first; else break; }
+        --last;
+        for (;;) { if (first == last) goto done; LB_SIDE(*last, left) if (!left) --last; else break; }
+        const Prim t = *first; *first = *last; *last = t;
+        ++first;
+    }
+done:
+#undef LB_SIDE
+    AL.blo = lbl; AL.bhi = lbh; AL.clo = lcl; AL.chi = lch; AR.blo = rbl; AR.bhi = rbh; AR.clo = rcl; AR.chi = rch;
+    return (uint32_t)(first - P);
+}
 
 struct Builder {
     Prim *prim;
@@ -107,7 +217,9 @@ struct Builder {
         const uint32_t count = w.count;
         const int T = coop ? threads : 1;
         Bounds nb;
-        if (T > 1) {
+        static const bool nofuse = getenv("LTR_BVH_NOFUSE") != nullptr;
+        if (w.has_nb && !nofuse) nb = w.nb;
+        else if (T > 1) {
             std::vector<Bounds> part(T);
             parallel_chunks(T, count, [&](int t, size_t b, size_t e) { bounds_of(P + b, e - b, part[t]); });
             nb = part[0];
@@ -119,34 +231,50 @@ struct Builder {
         N.inner = -1;
 
         const Box3 cb = nb.cb;
-        const float lo3[3] = { cb.lo.x, cb.lo.y, cb.lo.z }, ext3[3] = { cb.hi.x - cb.lo.x, cb.hi.y - cb.lo.y, cb.hi.z - cb.lo.z };
+        const float ext3[3] = { cb.hi.x - cb.lo.x, cb.hi.y - cb.lo.y, cb.hi.z - cb.lo.z };
         bool use[3]; float scale[3];
         for (int a = 0; a < 3; ++a) { use[a] = ext3[a] > 0; scale[a] = use[a] ? NB / ext3[a] : 0.f; }
-        Bins bins; bins.clear();
+        Bins bins;
+        std::vector<Bins> part;                           /* cooperative path: per-chunk bins, kept for the partition's left counts */
         if (T > 1) {
-            std::vector<Bins> part(T);
+            bins.clear();
+            part.resize(T);
             parallel_chunks(T, count, [&](int t, size_t b, size_t e) { part[t].clear(); bin_range(P + b, e - b, cb, use, scale, part[t]); });
             for (int t = 0; t < T; ++t) bins.merge(part[t]);
-        } else bin_range(P, count, cb, use, scale, bins);
+            bins.set_masks();
+        } else if (count > SPARSE_MAX) {
+            bins.clear();
+            bin_range(P, count, cb, use, scale, bins);
+            bins.set_masks();
+        } else bin_range_sparse(P, count, cb, scale, bins);
 
         int best_axis = -1, best_split = 0;
         float best_cost = FMAXV;
         for (int a = 0; a < 3; ++a) {
             if (!use[a]) continue;
-            float la[NB]; uint32_t lc[NB];
-            Box3 acc = { mk3(FMAXV), mk3(-FMAXV) };
+            /* Sweep over the NON-EMPTY bins only.  Between two neighbouring non-empty bins every split position gives the
+             * same two sides, hence the same cost; the dense sweep (positions NB-1 down to 1, strict <) keeps the highest of
+             * them, which is the non-empty bin that opens the right side -- so the choice below is the dense sweep's. */
+            float la[NB]; uint32_t lc[NB]; int bs[NB];
+            int K = 0;
+            __m128 alo = _mm_set1_ps(FMAXV), ahi = _mm_set1_ps(-FMAXV);
             uint32_t c = 0;
-            for (int b = 0; b < NB - 1; ++b) { grow(acc, bins.box[a][b]); c += bins.cnt[a][b]; la[b] = c ? half_area(acc) : 0; lc[b] = c; }
-            acc.lo = mk3(FMAXV); acc.hi = mk3(-FMAXV); c = 0;
-            for (int b = NB - 1; b > 0; --b) {
-                grow(acc, bins.box[a][b]); c += bins.cnt[a][b];
-                if (lc[b - 1] == 0 || c == 0) continue;
-                float cost = la[b - 1] * lc[b - 1] + half_area(acc) * c;
+            for (uint32_t m = bins.mask[a]; m; m &= m - 1) {
+                const int b = __builtin_ctz(m);
+                alo = _mm_min_ps(alo, bins.lo[a][b]); ahi = _mm_max_ps(ahi, bins.hi[a][b]); c += bins.cnt[a][b];
+                la[K] = half_area_v(alo, ahi); lc[K] = c; bs[K] = b; ++K;
+            }
+            alo = _mm_set1_ps(FMAXV); ahi = _mm_set1_ps(-FMAXV); c = 0;
+            for (int k = K - 1; k > 0; --k) {
+                const int b = bs[k];
+                alo = _mm_min_ps(alo, bins.lo[a][b]); ahi = _mm_max_ps(ahi, bins.hi[a][b]); c += bins.cnt[a][b];
+                float cost = la[k - 1] * lc[k - 1] + half_area_v(alo, ahi) * c;
                 if (cost < best_cost) { best_cost = cost; best_axis = a; best_split = b; }
             }
         }
 
         uint32_t mid;
+        l.has_nb = r.has_nb = false;
         if (best_axis < 0) {
             mid = count / 2;                               /* coincident centroids: split by index */
         } else if (w.depth > 40) {                         /* failsafe against degenerate SAH chains */
@@ -156,28 +284,46 @@ struct Builder {
             std::nth_element(P, P + mid, P + count, [=](const Prim &p, const Prim &q) { return axis_of(centroid(p), a) < axis_of(centroid(q), a); });
         } else {
             const int a = best_axis, sp = best_split;
-            const float lo = lo3[a], sc = scale[a];
-            auto is_left = [=](const Prim &t) { return bin_of(axis_of(centroid(t), a), lo, sc) < sp; };
+            /* side of a triangle = bin of its centroid on the chosen axis (the arithmetic of bin_range), and while the
+             * triangle is in registers its box and centroid go into the bounds of the side it lands on */
+            const __m128 half = _mm_set1_ps(0.5f), cblo = _mm_set_ps(0.f, cb.lo.z, cb.lo.y, cb.lo.x), sc4 = _mm_set_ps(0.f, scale[2], scale[1], scale[0]);
+            auto side = [=](const Prim &t, SideAcc &L, SideAcc &R) {
+                const __m128 l = ld_lo(t), h = ld_hi(t);
+                const __m128 c = _mm_mul_ps(_mm_add_ps(l, h), half);
+                alignas(16) int bi[4];
+                _mm_store_si128((__m128i *)bi, _mm_cvttps_epi32(_mm_mul_ps(_mm_sub_ps(c, cblo), sc4)));
+                const bool left = clamp_bin(bi[a]) < sp;
+                (left ? L : R).add(l, h, c);
+                return left;
+            };
+            SideAcc AL, AR;
+            AL.clear(); AR.clear();
             if (T > 1) {
-                /* stable partition through the scratch array: count per chunk, scan, scatter, copy back */
+                /* stable partition through the scratch array: left counts per chunk from the chunk's bins, scan, scatter, copy back */
                 std::vector<uint32_t> nl(T + 1, 0);
                 Prim *S = scratch + w.first;
-                parallel_chunks(T, count, [&](int t, size_t b, size_t e) { uint32_t c = 0; for (size_t i = b; i < e; ++i) c += is_left(P[i]); nl[t + 1] = c; });
-                for (int t = 0; t < T; ++t) nl[t + 1] += nl[t];
+                for (int t = 0; t < T; ++t) { uint32_t c = 0; for (int b = 0; b < sp; ++b) c += part[t].cnt[a][b]; nl[t + 1] = nl[t] + c; }
                 const uint32_t total_left = nl[T];
                 const size_t per = ((size_t)count + T - 1) / T;
+                std::vector<SideAcc> pl(T), pr(T);
                 parallel_chunks(T, count, [&](int t, size_t b, size_t e) {
                     size_t lpos = nl[t], rpos = total_left + (std::min((size_t)count, per * t) - nl[t]);
-                    for (size_t i = b; i < e; ++i) { if (is_left(P[i])) S[lpos++] = P[i]; else S[rpos++] = P[i]; }
+                    SideAcc L, R;
+                    L.clear(); R.clear();
+                    for (size_t i = b; i < e; ++i) { if (side(P[i], L, R)) S[lpos++] = P[i]; else S[rpos++] = P[i]; }
+                    pl[t] = L; pr[t] = R;
                 });
+                for (int t = 0; t < T; ++t) { AL.merge(pl[t]); AR.merge(pr[t]); }
                 parallel_chunks(T, count, [&](int, size_t b, size_t e) { if (e > b) memcpy(P + b, S + b, (e - b) * sizeof(Prim)); });
                 mid = total_left;
             } else if (count > COOP_MIN) {                 /* same (stable) order as the cooperative path: the tree does not depend on the thread count */
-                mid = (uint32_t)(std::stable_partition(P, P + count, is_left) - P);
+                mid = (uint32_t)(std::stable_partition(P, P + count, [&](const Prim &t) { return side(t, AL, AR); }) - P);
             } else {
-                mid = (uint32_t)(std::partition(P, P + count, is_left) - P);
+                mid = a == 0 ? partition_acc<0>(P, count, sp, cblo, sc4, AL, AR) : a == 1 ? partition_acc<1>(P, count, sp, cblo, sc4, AL, AR)
+                                                                                           : partition_acc<2>(P, count, sp, cblo, sc4, AL, AR);
             }
             if (mid == 0 || mid == count) mid = count / 2;
+            else { l.has_nb = r.has_nb = true; l.nb = AL.get(); r.nb = AR.get(); }
         }
         l.node = alloc(); r.node = alloc();
         tmp[w.node].left = l.node; tmp[w.node].right = r.node;
@@ -374,6 +520,7 @@ void build_scene_bvh(const float *tris9, size_t count, SceneBvh &out, int leaf_m
     auto tnow = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double tt = tnow();
     auto lap = [&](const char *w) { if (trace) { double t = tnow(); fprintf(stderr, "[bvh] %-12s %7.1f ms\n", w, t - tt); tt = t; } };
+    if (threads <= 0) { const char *e = getenv("LTR_BVH_THREADS"); threads = e ? atoi(e) : 0; }      /* env: measurements */
     if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
     if (threads < 1) threads = 1;
     if (threads > 64) threads = 64;
