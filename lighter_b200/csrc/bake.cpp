@@ -102,14 +102,15 @@ int nccl_allgather_cb(void *user, const void *send, void *recv, size_t bytes, vo
 struct Bake {
     ltrgpu_Ctx *gpu = nullptr;
     std::vector<ltrgpu_Inst> inst;
-    std::vector<V3> wpos, wnrm;
-    std::vector<float> vtex, ltex;
-    std::vector<ltrgpu_RasterTri> rtris;
-    std::vector<RefNode> rnodes;
-    std::vector<int32_t> ritems;
-    std::vector<float> rtree_tris;
+    /* big arrays, every element written after resize(): BigVec = no zero-fill, huge pages on request (bvh.h) */
+    BigVec<V3> wpos, wnrm;
+    BigVec<float> vtex, ltex;
+    BigVec<ltrgpu_RasterTri> rtris;
+    BigVec<RefNode> rnodes;
+    BigVec<int32_t> ritems;
+    BigVec<float> rtree_tris;
     SceneBvh bvh;
-    std::vector<float> bvh_tris;
+    BigVec<float> bvh_tris;
     std::vector<ltrgpu_Light> lights;
     std::vector<float> light_samples;         /* float4 per (light, sample): sampled-shadow extension table (host libm) */
     std::vector<uint8_t> light_inst;
@@ -175,7 +176,9 @@ void host_prepare(ltr_Scene *S)
     const size_t nv = vbase[ni];
     B.wpos.resize(nv); B.wnrm.resize(nv); B.vtex.resize(nv * 2); B.ltex.resize(nv * 2);
 
-    for (size_t i = 1; i < ni; ++i) {
+    /* one instance per task, as the reference does (its size_fn is called from pool threads, one per instance, concurrently:
+     * lighter.cpp:1054,326) */
+    auto xform_instance = [&](size_t i) {
         MeshInstance *mi = S->instances[i];
         ltr_Mesh *mesh = mi->mesh;
         const float *M = mi->matrix;
@@ -211,6 +214,15 @@ void host_prepare(ltr_Scene *S)
             B.ltex[(vbase[i] + v) * 2 + 0] = mesh->vtex2[v].x * lw - 0.5f;
             B.ltex[(vbase[i] + v) * 2 + 1] = mesh->vtex2[v].y * lh - 0.5f;
         }
+    };
+    {
+        const unsigned nthreads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), ni > 1 ? (unsigned)(ni - 1) : 1u));
+        std::atomic<size_t> next{1};
+        std::vector<std::thread> pool;
+        auto worker = [&]() { for (size_t i; (i = next.fetch_add(1)) < ni;) xform_instance(i); };
+        for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(worker);
+        worker();
+        for (auto &th : pool) th.join();
     }
     S->stats.t_prexform = now_s() - t0;
     t0 = now_s();
@@ -259,7 +271,7 @@ void host_prepare(ltr_Scene *S)
     });
     std::vector<size_t> o_stri(ni + 1, 0);
     for (size_t i = 0; i < ni; ++i) o_stri[i + 1] = o_stri[i] + ((i && S->instances[i]->shadow) ? itris[i].size() / 9 : 0);
-    std::vector<float> scene_tris(o_stri[ni] * 9);
+    BigVec<float> scene_tris(o_stri[ni] * 9);
     parallel_instances([&](size_t i) {
         if (i && S->instances[i]->shadow && !itris[i].empty()) memcpy(&scene_tris[o_stri[i] * 9], itris[i].data(), itris[i].size() * 4);
     });

@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <chrono>
 #include <emmintrin.h>
+#include <sys/mman.h>
 
 namespace {
 
@@ -496,6 +497,37 @@ struct Flattener4 {
 
 } // namespace
 
+/* Uninitialised work array backed by transparent huge pages where the kernel offers them on request (THP "madvise" mode):
+ * the builder touches ~150 MB of fresh memory per 1 M triangles, and with 4 KiB pages the page faults are a visible part
+ * of the build.  Falls back silently to ordinary pages. */
+template <class T> struct HugeArray {
+    T *p = nullptr;
+    explicit HugeArray(size_t n) { if (n) p = static_cast<T *>(lb_big_alloc(n * sizeof(T))); }
+    ~HugeArray() { free(p); }
+    HugeArray(const HugeArray &) = delete;
+    HugeArray &operator=(const HugeArray &) = delete;
+    T *get() const { return p; }
+    T &operator[](size_t i) const { return p[i]; }
+};
+
+void *lb_big_alloc(size_t n)
+{
+    static const bool no_huge = getenv("LTR_NO_HUGEPAGES") != nullptr;
+    void *q = nullptr;
+    if (n >= (4u << 20) && !no_huge) {
+        const size_t bytes = ((n + (2u << 20) - 1) >> 21) << 21;
+        if (posix_memalign(&q, 2u << 20, bytes) == 0) {
+#ifdef MADV_HUGEPAGE
+            madvise(q, bytes, MADV_HUGEPAGE);
+#endif
+            return q;
+        }
+    }
+    q = malloc(n ? n : 1);
+    if (!q) { fprintf(stderr, "lighter_b200: out of host memory (%zu bytes)\n", n); abort(); }
+    return q;
+}
+
 void build_scene_bvh(const float *tris9, size_t count, SceneBvh &out, int leaf_max, int threads)
 {
     out.nodes.clear();
@@ -525,7 +557,8 @@ void build_scene_bvh(const float *tris9, size_t count, SceneBvh &out, int leaf_m
     if (threads < 1) threads = 1;
     if (threads > 64) threads = 64;
     /* uninitialised working arrays: zero-filling ~140 MB on one thread costs more than the top of the build */
-    std::unique_ptr<Prim[]> prim(new Prim[count]), scratch(threads > 1 && count > COOP_MIN ? new Prim[count] : nullptr);
+    HugeArray<Prim> prim(count), scratch(threads > 1 && count > COOP_MIN ? count : 0);
+    if (!prim.get() || (threads > 1 && count > COOP_MIN && !scratch.get())) { fprintf(stderr, "lighter_b200: out of host memory in the BVH build\n"); abort(); }
     {
         std::vector<Box3> part(threads, Box3{ mk3(FMAXV), mk3(-FMAXV) });
         Prim *pp = prim.get();
@@ -546,7 +579,8 @@ void build_scene_bvh(const float *tris9, size_t count, SceneBvh &out, int leaf_m
 
     lap("prims");
     Builder B;
-    std::unique_ptr<Tmp[]> tmp(new Tmp[2 * count + 1]);
+    HugeArray<Tmp> tmp(2 * count + 1);
+    if (!tmp.get()) { fprintf(stderr, "lighter_b200: out of host memory in the BVH build\n"); abort(); }
     B.prim = prim.get(); B.scratch = scratch.get(); B.tmp = tmp.get();
     B.leaf_max = leaf_max;
     B.threads = threads;
@@ -613,8 +647,8 @@ void build_scene_bvh(const float *tris9, size_t count, SceneBvh &out, int leaf_m
 
 void build_bvh4(SceneBvh &bvh)
 {
-    const std::vector<BvhNode> &n2 = bvh.nodes;
-    std::vector<Bvh4Node> &n4 = bvh.nodes4;
+    const BigVec<BvhNode> &n2 = bvh.nodes;
+    BigVec<Bvh4Node> &n4 = bvh.nodes4;
     n4.clear();
     if (n2.empty()) return;
     n4.reserve(n2.size() / 2 + 1);

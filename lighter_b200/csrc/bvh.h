@@ -11,6 +11,9 @@
  */
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
+#include <new>
+#include <utility>
 #include <vector>
 #include "vmath.h"
 
@@ -35,10 +38,26 @@ struct Bvh4Node {                /* 128 bytes */
     int32_t pad[4];
 };
 
+/* Allocator of the builder's big arrays: elements are default-INITIALISED (resize() does not zero 70 MB that the flatten
+ * passes overwrite anyway) and large blocks ask for transparent huge pages (THP "madvise" mode; see bvh.cpp). */
+void *lb_big_alloc(size_t bytes);
+template <class T> struct LbBigAlloc {
+    typedef T value_type;
+    LbBigAlloc() = default;
+    template <class U> LbBigAlloc(const LbBigAlloc<U> &) {}
+    T *allocate(size_t n) { return static_cast<T *>(lb_big_alloc(n * sizeof(T))); }
+    void deallocate(T *p, size_t) { free(p); }
+    template <class U> void construct(U *) {}                                           /* default-init: left as is */
+    template <class U, class A0, class... A> void construct(U *p, A0 &&a0, A &&...a) { ::new ((void *)p) U(std::forward<A0>(a0), std::forward<A>(a)...); }
+    template <class U> bool operator==(const LbBigAlloc<U> &) const { return true; }
+    template <class U> bool operator!=(const LbBigAlloc<U> &) const { return false; }
+};
+template <class T> using BigVec = std::vector<T, LbBigAlloc<T>>;
+
 struct SceneBvh {
-    std::vector<BvhNode> nodes;          /* nodes[0] = root */
-    std::vector<Bvh4Node> nodes4;        /* nodes4[0] = root of the collapsed tree (build_bvh4) */
-    std::vector<uint32_t> order;         /* order[k] = original triangle index stored at slot k */
+    BigVec<BvhNode> nodes;               /* nodes[0] = root */
+    BigVec<Bvh4Node> nodes4;             /* nodes4[0] = root of the collapsed tree (build_bvh4) */
+    BigVec<uint32_t> order;              /* order[k] = original triangle index stored at slot k */
     Box3 bounds;
     int depth = 0;
 };
