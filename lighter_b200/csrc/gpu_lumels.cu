@@ -375,7 +375,10 @@ __device__ void reftree_offset_sample(const RefView &v, V3 &P, V3 N, float dist,
     }
 }
 
-__global__ void __launch_bounds__(LB_BLOCK)
+#ifndef LB_FIX_MINBLOCKS
+#define LB_FIX_MINBLOCKS 8        /* 64 registers: lumel stage 22.3 ms vs 24.5 uncapped (80 regs) on config 4 */
+#endif
+__global__ void __launch_bounds__(LB_BLOCK, LB_FIX_MINBLOCKS)
 lumel_fix_kernel(const ltrgpu_Inst *__restrict__ inst, uint32_t n_inst, RefView all, const BvhNode *__restrict__ bvh,
                  const RayTri *__restrict__ raytris, const PreparedTri *__restrict__ ptris, const uint32_t *__restrict__ tri_orig,
                  uint64_t first, uint64_t n_lumels, float max_correct_dist, float corr_min_dot,
