@@ -218,8 +218,7 @@ struct Builder {
         const uint32_t count = w.count;
         const int T = coop ? threads : 1;
         Bounds nb;
-        static const bool nofuse = getenv("LTR_BVH_NOFUSE") != nullptr;
-        if (w.has_nb && !nofuse) nb = w.nb;
+        if (w.has_nb) nb = w.nb;
         else if (T > 1) {
             std::vector<Bounds> part(T);
             parallel_chunks(T, count, [&](int t, size_t b, size_t e) { bounds_of(P + b, e - b, part[t]); });
@@ -512,7 +511,7 @@ template <class T> struct HugeArray {
 
 void *lb_big_alloc(size_t n)
 {
-    static const bool no_huge = getenv("LTR_NO_HUGEPAGES") != nullptr;
+    const bool no_huge = getenv("LTR_NO_HUGEPAGES") != nullptr;      /* read per call: tests flip it */
     void *q = nullptr;
     if (n >= (4u << 20) && !no_huge) {
         const size_t bytes = ((n + (2u << 20) - 1) >> 21) << 21;

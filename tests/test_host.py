@@ -117,6 +117,26 @@ def test_flat_bvh_invariants():
     assert b["ok"] and b["depth"] <= 20
 
 
+def test_flat_bvh_does_not_depend_on_thread_count_or_page_size(monkeypatch):
+    """The builder's cooperative top, its dynamically scheduled sub-trees, the SSE2 passes and the huge-page work arrays must
+    not change the tree: the triangle order (which encodes every partition) is the same for 1, 3 and 8 threads, with and
+    without huge pages, on a scene large enough (> 65536 triangles) to take the cooperative path."""
+    rng = np.random.default_rng(17)
+    n = 150_000
+    tris = (rng.uniform(-40, 40, (n, 1, 3)) * np.array([1, 1, 0.05]) + rng.uniform(-0.3, 0.3, (n, 3, 3))).astype(np.float32).reshape(n, 9)
+    ref = None
+    for threads, nohuge in (("1", False), ("3", False), ("8", False), ("8", True)):
+        monkeypatch.setenv("LTR_BVH_THREADS", threads)
+        if nohuge:
+            monkeypatch.setenv("LTR_NO_HUGEPAGES", "1")
+        b = api.test_bvh(tris, 2)
+        assert b["ok"], threads
+        key = (b["n_nodes"], b["depth"], b["order"].tobytes())
+        if ref is None:
+            ref = key
+        assert key == ref, (threads, nohuge)
+
+
 def test_bvh_entry_set_keeps_every_triangle_in_range_reachable():
     """csrc/bvh_entry.h: for bundles of segments (compact, scene-wide, degenerate, empty) the entry set must keep every
     triangle whose box overlaps the bundle box reachable, and the any-hit walk from the entry set must agree with the walk
