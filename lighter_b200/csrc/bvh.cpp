@@ -5,6 +5,9 @@
 #include <algorithm>
 #include <atomic>
 #include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <functional>
 #include <memory>
 #include <utility>
 #include <string.h>
@@ -134,15 +137,89 @@ inline float half_area_v(__m128 lo, __m128 hi)
     return e[0] * e[1] + e[1] * e[2] + e[2] * e[0];
 }
 
+/* A team of threads that lives for one build: the cooperative top of the tree runs ~55 short parallel passes, and spawning
+ * 15 threads for each of them cost more than the passes themselves (0.3-1 ms per spawn round on the bench host).  Plain
+ * mutex + condition variables, one job at a time, the caller is member 0. */
+class ThreadTeam {
+public:
+    explicit ThreadTeam(int members) : T(members)
+    {
+        for (int t = 1; t < T; ++t) th.emplace_back([this, t]() { member(t); });
+    }
+    ~ThreadTeam()
+    {
+        { std::lock_guard<std::mutex> g(m); quit = true; }
+        cv_work.notify_all();
+        for (auto &x : th) x.join();
+    }
+    int size() const { return T; }
+    /* runs f(0) .. f(T-1), one call per member, and returns when all are done */
+    void run(const std::function<void(int)> &f)
+    {
+        if (T <= 1) { f(0); return; }
+        { std::lock_guard<std::mutex> g(m); job = &f; remaining = T - 1; ++epoch; }
+        cv_work.notify_all();
+        f(0);
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [this]() { return remaining == 0; });
+        job = nullptr;
+    }
+private:
+    void member(int t)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)> *j;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv_work.wait(lk, [&]() { return quit || epoch != seen; });
+                if (quit) return;
+                seen = epoch;
+                j = job;
+            }
+            (*j)(t);
+            {
+                std::lock_guard<std::mutex> g(m);
+                if (--remaining == 0) cv_done.notify_one();
+            }
+        }
+    }
+    const int T;
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv_work, cv_done;
+    const std::function<void(int)> *job = nullptr;
+    uint64_t epoch = 0;
+    int remaining = 0;
+    bool quit = false;
+};
+thread_local ThreadTeam *tl_team = nullptr;       /* the team of the build running on this thread, if any */
+
 template <class F> void parallel_chunks(int threads, size_t n, F fn)      /* fn(chunk index, begin, end), chunk count == threads */
 {
-    std::vector<std::thread> pool;
     const size_t per = (n + threads - 1) / threads;
+    if (threads <= 1) { fn(0, 0, std::min(n, per)); return; }
+    if (tl_team && tl_team->size() == threads) {
+        tl_team->run([&](int t) { const size_t b = std::min(n, per * t), e = std::min(n, b + per); fn(t, b, e); });
+        return;
+    }
+    std::vector<std::thread> pool;
     for (int t = 1; t < threads; ++t) {
         const size_t b = std::min(n, per * t), e = std::min(n, b + per);
         pool.emplace_back([=]() { fn(t, b, e); });
     }
     fn(0, 0, std::min(n, per));
+    for (auto &th : pool) th.join();
+}
+
+/* `worker` on up to `members` threads (the team's, when this build has one of at least that size) */
+template <class F> void parallel_workers(int members, F worker)
+{
+    if (members <= 1) { worker(); return; }
+    if (tl_team && tl_team->size() >= members) { tl_team->run([&](int t) { if (t < members) worker(); }); return; }
+    std::vector<std::thread> pool;
+    for (int t = 1; t < members; ++t) pool.emplace_back(worker);
+    worker();
     for (auto &th : pool) th.join();
 }
 
@@ -389,11 +466,7 @@ struct Builder {
             std::vector<std::vector<Work>> part(small.size());
             std::atomic<size_t> cursor{0};
             auto worker = [&]() { for (size_t i; (i = cursor.fetch_add(1)) < small.size();) expand(small[i], part[i]); };
-            std::vector<std::thread> pool;
-            const int T = (int)std::min<size_t>((size_t)std::max(1, threads), small.size());
-            for (int t = 1; t < T; ++t) pool.emplace_back(worker);
-            worker();
-            for (auto &th : pool) th.join();
+            parallel_workers((int)std::min<size_t>((size_t)std::max(1, threads), small.size()), worker);
             for (auto &v : part) fine.insert(fine.end(), v.begin(), v.end());
         }
         small.swap(fine);
@@ -401,11 +474,7 @@ struct Builder {
         std::sort(small.begin(), small.end(), [](const Work &a, const Work &b) { return a.count != b.count ? a.count > b.count : a.first < b.first; });
         std::atomic<size_t> cursor{0};
         auto worker = [&]() { for (size_t i; (i = cursor.fetch_add(1)) < small.size();) build_serial(small[i]); };
-        std::vector<std::thread> pool;
-        const int T = (int)std::min<size_t>((size_t)std::max(1, threads), small.size());
-        for (int t = 1; t < T; ++t) pool.emplace_back(worker);
-        worker();
-        for (auto &th : pool) th.join();
+        parallel_workers((int)std::min<size_t>((size_t)std::max(1, threads), small.size()), worker);
         finish_sizes(root.node);
         subtrees.swap(small);
     }
@@ -556,6 +625,9 @@ void build_scene_bvh(const float *tris9, size_t count, SceneBvh &out, int leaf_m
     if (threads < 1) threads = 1;
     if (threads > 64) threads = 64;
     /* uninitialised working arrays: zero-filling ~140 MB on one thread costs more than the top of the build */
+    /* one team of threads for the whole build (only for scenes big enough to take the cooperative path) */
+    std::unique_ptr<ThreadTeam> team(threads > 1 && count > COOP_MIN ? new ThreadTeam(threads) : nullptr);
+    struct TeamScope { ThreadTeam *prev; explicit TeamScope(ThreadTeam *t) : prev(tl_team) { tl_team = t; } ~TeamScope() { tl_team = prev; } } team_scope(team.get());
     HugeArray<Prim> prim(count), scratch(threads > 1 && count > COOP_MIN ? count : 0);
     if (!prim.get() || (threads > 1 && count > COOP_MIN && !scratch.get())) { fprintf(stderr, "lighter_b200: out of host memory in the BVH build\n"); abort(); }
     {
@@ -614,11 +686,7 @@ void build_scene_bvh(const float *tris9, size_t count, SceneBvh &out, int leaf_m
         F.emit(root, 0, &is_cut, &cuts);
         std::atomic<size_t> cursor{0};
         auto worker = [&]() { for (size_t i; (i = cursor.fetch_add(1)) < cuts.size();) F.emit(cuts[i].first, cuts[i].second, nullptr, nullptr); };
-        std::vector<std::thread> pool;
-        const int T = (int)std::min<size_t>((size_t)threads, cuts.size());
-        for (int t = 1; t < T; ++t) pool.emplace_back(worker);
-        worker();
-        for (auto &th : pool) th.join();
+        parallel_workers((int)std::min<size_t>((size_t)threads, cuts.size()), worker);
     } else {
         F.emit(root, 0, nullptr, nullptr);
     }
@@ -631,11 +699,7 @@ void build_scene_bvh(const float *tris9, size_t count, SceneBvh &out, int leaf_m
             F4.emit(root, 0, tmp[root].inner_even / (threads * 8) + 64, &tasks);
             std::atomic<size_t> cursor{0};
             auto worker = [&]() { for (size_t i; (i = cursor.fetch_add(1)) < tasks.size();) F4.emit(tasks[i].t, tasks[i].slot, 0, nullptr); };
-            std::vector<std::thread> pool;
-            const int T = (int)std::min<size_t>((size_t)threads, tasks.size());
-            for (int t = 1; t < T; ++t) pool.emplace_back(worker);
-            worker();
-            for (auto &th : pool) th.join();
+            parallel_workers((int)std::min<size_t>((size_t)threads, tasks.size()), worker);
         } else {
             F4.emit(root, 0, 0, nullptr);
         }
