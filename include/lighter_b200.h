@@ -119,6 +119,8 @@ LTRAPI int ltrx_test_reftree(const float *tris9, u32 ntris, void *nodes_out, u32
  * when the lock-free table-level path was used, 0 for the plain rand() loop -- same values, same libc state afterwards */
 LTRAPI int ltrx_test_rand_fill(float *out, uint64_t n);
 LTRAPI int ltrx_test_bvh(const float *tris9, u32 ntris, int leaf_max, u32 *n_nodes, u32 *depth, u32 *order_out, float *bounds6);
+/* host-only: the host pre-pass of a scene without a device; FNV-1a fingerprints of the arrays it would upload */
+LTRAPI int ltrx_test_host_prepare(ltr_Scene *scene, uint64_t out_hash[12]);
 /* host-only: entry sets of segment bundles (csrc/bvh_entry.h) -- reachability self-check, root walk vs entry walk */
 LTRAPI int ltrx_test_bvh_entry(const float *tris9, u32 ntris, int leaf_max, const float *segs6, const u32 *bundle_off, u32 n_bundles,
                                u32 *entries_out, uint64_t *visits_root, uint64_t *visits_entry, uint64_t *entry_tests, u32 *mismatches);

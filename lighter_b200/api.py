@@ -136,7 +136,7 @@ LTRX_SYMBOLS = ["ltrx_Version", "ltrx_SetDevice", "ltrx_NcclUniqueId", "ltrx_Set
                 "ltrx_GetError", "ltrx_Prepare", "ltrx_BakeResident", "ltrx_Finish", "ltrx_SetDebug", "ltrx_GetLumels",
                 "ltrx_GetLinks", "ltrx_GetShadowFactors", "ltrx_SetShadowMode", "ltrx_GetShadowMasks", "ltrx_ShadowSampleSegment",
                 "ltrx_test_point_tri_distance", "ltrx_test_seg_tri",
-                "ltrx_test_scene_queries", "ltrx_test_march", "ltrx_test_spiral_dirs", "ltrx_test_reftree", "ltrx_test_bvh", "ltrx_test_bvh_entry",
+                "ltrx_test_scene_queries", "ltrx_test_march", "ltrx_test_spiral_dirs", "ltrx_test_reftree", "ltrx_test_bvh", "ltrx_test_bvh_entry", "ltrx_test_host_prepare",
                 "ltrx_test_rand_fill"]
 
 _lib = None
@@ -182,6 +182,7 @@ def lib() -> C.CDLL:
     L.ltrx_GetError.restype = C.c_char_p
     L.ltrx_GetError.argtypes = [vp]
     L.ltrx_Prepare.argtypes = [vp]
+    L.ltrx_test_host_prepare.argtypes = [vp, C.c_void_p]
     L.ltrx_BakeResident.argtypes = [vp, C.POINTER(C.c_float)]
     L.ltrx_Finish.argtypes = [vp]
     L.ltrx_SetDebug.argtypes = [vp, C.c_int]
@@ -341,6 +342,14 @@ class BakeHandle:
         err = self.L.ltrx_GetError(self.h)
         if err:
             raise RuntimeError("bake failed: " + err.decode())
+
+    def host_prepare_fingerprints(self) -> list:
+        """Host-only: run the host pre-pass (no device needed) and return FNV-1a fingerprints of the arrays it would upload."""
+        out = (C.c_uint64 * 12)()
+        if not self.L.ltrx_test_host_prepare(self.h, out):
+            self._raise_on_error()
+            raise RuntimeError("ltrx_test_host_prepare failed")
+        return [int(x) for x in out]
 
     def prepare(self):
         if not self.L.ltrx_Prepare(self.h):

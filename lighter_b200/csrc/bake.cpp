@@ -233,9 +233,10 @@ void host_prepare(ltr_Scene *S)
     double tt = now_s();
     auto lap = [&](const char *what) { if (trace) { double t = now_s(); fprintf(stderr, "[ltr host] accel %-28s %8.2f ms\n", what, (t - tt) * 1e3); tt = t; } };
     /* per instance: useful triangles of shadow-casting parts (phase 1), then -- concurrently -- the flat scene BVH
-     * over all of them on a background thread and the per-instance reference-order trees on this one */
-    std::vector<std::vector<float>> itris(ni);
-    std::vector<std::vector<Box3>> iboxes(ni);
+     * over all of them on a background thread and the per-instance reference-order trees on this one.
+     * The triangles of ALL instances are written once, instance after instance, straight into B.rtree_tris (the array the
+     * reference-order trees index); the scene BVH is built over the same memory when every instance casts shadows (the
+     * usual case), over a compacted copy otherwise. */
     std::vector<RefTree> itree(ni);
     auto parallel_instances = [&](const std::function<void(size_t)> &fn) {
         unsigned nthreads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)ni));
@@ -245,42 +246,63 @@ void host_prepare(ltr_Scene *S)
             pool.emplace_back([&]() { for (size_t i; (i = next.fetch_add(1)) < ni;) fn(i); });
         for (auto &th : pool) th.join();
     };
-    parallel_instances([&](size_t i) {
-        if (i == 0) return;
+    /* visits the useful triangles of instance i in part / index order (ref: lighter.cpp:349-384: parts with shadow == 0 and
+     * triangles whose cross product is near zero are dropped) */
+    auto for_useful_tris = [&](size_t i, auto &&emit) {
         MeshInstance *mi = S->instances[i];
         ltr_Mesh *mesh = mi->mesh;
-        std::vector<float> &T = itris[i];
-        std::vector<Box3> &boxes = iboxes[i];
         const V3 *wp = B.wpos.data() + vbase[i];
-        size_t cap = 0;
-        for (const MeshPart &mp : mesh->parts) if (mp.shadow) cap += mp.index_count / 3;
-        T.reserve(cap * 9); boxes.reserve(cap);
         for (const MeshPart &mp : mesh->parts) {
             if (!mp.shadow) continue;
             const V3 *vb = wp + mp.vertex_offset;
             const u32 *ib = mesh->indices.data() + mp.index_offset;
             for (u32 t = 0; t + 2 < mp.index_count; t += 3) {
-                V3 p1 = vb[ib[t]], p2 = vb[ib[t + 1]], p3 = vb[ib[t + 2]];
+                const V3 p1 = vb[ib[t]], p2 = vb[ib[t + 1]], p3 = vb[ib[t + 2]];
                 if (near_zero3(cross3(p2 - p1, p3 - p1))) continue;
-                const float f[9] = { p1.x, p1.y, p1.z, p2.x, p2.y, p2.z, p3.x, p3.y, p3.z };
-                T.insert(T.end(), f, f + 9);
-                Box3 b = { min3(p1, min3(p2, p3)), max3(p1, max3(p2, p3)) };
-                boxes.push_back(b);
+                emit(p1, p2, p3);
             }
         }
-    });
-    std::vector<size_t> o_stri(ni + 1, 0);
-    for (size_t i = 0; i < ni; ++i) o_stri[i + 1] = o_stri[i] + ((i && S->instances[i]->shadow) ? itris[i].size() / 9 : 0);
-    BigVec<float> scene_tris(o_stri[ni] * 9);
+    };
+    std::vector<size_t> n_itris(ni, 0), o_tri(ni + 1, 0);
     parallel_instances([&](size_t i) {
-        if (i && S->instances[i]->shadow && !itris[i].empty()) memcpy(&scene_tris[o_stri[i] * 9], itris[i].data(), itris[i].size() * 4);
+        if (i == 0) return;
+        size_t c = 0;
+        for_useful_tris(i, [&](const V3 &, const V3 &, const V3 &) { ++c; });
+        n_itris[i] = c;
     });
+    for (size_t i = 0; i < ni; ++i) o_tri[i + 1] = o_tri[i] + n_itris[i];
+    B.rtree_tris.resize(o_tri[ni] * 9);
+    BigVec<Box3> all_boxes(o_tri[ni]);
+    parallel_instances([&](size_t i) {
+        if (i == 0) return;
+        float *T = B.rtree_tris.data() + o_tri[i] * 9;
+        Box3 *bx = all_boxes.data() + o_tri[i];
+        for_useful_tris(i, [&](const V3 &p1, const V3 &p2, const V3 &p3) {
+            T[0] = p1.x; T[1] = p1.y; T[2] = p1.z; T[3] = p2.x; T[4] = p2.y; T[5] = p2.z; T[6] = p3.x; T[7] = p3.y; T[8] = p3.z;
+            T += 9;
+            bx->lo = min3(p1, min3(p2, p3)); bx->hi = max3(p1, max3(p2, p3));
+            ++bx;
+        });
+    });
+    /* the scene BVH covers the instances that cast shadows */
+    bool all_cast = true;
+    for (size_t i = 1; i < ni; ++i) if (n_itris[i] && !S->instances[i]->shadow) all_cast = false;
+    BigVec<float> scene_compact;
+    if (!all_cast) {
+        std::vector<size_t> o_stri(ni + 1, 0);
+        for (size_t i = 0; i < ni; ++i) o_stri[i + 1] = o_stri[i] + ((i && S->instances[i]->shadow) ? n_itris[i] : 0);
+        scene_compact.resize(o_stri[ni] * 9);
+        parallel_instances([&](size_t i) {
+            if (i && S->instances[i]->shadow && n_itris[i]) memcpy(&scene_compact[o_stri[i] * 9], &B.rtree_tris[o_tri[i] * 9], n_itris[i] * 36);
+        });
+    }
+    const float *scene_tris = all_cast ? B.rtree_tris.data() : scene_compact.data();
+    const size_t nst = all_cast ? o_tri[ni] : scene_compact.size() / 9;
     lap("world triangles");
     int leaf_max = BVH_LEAF_MAX;
     if (const char *e = getenv("LTR_BVH_LEAF")) leaf_max = atoi(e);
-    const size_t nst = scene_tris.size() / 9;
     std::thread bvh_thread([&]() {
-        build_scene_bvh(scene_tris.data(), nst, B.bvh, leaf_max, 0);
+        build_scene_bvh(scene_tris, nst, B.bvh, leaf_max, 0);
         /* triangles in BVH order */
         B.bvh_tris.resize(nst * 9);
         const unsigned T = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
@@ -292,7 +314,7 @@ void host_prepare(ltr_Scene *S)
         for (auto &th : pool) th.join();
     });
     struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } bvh_joiner{ bvh_thread };
-    parallel_instances([&](size_t i) { itree[i].build(i ? iboxes[i].data() : nullptr, i ? iboxes[i].size() : 0); });
+    parallel_instances([&](size_t i) { itree[i].build(i ? all_boxes.data() + o_tri[i] : nullptr, i ? n_itris[i] : 0); });
     lap("instance trees (threads)");
     S->completion.store(0.99f);
     /* instance tree over the root boxes (invalid boxes are dropped by the builder) */
@@ -305,7 +327,7 @@ void host_prepare(ltr_Scene *S)
      * instance copies its own slices (threads) -- at 1M triangles this is ~130 MB of host memory */
     uint64_t texel_off = 0;
     {
-        std::vector<size_t> o_node(ni + 1, 0), o_item(ni + 1, 0), o_tri(ni + 1, 0), o_rtri(ni + 1, 0);
+        std::vector<size_t> o_node(ni + 1, 0), o_item(ni + 1, 0), o_rtri(ni + 1, 0);     /* o_tri: the triangle offsets from above */
         for (size_t i = 0; i < ni; ++i) {
             ltrgpu_Inst &I = B.inst[i];
             MeshInstance *mi = S->instances[i];
@@ -313,20 +335,18 @@ void host_prepare(ltr_Scene *S)
             I.texel_off_lo = (uint32_t)texel_off; I.texel_off_hi = (uint32_t)(texel_off >> 32);
             texel_off += (uint64_t)I.lm_w * I.lm_h;
             I.node_off = (uint32_t)o_node[i]; I.item_off = (uint32_t)o_item[i]; I.tri_off = (uint32_t)o_tri[i];
-            I.tree_tris = (uint32_t)(itris[i].size() / 9);
+            I.tree_tris = (uint32_t)n_itris[i];
             I.shadow = (i && mi->shadow) ? 1 : 0;
             size_t nrt = 0;
             if (i) for (const MeshPart &mp : mi->mesh->parts) nrt += mp.index_count / 3;
             o_node[i + 1] = o_node[i] + itree[i].nodes.size();
             o_item[i + 1] = o_item[i] + itree[i].items.size();
-            o_tri[i + 1] = o_tri[i] + itris[i].size() / 9;
             o_rtri[i + 1] = o_rtri[i] + nrt;
         }
-        B.rnodes.resize(o_node[ni]); B.ritems.resize(o_item[ni]); B.rtree_tris.resize(o_tri[ni] * 9); B.rtris.resize(o_rtri[ni]);
+        B.rnodes.resize(o_node[ni]); B.ritems.resize(o_item[ni]); B.rtris.resize(o_rtri[ni]);      /* B.rtree_tris was filled in place above */
         auto copy_one = [&](size_t i) {
             if (!itree[i].nodes.empty()) memcpy(&B.rnodes[o_node[i]], itree[i].nodes.data(), itree[i].nodes.size() * sizeof(itree[i].nodes[0]));
             if (!itree[i].items.empty()) memcpy(&B.ritems[o_item[i]], itree[i].items.data(), itree[i].items.size() * sizeof(itree[i].items[0]));
-            if (!itris[i].empty()) memcpy(&B.rtree_tris[o_tri[i] * 9], itris[i].data(), itris[i].size() * 4);
             if (!i) return;
             MeshInstance *mi = S->instances[i];
             ltr_Mesh *mesh = mi->mesh;
@@ -785,6 +805,31 @@ int ltrx_Prepare(ltr_Scene *scene)
     int ok = guarded(scene, [&]() { host_prepare(scene); upload(scene); });
     scene->stage.store(ok ? "prepared" : nullptr);
     return ok;
+}
+
+/* host-only test hook: the host pre-pass alone (no device), fingerprints of everything it would upload */
+int ltrx_test_host_prepare(ltr_Scene *scene, uint64_t out_hash[12])
+{
+    if (scene->worker.joinable()) scene->worker.join();
+    if (!scene->bake) scene->bake = new Bake;
+    scene->error.clear();
+    int ok = guarded(scene, [&]() { host_prepare(scene); });
+    if (!ok) return 0;
+    const Bake &B = *scene->bake;
+    auto fnv = [](const void *p, size_t n) { uint64_t h = 1469598103934665603ull; const unsigned char *c = (const unsigned char *)p; for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 1099511628211ull; } return h; };
+    out_hash[0] = fnv(B.wpos.data(), B.wpos.size() * sizeof(V3));
+    out_hash[1] = fnv(B.wnrm.data(), B.wnrm.size() * sizeof(V3));
+    out_hash[2] = fnv(B.vtex.data(), B.vtex.size() * 4) ^ fnv(B.ltex.data(), B.ltex.size() * 4);
+    out_hash[3] = fnv(B.rtris.data(), B.rtris.size() * sizeof(B.rtris[0]));
+    out_hash[4] = fnv(B.rnodes.data(), B.rnodes.size() * sizeof(B.rnodes[0]));
+    out_hash[5] = fnv(B.ritems.data(), B.ritems.size() * 4);
+    out_hash[6] = fnv(B.rtree_tris.data(), B.rtree_tris.size() * 4);
+    out_hash[7] = fnv(B.bvh.nodes.data(), B.bvh.nodes.size() * sizeof(BvhNode));
+    out_hash[8] = fnv(B.bvh.nodes4.data(), B.bvh.nodes4.size() * sizeof(Bvh4Node));
+    out_hash[9] = fnv(B.bvh.order.data(), B.bvh.order.size() * 4);
+    out_hash[10] = fnv(B.bvh_tris.data(), B.bvh_tris.size() * 4);
+    out_hash[11] = fnv(B.inst.data(), B.inst.size() * sizeof(B.inst[0])) ^ fnv(B.light_inst.data(), B.light_inst.size());
+    return 1;
 }
 
 int ltrx_BakeResident(ltr_Scene *scene, float *gpu_ms_out)

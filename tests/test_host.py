@@ -117,6 +117,42 @@ def test_flat_bvh_invariants():
     assert b["ok"] and b["depth"] <= 20
 
 
+def _host_prepare_scenes():
+    from lighter_b200 import scenes
+    yield "basic", scenes.NAMED["basic"]()
+    yield "mesh2", scenes.NAMED["mesh2"]()
+    yield "rad1", scenes.NAMED["rad1"]()
+    yield "hugeoverlap", scenes.NAMED["hugeoverlap"]()
+    yield "config4_sibling", scenes.workload("config4_sibling")
+    sc = scenes.workload("config4_sibling")
+    for k, inst in enumerate(sc.instances):
+        if k % 2:
+            inst.shadow = 0                          # instances that do not cast shadows: the scene BVH gets a compacted copy
+    yield "sibling_noshadow_inst", sc
+    sc = scenes.NAMED["mesh2"]()
+    for m in sc.meshes:
+        for j, part in enumerate(m.parts):
+            if j % 2 == 0:
+                part.shadow = 0                      # parts that do not cast shadows never enter the triangle lists
+    yield "mesh2_noshadow_parts", sc
+
+
+def test_host_prepass_arrays_are_pinned():
+    """The host pre-pass (world transform, triangle lists, reference-order trees, raster list, scene BVH, instance table) runs
+    without a device; FNV-1a fingerprints of every array it would upload are pinned (tests/golden/host_prepare.json, generated
+    by this same hook before the pre-pass was reorganised around one shared triangle array), so host-side optimisation
+    cannot silently change what the GPU stages see."""
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "host_prepare.json")))
+    names = ["wpos", "wnrm", "tex", "rtris", "rnodes", "ritems", "rtree_tris", "bvh.nodes", "bvh.nodes4", "bvh.order", "bvh_tris", "inst+light_inst"]
+    for name, sc in _host_prepare_scenes():
+        with api.BakeHandle(sc) as h:
+            got = h.host_prepare_fingerprints()
+        diff = [names[i] for i in range(12) if hex(got[i]) != gold[name][i]]
+        assert not diff, (name, diff)
+
+
 def test_flat_bvh_does_not_depend_on_thread_count_or_page_size(monkeypatch):
     """The builder's cooperative top, its dynamically scheduled sub-trees, the SSE2 passes and the huge-page work arrays must
     not change the tree: the triangle order (which encodes every partition) is the same for 1, 3 and 8 threads, with and
