@@ -123,6 +123,17 @@ def test_bvh_entry(tris: np.ndarray, segs: np.ndarray, bundle_off: np.ndarray, l
                 mismatches=mm.value)
 
 
+def test_rad_cull(rowP, rowN, colP, colN):
+    """Host-only: the pair sweep's culling tests (csrc/rad_cull.h) for one block of row lumels against one block of column
+    lumels -> (block_ok, row_ok[nrows])."""
+    rowP, rowN, colP, colN = (np.ascontiguousarray(a, np.float32).reshape(-1, 3) for a in (rowP, rowN, colP, colN))
+    ok = C.c_int(0)
+    row_ok = np.zeros(len(rowP), np.uint8)
+    if not lib().ltrx_test_rad_cull(_fp(rowP), _fp(rowN), len(rowP), _fp(colP), _fp(colN), len(colP), C.byref(ok), row_ok.ctypes.data):
+        raise RuntimeError("ltrx_test_rad_cull: empty block")
+    return bool(ok.value), row_ok.astype(bool)
+
+
 class Links(C.Structure):
     _fields_ = [("rows", C.c_uint64), ("count", C.c_uint64), ("row_offset", C.POINTER(C.c_uint64)),
                 ("other", C.POINTER(u32)), ("factor", C.POINTER(C.c_float))]
@@ -136,7 +147,7 @@ LTRX_SYMBOLS = ["ltrx_Version", "ltrx_SetDevice", "ltrx_NcclUniqueId", "ltrx_Set
                 "ltrx_GetError", "ltrx_Prepare", "ltrx_BakeResident", "ltrx_Finish", "ltrx_SetDebug", "ltrx_GetLumels",
                 "ltrx_GetLinks", "ltrx_GetShadowFactors", "ltrx_SetShadowMode", "ltrx_GetShadowMasks", "ltrx_ShadowSampleSegment",
                 "ltrx_test_point_tri_distance", "ltrx_test_seg_tri",
-                "ltrx_test_scene_queries", "ltrx_test_march", "ltrx_test_spiral_dirs", "ltrx_test_reftree", "ltrx_test_bvh", "ltrx_test_bvh_entry", "ltrx_test_host_prepare",
+                "ltrx_test_scene_queries", "ltrx_test_march", "ltrx_test_spiral_dirs", "ltrx_test_reftree", "ltrx_test_bvh", "ltrx_test_bvh_entry", "ltrx_test_host_prepare", "ltrx_test_rad_cull",
                 "ltrx_test_rand_fill"]
 
 _lib = None
@@ -201,6 +212,7 @@ def lib() -> C.CDLL:
     L.ltrx_test_reftree.argtypes = [fp, u32, C.c_void_p, u32, C.c_void_p, u32, C.POINTER(u32), C.POINTER(u32)]
     L.ltrx_test_rand_fill.argtypes = [fp, C.c_uint64]
     L.ltrx_test_bvh.argtypes = [fp, u32, C.c_int, C.POINTER(u32), C.POINTER(u32), C.c_void_p, fp]
+    L.ltrx_test_rad_cull.argtypes = [fp, fp, u32, fp, fp, u32, C.POINTER(C.c_int), C.c_void_p]
     L.ltrx_test_bvh_entry.argtypes = [fp, u32, C.c_int, fp, C.c_void_p, u32, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                       C.POINTER(C.c_uint64), C.POINTER(u32)]
     _lib = L

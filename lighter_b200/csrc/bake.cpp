@@ -26,6 +26,7 @@
 
 #include "gpu.h"
 #include "bvh_entry.h"
+#include "rad_cull.h"
 #include "nccl_dl.h"
 #include "randfill.h"
 #include "scene.h"
@@ -805,6 +806,32 @@ int ltrx_Prepare(ltr_Scene *scene)
     int ok = guarded(scene, [&]() { host_prepare(scene); upload(scene); });
     scene->stage.store(ok ? "prepared" : nullptr);
     return ok;
+}
+
+/* host-only test hook: the culling tests of the radiosity pair sweep (rad_cull.h) on one block of row lumels against one block
+ * of column lumels -- bounds as rad_tile_bounds_kernel builds them (component-wise min / max of positions and normals).
+ * block_ok = tile_pair_may_link(rows, cols); row_ok[r] = row_group_may_link(row r, cols). */
+int ltrx_test_rad_cull(const float *rowP3, const float *rowN3, u32 nrows, const float *colP3, const float *colN3, u32 ncols, int *block_ok, uint8_t *row_ok)
+{
+    auto bounds = [](const float *P, const float *N, u32 n) {
+        float v[12];
+        for (int a = 0; a < 6; ++a) { v[a] = INFINITY; v[6 + a] = -INFINITY; }
+        for (u32 i = 0; i < n; ++i)
+            for (int a = 0; a < 3; ++a) {
+                v[a] = fminf(v[a], P[3 * i + a]); v[3 + a] = fminf(v[3 + a], N[3 * i + a]);
+                v[6 + a] = fmaxf(v[6 + a], P[3 * i + a]); v[9 + a] = fmaxf(v[9 + a], N[3 * i + a]);
+            }
+        TileBounds w;
+        w.plo = make_float4(v[0], v[1], v[2], 0.f); w.nlo = make_float4(v[3], v[4], v[5], 0.f);
+        w.phi = make_float4(v[6], v[7], v[8], 0.f); w.nhi = make_float4(v[9], v[10], v[11], 0.f);
+        return w;
+    };
+    if (!nrows || !ncols) return 0;
+    const TileBounds R = bounds(rowP3, rowN3, nrows), Cb = bounds(colP3, colN3, ncols);
+    *block_ok = tile_pair_may_link(R, Cb) ? 1 : 0;
+    for (u32 r = 0; r < nrows; ++r)
+        row_ok[r] = row_group_may_link(mk3(rowP3[3 * r], rowP3[3 * r + 1], rowP3[3 * r + 2]), mk3(rowN3[3 * r], rowN3[3 * r + 1], rowN3[3 * r + 2]), Cb) ? 1 : 0;
+    return 1;
 }
 
 /* host-only test hook: the host pre-pass alone (no device), fingerprints of everything it would upload */

@@ -1,0 +1,56 @@
+/*
+ * rad_cull.h -- the conservative culling tests of the radiosity pair sweep (host + device).
+ *
+ * The reference tests every lumel pair (lighter.cpp:735-752: dotA = Ni.d, dotB = Nj.(-d), both > 0.001, factor
+ * dotA*dotB/(len^4*pi) >= 0.001).  The sweep (gpu_radiosity.cu) skips whole blocks of pairs when interval bounds prove that
+ * no pair of the block can pass; these tests must never reject a block that holds a linking pair.  They are shared with the
+ * host so that tests/test_host.py can check exactly that against the oracle's pair criterion, without a GPU.
+ */
+#pragma once
+#include <vector_types.h>
+#include <vector_functions.h>    /* make_float4 on the host */
+#include "vmath.h"
+
+#define RAD_CUTOFF 17.85f       /* > sqrt(1/(0.001*pi)) = 17.8412; conservative */
+#define RAD_SKIP_BELOW 0.0009f  /* interval bounds below this cannot reach the 0.001 thresholds even with rounding */
+
+struct TileBounds { float4 plo, phi, nlo, nhi; };      /* 64 bytes: position box, normal-component box */
+
+/* max over n in [nl,nh], d in [dl,dh] of n*d (one axis) */
+LB_HD float imax_prod(float nl, float nh, float dl, float dh)
+{
+    return fmaxf(fmaxf(nl * dl, nl * dh), fmaxf(nh * dl, nh * dh));
+}
+
+/* can any lumel pair of the two tiles link?  Conservative (never rejects a linking pair). */
+LB_HD bool tile_pair_may_link(const TileBounds &R, const TileBounds &C)
+{
+    /* d = P_c - P_r per axis */
+    const float dlx = C.plo.x - R.phi.x, dhx = C.phi.x - R.plo.x;
+    const float dly = C.plo.y - R.phi.y, dhy = C.phi.y - R.plo.y;
+    const float dlz = C.plo.z - R.phi.z, dhz = C.phi.z - R.plo.z;
+    const float gx = fmaxf(fmaxf(dlx, -dhx), 0.f), gy = fmaxf(fmaxf(dly, -dhy), 0.f), gz = fmaxf(fmaxf(dlz, -dhz), 0.f);
+    const float min_len2 = gx * gx + gy * gy + gz * gz;
+    if (!(min_len2 <= RAD_CUTOFF * RAD_CUTOFF)) return false;         /* also rejects padding tiles (inf/nan) */
+    const float maxA = imax_prod(R.nlo.x, R.nhi.x, dlx, dhx) + imax_prod(R.nlo.y, R.nhi.y, dly, dhy) + imax_prod(R.nlo.z, R.nhi.z, dlz, dhz);
+    const float maxB = imax_prod(C.nlo.x, C.nhi.x, -dhx, -dlx) + imax_prod(C.nlo.y, C.nhi.y, -dhy, -dly) + imax_prod(C.nlo.z, C.nhi.z, -dhz, -dlz);
+    if (maxA < RAD_SKIP_BELOW || maxB < RAD_SKIP_BELOW) return false;
+    if (min_len2 > 0.f && maxA * maxB < RAD_SKIP_BELOW * 3.14159265f * min_len2 * min_len2) return false;
+    return true;
+}
+
+/* can row lumel (P, N) link with any lumel of the group bounded by C?  Conservative, like tile_pair_may_link: the maximum of
+ * the row's linear form N.(c - P) over the group's position box is exact; the group's side uses interval products. */
+LB_HD bool row_group_may_link(const V3 &P, const V3 &N, const TileBounds &C)
+{
+    const float lx = C.plo.x - P.x, hx = C.phi.x - P.x, ly = C.plo.y - P.y, hy = C.phi.y - P.y, lz = C.plo.z - P.z, hz = C.phi.z - P.z;   /* d = c - P per axis */
+    const float gx = fmaxf(fmaxf(lx, -hx), 0.f), gy = fmaxf(fmaxf(ly, -hy), 0.f), gz = fmaxf(fmaxf(lz, -hz), 0.f);
+    const float min_len2 = gx * gx + gy * gy + gz * gz;
+    if (!(min_len2 <= RAD_CUTOFF * RAD_CUTOFF)) return false;
+    const float maxA = fmaxf(N.x * lx, N.x * hx) + fmaxf(N.y * ly, N.y * hy) + fmaxf(N.z * lz, N.z * hz);
+    const float maxB = imax_prod(C.nlo.x, C.nhi.x, -hx, -lx) + imax_prod(C.nlo.y, C.nhi.y, -hy, -ly) + imax_prod(C.nlo.z, C.nhi.z, -hz, -lz);
+    if (maxA < RAD_SKIP_BELOW || maxB < RAD_SKIP_BELOW) return false;
+    if (min_len2 > 0.f && maxA * maxB < RAD_SKIP_BELOW * 3.14159265f * min_len2 * min_len2) return false;
+    return true;
+}
+

@@ -117,6 +117,68 @@ def test_flat_bvh_invariants():
     assert b["ok"] and b["depth"] <= 20
 
 
+def _pair_links(Pr, Nr, Pc, Nc):
+    """The reference's pair criterion in its float32 operation order (lighter.cpp:735-750): dotA = Ni.d, dotB = Nj.(-d) with
+    d = Pj - Pi, both > 0.001, factor dotA*dotB/(len^4*pi) >= 0.001.  Returns the (rows, cols) matrix of passing pairs."""
+    f = np.float32
+    d = (Pc[None, :, :] - Pr[:, None, :]).astype(f)
+    dot = lambda a, b: ((a[..., 0] * b[..., 0]).astype(f) + (a[..., 1] * b[..., 1]).astype(f)).astype(f) + (a[..., 2] * b[..., 2]).astype(f)
+    dA = dot(np.broadcast_to(Nr[:, None, :], d.shape), d).astype(f)
+    dB = dot(np.broadcast_to(Nc[None, :, :], d.shape), (-d).astype(f)).astype(f)
+    l2 = dot(d, d).astype(f)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        fac = ((dA * dB).astype(f) / ((l2 * l2).astype(f) * f(3.14159274101257324)).astype(f)).astype(f)
+    return (dA > f(0.001)) & (dB > f(0.001)) & ~(fac < f(0.001))
+
+
+def test_radiosity_culling_never_rejects_a_linking_pair(oracle):
+    """csrc/rad_cull.h (shared by the pair-sweep kernel and this host hook): the tile x tile interval test and the per-row
+    group test may only skip blocks in which NO pair passes the reference's pair criterion.  Blocks are drawn around the
+    thresholds: grazing normals, distances around the 17.84-unit cut-off, facing / averted / coplanar patches, large
+    coordinates.  The numpy criterion used as truth is itself anchored to the oracle's candidate count."""
+    rng = np.random.default_rng(23)
+
+    def unit(v):
+        return (v / np.linalg.norm(v, axis=-1, keepdims=True)).astype(np.float32)
+
+    # anchor: candidates of a random point set, numpy criterion vs the oracle's own count (no triangles: nothing is blocked)
+    P = rng.uniform(-3, 3, (160, 3)).astype(np.float32)
+    N = unit(rng.normal(size=(160, 3)))
+    m = _pair_links(P, N, P, N)
+    n_np = int(np.triu(m, 1).sum())
+    _, _, _, pairs, segs = oracle.rad_links(np.zeros((0, 9), np.float32), P, N)
+    assert pairs == 160 * 159 // 2 and segs == n_np and n_np > 100
+
+    linking_blocks = culled_blocks = 0
+    for trial in range(1500):
+        nr, nc = int(rng.choice([1, 8, 32])), int(rng.choice([4, 8, 128]))
+        off = rng.choice([0.0, 50.0, 390.0]) * rng.uniform(-1, 1, 3)
+        cr = off + rng.uniform(-1, 1, 3)
+        kind = trial % 5
+        dist = [rng.uniform(0.05, 2.0), rng.uniform(2.0, 12.0), rng.uniform(17.0, 18.5), rng.uniform(0.3, 6.0), rng.uniform(18.0, 30.0)][kind]
+        dirv = unit(rng.normal(size=3))
+        cc = cr + dirv * dist
+        Pr = (cr + rng.normal(size=(nr, 3)) * rng.choice([0.02, 0.2, 0.8])).astype(np.float32)
+        Pc = (cc + rng.normal(size=(nc, 3)) * rng.choice([0.02, 0.2, 0.8])).astype(np.float32)
+        if kind == 3:                                # nearly coplanar patches with grazing normals (floor-to-floor pairs)
+            n0 = unit(np.cross(dirv, rng.normal(size=3)))
+            Nr = unit(n0 + rng.normal(size=(nr, 3)) * 0.02 + dirv * rng.uniform(-0.01, 0.02))
+            Nc = unit(n0 + rng.normal(size=(nc, 3)) * 0.02 - dirv * rng.uniform(-0.01, 0.02))
+        else:                                        # facing each other, with a random spread
+            spread = rng.choice([0.0, 0.3, 1.5])
+            Nr = unit(dirv + rng.normal(size=(nr, 3)) * spread)
+            Nc = unit(-dirv + rng.normal(size=(nc, 3)) * spread)
+        truth = _pair_links(Pr, Nr, Pc, Nc)
+        block_ok, row_ok = api.test_rad_cull(Pr, Nr, Pc, Nc)
+        if truth.any():
+            linking_blocks += 1
+            assert block_ok, (trial, kind)
+        else:
+            culled_blocks += not block_ok
+        assert (row_ok | ~truth.any(1)).all(), (trial, kind)
+    assert linking_blocks > 300 and culled_blocks > 100, (linking_blocks, culled_blocks)
+
+
 def _host_prepare_scenes():
     from lighter_b200 import scenes
     yield "basic", scenes.NAMED["basic"]()
