@@ -121,7 +121,7 @@ LTRAPI int ltrx_test_rand_fill(float *out, uint64_t n);
 LTRAPI int ltrx_test_bvh(const float *tris9, u32 ntris, int leaf_max, u32 *n_nodes, u32 *depth, u32 *order_out, float *bounds6);
 /* host-only: the conservative culling tests of the radiosity pair sweep (csrc/rad_cull.h) on one row block x one column block */
 LTRAPI int ltrx_test_rad_cull(const float *rowP3, const float *rowN3, u32 nrows, const float *colP3, const float *colN3, u32 ncols,
-                              int *block_ok, uint8_t *row_ok);
+                              int *block_ok, uint8_t *row_ok, uint8_t *pair_fast /* nrows*ncols or NULL */);
 /* host-only: the host pre-pass of a scene without a device; FNV-1a fingerprints of the arrays it would upload */
 LTRAPI int ltrx_test_host_prepare(ltr_Scene *scene, uint64_t out_hash[12]);
 /* host-only: entry sets of segment bundles (csrc/bvh_entry.h) -- reachability self-check, root walk vs entry walk */

@@ -125,13 +125,14 @@ def test_bvh_entry(tris: np.ndarray, segs: np.ndarray, bundle_off: np.ndarray, l
 
 def test_rad_cull(rowP, rowN, colP, colN):
     """Host-only: the pair sweep's culling tests (csrc/rad_cull.h) for one block of row lumels against one block of column
-    lumels -> (block_ok, row_ok[nrows])."""
+    lumels -> (block_ok, row_ok[nrows], pair_fast[nrows, ncols])."""
     rowP, rowN, colP, colN = (np.ascontiguousarray(a, np.float32).reshape(-1, 3) for a in (rowP, rowN, colP, colN))
     ok = C.c_int(0)
     row_ok = np.zeros(len(rowP), np.uint8)
-    if not lib().ltrx_test_rad_cull(_fp(rowP), _fp(rowN), len(rowP), _fp(colP), _fp(colN), len(colP), C.byref(ok), row_ok.ctypes.data):
+    fast = np.zeros((len(rowP), len(colP)), np.uint8)
+    if not lib().ltrx_test_rad_cull(_fp(rowP), _fp(rowN), len(rowP), _fp(colP), _fp(colN), len(colP), C.byref(ok), row_ok.ctypes.data, fast.ctypes.data):
         raise RuntimeError("ltrx_test_rad_cull: empty block")
-    return bool(ok.value), row_ok.astype(bool)
+    return bool(ok.value), row_ok.astype(bool), fast.astype(bool)
 
 
 class Links(C.Structure):
@@ -212,7 +213,7 @@ def lib() -> C.CDLL:
     L.ltrx_test_reftree.argtypes = [fp, u32, C.c_void_p, u32, C.c_void_p, u32, C.POINTER(u32), C.POINTER(u32)]
     L.ltrx_test_rand_fill.argtypes = [fp, C.c_uint64]
     L.ltrx_test_bvh.argtypes = [fp, u32, C.c_int, C.POINTER(u32), C.POINTER(u32), C.c_void_p, fp]
-    L.ltrx_test_rad_cull.argtypes = [fp, fp, u32, fp, fp, u32, C.POINTER(C.c_int), C.c_void_p]
+    L.ltrx_test_rad_cull.argtypes = [fp, fp, u32, fp, fp, u32, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
     L.ltrx_test_bvh_entry.argtypes = [fp, u32, C.c_int, fp, C.c_void_p, u32, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                       C.POINTER(C.c_uint64), C.POINTER(u32)]
     _lib = L

@@ -810,8 +810,10 @@ int ltrx_Prepare(ltr_Scene *scene)
 
 /* host-only test hook: the culling tests of the radiosity pair sweep (rad_cull.h) on one block of row lumels against one block
  * of column lumels -- bounds as rad_tile_bounds_kernel builds them (component-wise min / max of positions and normals).
- * block_ok = tile_pair_may_link(rows, cols); row_ok[r] = row_group_may_link(row r, cols). */
-int ltrx_test_rad_cull(const float *rowP3, const float *rowN3, u32 nrows, const float *colP3, const float *colN3, u32 ncols, int *block_ok, uint8_t *row_ok)
+ * block_ok = tile_pair_may_link(rows, cols); row_ok[r] = row_group_may_link(row r, cols); pair_fast[r * ncols + c] (optional) =
+ * the lock-step FMA pre-filter of the pair. */
+int ltrx_test_rad_cull(const float *rowP3, const float *rowN3, u32 nrows, const float *colP3, const float *colN3, u32 ncols, int *block_ok, uint8_t *row_ok,
+                       uint8_t *pair_fast)
 {
     auto bounds = [](const float *P, const float *N, u32 n) {
         float v[12];
@@ -831,6 +833,12 @@ int ltrx_test_rad_cull(const float *rowP3, const float *rowN3, u32 nrows, const 
     *block_ok = tile_pair_may_link(R, Cb) ? 1 : 0;
     for (u32 r = 0; r < nrows; ++r)
         row_ok[r] = row_group_may_link(mk3(rowP3[3 * r], rowP3[3 * r + 1], rowP3[3 * r + 2]), mk3(rowN3[3 * r], rowN3[3 * r + 1], rowN3[3 * r + 2]), Cb) ? 1 : 0;
+    if (pair_fast)
+        for (u32 r = 0; r < nrows; ++r)
+            for (u32 c = 0; c < ncols; ++c)
+                pair_fast[(size_t)r * ncols + c] = rad_fast_filter(mk3(rowP3[3 * r], rowP3[3 * r + 1], rowP3[3 * r + 2]), mk3(rowN3[3 * r], rowN3[3 * r + 1], rowN3[3 * r + 2]),
+                                                                   make_float4(colP3[3 * c], colP3[3 * c + 1], colP3[3 * c + 2], 0.f),
+                                                                   make_float4(colN3[3 * c], colN3[3 * c + 1], colN3[3 * c + 2], 0.f)) ? 1 : 0;
     return 1;
 }
 

@@ -263,14 +263,7 @@ __device__ __forceinline__ void rad_sweep_tile(const RadColBuf<G> &B, const Tile
 #pragma unroll
             for (unsigned q = 0; q < (unsigned)CH; ++q) {
                 const float4 pj = B.sp[kb + q], nj = B.sn[kb + q];
-                const float dx = pj.x - Pr.x, dy = pj.y - Pr.y, dz = pj.z - Pr.z;
-                /* fast filter: an FMA dot differs from the reference's mul/add dot by < 1e-5 for any pair close
-                 * enough to link (|d| <= 17.85), and the factor inequality dr*dj >= 0.001*pi*len^4 is evaluated
-                 * with relative error ~1e-6: with every threshold lowered by 10 % no linking pair is lost */
-                const float drf = __fmaf_rn(Nr.z, dz, __fmaf_rn(Nr.y, dy, Nr.x * dx));
-                const float djf = -__fmaf_rn(nj.z, dz, __fmaf_rn(nj.y, dy, nj.x * dx));
-                const float l2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-                if (fminf(drf, djf) > RAD_SKIP_BELOW && drf * djf >= (RAD_SKIP_BELOW * 3.14159265f) * (l2 * l2)) bits |= 1u << q;
+                if (rad_fast_filter(Pr, Nr, pj, nj)) bits |= 1u << q;
             }
             if (__any_sync(0xffffffffu, bits != 0)) {
                 /* compaction: exclusive scan of the per-lane survivor counts, then every lane appends its own */

@@ -54,3 +54,23 @@ LB_HD bool row_group_may_link(const V3 &P, const V3 &N, const TileBounds &C)
     return true;
 }
 
+
+/* lumel x lumel fast filter of the sweep's lock-step phase: an FMA dot differs from the reference's mul/add dot by < 1e-5 for
+ * any pair close enough to link (|d| <= 17.85), and the factor inequality dr*dj >= 0.001*pi*len^4 is evaluated with relative
+ * error ~1e-6: with every threshold lowered by 10 % no linking pair is lost.  Survivors are re-evaluated exactly. */
+LB_HD float rad_fma(float a, float b, float c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
+LB_HD bool rad_fast_filter(const V3 &Pr, const V3 &Nr, const float4 &pj, const float4 &nj)
+{
+    const float dx = pj.x - Pr.x, dy = pj.y - Pr.y, dz = pj.z - Pr.z;
+    const float drf = rad_fma(Nr.z, dz, rad_fma(Nr.y, dy, Nr.x * dx));
+    const float djf = -rad_fma(nj.z, dz, rad_fma(nj.y, dy, nj.x * dx));
+    const float l2 = rad_fma(dz, dz, rad_fma(dy, dy, dx * dx));
+    return fminf(drf, djf) > RAD_SKIP_BELOW && drf * djf >= (RAD_SKIP_BELOW * 3.14159265f) * (l2 * l2);
+}

@@ -133,7 +133,8 @@ def _pair_links(Pr, Nr, Pc, Nc):
 
 def test_radiosity_culling_never_rejects_a_linking_pair(oracle):
     """csrc/rad_cull.h (shared by the pair-sweep kernel and this host hook): the tile x tile interval test and the per-row
-    group test may only skip blocks in which NO pair passes the reference's pair criterion.  Blocks are drawn around the
+    group test may only skip blocks in which NO pair passes the reference's pair criterion, and the FMA pre-filter may only drop
+    pairs that fail it.  Blocks are drawn around the
     thresholds: grazing normals, distances around the 17.84-unit cut-off, facing / averted / coplanar patches, large
     coordinates.  The numpy criterion used as truth is itself anchored to the oracle's candidate count."""
     rng = np.random.default_rng(23)
@@ -149,7 +150,7 @@ def test_radiosity_culling_never_rejects_a_linking_pair(oracle):
     _, _, _, pairs, segs = oracle.rad_links(np.zeros((0, 9), np.float32), P, N)
     assert pairs == 160 * 159 // 2 and segs == n_np and n_np > 100
 
-    linking_blocks = culled_blocks = 0
+    linking_blocks = culled_blocks = n_fast = n_truth = 0
     for trial in range(1500):
         nr, nc = int(rng.choice([1, 8, 32])), int(rng.choice([4, 8, 128]))
         off = rng.choice([0.0, 50.0, 390.0]) * rng.uniform(-1, 1, 3)
@@ -169,7 +170,9 @@ def test_radiosity_culling_never_rejects_a_linking_pair(oracle):
             Nr = unit(dirv + rng.normal(size=(nr, 3)) * spread)
             Nc = unit(-dirv + rng.normal(size=(nc, 3)) * spread)
         truth = _pair_links(Pr, Nr, Pc, Nc)
-        block_ok, row_ok = api.test_rad_cull(Pr, Nr, Pc, Nc)
+        block_ok, row_ok, fast = api.test_rad_cull(Pr, Nr, Pc, Nc)
+        assert (fast | ~truth).all(), (trial, kind)            # the lock-step FMA pre-filter keeps every linking pair
+        n_fast += int(fast.sum()); n_truth += int(truth.sum())
         if truth.any():
             linking_blocks += 1
             assert block_ok, (trial, kind)
@@ -177,6 +180,7 @@ def test_radiosity_culling_never_rejects_a_linking_pair(oracle):
             culled_blocks += not block_ok
         assert (row_ok | ~truth.any(1)).all(), (trial, kind)
     assert linking_blocks > 300 and culled_blocks > 100, (linking_blocks, culled_blocks)
+    assert n_truth > 10000 and n_fast < 1.5 * n_truth, (n_fast, n_truth)      # ... and is not vacuous: few extra survivors
 
 
 def _host_prepare_scenes():
