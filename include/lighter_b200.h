@@ -119,6 +119,9 @@ LTRAPI int ltrx_test_reftree(const float *tris9, u32 ntris, void *nodes_out, u32
  * when the lock-free table-level path was used, 0 for the plain rand() loop -- same values, same libc state afterwards */
 LTRAPI int ltrx_test_rand_fill(float *out, uint64_t n);
 LTRAPI int ltrx_test_bvh(const float *tris9, u32 ntris, int leaf_max, u32 *n_nodes, u32 *depth, u32 *order_out, float *bounds6);
+/* host-only: per-segment cost (4-wide node reads, triangle tests) of the walk from the bundle's entry set */
+LTRAPI int ltrx_test_bvh_entry_cost(const float *tris9, u32 ntris, int leaf_max, const float *segs6, const u32 *bundle_off, u32 n_bundles,
+                                    uint32_t *nodes_out, uint32_t *tris_out);
 /* host-only: the conservative culling tests of the radiosity pair sweep (csrc/rad_cull.h) on one row block x one column block */
 LTRAPI int ltrx_test_rad_cull(const float *rowP3, const float *rowN3, u32 nrows, const float *colP3, const float *colN3, u32 ncols,
                               int *block_ok, uint8_t *row_ok, uint8_t *pair_fast /* nrows*ncols or NULL */);

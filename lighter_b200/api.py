@@ -123,6 +123,17 @@ def test_bvh_entry(tris: np.ndarray, segs: np.ndarray, bundle_off: np.ndarray, l
                 mismatches=mm.value)
 
 
+def test_bvh_entry_cost(tris: np.ndarray, segs: np.ndarray, bundle_off: np.ndarray, leaf_max: int = 2):
+    """Host-only: per-segment (4-wide node reads, triangle tests) of the any-hit walk from each bundle's entry set."""
+    tris = np.ascontiguousarray(tris, np.float32)
+    segs = np.ascontiguousarray(segs, np.float32).reshape(-1, 6)
+    off = np.ascontiguousarray(bundle_off, np.uint32)
+    nodes, tests = np.zeros(len(segs), np.uint32), np.zeros(len(segs), np.uint32)
+    if not lib().ltrx_test_bvh_entry_cost(_fp(tris), len(tris), leaf_max, _fp(segs), off.ctypes.data, len(off) - 1, nodes.ctypes.data, tests.ctypes.data):
+        raise RuntimeError("ltrx_test_bvh_entry_cost failed")
+    return nodes, tests
+
+
 def test_rad_cull(rowP, rowN, colP, colN):
     """Host-only: the pair sweep's culling tests (csrc/rad_cull.h) for one block of row lumels against one block of column
     lumels -> (block_ok, row_ok[nrows], pair_fast[nrows, ncols])."""
@@ -148,7 +159,7 @@ LTRX_SYMBOLS = ["ltrx_Version", "ltrx_SetDevice", "ltrx_NcclUniqueId", "ltrx_Set
                 "ltrx_GetError", "ltrx_Prepare", "ltrx_BakeResident", "ltrx_Finish", "ltrx_SetDebug", "ltrx_GetLumels",
                 "ltrx_GetLinks", "ltrx_GetShadowFactors", "ltrx_SetShadowMode", "ltrx_GetShadowMasks", "ltrx_ShadowSampleSegment",
                 "ltrx_test_point_tri_distance", "ltrx_test_seg_tri",
-                "ltrx_test_scene_queries", "ltrx_test_march", "ltrx_test_spiral_dirs", "ltrx_test_reftree", "ltrx_test_bvh", "ltrx_test_bvh_entry", "ltrx_test_host_prepare", "ltrx_test_rad_cull",
+                "ltrx_test_scene_queries", "ltrx_test_march", "ltrx_test_spiral_dirs", "ltrx_test_reftree", "ltrx_test_bvh", "ltrx_test_bvh_entry", "ltrx_test_bvh_entry_cost", "ltrx_test_host_prepare", "ltrx_test_rad_cull",
                 "ltrx_test_rand_fill"]
 
 _lib = None
@@ -213,6 +224,7 @@ def lib() -> C.CDLL:
     L.ltrx_test_reftree.argtypes = [fp, u32, C.c_void_p, u32, C.c_void_p, u32, C.POINTER(u32), C.POINTER(u32)]
     L.ltrx_test_rand_fill.argtypes = [fp, C.c_uint64]
     L.ltrx_test_bvh.argtypes = [fp, u32, C.c_int, C.POINTER(u32), C.POINTER(u32), C.c_void_p, fp]
+    L.ltrx_test_bvh_entry_cost.argtypes = [fp, u32, C.c_int, fp, C.c_void_p, u32, C.c_void_p, C.c_void_p]
     L.ltrx_test_rad_cull.argtypes = [fp, fp, u32, fp, fp, u32, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
     L.ltrx_test_bvh_entry.argtypes = [fp, u32, C.c_int, fp, C.c_void_p, u32, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                       C.POINTER(C.c_uint64), C.POINTER(u32)]

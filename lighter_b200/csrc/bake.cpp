@@ -962,6 +962,74 @@ static bool host_bvh4_anyhit(const SceneBvh &bvh, const std::vector<RayTri> &rt,
     return hit;
 }
 
+/* host model again, with a triangle-test counter (per-segment cost profile for tools/entry_estimate.py) */
+static void host_bvh4_cost(const SceneBvh &bvh, const std::vector<RayTri> &rt, V3 l1, V3 l2, std::vector<int32_t> &stack, uint32_t *nodes, uint32_t *tris)
+{
+    const V3 d = l2 - l1;
+    const float ix = d.x != 0 ? 1.0f / d.x : 1e30f, iy = d.y != 0 ? 1.0f / d.y : 1e30f, iz = d.z != 0 ? 1.0f / d.z : 1e30f;
+    bool hit = false;
+    while (!stack.empty() && !hit) {
+        const int32_t ni = stack.back(); stack.pop_back();
+        const Bvh4Node &n = bvh.nodes4[ni];
+        ++*nodes;
+        for (int c = 0; c < 4 && !hit; ++c) {
+            if (n.c[c] == BVH4_EMPTY) continue;
+            const float x0 = (n.lox[c] - l1.x) * ix, x1 = (n.hix[c] - l1.x) * ix, y0 = (n.loy[c] - l1.y) * iy, y1 = (n.hiy[c] - l1.y) * iy;
+            const float z0 = (n.loz[c] - l1.z) * iz, z1 = (n.hiz[c] - l1.z) * iz;
+            const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
+            const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));
+            if (!(t0 <= t1 + 2e-6f)) continue;
+            if (n.c[c] < 0) {
+                const uint32_t code = ~n.c[c];
+                for (uint32_t t = code >> 3; t < (code >> 3) + (code & 7u) && !hit; ++t) { ++*tris; hit = seg_tri_prepared(l1, d, rt[t]) < 1.0f; }
+            } else stack.push_back(n.c[c]);
+        }
+    }
+}
+
+/* host-only: per-segment cost of the entry walk (4-wide node reads, triangle tests until the first hit) for bundles of
+ * segments -- the input of the SIMT-efficiency estimate in tools/entry_estimate.py */
+int ltrx_test_bvh_entry_cost(const float *tris9, u32 ntris, int leaf_max, const float *segs6, const u32 *bundle_off, u32 n_bundles,
+                             uint32_t *nodes_out, uint32_t *tris_out)
+{
+    SceneBvh bvh;
+    build_scene_bvh(tris9, ntris, bvh, leaf_max, 0);
+    if (bvh.nodes4.empty()) return 0;
+    std::vector<RayTri> rt(ntris);
+    for (u32 t = 0; t < ntris; ++t) {
+        const float *v = tris9 + 9 * (size_t)bvh.order[t];
+        prepare_raytri(mk3(v[0], v[1], v[2]), mk3(v[3], v[4], v[5]), mk3(v[6], v[7], v[8]), rt[t]);
+    }
+    std::vector<int32_t> stack;
+    for (u32 b = 0; b < n_bundles; ++b) {
+        float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
+        for (u32 s = bundle_off[b]; s < bundle_off[b + 1]; ++s)
+            for (int e = 0; e < 2; ++e) {
+                const float *p = segs6 + 6 * (size_t)s + 3 * e;
+                lx = fminf(lx, p[0]); ly = fminf(ly, p[1]); lz = fminf(lz, p[2]); hx = fmaxf(hx, p[0]); hy = fmaxf(hy, p[1]); hz = fmaxf(hz, p[2]);
+            }
+        BvhEntrySet E;
+        E.n = 0;
+        if (lx <= hx) { bvh_entry_pad(lx, ly, lz, hx, hy, hz); bvh4_entry_search(bvh.nodes4.data(), lx, ly, lz, hx, hy, hz, E); }
+        for (u32 s = bundle_off[b]; s < bundle_off[b + 1]; ++s) {
+            const float *p = segs6 + 6 * (size_t)s;
+            const V3 A = mk3(p[0], p[1], p[2]), B = mk3(p[3], p[4], p[5]), d = B - A;
+            const float ix = d.x != 0 ? 1.0f / d.x : 1e30f, iy = d.y != 0 ? 1.0f / d.y : 1e30f, iz = d.z != 0 ? 1.0f / d.z : 1e30f;
+            stack.clear();
+            for (int i = 0; i < E.n; ++i) {
+                const float x0 = (E.lox[i] - A.x) * ix, x1 = (E.hix[i] - A.x) * ix, y0 = (E.loy[i] - A.y) * iy, y1 = (E.hiy[i] - A.y) * iy;
+                const float z0 = (E.loz[i] - A.z) * iz, z1 = (E.hiz[i] - A.z) * iz;
+                const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
+                const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));
+                if (t0 <= t1 + 2e-6f) stack.push_back(E.node[i]);
+            }
+            nodes_out[s] = 0; tris_out[s] = 0;
+            host_bvh4_cost(bvh, rt, A, B, stack, nodes_out + s, tris_out + s);
+        }
+    }
+    return 1;
+}
+
 /* host-only check of the entry sets (bvh_entry.h) on bundles of segments: per bundle the box of its segments is padded,
  * the entry set searched, and every segment walked twice -- from the root and from the entry set.  Returns 0 if any
  * triangle whose box overlaps a bundle box is unreachable from that bundle's entry set; *mismatches counts segments

@@ -97,6 +97,24 @@ def main():
     ns = len(segs)
     print("4-wide node reads per segment: root %.2f  entry %.2f (+ %.2f entry boxes)" % (r["visits_root"] / ns, r["visits_entry"] / ns, r["entry_tests"] / ns))
     print("entries per chunk: mean %.2f  hist %s" % (r["entries"].mean(), np.bincount(r["entries"], minlength=9)))
+    # SIMT waiting: a warp traces 32 consecutive segments of a chunk in lock step, so a batch costs what its slowest lane costs.
+    # Cost model per segment (instruction slots, from the ncu hot-line shares): 110 per node read, 70 per triangle test.
+    nodes, tests = api.test_bvh_entry_cost(tris, segs, np.array(offs, np.uint32), leaf_max=2)
+    cost = 110.0 * nodes + 70.0 * tests
+    lock = refill = useful = 0.0
+    for b in range(len(offs) - 1):
+        c = cost[offs[b]:offs[b + 1]]
+        useful += c.sum()
+        pad = (-len(c)) % 32
+        cb = np.concatenate([c, np.zeros(pad)]).reshape(-1, 32)
+        lock += cb.max(1).sum() * 32                      # every batch waits for its slowest lane
+        lanes = np.zeros(32)                              # lane refill: each lane takes the chunk's next segment when it is done
+        for x in c:
+            lanes[lanes.argmin()] += x
+        refill += lanes.max() * 32
+    print("walk cost per segment (model): %.0f slots; lock-step batches use %.0f %% of their lane slots, lane refill within a chunk %.0f %%"
+          % (useful / ns, 100 * useful / lock, 100 * useful / refill))
+    print("=> upper bound of the gain from lane refill on the traversal part: %.0f %%" % (100 * (1 - refill / lock)))
 
 
 if __name__ == "__main__":
