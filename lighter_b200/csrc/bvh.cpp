@@ -581,6 +581,7 @@ template <class T> struct HugeArray {
 void *lb_big_alloc(size_t n)
 {
     const bool no_huge = getenv("LTR_NO_HUGEPAGES") != nullptr;      /* read per call: tests flip it */
+    const bool poison = getenv("LTR_POISON_BIGALLOC") != nullptr;    /* tests: fresh pages are zero, which would hide an element nobody writes */
     void *q = nullptr;
     if (n >= (4u << 20) && !no_huge) {
         const size_t bytes = ((n + (2u << 20) - 1) >> 21) << 21;
@@ -588,11 +589,13 @@ void *lb_big_alloc(size_t n)
 #ifdef MADV_HUGEPAGE
             madvise(q, bytes, MADV_HUGEPAGE);
 #endif
+            if (poison) memset(q, 0xA5, bytes);
             return q;
         }
     }
     q = malloc(n ? n : 1);
     if (!q) { fprintf(stderr, "lighter_b200: out of host memory (%zu bytes)\n", n); abort(); }
+    if (poison) memset(q, 0xA5, n ? n : 1);
     return q;
 }
 

@@ -203,11 +203,15 @@ def _host_prepare_scenes():
     yield "mesh2_noshadow_parts", sc
 
 
-def test_host_prepass_arrays_are_pinned():
+@pytest.mark.parametrize("poison", [False, True])
+def test_host_prepass_arrays_are_pinned(poison, monkeypatch):
     """The host pre-pass (world transform, triangle lists, reference-order trees, raster list, scene BVH, instance table) runs
     without a device; FNV-1a fingerprints of every array it would upload are pinned (tests/golden/host_prepare.json, generated
     by this same hook before the pre-pass was reorganised around one shared triangle array), so host-side optimisation
-    cannot silently change what the GPU stages see."""
+    cannot silently change what the GPU stages see.  poison=True fills every default-initialised big array with a byte pattern
+    first (fresh pages are zero and would hide an element that nobody writes)."""
+    if poison:
+        monkeypatch.setenv("LTR_POISON_BIGALLOC", "1")
     import json
     import os
     gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "host_prepare.json")))
