@@ -110,6 +110,10 @@ LTRAPI int ltrx_test_scene_queries(const float *tris9, u32 ntris,
                                    int   *closest_tri_out);
 LTRAPI int ltrx_test_march(const float *tris9, u32 ntris, const float *from3, const float *to3,
                            const float *k, u32 n, float *out, u32 *steps_out);
+/* the scene BVH built on the device (csrc/gpu_bvh.cu) against the host builder (csrc/bvh.cpp) on the same triangles: sizes,
+ * inner levels, device build time (CUDA events) and the number of records that differ (0 for non-degenerate input) */
+LTRAPI int ltrx_test_device_bvh(const float *tris9, u32 ntris, int leaf_max, u32 *n_nodes, u32 *n_nodes4, int *height, float *build_ms,
+                                u32 *mismatch_nodes, u32 *mismatch_nodes4, u32 *mismatch_leaves, int *host_height);
 LTRAPI int ltrx_test_spiral_dirs(const float *nrm3, const float *randoff, u32 n, int samples, float *out3);
 /* host-only builders (no GPU): the reference-order tree (8 words per node: lo3, hi3, ch, ido; item stream
  * "<count> ids...") and the flat scene BVH with a structural self-check (returns 0 when it fails) */

@@ -159,7 +159,7 @@ LTRX_SYMBOLS = ["ltrx_Version", "ltrx_SetDevice", "ltrx_NcclUniqueId", "ltrx_Set
                 "ltrx_GetError", "ltrx_Prepare", "ltrx_BakeResident", "ltrx_Finish", "ltrx_SetDebug", "ltrx_GetLumels",
                 "ltrx_GetLinks", "ltrx_GetShadowFactors", "ltrx_SetShadowMode", "ltrx_GetShadowMasks", "ltrx_ShadowSampleSegment",
                 "ltrx_test_point_tri_distance", "ltrx_test_seg_tri",
-                "ltrx_test_scene_queries", "ltrx_test_march", "ltrx_test_spiral_dirs", "ltrx_test_reftree", "ltrx_test_bvh", "ltrx_test_bvh_entry", "ltrx_test_bvh_entry_cost", "ltrx_test_host_prepare", "ltrx_test_rad_cull",
+                "ltrx_test_scene_queries", "ltrx_test_device_bvh", "ltrx_test_march", "ltrx_test_spiral_dirs", "ltrx_test_reftree", "ltrx_test_bvh", "ltrx_test_bvh_entry", "ltrx_test_bvh_entry_cost", "ltrx_test_host_prepare", "ltrx_test_rad_cull",
                 "ltrx_test_rand_fill"]
 
 _lib = None
@@ -220,6 +220,7 @@ def lib() -> C.CDLL:
     L.ltrx_test_seg_tri.argtypes = [fp, fp, fp, u32, fp]
     L.ltrx_test_scene_queries.argtypes = [fp, u32, fp, fp, u32, fp, ip, fp, ip]
     L.ltrx_test_march.argtypes = [fp, u32, fp, fp, fp, u32, fp, C.POINTER(u32)]
+    L.ltrx_test_device_bvh.argtypes = [fp, u32, C.c_int, C.POINTER(u32), C.POINTER(u32), ip, fp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), ip]
     L.ltrx_test_spiral_dirs.argtypes = [fp, fp, u32, C.c_int, fp]
     L.ltrx_test_reftree.argtypes = [fp, u32, C.c_void_p, u32, C.c_void_p, u32, C.POINTER(u32), C.POINTER(u32)]
     L.ltrx_test_rand_fill.argtypes = [fp, C.c_uint64]
@@ -512,6 +513,18 @@ def test_scene_queries(tris: np.ndarray, a: np.ndarray, b: np.ndarray) -> dict:
                                          _fp(closest), ctri.ctypes.data_as(ip)):
         raise RuntimeError("ltrx_test_scene_queries failed (no CUDA device?)")
     return dict(dist=dist, anyhit=anyhit, closest=closest, closest_tri=ctri)
+
+
+def test_device_bvh(tris: np.ndarray, leaf_max: int = 2) -> dict:
+    """The scene BVH built on the device against the host builder on the same triangles (csrc/gpu_bvh.cu vs csrc/bvh.cpp)."""
+    tris = np.ascontiguousarray(tris, np.float32)
+    nn, nn4, mn, mn4, ml = u32(), u32(), u32(), u32(), u32()
+    h, hh, ms = C.c_int(), C.c_int(), C.c_float()
+    if not lib().ltrx_test_device_bvh(_fp(tris), len(tris), leaf_max, C.byref(nn), C.byref(nn4), C.byref(h), C.byref(ms), C.byref(mn), C.byref(mn4),
+                                      C.byref(ml), C.byref(hh)):
+        raise RuntimeError("ltrx_test_device_bvh failed (no CUDA device?)")
+    return dict(n_nodes=nn.value, n_nodes4=nn4.value, height=h.value, host_height=hh.value, build_ms=ms.value,
+                mismatch_nodes=mn.value, mismatch_nodes4=mn4.value, mismatch_leaves=ml.value)
 
 
 def test_march(tris: np.ndarray, frm: np.ndarray, to: np.ndarray, k: np.ndarray) -> tuple:

@@ -111,7 +111,11 @@ struct Bake {
     BigVec<int32_t> ritems;
     BigVec<float> rtree_tris;
     SceneBvh bvh;
-    BigVec<float> bvh_tris;
+    BigVec<float> bvh_tris;                   /* host-built tree: triangles in BVH order; device build: the compacted scene-order triangles (if not every instance casts) */
+    bool device_bvh = true;                   /* the scene BVH is built on the device (gpu_bvh.cu); false: bvh.cpp (LTR_BVH_HOST=1, tiny scenes, host-only test hooks) */
+    const float *scene_tris = nullptr;        /* device build: the triangles the tree is built over, scene order */
+    size_t n_scene_tris = 0;
+    int bvh_leaf_max = BVH_LEAF_MAX;
     std::vector<ltrgpu_Light> lights;
     std::vector<float> light_samples;         /* float4 per (light, sample): sampled-shadow extension table (host libm) */
     std::vector<uint8_t> light_inst;
@@ -160,7 +164,7 @@ void gpu_check(ltr_Scene *S, int rc, const char *what)
 /* ------------------------------------------------------------------------------------------
  * host pre-pass
  * ------------------------------------------------------------------------------------------ */
-void host_prepare(ltr_Scene *S)
+void host_prepare(ltr_Scene *S, bool force_host_bvh = false)
 {
     Bake &B = *S->bake;
     const ltr_Config &cfg = S->config;
@@ -171,8 +175,6 @@ void host_prepare(ltr_Scene *S)
     S->completion.store(0.f);
     B.inst.assign(ni, ltrgpu_Inst());
     std::vector<size_t> vbase(ni + 1, 0);
-    for (size_t i = 1; i < ni; ++i) vbase[i + 1] = vbase[i] + S->instances[i]->mesh->vpos.size();
-    vbase[1] = 0;
     for (size_t i = 1; i < ni; ++i) vbase[i + 1] = vbase[i] + S->instances[i]->mesh->vpos.size();
     const size_t nv = vbase[ni];
     B.wpos.resize(nv); B.wnrm.resize(nv); B.vtex.resize(nv * 2); B.ltex.resize(nv * 2);
@@ -302,7 +304,21 @@ void host_prepare(ltr_Scene *S)
     lap("world triangles");
     int leaf_max = BVH_LEAF_MAX;
     if (const char *e = getenv("LTR_BVH_LEAF")) leaf_max = atoi(e);
-    std::thread bvh_thread([&]() {
+    if (leaf_max < 1) leaf_max = 1;
+    if (leaf_max > 7) leaf_max = 7;
+    B.bvh_leaf_max = leaf_max;
+    /* The flat scene BVH is built on the device during upload() (gpu_bvh.cu: the same binned SAH, a few milliseconds instead
+     * of 70-100 ms of host threads, and nothing for the ranks of a multi-GPU bake to repeat on the same cores).  The host
+     * builder remains for scenes that fit one leaf, for the host-only test hooks and as an A/B switch (LTR_BVH_HOST=1). */
+    B.device_bvh = !force_host_bvh && !getenv("LTR_BVH_HOST") && nst > (size_t)leaf_max;
+    B.scene_tris = nullptr; B.n_scene_tris = 0;
+    std::thread bvh_thread;
+    if (B.device_bvh) {
+        B.bvh = SceneBvh();
+        if (all_cast) { B.bvh_tris.clear(); B.scene_tris = B.rtree_tris.data(); }
+        else { B.bvh_tris.swap(scene_compact); B.scene_tris = B.bvh_tris.data(); }
+        B.n_scene_tris = nst;
+    } else bvh_thread = std::thread([&]() {
         build_scene_bvh(scene_tris, nst, B.bvh, leaf_max, 0);
         /* triangles in BVH order */
         B.bvh_tris.resize(nst * 9);
@@ -371,7 +387,7 @@ void host_prepare(ltr_Scene *S)
     }
     lap("concatenate + raster list");
     /* flat scene BVH over the shadow-casting triangles: built in the background since the world triangles were ready */
-    bvh_thread.join();
+    if (bvh_thread.joinable()) bvh_thread.join();
     lap("scene BVH (overlapped) + reorder");
     /* lights and the light -> instance table */
     const size_t nl = S->lights.size();
@@ -470,9 +486,16 @@ void upload(ltr_Scene *S)
     d.n_rnodes = (uint32_t)B.rnodes.size(); d.rnodes = B.rnodes.data();
     d.n_ritems = (uint32_t)B.ritems.size(); d.ritems = B.ritems.data();
     d.n_rtree_tris = (uint32_t)(B.rtree_tris.size() / 9); d.rtree_tris9 = B.rtree_tris.data();
-    d.n_bvh_nodes = (uint32_t)B.bvh.nodes.size(); d.bvh = B.bvh.nodes.data();
-    d.n_bvh4_nodes = (uint32_t)B.bvh.nodes4.size(); d.bvh4 = B.bvh.nodes4.data();
-    d.n_tris = (uint32_t)(B.bvh_tris.size() / 9); d.tris9 = B.bvh_tris.data(); d.tri_orig = B.bvh.order.data();
+    d.bvh_leaf_max = B.bvh_leaf_max;
+    if (B.device_bvh) {
+        d.n_bvh_nodes = d.n_bvh4_nodes = 0; d.bvh = nullptr; d.bvh4 = nullptr; d.tri_orig = nullptr;
+        d.n_tris = (uint32_t)B.n_scene_tris; d.tris9 = B.scene_tris;
+    } else {
+        d.n_bvh_nodes = (uint32_t)B.bvh.nodes.size(); d.bvh = B.bvh.nodes.data();
+        d.n_bvh4_nodes = (uint32_t)B.bvh.nodes4.size(); d.bvh4 = B.bvh.nodes4.data();
+        d.n_tris = (uint32_t)(B.bvh_tris.size() / 9); d.tris9 = B.bvh_tris.data(); d.tri_orig = B.bvh.order.data();
+        d.bvh_height = B.bvh.depth;
+    }
     d.n_lights = (uint32_t)B.lights.size(); d.lights = B.lights.data(); d.light_inst = B.light_inst.data();
     d.n_light_samples = (uint32_t)(B.light_samples.size() / 4); d.light_samples4 = B.light_samples.data();
     d.n_probes = (uint32_t)ppos.size(); d.probe_pos = ppos.data(); d.probe_nrm = pnrm.data();
@@ -482,6 +505,12 @@ void upload(ltr_Scene *S)
     if (trace) fprintf(stderr, "[ltr host] upload context + descriptors      %8.2f ms\n", (now_s() - t0) * 1e3);
     double tu = now_s();
     gpu_check(S, ltrgpu_upload_scene(B.gpu, &d), "scene upload");
+    {
+        uint32_t nn = 0; int hh = 0; float bms = 0.f;
+        ltrgpu_bvh_info(B.gpu, &nn, &hh, &bms);
+        S->stats.n_bvh_nodes = nn;
+        if (trace) fprintf(stderr, "[ltr host] scene BVH: %u nodes, %d levels, %s %.2f ms\n", nn, hh, B.device_bvh ? "built on the device in" : "host-built, device time", bms);
+    }
     if (trace) fprintf(stderr, "[ltr host] upload scene arrays               %8.2f ms\n", (now_s() - tu) * 1e3);
 
     if (S->world > 1 && !B.comm) {
@@ -848,7 +877,7 @@ int ltrx_test_host_prepare(ltr_Scene *scene, uint64_t out_hash[12])
     if (scene->worker.joinable()) scene->worker.join();
     if (!scene->bake) scene->bake = new Bake;
     scene->error.clear();
-    int ok = guarded(scene, [&]() { host_prepare(scene); });
+    int ok = guarded(scene, [&]() { host_prepare(scene, /*force_host_bvh=*/true); });
     if (!ok) return 0;
     const Bake &B = *scene->bake;
     auto fnv = [](const void *p, size_t n) { uint64_t h = 1469598103934665603ull; const unsigned char *c = (const unsigned char *)p; for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 1099511628211ull; } return h; };

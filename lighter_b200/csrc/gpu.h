@@ -65,10 +65,14 @@ typedef struct ltrgpu_SceneDesc {
     uint32_t n_rnodes;        const RefNode *rnodes;
     uint32_t n_ritems;        const int32_t *ritems;
     uint32_t n_rtree_tris;    const float *rtree_tris9;
-    /* flat scene BVH over shadow-casting triangles, triangles already in BVH order */
+    /* flat scene BVH over shadow-casting triangles.
+     *   bvh != NULL: built on the host (bvh.cpp), tris9 already in BVH order, tri_orig = original index per slot;
+     *   bvh == NULL: tris9 is in SCENE order and the tree is built on the device (gpu_bvh.cu) with leaves of <= bvh_leaf_max
+     *                triangles; tris9 may alias rtree_tris9 (every instance casts shadows), then it is uploaded once. */
     uint32_t n_bvh_nodes;     const BvhNode *bvh;
     uint32_t n_bvh4_nodes;    const Bvh4Node *bvh4;            /* 4-wide collapse of the same tree (any-hit walks) */
     uint32_t n_tris;          const float *tris9; const uint32_t *tri_orig;
+    int bvh_leaf_max, bvh_height;                              /* bvh_height: inner levels of a host-built tree */
     /* lights + light->instance visibility table [n_lights][n_inst] */
     uint32_t n_lights;        const ltrgpu_Light *lights; const uint8_t *light_inst;
     uint32_t n_light_samples; const float *light_samples4;     /* sampled-shadow extension: float4 per (light, sample) */
@@ -107,6 +111,8 @@ void *ltrgpu_stream(ltrgpu_Ctx *ctx);
 void ltrgpu_release_memory(void);           /* return the caching allocator's idle device blocks to the driver */
 
 int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *desc);
+/* the scene BVH as resident on the device: binary node count, inner levels, device build time (0 = host-built) */
+int ltrgpu_bvh_info(ltrgpu_Ctx *ctx, uint32_t *n_nodes, int *height, float *build_ms);
 
 /* stage: lumel generation (raster -> ordered compaction -> concave-edge offset -> overlap correction).
  * inst_lumel_off receives n_inst+1 prefix offsets into the global lumel array (probes first). */

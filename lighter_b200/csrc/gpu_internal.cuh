@@ -31,6 +31,8 @@ struct ltrgpu_Ctx {
     /* ---- uploaded scene ---- */
     uint32_t n_inst = 0, n_verts = 0, n_rtris = 0, n_rnodes = 0, n_ritems = 0, n_rtree_tris = 0;
     uint32_t n_bvh_nodes = 0, n_tris = 0, n_lights = 0, n_probes = 0;
+    int bvh_height = 0;                       /* inner levels of the scene BVH (validated against BVH_STACK at upload) */
+    float bvh_build_ms = 0.f;                 /* device build: CUDA-event time of the builder, 0 for a host-built tree */
     uint64_t n_texels = 0;
     ltrgpu_Inst *d_inst = nullptr;
     ltrgpu_Inst *h_inst = nullptr;
@@ -146,6 +148,16 @@ template <class T> static inline int dev_upload(ltrgpu_Ctx *ctx, T **p, const vo
 template <class T> static inline void dev_free(T **p) { if (*p) { lb_free(*p); *p = nullptr; } }
 
 static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+/* The flat scene BVH built on the device (gpu_bvh.cu): binary nodes, their 4-wide collapse and the triangle order, all in
+ * lb_malloc'ed device memory owned by the caller.  n must exceed leaf_max (smaller scenes are one wrapped leaf: bvh.cpp). */
+struct LbDeviceBvh {
+    BvhNode *nodes; Bvh4Node *nodes4; uint32_t *order;
+    uint32_t n_nodes, n_nodes4;
+    int height;                 /* levels of inner nodes */
+    unsigned launches;
+};
+int lb_build_bvh_device(cudaStream_t st, const float *d_tris9, uint32_t n, int leaf_max, int num_sms, LbDeviceBvh *out, char *err, size_t errlen);
 
 /* ------------------------------------------------------------------------------------------
  * device helpers

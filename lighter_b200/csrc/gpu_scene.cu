@@ -152,11 +152,12 @@ int lb_upload_staged(ltrgpu_Ctx *ctx, void *dst, const void *src, size_t bytes)
 
 /* one thread per BVH-order triangle: expand the 9 floats into the two prepared records
  * (geom.h) with the reference's exact expressions. */
-__global__ void prepare_tris_kernel(const float *__restrict__ tris9, uint32_t n, PreparedTri *__restrict__ pt, RayTri *__restrict__ rt)
+__global__ void prepare_tris_kernel(const float *__restrict__ tris9, const uint32_t *__restrict__ order /* slot -> triangle, or NULL */, uint32_t n,
+                                    PreparedTri *__restrict__ pt, RayTri *__restrict__ rt)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float *t = tris9 + 9ull * i;
+    const float *t = tris9 + 9ull * (order ? order[i] : i);
     V3 a = mk3(t[0], t[1], t[2]), b = mk3(t[3], t[4], t[5]), c = mk3(t[6], t[7], t[8]);
     PreparedTri P;
     prepare_tri(a, b, c, P);
@@ -332,9 +333,6 @@ extern "C" int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *d)
     if (dev_upload(ctx, &ctx->d_rnodes, d->rnodes, d->n_rnodes)) return 1;
     if (dev_upload(ctx, &ctx->d_ritems, d->ritems, d->n_ritems)) return 1;
     if (dev_upload(ctx, &ctx->d_rtree_tris, d->rtree_tris9, (size_t)d->n_rtree_tris * 9)) return 1;
-    if (dev_upload(ctx, &ctx->d_bvh, d->bvh, d->n_bvh_nodes)) return 1;
-    if (dev_upload(ctx, &ctx->d_bvh4, d->bvh4, d->n_bvh4_nodes)) return 1;
-    if (dev_upload(ctx, &ctx->d_tri_orig, d->tri_orig, d->n_tris)) return 1;
     if (dev_upload(ctx, &ctx->d_lights, d->lights, d->n_lights)) return 1;
     if (dev_upload(ctx, &ctx->d_light_inst, d->light_inst, (size_t)d->n_lights * d->n_inst)) return 1;
     if (dev_upload(ctx, &ctx->d_light_samples, d->light_samples4, d->n_light_samples)) return 1;
@@ -345,14 +343,41 @@ extern "C" int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *d)
     if (dev_upload(ctx, &ctx->d_ao_sin, d->ao_sin_side, ns)) return 1;
     if (dev_upload(ctx, &ctx->d_blur_kernel, d->blur_kernel, d->blur_kernel ? 2 * d->blur_ext + 1 : 0)) return 1;
 
-    /* triangles: upload raw, expand on device, drop raw */
+    /* scene BVH + its triangles: raw triangles up, expanded on the device into the two prepared records, raw dropped */
     float *d_raw = nullptr;
-    if (dev_upload(ctx, &d_raw, d->tris9, (size_t)d->n_tris * 9)) return 1;
+    const bool raw_is_rtree = d->bvh == nullptr && d->tris9 == d->rtree_tris9 && d->n_tris == d->n_rtree_tris;
+    if (raw_is_rtree) d_raw = ctx->d_rtree_tris;
+    else if (dev_upload(ctx, &d_raw, d->tris9, (size_t)d->n_tris * 9)) return 1;
     if (dev_alloc(ctx, &ctx->d_ptris, d->n_tris)) return 1;
     if (dev_alloc(ctx, &ctx->d_raytris, d->n_tris)) return 1;
-    if (d->n_tris) {
-        prepare_tris_kernel<<<grid_for(d->n_tris, 256), 256, 0, ctx->stream>>>(d_raw, d->n_tris, ctx->d_ptris, ctx->d_raytris);
+    ctx->bvh_build_ms = 0.f;
+    if (d->bvh) {
+        if (dev_upload(ctx, &ctx->d_bvh, d->bvh, d->n_bvh_nodes)) return 1;
+        if (dev_upload(ctx, &ctx->d_bvh4, d->bvh4, d->n_bvh4_nodes)) return 1;
+        if (dev_upload(ctx, &ctx->d_tri_orig, d->tri_orig, d->n_tris)) return 1;
+        ctx->bvh_height = d->bvh_height;
+        if (d->n_tris) {
+            prepare_tris_kernel<<<grid_for(d->n_tris, 256), 256, 0, ctx->stream>>>(d_raw, nullptr, d->n_tris, ctx->d_ptris, ctx->d_raytris);
+            CU_LAUNCH_CHECK(ctx);
+        }
+    } else {
+        dev_free(&ctx->d_bvh); dev_free(&ctx->d_bvh4); dev_free(&ctx->d_tri_orig);
+        LbDeviceBvh T;
+        CU_TRY(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
+        if (lb_build_bvh_device(ctx->stream, d_raw, d->n_tris, d->bvh_leaf_max, ctx->num_sms, &T, ctx->err, sizeof(ctx->err))) return 1;
+        CU_TRY(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
+        ctx->d_bvh = T.nodes; ctx->d_bvh4 = T.nodes4; ctx->d_tri_orig = T.order;
+        ctx->n_bvh_nodes = T.n_nodes; ctx->bvh_height = T.height;
+        ctx->host_counters.kernel_launches += T.launches;
+        prepare_tris_kernel<<<grid_for(d->n_tris, 256), 256, 0, ctx->stream>>>(d_raw, ctx->d_tri_orig, d->n_tris, ctx->d_ptris, ctx->d_raytris);
         CU_LAUNCH_CHECK(ctx);
+        CU_TRY(ctx, cudaEventSynchronize(ctx->ev_k1));
+        CU_TRY(ctx, cudaEventElapsedTime(&ctx->bvh_build_ms, ctx->ev_k0, ctx->ev_k1));
+    }
+    /* the traversal stacks are fixed (BVH_STACK): binary walks push one node per level, the 4-wide walk up to three per two levels */
+    if (ctx->bvh_height > 40) {
+        snprintf(ctx->err, sizeof(ctx->err), "scene BVH is %d levels deep; the traversal stacks hold 40", ctx->bvh_height);
+        return 1;
     }
     /* reference-order triangles (lumel generation): point-query terms precomputed once instead of per query */
     if (dev_alloc(ctx, &ctx->d_rtree_ptris, d->n_rtree_tris)) return 1;
@@ -360,11 +385,19 @@ extern "C" int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *d)
     if (d->n_rtree_tris) {
         tri_boxes_kernel<<<grid_for(d->n_rtree_tris, 256), 256, 0, ctx->stream>>>(ctx->d_rtree_tris, d->n_rtree_tris, ctx->d_rtree_boxes);
         CU_LAUNCH_CHECK(ctx);
-        prepare_tris_kernel<<<grid_for(d->n_rtree_tris, 256), 256, 0, ctx->stream>>>(ctx->d_rtree_tris, d->n_rtree_tris, ctx->d_rtree_ptris, nullptr);
+        prepare_tris_kernel<<<grid_for(d->n_rtree_tris, 256), 256, 0, ctx->stream>>>(ctx->d_rtree_tris, nullptr, d->n_rtree_tris, ctx->d_rtree_ptris, nullptr);
         CU_LAUNCH_CHECK(ctx);
     }
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    lb_free(d_raw);
+    if (!raw_is_rtree) lb_free(d_raw);
+    return 0;
+}
+
+extern "C" int ltrgpu_bvh_info(ltrgpu_Ctx *ctx, uint32_t *n_nodes, int *height, float *build_ms)
+{
+    if (n_nodes) *n_nodes = ctx->n_bvh_nodes;
+    if (height) *height = ctx->bvh_height;
+    if (build_ms) *build_ms = ctx->bvh_build_ms;
     return 0;
 }
 

@@ -5,6 +5,7 @@
  */
 #include "gpu_internal.cuh"
 
+#include <algorithm>
 #include <vector>
 
 #include "lighter_b200.h"
@@ -150,11 +151,41 @@ __global__ void t_prepare_kernel(const float *tris9, uint32_t n, PreparedTri *pt
     RayTri R; prepare_raytri(a, b, c, R); rt[i] = R;
 }
 
-bool scene_to_device(Dev &D, const float *tris9, uint32_t ntris, SceneOnDevice &S)
+__global__ void t_prepare_ordered_kernel(const float *tris9, const uint32_t *order, uint32_t n, PreparedTri *pt, RayTri *rt)
 {
-    SceneBvh bvh;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *t = tris9 + 9ull * order[i];
+    V3 a = mk3(t[0], t[1], t[2]), b = mk3(t[3], t[4], t[5]), c = mk3(t[6], t[7], t[8]);
+    PreparedTri P; prepare_tri(a, b, c, P); pt[i] = P;
+    RayTri R; prepare_raytri(a, b, c, R); rt[i] = R;
+}
+
+struct DeviceTree {                /* a device-built tree kept alive for the duration of a test call */
+    LbDeviceBvh T = { nullptr, nullptr, nullptr, 0, 0, 0, 0 };
+    ~DeviceTree() { lb_free(T.nodes); lb_free(T.nodes4); lb_free(T.order); }
+};
+
+/* The scene the way a bake sets it up: the BVH built on the device (gpu_bvh.cu) unless the scene fits one leaf or
+ * LTR_BVH_HOST=1 asks for the host builder (A/B). */
+bool scene_to_device(Dev &D, DeviceTree &DT, const float *tris9, uint32_t ntris, SceneOnDevice &S)
+{
     int leaf_max = BVH_LEAF_MAX;
     if (const char *e = getenv("LTR_BVH_LEAF")) leaf_max = atoi(e);
+    if (leaf_max < 1) leaf_max = 1;
+    if (leaf_max > 7) leaf_max = 7;
+    S.pt = D.alloc<PreparedTri>(ntris);
+    S.rt = D.alloc<RayTri>(ntris);
+    if (ntris > (uint32_t)leaf_max && !getenv("LTR_BVH_HOST")) {
+        float *d_raw = D.up(tris9, (size_t)ntris * 9);
+        if (!D.ok) return false;
+        char err[256] = { 0 };
+        if (lb_build_bvh_device(nullptr, d_raw, ntris, leaf_max, 148, &DT.T, err, sizeof(err))) { fprintf(stderr, "lighter_b200: %s\n", err); return false; }
+        S.bvh = DT.T.nodes; S.bvh4 = DT.T.nodes4; S.orig = DT.T.order;
+        t_prepare_ordered_kernel<<<(ntris + 255) / 256, 256>>>(d_raw, DT.T.order, ntris, S.pt, S.rt);
+        return cudaDeviceSynchronize() == cudaSuccess;
+    }
+    SceneBvh bvh;
     build_scene_bvh(tris9, ntris, bvh, leaf_max, 0);
     std::vector<float> ordered((size_t)ntris * 9);
     for (uint32_t k = 0; k < ntris; ++k) memcpy(&ordered[(size_t)k * 9], tris9 + (size_t)bvh.order[k] * 9, 36);
@@ -162,8 +193,6 @@ bool scene_to_device(Dev &D, const float *tris9, uint32_t ntris, SceneOnDevice &
     S.bvh = D.up(bvh.nodes.data(), bvh.nodes.size());
     S.bvh4 = D.up(bvh.nodes4.data(), bvh.nodes4.size());
     S.orig = D.up(bvh.order.data(), bvh.order.size());
-    S.pt = D.alloc<PreparedTri>(ntris);
-    S.rt = D.alloc<RayTri>(ntris);
     if (!D.ok) return false;
     if (ntris) t_prepare_kernel<<<(ntris + 255) / 256, 256>>>(d_raw, ntris, S.pt, S.rt);
     return cudaDeviceSynchronize() == cudaSuccess;
@@ -202,8 +231,9 @@ int ltrx_test_scene_queries(const float *tris9, u32 ntris, const float *a3, cons
 {
     if (!have_device()) return 0;
     Dev D;
+    DeviceTree DT;
     SceneOnDevice S;
-    if (!scene_to_device(D, tris9, ntris, S)) return 0;
+    if (!scene_to_device(D, DT, tris9, ntris, S)) return 0;
     float *da = D.up(a3, (size_t)n * 3), *db = D.up(b3, (size_t)n * 3);
     float *dd = dist_out ? D.alloc<float>(n) : nullptr, *dc = closest_out ? D.alloc<float>(n) : nullptr;
     int *dh = anyhit_out ? D.alloc<int>(n) : nullptr, *dct = closest_tri_out ? D.alloc<int>(n) : nullptr;
@@ -218,8 +248,9 @@ int ltrx_test_march(const float *tris9, u32 ntris, const float *from3, const flo
 {
     if (!have_device()) return 0;
     Dev D;
+    DeviceTree DT;
     SceneOnDevice S;
-    if (!scene_to_device(D, tris9, ntris, S)) return 0;
+    if (!scene_to_device(D, DT, tris9, ntris, S)) return 0;
     float *df = D.up(from3, (size_t)n * 3), *dt = D.up(to3, (size_t)n * 3), *dk = D.up(k, n), *dout = D.alloc<float>(n);
     u32 *ds = steps_out ? D.alloc<u32>(n) : nullptr;
     if (!D.ok) return 0;
@@ -243,6 +274,66 @@ int ltrx_test_spiral_dirs(const float *nrm3, const float *randoff, u32 n, int sa
     if (cudaDeviceSynchronize() != cudaSuccess) return 0;
     D.down(out3, dout, (size_t)n * samples * 3);
     return D.ok;
+}
+
+/* The device builder against the host builder on the same triangles: both run the same binned SAH, so for non-degenerate
+ * input the trees must be EQUAL -- binary nodes (boxes numerically, child codes exactly), 4-wide nodes, and the triangle
+ * set of every leaf.  Returns 0 on a device failure; the mismatch counters say how many records differ. */
+int ltrx_test_device_bvh(const float *tris9, u32 ntris, int leaf_max, u32 *n_nodes, u32 *n_nodes4, int *height, float *build_ms,
+                         u32 *mismatch_nodes, u32 *mismatch_nodes4, u32 *mismatch_leaves, int *host_height)
+{
+    if (!have_device()) return 0;
+    Dev D;
+    DeviceTree DT;
+    float *d_raw = D.up(tris9, (size_t)ntris * 9);
+    if (!D.ok) return 0;
+    char err[256] = { 0 };
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    { LbDeviceBvh W; if (lb_build_bvh_device(nullptr, d_raw, ntris, leaf_max, 148, &W, err, sizeof(err)) == 0) { lb_free(W.nodes); lb_free(W.nodes4); lb_free(W.order); } }   /* warm the allocator */
+    cudaEventRecord(e0, nullptr);
+    if (lb_build_bvh_device(nullptr, d_raw, ntris, leaf_max, 148, &DT.T, err, sizeof(err))) { fprintf(stderr, "lighter_b200: %s\n", err); return 0; }
+    cudaEventRecord(e1, nullptr);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(build_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *n_nodes = DT.T.n_nodes; *n_nodes4 = DT.T.n_nodes4; *height = DT.T.height;
+    std::vector<BvhNode> dn(DT.T.n_nodes);
+    std::vector<Bvh4Node> dn4(DT.T.n_nodes4);
+    std::vector<uint32_t> dord(ntris);
+    D.down(dn.data(), DT.T.nodes, dn.size()); D.down(dn4.data(), DT.T.nodes4, dn4.size()); D.down(dord.data(), DT.T.order, dord.size());
+    if (!D.ok) return 0;
+    SceneBvh H;
+    build_scene_bvh(tris9, ntris, H, leaf_max, 0);
+    *host_height = H.depth;
+    *mismatch_nodes = *mismatch_nodes4 = *mismatch_leaves = 0;
+    if (H.nodes.size() != dn.size()) *mismatch_nodes = (u32)(H.nodes.size() > dn.size() ? H.nodes.size() - dn.size() : dn.size() - H.nodes.size()) + 1u;
+    if (H.nodes4.size() != dn4.size()) *mismatch_nodes4 = (u32)(H.nodes4.size() > dn4.size() ? H.nodes4.size() - dn4.size() : dn4.size() - H.nodes4.size()) + 1u;
+    std::vector<uint32_t> a, b;
+    for (size_t i = 0; i < H.nodes.size() && i < dn.size(); ++i) {
+        const BvhNode &x = H.nodes[i], &y = dn[i];
+        const bool same = x.lo0x == y.lo0x && x.lo0y == y.lo0y && x.lo0z == y.lo0z && x.hi0x == y.hi0x && x.hi0y == y.hi0y && x.hi0z == y.hi0z &&
+                          x.lo1x == y.lo1x && x.lo1y == y.lo1y && x.lo1z == y.lo1z && x.hi1x == y.hi1x && x.hi1y == y.hi1y && x.hi1z == y.hi1z &&
+                          x.c0 == y.c0 && x.c1 == y.c1;
+        if (!same) { ++*mismatch_nodes; continue; }
+        const int32_t cs[2] = { x.c0, x.c1 };
+        for (int k = 0; k < 2; ++k) {
+            if (cs[k] >= 0) continue;
+            const uint32_t code = ~cs[k], first = code >> 3, cnt = code & 7u;
+            if (first + cnt > ntris) { ++*mismatch_leaves; continue; }
+            a.assign(H.order.begin() + first, H.order.begin() + first + cnt); b.assign(dord.begin() + first, dord.begin() + first + cnt);
+            std::sort(a.begin(), a.end());
+            if (a != b) ++*mismatch_leaves;                            /* the device lists a leaf's triangles in ascending index */
+        }
+    }
+    for (size_t i = 0; i < H.nodes4.size() && i < dn4.size(); ++i) {
+        const Bvh4Node &x = H.nodes4[i], &y = dn4[i];
+        bool same = true;
+        for (int j = 0; j < 4 && same; ++j)
+            same = x.c[j] == y.c[j] && (x.c[j] == BVH4_EMPTY || (x.lox[j] == y.lox[j] && x.loy[j] == y.loy[j] && x.loz[j] == y.loz[j] && x.hix[j] == y.hix[j] && x.hiy[j] == y.hiy[j] && x.hiz[j] == y.hiz[j]));
+        if (!same) ++*mismatch_nodes4;
+    }
+    return 1;
 }
 
 } /* extern "C" */
