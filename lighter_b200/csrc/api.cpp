@@ -11,8 +11,9 @@
  *     before the start ("not started")                           lighter.cpp:1147-1164, lighter_int.hpp:971
  *   - outputs are owned by the scene until ltr_DestroyScene      lighter_int.hpp:982-994
  * Differences, on purpose: ltr_DestroyScene joins the bake thread first (the reference frees under
- * a running worker); errors from CUDA/NCCL are reported through the stage string
- * ("failed: ...") and ltrx_GetError, never thrown across the C ABI.
+ * a running worker); errors from CUDA/NCCL are never thrown across the C ABI: after a failed bake
+ * ltr_GetStatus returns 0 (done) with the stage string "failed: <reason>" instead of "finished" and
+ * lightmap_count stays 0; ltrx_GetError returns the same reason.
  */
 #include <stdlib.h>
 #include <string.h>
@@ -74,7 +75,7 @@ LTRBOOL ltr_GetStatus(ltr_Scene *scene, ltr_WorkStatus *wsout)
 {
     const char *st = scene->stage.load(std::memory_order_acquire);
     wsout->completion = scene->completion.load(std::memory_order_relaxed);
-    wsout->stage = st ? st : "finished";
+    wsout->stage = st ? st : (scene->failed_stage.empty() ? "finished" : scene->failed_stage.c_str());
     return st != nullptr;
 }
 

@@ -112,6 +112,7 @@ struct Bake {
     BigVec<float> rtree_tris;
     SceneBvh bvh;
     BigVec<float> bvh_tris;                   /* host-built tree: triangles in BVH order; device build: the compacted scene-order triangles (if not every instance casts) */
+    bool all_cast = true;                     /* every instance with triangles casts shadows: scene BVH == the triangles of the instance trees */
     bool device_bvh = true;                   /* the scene BVH is built on the device (gpu_bvh.cu); false: bvh.cpp (LTR_BVH_HOST=1, tiny scenes, host-only test hooks) */
     const float *scene_tris = nullptr;        /* device build: the triangles the tree is built over, scene order */
     size_t n_scene_tris = 0;
@@ -125,6 +126,7 @@ struct Bake {
     bool prepared = false;
     void *comm = nullptr;
     const NcclApi *nccl = nullptr;
+    int world = 1;
     /* debug copies */
     std::vector<float> d_pos, d_nrm, d_rad, d_rgb, d_fvis, d_lfac;
     std::vector<uint32_t> d_loc, d_lother;
@@ -142,12 +144,20 @@ int nccl_allgather_cb(void *user, const void *send, void *recv, size_t bytes, vo
     return rc;
 }
 
-int nccl_allreduce_cb(void *user, float *buf, size_t n, void *stream)
+/* uneven in-place all-gather: one broadcast per rank, fused into one NCCL group */
+int nccl_gatherv_cb(void *user, void *buf, const uint64_t *off, void *stream)
 {
     Bake *B = (Bake *)user;
     if (!B->nccl || !B->comm) return 1;
-    int rc = B->nccl->AllReduce(buf, buf, n, /*ncclFloat32*/ 7, /*ncclSum*/ 0, B->comm, stream);
-    if (rc != 0) fprintf(stderr, "lighter_b200: ncclAllReduce failed: %s\n", B->nccl->GetErrorString(rc));
+    int rc = B->nccl->GroupStart();
+    for (int r = 0; rc == 0 && r < B->world; ++r) {
+        if (off[r + 1] <= off[r]) continue;
+        char *p = (char *)buf + off[r];
+        rc = B->nccl->Broadcast(p, p, (size_t)(off[r + 1] - off[r]), /*ncclUint8*/ 1, r, B->comm, stream);
+    }
+    const int rc2 = B->nccl->GroupEnd();
+    if (rc == 0) rc = rc2;
+    if (rc != 0) fprintf(stderr, "lighter_b200: ncclBroadcast group failed: %s\n", B->nccl->GetErrorString(rc));
     return rc;
 }
 
@@ -290,6 +300,7 @@ void host_prepare(ltr_Scene *S, bool force_host_bvh = false)
     /* the scene BVH covers the instances that cast shadows */
     bool all_cast = true;
     for (size_t i = 1; i < ni; ++i) if (n_itris[i] && !S->instances[i]->shadow) all_cast = false;
+    B.all_cast = all_cast;
     BigVec<float> scene_compact;
     if (!all_cast) {
         std::vector<size_t> o_stri(ni + 1, 0);
@@ -487,6 +498,7 @@ void upload(ltr_Scene *S)
     d.n_ritems = (uint32_t)B.ritems.size(); d.ritems = B.ritems.data();
     d.n_rtree_tris = (uint32_t)(B.rtree_tris.size() / 9); d.rtree_tris9 = B.rtree_tris.data();
     d.bvh_leaf_max = B.bvh_leaf_max;
+    d.scene_covers_rtree = B.all_cast ? 1 : 0;
     if (B.device_bvh) {
         d.n_bvh_nodes = d.n_bvh4_nodes = 0; d.bvh = nullptr; d.bvh4 = nullptr; d.tri_orig = nullptr;
         d.n_tris = (uint32_t)B.n_scene_tris; d.tris9 = B.scene_tris;
@@ -554,7 +566,8 @@ void gpu_stages(ltr_Scene *S)
     S->completion.store(0.f);
     B.lumel_off.assign(ni + 1, 0);
     gpu_check(S, ltrgpu_set_world(B.gpu, S->rank, S->world, S->world > 1 ? nccl_allgather_cb : nullptr, &B), "world");
-    gpu_check(S, ltrgpu_set_allreduce(B.gpu, S->world > 1 ? nccl_allreduce_cb : nullptr), "world");
+    B.world = S->world;
+    gpu_check(S, ltrgpu_set_gatherv(B.gpu, S->world > 1 ? nccl_gatherv_cb : nullptr), "world");
     gpu_check(S, ltrgpu_generate_lumels(B.gpu, B.lumel_off.data()), "lumel generation");
     const uint64_t n = B.lumel_off[ni];
     uint64_t sb = 0, se = n;
@@ -581,9 +594,8 @@ void gpu_stages(ltr_Scene *S)
     }
 
     t0 = now_s();
-    if (!S->lights.empty()) {
-        S->stage.store("rendering lightmaps");
-        S->completion.store(0.f);
+    if (!S->lights.empty() || cfg.generate_normalmap_data) {       /* without lights only the normal-map terms are produced (the reference names no stage then) */
+        if (!S->lights.empty()) { S->stage.store("rendering lightmaps"); S->completion.store(0.f); }
         gpu_check(S, ltrgpu_direct_light(B.gpu), "direct light");
         S->completion.store(1.f);
         if (S->keep_debug) {
@@ -751,6 +763,7 @@ template <class F> int guarded(ltr_Scene *S, F f)
     catch (const Fail &e) { S->error = e.msg; }
     catch (const std::exception &e) { S->error = std::string("exception: ") + e.what(); }
     fprintf(stderr, "lighter_b200: bake failed: %s\n", S->error.c_str());
+    S->failed_stage = "failed: " + S->error;          /* what ltr_GetStatus reports once the bake thread is done (api.cpp) */
     return 0;
 }
 
@@ -760,6 +773,7 @@ void bake_main(ltr_Scene *S)
 {
     const double t0 = now_s();
     S->error.clear();
+    S->failed_stage.clear();
     if (!S->bake) S->bake = new Bake;
     guarded(S, [&]() {
         host_prepare(S);
@@ -968,7 +982,7 @@ int ltrx_test_reftree(const float *tris9, u32 ntris, void *nodes_out, u32 nodes_
 static bool host_bvh4_anyhit(const SceneBvh &bvh, const std::vector<RayTri> &rt, V3 l1, V3 l2, std::vector<int32_t> &stack, uint64_t *visits)
 {
     const V3 d = l2 - l1;
-    const float ix = d.x != 0 ? 1.0f / d.x : 1e30f, iy = d.y != 0 ? 1.0f / d.y : 1e30f, iz = d.z != 0 ? 1.0f / d.z : 1e30f;
+    const float ix = lb_slab_inv(d.x), iy = lb_slab_inv(d.y), iz = lb_slab_inv(d.z);
     bool hit = false;
     while (!stack.empty()) {
         const int32_t ni = stack.back(); stack.pop_back();
@@ -976,8 +990,8 @@ static bool host_bvh4_anyhit(const SceneBvh &bvh, const std::vector<RayTri> &rt,
         ++*visits;
         for (int c = 0; c < 4; ++c) {
             if (n.c[c] == BVH4_EMPTY) continue;
-            const float x0 = (n.lox[c] - l1.x) * ix, x1 = (n.hix[c] - l1.x) * ix, y0 = (n.loy[c] - l1.y) * iy, y1 = (n.hiy[c] - l1.y) * iy;
-            const float z0 = (n.loz[c] - l1.z) * iz, z1 = (n.hiz[c] - l1.z) * iz;
+            const float x0 = (n.lox[c] - l1.x) * ix, x1 = (n.hix[c] - lb_slab_origin_hi(l1.x, d.x)) * ix, y0 = (n.loy[c] - l1.y) * iy, y1 = (n.hiy[c] - lb_slab_origin_hi(l1.y, d.y)) * iy;
+            const float z0 = (n.loz[c] - l1.z) * iz, z1 = (n.hiz[c] - lb_slab_origin_hi(l1.z, d.z)) * iz;
             const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
             const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));
             if (!(t0 <= t1 + 2e-6f)) continue;
@@ -995,7 +1009,7 @@ static bool host_bvh4_anyhit(const SceneBvh &bvh, const std::vector<RayTri> &rt,
 static void host_bvh4_cost(const SceneBvh &bvh, const std::vector<RayTri> &rt, V3 l1, V3 l2, std::vector<int32_t> &stack, uint32_t *nodes, uint32_t *tris)
 {
     const V3 d = l2 - l1;
-    const float ix = d.x != 0 ? 1.0f / d.x : 1e30f, iy = d.y != 0 ? 1.0f / d.y : 1e30f, iz = d.z != 0 ? 1.0f / d.z : 1e30f;
+    const float ix = lb_slab_inv(d.x), iy = lb_slab_inv(d.y), iz = lb_slab_inv(d.z);
     bool hit = false;
     while (!stack.empty() && !hit) {
         const int32_t ni = stack.back(); stack.pop_back();
@@ -1003,8 +1017,8 @@ static void host_bvh4_cost(const SceneBvh &bvh, const std::vector<RayTri> &rt, V
         ++*nodes;
         for (int c = 0; c < 4 && !hit; ++c) {
             if (n.c[c] == BVH4_EMPTY) continue;
-            const float x0 = (n.lox[c] - l1.x) * ix, x1 = (n.hix[c] - l1.x) * ix, y0 = (n.loy[c] - l1.y) * iy, y1 = (n.hiy[c] - l1.y) * iy;
-            const float z0 = (n.loz[c] - l1.z) * iz, z1 = (n.hiz[c] - l1.z) * iz;
+            const float x0 = (n.lox[c] - l1.x) * ix, x1 = (n.hix[c] - lb_slab_origin_hi(l1.x, d.x)) * ix, y0 = (n.loy[c] - l1.y) * iy, y1 = (n.hiy[c] - lb_slab_origin_hi(l1.y, d.y)) * iy;
+            const float z0 = (n.loz[c] - l1.z) * iz, z1 = (n.hiz[c] - lb_slab_origin_hi(l1.z, d.z)) * iz;
             const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
             const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));
             if (!(t0 <= t1 + 2e-6f)) continue;
@@ -1043,11 +1057,11 @@ int ltrx_test_bvh_entry_cost(const float *tris9, u32 ntris, int leaf_max, const 
         for (u32 s = bundle_off[b]; s < bundle_off[b + 1]; ++s) {
             const float *p = segs6 + 6 * (size_t)s;
             const V3 A = mk3(p[0], p[1], p[2]), B = mk3(p[3], p[4], p[5]), d = B - A;
-            const float ix = d.x != 0 ? 1.0f / d.x : 1e30f, iy = d.y != 0 ? 1.0f / d.y : 1e30f, iz = d.z != 0 ? 1.0f / d.z : 1e30f;
+            const float ix = lb_slab_inv(d.x), iy = lb_slab_inv(d.y), iz = lb_slab_inv(d.z);
             stack.clear();
             for (int i = 0; i < E.n; ++i) {
-                const float x0 = (E.lox[i] - A.x) * ix, x1 = (E.hix[i] - A.x) * ix, y0 = (E.loy[i] - A.y) * iy, y1 = (E.hiy[i] - A.y) * iy;
-                const float z0 = (E.loz[i] - A.z) * iz, z1 = (E.hiz[i] - A.z) * iz;
+                const float x0 = (E.lox[i] - A.x) * ix, x1 = (E.hix[i] - lb_slab_origin_hi(A.x, d.x)) * ix, y0 = (E.loy[i] - A.y) * iy, y1 = (E.hiy[i] - lb_slab_origin_hi(A.y, d.y)) * iy;
+                const float z0 = (E.loz[i] - A.z) * iz, z1 = (E.hiz[i] - lb_slab_origin_hi(A.z, d.z)) * iz;
                 const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
                 const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));
                 if (t0 <= t1 + 2e-6f) stack.push_back(E.node[i]);
@@ -1144,11 +1158,11 @@ int ltrx_test_bvh_entry(const float *tris9, u32 ntris, int leaf_max, const float
             const bool h_root = host_bvh4_anyhit(bvh, rt, A, B, stack, visits_root);
             /* the entry tests of the device walk (gpu_internal.cuh: bvh4_anyhit_entries) */
             const V3 d = B - A;
-            const float ix = d.x != 0 ? 1.0f / d.x : 1e30f, iy = d.y != 0 ? 1.0f / d.y : 1e30f, iz = d.z != 0 ? 1.0f / d.z : 1e30f;
+            const float ix = lb_slab_inv(d.x), iy = lb_slab_inv(d.y), iz = lb_slab_inv(d.z);
             stack.clear();
             for (int i = 0; i < E.n; ++i) {
-                const float x0 = (E.lox[i] - A.x) * ix, x1 = (E.hix[i] - A.x) * ix, y0 = (E.loy[i] - A.y) * iy, y1 = (E.hiy[i] - A.y) * iy;
-                const float z0 = (E.loz[i] - A.z) * iz, z1 = (E.hiz[i] - A.z) * iz;
+                const float x0 = (E.lox[i] - A.x) * ix, x1 = (E.hix[i] - lb_slab_origin_hi(A.x, d.x)) * ix, y0 = (E.loy[i] - A.y) * iy, y1 = (E.hiy[i] - lb_slab_origin_hi(A.y, d.y)) * iy;
+                const float z0 = (E.loz[i] - A.z) * iz, z1 = (E.hiz[i] - lb_slab_origin_hi(A.z, d.z)) * iz;
                 const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
                 const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));
                 if (t0 <= t1 + 2e-6f) stack.push_back(E.node[i]);

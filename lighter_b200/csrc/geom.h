@@ -8,6 +8,19 @@
 #pragma once
 #include "vmath.h"
 
+/* The branch-free slab test of the any-hit walks (gpu_internal.cuh) and an axis the segment does not move along (d == 0
+ * exactly: lumels on the shared edge of two tiles, wall lumels).  Such an axis constrains nothing as long as the origin lies
+ * inside the box's range on it, FACES INCLUDED (the reference skips the axis altogether: RayAABBTest, lighter_math.cpp:618-650).
+ * A huge finite inverse does that without a branch: (lo - o) * 1e30 and (hi - o) * 1e30 keep their signs, so the axis
+ * contributes (-huge, +huge) inside and an empty interval outside -- except ON a face, where the product is 0.  On the lower
+ * face that is harmless (the interval starts at 0 anyway); on the upper face it ends the interval at 0 and the box is lost.
+ * So the upper faces are tested against lb_slab_origin_hi: the origin itself on an axis the segment moves along, one ulp
+ * below it on an axis it does not -- hi - o' is then a positive ulp on the face and the axis drops out.  Per ray, outside
+ * the loop; the loop's instruction count is unchanged.  Round 1 did not do this and lost the hits of segments lying in a
+ * tile's boundary plane (16 of 22 561 links on the config-4 sibling). */
+LB_HD float lb_slab_inv(float d) { return d != 0 ? 1.0f / d : 1e30f; }
+LB_HD float lb_slab_origin_hi(float o, float d) { return d != 0 ? o : nextafterf(o, -INFINITY); }
+
 /* ------------------------------------------------------------------------------------------
  * Point / triangle distance  (ref: lighter_math.cpp:875-913)
  *

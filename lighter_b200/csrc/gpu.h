@@ -73,6 +73,7 @@ typedef struct ltrgpu_SceneDesc {
     uint32_t n_bvh4_nodes;    const Bvh4Node *bvh4;            /* 4-wide collapse of the same tree (any-hit walks) */
     uint32_t n_tris;          const float *tris9; const uint32_t *tri_orig;
     int bvh_leaf_max, bvh_height;                              /* bvh_height: inner levels of a host-built tree */
+    int scene_covers_rtree;                                    /* every instance casts shadows: the scene BVH holds exactly the triangles of the instance trees */
     /* lights + light->instance visibility table [n_lights][n_inst] */
     uint32_t n_lights;        const ltrgpu_Light *lights; const uint8_t *light_inst;
     uint32_t n_light_samples; const float *light_samples4;     /* sampled-shadow extension: float4 per (light, sample) */
@@ -100,9 +101,9 @@ typedef struct ltrgpu_Counters {
 /* all-gather hook for the multi-GPU radiance exchange: gathers `bytes_per_rank` bytes from
  * `send` (device) of every rank into `recv` (device, world*bytes_per_rank) on `stream`. */
 typedef int (*ltrgpu_allgather_fn)(void *user, const void *send, void *recv, size_t bytes_per_rank, void *cuda_stream);
-/* in-place float sum over the ranks (the direct-light factor table: every entry is written by exactly one rank, the
- * others hold 0, so the sum is exact) */
-typedef int (*ltrgpu_allreduce_fn)(void *user, float *buf, size_t n_floats, void *cuda_stream);
+/* in-place all-gather of UNEVEN contiguous slices: rank r owns bytes [offsets[r], offsets[r+1]) of `buf` (device) and every
+ * rank ends up with all of them (the direct-light colours: runs of equal march cost, not of equal length) */
+typedef int (*ltrgpu_gatherv_fn)(void *user, void *buf, const uint64_t *offsets /* world+1 */, void *cuda_stream);
 
 int  ltrgpu_create(ltrgpu_Ctx **out, int device);
 void ltrgpu_destroy(ltrgpu_Ctx *ctx);
@@ -120,7 +121,7 @@ int ltrgpu_generate_lumels(ltrgpu_Ctx *ctx, uint64_t *inst_lumel_off);
 
 /* multi-GPU identity of this context and the all-gather hook; call before ltrgpu_generate_lumels */
 int ltrgpu_set_world(ltrgpu_Ctx *ctx, int rank, int world, ltrgpu_allgather_fn allgather, void *allgather_user);
-int ltrgpu_set_allreduce(ltrgpu_Ctx *ctx, ltrgpu_allreduce_fn allreduce);      /* same user pointer as the all-gather hook */
+int ltrgpu_set_gatherv(ltrgpu_Ctx *ctx, ltrgpu_gatherv_fn gatherv);            /* same user pointer as the all-gather hook */
 
 /* restrict the per-lumel stages to global lumels [begin,end) (multi-GPU shard); default = all */
 int ltrgpu_set_shard(ltrgpu_Ctx *ctx, uint64_t begin, uint64_t end, int rank, int world,

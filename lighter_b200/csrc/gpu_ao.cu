@@ -55,8 +55,10 @@ ao_trace_kernel(const BvhNode *__restrict__ bvh, const RayTri *__restrict__ rayt
         const V3 origin = SP + SN * (LB_SMALL * 2);
         const float ro = valid ? randoff[li] : 0.f;
         if (ENTRY) {
-            /* |spiral_dir| = 1 up to rounding, so every end point is within ao_distance (1 + 1e-3) of its origin */
-            const float reach = ao_distance * 1.001f;
+            /* |spiral_dir| <= max(|SN|, 1) up to rounding (lumel normals are unit, probe normals are whatever the caller gave:
+             * the reference does not normalise them, lighter_int.hpp:456-471), so every end point is within that many
+             * |ao_distance| of its origin */
+            const float reach = fabsf(ao_distance) * fmaxf(len3(SN), 1.0f) * 1.001f;
             float lx = origin.x - reach, ly = origin.y - reach, lz = origin.z - reach, hx = origin.x + reach, hy = origin.y + reach, hz = origin.z + reach;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {

@@ -497,8 +497,10 @@ __global__ void gb_emit_kernel(const GbNode *__restrict__ nodes, uint32_t n_node
     }
     const GbNode &L = nodes[N.left], &R = nodes[N.right];
     BvhNode o;
-    o.lo0x = gb_dec(L.blo[0]); o.lo0y = gb_dec(L.blo[1]); o.lo0z = gb_dec(L.blo[2]); o.hi0x = gb_dec(L.bhi[0]); o.hi0y = gb_dec(L.bhi[1]); o.hi0z = gb_dec(L.bhi[2]);
-    o.lo1x = gb_dec(R.blo[0]); o.lo1y = gb_dec(R.blo[1]); o.lo1z = gb_dec(R.blo[2]); o.hi1x = gb_dec(R.bhi[0]); o.hi1y = gb_dec(R.bhi[1]); o.hi1z = gb_dec(R.bhi[2]);
+    o.lo0x = gb_dec(L.blo[0]); o.lo0y = gb_dec(L.blo[1]); o.lo0z = gb_dec(L.blo[2]);
+    o.hi0x = gb_dec(L.bhi[0]); o.hi0y = gb_dec(L.bhi[1]); o.hi0z = gb_dec(L.bhi[2]);
+    o.lo1x = gb_dec(R.blo[0]); o.lo1y = gb_dec(R.blo[1]); o.lo1z = gb_dec(R.blo[2]);
+    o.hi1x = gb_dec(R.bhi[0]); o.hi1y = gb_dec(R.bhi[1]); o.hi1z = gb_dec(R.bhi[2]);
     o.c0 = L.left < 0 ? gb_leaf_code(L.first, L.count) : L.out_slot;
     o.c1 = R.left < 0 ? gb_leaf_code(R.first, R.count) : R.out_slot;
     o.pad0 = o.pad1 = 0;

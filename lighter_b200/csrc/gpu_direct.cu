@@ -21,6 +21,8 @@
 
 #include <stdlib.h>
 
+#include <vector>
+
 struct ShadeTerms {
     float pre;         /* product of the non-shadow factors the reference tests against <= 0 */
     float f_dist, f_ndotl, f_dir;
@@ -80,21 +82,22 @@ __device__ __forceinline__ bool light_is_supported(unsigned type) { return type 
 __global__ void direct_classify_kernel(const ltrgpu_Light *__restrict__ lights, uint32_t l0, uint32_t l1,
                                        const uint8_t *__restrict__ light_inst, uint32_t n_inst,
                                        const float4 *__restrict__ lpos, const float4 *__restrict__ lnrm, const uint32_t *__restrict__ linst,
-                                       uint64_t sh_begin, uint32_t n_local, const uint32_t *__restrict__ cuts /* [2]: my first / end block, or NULL */,
+                                       uint64_t sh_begin, uint32_t n_local,
                                        uint32_t *__restrict__ block_w /* weight pass: per 1024-lumel block, or NULL */,
                                        uint2 *__restrict__ active, uint32_t *active_count)
 {
-    /* (sh_begin, n_local) is the range the factor table covers.  With several GPUs that is the WHOLE lumel array: a first
-     * pass (block_w != NULL) sums an integer cost estimate of the marches per 1024-lumel block -- identical on every rank --
-     * the blocks are cut into `world` contiguous runs of equal cost, and the second pass lists the pairs of this rank's
-     * run.  Contiguous = each rank's marches stay in one part of the BVH (an interleaved deal was measured 30 % slower
-     * per march: every rank then streams the whole 200 MB scene through its L2); equal cost, because march work is
-     * concentrated around the lights (equal lumel counts: 17 ms on the slowest of 8 ranks against a 6 ms mean). */
+    /* (sh_begin, n_local) is the lumel range this launch looks at.  With several GPUs a first pass over ALL lumels and ALL
+     * lights (block_w != NULL) sums an integer cost estimate of the marches per 1024-lumel block -- identical on every rank --
+     * the blocks are cut into `world` contiguous runs of equal cost (direct_cuts_kernel), and each rank lists, marches and
+     * shades the pairs of its own run.  Contiguous = each rank's marches stay in one part of the BVH (an interleaved deal
+     * was measured 30 % slower per march: every rank then streams the whole 200 MB scene through its L2); equal cost,
+     * because march work is concentrated around the lights (equal lumel counts: 17 ms on the slowest of 8 ranks against a
+     * 6 ms mean). */
     const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t l = l0 + blockIdx.y;
     bool want = false;
     const uint32_t blk = (uint32_t)((sh_begin + li) >> 10);
-    if (li < n_local && l < l1 && (!cuts || (blk >= cuts[0] && blk < cuts[1]))) {
+    if (li < n_local && l < l1) {
         const ltrgpu_Light L = lights[l];
         const uint64_t g = sh_begin + li;
         if (light_is_supported(L.type) && light_inst[(size_t)l * n_inst + linst[g]]) {
@@ -350,28 +353,49 @@ extern "C" int ltrgpu_direct_light(ltrgpu_Ctx *ctx)
 {
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    const uint64_t n_local64 = ctx->sh_end - ctx->sh_begin;
-    if (n_local64 == 0 || ctx->n_lights == 0) return 0;
-    if (n_local64 > 0x7fffffffull || ctx->n_lumels > 0x7fffffffull) { snprintf(ctx->err, sizeof(ctx->err), "shard too large"); return 1; }
-    const uint32_t n_local = (uint32_t)n_local64;
-    /* The factor table f_vis[light][lumel].  One GPU: columns = this shard.  Several GPUs: columns = ALL lumels; each
-     * rank marches the pairs of the lumel blocks dealt to it round-robin (balanced), the tables are summed over the
-     * ranks (every entry is non-zero on one rank at most: exact), then each rank shades its own contiguous range. */
-    const bool spread = ctx->world > 1 && ctx->allreduce && !getenv("LTR_DIRECT_CONTIGUOUS");     /* env: A/B switch back to contiguous ranges */
-    const uint64_t tab_base = spread ? 0 : ctx->sh_begin;
-    const uint32_t tab_n = spread ? (uint32_t)ctx->n_lumels : n_local;
-    const uint32_t n_blocks = (uint32_t)((ctx->n_lumels + 1023) >> 10);
-    uint32_t *d_block_w = nullptr, *d_cuts = nullptr;
-    if (spread) {
+    /* every early return below depends on values that are identical on every rank (collectives follow) */
+    if (ctx->n_lumels == 0) return 0;
+    if (ctx->n_lumels > 0x7fffffffull) { snprintf(ctx->err, sizeof(ctx->err), "too many lumels"); return 1; }
+    if (ctx->n_lights == 0 && !ctx->params.normalmap) return 0;
+    const uint32_t world = (uint32_t)(ctx->world > 0 ? ctx->world : 1);
+    const uint32_t n_all = (uint32_t)ctx->n_lumels;
+    const uint32_t n_blocks = (n_all + 1023u) >> 10;
+    CU_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+
+    /* This rank's run of 1024-lumel blocks.  One GPU: everything.  Several: contiguous runs of equal estimated march cost;
+     * a rank marches AND shades the lumels of its run -- all lights of a lumel are on one rank, so the factor table never
+     * leaves the GPU (lights x lumels x 4 B: it was all-reduced before, 279 MB on config 4 and growing with the light count)
+     * and only the shaded colours are exchanged (16 B per lumel, independent of the light count). */
+    std::vector<uint32_t> cuts(world + 1, 0);
+    cuts[world] = n_blocks;
+    if (world > 1) {
+        if (!ctx->gatherv) { snprintf(ctx->err, sizeof(ctx->err), "sharded bake without a gather hook"); return 1; }
+        uint32_t *d_block_w = nullptr, *d_cuts = nullptr;
         if (dev_alloc(ctx, &d_block_w, n_blocks)) return 1;
-        if (dev_alloc(ctx, &d_cuts, (size_t)ctx->world + 1)) return 1;
+        if (dev_alloc(ctx, &d_cuts, (size_t)world + 1)) return 1;
+        CU_TRY(ctx, cudaMemsetAsync(d_block_w, 0, (size_t)n_blocks * 4, st));
+        for (uint32_t l0 = 0; l0 < ctx->n_lights; l0 += 65535u) {
+            const uint32_t l1 = l0 + 65535u < ctx->n_lights ? l0 + 65535u : ctx->n_lights;
+            dim3 grid(grid_for(n_all, 256), l1 - l0);
+            direct_classify_kernel<<<grid, 256, 0, st>>>(ctx->d_lights, l0, l1, ctx->d_light_inst, ctx->n_inst, ctx->d_lpos, ctx->d_lnrm, ctx->d_linst, 0, n_all,
+                                                         d_block_w, nullptr, nullptr);
+            CU_LAUNCH_CHECK(ctx);
+        }
+        direct_cuts_kernel<<<1, 32, 0, st>>>(d_block_w, n_blocks, world, d_cuts);
+        CU_LAUNCH_CHECK(ctx);
+        CU_TRY(ctx, cudaMemcpyAsync(cuts.data(), d_cuts, (size_t)(world + 1) * 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        lb_free(d_block_w); lb_free(d_cuts);
     }
+    auto lumel_of = [&](uint32_t blk) { const uint64_t v = (uint64_t)blk << 10; return v < n_all ? v : (uint64_t)n_all; };
+    const uint64_t tab_base = lumel_of(cuts[ctx->rank]);
+    const uint32_t tab_n = (uint32_t)(lumel_of(cuts[ctx->rank + 1]) - tab_base);        /* may be 0: this rank only takes part in the exchange */
 
     /* lights are processed in chunks so that the factor table stays within a fixed budget;
      * accumulation order over chunks is still the light order */
     const bool sampled = ctx->params.shadow_mode == 1;
     const size_t budget = (size_t)8 << 30;
-    uint32_t chunk = (uint32_t)(budget / ((size_t)tab_n * (sampled ? 20 : 12)));
+    uint32_t chunk = (uint32_t)(budget / ((size_t)(tab_n ? tab_n : 1) * (sampled ? 20 : 12)));
     if (chunk < 1) chunk = 1;
     if (chunk > ctx->n_lights) chunk = ctx->n_lights;
     if (ctx->params.normalmap) chunk = ctx->n_lights;           /* the normal map needs every factor resident */
@@ -382,28 +406,18 @@ extern "C" int ltrgpu_direct_light(ltrgpu_Ctx *ctx)
     if (sampled && dev_alloc(ctx, &ctx->d_smask, (size_t)chunk * tab_n)) return 1;
     ctx->fvis_tab_base = tab_base; ctx->fvis_tab_n = tab_n;
 
-    cudaEvent_t m0, m1;
-    CU_TRY(ctx, cudaEventCreate(&m0));
-    CU_TRY(ctx, cudaEventCreate(&m1));
-    CU_TRY(ctx, cudaEventRecord(ctx->ev0, st));
-    float march_ms = 0;
-    for (uint32_t l0 = 0; l0 < ctx->n_lights; l0 += chunk) {
+    std::vector<cudaEvent_t> mev;
+    for (uint32_t l0 = 0; tab_n && l0 < ctx->n_lights; l0 += chunk) {
         uint32_t l1 = l0 + chunk < ctx->n_lights ? l0 + chunk : ctx->n_lights;
         CU_TRY(ctx, cudaMemsetAsync(ctx->d_active_count, 0, 8, st));
         CU_TRY(ctx, cudaMemsetAsync(ctx->d_fvis, 0, (size_t)(l1 - l0) * tab_n * 4, st));
         dim3 grid(grid_for(tab_n, 256), l1 - l0);
-        if (spread) {
-            CU_TRY(ctx, cudaMemsetAsync(d_block_w, 0, (size_t)n_blocks * 4, st));
-            direct_classify_kernel<<<grid, 256, 0, st>>>(ctx->d_lights, l0, l1, ctx->d_light_inst, ctx->n_inst, ctx->d_lpos, ctx->d_lnrm,
-                                                         ctx->d_linst, tab_base, tab_n, nullptr, d_block_w, nullptr, nullptr);
-            CU_LAUNCH_CHECK(ctx);
-            direct_cuts_kernel<<<1, 32, 0, st>>>(d_block_w, n_blocks, (uint32_t)ctx->world, d_cuts);
-            CU_LAUNCH_CHECK(ctx);
-        }
         direct_classify_kernel<<<grid, 256, 0, st>>>(ctx->d_lights, l0, l1, ctx->d_light_inst, ctx->n_inst, ctx->d_lpos, ctx->d_lnrm,
-                                                     ctx->d_linst, tab_base, tab_n, spread ? d_cuts + ctx->rank : nullptr, nullptr,
-                                                     ctx->d_active, ctx->d_active_count);
+                                                     ctx->d_linst, tab_base, tab_n, nullptr, ctx->d_active, ctx->d_active_count);
         CU_LAUNCH_CHECK(ctx);
+        cudaEvent_t m0, m1;
+        CU_TRY(ctx, cudaEventCreate(&m0)); mev.push_back(m0);
+        CU_TRY(ctx, cudaEventCreate(&m1)); mev.push_back(m1);
         CU_TRY(ctx, cudaEventRecord(m0, st));
         unsigned blocks = (unsigned)ctx->num_sms * 16;
         if (!sampled) {
@@ -423,33 +437,35 @@ extern "C" int ltrgpu_direct_light(ltrgpu_Ctx *ctx)
             CU_LAUNCH_CHECK(ctx);
         }
         CU_TRY(ctx, cudaEventRecord(m1, st));
-        if (spread && ctx->allreduce(ctx->allgather_user, ctx->d_fvis, (size_t)(l1 - l0) * tab_n, st)) {
-            snprintf(ctx->err, sizeof(ctx->err), "direct light: all-reduce of the shadow factors failed");
-            return 1;
-        }
-        direct_accumulate_kernel<<<grid_for(n_local, 256), 256, 0, st>>>(ctx->d_lights, l0, l1, ctx->d_light_inst, ctx->n_inst, ctx->d_lpos,
-                                                                        ctx->d_lnrm, ctx->d_linst, ctx->sh_begin, n_local, ctx->d_fvis, tab_base, tab_n, ctx->d_lrgb);
+        direct_accumulate_kernel<<<grid_for(tab_n, 256), 256, 0, st>>>(ctx->d_lights, l0, l1, ctx->d_light_inst, ctx->n_inst, ctx->d_lpos,
+                                                                      ctx->d_lnrm, ctx->d_linst, tab_base, tab_n, ctx->d_fvis, tab_base, tab_n, ctx->d_lrgb);
         CU_LAUNCH_CHECK(ctx);
-        if (ctx->params.normalmap) {
-            if (dev_alloc(ctx, &ctx->d_lnmap, ctx->n_lumels + LB_PAD)) return 1;
-            normalmap_kernel<<<grid_for(n_local, 256), 256, 0, st>>>(ctx->d_lights, ctx->n_lights, ctx->d_light_inst, ctx->n_inst, ctx->d_lpos,
-                                                                    ctx->d_lnrm, ctx->d_linst, ctx->sh_begin, n_local, ctx->d_fvis, tab_base, tab_n,
-                                                                    ctx->params.amb_brightness, ctx->d_lnmap);
+    }
+    if (ctx->params.normalmap) {
+        /* also without any light: the reference then writes normalize(N * ambient brightness), focus 1 (lighter.cpp:977-1012) */
+        if (dev_alloc(ctx, &ctx->d_lnmap, ctx->n_lumels + LB_PAD)) return 1;
+        if (tab_n) {
+            normalmap_kernel<<<grid_for(tab_n, 256), 256, 0, st>>>(ctx->d_lights, ctx->n_lights, ctx->d_light_inst, ctx->n_inst, ctx->d_lpos,
+                                                                  ctx->d_lnrm, ctx->d_linst, tab_base, tab_n, ctx->d_fvis, tab_base, tab_n,
+                                                                  ctx->params.amb_brightness, ctx->d_lnmap);
             CU_LAUNCH_CHECK(ctx);
         }
-        CU_TRY(ctx, cudaStreamSynchronize(st));
-        float ms = 0;
-        cudaEventElapsedTime(&ms, m0, m1);
-        march_ms += ms;
+    }
+    if (world > 1) {
+        /* every rank gets the shaded colours (and normal-map terms) of every lumel: rank r's run is broadcast from r */
+        std::vector<uint64_t> off(world + 1);
+        for (uint32_t r = 0; r <= world; ++r) off[r] = lumel_of(cuts[r]) * sizeof(float4);
+        if (ctx->n_lights && ctx->gatherv(ctx->allgather_user, ctx->d_lrgb, off.data(), st)) { snprintf(ctx->err, sizeof(ctx->err), "direct light: exchange of the lumel colours failed"); return 1; }
+        if (ctx->params.normalmap && ctx->gatherv(ctx->allgather_user, ctx->d_lnmap, off.data(), st)) { snprintf(ctx->err, sizeof(ctx->err), "direct light: exchange of the normal-map terms failed"); return 1; }
     }
     CU_TRY(ctx, cudaEventRecord(ctx->ev1, st));
     CU_TRY(ctx, cudaStreamSynchronize(st));
-    float ms = 0;
+    float ms = 0, march_ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    for (size_t k = 0; k + 1 < mev.size(); k += 2) { float m = 0; cudaEventElapsedTime(&m, mev[k], mev[k + 1]); march_ms += m; }
+    for (cudaEvent_t e : mev) cudaEventDestroy(e);
     ctx->host_counters.ms_direct += ms;
     ctx->host_counters.ms_march += march_ms;
-    cudaEventDestroy(m0); cudaEventDestroy(m1);
-    lb_free(d_block_w); lb_free(d_cuts);
     return 0;
 }
 
@@ -458,6 +474,7 @@ extern "C" int ltrgpu_download_shadow_factors(ltrgpu_Ctx *ctx, uint32_t light, f
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     const uint64_t n_local = ctx->sh_end - ctx->sh_begin;
     if (!ctx->d_fvis || light >= ctx->n_lights) { snprintf(ctx->err, sizeof(ctx->err), "no shadow factors"); return 1; }
+    if (ctx->fvis_tab_base != ctx->sh_begin || ctx->fvis_tab_n != n_local) { snprintf(ctx->err, sizeof(ctx->err), "shadow-factor dumps are single-GPU only"); return 1; }
     CU_TRY(ctx, cudaMemcpyAsync(out, ctx->d_fvis + (size_t)light * ctx->fvis_tab_n + (ctx->sh_begin - ctx->fvis_tab_base), n_local * 4,
                                 cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -469,6 +486,7 @@ extern "C" int ltrgpu_download_shadow_masks(ltrgpu_Ctx *ctx, uint32_t light, uin
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     const uint64_t n_local = ctx->sh_end - ctx->sh_begin;
     if (!ctx->d_smask || light >= ctx->n_lights) { snprintf(ctx->err, sizeof(ctx->err), "no shadow masks (sampled mode only)"); return 1; }
+    if (ctx->fvis_tab_base != ctx->sh_begin || ctx->fvis_tab_n != n_local) { snprintf(ctx->err, sizeof(ctx->err), "shadow-mask dumps are single-GPU only"); return 1; }
     CU_TRY(ctx, cudaMemcpyAsync(out, ctx->d_smask + (size_t)light * ctx->fvis_tab_n + (ctx->sh_begin - ctx->fvis_tab_base), n_local * 8,
                                 cudaMemcpyDeviceToHost, ctx->stream));      /* several GPUs: only the pairs this rank marched are set */
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));

@@ -245,7 +245,7 @@ extern "C" int ltrgpu_finalize(ltrgpu_Ctx *ctx)
     const uint64_t nt = ctx->n_texels;
 
     if (gather_shards(ctx, ctx->d_lrgb)) return 1;
-    if (ctx->params.normalmap && ctx->d_lnmap && gather_shards(ctx, ctx->d_lnmap)) return 1;
+    /* the normal-map terms of every lumel are on every rank since the direct stage (gpu_direct.cu) */
 
     /* image layout tables (full-size images, then output images) */
     uint64_t *h_off = (uint64_t *)malloc(sizeof(uint64_t) * (ni + 1));

@@ -48,6 +48,11 @@ struct ltrgpu_Ctx {
     Bvh4Node *d_bvh4 = nullptr;               /* 4-wide collapse of d_bvh for the any-hit walks */
     PreparedTri *d_ptris = nullptr;
     RayTri *d_raytris = nullptr;
+    /* flat BVH over the triangles of ALL instance trees (lumel_classify_kernel): aliases the scene BVH when every instance
+     * casts shadows, a second device-built tree otherwise, NULL when neither exists */
+    BvhNode *d_lbvh = nullptr;
+    PreparedTri *d_lbvh_ptris = nullptr;
+    bool lbvh_owned = false;
     uint32_t *d_tri_orig = nullptr;
     ltrgpu_Light *d_lights = nullptr;
     ltrgpu_Light *h_lights = nullptr;
@@ -70,7 +75,7 @@ struct ltrgpu_Ctx {
     uint64_t sh_begin = 0, sh_end = 0;
     int rank = 0, world = 1;
     ltrgpu_allgather_fn allgather = nullptr;
-    ltrgpu_allreduce_fn allreduce = nullptr;
+    ltrgpu_gatherv_fn gatherv = nullptr;
     void *allgather_user = nullptr;
 
     /* ---- direct light ---- */
@@ -406,8 +411,8 @@ __device__ __forceinline__ float bvh_segment_entries(const BvhNode *__restrict__
  * Any-hit specialisation for the radiosity visibility rays (billions per bake, ~98 % of them misses,
  * and the kernel is instruction-issue bound -- ncu: IPC 3.3 of 4): no child ordering (a miss must
  * visit every overlapped node anyway), no entry-distance stack, branch-free handling of zero
- * direction components (inverse replaced by a huge finite value: (lo-o)*1e30 keeps the sign, is 0 on
- * the boundary and never NaN), absolute slack on the slab comparison.  Box tests may use any
+ * direction components (huge finite inverse, upper faces tested against an origin one ulp down:
+ * geom.h lb_slab_inv / lb_slab_origin_hi), absolute slack on the slab comparison.  Box tests may use any
  * conservative arithmetic; the triangle test keeps the reference's exact operand order.
  */
 template <int FLUSH = 10>  /* postponed triangles that trigger the test phase: high for rays that mostly miss, low for rays that are often blocked */
@@ -423,7 +428,8 @@ __device__ __forceinline__ bool bvh_anyhit(const BvhNode *__restrict__ nodes, co
     int tq[TQ];
     int sp = 0, nq = 0;
     const V3 d = l2 - l1;
-    const float ix = d.x != 0 ? 1.0f / d.x : 1e30f, iy = d.y != 0 ? 1.0f / d.y : 1e30f, iz = d.z != 0 ? 1.0f / d.z : 1e30f;
+    const float ix = lb_slab_inv(d.x), iy = lb_slab_inv(d.y), iz = lb_slab_inv(d.z);
+    const V3 l1h = mk3(lb_slab_origin_hi(l1.x, d.x), lb_slab_origin_hi(l1.y, d.y), lb_slab_origin_hi(l1.z, d.z));
     int node = 0;
     for (;;) {
         while (node >= 0) {
@@ -433,13 +439,13 @@ __device__ __forceinline__ bool bvh_anyhit(const BvhNode *__restrict__ nodes, co
             ts.nodes++;
             bool hit0, hit1;
             {
-                float x0 = (a.x - l1.x) * ix, x1 = (a.w - l1.x) * ix, y0 = (a.y - l1.y) * iy, y1 = (b.x - l1.y) * iy, z0 = (a.z - l1.z) * iz, z1 = (b.y - l1.z) * iz;
+                float x0 = (a.x - l1.x) * ix, x1 = (a.w - l1h.x) * ix, y0 = (a.y - l1.y) * iy, y1 = (b.x - l1h.y) * iy, z0 = (a.z - l1.z) * iz, z1 = (b.y - l1h.z) * iz;
                 float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
                 float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));
                 hit0 = t0 <= t1 + 2e-6f;
             }
             {
-                float x0 = (b.z - l1.x) * ix, x1 = (c.y - l1.x) * ix, y0 = (b.w - l1.y) * iy, y1 = (c.z - l1.y) * iy, z0 = (c.x - l1.z) * iz, z1 = (c.w - l1.z) * iz;
+                float x0 = (b.z - l1.x) * ix, x1 = (c.y - l1h.x) * ix, y0 = (b.w - l1.y) * iy, y1 = (c.z - l1h.y) * iy, z0 = (c.x - l1.z) * iz, z1 = (c.w - l1h.z) * iz;
                 float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
                 float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));
                 hit1 = t0 <= t1 + 2e-6f;
@@ -472,7 +478,7 @@ __device__ __forceinline__ bool bvh_anyhit(const BvhNode *__restrict__ nodes, co
  * boxes, one for the child codes).  A visit is counted as two node units (128 bytes = two 64-byte binary nodes).
  */
 template <int FLUSH>
-__device__ __forceinline__ bool bvh4_anyhit_core(const Bvh4Node *__restrict__ nodes, const RayTri *__restrict__ tris, const V3 l1, const V3 d,
+__device__ __forceinline__ bool bvh4_anyhit_core(const Bvh4Node *__restrict__ nodes, const RayTri *__restrict__ tris, const V3 l1, const V3 l1h, const V3 d,
                                                  const float ix, const float iy, const float iz, int (&stack_n)[BVH_STACK], int sp, int node, TravStats &ts)
 {
     /* Measured and NOT adopted (B200, config 4): picking the near / far plane of every slab by the sign of the direction
@@ -491,8 +497,8 @@ __device__ __forceinline__ bool bvh4_anyhit_core(const Bvh4Node *__restrict__ no
             int next = -1;
 #define LB_BVH4_CHILD(LX, LY, LZ, HX, HY, HZ, C)                                                                        \
             {                                                                                                           \
-                const float x0 = ((LX) - l1.x) * ix, x1 = ((HX) - l1.x) * ix, y0 = ((LY) - l1.y) * iy, y1 = ((HY) - l1.y) * iy; \
-                const float z0 = ((LZ) - l1.z) * iz, z1 = ((HZ) - l1.z) * iz;                                           \
+                const float x0 = ((LX) - l1.x) * ix, x1 = ((HX) - l1h.x) * ix, y0 = ((LY) - l1.y) * iy, y1 = ((HY) - l1h.y) * iy; \
+                const float z0 = ((LZ) - l1.z) * iz, z1 = ((HZ) - l1h.z) * iz;                                          \
                 const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));                 \
                 const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));                 \
                 if (t0 <= t1 + 2e-6f && (C) != BVH4_EMPTY) {                                                            \
@@ -524,8 +530,9 @@ __device__ __forceinline__ bool bvh4_anyhit(const Bvh4Node *__restrict__ nodes, 
 {
     int stack_n[BVH_STACK];
     const V3 d = l2 - l1;
-    const float ix = d.x != 0 ? 1.0f / d.x : 1e30f, iy = d.y != 0 ? 1.0f / d.y : 1e30f, iz = d.z != 0 ? 1.0f / d.z : 1e30f;
-    return bvh4_anyhit_core<FLUSH>(nodes, tris, l1, d, ix, iy, iz, stack_n, 0, 0, ts);
+    const float ix = lb_slab_inv(d.x), iy = lb_slab_inv(d.y), iz = lb_slab_inv(d.z);
+    const V3 l1h = mk3(lb_slab_origin_hi(l1.x, d.x), lb_slab_origin_hi(l1.y, d.y), lb_slab_origin_hi(l1.z, d.z));
+    return bvh4_anyhit_core<FLUSH>(nodes, tris, l1, l1h, d, ix, iy, iz, stack_n, 0, 0, ts);
 }
 
 /*
@@ -540,11 +547,12 @@ __device__ __forceinline__ bool bvh4_anyhit_entries(const Bvh4Node *__restrict__
     int stack_n[BVH_STACK];
     int sp = 0;
     const V3 d = l2 - l1;
-    const float ix = d.x != 0 ? 1.0f / d.x : 1e30f, iy = d.y != 0 ? 1.0f / d.y : 1e30f, iz = d.z != 0 ? 1.0f / d.z : 1e30f;
+    const float ix = lb_slab_inv(d.x), iy = lb_slab_inv(d.y), iz = lb_slab_inv(d.z);
+    const V3 l1h = mk3(lb_slab_origin_hi(l1.x, d.x), lb_slab_origin_hi(l1.y, d.y), lb_slab_origin_hi(l1.z, d.z));
     const int n = E.n;
     for (int i = 0; i < n; ++i) {
-        const float x0 = (E.lox[i] - l1.x) * ix, x1 = (E.hix[i] - l1.x) * ix, y0 = (E.loy[i] - l1.y) * iy, y1 = (E.hiy[i] - l1.y) * iy;
-        const float z0 = (E.loz[i] - l1.z) * iz, z1 = (E.hiz[i] - l1.z) * iz;
+        const float x0 = (E.lox[i] - l1.x) * ix, x1 = (E.hix[i] - l1h.x) * ix, y0 = (E.loy[i] - l1.y) * iy, y1 = (E.hiy[i] - l1h.y) * iy;
+        const float z0 = (E.loz[i] - l1.z) * iz, z1 = (E.hiz[i] - l1h.z) * iz;
         const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
         const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));
         if (t0 <= t1 + 2e-6f) stack_n[sp++] = E.node[i];
@@ -552,7 +560,7 @@ __device__ __forceinline__ bool bvh4_anyhit_entries(const Bvh4Node *__restrict__
     ts.entries += (unsigned)n;
     if (sp == 0) return false;
     const int node = stack_n[--sp];
-    return bvh4_anyhit_core<FLUSH>(nodes, tris, l1, d, ix, iy, iz, stack_n, sp, node, ts);
+    return bvh4_anyhit_core<FLUSH>(nodes, tris, l1, l1h, d, ix, iy, iz, stack_n, sp, node, ts);
 }
 
 /*

@@ -275,10 +275,19 @@ __device__ float reftree_closest(const RefView &v, V3 from, V3 to, int *tid)
     int stack[24];
     int sp = 0;
     stack[sp++] = 0;
+    /* The reference's ray/box test accepts boxes BEHIND the origin (lighter_math.cpp:618-650 has no tmax >= 0 check), so its
+     * walk follows the whole line through the instance; a triangle can only be hit inside the segment's own box, and a node
+     * box contains every triangle below it, so nodes that miss that box (widened like the per-triangle pre-test) are skipped:
+     * same hits, same first-met order among them.  On a 500 k-triangle instance this is most of the walk. */
+    const float sbe = 1e-4f;
+    const V3 slo = min3(from, to), shi = max3(from, to);
     while (sp) {
         int node = stack[--sp];
         RefNode N = v.nodes[node];
         if (!ref_ray_box(r, N.lo, N.hi)) continue;
+        if (slo.x > N.hi.x + sbe * (1.0f + fabsf(N.hi.x)) || shi.x < N.lo.x - sbe * (1.0f + fabsf(N.lo.x)) ||
+            slo.y > N.hi.y + sbe * (1.0f + fabsf(N.hi.y)) || shi.y < N.lo.y - sbe * (1.0f + fabsf(N.lo.y)) ||
+            slo.z > N.hi.z + sbe * (1.0f + fabsf(N.hi.z)) || shi.z < N.lo.z - sbe * (1.0f + fabsf(N.lo.z))) continue;
         if (N.ido != -1) {
             int cnt = v.items[N.ido];
             for (int k = 0; k < cnt; ++k) {
@@ -301,6 +310,26 @@ __device__ float reftree_closest(const RefView &v, V3 from, V3 to, int *tid)
     return closest;
 }
 
+/* The tests a triangle must pass before it may move the sample (ref: SampleOffsetQuery, lighter_math.cpp:991-1038), up to but
+ * not including the closest-hit probe; on success the target position and the slide direction. */
+__device__ __forceinline__ bool offset_tri_tests(const PreparedTri &PT, V3 P, V3 N, float dist, V3 &Pnew, V3 &projTPN)
+{
+    float ndst = point_tri_distance_prepared(P, PT);
+    if (!(ndst < dist)) return false;
+    V3 TPN = -tri_back_normal(PT.t0, PT.t1, PT.t2);
+    float TPD = dot3(TPN, PT.t0);
+    float sigdst = dot3(TPN, P) - TPD;
+    if (!(sigdst <= LB_SMALL)) return false;
+    V3 Pextr = P + norm3(TPN + N) * -sigdst * 1.41f;
+    if (!point_proj_on_tri(Pextr, PT)) return false;
+    float projDot = dot3(TPN, N);
+    if (!(fabsf(projDot) < 0.95f)) return false;
+    projTPN = norm3(TPN - N * projDot);
+    float dotFactor = 1.0f - fabsf(projDot);
+    Pnew = P + projTPN * (-sigdst / dotFactor + LB_SMALL);
+    return true;
+}
+
 /* One candidate triangle of the concave-edge offset, evaluated with the CURRENT (possibly already moved)
  * sample position -- the reference mutates P while it walks (lighter_math.cpp:991-1038). */
 __device__ __forceinline__ void offset_one_tri(const RefView &v, int id, V3 &P, V3 N, float dist)
@@ -317,19 +346,8 @@ __device__ __forceinline__ void offset_one_tri(const RefView &v, int id, V3 &P, 
     }
     PreparedTri PT;
     load_prepared(v.ptris + id, PT);
-    float ndst = point_tri_distance_prepared(P, PT);
-    if (!(ndst < dist)) return;
-    V3 TPN = -tri_back_normal(PT.t0, PT.t1, PT.t2);
-    float TPD = dot3(TPN, PT.t0);
-    float sigdst = dot3(TPN, P) - TPD;
-    if (!(sigdst <= LB_SMALL)) return;
-    V3 Pextr = P + norm3(TPN + N) * -sigdst * 1.41f;
-    if (!point_proj_on_tri(Pextr, PT)) return;
-    float projDot = dot3(TPN, N);
-    if (!(fabsf(projDot) < 0.95f)) return;
-    V3 projTPN = norm3(TPN - N * projDot);
-    float dotFactor = 1.0f - fabsf(projDot);
-    V3 Pnew = P + projTPN * (-sigdst / dotFactor + LB_SMALL);
+    V3 Pnew, projTPN;
+    if (!offset_tri_tests(PT, P, N, dist, Pnew, projTPN)) return;
     int tid = -1;
     float d = reftree_closest(v, P + (N + projTPN) * LB_SMALL, Pnew, &tid);
     if (d >= 0.9f || tid == id) P = Pnew;
@@ -375,68 +393,158 @@ __device__ void reftree_offset_sample(const RefView &v, V3 &P, V3 N, float dist,
     }
 }
 
+/*
+ * Which lumels can the concave-edge offset move at all?  The reference walks every instance's tree for every lumel
+ * (lighter.cpp:445-446) and mutates P as it goes, so the outcome depends on the order of the triangles -- but the FIRST
+ * triangle to move a sample is evaluated at the sample's original position, and must pass every test of SampleOffsetQuery
+ * there.  A lumel for which no triangle of any instance passes those tests at P0 is therefore left where it is, whatever
+ * the order.  This kernel answers that question with a distance-bounded walk of a flat BVH over the triangles of ALL
+ * instance trees (the scene BVH when every instance casts shadows), evaluating the reference's own test chain
+ * (offset_tri_tests) at the leaves; lumels with a potential mover are listed for the exact reference-order pass.
+ * Typically a few per cent of the lumels (the texels along concave edges); one coherent query per lumel instead of a
+ * divergent walk of reference-order trees whose leaves can hold thousands of triangles (flat ceilings: volume-0 nodes
+ * are never split, lighter_math.cpp:712-736).
+ */
+__device__ __forceinline__ bool lumel_has_mover(const BvhNode *__restrict__ nodes, const PreparedTri *__restrict__ tris, V3 P, V3 N, float dist)
+{
+    /* same slack as the per-triangle pre-test of offset_one_tri: never rejects a triangle the exact test would accept */
+    const float lim = dist * 1.01f + 2e-6f * (1.0f + fabsf(P.x) + fabsf(P.y) + fabsf(P.z));
+    const float lim2 = lim * lim;
+    int stack[BVH_STACK];
+    int sp = 0, node = 0;
+    for (;;) {
+        const float4 *n4 = reinterpret_cast<const float4 *>(nodes + node);
+        const float4 a = __ldg(n4), b = __ldg(n4 + 1), c = __ldg(n4 + 2);
+        const int4 k = __ldg(reinterpret_cast<const int4 *>(n4 + 3));
+        const float d0 = box_dist2(P, a.x, a.y, a.z, a.w, b.x, b.y), d1 = box_dist2(P, b.z, b.w, c.x, c.y, c.z, c.w);
+        int next = -1;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const int cc = side ? k.y : k.x;
+            if (!((side ? d1 : d0) <= lim2)) continue;
+            if (cc < 0) {
+                const unsigned code = ~cc, first = code >> 3, cnt = code & 7u;
+                for (unsigned t = 0; t < cnt; ++t) {
+                    PreparedTri PT;
+                    load_prepared(tris + first + t, PT);
+                    V3 Pnew, dir;
+                    if (offset_tri_tests(PT, P, N, dist, Pnew, dir)) return true;
+                }
+            } else if (next < 0) next = cc;
+            else stack[sp++] = cc;
+        }
+        if (next >= 0) node = next;
+        else if (sp) node = stack[--sp];
+        else return false;
+    }
+}
+
+__global__ void __launch_bounds__(LB_BLOCK)
+lumel_classify_kernel(const BvhNode *__restrict__ bvh, const PreparedTri *__restrict__ ptris, uint64_t first, uint64_t n_lumels,
+                      const float4 *__restrict__ lpos, const float4 *__restrict__ lnrm, const float4 *__restrict__ lrad,
+                      uint32_t *__restrict__ list, uint32_t *list_count)
+{
+    const uint64_t i = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool flag = false;
+    if (i < n_lumels) flag = bvh == nullptr || lumel_has_mover(bvh, ptris, ld3(lpos[i]), ld3(lnrm[i]), sqrtf(lrad[i].w));
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (!m) return;
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(list_count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (flag) list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)(i - first);
+}
+
+/* The exact pass for the listed lumels: every instance in order, its tree walked in the reference's order with the sample
+ * position as it stands (ref: lighter.cpp:445-446, lighter_math.cpp:991-1044). */
 #ifndef LB_FIX_MINBLOCKS
-#define LB_FIX_MINBLOCKS 8        /* 64 registers: lumel stage 22.3 ms vs 24.5 uncapped (80 regs) on config 4 */
+#define LB_FIX_MINBLOCKS 6        /* 80 registers: the exact pass only sees the few per cent of lumels near concave edges; no spills */
 #endif
 __global__ void __launch_bounds__(LB_BLOCK, LB_FIX_MINBLOCKS)
-lumel_fix_kernel(const ltrgpu_Inst *__restrict__ inst, uint32_t n_inst, RefView all, const BvhNode *__restrict__ bvh,
-                 const RayTri *__restrict__ raytris, const PreparedTri *__restrict__ ptris, const uint32_t *__restrict__ tri_orig,
-                 uint64_t first, uint64_t n_lumels, float max_correct_dist, float corr_min_dot,
-                 float4 *lpos, const float4 *__restrict__ lnrm, const float4 *__restrict__ lrad, unsigned long long *counters)
+lumel_offset_kernel(const ltrgpu_Inst *__restrict__ inst, uint32_t n_inst, RefView all, uint64_t first, const uint32_t *__restrict__ list,
+                    const uint32_t *__restrict__ list_count, float4 *lpos, const float4 *__restrict__ lnrm, const float4 *__restrict__ lrad)
 {
-    uint64_t i = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned rays = 0;
-    const bool active = i < n_lumels;
+    const uint32_t n = *list_count;
     const unsigned lane = threadIdx.x & 31u;
-    V3 P = mk3(0.f), N = mk3(0.f);
-    float dist = 0.f;
-    if (active) { P = ld3(lpos[i]); N = ld3(lnrm[i]); dist = sqrtf(lrad[i].w); }
-    {
-        /* instances whose tree can matter to ANY lumel of this warp: one instance root box per lane against the
-         * union of the warp's query boxes, then the survivors in ascending order (the reference's order) */
-        float ul[3] = { active ? P.x - dist : INFINITY, active ? P.y - dist : INFINITY, active ? P.z - dist : INFINITY };
-        float uh[3] = { active ? P.x + dist : -INFINITY, active ? P.y + dist : -INFINITY, active ? P.z + dist : -INFINITY };
-        for (int o = 16; o > 0; o >>= 1)
-            for (int a = 0; a < 3; ++a) { ul[a] = fminf(ul[a], __shfl_xor_sync(0xffffffffu, ul[a], o)); uh[a] = fmaxf(uh[a], __shfl_xor_sync(0xffffffffu, uh[a], o)); }
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t w0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; w0 < n; w0 += warps * 32u) {
+        const bool active = w0 + lane < n;
+        uint64_t i = 0;
+        V3 P = mk3(0.f), N = mk3(0.f);
+        float dist = 0.f;
+        if (active) { i = first + list[w0 + lane]; P = ld3(lpos[i]); N = ld3(lnrm[i]); dist = sqrtf(lrad[i].w); }
         for (uint32_t base = 0; base < n_inst; base += 32) {
-            const uint32_t m = base + lane;
-            bool ok = false;
-            if (m < n_inst) {
-                const RefNode R = all.nodes[inst[m].node_off];
-                ok = !(ul[0] > R.hi.x || uh[0] < R.lo.x || ul[1] > R.hi.y || uh[1] < R.lo.y || ul[2] > R.hi.z || uh[2] < R.lo.z);
-            }
-            unsigned mask = __ballot_sync(0xffffffffu, ok);
-            while (mask) {
+            /* instances of this group whose root box meets the union of the lanes' query boxes AS THE SAMPLES STAND NOW;
+             * the union is taken again whenever an instance has moved a sample (the reference builds the query box of
+             * every instance around the current position) */
+            int done_to = (int)base - 1;
+            bool fresh = true;
+            unsigned mask = 0;
+            for (;;) {
+                if (fresh) {
+                    float ul[3] = { active ? P.x - dist : INFINITY, active ? P.y - dist : INFINITY, active ? P.z - dist : INFINITY };
+                    float uh[3] = { active ? P.x + dist : -INFINITY, active ? P.y + dist : -INFINITY, active ? P.z + dist : -INFINITY };
+                    for (int o = 16; o > 0; o >>= 1)
+                        for (int a = 0; a < 3; ++a) { ul[a] = fminf(ul[a], __shfl_xor_sync(0xffffffffu, ul[a], o)); uh[a] = fmaxf(uh[a], __shfl_xor_sync(0xffffffffu, uh[a], o)); }
+                    const uint32_t m = base + lane;
+                    bool ok = false;
+                    if (m < n_inst && (int)m > done_to) {
+                        const RefNode R = all.nodes[inst[m].node_off];
+                        ok = !(ul[0] > R.hi.x || uh[0] < R.lo.x || ul[1] > R.hi.y || uh[1] < R.lo.y || ul[2] > R.hi.z || uh[2] < R.lo.z);
+                    }
+                    mask = __ballot_sync(0xffffffffu, ok);
+                    fresh = false;
+                }
+                if (!mask) break;
                 const uint32_t mm = base + (uint32_t)__ffs(mask) - 1u;
                 mask &= mask - 1u;
+                done_to = (int)mm;
                 const ltrgpu_Inst I = inst[mm];
                 RefView v = { all.nodes + I.node_off, all.items + I.item_off, all.tris9 + 9ull * I.tri_off, all.ptris + I.tri_off, all.boxes + 2ull * I.tri_off };
-                reftree_offset_sample(v, P, N, dist, active);
+                const V3 before = P;
+                reftree_offset_sample(v, P, N, dist, active);     /* lanes whose own box misses the tree fall out at its root */
+                if (__any_sync(0xffffffffu, P.x != before.x || P.y != before.y || P.z != before.z)) fresh = true;
             }
         }
+        if (active) lpos[i] = make_float4(P.x, P.y, P.z, 0.f);
     }
-    if (active) {
-        if (max_correct_dist) {
-            int itsleft = 100;
-            float md = max_correct_dist;
-            V3 PEnd = P + N * md;
-            while (md > LB_SMALL && itsleft-- > 0) {
-                V3 dn = norm3(PEnd - P);
-                V3 mA = P + dn * LB_SMALL, mB = PEnd - dn * LB_SMALL;
-                int slot = -1;
-                TravStats ts = { 0, 0 };
-                float q = bvh_segment<false>(bvh, raytris, tri_orig, mA, mB, &slot, ts);
-                ++rays;
-                V3 hitnrm = mk3(0.f);
-                if (slot >= 0) {
-                    const PreparedTri *T = ptris + slot;
-                    hitnrm = tri_back_normal(T->t0, T->t1, T->t2);
-                }
-                if (-dot3(hitnrm, N) < corr_min_dot) break;
-                if (q < LB_SMALL) q = LB_SMALL;
-                P = P * (1.0f - q) + PEnd * q;
-                md *= (1.0f - q);
+}
+
+/* Overlap correction (ref: lighter.cpp:449-465): up to 100 closest-hit probes along the normal; one lumel per thread,
+ * neighbouring lumels in a warp. */
+#ifndef LB_CORR_MINBLOCKS
+#define LB_CORR_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(LB_BLOCK, LB_CORR_MINBLOCKS)
+lumel_correct_kernel(const BvhNode *__restrict__ bvh, const RayTri *__restrict__ raytris, const PreparedTri *__restrict__ ptris, const uint32_t *__restrict__ tri_orig,
+                     uint64_t first, uint64_t n_lumels, float max_correct_dist, float corr_min_dot,
+                     float4 *lpos, const float4 *__restrict__ lnrm, unsigned long long *counters)
+{
+    const uint64_t i = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned rays = 0;
+    if (i < n_lumels) {
+        V3 P = ld3(lpos[i]);
+        const V3 N = ld3(lnrm[i]);
+        int itsleft = 100;
+        float md = max_correct_dist;
+        const V3 PEnd = P + N * md;
+        while (md > LB_SMALL && itsleft-- > 0) {
+            V3 dn = norm3(PEnd - P);
+            V3 mA = P + dn * LB_SMALL, mB = PEnd - dn * LB_SMALL;
+            int slot = -1;
+            TravStats ts = { 0, 0 };
+            float q = bvh_segment<false>(bvh, raytris, tri_orig, mA, mB, &slot, ts);
+            ++rays;
+            V3 hitnrm = mk3(0.f);
+            if (slot >= 0) {
+                const PreparedTri *T = ptris + slot;
+                hitnrm = tri_back_normal(T->t0, T->t1, T->t2);
             }
+            if (-dot3(hitnrm, N) < corr_min_dot) break;
+            if (q < LB_SMALL) q = LB_SMALL;
+            P = P * (1.0f - q) + PEnd * q;
+            md *= (1.0f - q);
         }
         lpos[i] = make_float4(P.x, P.y, P.z, 0.f);
     }
@@ -533,10 +641,32 @@ extern "C" int ltrgpu_generate_lumels(ltrgpu_Ctx *ctx, uint64_t *inst_lumel_off)
         if (b < ctx->n_probes) b = ctx->n_probes;
         RefView all = { ctx->d_rnodes, ctx->d_ritems, ctx->d_rtree_tris, ctx->d_rtree_ptris, ctx->d_rtree_boxes };
         if (e > b) {
-            lumel_fix_kernel<<<grid_for(e - b, LB_BLOCK), LB_BLOCK, 0, st>>>(
-                ctx->d_inst, ctx->n_inst, all, ctx->d_bvh, ctx->d_raytris, ctx->d_ptris, ctx->d_tri_orig, b, e,
-                ctx->params.max_correct_dist, ctx->params.corr_min_dot, ctx->d_lpos, ctx->d_lnrm, ctx->d_lrad, ctx->d_counters);
+            /* 1. which lumels can the concave-edge offset move (flat BVH over the triangles of every instance tree; without
+             *    one -- LTR_LUMEL_CLASSIFY=0, or a scene too small to have it -- every lumel takes the exact pass) */
+            uint32_t *d_list = nullptr, *d_list_count = nullptr;
+            if (dev_alloc(ctx, &d_list, e - b)) return 1;
+            if (dev_alloc(ctx, &d_list_count, 1)) return 1;
+            CU_TRY(ctx, cudaMemsetAsync(d_list_count, 0, 4, st));
+            const bool classify = ctx->d_lbvh != nullptr && !getenv("LTR_LUMEL_CLASSIFY_OFF");
+            lumel_classify_kernel<<<grid_for(e - b, LB_BLOCK), LB_BLOCK, 0, st>>>(classify ? ctx->d_lbvh : nullptr, ctx->d_lbvh_ptris, b, e, ctx->d_lpos, ctx->d_lnrm,
+                                                                                 ctx->d_lrad, d_list, d_list_count);
             CU_LAUNCH_CHECK(ctx);
+            /* 2. the exact reference-order pass over the listed lumels (persistent warps over a device-side count) */
+            lumel_offset_kernel<<<(unsigned)ctx->num_sms * 8u, LB_BLOCK, 0, st>>>(ctx->d_inst, ctx->n_inst, all, b, d_list, d_list_count, ctx->d_lpos, ctx->d_lnrm, ctx->d_lrad);
+            CU_LAUNCH_CHECK(ctx);
+            /* 3. overlap correction of every lumel */
+            if (ctx->params.max_correct_dist) {
+                lumel_correct_kernel<<<grid_for(e - b, LB_BLOCK), LB_BLOCK, 0, st>>>(ctx->d_bvh, ctx->d_raytris, ctx->d_ptris, ctx->d_tri_orig, b, e,
+                                                                                    ctx->params.max_correct_dist, ctx->params.corr_min_dot, ctx->d_lpos, ctx->d_lnrm, ctx->d_counters);
+                CU_LAUNCH_CHECK(ctx);
+            }
+            if (getenv("LTR_TRACE")) {
+                uint32_t hc = 0;
+                CU_TRY(ctx, cudaMemcpyAsync(&hc, d_list_count, 4, cudaMemcpyDeviceToHost, st));
+                CU_TRY(ctx, cudaStreamSynchronize(st));
+                fprintf(stderr, "[ltr rank %d] lumel offset: %u of %llu lumels take the reference-order pass\n", ctx->rank, hc, (unsigned long long)(e - b));
+            }
+            lb_free(d_list); lb_free(d_list_count);
         }
         if (world > 1) {
             if (!ctx->allgather || ctx->allgather(ctx->allgather_user, ctx->d_lpos + chunk * ctx->rank, ctx->d_lpos, chunk * sizeof(float4), st)) {

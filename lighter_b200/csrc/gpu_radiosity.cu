@@ -762,13 +762,9 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
         fprintf(stderr, "[ltr rank %d] radiosity %-22s %8.2f ms\n", ctx->rank, label, (t_.tv_sec - tr0.tv_sec) * 1e3 + (t_.tv_nsec - tr0.tv_nsec) * 1e-6); tr0 = t_; } } while (0)
 
     {
-        /* the emitted light of EVERY lumel is needed: gather the direct-light shards first */
-        if (world > 1) {
-            const uint64_t chunk = (n + world - 1) / world;
-            RAD_TRY(rad_allgather(ctx, ctx->d_lrgb, chunk, "direct light"));
-        }
+        /* the emitted light of EVERY lumel is needed: the direct stage has left the colours of all lumels on every rank
+         * (its own exchange, gpu_direct.cu) */
         lrgb_full = ctx->d_lrgb;
-        RAD_TRACE("gather direct light");
 
         /* ---- 1. Morton sort ---- */
         RAD_TRY(dev_alloc(ctx, &mkeys, n)); RAD_TRY(dev_alloc(ctx, &mkeys_alt, n));

@@ -242,6 +242,7 @@ extern "C" void ltrgpu_destroy(ltrgpu_Ctx *ctx)
     free_bake_state(ctx);
     dev_free(&ctx->d_inst); dev_free(&ctx->d_wpos); dev_free(&ctx->d_wnrm); dev_free(&ctx->d_vtex); dev_free(&ctx->d_ltex);
     dev_free(&ctx->d_rtris); dev_free(&ctx->d_rnodes); dev_free(&ctx->d_ritems); dev_free(&ctx->d_rtree_tris); dev_free(&ctx->d_rtree_ptris); dev_free(&ctx->d_rtree_boxes);
+    if (ctx->lbvh_owned) { lb_free(ctx->d_lbvh); lb_free(ctx->d_lbvh_ptris); }
     dev_free(&ctx->d_bvh); dev_free(&ctx->d_bvh4); dev_free(&ctx->d_ptris); dev_free(&ctx->d_raytris); dev_free(&ctx->d_tri_orig);
     dev_free(&ctx->d_lights); dev_free(&ctx->d_light_inst); dev_free(&ctx->d_light_samples); dev_free(&ctx->d_probe_pos); dev_free(&ctx->d_probe_nrm);
     dev_free(&ctx->d_ao_cos); dev_free(&ctx->d_ao_sin); dev_free(&ctx->d_blur_kernel); dev_free(&ctx->d_counters);
@@ -379,6 +380,21 @@ extern "C" int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *d)
         snprintf(ctx->err, sizeof(ctx->err), "scene BVH is %d levels deep; the traversal stacks hold 40", ctx->bvh_height);
         return 1;
     }
+    /* flat BVH over the triangles of every instance tree, for lumel_classify_kernel (gpu_lumels.cu) */
+    if (ctx->lbvh_owned) { lb_free(ctx->d_lbvh); lb_free(ctx->d_lbvh_ptris); }
+    ctx->d_lbvh = nullptr; ctx->d_lbvh_ptris = nullptr; ctx->lbvh_owned = false;
+    if (d->scene_covers_rtree) { ctx->d_lbvh = ctx->d_bvh; ctx->d_lbvh_ptris = ctx->d_ptris; }
+    else if (d->n_rtree_tris > (uint32_t)(d->bvh_leaf_max > 0 ? d->bvh_leaf_max : BVH_LEAF_MAX)) {
+        LbDeviceBvh T;
+        if (lb_build_bvh_device(ctx->stream, ctx->d_rtree_tris, d->n_rtree_tris, d->bvh_leaf_max > 0 ? d->bvh_leaf_max : BVH_LEAF_MAX, ctx->num_sms, &T, ctx->err, sizeof(ctx->err))) return 1;
+        ctx->host_counters.kernel_launches += T.launches;
+        ctx->d_lbvh = T.nodes; ctx->lbvh_owned = true;
+        CU_TRY(ctx, lb_malloc(&ctx->d_lbvh_ptris, (size_t)d->n_rtree_tris * sizeof(PreparedTri)));
+        prepare_tris_kernel<<<grid_for(d->n_rtree_tris, 256), 256, 0, ctx->stream>>>(ctx->d_rtree_tris, T.order, d->n_rtree_tris, ctx->d_lbvh_ptris, nullptr);
+        CU_LAUNCH_CHECK(ctx);
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        lb_free(T.nodes4); lb_free(T.order);
+    }
     /* reference-order triangles (lumel generation): point-query terms precomputed once instead of per query */
     if (dev_alloc(ctx, &ctx->d_rtree_ptris, d->n_rtree_tris)) return 1;
     if (dev_alloc(ctx, &ctx->d_rtree_boxes, (size_t)d->n_rtree_tris * 2)) return 1;
@@ -408,7 +424,7 @@ extern "C" int ltrgpu_set_world(ltrgpu_Ctx *ctx, int rank, int world, ltrgpu_all
     return 0;
 }
 
-extern "C" int ltrgpu_set_allreduce(ltrgpu_Ctx *ctx, ltrgpu_allreduce_fn allreduce) { ctx->allreduce = allreduce; return 0; }
+extern "C" int ltrgpu_set_gatherv(ltrgpu_Ctx *ctx, ltrgpu_gatherv_fn gatherv) { ctx->gatherv = gatherv; return 0; }
 
 extern "C" int ltrgpu_set_shard(ltrgpu_Ctx *ctx, uint64_t begin, uint64_t end, int rank, int world,
                                 ltrgpu_allgather_fn allgather, void *allgather_user)

@@ -15,7 +15,9 @@ struct NcclApi {
     int (*CommInitRank)(void **comm, int nranks, NcclId id, int rank);
     int (*CommDestroy)(void *comm);
     int (*AllGather)(const void *send, void *recv, size_t count, int dtype, void *comm, void *stream);
-    int (*AllReduce)(const void *send, void *recv, size_t count, int dtype, int op, void *comm, void *stream);
+    int (*Broadcast)(const void *send, void *recv, size_t count, int dtype, int root, void *comm, void *stream);
+    int (*GroupStart)(void);
+    int (*GroupEnd)(void);
     const char *(*GetErrorString)(int);
 };
 

@@ -76,6 +76,7 @@ struct ltr_Scene {
     /* diagnostics */
     ltrx_Stats stats;
     std::string error;                        /* first fatal error of the bake, "" if none */
+    std::string failed_stage;                 /* "failed: <error>": the stage string ltr_GetStatus hands out after a failed bake */
     int shadow_mode = 0;                      /* 0 = reference distance march, 1 = sampled any-hit shadow rays (ltrx_SetShadowMode) */
     int keep_debug = 0;                       /* keep stage arrays for ltrx_Get* */
     struct Bake *bake = nullptr;              /* pipeline state incl. device buffers (bake.cpp) */

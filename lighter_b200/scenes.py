@@ -319,7 +319,43 @@ def scene_rad1() -> Scene:
     return s
 
 
+def scene_corner(normalmap: int = 0) -> Scene:
+    """Three separate instances meeting in one concave corner (floor, wall at x=0, wall at y=0) plus a low step lying on
+    the floor: lumels next to an edge are pushed by one instance's triangles and then tested against the next instance
+    at the MOVED position (ref: lighter.cpp:445-446, lighter_math.cpp:1040-1044).  Not a scenario of the reference's own
+    driver; parity fixtures for it come from the live reference."""
+    s = Scene("corner")
+    s.cfg.update(ao_distance=1.0, blur_size=0.0, generate_normalmap_data=normalmap, global_size_factor=6.0)
+    const = lambda v: (lambda p: np.tile(np.asarray(v, np.float64), (len(p), 1)))
+    g = 0.04
+    floor = _grid_patch(np.array([0.0, 0.0, 0.0]), np.array([4.0, 0, 0]), np.array([0, 4.0, 0]), 5, 5, const((0, 0, 1)), (g, g, 1 - g, 1 - g))
+    wallx = _grid_patch(np.array([0.0, 4.0, 0.0]), np.array([0, -4.0, 0]), np.array([0, 0, 3.0]), 4, 3, const((1, 0, 0)), (g, g, 1 - g, 1 - g))
+    wally = _grid_patch(np.array([0.0, 0.0, 0.0]), np.array([4.0, 0, 0]), np.array([0, 0, 3.0]), 3, 4, const((0, 1, 0)), (g, g, 1 - g, 1 - g))
+    for k, (name, (pos, nrm, uv, idx)) in enumerate((("floor", floor), ("wallx", wallx), ("wally", wally))):
+        s.meshes.append(Mesh(name, [Part(pos, nrm, uv.copy(), uv, idx, 1)]))
+        s.instances.append(Instance(k, IDENTITY.copy(), 1.0, 1, name))
+    # the step: a box 1.2 x 0.9 x 0.35 standing in the corner region, five faces, one instance, rotated a little about z
+    x0, x1, y0, y1, z1 = 0.0, 1.2, 0.0, 0.9, 0.35
+    faces = [(np.array([x0, y0, 0.0]), np.array([x1 - x0, 0, 0.0]), np.array([0, 0, z1]), (0, -1, 0)),
+             (np.array([x1, y0, 0.0]), np.array([0, y1 - y0, 0.0]), np.array([0, 0, z1]), (1, 0, 0)),
+             (np.array([x1, y1, 0.0]), np.array([x0 - x1, 0, 0.0]), np.array([0, 0, z1]), (0, 1, 0)),
+             (np.array([x0, y1, 0.0]), np.array([0, y0 - y1, 0.0]), np.array([0, 0, z1]), (-1, 0, 0)),
+             (np.array([x0, y0, z1]), np.array([x1 - x0, 0, 0.0]), np.array([0, y1 - y0, 0.0]), (0, 0, 1))]
+    pos, nrm, uv, idx, base = [], [], [], [], 0
+    for k, (o, du, dv, nn) in enumerate(faces):
+        p, n_, t, i = _grid_patch(o, du, dv, 2, 2, const(nn), (k * 0.2 + 0.02, 0.02, (k + 1) * 0.2 - 0.02, 0.5))
+        pos.append(p); nrm.append(n_); uv.append(t); idx.append(i + base); base += len(p)
+    s.meshes.append(Mesh("step", [Part(np.concatenate(pos), np.concatenate(nrm), np.concatenate(uv).copy(), np.concatenate(uv), np.concatenate(idx), 1)]))
+    c, sn = np.float32(np.cos(0.3)), np.float32(np.sin(0.3))
+    m = np.array([[c, sn, 0, 0], [-sn, c, 0, 0], [0, 0, 1, 0], [0.9, 0.6, 0.0, 1]], np.float32)
+    s.instances.append(Instance(3, m, 1.0, 1, "step"))
+    s.lights.append(Light(LT_POINT, (2.5, 2.2, 2.4), color_rgb=(0.9, 0.8, 0.6), range=9.0, power=1.0, light_radius=0.15, shadow_sample_count=4))
+    s.lights.append(Light(LT_SPOT, (3.4, 0.8, 2.0), (-0.6, 0.1, -0.8), (1.0, 0.0, 0.0), (0.2, 0.5, 0.9), 8.0, 1.0, 0.1, 4, 50.0, 20.0, 0.7))
+    return s
+
+
 NAMED = {
+    "corner": scene_corner,
     "basic": scene_basic, "hugeoverlap": scene_hugeoverlap, "mesh1": scene_mesh1,
     "mesh2": scene_mesh2, "rad1": scene_rad1,
 }

@@ -6,6 +6,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 from conftest import GOLD, ROOT
 from lighter_b200 import api, scenes
@@ -131,3 +132,32 @@ def test_ltr_sleep():
     t0 = time.perf_counter()
     api.lib().ltr_Sleep(20)
     assert 0.015 < time.perf_counter() - t0 < 0.5
+
+
+def test_failed_bake_is_visible_through_the_plain_api():
+    """Without a CUDA device (this suite runs on CPU) a bake must FAIL LOUDLY -- there is no CPU fallback -- and a caller that
+    only knows lighter.h must be able to see it: ltr_GetStatus ends the polling loop with the stage "failed: ...", no outputs."""
+    import ctypes as C
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a CUDA device is present: nothing fails")
+    except ImportError:
+        pass
+    from lighter_b200 import scenes
+    h = api.BakeHandle(scenes.scene_basic())
+    L = api.lib()
+    st = api.WorkStatus()
+    L.ltr_Start(h.h)
+    for _ in range(20000):
+        if not L.ltr_GetStatus(h.h, C.byref(st)):
+            break
+        L.ltr_Sleep(1)
+    assert not L.ltr_GetStatus(h.h, C.byref(st))
+    assert st.stage.startswith(b"failed: "), st.stage
+    assert b"CUDA" in st.stage or b"device" in st.stage
+    info = api.WorkOutputInfo()
+    L.ltr_GetWorkOutputInfo(h.h, C.byref(info))
+    assert info.lightmap_count == 0
+    assert L.ltrx_GetError(h.h).decode() in st.stage.decode()
+    h.close()

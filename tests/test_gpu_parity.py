@@ -69,6 +69,39 @@ def test_bvh_queries_equal_brute_force(oracle, ntris, leaf, monkeypatch):
     assert bits_equal(q["closest"], c) and np.array_equal(q["closest_tri"], tid)
 
 
+def test_anyhit_of_segments_lying_in_box_face_planes(oracle):
+    """Segments with an exactly zero direction component whose origin lies exactly ON a face of the boxes they must enter
+    (lumels on the shared edge of two tiles, wall lumels: x = 25.0 on both ends).  The reference skips such an axis in its
+    ray/box test (lighter_math.cpp:618-650); a slab test that turns the face's term into 0 loses these hits (round-1 bug:
+    16 of 22 561 links of the config-4 sibling)."""
+    g = np.arange(0, 9, dtype=np.float32) * np.float32(3.125)                     # exactly representable grid lines 0 .. 25
+    quads = []
+    for i in range(8):
+        for j in range(8):
+            x0, x1, y0, y1 = g[i], g[i + 1], g[j], g[j + 1]
+            z = np.float32(0.25) * np.sin(np.float32(0.9) * np.array([x0, x1, x1, x0], np.float32)) * np.cos(np.float32(0.7) * np.array([y0, y0, y1, y1], np.float32))
+            p = [(x0, y0, z[0]), (x1, y0, z[1]), (x1, y1, z[2]), (x0, y1, z[3])]
+            quads.append([*p[0], *p[1], *p[2]]); quads.append([*p[2], *p[3], *p[0]])
+    tris = np.array(quads, np.float32)
+    rng = np.random.default_rng(3)
+    n = 900
+    a = np.zeros((n, 3), np.float32); b = np.zeros((n, 3), np.float32)
+    plane = rng.choice(g, n)                                                      # a grid line: the face of every box next to it
+    axis = rng.integers(0, 2, n)
+    u0, u1 = rng.uniform(0, 25, n).astype(np.float32), rng.uniform(0, 25, n).astype(np.float32)
+    for k in range(n):
+        o = 1 - axis[k]
+        a[k, axis[k]] = b[k, axis[k]] = plane[k]
+        a[k, o], b[k, o] = u0[k], u1[k]
+        a[k, 2], b[k, 2] = rng.uniform(0.3, 4.0), rng.uniform(-0.6, -0.05)        # from above the terrain to below it: blocked
+    q = api.test_scene_queries(tris, a, b)
+    want = oracle.anyhit_raw(tris, a, b)
+    assert np.array_equal(q["anyhit"], want)
+    assert want.sum() > n // 2
+    c, tid = oracle.closest_raw(tris, a, b)
+    assert bits_equal(q["closest"], c) and np.array_equal(q["closest_tri"], tid)
+
+
 def test_empty_scene_queries():
     a = np.zeros((4, 3), np.float32); b = np.ones((4, 3), np.float32)
     q = api.test_scene_queries(np.zeros((0, 9), np.float32), a, b)
@@ -182,10 +215,12 @@ def test_radiosity_pair_sweep_group_sizes_agree_on_config4_sibling(monkeypatch):
         assert key == base[0], (group, key, base[0])
         for a, b in zip(out["lightmaps"], base[1]["lightmaps"]):
             assert bits_equal(a["rgb"], b["rgb"]), group
+    assert base[0] == (486607, 2 * 22561)            # the reference's own counts (tests/golden/ref_counts.json; links: brute force == reference)
     if parity.have_reference():
         ref = parity.run_reference(sc, threads=1, internals=False)
         for a, b in zip(base[1]["lightmaps"], ref["lightmaps"]):
-            assert parity.meets_bar(parity.texel_parity(a["rgb"], b["rgb"]))
+            p = parity.texel_parity(a["rgb"], b["rgb"])
+            assert parity.meets_bar(p) and p["max"] <= 1, p
 
 
 def test_radiosity_small_candidate_buffer_forces_batches_and_retries(bakes, monkeypatch):
@@ -213,7 +248,8 @@ def test_ray_counts_equal_reference_instrumented_counts():
 
 # ---- live against the reference on this host (when oracle/_ref travelled) ----------------------------
 def _variant(name):
-    sc = scenes.NAMED[name.split("+")[0]]()
+    base = name.split("+")[0]
+    sc = scenes.NAMED[base]() if base in scenes.NAMED else scenes.workload(base)
     if "+ds2x" in name:
         sc.cfg["ds2x"] = 1
     if "+blur" in name:
@@ -229,11 +265,18 @@ def _variant(name):
             lt.power = 0.0
     if "+noshadowinst" in name:
         sc.instances[0].shadow = 0
+    if "+nolights" in name:
+        sc.lights = []
+    if "+normalmap" in name:
+        sc.cfg["generate_normalmap_data"] = 1
+    if "+noshadowstep" in name:
+        sc.instances[3].shadow = 0          # corner: the step keeps its tree (it still pushes samples) but leaves the scene BVH
     return sc
 
 
 @pytest.mark.parametrize("name", ["mesh1+ds2x+blur", "mesh1+aoneg+ambient+probes", "rad1+probes+ambient", "basic+power0",
-                                  "mesh2+noshadowinst", "basic+probes"])
+                                  "mesh2+noshadowinst", "basic+probes", "config3_sibling", "config4_sibling", "corner", "corner+normalmap",
+                                  "corner+noshadowstep", "mesh2+nolights+ambient", "mesh1+nolights+normalmap+ambient"])
 def test_config_variants_against_live_reference(name):
     if not parity.have_reference():
         pytest.skip("oracle/_ref not on this box")
@@ -246,11 +289,30 @@ def test_config_variants_against_live_reference(name):
         assert (a["uid"], a["width"], a["height"]) == (b["uid"], b["width"], b["height"])
         p = parity.texel_parity(a["rgb"], b["rgb"])
         assert parity.meets_bar(p) and p["max"] <= 1, (name, p)
+        assert (a["normals"] is None) == (b["normals"] is None)
+        if a["normals"] is not None:
+            dn = np.abs(parity.quantize8(a["normals"] * 0.5 + 0.5) - parity.quantize8(b["normals"] * 0.5 + 0.5))
+            assert dn.mean() <= 0.01 and (dn.max(axis=2) <= 2).mean() >= 0.995, (name, float(dn.mean()))
     for a, b in zip(out["instances"], ref["instances"]):
         if a["n"]:
-            assert bits_equal(a["pos"], b["pos"])
+            assert bits_equal(a["pos"], b["pos"]), name
     if len(ref["probes"]):
         assert np.abs(out["probes"] - ref["probes"]).max() < 1e-6
+
+
+def test_lumel_classification_does_not_change_any_position(monkeypatch):
+    """The pre-pass that lists the lumels a concave-edge offset can move (lumel_classify_kernel) against the exact
+    reference-order pass over EVERY lumel (LTR_LUMEL_CLASSIFY_OFF=1): identical positions, and the list is short."""
+    for name in ("corner", "mesh2", "config4_sibling"):
+        sc = _variant(name)
+        a = api.bake(sc, debug=True)
+        monkeypatch.setenv("LTR_LUMEL_CLASSIFY_OFF", "1")
+        b = api.bake(sc, debug=True)
+        monkeypatch.delenv("LTR_LUMEL_CLASSIFY_OFF")
+        for x, y in zip(a["instances"], b["instances"]):
+            assert bits_equal(x["pos"], y["pos"]), name
+        for x, y in zip(a["lightmaps"], b["lightmaps"]):
+            assert bits_equal(x["rgb"], y["rgb"]), name
 
 
 def test_degenerate_inputs():
