@@ -92,6 +92,8 @@ LTRAPI const char *ltrx_GetError(ltr_Scene *scene);   /* "" when the last bake s
 LTRAPI int         ltrx_Prepare(ltr_Scene *scene);    /* host pre-pass + upload; synchronous */
 LTRAPI int         ltrx_BakeResident(ltr_Scene *scene, float *gpu_ms_out); /* GPU stages only, synchronous */
 LTRAPI int         ltrx_Finish(ltr_Scene *scene);     /* read back outputs after ltrx_BakeResident */
+/* FNV-1a-64 of the float bytes of all lightmaps in output order followed by the probe colours (0 = no outputs yet) */
+LTRAPI int         ltrx_OutputHash(ltr_Scene *scene, uint64_t *fnv1a64);
 
 /* stage dumps (valid after a bake run with ltrx_SetDebug(scene,1)) --------------------------- */
 LTRAPI int ltrx_SetDebug(ltr_Scene *scene, int keep_stage_arrays);

@@ -156,7 +156,7 @@ LTR_SYMBOLS = ["ltr_DefaultSizeFunc", "ltr_CreateScene", "ltr_DestroyScene", "lt
                "ltr_Sleep", "ltr_GetConfig", "ltr_SetConfig", "ltr_CreateMesh", "ltr_MeshAddPart", "ltr_MeshAddInstance",
                "ltr_LightAdd", "ltr_SampleAdd", "ltr_GetWorkOutputInfo", "ltr_GetWorkOutput", "ltr_NextPowerOfTwo"]
 LTRX_SYMBOLS = ["ltrx_Version", "ltrx_SetDevice", "ltrx_NcclUniqueId", "ltrx_SetShard", "ltrx_ShardRange", "ltrx_GetStats",
-                "ltrx_GetError", "ltrx_Prepare", "ltrx_BakeResident", "ltrx_Finish", "ltrx_SetDebug", "ltrx_GetLumels",
+                "ltrx_GetError", "ltrx_Prepare", "ltrx_BakeResident", "ltrx_Finish", "ltrx_OutputHash", "ltrx_SetDebug", "ltrx_GetLumels",
                 "ltrx_GetLinks", "ltrx_GetShadowFactors", "ltrx_SetShadowMode", "ltrx_GetShadowMasks", "ltrx_ShadowSampleSegment",
                 "ltrx_test_point_tri_distance", "ltrx_test_seg_tri",
                 "ltrx_test_scene_queries", "ltrx_test_device_bvh", "ltrx_test_march", "ltrx_test_spiral_dirs", "ltrx_test_reftree", "ltrx_test_bvh", "ltrx_test_bvh_entry", "ltrx_test_bvh_entry_cost", "ltrx_test_host_prepare", "ltrx_test_rad_cull",
@@ -208,6 +208,7 @@ def lib() -> C.CDLL:
     L.ltrx_test_host_prepare.argtypes = [vp, C.c_void_p]
     L.ltrx_BakeResident.argtypes = [vp, C.POINTER(C.c_float)]
     L.ltrx_Finish.argtypes = [vp]
+    L.ltrx_OutputHash.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.ltrx_SetDebug.argtypes = [vp, C.c_int]
     L.ltrx_GetLumels.argtypes = [vp, u32, C.POINTER(Lumels)]
     L.ltrx_GetLinks.argtypes = [vp, C.POINTER(Links)]
@@ -393,6 +394,13 @@ class BakeHandle:
         if not self.L.ltrx_Finish(self.h):
             self._raise_on_error()
             raise RuntimeError("ltrx_Finish failed")
+
+    def output_hash(self) -> str:
+        """FNV-1a-64 (hex) of all lightmaps + probe colours of the last bake, computed by the library over its own output arrays."""
+        h = C.c_uint64(0)
+        if not self.L.ltrx_OutputHash(self.h, C.byref(h)):
+            return ""
+        return f"{h.value:016x}"
 
     def stats(self) -> dict:
         s = Stats()

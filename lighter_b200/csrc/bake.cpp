@@ -933,6 +933,18 @@ int ltrx_Finish(ltr_Scene *scene)
 
 int ltrx_SetDebug(ltr_Scene *scene, int keep) { scene->keep_debug = keep; return 1; }
 
+/* FNV-1a-64 over the float bytes of every lightmap in output order (the fingerprint SURVEY 8c uses for the reference's
+ * lightmap_rgb arrays), then over the probe colours; bench.py prints it and checks a sharded bake against the single-GPU one */
+int ltrx_OutputHash(ltr_Scene *scene, uint64_t *fnv1a64)
+{
+    uint64_t h = 1469598103934665603ull;
+    auto feed = [&h](const void *p, size_t n) { const unsigned char *c = (const unsigned char *)p; for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 1099511628211ull; } };
+    for (const ltr_WorkOutput &wo : scene->outputs) feed(wo.lightmap_rgb, (size_t)wo.width * wo.height * 12);
+    for (const ltr_SampleInfo &p : scene->probes) feed(p.out_color, 12);
+    *fnv1a64 = h;
+    return scene->outputs.empty() && scene->probes.empty() ? 0 : 1;
+}
+
 int ltrx_GetLumels(ltr_Scene *scene, u32 instance, ltrx_Lumels *out)
 {
     Bake *B = scene->bake;

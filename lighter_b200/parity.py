@@ -65,6 +65,32 @@ def run_reference(scene: scenes.Scene, threads: int = 1, internals: bool = True,
         return scenes.read_output(op)
 
 
+REF_STAGES = ("transforming spatial data", "generating data structures", "generating samples", "rendering lightmaps", "calculating radiosity",
+              "bouncing light", "committing radiosity", "rendering ambient occlusion", "exporting lightmaps")
+
+
+def run_reference_timed(scene: scenes.Scene, threads: int = 0, timeout: float = 3600) -> dict:
+    """One bake of the UNMODIFIED reference with its stage transitions time-stamped by the driver's 200 us polling loop
+    (oracle/bake_driver.cpp prints `[ t s] stage` on stderr): wall seconds per reference stage (lighter.cpp:1052-1138)."""
+    if not have_reference():
+        raise RuntimeError("oracle/_ref/ref_bake is missing: run `make -C oracle ref` where /root/reference exists")
+    import re
+    with tempfile.TemporaryDirectory() as td:
+        sp, op = os.path.join(td, "scene.bin"), os.path.join(td, "out.bin")
+        scene.write(sp)
+        cmd = [REF_BAKE, sp, op]
+        if threads > 0:
+            cmd += ["--threads", str(threads)]
+        r = subprocess.run(cmd, check=True, timeout=timeout, capture_output=True, text=True)
+        out = scenes.read_output(op)
+    marks = [(float(t), name.strip()) for t, name in re.findall(r"\[\s*([0-9.]+)s\]\s+(.*)", r.stderr)]
+    stage_s = {}
+    for k, (t, name) in enumerate(marks):
+        end = marks[k + 1][0] if k + 1 < len(marks) else out["wall_s"]
+        stage_s[name] = stage_s.get(name, 0.0) + max(end - t, 0.0)
+    return dict(wall_s=out["wall_s"], threads=out["threads"], stage_s=stage_s, lightmaps=out["lightmaps"])
+
+
 def fnv1a64(data: bytes) -> int:
     h = 0xcbf29ce484222325
     for x in data:
