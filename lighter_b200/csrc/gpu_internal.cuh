@@ -564,6 +564,116 @@ __device__ __forceinline__ bool bvh4_anyhit_entries(const Bvh4Node *__restrict__
 }
 
 /*
+ * The entry-set walk again, with the box tests in FMA form (rad_visibility_kernel; LB_VIS_FMA=0 selects the plain form for A/B).
+ *
+ *   t = (face - o) * inv  =  fma(face, inv, -(o * inv))          one instruction per face instead of two
+ *
+ * The product o * inv is rounded once per ray, so t carries an absolute error of ~2^-24 |o * inv| (1e-4 and more for short
+ * rays far from the origin): this form can only be used as a CONSERVATIVE pre-filter -- its slack `eps` covers that error,
+ * so it never rejects a box the plain test accepts.  What keeps the results bit-identical to the plain walk: an inner child
+ * that passes too easily only costs a visit, and a LEAF child that passes is re-tested with the plain, exact-as-before
+ * arithmetic (lb_slab_inv / lb_slab_origin_hi, slack 2e-6) before its triangles are queued -- the set of triangles tested,
+ * and with it every hit / miss, is that of bvh4_anyhit_entries.  Per ray: 4.4 node visits x 4 children x 6 instructions and
+ * 7 entry boxes x 6 instructions fewer, ~1.5 exact re-tests more.
+ * The ray's origin and direction are only needed by the re-test and by the triangle tests: they wait in shared memory
+ * (6 floats per thread, [component][thread]) instead of occupying six registers across the node loop.
+ */
+struct SlabF { float ix, iy, iz, nlx, nly, nlz, nhx, nhy, nhz, eps; };
+
+__device__ __forceinline__ SlabF make_slabf(V3 l1, V3 d)
+{
+    const float BIG = 1099511627776.0f;            /* 2^40 on an axis the segment does not move along: products by a power of two are exact, so
+                                                    * fma(face, BIG, -(o * BIG)) has the exact sign of face - o and is 0 on the face (geom.h) */
+    SlabF S;
+    S.ix = d.x != 0 ? __frcp_rn(d.x) : BIG; S.iy = d.y != 0 ? __frcp_rn(d.y) : BIG; S.iz = d.z != 0 ? __frcp_rn(d.z) : BIG;
+    S.nlx = -(l1.x * S.ix); S.nly = -(l1.y * S.iy); S.nlz = -(l1.z * S.iz);
+    S.nhx = -(lb_slab_origin_hi(l1.x, d.x) * S.ix); S.nhy = -(lb_slab_origin_hi(l1.y, d.y) * S.iy); S.nhz = -(lb_slab_origin_hi(l1.z, d.z) * S.iz);
+    const float m = fmaxf(fmaxf(d.x != 0 ? fabsf(S.nlx) : 0.f, d.y != 0 ? fabsf(S.nly) : 0.f), d.z != 0 ? fabsf(S.nlz) : 0.f);
+    S.eps = 2e-6f + 2.4e-7f * m;                   /* 4 x (2^-24 |o * inv|) on top of the plain test's own slack */
+    return S;
+}
+
+__device__ __forceinline__ bool slabf_hit(const SlabF &S, float lx, float ly, float lz, float hx, float hy, float hz)
+{
+    const float x0 = __fmaf_rn(lx, S.ix, S.nlx), x1 = __fmaf_rn(hx, S.ix, S.nhx), y0 = __fmaf_rn(ly, S.iy, S.nly), y1 = __fmaf_rn(hy, S.iy, S.nhy);
+    const float z0 = __fmaf_rn(lz, S.iz, S.nlz), z1 = __fmaf_rn(hz, S.iz, S.nhz);
+    const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
+    const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));
+    return t0 <= t1 + S.eps;
+}
+
+/* the plain test (what bvh4_anyhit_core does): the two origins come back from shared memory, the inverse direction is the
+ * pre-filter's (__frcp_rn is the correctly rounded 1/d of the plain form; on a zero axis 2^40 instead of 1e30 decides alike:
+ * the products are 0 or far outside [0,1] either way) */
+__device__ __forceinline__ bool slab_exact_hit(const SlabF &S, const float *s_ray, float lx, float ly, float lz, float hx, float hy, float hz)
+{
+    const float x0 = (lx - s_ray[0]) * S.ix, x1 = (hx - s_ray[3 * LB_BLOCK]) * S.ix, y0 = (ly - s_ray[LB_BLOCK]) * S.iy, y1 = (hy - s_ray[4 * LB_BLOCK]) * S.iy;
+    const float z0 = (lz - s_ray[2 * LB_BLOCK]) * S.iz, z1 = (hz - s_ray[5 * LB_BLOCK]) * S.iz;
+    const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
+    const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));
+    return t0 <= t1 + 2e-6f;
+}
+
+template <int FLUSH>
+__device__ __forceinline__ bool bvh4_anyhit_entries_f(const Bvh4Node *__restrict__ nodes, const RayTri *__restrict__ tris, const BvhEntrySet &E,
+                                                      const V3 l1, const V3 l2, float *s_ray /* this thread's column of [9][LB_BLOCK] */, TravStats &ts)
+{
+    constexpr int TQ = FLUSH + 28;
+    int stack_n[BVH_STACK];
+    int tq[TQ];
+    int sp = 0, nq = 0;
+    unsigned visits = 0;                             /* per ray; the long-lived counters in ts are touched once per ray, not once per node */
+    {
+        const V3 d = l2 - l1;
+        s_ray[0] = l1.x; s_ray[LB_BLOCK] = l1.y; s_ray[2 * LB_BLOCK] = l1.z;
+        s_ray[3 * LB_BLOCK] = lb_slab_origin_hi(l1.x, d.x); s_ray[4 * LB_BLOCK] = lb_slab_origin_hi(l1.y, d.y); s_ray[5 * LB_BLOCK] = lb_slab_origin_hi(l1.z, d.z);
+        s_ray[6 * LB_BLOCK] = d.x; s_ray[7 * LB_BLOCK] = d.y; s_ray[8 * LB_BLOCK] = d.z;
+    }
+    const SlabF S = make_slabf(l1, l2 - l1);
+    const int n = E.n;
+    for (int i = 0; i < n; ++i)
+        if (slabf_hit(S, E.lox[i], E.loy[i], E.loz[i], E.hix[i], E.hiy[i], E.hiz[i])) stack_n[sp++] = E.node[i];
+    ts.entries += (unsigned)n;
+    if (sp == 0) return false;
+    int node = stack_n[--sp];
+    for (;;) {
+        while (node >= 0) {
+            const float4 *n4 = reinterpret_cast<const float4 *>(nodes + node);
+            const float4 lx = __ldg(n4), ly = __ldg(n4 + 1), lz = __ldg(n4 + 2), hx = __ldg(n4 + 3), hy = __ldg(n4 + 4), hz = __ldg(n4 + 5);
+            const int4 k = __ldg(reinterpret_cast<const int4 *>(n4 + 6));
+            ++visits;
+            int next = -1;
+#define LB_BVH4_CHILD_F(LX, LY, LZ, HX, HY, HZ, C)                                                                      \
+            if (slabf_hit(S, LX, LY, LZ, HX, HY, HZ) && (C) != BVH4_EMPTY) {                                            \
+                if ((C) < 0) {                                                                                          \
+                    if (slab_exact_hit(S, s_ray, LX, LY, LZ, HX, HY, HZ)) {                                             \
+                        const unsigned code = ~(C); for (unsigned t = 0, first = code >> 3; t < (code & 7u); ++t) tq[nq++] = (int)(first + t); \
+                    }                                                                                                   \
+                } else if (next < 0) next = (C);                                                                        \
+                else stack_n[sp++] = (C);                                                                               \
+            }
+            LB_BVH4_CHILD_F(lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, k.x)
+            LB_BVH4_CHILD_F(lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, k.y)
+            LB_BVH4_CHILD_F(lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, k.z)
+            LB_BVH4_CHILD_F(lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, k.w)
+#undef LB_BVH4_CHILD_F
+            node = next >= 0 ? next : (sp ? stack_n[--sp] : -1);
+            if (nq >= FLUSH) break;
+        }
+        if (nq) {
+            const V3 o = mk3(s_ray[0], s_ray[LB_BLOCK], s_ray[2 * LB_BLOCK]), d = mk3(s_ray[6 * LB_BLOCK], s_ray[7 * LB_BLOCK], s_ray[8 * LB_BLOCK]);
+            ts.tris += (unsigned)nq;
+            while (nq) {
+                RayTri T;
+                load_raytri(tris + tq[--nq], T);
+                if (seg_tri_prepared(o, d, T) < 1.0f) { ts.tris -= (unsigned)nq; ts.nodes += 2u * visits; return true; }
+            }
+        }
+        if (node < 0) { ts.nodes += 2u * visits; return false; }
+    }
+}
+
+/*
  * Warp-cooperative form of bvh_entry_search_t (bvh_entry.h): the same frontier, the same picks and the same slot
  * assignment -- hence the same entry set as the scalar host model -- but entry i lives in the registers of lane i and the
  * children of the picked node are tested one per lane, so an iteration is a few dozen warp instructions instead of a

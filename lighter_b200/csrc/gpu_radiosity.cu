@@ -467,6 +467,12 @@ template <int G> static size_t rad_sweep_smem() { return sizeof(RadColBuf<G>) * 
 #ifndef LB_VIS_FLUSH
 #define LB_VIS_FLUSH 10
 #endif
+#ifndef LB_VIS_FMA
+#define LB_VIS_FMA 0            /* 1 = box tests in FMA form with an exact re-test at the leaves (gpu_internal.cuh: bvh4_anyhit_entries_f): measured SLOWER on B200 (271 vs 235 ms, profiles/r02_ab_runs.md), kept for A/B */
+#endif
+#ifndef LB_VIS_LEAN
+#define LB_VIS_LEAN 1           /* register-lean batch loop of the visibility kernel (see there); 0 = the round-1 software pipeline */
+#endif
 #ifndef LB_VIS_MINBLOCKS
 #define LB_VIS_MINBLOCKS 9      /* 56 registers: measured optimum on B200 (48 regs: +2 %, 40: +10 %, 72-80 uncapped: +12 %) */
 #endif
@@ -479,6 +485,13 @@ rad_visibility_kernel(const Bvh4Node *__restrict__ bvh, const RayTri *__restrict
                       uint32_t *chunk_cursor, unsigned long long *counters)
 {
     __shared__ BvhEntrySet s_entry[LB_BLOCK / 32];
+#if LB_VIS_FMA
+    __shared__ float s_ray[9][LB_BLOCK];
+#endif
+#if LB_VIS_LEAN
+    __shared__ unsigned s_stat[4][LB_BLOCK];      /* per thread: segments, node visits, triangle tests, entry tests */
+    s_stat[0][threadIdx.x] = s_stat[1][threadIdx.x] = s_stat[2][threadIdx.x] = s_stat[3][threadIdx.x] = 0u;
+#endif
     unsigned segs = 0;
     TravStats ts = { 0, 0 };
     const unsigned lane = threadIdx.x & 31u;
@@ -519,6 +532,84 @@ rad_visibility_kernel(const Bvh4Node *__restrict__ bvh, const RayTri *__restrict
             bvh_entry_pad(lx, ly, lz, hx, hy, hz);
             bvh_entry_search_warp<Bvh4Access>(bvh, lx, ly, lz, hx, hy, hz, E, lane);   /* syncs the warp before it overwrites the previous chunk's set */
         }
+#if LB_VIS_LEAN
+        /* Register-lean batch loop.  Across the walk only `blocked`, the batch position and the lane's statistics slots are
+         * alive: the candidate record, the two lumel indices and the factor are READ AGAIN for the 4 % of segments that are
+         * blocked (L1 hits), the records of later batches are brought close by address-only prefetches (two batches ahead)
+         * and the next batch's record is loaded just to prefetch its lumels, then dropped.  The walk statistics live in
+         * shared memory.  ptxas at 56 registers: 132 -> 0 bytes of spills in the node loop's kernel (the round-1 form kept
+         * two prefetched records, the current one, both indices and four counters in registers across the walk). */
+        for (unsigned i = 0; i < RAD_CHUNK; i += 32u) {
+            if (e0 + i >= n_cand) break;              /* warp-uniform */
+            const unsigned long long e = e0 + i + lane;
+            const RadCand *cp = cand + e;
+            bool blocked = false, valid = false;
+            {
+                if (i + 64u < RAD_CHUNK && e + 64u < n_cand) asm volatile("prefetch.global.L1 [%0];" :: "l"(cp + 64));
+                if (i + 32u < RAD_CHUNK && e + 32u < n_cand) {
+                    const RadCand cn = cp[32];
+                    if (cn.a != RAD_PAD) {
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(spos + cn.a));
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(spos + cn.b));
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(sidx + cn.a));
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(sidx + cn.b));
+                    }
+                }
+                RadCand c = { RAD_PAD, 0, 0.f };
+                if (e < n_cand) c = *cp;
+                valid = c.a != RAD_PAD;
+                if (!__any_sync(0xffffffffu, valid)) continue;
+                if (valid) {                              /* RAD_PAD: unused slot of a warp's output chunk */
+                    const bool a_first = sidx[c.a] < sidx[c.b];         /* the reference traces from the lower lumel index */
+                    const V3 A = ld3(spos[a_first ? c.a : c.b]), B = ld3(spos[a_first ? c.b : c.a]);
+                    const V3 dn = norm3(B - A);
+                    const V3 mA = A + dn * LB_SMALL, mB = B - dn * LB_SMALL;
+                    TravStats t1 = { 0, 0, 0 };
+#if LB_VIS_FMA
+                    blocked = ENTRY ? bvh4_anyhit_entries_f<LB_VIS_FLUSH>(bvh, raytris, E, mA, mB, &s_ray[0][threadIdx.x], t1) : bvh4_anyhit<LB_VIS_FLUSH>(bvh, raytris, mA, mB, t1);
+#else
+                    blocked = ENTRY ? bvh4_anyhit_entries<LB_VIS_FLUSH>(bvh, raytris, E, mA, mB, t1) : bvh4_anyhit<LB_VIS_FLUSH>(bvh, raytris, mA, mB, t1);
+#endif
+                    s_stat[0][threadIdx.x] += 1u; s_stat[1][threadIdx.x] += t1.nodes; s_stat[2][threadIdx.x] += t1.tris; s_stat[3][threadIdx.x] += t1.entries;
+                }
+            }
+            const unsigned bm = __ballot_sync(0xffffffffu, blocked);
+            if (!bm) continue;                        /* 96 % of the segments are free: most batches end here */
+            unsigned emit = 0;                        /* bit 0: link for row a (always mine), bit 1: row b is mine too, bit 2: row b lives on another rank */
+            RadCand c = { 0, 0, 0.f };
+            uint32_t oa = 0, ob = 0;
+            if (blocked) {
+                asm volatile("" : "+l"(cp));          /* the record is read again (it was not kept across the walk) */
+                c = *cp;
+                oa = sidx[c.a]; ob = sidx[c.b];
+                emit = 1u | ((c.b >= my_k0 && c.b < my_k1) ? 2u : 4u);
+            }
+            const unsigned cnt = __popc(emit & 3u);
+            unsigned pre = cnt;
+            for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= (unsigned)o) pre += t; }
+            const unsigned total = __shfl_sync(0xffffffffu, pre, 31);
+            {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(link_count, (unsigned long long)total);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                unsigned long long at = base + (pre - cnt);
+                if (emit & 1u) { keys[at] = ((unsigned long long)c.a << 32) | ob; factors[at] = c.factor; ++at; }
+                if (emit & 2u) { keys[at] = ((unsigned long long)c.b << 32) | oa; factors[at] = c.factor; }
+            }
+            const unsigned mm = __ballot_sync(0xffffffffu, (emit & 4u) != 0);
+            if (mm) {                                 /* mirrored link for a row owned by another rank: queued for the exchange */
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(mirror_count, (unsigned long long)__popc(mm));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (emit & 4u) {
+                    const unsigned long long at = base + __popc(mm & ((1u << lane) - 1u));
+                    if (at < mirror_cap) mirror[at] = make_uint4(c.b, oa, __float_as_uint(c.factor), 0u);
+                }
+            }
+        }
+    }
+    segs = s_stat[0][threadIdx.x]; ts.nodes = s_stat[1][threadIdx.x]; ts.tris = s_stat[2][threadIdx.x]; ts.entries = s_stat[3][threadIdx.x];
+#else
         /* software pipeline over the chunk's 32 batches: the candidate records are loaded two batches ahead, the lumels of
          * the next batch's candidates are prefetched into L1 while this batch is traced (ncu: a fifth of the kernel's stall
          * samples sat on the candidate -> position load chain) */
@@ -550,7 +641,11 @@ rad_visibility_kernel(const Bvh4Node *__restrict__ bvh, const RayTri *__restrict
                 const V3 dn = norm3(B - A);
                 const V3 mA = A + dn * LB_SMALL, mB = B - dn * LB_SMALL;
                 ++segs;
+#if LB_VIS_FMA
+                const bool blocked = ENTRY ? bvh4_anyhit_entries_f<LB_VIS_FLUSH>(bvh, raytris, E, mA, mB, &s_ray[0][threadIdx.x], ts) : bvh4_anyhit<LB_VIS_FLUSH>(bvh, raytris, mA, mB, ts);
+#else
                 const bool blocked = ENTRY ? bvh4_anyhit_entries<LB_VIS_FLUSH>(bvh, raytris, E, mA, mB, ts) : bvh4_anyhit<LB_VIS_FLUSH>(bvh, raytris, mA, mB, ts);
+#endif
                 if (blocked) emit = 1u | ((c.b >= my_k0 && c.b < my_k1) ? 2u : 4u);
             }
             const unsigned cnt = __popc(emit & 3u);
@@ -579,6 +674,7 @@ rad_visibility_kernel(const Bvh4Node *__restrict__ bvh, const RayTri *__restrict
             }
         }
     }
+#endif
     count_add(counters, CNT_RAD_SEGMENTS, segs);
     count_add(counters, CNT_RAY_NODE_VISITS, ts.nodes);
     count_add(counters, CNT_RAY_TRI_TESTS, ts.tris);
