@@ -69,6 +69,9 @@ LTRAPI const char *ltrx_Version(void);
 LTRAPI int  ltrx_SetDevice(ltr_Scene *scene, int cuda_device);
 LTRAPI int  ltrx_NcclUniqueId(unsigned char out_id[LTRX_NCCL_ID_BYTES]);
 LTRAPI int  ltrx_SetShard(ltr_Scene *scene, int rank, int world, const unsigned char *nccl_id /* NULL iff world==1 */);
+/* sharded bake: 1 = only rank 0 reads the finished lightmaps back to the host (the other ranks report lightmap_count 0);
+ * 0 (default) = every rank gets every lightmap, as a caller of the plain API expects */
+LTRAPI int  ltrx_SetOutputRoot(ltr_Scene *scene, int root_only);
 LTRAPI void ltrx_ShardRange(uint64_t n, int rank, int world, uint64_t *begin, uint64_t *end);
 
 /* direct-light shadow term ----------------------------------------------------------------------

@@ -155,7 +155,7 @@ class Links(C.Structure):
 LTR_SYMBOLS = ["ltr_DefaultSizeFunc", "ltr_CreateScene", "ltr_DestroyScene", "ltr_Start", "ltr_Abort", "ltr_GetStatus",
                "ltr_Sleep", "ltr_GetConfig", "ltr_SetConfig", "ltr_CreateMesh", "ltr_MeshAddPart", "ltr_MeshAddInstance",
                "ltr_LightAdd", "ltr_SampleAdd", "ltr_GetWorkOutputInfo", "ltr_GetWorkOutput", "ltr_NextPowerOfTwo"]
-LTRX_SYMBOLS = ["ltrx_Version", "ltrx_SetDevice", "ltrx_NcclUniqueId", "ltrx_SetShard", "ltrx_ShardRange", "ltrx_GetStats",
+LTRX_SYMBOLS = ["ltrx_Version", "ltrx_SetDevice", "ltrx_SetOutputRoot", "ltrx_NcclUniqueId", "ltrx_SetShard", "ltrx_ShardRange", "ltrx_GetStats",
                 "ltrx_GetError", "ltrx_Prepare", "ltrx_BakeResident", "ltrx_Finish", "ltrx_OutputHash", "ltrx_SetDebug", "ltrx_GetLumels",
                 "ltrx_GetLinks", "ltrx_GetShadowFactors", "ltrx_SetShadowMode", "ltrx_GetShadowMasks", "ltrx_ShadowSampleSegment",
                 "ltrx_test_point_tri_distance", "ltrx_test_seg_tri",
@@ -199,6 +199,7 @@ def lib() -> C.CDLL:
     L.ltrx_SetDevice.argtypes = [vp, C.c_int]
     L.ltrx_NcclUniqueId.argtypes = [C.c_char_p]
     L.ltrx_SetShard.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    L.ltrx_SetOutputRoot.argtypes = [vp, C.c_int]
     L.ltrx_ShardRange.restype = None
     L.ltrx_ShardRange.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.ltrx_GetStats.argtypes = [vp, C.POINTER(Stats)]
@@ -277,7 +278,7 @@ class BakeHandle:
     """A scene fed through the C API, kept alive so outputs (owned by the scene) stay valid."""
 
     def __init__(self, scene: _scenes.Scene, debug: bool = False, device: int | None = None, shard: tuple | None = None,
-                 reset_rand: bool = True, shadow_mode: int = 0):
+                 reset_rand: bool = True, shadow_mode: int = 0, output_root_only: bool = False):
         L = lib()
         self.L = L
         self.scene_desc = scene
@@ -320,6 +321,8 @@ class BakeHandle:
             rank, world, nccl_id = shard
             if not L.ltrx_SetShard(self.h, rank, world, nccl_id):
                 raise RuntimeError("ltrx_SetShard rejected the shard")
+            if output_root_only:
+                L.ltrx_SetOutputRoot(self.h, 1)
 
         meshes = []
         for m in scene.meshes:

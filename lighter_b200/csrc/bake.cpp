@@ -112,6 +112,12 @@ struct Bake {
     BigVec<float> rtree_tris;
     SceneBvh bvh;
     BigVec<float> bvh_tris;                   /* host-built tree: triangles in BVH order; device build: the compacted scene-order triangles (if not every instance casts) */
+    /* multi-GPU host pre-pass: instances are dealt to the ranks in contiguous runs; a rank transforms, lists and builds the
+     * reference-order trees of ITS instances only, uploads those slices, and the device arrays are completed by an
+     * all-gather over NVLink (upload()).  inst_cut[r] = first instance of rank r; sh_* = the slice boundaries of the
+     * concatenated arrays in elements, world + 1 entries each (empty = one rank: everything is local). */
+    std::vector<size_t> inst_cut;
+    std::vector<uint64_t> sh_verts, sh_rtris, sh_rnodes, sh_ritems, sh_tris;
     bool all_cast = true;                     /* every instance with triangles casts shadows: scene BVH == the triangles of the instance trees */
     bool device_bvh = true;                   /* the scene BVH is built on the device (gpu_bvh.cu); false: bvh.cpp (LTR_BVH_HOST=1, tiny scenes, host-only test hooks) */
     const float *scene_tris = nullptr;        /* device build: the triangles the tree is built over, scene order */
@@ -189,6 +195,35 @@ void host_prepare(ltr_Scene *S, bool force_host_bvh = false)
     const size_t nv = vbase[ni];
     B.wpos.resize(nv); B.wnrm.resize(nv); B.vtex.resize(nv * 2); B.ltex.resize(nv * 2);
 
+    /* Which instances are this rank's?  One rank, a host-built BVH (it needs every triangle here) or the host-only test
+     * hook: all of them.  Otherwise contiguous runs of about equal weight (vertices + triangles, what the transform and the
+     * tree builds cost); instance 0 (the probe container) goes with rank 0. */
+    bool every_instance_casts = true;              /* otherwise the scene BVH needs a compacted triangle list, made on the host from all triangles */
+    for (size_t i = 1; i < ni; ++i) if (!S->instances[i]->shadow) every_instance_casts = false;
+    const int world = (S->world > 1 && !force_host_bvh && !getenv("LTR_BVH_HOST") && !getenv("LTR_HOST_PREPASS_REPLICATED") && every_instance_casts && B.gpu && B.comm) ? S->world : 1;
+    const int rank = world > 1 ? S->rank : 0;
+    B.inst_cut.assign((size_t)world + 1, ni);
+    B.inst_cut[0] = 0;
+    if (world > 1) {
+        std::vector<uint64_t> w(ni + 1, 0);
+        for (size_t i = 1; i < ni; ++i) w[i + 1] = w[i] + S->instances[i]->mesh->vpos.size() + S->instances[i]->mesh->indices.size();
+        int r = 1;
+        for (size_t i = 1; i < ni && r < world; ++i)
+            while (r < world && w[i + 1] * (uint64_t)world >= w[ni] * (uint64_t)r) B.inst_cut[r++] = i + 1;
+    }
+    const size_t my_i0 = B.inst_cut[rank], my_i1 = B.inst_cut[rank + 1];
+    /* the processes of a multi-GPU bake share the host's cores */
+    const unsigned hw_threads = std::max(1u, std::thread::hardware_concurrency() / (unsigned)std::max(1, S->world));
+    /* per-instance results the other ranks need: two small tables, all-gathered (exchange below) */
+    auto exchange = [&](std::vector<uint32_t> &tab, size_t k) {     /* tab: ni x k words, valid for my instances; filled for all on return */
+        if (world <= 1) return;
+        std::vector<uint32_t> all(tab.size() * (size_t)world);
+        gpu_check(S, ltrgpu_host_allgather(B.gpu, tab.data(), all.data(), tab.size() * 4), "instance table exchange");
+        for (int r = 0; r < world; ++r)
+            for (size_t i = B.inst_cut[r]; i < B.inst_cut[r + 1]; ++i)
+                memcpy(&tab[i * k], &all[(size_t)r * tab.size() + i * k], k * 4);
+    };
+
     /* one instance per task, as the reference does (its size_fn is called from pool threads, one per instance, concurrently:
      * lighter.cpp:1054,326) */
     auto xform_instance = [&](size_t i) {
@@ -229,10 +264,11 @@ void host_prepare(ltr_Scene *S, bool force_host_bvh = false)
         }
     };
     {
-        const unsigned nthreads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), ni > 1 ? (unsigned)(ni - 1) : 1u));
-        std::atomic<size_t> next{1};
+        const size_t first = std::max<size_t>(my_i0, 1);
+        const unsigned nthreads = std::max(1u, std::min<unsigned>(hw_threads, my_i1 > first ? (unsigned)(my_i1 - first) : 1u));
+        std::atomic<size_t> next{first};
         std::vector<std::thread> pool;
-        auto worker = [&]() { for (size_t i; (i = next.fetch_add(1)) < ni;) xform_instance(i); };
+        auto worker = [&]() { for (size_t i; (i = next.fetch_add(1)) < my_i1;) xform_instance(i); };
         for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(worker);
         worker();
         for (auto &th : pool) th.join();
@@ -251,12 +287,12 @@ void host_prepare(ltr_Scene *S, bool force_host_bvh = false)
      * reference-order trees index); the scene BVH is built over the same memory when every instance casts shadows (the
      * usual case), over a compacted copy otherwise. */
     std::vector<RefTree> itree(ni);
-    auto parallel_instances = [&](const std::function<void(size_t)> &fn) {
-        unsigned nthreads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)ni));
-        std::atomic<size_t> next{0};
+    auto parallel_instances = [&](const std::function<void(size_t)> &fn) {           /* over THIS RANK's instances */
+        unsigned nthreads = std::max(1u, std::min<unsigned>(hw_threads, (unsigned)(my_i1 - my_i0)));
+        std::atomic<size_t> next{my_i0};
         std::vector<std::thread> pool;
         for (unsigned t = 0; t < nthreads; ++t)
-            pool.emplace_back([&]() { for (size_t i; (i = next.fetch_add(1)) < ni;) fn(i); });
+            pool.emplace_back([&]() { for (size_t i; (i = next.fetch_add(1)) < my_i1;) fn(i); });
         for (auto &th : pool) th.join();
     };
     /* visits the useful triangles of instance i in part / index order (ref: lighter.cpp:349-384: parts with shadow == 0 and
@@ -283,6 +319,12 @@ void host_prepare(ltr_Scene *S, bool force_host_bvh = false)
         for_useful_tris(i, [&](const V3 &, const V3 &, const V3 &) { ++c; });
         n_itris[i] = c;
     });
+    {   /* exchange 1: lightmap sizes (size_fn ran on the owner only) and triangle counts */
+        std::vector<uint32_t> tab(ni * 3, 0);
+        for (size_t i = std::max<size_t>(my_i0, 1); i < my_i1; ++i) { tab[i * 3] = S->instances[i]->lm_width; tab[i * 3 + 1] = S->instances[i]->lm_height; tab[i * 3 + 2] = (uint32_t)n_itris[i]; }
+        exchange(tab, 3);
+        for (size_t i = 1; i < ni; ++i) { S->instances[i]->lm_width = tab[i * 3]; S->instances[i]->lm_height = tab[i * 3 + 1]; n_itris[i] = tab[i * 3 + 2]; }
+    }
     for (size_t i = 0; i < ni; ++i) o_tri[i + 1] = o_tri[i] + n_itris[i];
     B.rtree_tris.resize(o_tri[ni] * 9);
     BigVec<Box3> all_boxes(o_tri[ni]);
@@ -345,9 +387,16 @@ void host_prepare(ltr_Scene *S, bool force_host_bvh = false)
     parallel_instances([&](size_t i) { itree[i].build(i ? all_boxes.data() + o_tri[i] : nullptr, i ? n_itris[i] : 0); });
     lap("instance trees (threads)");
     S->completion.store(0.99f);
+    /* exchange 2: tree sizes and root boxes */
+    std::vector<uint32_t> ttab(ni * 8, 0);
+    for (size_t i = my_i0; i < my_i1; ++i) {
+        ttab[i * 8] = (uint32_t)itree[i].nodes.size(); ttab[i * 8 + 1] = (uint32_t)itree[i].items.size();
+        memcpy(&ttab[i * 8 + 2], &itree[i].nodes[0].lo, 12); memcpy(&ttab[i * 8 + 5], &itree[i].nodes[0].hi, 12);
+    }
+    exchange(ttab, 8);
     /* instance tree over the root boxes (invalid boxes are dropped by the builder) */
     std::vector<Box3> ibox(ni);
-    for (size_t i = 0; i < ni; ++i) { ibox[i].lo = itree[i].nodes[0].lo; ibox[i].hi = itree[i].nodes[0].hi; }
+    for (size_t i = 0; i < ni; ++i) { memcpy(&ibox[i].lo, &ttab[i * 8 + 2], 12); memcpy(&ibox[i].hi, &ttab[i * 8 + 5], 12); }
     RefTree inst_tree;
     inst_tree.build(ibox.data(), ni);
 
@@ -367,11 +416,17 @@ void host_prepare(ltr_Scene *S, bool force_host_bvh = false)
             I.shadow = (i && mi->shadow) ? 1 : 0;
             size_t nrt = 0;
             if (i) for (const MeshPart &mp : mi->mesh->parts) nrt += mp.index_count / 3;
-            o_node[i + 1] = o_node[i] + itree[i].nodes.size();
-            o_item[i + 1] = o_item[i] + itree[i].items.size();
+            o_node[i + 1] = o_node[i] + ttab[i * 8];
+            o_item[i + 1] = o_item[i] + ttab[i * 8 + 1];
             o_rtri[i + 1] = o_rtri[i] + nrt;
         }
         B.rnodes.resize(o_node[ni]); B.ritems.resize(o_item[ni]); B.rtris.resize(o_rtri[ni]);      /* B.rtree_tris was filled in place above */
+        B.sh_verts.clear(); B.sh_rtris.clear(); B.sh_rnodes.clear(); B.sh_ritems.clear(); B.sh_tris.clear();
+        if (world > 1)
+            for (int r = 0; r <= world; ++r) {
+                const size_t c = B.inst_cut[r];
+                B.sh_verts.push_back(vbase[c]); B.sh_rtris.push_back(o_rtri[c]); B.sh_rnodes.push_back(o_node[c]); B.sh_ritems.push_back(o_item[c]); B.sh_tris.push_back(o_tri[c]);
+            }
         auto copy_one = [&](size_t i) {
             if (!itree[i].nodes.empty()) memcpy(&B.rnodes[o_node[i]], itree[i].nodes.data(), itree[i].nodes.size() * sizeof(itree[i].nodes[0]));
             if (!itree[i].items.empty()) memcpy(&B.ritems[o_item[i]], itree[i].items.data(), itree[i].items.size() * sizeof(itree[i].items[0]));
@@ -389,12 +444,7 @@ void host_prepare(ltr_Scene *S, bool force_host_bvh = false)
                 }
             }
         };
-        unsigned nthreads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)ni));
-        std::atomic<size_t> next{0};
-        std::vector<std::thread> pool;
-        for (unsigned t = 0; t < nthreads; ++t)
-            pool.emplace_back([&]() { for (size_t i; (i = next.fetch_add(1)) < ni;) copy_one(i); });
-        for (auto &th : pool) th.join();
+        parallel_instances(copy_one);
     }
     lap("concatenate + raster list");
     /* flat scene BVH over the shadow-casting triangles: built in the background since the world triangles were ready */
@@ -464,17 +514,48 @@ void host_prepare(ltr_Scene *S, bool force_host_bvh = false)
     B.prepared = true;
 }
 
-void upload(ltr_Scene *S)
+/* GPU context, NCCL communicator and the collective hooks: before the host pre-pass, which already exchanges two small tables */
+void connect(ltr_Scene *S)
 {
     Bake &B = *S->bake;
-    const ltr_Config &cfg = S->config;
-    double t0 = now_s();
     if (!B.gpu) {
         if (ltrgpu_create(&B.gpu, S->device)) {
             Fail f; f.msg = std::string("CUDA device unavailable: ") + (B.gpu ? ltrgpu_last_error(B.gpu) : "no CUDA device (this library has no CPU fallback)");
             throw f;
         }
     }
+    if (S->world > 1 && !B.comm) {
+        char err[256];
+        B.nccl = nccl_api(err, sizeof(err));
+        if (!B.nccl) { Fail f; f.msg = std::string("NCCL unavailable: ") + err; throw f; }
+        if (!S->have_nccl_id) { Fail f; f.msg = "sharded bake without an NCCL unique id (call ltrx_SetShard)"; throw f; }
+        NcclId id;
+        memcpy(&id, S->nccl_id, sizeof(id));
+        /* One communicator per (unique id, rank, world) per process, shared by every scene that names
+         * the same id: an NCCL unique id can seed ncclCommInitRank only once. */
+        static std::mutex comm_mu;
+        static std::map<std::string, void *> comm_cache;
+        std::string key((const char *)S->nccl_id, sizeof(S->nccl_id));
+        key += "/" + std::to_string(S->rank) + "/" + std::to_string(S->world);
+        std::lock_guard<std::mutex> g(comm_mu);
+        auto it = comm_cache.find(key);
+        if (it != comm_cache.end()) B.comm = it->second;
+        else {
+            int rc = B.nccl->CommInitRank(&B.comm, S->world, id, S->rank);
+            if (rc != 0) { B.comm = nullptr; Fail f; f.msg = std::string("ncclCommInitRank: ") + B.nccl->GetErrorString(rc); throw f; }
+            comm_cache[key] = B.comm;
+        }
+    }
+    B.world = S->world;
+    gpu_check(S, ltrgpu_set_world(B.gpu, S->rank, S->world, S->world > 1 ? nccl_allgather_cb : nullptr, &B), "world");
+    gpu_check(S, ltrgpu_set_gatherv(B.gpu, S->world > 1 ? nccl_gatherv_cb : nullptr), "world");
+}
+
+void upload(ltr_Scene *S)
+{
+    Bake &B = *S->bake;
+    const ltr_Config &cfg = S->config;
+    double t0 = now_s();
     std::vector<V3> ppos(S->probes.size()), pnrm(S->probes.size());
     for (size_t i = 0; i < S->probes.size(); ++i) {
         ppos[i] = mk3(S->probes[i].position[0], S->probes[i].position[1], S->probes[i].position[2]);
@@ -499,6 +580,7 @@ void upload(ltr_Scene *S)
     d.n_rtree_tris = (uint32_t)(B.rtree_tris.size() / 9); d.rtree_tris9 = B.rtree_tris.data();
     d.bvh_leaf_max = B.bvh_leaf_max;
     d.scene_covers_rtree = B.all_cast ? 1 : 0;
+    if (!B.sh_verts.empty()) { d.shard_verts = B.sh_verts.data(); d.shard_rtris = B.sh_rtris.data(); d.shard_rnodes = B.sh_rnodes.data(); d.shard_ritems = B.sh_ritems.data(); d.shard_tris = B.sh_tris.data(); }
     if (B.device_bvh) {
         d.n_bvh_nodes = d.n_bvh4_nodes = 0; d.bvh = nullptr; d.bvh4 = nullptr; d.tri_orig = nullptr;
         d.n_tris = (uint32_t)B.n_scene_tris; d.tris9 = B.scene_tris;
@@ -525,28 +607,6 @@ void upload(ltr_Scene *S)
     }
     if (trace) fprintf(stderr, "[ltr host] upload scene arrays               %8.2f ms\n", (now_s() - tu) * 1e3);
 
-    if (S->world > 1 && !B.comm) {
-        char err[256];
-        B.nccl = nccl_api(err, sizeof(err));
-        if (!B.nccl) { Fail f; f.msg = std::string("NCCL unavailable: ") + err; throw f; }
-        if (!S->have_nccl_id) { Fail f; f.msg = "sharded bake without an NCCL unique id (call ltrx_SetShard)"; throw f; }
-        NcclId id;
-        memcpy(&id, S->nccl_id, sizeof(id));
-        /* One communicator per (unique id, rank, world) per process, shared by every scene that names
-         * the same id: an NCCL unique id can seed ncclCommInitRank only once. */
-        static std::mutex comm_mu;
-        static std::map<std::string, void *> comm_cache;
-        std::string key((const char *)S->nccl_id, sizeof(S->nccl_id));
-        key += "/" + std::to_string(S->rank) + "/" + std::to_string(S->world);
-        std::lock_guard<std::mutex> g(comm_mu);
-        auto it = comm_cache.find(key);
-        if (it != comm_cache.end()) B.comm = it->second;
-        else {
-            int rc = B.nccl->CommInitRank(&B.comm, S->world, id, S->rank);
-            if (rc != 0) { B.comm = nullptr; Fail f; f.msg = std::string("ncclCommInitRank: ") + B.nccl->GetErrorString(rc); throw f; }
-            comm_cache[key] = B.comm;
-        }
-    }
     S->stats.t_upload = now_s() - t0;
 }
 
@@ -679,6 +739,8 @@ void gpu_stages(ltr_Scene *S)
     S->stats.t_finalize = now_s() - t0;
 }
 
+void collect_counters(ltr_Scene *S);
+
 void readback(ltr_Scene *S)
 {
     Bake &B = *S->bake;
@@ -687,6 +749,11 @@ void readback(ltr_Scene *S)
     for (ltr_WorkOutput &wo : S->outputs) free(wo.normals_xyzf);
     S->outputs.clear();
     ltrgpu_host_free(S->output_arena); S->output_arena = nullptr;
+    if (S->output_root_only && S->world > 1 && S->rank != 0) {       /* ltrx_SetOutputRoot: only rank 0 brings the lightmaps to the host */
+        S->stats.t_readback = now_s() - t0;
+        collect_counters(S);
+        return;
+    }
     /* every lightmap in ONE device -> host copy into one page-locked block owned by the scene */
     std::vector<uint64_t> out_off(ni + 1, 0);
     gpu_check(S, ltrgpu_output_layout(B.gpu, out_off.data()), "output layout");
@@ -776,6 +843,7 @@ void bake_main(ltr_Scene *S)
     S->failed_stage.clear();
     if (!S->bake) S->bake = new Bake;
     guarded(S, [&]() {
+        connect(S);
         host_prepare(S);
         upload(S);
         gpu_stages(S);
@@ -846,7 +914,7 @@ int ltrx_Prepare(ltr_Scene *scene)
     if (scene->worker.joinable()) scene->worker.join();
     if (!scene->bake) scene->bake = new Bake;
     scene->error.clear();
-    int ok = guarded(scene, [&]() { host_prepare(scene); upload(scene); });
+    int ok = guarded(scene, [&]() { connect(scene); host_prepare(scene); upload(scene); });
     scene->stage.store(ok ? "prepared" : nullptr);
     return ok;
 }
@@ -932,6 +1000,8 @@ int ltrx_Finish(ltr_Scene *scene)
 }
 
 int ltrx_SetDebug(ltr_Scene *scene, int keep) { scene->keep_debug = keep; return 1; }
+
+int ltrx_SetOutputRoot(ltr_Scene *scene, int root_only) { scene->output_root_only = root_only; return 1; }
 
 /* FNV-1a-64 over the float bytes of every lightmap in output order (the fingerprint SURVEY 8c uses for the reference's
  * lightmap_rgb arrays), then over the probe colours; bench.py prints it and checks a sharded bake against the single-GPU one */

@@ -73,6 +73,11 @@ typedef struct ltrgpu_SceneDesc {
     uint32_t n_bvh4_nodes;    const Bvh4Node *bvh4;            /* 4-wide collapse of the same tree (any-hit walks) */
     uint32_t n_tris;          const float *tris9; const uint32_t *tri_orig;
     int bvh_leaf_max, bvh_height;                              /* bvh_height: inner levels of a host-built tree */
+    /* multi-GPU: the concatenated per-instance arrays hold valid data only in THIS rank's slice; shard_x[r] .. shard_x[r+1]
+     * (elements, world + 1 entries, NULL = everything is valid) is rank r's slice of: wpos / wnrm / vtex2 / ltex2 (verts),
+     * rtris, rnodes, ritems, rtree_tris9 (tris).  The upload sends the slice and completes the device arrays by an
+     * all-gather over NVLink. */
+    const uint64_t *shard_verts, *shard_rtris, *shard_rnodes, *shard_ritems, *shard_tris;
     int scene_covers_rtree;                                    /* every instance casts shadows: the scene BVH holds exactly the triangles of the instance trees */
     /* lights + light->instance visibility table [n_lights][n_inst] */
     uint32_t n_lights;        const ltrgpu_Light *lights; const uint8_t *light_inst;
@@ -121,7 +126,9 @@ int ltrgpu_generate_lumels(ltrgpu_Ctx *ctx, uint64_t *inst_lumel_off);
 
 /* multi-GPU identity of this context and the all-gather hook; call before ltrgpu_generate_lumels */
 int ltrgpu_set_world(ltrgpu_Ctx *ctx, int rank, int world, ltrgpu_allgather_fn allgather, void *allgather_user);
-int ltrgpu_set_gatherv(ltrgpu_Ctx *ctx, ltrgpu_gatherv_fn gatherv);            /* same user pointer as the all-gather hook */
+int ltrgpu_set_gatherv(ltrgpu_Ctx *ctx, ltrgpu_gatherv_fn gatherv);
+/* all-gather of a small HOST table through the device and the all-gather hook: recv = world x bytes, rank-major (synchronous) */
+int ltrgpu_host_allgather(ltrgpu_Ctx *ctx, const void *send, void *recv, size_t bytes);            /* same user pointer as the all-gather hook */
 
 /* restrict the per-lumel stages to global lumels [begin,end) (multi-GPU shard); default = all */
 int ltrgpu_set_shard(ltrgpu_Ctx *ctx, uint64_t begin, uint64_t end, int rank, int world,

@@ -307,6 +307,24 @@ extern "C" int ltrgpu_reset_bake(ltrgpu_Ctx *ctx)
     return 0;
 }
 
+/* one concatenated per-instance array: allocate all of it, send this rank's slice, all-gather the rest */
+template <class T> static int upload_sharded(ltrgpu_Ctx *ctx, T **p, const T *host, size_t total, size_t per_elem /* Ts per element */, const uint64_t *shard)
+{
+    if (!shard || ctx->world <= 1) return dev_upload(ctx, p, host, total * per_elem);
+    if (dev_alloc(ctx, p, total * per_elem)) return 1;
+    const uint64_t b = shard[ctx->rank] * per_elem, e = shard[ctx->rank + 1] * per_elem;
+    if (e > b) {
+        if (lb_upload_staged(ctx, *p + b, host + b, (e - b) * sizeof(T))) return 1;
+        ctx->host_counters.h2d_bytes += (e - b) * sizeof(T);
+    }
+    if (!ctx->gatherv) { snprintf(ctx->err, sizeof(ctx->err), "sharded scene upload without a gather hook"); return 1; }
+    uint64_t off[65];
+    if (ctx->world > 64) { snprintf(ctx->err, sizeof(ctx->err), "more than 64 ranks"); return 1; }
+    for (int r = 0; r <= ctx->world; ++r) off[r] = shard[r] * per_elem * sizeof(T);
+    if (ctx->gatherv(ctx->allgather_user, *p, off, ctx->stream)) { snprintf(ctx->err, sizeof(ctx->err), "scene upload: all-gather of the instance slices failed"); return 1; }
+    return 0;
+}
+
 extern "C" int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *d)
 {
     CU_TRY(ctx, cudaSetDevice(ctx->device));
@@ -326,14 +344,14 @@ extern "C" int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *d)
     for (uint32_t i = 0; i < d->n_inst; ++i) ctx->n_texels += (uint64_t)d->inst[i].lm_w * d->inst[i].lm_h;
 
     if (dev_upload(ctx, &ctx->d_inst, d->inst, d->n_inst)) return 1;
-    if (dev_upload(ctx, &ctx->d_wpos, d->wpos, d->n_verts)) return 1;
-    if (dev_upload(ctx, &ctx->d_wnrm, d->wnrm, d->n_verts)) return 1;
-    if (dev_upload(ctx, &ctx->d_vtex, d->vtex2, d->n_verts)) return 1;
-    if (dev_upload(ctx, &ctx->d_ltex, d->ltex2, d->n_verts)) return 1;
-    if (dev_upload(ctx, &ctx->d_rtris, d->rtris, d->n_rtris)) return 1;
-    if (dev_upload(ctx, &ctx->d_rnodes, d->rnodes, d->n_rnodes)) return 1;
-    if (dev_upload(ctx, &ctx->d_ritems, d->ritems, d->n_ritems)) return 1;
-    if (dev_upload(ctx, &ctx->d_rtree_tris, d->rtree_tris9, (size_t)d->n_rtree_tris * 9)) return 1;
+    if (upload_sharded(ctx, &ctx->d_wpos, d->wpos, d->n_verts, 1, d->shard_verts)) return 1;
+    if (upload_sharded(ctx, &ctx->d_wnrm, d->wnrm, d->n_verts, 1, d->shard_verts)) return 1;
+    if (upload_sharded(ctx, (float **)&ctx->d_vtex, d->vtex2, d->n_verts, 2, d->shard_verts)) return 1;
+    if (upload_sharded(ctx, (float **)&ctx->d_ltex, d->ltex2, d->n_verts, 2, d->shard_verts)) return 1;
+    if (upload_sharded(ctx, &ctx->d_rtris, d->rtris, d->n_rtris, 1, d->shard_rtris)) return 1;
+    if (upload_sharded(ctx, &ctx->d_rnodes, d->rnodes, d->n_rnodes, 1, d->shard_rnodes)) return 1;
+    if (upload_sharded(ctx, &ctx->d_ritems, d->ritems, d->n_ritems, 1, d->shard_ritems)) return 1;
+    if (upload_sharded(ctx, &ctx->d_rtree_tris, d->rtree_tris9, d->n_rtree_tris, 9, d->shard_tris)) return 1;
     if (dev_upload(ctx, &ctx->d_lights, d->lights, d->n_lights)) return 1;
     if (dev_upload(ctx, &ctx->d_light_inst, d->light_inst, (size_t)d->n_lights * d->n_inst)) return 1;
     if (dev_upload(ctx, &ctx->d_light_samples, d->light_samples4, d->n_light_samples)) return 1;
@@ -406,6 +424,22 @@ extern "C" int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *d)
     }
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (!raw_is_rtree) lb_free(d_raw);
+    return 0;
+}
+
+extern "C" int ltrgpu_host_allgather(ltrgpu_Ctx *ctx, const void *send, void *recv, size_t bytes)
+{
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (ctx->world <= 1) { memcpy(recv, send, bytes); return 0; }
+    if (!ctx->allgather) { snprintf(ctx->err, sizeof(ctx->err), "no all-gather hook"); return 1; }
+    const size_t padded = (bytes + 15) & ~(size_t)15;
+    char *d = nullptr;
+    if (dev_alloc(ctx, &d, padded * ctx->world)) return 1;
+    CU_TRY(ctx, cudaMemcpyAsync(d + padded * ctx->rank, send, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->allgather(ctx->allgather_user, d + padded * ctx->rank, d, padded, ctx->stream)) { lb_free(d); snprintf(ctx->err, sizeof(ctx->err), "host table all-gather failed"); return 1; }
+    for (int r = 0; r < ctx->world; ++r) CU_TRY(ctx, cudaMemcpyAsync((char *)recv + bytes * r, d + padded * r, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    lb_free(d);
     return 0;
 }
 

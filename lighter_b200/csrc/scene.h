@@ -78,6 +78,7 @@ struct ltr_Scene {
     std::string error;                        /* first fatal error of the bake, "" if none */
     std::string failed_stage;                 /* "failed: <error>": the stage string ltr_GetStatus hands out after a failed bake */
     int shadow_mode = 0;                      /* 0 = reference distance march, 1 = sampled any-hit shadow rays (ltrx_SetShadowMode) */
+    int output_root_only = 0;                 /* sharded bake: only rank 0 reads the lightmaps back (ltrx_SetOutputRoot); the others report none */
     int keep_debug = 0;                       /* keep stage arrays for ltrx_Get* */
     struct Bake *bake = nullptr;              /* pipeline state incl. device buffers (bake.cpp) */
 };

@@ -9,7 +9,7 @@ LTR_TRACE_HOST=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-
 python - <<PY
 import json
 try:
-    d = json.load(open("gpurun_out/${T}_bench_n$N.json"))
+    d = json.loads(open("gpurun_out/${T}_bench_n$N.json").read().strip().splitlines()[-1])
     print("N=$N ms/step %.2f  e2e wall %.4f  parity %s" % (d["ms_per_step"], d["bake_wall_s"], d["parity"]["match"]))
     print(" stage_ms", {k: round(v, 2) for k, v in d["stage_ms"].items()})
     print(" host_s", {k: round(v, 4) for k, v in d["e2e"]["host_s"].items()})
