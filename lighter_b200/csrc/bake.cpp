@@ -793,19 +793,7 @@ void readback(ltr_Scene *S)
     }
     S->stats.t_readback = now_s() - t0;
 
-    ltrgpu_Counters c;
-    if (ltrgpu_get_counters(B.gpu, &c) == 0) {
-        ltrx_Stats &st = S->stats;
-        st.n_marches = c.marches; st.n_distance_queries = c.distance_queries; st.n_ao_segments = c.ao_segments;
-        st.n_correction_rays = c.correction_rays; st.n_rad_pairs = c.rad_pairs; st.n_rad_segments = c.rad_segments;
-        st.n_rad_links = c.rad_links; st.n_node_visits = c.node_visits; st.n_tri_tests = c.tri_tests;
-        st.n_ray_node_visits = c.ray_node_visits; st.n_ray_tri_tests = c.ray_tri_tests; st.n_rad_tile_loads = c.rad_tile_loads;
-        st.kernel_launches = c.kernel_launches; st.h2d_bytes = c.h2d_bytes; st.d2h_bytes = c.d2h_bytes; st.n_rad_batches = c.rad_batches; st.n_shadow_rays = c.shadow_rays; st.n_ray_entry_tests = c.ray_entry_tests;
-        st.gpu_ms_samples = c.ms_samples; st.gpu_ms_direct = c.ms_direct; st.gpu_ms_march = c.ms_march;
-        st.gpu_ms_radiosity = c.ms_radiosity; st.gpu_ms_ao = c.ms_ao; st.gpu_ms_finalize = c.ms_finalize;
-        st.gpu_ms_total = c.ms_samples + c.ms_direct + c.ms_radiosity + c.ms_ao + c.ms_finalize;
-        st.gpu_ms_rad_pairs = c.ms_rad_pairs; st.gpu_ms_rad_vis = c.ms_rad_vis; st.gpu_ms_span = c.ms_span;
-    }
+    collect_counters(S);
 }
 
 void collect_counters(ltr_Scene *S)

@@ -38,6 +38,19 @@ struct Bvh4Node {                /* 128 bytes */
     int32_t pad[4];
 };
 
+/* A/B variant (LB_VIS_Q8=1, profiles/r02_ab_runs.md): the 4-wide node compressed to 64 bytes -- the four child boxes as 8-bit
+ * offsets from the node's own corner in power-of-two steps (north_star's "compressed nodes"; the reference's node is
+ * lighter_int.hpp:708-714).  Planes are rounded OUTWARDS and widened by one more step, so the decoded boxes contain the float
+ * boxes with at least one step to spare (that step absorbs the rounding of the walk's fused decode, gpu_internal.cuh). */
+struct Bvh4QNode {               /* 64 bytes = 4 x 16 */
+    float ox, oy, oz;            /* corner: one step below the lowest child plane */
+    uint32_t exps;               /* biased float exponents of the three steps: ex | ey << 8 | ez << 16 */
+    uint32_t qlox, qloy, qloz, qhix;   /* byte c of each word = child c */
+    uint32_t qhiy, qhiz;
+    int32_t c[4];                /* as Bvh4Node::c */
+    uint32_t pad[2];
+};
+
 /* Allocator of the builder's big arrays: elements are default-INITIALISED (resize() does not zero 70 MB that the flatten
  * passes overwrite anyway) and large blocks ask for transparent huge pages (THP "madvise" mode; see bvh.cpp). */
 void *lb_big_alloc(size_t bytes);

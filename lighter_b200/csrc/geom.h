@@ -18,7 +18,7 @@
  * below it on an axis it does not -- hi - o' is then a positive ulp on the face and the axis drops out.  Per ray, outside
  * the loop; the loop's instruction count is unchanged.  Round 1 did not do this and lost the hits of segments lying in a
  * tile's boundary plane (16 of 22 561 links on the config-4 sibling). */
-LB_HD float lb_slab_inv(float d) { return d != 0 ? 1.0f / d : 1e30f; }
+LB_HD float lb_slab_inv(float d) { return d != 0 ? 1.0f / d : 1e30f; }    /* nvcc already compiles this to the reciprocal path: __frcp_rn gives the same SASS length */
 LB_HD float lb_slab_origin_hi(float o, float d) { return d != 0 ? o : nextafterf(o, -INFINITY); }
 
 /* ------------------------------------------------------------------------------------------

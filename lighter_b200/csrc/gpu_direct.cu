@@ -125,24 +125,6 @@ __global__ void direct_classify_kernel(const ltrgpu_Light *__restrict__ lights, 
     }
 }
 
-/* ref: lighter.cpp:190-207 */
-__device__ __forceinline__ float march_shadow(const BvhNode *__restrict__ bvh, const PreparedTri *__restrict__ tris,
-                                              V3 from, V3 to, float k, unsigned &queries, TravStats &ts)
-{
-    V3 rd = norm3(to - from);
-    float maxt = len3(to - from);
-    float res = 1.0f;
-    for (float t = 0.001f; t < maxt;) {
-        float h = bvh_distance(bvh, tris, from + rd * t, 2.0f, 0.001f, ts);
-        ++queries;
-        if (h < 0.001f) return 0.0f;
-        res = fminr(res, h / fminr(t * k, 2.0f));
-        h = fminr(h, 1.0f);
-        t += h;
-    }
-    return res;
-}
-
 #ifndef LB_MARCH_MINBLOCKS
 #define LB_MARCH_MINBLOCKS 8      /* 64 registers: measured on B200 (config 4): 41.3 ms vs 42.3 uncapped (72 regs), 52.8 at 10 blocks (spills) */
 #endif

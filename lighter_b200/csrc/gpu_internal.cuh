@@ -10,6 +10,16 @@
 #include "gpu.h"
 #include "bvh_entry.h"
 
+#ifndef LB_VIS_LEAFQ
+#define LB_VIS_LEAFQ 1                    /* 1 = the any-hit walk of the 4-wide tree queues leaf codes instead of triangle indices (bvh4_anyhit_core) */
+#endif
+#ifndef LB_VIS_SMEMNODES
+#define LB_VIS_SMEMNODES 0                /* 1 = the records of a chunk's entry nodes are copied to shared memory and the walk's first visit of each reads them there (north_star's "shared-memory node caching"): A/B variant */
+#endif
+#define LB_SM_TAG 0x40000000
+#ifndef LB_VIS_Q8
+#define LB_VIS_Q8 0                       /* 1 = the visibility walk reads 64-byte quantised nodes (Bvh4QNode): A/B variant, see profiles/r02_ab_runs.md */
+#endif
 #define LB_BLOCK 128                      /* traversal kernels: 4 warps per CTA, many CTAs per SM */
 #define LB_PAD 1024                       /* slack elements on per-lumel arrays so shards can be padded to equal size */
 
@@ -46,6 +56,8 @@ struct ltrgpu_Ctx {
     PreparedTri *d_rtree_ptris = nullptr;     /* the same triangles with the point-query terms precomputed (lumel_fix_kernel) */
     BvhNode *d_bvh = nullptr;
     Bvh4Node *d_bvh4 = nullptr;               /* 4-wide collapse of d_bvh for the any-hit walks */
+    Bvh4QNode *d_bvh4q = nullptr;             /* LB_VIS_Q8 builds only: the same nodes quantised to 64 bytes */
+    uint32_t n_bvh4_nodes = 0;
     PreparedTri *d_ptris = nullptr;
     RayTri *d_raytris = nullptr;
     /* flat BVH over the triangles of ALL instance trees (lumel_classify_kernel): aliases the scene BVH when every instance
@@ -276,6 +288,35 @@ __device__ __forceinline__ float bvh_distance(const BvhNode *__restrict__ nodes,
     }
 }
 
+/*
+ * ref: lighter.cpp:190-207 (CalcInvShadowFactor): sphere tracing from the lumel to the light, every step a nearest-distance
+ * query capped at 2 (MAX_PENUMBRA_SIZE), steps capped at 1 (MAX_PENUMBRA_STEP).  Shared by direct_march_kernel and the test
+ * entry point (ltrx_test_march).
+ *
+ * Measured and NOT adopted (round 2, profiles/r02_ab_runs.md "open-air windows"): after a capped answer a lane asked ONE box
+ * question -- "is every leaf box farther than 2.01 from the bounding box of my next K positions?" -- and replayed the K
+ * predictable steps (h = 2, t += 1) without walking the tree.  Bit-identical factors and step counts, 18 % fewer node
+ * visits, and 3.2x SLOWER (config 4: 131.6 vs 41.4 ms, config 3: 291 vs 90): lanes that jump K steps ahead of their
+ * neighbours leave the lock step in which the 32 marches of a warp read the same nodes, and the walks of a warp stop
+ * sharing cache lines.  The cost of a march is its near-surface steps, not the open-air ones (2-3 node visits each).
+ */
+__device__ __forceinline__ float march_shadow(const BvhNode *__restrict__ bvh, const PreparedTri *__restrict__ tris,
+                                              V3 from, V3 to, float k, unsigned &queries, TravStats &ts)
+{
+    V3 rd = norm3(to - from);
+    float maxt = len3(to - from);
+    float res = 1.0f;
+    for (float t = 0.001f; t < maxt;) {
+        float h = bvh_distance(bvh, tris, from + rd * t, 2.0f, 0.001f, ts);
+        ++queries;
+        if (h < 0.001f) return 0.0f;
+        res = fminr(res, h / fminr(t * k, 2.0f));
+        h = fminr(h, 1.0f);
+        t += h;
+    }
+    return res;
+}
+
 /* Segment set-up for BVH traversal: parametrised over [0,1] on l1 -> l2 so that box entry
  * distances compare directly with the hit parameter of seg_tri_prepared. */
 struct SegRay { V3 o, d, inv; };
@@ -479,12 +520,67 @@ __device__ __forceinline__ bool bvh_anyhit(const BvhNode *__restrict__ nodes, co
  */
 template <int FLUSH>
 __device__ __forceinline__ bool bvh4_anyhit_core(const Bvh4Node *__restrict__ nodes, const RayTri *__restrict__ tris, const V3 l1, const V3 l1h, const V3 d,
-                                                 const float ix, const float iy, const float iz, int (&stack_n)[BVH_STACK], int sp, int node, TravStats &ts)
+                                                 const float ix, const float iy, const float iz, int (&stack_n)[BVH_STACK], int sp, int node, TravStats &ts,
+                                                 const Bvh4Node *sm_nodes = nullptr /* LB_VIS_SMEMNODES: shared-memory copies of the entry nodes, addressed as LB_SM_TAG + slot */)
 {
     /* Measured and NOT adopted (B200, config 4): picking the near / far plane of every slab by the sign of the direction
      * (bit-identical to min/max, 4 three-way min/max per child instead of 10 two-way) needs a separate address per
      * float4 of the node; the extra pointers cost 16-24 registers and the kernel is more sensitive to occupancy than to
      * those instructions: 265 ms vs 236 ms for this form at 56 registers. */
+#if LB_VIS_LEAFQ
+    /* The queue holds LEAF CODES (first << 3 | count), one store per leaf met; the triangles of a leaf are enumerated in the
+     * test phase.  (The round-1 form stored every triangle index: a chain of up to seven store + branch steps per leaf in
+     * the node loop.)  The test phase starts after (FLUSH + 1) / 2 queued leaves (leaves hold <= 2 triangles by default). */
+    constexpr int LQ = (FLUSH + 1) / 2;
+    unsigned tq[LQ + 3];                             /* LQ - 1 pending + the four children of one node */
+    int nq = 0;
+    for (;;) {
+        while (node >= 0) {
+#if LB_VIS_SMEMNODES
+            /* generic loads: an entry node (LB_SM_TAG + slot) comes from its shared-memory copy, every other node from global memory */
+            const float4 *n4 = reinterpret_cast<const float4 *>(node >= LB_SM_TAG ? sm_nodes + (node - LB_SM_TAG) : nodes + node);
+            const float4 lx = n4[0], ly = n4[1], lz = n4[2], hx = n4[3], hy = n4[4], hz = n4[5];
+            const int4 k = *reinterpret_cast<const int4 *>(n4 + 6);
+#else
+            const float4 *n4 = reinterpret_cast<const float4 *>(nodes + node);
+            const float4 lx = __ldg(n4), ly = __ldg(n4 + 1), lz = __ldg(n4 + 2), hx = __ldg(n4 + 3), hy = __ldg(n4 + 4), hz = __ldg(n4 + 5);
+            const int4 k = __ldg(reinterpret_cast<const int4 *>(n4 + 6));
+#endif
+            ts.nodes += 2;
+            int next = -1;
+#define LB_BVH4_CHILD(LX, LY, LZ, HX, HY, HZ, C)                                                                        \
+            {                                                                                                           \
+                const float x0 = ((LX) - l1.x) * ix, x1 = ((HX) - l1h.x) * ix, y0 = ((LY) - l1.y) * iy, y1 = ((HY) - l1h.y) * iy; \
+                const float z0 = ((LZ) - l1.z) * iz, z1 = ((HZ) - l1h.z) * iz;                                          \
+                const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));                 \
+                const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));                 \
+                if (t0 <= t1 + 2e-6f && (C) != BVH4_EMPTY) {                                                            \
+                    if ((C) < 0) tq[nq++] = ~(unsigned)(C);                                                             \
+                    else if (next < 0) next = (C);                                                                      \
+                    else stack_n[sp++] = (C);                                                                           \
+                }                                                                                                       \
+            }
+            LB_BVH4_CHILD(lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, k.x)
+            LB_BVH4_CHILD(lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, k.y)
+            LB_BVH4_CHILD(lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, k.z)
+            LB_BVH4_CHILD(lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, k.w)
+#undef LB_BVH4_CHILD
+            node = next >= 0 ? next : (sp ? stack_n[--sp] : -1);
+            if (nq >= LQ) break;
+        }
+        while (nq) {
+            const unsigned code = tq[--nq];
+            const RayTri *tp = tris + (code >> 3);
+            for (unsigned t = code & 7u; t; --t, ++tp) {
+                RayTri T;
+                load_raytri(tp, T);
+                ts.tris++;
+                if (seg_tri_prepared(l1, d, T) < 1.0f) return true;
+            }
+        }
+        if (node < 0) return false;
+    }
+#else
     constexpr int TQ = FLUSH + 28;                   /* FLUSH - 1 pending + four leaves of up to 7 triangles */
     int tq[TQ];
     int nq = 0;
@@ -523,6 +619,7 @@ __device__ __forceinline__ bool bvh4_anyhit_core(const Bvh4Node *__restrict__ no
         }
         if (node < 0) return false;
     }
+#endif
 }
 
 template <int FLUSH = 10>
@@ -542,7 +639,7 @@ __device__ __forceinline__ bool bvh4_anyhit(const Bvh4Node *__restrict__ nodes, 
  */
 template <int FLUSH = 10>
 __device__ __forceinline__ bool bvh4_anyhit_entries(const Bvh4Node *__restrict__ nodes, const RayTri *__restrict__ tris, const BvhEntrySet &E,
-                                                    V3 l1, V3 l2, TravStats &ts)
+                                                    V3 l1, V3 l2, TravStats &ts, const Bvh4Node *sm_nodes = nullptr)
 {
     int stack_n[BVH_STACK];
     int sp = 0;
@@ -555,12 +652,16 @@ __device__ __forceinline__ bool bvh4_anyhit_entries(const Bvh4Node *__restrict__
         const float z0 = (E.loz[i] - l1.z) * iz, z1 = (E.hiz[i] - l1h.z) * iz;
         const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
         const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));
+#if LB_VIS_SMEMNODES
+        if (t0 <= t1 + 2e-6f) stack_n[sp++] = LB_SM_TAG + i;
+#else
         if (t0 <= t1 + 2e-6f) stack_n[sp++] = E.node[i];
+#endif
     }
     ts.entries += (unsigned)n;
     if (sp == 0) return false;
     const int node = stack_n[--sp];
-    return bvh4_anyhit_core<FLUSH>(nodes, tris, l1, l1h, d, ix, iy, iz, stack_n, sp, node, ts);
+    return bvh4_anyhit_core<FLUSH>(nodes, tris, l1, l1h, d, ix, iy, iz, stack_n, sp, node, ts, sm_nodes);
 }
 
 /*
@@ -670,6 +771,150 @@ __device__ __forceinline__ bool bvh4_anyhit_entries_f(const Bvh4Node *__restrict
             }
         }
         if (node < 0) { ts.nodes += 2u * visits; return false; }
+    }
+}
+
+/*
+ * LB_VIS_FMA == 2: the FMA-form walk WITHOUT the exact re-test at the leaves and without the shared-memory copy of the ray.
+ * Why no re-test is needed for identical results: a segment is blocked iff SOME triangle of the scene passes the exact
+ * seg_tri_prepared test; box tests only prune.  slabf_hit never rejects a box the plain test accepts, so the triangles
+ * tested here are a superset of the plain walk's and a subset of the scene: blocked / free come out the same (only the
+ * triangle-test counter differs).  Leaves are queued as codes (see bvh4_anyhit_core, LB_VIS_LEAFQ).
+ */
+template <int FLUSH>
+__device__ __forceinline__ bool bvh4_anyhit_entries_f2(const Bvh4Node *__restrict__ nodes, const RayTri *__restrict__ tris, const BvhEntrySet &E,
+                                                       const V3 l1, const V3 l2, TravStats &ts)
+{
+    constexpr int LQ = (FLUSH + 1) / 2;
+    int stack_n[BVH_STACK];
+    unsigned tq[LQ + 3];
+    int sp = 0, nq = 0;
+    const V3 d = l2 - l1;
+    const SlabF S = make_slabf(l1, d);
+    const int n = E.n;
+    for (int i = 0; i < n; ++i)
+        if (slabf_hit(S, E.lox[i], E.loy[i], E.loz[i], E.hix[i], E.hiy[i], E.hiz[i])) stack_n[sp++] = E.node[i];
+    ts.entries += (unsigned)n;
+    if (sp == 0) return false;
+    int node = stack_n[--sp];
+    for (;;) {
+        while (node >= 0) {
+            const float4 *n4 = reinterpret_cast<const float4 *>(nodes + node);
+            const float4 lx = __ldg(n4), ly = __ldg(n4 + 1), lz = __ldg(n4 + 2), hx = __ldg(n4 + 3), hy = __ldg(n4 + 4), hz = __ldg(n4 + 5);
+            const int4 k = __ldg(reinterpret_cast<const int4 *>(n4 + 6));
+            ts.nodes += 2;
+            int next = -1;
+#define LB_BVH4_CHILD_F2(LX, LY, LZ, HX, HY, HZ, C)                                                                     \
+            if (slabf_hit(S, LX, LY, LZ, HX, HY, HZ) && (C) != BVH4_EMPTY) {                                            \
+                if ((C) < 0) tq[nq++] = ~(unsigned)(C);                                                                 \
+                else if (next < 0) next = (C);                                                                          \
+                else stack_n[sp++] = (C);                                                                               \
+            }
+            LB_BVH4_CHILD_F2(lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, k.x)
+            LB_BVH4_CHILD_F2(lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, k.y)
+            LB_BVH4_CHILD_F2(lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, k.z)
+            LB_BVH4_CHILD_F2(lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, k.w)
+#undef LB_BVH4_CHILD_F2
+            node = next >= 0 ? next : (sp ? stack_n[--sp] : -1);
+            if (nq >= LQ) break;
+        }
+        while (nq) {
+            const unsigned code = tq[--nq];
+            const RayTri *tp = tris + (code >> 3);
+            for (unsigned t = code & 7u; t; --t, ++tp) {
+                RayTri T;
+                load_raytri(tp, T);
+                ts.tris++;
+                if (seg_tri_prepared(l1, d, T) < 1.0f) return true;
+            }
+        }
+        if (node < 0) return false;
+    }
+}
+
+/*
+ * LB_VIS_Q8: the entry-set walk over 64-byte quantised nodes (bvh.h Bvh4QNode): 4 instead of 7 sixteen-byte loads per visit.
+ * A child plane is corner + q * step; in the ray's parameter space
+ *     t = (corner + q * step - o) * inv = q * (step * inv) + (corner - o) * inv
+ * so per node and axis: sx = step * inv (exact: the step is a power of two), b = fma(corner, inv, -(o * inv)) for the lower
+ * and the upper origin, and per plane ONE fma.  The byte q becomes a float without a conversion instruction: PRMT puts it
+ * under the exponent of 2^23 (0x4B000000 | q = 8388608 + q exactly) and the constant is folded into b:
+ *     t = fma(8388608 + q, sx, b - 8388608 * sx).
+ * Rounding: b - 8388608 * sx is off by at most half an ulp of 2^23 * sx = sx / 2 -- half a quantisation step in t -- which
+ * the builder's one-step widening covers; the remaining terms are those of the FMA form (make_slabf's eps).  Box tests only
+ * prune, so as with LB_VIS_FMA == 2 blocked / free are those of the plain walk.
+ */
+__device__ __forceinline__ float q8_magic(uint32_t word, int byte)
+{
+    uint32_t r;
+    switch (byte) {                                  /* selector nibbles pick: byte k of `word` as the low byte, 00 00 4B above it */
+    case 0: asm("prmt.b32 %0, %1, %2, 0x7440;" : "=r"(r) : "r"(word), "r"(0x4B000000u)); break;
+    case 1: asm("prmt.b32 %0, %1, %2, 0x7441;" : "=r"(r) : "r"(word), "r"(0x4B000000u)); break;
+    case 2: asm("prmt.b32 %0, %1, %2, 0x7442;" : "=r"(r) : "r"(word), "r"(0x4B000000u)); break;
+    default: asm("prmt.b32 %0, %1, %2, 0x7443;" : "=r"(r) : "r"(word), "r"(0x4B000000u)); break;
+    }
+    return __uint_as_float(r);
+}
+
+template <int FLUSH>
+__device__ __forceinline__ bool bvh4q_anyhit_entries(const Bvh4QNode *__restrict__ nodes, const RayTri *__restrict__ tris, const BvhEntrySet &E,
+                                                     const V3 l1, const V3 l2, TravStats &ts)
+{
+    constexpr int LQ = (FLUSH + 1) / 2;
+    int stack_n[BVH_STACK];
+    unsigned tq[LQ + 3];
+    int sp = 0, nq = 0;
+    const V3 d = l2 - l1;
+    const SlabF S = make_slabf(l1, d);
+    const int n = E.n;
+    for (int i = 0; i < n; ++i)
+        if (slabf_hit(S, E.lox[i], E.loy[i], E.loz[i], E.hix[i], E.hiy[i], E.hiz[i])) stack_n[sp++] = E.node[i];
+    ts.entries += (unsigned)n;
+    if (sp == 0) return false;
+    int node = stack_n[--sp];
+    for (;;) {
+        while (node >= 0) {
+            const uint4 *n4 = reinterpret_cast<const uint4 *>(nodes + node);
+            const uint4 a = __ldg(n4), b = __ldg(n4 + 1), c = __ldg(n4 + 2), k4 = __ldg(n4 + 3);
+            ts.nodes += 1;                           /* 64 bytes per visit */
+            const float sx = __uint_as_float((a.w & 0xffu) << 23) * S.ix, sy = __uint_as_float((a.w & 0xff00u) << 15) * S.iy, sz = __uint_as_float((a.w & 0xff0000u) << 7) * S.iz;
+            const float ox = __uint_as_float(a.x), oy = __uint_as_float(a.y), oz = __uint_as_float(a.z);
+            const float blx = __fmaf_rn(-8388608.f, sx, __fmaf_rn(ox, S.ix, S.nlx)), bhx = __fmaf_rn(-8388608.f, sx, __fmaf_rn(ox, S.ix, S.nhx));
+            const float bly = __fmaf_rn(-8388608.f, sy, __fmaf_rn(oy, S.iy, S.nly)), bhy = __fmaf_rn(-8388608.f, sy, __fmaf_rn(oy, S.iy, S.nhy));
+            const float blz = __fmaf_rn(-8388608.f, sz, __fmaf_rn(oz, S.iz, S.nlz)), bhz = __fmaf_rn(-8388608.f, sz, __fmaf_rn(oz, S.iz, S.nhz));
+            int next = -1;
+#define LB_BVH4Q_CHILD(B, C)                                                                                            \
+            {                                                                                                           \
+                const float x0 = __fmaf_rn(q8_magic(b.x, B), sx, blx), x1 = __fmaf_rn(q8_magic(b.w, B), sx, bhx);        \
+                const float y0 = __fmaf_rn(q8_magic(b.y, B), sy, bly), y1 = __fmaf_rn(q8_magic(c.x, B), sy, bhy);        \
+                const float z0 = __fmaf_rn(q8_magic(b.z, B), sz, blz), z1 = __fmaf_rn(q8_magic(c.y, B), sz, bhz);        \
+                const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));                 \
+                const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));                 \
+                if (t0 <= t1 + S.eps && (C) != BVH4_EMPTY) {                                                            \
+                    if ((C) < 0) tq[nq++] = ~(unsigned)(C);                                                             \
+                    else if (next < 0) next = (C);                                                                      \
+                    else stack_n[sp++] = (C);                                                                           \
+                }                                                                                                       \
+            }
+            LB_BVH4Q_CHILD(0, (int)c.z)
+            LB_BVH4Q_CHILD(1, (int)c.w)
+            LB_BVH4Q_CHILD(2, (int)k4.x)
+            LB_BVH4Q_CHILD(3, (int)k4.y)
+#undef LB_BVH4Q_CHILD
+            node = next >= 0 ? next : (sp ? stack_n[--sp] : -1);
+            if (nq >= LQ) break;
+        }
+        while (nq) {
+            const unsigned code = tq[--nq];
+            const RayTri *tp = tris + (code >> 3);
+            for (unsigned t = code & 7u; t; --t, ++tp) {
+                RayTri T;
+                load_raytri(tp, T);
+                ts.tris++;
+                if (seg_tri_prepared(l1, d, T) < 1.0f) return true;
+            }
+        }
+        if (node < 0) return false;
     }
 }
 

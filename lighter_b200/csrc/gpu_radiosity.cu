@@ -478,14 +478,20 @@ template <int G> static size_t rad_sweep_smem() { return sizeof(RadColBuf<G>) * 
 #endif
 template <bool ENTRY>
 __global__ void __launch_bounds__(LB_BLOCK, LB_VIS_MINBLOCKS)
-rad_visibility_kernel(const Bvh4Node *__restrict__ bvh, const RayTri *__restrict__ raytris, const float4 *__restrict__ spos,
+rad_visibility_kernel(const Bvh4Node *__restrict__ bvh, const Bvh4QNode *__restrict__ bvhq, const RayTri *__restrict__ raytris, const float4 *__restrict__ spos,
                       const uint32_t *__restrict__ sidx, const RadCand *__restrict__ cand, unsigned long long n_cand,
                       uint32_t my_k0, uint32_t my_k1, unsigned long long *__restrict__ keys, float *__restrict__ factors,
                       unsigned long long *link_count, uint4 *__restrict__ mirror, unsigned long long mirror_cap, unsigned long long *mirror_count,
                       uint32_t *chunk_cursor, unsigned long long *counters)
 {
     __shared__ BvhEntrySet s_entry[LB_BLOCK / 32];
-#if LB_VIS_FMA
+#if LB_VIS_SMEMNODES
+    __shared__ __align__(16) Bvh4Node s_enode[LB_BLOCK / 32][BVH_ENTRY_MAX];
+    const Bvh4Node *sm_nodes = s_enode[threadIdx.x >> 5];
+#else
+    const Bvh4Node *sm_nodes = nullptr;
+#endif
+#if LB_VIS_FMA == 1
     __shared__ float s_ray[9][LB_BLOCK];
 #endif
 #if LB_VIS_LEAN
@@ -531,6 +537,11 @@ rad_visibility_kernel(const Bvh4Node *__restrict__ bvh, const RayTri *__restrict
             if (!(lx <= hx)) continue;                /* warp-uniform: the chunk holds only unused slots */
             bvh_entry_pad(lx, ly, lz, hx, hy, hz);
             bvh_entry_search_warp<Bvh4Access>(bvh, lx, ly, lz, hx, hy, hz, E, lane);   /* syncs the warp before it overwrites the previous chunk's set */
+#if LB_VIS_SMEMNODES
+            for (unsigned q = lane; q < (unsigned)E.n * 8u; q += 32u)                  /* 8 float4 per node record */
+                reinterpret_cast<float4 *>(s_enode[threadIdx.x >> 5])[q] = __ldg(reinterpret_cast<const float4 *>(bvh + E.node[q >> 3]) + (q & 7u));
+            __syncwarp();
+#endif
         }
 #if LB_VIS_LEAN
         /* Register-lean batch loop.  Across the walk only `blocked`, the batch position and the lane's statistics slots are
@@ -565,10 +576,14 @@ rad_visibility_kernel(const Bvh4Node *__restrict__ bvh, const RayTri *__restrict
                     const V3 dn = norm3(B - A);
                     const V3 mA = A + dn * LB_SMALL, mB = B - dn * LB_SMALL;
                     TravStats t1 = { 0, 0, 0 };
-#if LB_VIS_FMA
+#if LB_VIS_Q8
+                    blocked = ENTRY ? bvh4q_anyhit_entries<LB_VIS_FLUSH>(bvhq, raytris, E, mA, mB, t1) : bvh4_anyhit<LB_VIS_FLUSH>(bvh, raytris, mA, mB, t1);
+#elif LB_VIS_FMA == 2
+                    blocked = ENTRY ? bvh4_anyhit_entries_f2<LB_VIS_FLUSH>(bvh, raytris, E, mA, mB, t1) : bvh4_anyhit<LB_VIS_FLUSH>(bvh, raytris, mA, mB, t1);
+#elif LB_VIS_FMA
                     blocked = ENTRY ? bvh4_anyhit_entries_f<LB_VIS_FLUSH>(bvh, raytris, E, mA, mB, &s_ray[0][threadIdx.x], t1) : bvh4_anyhit<LB_VIS_FLUSH>(bvh, raytris, mA, mB, t1);
 #else
-                    blocked = ENTRY ? bvh4_anyhit_entries<LB_VIS_FLUSH>(bvh, raytris, E, mA, mB, t1) : bvh4_anyhit<LB_VIS_FLUSH>(bvh, raytris, mA, mB, t1);
+                    blocked = ENTRY ? bvh4_anyhit_entries<LB_VIS_FLUSH>(bvh, raytris, E, mA, mB, t1, sm_nodes) : bvh4_anyhit<LB_VIS_FLUSH>(bvh, raytris, mA, mB, t1);
 #endif
                     s_stat[0][threadIdx.x] += 1u; s_stat[1][threadIdx.x] += t1.nodes; s_stat[2][threadIdx.x] += t1.tris; s_stat[3][threadIdx.x] += t1.entries;
                 }
@@ -1016,7 +1031,7 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
                 unsigned cap = (unsigned)ctx->num_sms * 16;
                 unsigned blocks = want > cap ? cap : (unsigned)want;
                 RAD_CU(cudaEventRecord(ctx->ev_k0, st));
-#define RAD_VIS(ENTRY) rad_visibility_kernel<ENTRY><<<blocks, LB_BLOCK, 0, st>>>(ctx->d_bvh4, ctx->d_raytris, spos, sidx, cand, nc, (uint32_t)k0, (uint32_t)k1, \
+#define RAD_VIS(ENTRY) rad_visibility_kernel<ENTRY><<<blocks, LB_BLOCK, 0, st>>>(ctx->d_bvh4, ctx->d_bvh4q, ctx->d_raytris, spos, sidx, cand, nc, (uint32_t)k0, (uint32_t)k1, \
                                                                   keys + link_used, fac + link_used, d_cnt + 1,                                                \
                                                                   mirror ? mirror + mirror_used : nullptr, mirror ? mirror_cap - mirror_used : 0, d_cnt + 2,  \
                                                                   (uint32_t *)(d_cnt + 3) + 1, ctx->d_counters)

@@ -150,6 +150,47 @@ int lb_upload_staged(ltrgpu_Ctx *ctx, void *dst, const void *src, size_t bytes)
     return 0;
 }
 
+#if LB_VIS_Q8
+/* Bvh4Node -> Bvh4QNode (bvh.h), one thread per node.  Per axis: step = the power of two >= extent / 250 (at least 2^-12),
+ * corner = lowest child plane minus one step, rounded down; a lower plane is floor((lo - corner) / step) - 1, an upper plane
+ * ceil((hi - corner) / step) + 1 (computed in double: exact for these magnitudes), so corner + q * step lies at least one
+ * full step outside the float plane.  Unused slots get an inverted box. */
+__global__ void quantise_bvh4_kernel(const Bvh4Node *__restrict__ in, uint32_t n, Bvh4QNode *__restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Bvh4Node N = in[i];
+    Bvh4QNode Q;
+    const float *lo[3] = { N.lox, N.loy, N.loz }, *hi[3] = { N.hix, N.hiy, N.hiz };
+    float corner[3];
+    uint32_t ql[3] = { 0, 0, 0 }, qh[3] = { 0, 0, 0 }, exps = 0;
+    for (int a = 0; a < 3; ++a) {
+        float mn = INFINITY, mx = -INFINITY;
+        for (int c = 0; c < 4; ++c) if (N.c[c] != BVH4_EMPTY) { mn = fminf(mn, lo[a][c]); mx = fmaxf(mx, hi[a][c]); }
+        if (!(mn <= mx)) { mn = mx = 0.f; }
+        int e;
+        frexpf(fmaxf((mx - mn) / 250.0f, 1.0f / 4096.0f), &e);          /* x = m * 2^e, m in [0.5, 1): 2^e >= x */
+        const float step = ldexpf(1.0f, e);
+        const float o = __fsub_rd(mn, step);
+        corner[a] = o;
+        exps |= (uint32_t)(e + 127) << (8 * a);
+        for (int c = 0; c < 4; ++c) {
+            uint32_t l = 255u, h = 0u;
+            if (N.c[c] != BVH4_EMPTY) {
+                const double fl = floor(((double)lo[a][c] - (double)o) / (double)step) - 1.0, ch = ceil(((double)hi[a][c] - (double)o) / (double)step) + 1.0;
+                l = (uint32_t)fmin(fmax(fl, 0.0), 255.0); h = (uint32_t)fmin(fmax(ch, 0.0), 255.0);
+            }
+            ql[a] |= l << (8 * c); qh[a] |= h << (8 * c);
+        }
+    }
+    Q.ox = corner[0]; Q.oy = corner[1]; Q.oz = corner[2]; Q.exps = exps;
+    Q.qlox = ql[0]; Q.qloy = ql[1]; Q.qloz = ql[2]; Q.qhix = qh[0]; Q.qhiy = qh[1]; Q.qhiz = qh[2];
+    for (int c = 0; c < 4; ++c) Q.c[c] = N.c[c];
+    Q.pad[0] = Q.pad[1] = 0;
+    out[i] = Q;
+}
+#endif
+
 /* one thread per BVH-order triangle: expand the 9 floats into the two prepared records
  * (geom.h) with the reference's exact expressions. */
 __global__ void prepare_tris_kernel(const float *__restrict__ tris9, const uint32_t *__restrict__ order /* slot -> triangle, or NULL */, uint32_t n,
@@ -243,7 +284,7 @@ extern "C" void ltrgpu_destroy(ltrgpu_Ctx *ctx)
     dev_free(&ctx->d_inst); dev_free(&ctx->d_wpos); dev_free(&ctx->d_wnrm); dev_free(&ctx->d_vtex); dev_free(&ctx->d_ltex);
     dev_free(&ctx->d_rtris); dev_free(&ctx->d_rnodes); dev_free(&ctx->d_ritems); dev_free(&ctx->d_rtree_tris); dev_free(&ctx->d_rtree_ptris); dev_free(&ctx->d_rtree_boxes);
     if (ctx->lbvh_owned) { lb_free(ctx->d_lbvh); lb_free(ctx->d_lbvh_ptris); }
-    dev_free(&ctx->d_bvh); dev_free(&ctx->d_bvh4); dev_free(&ctx->d_ptris); dev_free(&ctx->d_raytris); dev_free(&ctx->d_tri_orig);
+    dev_free(&ctx->d_bvh); dev_free(&ctx->d_bvh4); dev_free(&ctx->d_bvh4q); dev_free(&ctx->d_ptris); dev_free(&ctx->d_raytris); dev_free(&ctx->d_tri_orig);
     dev_free(&ctx->d_lights); dev_free(&ctx->d_light_inst); dev_free(&ctx->d_light_samples); dev_free(&ctx->d_probe_pos); dev_free(&ctx->d_probe_nrm);
     dev_free(&ctx->d_ao_cos); dev_free(&ctx->d_ao_sin); dev_free(&ctx->d_blur_kernel); dev_free(&ctx->d_counters);
     free(ctx->h_inst); free(ctx->h_lights); free(ctx->h_inst_lumel_off);
@@ -374,7 +415,7 @@ extern "C" int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *d)
         if (dev_upload(ctx, &ctx->d_bvh, d->bvh, d->n_bvh_nodes)) return 1;
         if (dev_upload(ctx, &ctx->d_bvh4, d->bvh4, d->n_bvh4_nodes)) return 1;
         if (dev_upload(ctx, &ctx->d_tri_orig, d->tri_orig, d->n_tris)) return 1;
-        ctx->bvh_height = d->bvh_height;
+        ctx->bvh_height = d->bvh_height; ctx->n_bvh4_nodes = d->n_bvh4_nodes;
         if (d->n_tris) {
             prepare_tris_kernel<<<grid_for(d->n_tris, 256), 256, 0, ctx->stream>>>(d_raw, nullptr, d->n_tris, ctx->d_ptris, ctx->d_raytris);
             CU_LAUNCH_CHECK(ctx);
@@ -386,13 +427,20 @@ extern "C" int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *d)
         if (lb_build_bvh_device(ctx->stream, d_raw, d->n_tris, d->bvh_leaf_max, ctx->num_sms, &T, ctx->err, sizeof(ctx->err))) return 1;
         CU_TRY(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
         ctx->d_bvh = T.nodes; ctx->d_bvh4 = T.nodes4; ctx->d_tri_orig = T.order;
-        ctx->n_bvh_nodes = T.n_nodes; ctx->bvh_height = T.height;
+        ctx->n_bvh_nodes = T.n_nodes; ctx->bvh_height = T.height; ctx->n_bvh4_nodes = T.n_nodes4;
         ctx->host_counters.kernel_launches += T.launches;
         prepare_tris_kernel<<<grid_for(d->n_tris, 256), 256, 0, ctx->stream>>>(d_raw, ctx->d_tri_orig, d->n_tris, ctx->d_ptris, ctx->d_raytris);
         CU_LAUNCH_CHECK(ctx);
         CU_TRY(ctx, cudaEventSynchronize(ctx->ev_k1));
         CU_TRY(ctx, cudaEventElapsedTime(&ctx->bvh_build_ms, ctx->ev_k0, ctx->ev_k1));
     }
+#if LB_VIS_Q8
+    if (dev_alloc(ctx, &ctx->d_bvh4q, ctx->n_bvh4_nodes)) return 1;
+    if (ctx->n_bvh4_nodes) {
+        quantise_bvh4_kernel<<<grid_for(ctx->n_bvh4_nodes, 128), 128, 0, ctx->stream>>>(ctx->d_bvh4, ctx->n_bvh4_nodes, ctx->d_bvh4q);
+        CU_LAUNCH_CHECK(ctx);
+    }
+#endif
     /* the traversal stacks are fixed (BVH_STACK): binary walks push one node per level, the 4-wide walk up to three per two levels */
     if (ctx->bvh_height > 40) {
         snprintf(ctx->err, sizeof(ctx->err), "scene BVH is %d levels deep; the traversal stacks hold 40", ctx->bvh_height);

@@ -10,21 +10,11 @@
 
 #include "lighter_b200.h"
 
+/* the production march (gpu_internal.cuh march_shadow) */
 __device__ __forceinline__ float march_shadow_test(const BvhNode *bvh, const PreparedTri *tris, V3 from, V3 to, float k, unsigned &queries)
 {
     TravStats ts = { 0, 0 };
-    V3 rd = norm3(to - from);
-    float maxt = len3(to - from);
-    float res = 1.0f;
-    for (float t = 0.001f; t < maxt;) {
-        float h = bvh_distance(bvh, tris, from + rd * t, 2.0f, 0.001f, ts);
-        ++queries;
-        if (h < 0.001f) return 0.0f;
-        res = fminr(res, h / fminr(t * k, 2.0f));
-        h = fminr(h, 1.0f);
-        t += h;
-    }
-    return res;
+    return march_shadow(bvh, tris, from, to, k, queries, ts);
 }
 
 __global__ void t_ptd_kernel(const float *pts, const float *tris, uint32_t n, float *out)

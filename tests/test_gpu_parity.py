@@ -123,6 +123,33 @@ def test_shadow_march_equals_oracle(oracle):
     assert (got == 0).any() and (got == 1).any() and ((got > 0) & (got < 1)).any()
 
 
+@pytest.mark.parametrize("name", ["config4_sibling", "config3_sibling"])
+def test_shadow_march_long_equals_oracle(oracle, name):
+    """The production march (gpu_internal.cuh march_shadow) on the synthetic terrain / interior siblings: marches of up to 60
+    units from just above the surfaces towards lights in open air, past pillars and under ceilings.  Factors and step counts
+    must equal the oracle's brute-force march bit for bit."""
+    sc = scenes.workload(name)
+    tris = scene_tris(sc)
+    rng = np.random.default_rng(5)
+    n = 240
+    t3 = tris.reshape(-1, 3, 3)
+    pick = rng.integers(0, len(t3), n)
+    w = rng.dirichlet((1, 1, 1), n).astype(np.float32)
+    on = (t3[pick] * w[:, :, None]).sum(1)
+    nrm = np.cross(t3[pick, 1] - t3[pick, 0], t3[pick, 2] - t3[pick, 0])
+    nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-20)
+    frm = (on + nrm * 0.005).astype(np.float32)
+    lights = np.array([L.position for L in sc.lights if L.type != 3] or [[0, 0, 10]], np.float32)
+    to = lights[rng.integers(0, len(lights), n)].copy()
+    to[::4] = frm[::4] + np.array([20.0, -30.0, 45.0], np.float32)          # long marches into the sky
+    to[1::4] = frm[1::4] + rng.uniform(-40, 40, (len(to[1::4]), 3)).astype(np.float32)
+    k = rng.choice(np.array([0.05, 0.2, 0.5], np.float32), n)
+    got, steps = api.test_march(tris, frm, to, k)
+    want, wsteps = oracle.march(tris, frm, to, k)
+    assert bits_equal(got, want) and np.array_equal(steps, wsteps)
+    assert steps.max() >= 40 and (got == 0).any() and (got > 0).any()
+
+
 # ---- full bakes against the golden fixtures ----------------------------------------------------------
 @pytest.mark.parametrize("name", ["basic", "hugeoverlap", "mesh1", "rad1"])
 def test_bake_matches_reference_golden(name, bakes):

@@ -115,6 +115,17 @@ def main():
     print("walk cost per segment (model): %.0f slots; lock-step batches use %.0f %% of their lane slots, lane refill within a chunk %.0f %%"
           % (useful / ns, 100 * useful / lock, 100 * useful / refill))
     print("=> upper bound of the gain from lane refill on the traversal part: %.0f %%" % (100 * (1 - refill / lock)))
+    # refill inside groups of G segments only (a per-warp ring of G prepared rays, drained before the next G are prepared)
+    for G in (64, 128, 256, 512):
+        tot = 0.0
+        for b in range(len(offs) - 1):
+            c = cost[offs[b]:offs[b + 1]]
+            for g0 in range(0, len(c), G):
+                lanes = np.zeros(32)
+                for x in c[g0:g0 + G]:
+                    lanes[lanes.argmin()] += x
+                tot += lanes.max() * 32
+        print("   refill within groups of %4d segments: %.0f %% of the lane slots used" % (G, 100 * useful / tot))
 
 
 if __name__ == "__main__":
