@@ -45,6 +45,7 @@ typedef struct ltrx_Stats {
     uint64_t n_rad_batches;                   /* launches of the pair-sweep / visibility kernel pair (candidate buffer refills) */
     uint64_t n_shadow_rays;                   /* sampled-shadow extension: any-hit rays, lumel x light x sample */
     uint64_t n_ray_entry_tests;               /* entry boxes tested by rays that start at a bundle's entry set instead of the root */
+    double t_sample_fn;                       /* host seconds the sample_fn thread ran (request chunks + callbacks); overlaps t_direct and t_radiosity */
 } ltrx_Stats;
 
 typedef struct ltrx_Lumels {
@@ -64,6 +65,8 @@ typedef struct ltrx_Links {
 } ltrx_Links;
 
 LTRAPI const char *ltrx_Version(void);
+/* example native material callback, assignable to ltr_Config::sample_fn (see bake.cpp) */
+LTRAPI LTRBOOL ltrx_SampleFnChecker(ltr_Config *config, ltr_SampleRequest *req);
 
 /* multi-GPU -------------------------------------------------------------------------------- */
 LTRAPI int  ltrx_SetDevice(ltr_Scene *scene, int cuda_device);

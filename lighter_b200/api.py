@@ -96,7 +96,8 @@ class Stats(C.Structure):
                                            "n_distance_queries", "n_ao_segments", "n_correction_rays", "n_rad_pairs",
                                            "n_rad_segments", "n_rad_links", "n_node_visits", "n_tri_tests",
                                            "n_ray_node_visits", "n_ray_tri_tests", "n_rad_tile_loads",
-                                           "kernel_launches", "h2d_bytes", "d2h_bytes", "n_rad_batches", "n_shadow_rays", "n_ray_entry_tests")])
+                                           "kernel_launches", "h2d_bytes", "d2h_bytes", "n_rad_batches", "n_shadow_rays", "n_ray_entry_tests")] +
+                [("t_sample_fn", C.c_double)])
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -155,7 +156,7 @@ class Links(C.Structure):
 LTR_SYMBOLS = ["ltr_DefaultSizeFunc", "ltr_CreateScene", "ltr_DestroyScene", "ltr_Start", "ltr_Abort", "ltr_GetStatus",
                "ltr_Sleep", "ltr_GetConfig", "ltr_SetConfig", "ltr_CreateMesh", "ltr_MeshAddPart", "ltr_MeshAddInstance",
                "ltr_LightAdd", "ltr_SampleAdd", "ltr_GetWorkOutputInfo", "ltr_GetWorkOutput", "ltr_NextPowerOfTwo"]
-LTRX_SYMBOLS = ["ltrx_Version", "ltrx_SetDevice", "ltrx_SetOutputRoot", "ltrx_NcclUniqueId", "ltrx_SetShard", "ltrx_ShardRange", "ltrx_GetStats",
+LTRX_SYMBOLS = ["ltrx_Version", "ltrx_SampleFnChecker", "ltrx_SetDevice", "ltrx_SetOutputRoot", "ltrx_NcclUniqueId", "ltrx_SetShard", "ltrx_ShardRange", "ltrx_GetStats",
                 "ltrx_GetError", "ltrx_Prepare", "ltrx_BakeResident", "ltrx_Finish", "ltrx_OutputHash", "ltrx_SetDebug", "ltrx_GetLumels",
                 "ltrx_GetLinks", "ltrx_GetShadowFactors", "ltrx_SetShadowMode", "ltrx_GetShadowMasks", "ltrx_ShadowSampleSegment",
                 "ltrx_test_point_tri_distance", "ltrx_test_seg_tri",
@@ -298,6 +299,8 @@ class BakeHandle:
         cfg.ao_color_rgb = VEC3(*c["ao_color"])
         if c["sample_fn_kind"] == 1:
             cfg.sample_fn = _redwall_sample_fn
+        elif c["sample_fn_kind"] == 2:          # the library's native example callback (no interpreter in the per-lumel loop)
+            cfg.sample_fn = C.cast(L.ltrx_SampleFnChecker, SAMPLE_FN)
         if c["size_fn_kind"] == 1:
             forced = {i.ident.encode(): i.force_size for i in scene.instances if i.force_size[0]}
 

@@ -611,6 +611,81 @@ void upload(ltr_Scene *S)
 }
 
 /* ------------------------------------------------------------------------------------------
+ * sample_fn batching (ref: lighter.cpp:690-715)
+ * ------------------------------------------------------------------------------------------ */
+struct MaterialJob {
+    static constexpr uint32_t CHUNK = 1u << 18;       /* lumels per chunk: 12 MB of request records */
+    float *diffuse = nullptr, *emissive = nullptr;     /* n x 3 each, page-locked: uploaded by one DMA each */
+    ltrgpu_SampleReq *req[2] = { nullptr, nullptr };
+    std::thread th;
+    std::string error;
+    double seconds = 0;
+    bool started = false;
+
+    void start(ltr_Scene *S, uint64_t n)
+    {
+        Bake &B = *S->bake;
+        gpu_check(S, ltrgpu_sample_requests_begin(B.gpu), "sample requests");
+        diffuse = (float *)ltrgpu_host_alloc(n * 12); emissive = (float *)ltrgpu_host_alloc(n * 12);
+        for (int b = 0; b < 2; ++b) req[b] = (ltrgpu_SampleReq *)ltrgpu_host_alloc((size_t)CHUNK * sizeof(ltrgpu_SampleReq));
+        if (!diffuse || !emissive || !req[0] || !req[1]) { Fail f; f.msg = "out of host memory for the material tables"; throw f; }
+        started = true;
+        th = std::thread([this, S, n]() { run(S, n); });
+    }
+    void run(ltr_Scene *S, uint64_t n)
+    {
+        const double t0 = now_s();
+        Bake &B = *S->bake;
+        const uint64_t first_mesh = B.lumel_off[1];                     /* probes (instance 0) never reach the callback: diffuse 0 on the device */
+        for (uint64_t i = 0; i < first_mesh * 3; ++i) { diffuse[i] = 1.f; emissive[i] = 0.f; }
+        auto count_at = [&](uint64_t c0) { return (uint32_t)std::min<uint64_t>(CHUNK, n - c0); };
+        size_t m = 1;                                                   /* instance of the current lumel */
+        int slot = 0;
+        if (first_mesh < n && ltrgpu_sample_requests_issue(B.gpu, first_mesh, count_at(first_mesh), req[0], 0)) { error = ltrgpu_aux_error(B.gpu); return; }
+        for (uint64_t c0 = first_mesh; c0 < n; c0 += CHUNK, slot ^= 1) {
+            const uint32_t cnt = count_at(c0);
+            const uint64_t c1 = c0 + cnt;
+            if (c1 < n && ltrgpu_sample_requests_issue(B.gpu, c1, count_at(c1), req[slot ^ 1], slot ^ 1)) { error = ltrgpu_aux_error(B.gpu); return; }
+            if (ltrgpu_sample_requests_wait(B.gpu, slot)) { error = ltrgpu_aux_error(B.gpu); return; }
+            const ltrgpu_SampleReq *q = req[slot];
+            for (uint32_t k = 0; k < cnt; ++k) {
+                const uint64_t i = c0 + k;
+                while (i >= B.lumel_off[m + 1]) ++m;
+                const MeshInstance *mi = S->instances[m];
+                ltr_SampleRequest r;
+                memset(&r, 0, sizeof(r));
+                memcpy(r.position, q[k].pos, 12); memcpy(r.normal, q[k].nrm, 12);
+                r.tex0u = q[k].tex0[0]; r.tex0v = q[k].tex0[1]; r.tex1u = q[k].tex1[0]; r.tex1v = q[k].tex1[1];
+                r.part_id = q[k].part_id;
+                r.mesh_ident = mi->mesh->ident.c_str(); r.mesh_ident_size = mi->mesh->ident.size();
+                r.inst_ident = mi->ident.c_str(); r.inst_ident_size = mi->ident.size();
+                r.out_diffuse_color[0] = r.out_diffuse_color[1] = r.out_diffuse_color[2] = 1;
+                float *dd = diffuse + i * 3, *ee = emissive + i * 3;
+                if (S->config.sample_fn(&S->config, &r)) { memcpy(dd, r.out_diffuse_color, 12); memcpy(ee, r.out_emissive_color, 12); }
+                else { dd[0] = dd[1] = dd[2] = 1.f; ee[0] = ee[1] = ee[2] = 0.f; }
+            }
+        }
+        seconds = now_s() - t0;
+    }
+    /* ltrgpu_materials_fn: called by the radiosity stage when the bounces need the materials */
+    static int ready(void *user, const float **d, const float **e)
+    {
+        MaterialJob *J = (MaterialJob *)user;
+        *d = *e = nullptr;
+        if (!J->started) return 0;
+        if (J->th.joinable()) J->th.join();
+        if (!J->error.empty()) return 1;
+        *d = J->diffuse; *e = J->emissive;
+        return 0;
+    }
+    ~MaterialJob()
+    {
+        if (th.joinable()) th.join();
+        ltrgpu_host_free(diffuse); ltrgpu_host_free(emissive); ltrgpu_host_free(req[0]); ltrgpu_host_free(req[1]);
+    }
+};
+
+/* ------------------------------------------------------------------------------------------
  * GPU stages (re-runnable on a resident scene)
  * ------------------------------------------------------------------------------------------ */
 void gpu_stages(ltr_Scene *S)
@@ -636,6 +711,14 @@ void gpu_stages(ltr_Scene *S)
     S->stats.n_lumels_total = n;
     S->stats.n_lumels_local = se - sb;
     S->stats.t_samples = now_s() - t0;
+
+    /* sample_fn (the material callback, ref: lighter.cpp:690-715) runs on its own host thread from here on, concurrently with
+     * the direct-light stage and radiosity link generation on the GPU; radiosity waits for it right before the first bounce
+     * (MaterialJob::ready).  Calls are made one at a time in the reference's order -- instance ascending, lumel ascending --
+     * because a callback may keep state; what is batched is everything around them: the request fields are computed on the
+     * device and arrive in pinned chunks on a second stream (chunk k+1 in flight while the callbacks of chunk k run). */
+    MaterialJob matjob;
+    if (cfg.bounce_count && cfg.sample_fn && n) matjob.start(S, n);
 
     /* Replay of the reference's rand() consumption for the AO pass: one randf() per lumel, instance by
      * instance (probe container first), lumel index ascending (lighter.cpp:819,1130-1135).  The draws
@@ -677,39 +760,10 @@ void gpu_stages(ltr_Scene *S)
     if (cfg.bounce_count) {
         S->stage.store("calculating radiosity");
         S->completion.store(0.f);
-        std::vector<float> diffuse, emissive;
-        if (cfg.sample_fn && n) {
-            /* material callback round trip: lumels to host, one call per mesh lumel in global order
-             * (instance ascending, lumel ascending), results back to the device */
-            std::vector<float> pos(n * 3), nrm(n * 3), rad(n * 4);
-            std::vector<uint32_t> loc(n);
-            gpu_check(S, ltrgpu_download_lumels(B.gpu, pos.data(), nrm.data(), loc.data(), rad.data(), nullptr), "lumel download");
-            diffuse.assign(n * 3, 1.f); emissive.assign(n * 3, 0.f);
-            for (size_t m = 1; m < ni; ++m) {
-                MeshInstance *mi = S->instances[m];
-                for (uint64_t i = B.lumel_off[m]; i < B.lumel_off[m + 1]; ++i) {
-                    V3 N = norm3(mk3(nrm[i * 3], nrm[i * 3 + 1], nrm[i * 3 + 2]));
-                    const int lx = (int)(loc[i] % mi->lm_width), ly = (int)(loc[i] / mi->lm_width);
-                    ltr_SampleRequest req;
-                    memset(&req, 0, sizeof(req));
-                    req.position[0] = pos[i * 3]; req.position[1] = pos[i * 3 + 1]; req.position[2] = pos[i * 3 + 2];
-                    req.normal[0] = N.x; req.normal[1] = N.y; req.normal[2] = N.z;
-                    req.tex0u = rad[i * 4]; req.tex0v = rad[i * 4 + 1];
-                    req.tex1u = (lx + 0.5f) / mi->lm_width; req.tex1v = (ly + 0.5f) / mi->lm_height;
-                    req.part_id = (uint32_t)rad[i * 4 + 2];
-                    req.mesh_ident = mi->mesh->ident.c_str(); req.mesh_ident_size = mi->mesh->ident.size();
-                    req.inst_ident = mi->ident.c_str(); req.inst_ident_size = mi->ident.size();
-                    req.out_diffuse_color[0] = req.out_diffuse_color[1] = req.out_diffuse_color[2] = 1;
-                    if (cfg.sample_fn(&S->config, &req)) {
-                        memcpy(&diffuse[i * 3], req.out_diffuse_color, 12);
-                        memcpy(&emissive[i * 3], req.out_emissive_color, 12);
-                    }
-                }
-            }
-        }
         S->stage.store("bouncing light");
-        gpu_check(S, ltrgpu_radiosity(B.gpu, diffuse.empty() ? nullptr : diffuse.data(), diffuse.empty() ? nullptr : emissive.data(), cfg.bounce_count),
-                  "radiosity");
+        gpu_check(S, ltrgpu_radiosity_ex(B.gpu, MaterialJob::ready, &matjob, cfg.bounce_count), "radiosity");
+        if (!matjob.error.empty()) { Fail f; f.msg = matjob.error; throw f; }
+        S->stats.t_sample_fn = matjob.seconds;
         S->stage.store("committing radiosity");
         S->completion.store(1.f);
     }
@@ -858,6 +912,19 @@ void bake_free(ltr_Scene *S)
 extern "C" {
 
 const char *ltrx_Version(void) { return "lighter_b200 0.1 (sm_100a)"; }
+
+/* A ready-made native material callback for ltr_Config::sample_fn (callers in Python / ctypes can time large bakes without
+ * a per-lumel trip through the interpreter): 4-unit checker of two albedos, the second graded by the lightmap u coordinate,
+ * downward-facing surfaces glow, every 64th (cell, part) combination is declined (return 0 = keep the defaults). */
+LTRBOOL ltrx_SampleFnChecker(ltr_Config *, ltr_SampleRequest *req)
+{
+    const int s = (int)floorf(req->position[0] * 0.25f) + (int)floorf(req->position[1] * 0.25f);
+    if (((s ^ (int)req->part_id) & 63) == 63) return 0;
+    if (s & 1) { req->out_diffuse_color[0] = 0.5f; req->out_diffuse_color[1] = 0.05f; req->out_diffuse_color[2] = 0.02f; }
+    else { req->out_diffuse_color[0] = 0.7f; req->out_diffuse_color[1] = 0.7f * req->tex1u; req->out_diffuse_color[2] = 0.6f; }
+    if (req->normal[2] < -0.5f) { req->out_emissive_color[0] = 0.1f; req->out_emissive_color[1] = 0.1f; req->out_emissive_color[2] = 0.3f; }
+    return 1;
+}
 
 int ltrx_SetDevice(ltr_Scene *scene, int cuda_device) { scene->device = cuda_device; return 1; }
 

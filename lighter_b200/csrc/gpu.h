@@ -142,6 +142,26 @@ int ltrgpu_download_lumels(ltrgpu_Ctx *ctx, float *pos3, float *nrm3, uint32_t *
 /* stage: radiosity.  diffuse3 / emissive3: per global lumel material from the host callback, or
  * NULL for (1,1,1) / no extra emission on mesh lumels (probes always diffuse 0, area 0). */
 int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const float *emissive3, int bounces);
+/* The same with the materials asked for as late as possible: `fn` is called once, after link generation and right before
+ * the first bounce reads the materials (it may block: bake.cpp waits there for the sample_fn callbacks, which ran on a
+ * host thread while the GPU did direct light and link generation).  fn returns 0 and the two host arrays (or NULLs). */
+typedef int (*ltrgpu_materials_fn)(void *user, const float **diffuse3, const float **emissive3);
+int ltrgpu_radiosity_ex(ltrgpu_Ctx *ctx, ltrgpu_materials_fn fn, void *user, int bounces);
+
+/* sample_fn batching (ref: lighter.cpp:690-715 builds one ltr_SampleRequest per mesh lumel on the host).  The request
+ * fields are computed on the device -- normalised normal, tex1 = (texel + 0.5) / lightmap size, with the reference's float
+ * operations -- and come back in chunks on a SECOND stream, so a host thread can run the callbacks of chunk k while chunk
+ * k+1 is packed and copied and while the bake stream runs direct light and link generation.  Thread contract: _begin on
+ * the bake thread after ltrgpu_generate_lumels; _issue / _wait from ONE other thread. */
+typedef struct ltrgpu_SampleReq {      /* 48 bytes */
+    float pos[3], nrm[3];              /* lumel position, NORMALISED normal */
+    float tex0[2], tex1[2];
+    uint32_t part_id, inst;
+} ltrgpu_SampleReq;
+int ltrgpu_sample_requests_begin(ltrgpu_Ctx *ctx);
+int ltrgpu_sample_requests_issue(ltrgpu_Ctx *ctx, uint64_t first, uint32_t count, ltrgpu_SampleReq *host_pinned, int slot /* 0 or 1 */);
+int ltrgpu_sample_requests_wait(ltrgpu_Ctx *ctx, int slot);
+const char *ltrgpu_aux_error(ltrgpu_Ctx *ctx);        /* error text of the three calls above when made from the material thread */
 
 /* stage: ambient occlusion; randoff has one value per lumel OF THIS SHARD (host rand() replay, sliced by the caller) */
 int ltrgpu_ambient_occlusion(ltrgpu_Ctx *ctx, const float *randoff);

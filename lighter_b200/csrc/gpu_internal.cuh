@@ -113,6 +113,14 @@ struct ltrgpu_Ctx {
     uint32_t *h_out_w = nullptr, *h_out_h = nullptr;
     float *d_out = nullptr;                   /* output images after optional ds2x */
 
+    /* ---- sample_fn batching (second stream; touched by the material thread only, see gpu.h) ---- */
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_lumels = nullptr, ev_req[2] = { nullptr, nullptr };
+    ltrgpu_SampleReq *d_req[2] = { nullptr, nullptr };
+    uint32_t req_cap[2] = { 0, 0 };
+    char aux_err[256] = {0};
+    unsigned long long aux_d2h_bytes = 0, aux_launches = 0;   /* added to the bake's counters by ltrgpu_get_counters */
+
     /* ---- counters ---- */
     unsigned long long *d_counters = nullptr; /* see CNT_* */
     ltrgpu_Counters host_counters;

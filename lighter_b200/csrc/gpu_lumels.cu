@@ -689,6 +689,80 @@ extern "C" int ltrgpu_generate_lumels(ltrgpu_Ctx *ctx, uint64_t *inst_lumel_off)
     return 0;
 }
 
+/* one ltr_SampleRequest's worth of fields per mesh lumel (ref: lighter.cpp:690-706) */
+__global__ void sample_request_kernel(const float4 *__restrict__ lpos, const float4 *__restrict__ lnrm, const float4 *__restrict__ lrad,
+                                      const uint32_t *__restrict__ lloc, const uint32_t *__restrict__ linst, const ltrgpu_Inst *__restrict__ inst,
+                                      uint64_t first, uint32_t count, ltrgpu_SampleReq *__restrict__ out)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const uint64_t i = first + k;
+    const float4 P = lpos[i], R = lrad[i];
+    const V3 N = norm3(ld3(lnrm[i]));
+    const uint32_t in = linst[i], L = lloc[i];
+    const uint32_t w = inst[in].lm_w, h = inst[in].lm_h;
+    const int lx = (int)(L % w), ly = (int)(L / w);
+    ltrgpu_SampleReq q;
+    q.pos[0] = P.x; q.pos[1] = P.y; q.pos[2] = P.z;
+    q.nrm[0] = N.x; q.nrm[1] = N.y; q.nrm[2] = N.z;
+    q.tex0[0] = R.x; q.tex0[1] = R.y;
+    q.tex1[0] = ((float)lx + 0.5f) / (float)w; q.tex1[1] = ((float)ly + 0.5f) / (float)h;
+    q.part_id = (uint32_t)R.z; q.inst = in;
+    out[k] = q;
+}
+
+#define AUX_TRY(ctx, call)                                                                         \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            snprintf((ctx)->aux_err, sizeof((ctx)->aux_err), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return 1;                                                                              \
+        }                                                                                          \
+    } while (0)
+
+extern "C" int ltrgpu_sample_requests_begin(ltrgpu_Ctx *ctx)
+{
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->aux_stream) {
+        CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_lumels, cudaEventDisableTiming));
+        for (int b = 0; b < 2; ++b) CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_req[b], cudaEventDisableTiming));
+    }
+    /* the second stream may read the lumel arrays once everything queued on the bake stream so far has run */
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_lumels, ctx->stream));
+    CU_TRY(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_lumels, 0));
+    ctx->aux_err[0] = 0;
+    return 0;
+}
+
+extern "C" int ltrgpu_sample_requests_issue(ltrgpu_Ctx *ctx, uint64_t first, uint32_t count, ltrgpu_SampleReq *host_pinned, int slot)
+{
+    AUX_TRY(ctx, cudaSetDevice(ctx->device));             /* the calling thread is not the bake thread */
+    if (!count) return 0;
+    if (first + count > ctx->n_lumels || (slot != 0 && slot != 1)) { snprintf(ctx->aux_err, sizeof(ctx->aux_err), "sample request range out of bounds"); return 1; }
+    if (ctx->req_cap[slot] < count) {
+        if (ctx->d_req[slot]) lb_free(ctx->d_req[slot]);
+        ctx->d_req[slot] = nullptr; ctx->req_cap[slot] = 0;
+        AUX_TRY(ctx, lb_malloc(&ctx->d_req[slot], (size_t)count * sizeof(ltrgpu_SampleReq)));
+        ctx->req_cap[slot] = count;
+    }
+    sample_request_kernel<<<grid_for(count, 256), 256, 0, ctx->aux_stream>>>(ctx->d_lpos, ctx->d_lnrm, ctx->d_lrad, ctx->d_lloc, ctx->d_linst, ctx->d_inst,
+                                                                               first, count, ctx->d_req[slot]);
+    AUX_TRY(ctx, cudaGetLastError());
+    AUX_TRY(ctx, cudaMemcpyAsync(host_pinned, ctx->d_req[slot], (size_t)count * sizeof(ltrgpu_SampleReq), cudaMemcpyDeviceToHost, ctx->aux_stream));
+    AUX_TRY(ctx, cudaEventRecord(ctx->ev_req[slot], ctx->aux_stream));
+    ctx->aux_launches += 1; ctx->aux_d2h_bytes += (unsigned long long)count * sizeof(ltrgpu_SampleReq);
+    return 0;
+}
+
+extern "C" int ltrgpu_sample_requests_wait(ltrgpu_Ctx *ctx, int slot)
+{
+    AUX_TRY(ctx, cudaEventSynchronize(ctx->ev_req[slot]));
+    return 0;
+}
+
+extern "C" const char *ltrgpu_aux_error(ltrgpu_Ctx *ctx) { return ctx->aux_err; }
+
 extern "C" int ltrgpu_download_lumels(ltrgpu_Ctx *ctx, float *pos3, float *nrm3, uint32_t *loc, float *radinfo4, float *rgb3)
 {
     CU_TRY(ctx, cudaSetDevice(ctx->device));

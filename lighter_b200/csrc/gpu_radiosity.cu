@@ -821,8 +821,23 @@ static int rad_allgather(ltrgpu_Ctx *ctx, float4 *buf, uint64_t chunk_elems, con
     return 0;
 }
 
+struct RadHostMaterials { const float *diffuse3, *emissive3; };
+static int rad_host_materials(void *user, const float **d, const float **e)
+{
+    const RadHostMaterials *m = (const RadHostMaterials *)user;
+    *d = m->diffuse3; *e = m->emissive3;
+    return 0;
+}
+
 extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const float *emissive3, int bounces)
 {
+    RadHostMaterials m = { diffuse3, emissive3 };
+    return ltrgpu_radiosity_ex(ctx, rad_host_materials, &m, bounces);
+}
+
+extern "C" int ltrgpu_radiosity_ex(ltrgpu_Ctx *ctx, ltrgpu_materials_fn materials, void *materials_user, int bounces)
+{
+    const float *diffuse3 = nullptr, *emissive3 = nullptr;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const uint64_t n = ctx->n_lumels;
@@ -1138,6 +1153,7 @@ extern "C" int ltrgpu_radiosity(ltrgpu_Ctx *ctx, const float *diffuse3, const fl
         /* ---- bounces ---- */
         RAD_TRY(dev_alloc(ctx, &diff, n_pad)); RAD_TRY(dev_alloc(ctx, &total, n_pad)); RAD_TRY(dev_alloc(ctx, &out, n_pad));
         RAD_TRY(dev_alloc(ctx, &Es, n_pad)); RAD_TRY(dev_alloc(ctx, &Eo, n + LB_PAD));
+        if (materials && materials(materials_user, &diffuse3, &emissive3)) { snprintf(ctx->err, sizeof(ctx->err), "material callbacks failed"); rc = 1; goto done; }
         if (diffuse3) { RAD_TRY(dev_upload(ctx, &d_diffuse, diffuse3, n * 3)); RAD_TRY(dev_upload(ctx, &d_emissive, emissive3, n * 3)); }
         rad_init_kernel<<<grid_for(n_rows, 256), 256, 0, st>>>(lrgb_full, ctx->d_lrad, d_diffuse, d_emissive, ctx->d_rad_sidx, ctx->n_probes, n, k0, k1, diff, total, out);
         RAD_LAUNCHED();

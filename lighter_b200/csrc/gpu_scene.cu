@@ -296,6 +296,9 @@ extern "C" void ltrgpu_destroy(ltrgpu_Ctx *ctx)
     if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
     if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
     for (int b = 0; b < 2; ++b) { ltrgpu_host_free(ctx->stage_buf[b]); if (ctx->stage_ev[b]) cudaEventDestroy(ctx->stage_ev[b]); }
+    for (int b = 0; b < 2; ++b) { if (ctx->d_req[b]) lb_free(ctx->d_req[b]); if (ctx->ev_req[b]) cudaEventDestroy(ctx->ev_req[b]); }
+    if (ctx->ev_lumels) cudaEventDestroy(ctx->ev_lumels);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     /* cached device blocks stay in the pool for the next bake of this process (ltrgpu_release_memory drops them) */
     delete ctx;
@@ -523,6 +526,8 @@ extern "C" int ltrgpu_get_counters(ltrgpu_Ctx *ctx, ltrgpu_Counters *out)
     CU_TRY(ctx, cudaMemcpyAsync(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ltrgpu_Counters &h = ctx->host_counters;
+    h.kernel_launches += ctx->aux_launches; h.d2h_bytes += ctx->aux_d2h_bytes;     /* sample_fn batching (second stream; its thread has been joined by now) */
+    ctx->aux_launches = ctx->aux_d2h_bytes = 0;
     h.marches = c[CNT_MARCHES]; h.distance_queries = c[CNT_DIST_QUERIES]; h.ao_segments = c[CNT_AO_SEGMENTS];
     h.correction_rays = c[CNT_CORR_RAYS]; h.rad_pairs = c[CNT_RAD_PAIRS]; h.rad_segments = c[CNT_RAD_SEGMENTS];
     h.rad_links = c[CNT_RAD_LINKS]; h.node_visits = c[CNT_NODE_VISITS]; h.tri_tests = c[CNT_TRI_TESTS];

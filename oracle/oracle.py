@@ -51,6 +51,8 @@ class Oracle:
         L.o_ao_lumel.argtypes = [fp, C.c_int, fp, fp, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, fp, fp]
         L.o_rad_links.restype = C.c_long
         L.o_rad_links.argtypes = [fp, C.c_int, fp, fp, C.c_int, C.c_long, up, up, fp, C.POINTER(C.c_long), C.POINTER(C.c_long)]
+        L.o_rad_row.restype = C.c_long
+        L.o_rad_row.argtypes = [fp, C.c_int, fp, fp, fp, fp, C.c_int, C.c_int, C.POINTER(C.c_uint8), fp, C.POINTER(C.c_long)]
         L.o_rad_bounce.argtypes = [up, up, fp, C.c_long, C.c_int, fp, fp, fp, C.c_int, fp]
         L.o_scatter_dilate.argtypes = [fp, up, C.c_int, C.c_int, C.c_int, fp]
         L.o_gauss_kernel.argtypes = [fp, C.c_int, C.c_float]
@@ -145,6 +147,16 @@ class Oracle:
                                C.byref(pt), C.byref(sg))
         assert n <= cap
         return li[:n], lj[:n], lf[:n], pt.value, sg.value
+
+    def rad_row(self, tris, self_pos, self_nrm, pos, nrm, rank_of_self):
+        """One row of the link double loop (lighter.cpp:728-760): lumel `self` against the candidates pos/nrm (ascending global
+        order, self excluded; rank_of_self = how many of them have a lower global index).  Returns (linked mask, factors, segments)."""
+        tris, pos, nrm = _c(tris), _c(pos), _c(nrm)
+        sp, sn = _c(self_pos), _c(self_nrm)
+        linked, fac, sg = np.zeros(len(pos), np.uint8), np.zeros(len(pos), np.float32), C.c_long()
+        self.L.o_rad_row(_f(tris), len(tris), _f(sp), _f(sn), _f(pos), _f(nrm), len(pos), int(rank_of_self),
+                         linked.ctypes.data_as(C.POINTER(C.c_uint8)), _f(fac), C.byref(sg))
+        return linked.astype(bool), fac, sg.value
 
     def rad_bounce(self, li, lj, lf, diffuse, emit, area, bounces):
         li, lj, lf = _c(li, np.uint32), _c(lj, np.uint32), _c(lf)

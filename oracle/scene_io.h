@@ -20,6 +20,7 @@
 #pragma once
 #include <stdio.h>
 #include <stdlib.h>
+#include <math.h>
 #include <string.h>
 #include <stdint.h>
 #include <string>
@@ -141,6 +142,20 @@ static LTRBOOL redwall_sample_fn(ltr_Config *, ltr_SampleRequest *req)
     return 1;
 }
 
+/* material hook for cfg.sample_fn_kind == 2: a position / normal / part dependent rule for the synthetic workloads (4-unit
+ * checker of two albedos, downward-facing surfaces glow, every 64th call is declined) -- the same rule the library exports as
+ * ltrx_SampleFnChecker so that large bakes can be timed with a native callback; stated twice on purpose (the oracle links
+ * nothing of the product). */
+static LTRBOOL checker_sample_fn(ltr_Config *, ltr_SampleRequest *req)
+{
+    const int s = (int)floorf(req->position[0] * 0.25f) + (int)floorf(req->position[1] * 0.25f);
+    if (((s ^ (int)req->part_id) & 63) == 63) return 0;
+    if (s & 1) { req->out_diffuse_color[0] = 0.5f; req->out_diffuse_color[1] = 0.05f; req->out_diffuse_color[2] = 0.02f; }
+    else { req->out_diffuse_color[0] = 0.7f; req->out_diffuse_color[1] = 0.7f * req->tex1u; req->out_diffuse_color[2] = 0.6f; }
+    if (req->normal[2] < -0.5f) { req->out_emissive_color[0] = 0.1f; req->out_emissive_color[1] = 0.1f; req->out_emissive_color[2] = 0.3f; }
+    return 1;
+}
+
 /* Feed the scene through the public API.  `threads` <= 0 keeps the library default. */
 static ltr_Scene *build(SceneFile &S, int threads)
 {
@@ -157,7 +172,7 @@ static ltr_Scene *build(SceneFile &S, int threads)
     memcpy(cfg.clear_color, c.clear_color, 12);
     memcpy(cfg.ambient_color, c.ambient_color, 12);
     cfg.bounce_count = c.bounce_count;
-    cfg.sample_fn = c.sample_fn_kind == 1 ? redwall_sample_fn : NULL;
+    cfg.sample_fn = c.sample_fn_kind == 1 ? redwall_sample_fn : c.sample_fn_kind == 2 ? checker_sample_fn : NULL;
     cfg.ao_distance = c.ao_distance;
     cfg.ao_multiplier = c.ao_multiplier;
     cfg.ao_falloff = c.ao_falloff;

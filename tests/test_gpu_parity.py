@@ -296,6 +296,9 @@ def _variant(name):
         sc.lights = []
     if "+normalmap" in name:
         sc.cfg["generate_normalmap_data"] = 1
+    if "+checker" in name:
+        sc.cfg["sample_fn_kind"] = 2         # native position / normal / part dependent material callback (both sides state the same rule)
+        sc.cfg["bounce_count"] = max(sc.cfg["bounce_count"], 2)
     if "+noshadowstep" in name:
         sc.instances[3].shadow = 0          # corner: the step keeps its tree (it still pushes samples) but leaves the scene BVH
     return sc
@@ -303,7 +306,8 @@ def _variant(name):
 
 @pytest.mark.parametrize("name", ["mesh1+ds2x+blur", "mesh1+aoneg+ambient+probes", "rad1+probes+ambient", "basic+power0",
                                   "mesh2+noshadowinst", "basic+probes", "config3_sibling", "config4_sibling", "corner", "corner+normalmap",
-                                  "corner+noshadowstep", "mesh2+nolights+ambient", "mesh1+nolights+normalmap+ambient"])
+                                  "corner+noshadowstep", "mesh2+nolights+ambient", "mesh1+nolights+normalmap+ambient",
+                                  "config4_sibling+checker", "rad1+checker+probes", "corner+checker"])
 def test_config_variants_against_live_reference(name):
     if not parity.have_reference():
         pytest.skip("oracle/_ref not on this box")
@@ -325,6 +329,49 @@ def test_config_variants_against_live_reference(name):
             assert bits_equal(a["pos"], b["pos"]), name
     if len(ref["probes"]):
         assert np.abs(out["probes"] - ref["probes"]).max() < 1e-6
+
+
+def test_sample_fn_requests_are_the_reference_requests():
+    """sample_fn batching (bake.cpp MaterialJob): the callback is called once per mesh lumel, in the reference's order, with the
+    reference's request fields.  A recording Python callback on both... the reference cannot host a Python callback, so the
+    fields are checked against the lumel dump of the same bake: position, normalised normal, tex0, tex1 = (texel + 0.5) / size,
+    part id, and the instance idents in order; and the declined calls (return 0) keep the default material."""
+    sc = scenes.scene_rad1()
+    seen = []
+
+    @api.SAMPLE_FN
+    def rec(cfg, req):
+        r = req.contents
+        seen.append((tuple(r.position), tuple(r.normal), r.tex0u, r.tex0v, r.tex1u, r.tex1v, r.part_id,
+                     api.C.string_at(r.inst_ident, r.inst_ident_size), api.C.string_at(r.mesh_ident, r.mesh_ident_size),
+                     tuple(r.out_diffuse_color), tuple(r.out_emissive_color)))
+        if len(seen) % 3 == 0:
+            return 0
+        r.out_diffuse_color[0] = 0.25
+        return 1
+
+    with api.BakeHandle(sc, debug=True) as h:
+        cfg = api.Config()
+        h.L.ltr_GetConfig(api.C.byref(cfg), h.h)
+        cfg.sample_fn = rec
+        h.L.ltr_SetConfig(h.h, api.C.byref(cfg))
+        h.run()
+        insts = [h.lumels(i) for i in range(1, len(sc.instances) + 1)]       # instance 0 is the probe container: never asked
+    n = sum(i["n"] for i in insts)
+    assert len(seen) == n and n > 2000
+    k = 0
+    for inst, idesc in zip(insts, sc.instances):
+        w, hgt = inst["width"], inst["height"]
+        for j in range(inst["n"]):
+            pos, nrm, t0u, t0v, t1u, t1v, part, iid, mid, dflt, emis = seen[k]
+            assert np.array_equal(np.float32(pos), inst["pos"][j])
+            nn = inst["nrm"][j].astype(np.float32)
+            assert np.allclose(np.float32(nrm), nn / np.linalg.norm(nn), atol=2e-7)
+            assert (np.float32(t0u), np.float32(t0v)) == (inst["radinfo"][j][0], inst["radinfo"][j][1])
+            lx, ly = int(inst["loc"][j]) % w, int(inst["loc"][j]) // w
+            assert np.float32(t1u) == (np.float32(lx) + np.float32(0.5)) / np.float32(w) and np.float32(t1v) == (np.float32(ly) + np.float32(0.5)) / np.float32(hgt)
+            assert part == int(inst["radinfo"][j][2]) and iid == idesc.ident.encode() and dflt == (1.0, 1.0, 1.0) and emis == (0.0, 0.0, 0.0)
+            k += 1
 
 
 def test_lumel_classification_does_not_change_any_position(monkeypatch):
