@@ -28,7 +28,8 @@ struct RefTree {
     std::vector<RefNode> nodes;
     std::vector<int32_t> items;
 
-    void build(const Box3 *boxes, size_t count);
+    /* threads > 1: the halves of big nodes are built concurrently (same bytes as the serial build; reftree.cpp) */
+    void build(const Box3 *boxes, size_t count, int threads = 1);
 
     /* box query in pre-order (node items, first child, second child); calls f(ids,count) */
     template <class F> void query(V3 qlo, V3 qhi, F &f, int32_t node = 0) const

@@ -84,13 +84,26 @@ def test_mesh_import_counts():
     assert sc.triangle_count() == 246 + 2048
 
 
-def test_reference_order_tree_equals_reference_dump(refprims):
+@pytest.mark.parametrize("threads,fork_min", [(1, 0), (4, 8), (3, 300)])
+def test_reference_order_tree_equals_reference_dump(refprims, monkeypatch, threads, fork_min):
+    """threads > 1: the halves of big nodes are built by different threads and spliced (reftree.cpp); the bytes must still be
+    the reference's.  Inputs include a 200 x 150 grid whose triangle centres tie on every axis (the order among ties is
+    whatever std::sort leaves -- the reference's and ours must leave the same)."""
     import ctypes as C
+    if threads > 1:
+        monkeypatch.setenv("LTR_REFTREE_THREADS", str(threads))
+        monkeypatch.setenv("LTR_REFTREE_FORK_MIN", str(fork_min))
     rng = np.random.default_rng(3)
-    for n in (0, 1, 4, 5, 33, 700, 6000):
+    for n in (0, 1, 4, 5, 33, 700, 6000, 60000):
         tris = (rng.uniform(-5, 5, (n, 1, 3)) + rng.uniform(-0.6, 0.6, (n, 3, 3))).astype(np.float32).reshape(n, 9)
         if n >= 33:                                   # big triangles that must stay in inner nodes
             tris[::11] = (tris[::11].reshape(-1, 3, 3) * np.float32(6)).reshape(-1, 9)
+        if n == 60000:                                # regular grid: many equal keys
+            gx, gy = np.meshgrid(np.arange(200, dtype=np.float32), np.arange(150, dtype=np.float32), indexing="ij")
+            o = np.stack([gx.ravel(), gy.ravel(), np.zeros(gx.size, np.float32)], 1) * np.float32(0.25)
+            e = np.float32(0.25)
+            a = np.concatenate([o, o + [e, 0, 0], o + [e, e, 0]], 1); b = np.concatenate([o, o + [e, e, 0], o + [0, e, 0]], 1)
+            tris = np.concatenate([a, b]).astype(np.float32)
         nodes, items = api.test_reftree(tris)
         h = refprims.L.refp_tritree_create(tris.ctypes.data_as(C.POINTER(C.c_float)), n)
         assert refprims.L.refp_tritree_tri_count(h) == n
