@@ -151,9 +151,13 @@ LB_HD void shadow_sample_segment(unsigned type, V3 Lpos, float range, V3 smp, V3
     to = Lpos + rt * smp.x + up * smp.y;
 }
 
+/* USEFUL = true: the caller guarantees !near_zero3(T.n) -- every triangle of the scene BVH: the collision data only takes
+ * triangles that pass exactly this test on exactly this cross product (lighter.cpp:349-384 CheckIsUseful; bake.cpp
+ * for_useful_tris) -- so the per-test check is dead there. */
+template <bool USEFUL = false>
 LB_HD float seg_tri_prepared(V3 l1, V3 dir /* = l2 - l1 */, const RayTri &T)
 {
-    if (near_zero3(T.n)) return LB_NO_HIT;
+    if (!USEFUL && near_zero3(T.n)) return LB_NO_HIT;
     V3 w0 = l1 - T.p1;
     float a = -dot3(T.n, w0);
     float b = dot3(T.n, dir);

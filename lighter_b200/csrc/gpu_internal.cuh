@@ -226,9 +226,9 @@ __device__ __forceinline__ void load_prepared(const PreparedTri *src, PreparedTr
  * that h < 0.001, lighter.cpp:200-201).  Pruning is conservative: a sub-tree is skipped only when
  * its box is farther than the best distance so far.
  */
-template <int FLUSH = 3>
+template <int FLUSH = 3, bool HINT = false>
 __device__ __forceinline__ float bvh_distance(const BvhNode *__restrict__ nodes, const PreparedTri *__restrict__ tris,
-                                              V3 p, float radius, float stop_below, TravStats &ts)
+                                              V3 p, float radius, float stop_below, TravStats &ts, int *hint = nullptr)
 {
     /* Two-phase walk: the node loop (nearer child first, sub-trees farther than the best distance so far pruned) only
      * QUEUES the triangles of the leaves it reaches; once FLUSH are pending, or the walk is over, they are evaluated
@@ -243,7 +243,33 @@ __device__ __forceinline__ float bvh_distance(const BvhNode *__restrict__ nodes,
     float tqd[TQ];
     int sp = 0, nq = 0;
     float best = radius;
-    float best2 = best * best * 1.000001f;
+    /* Pruning bound.  The reference's point/triangle distance (geom.h, lighter_math.cpp:875-913) subtracts dot products of
+     * world coordinates, so its value carries an ABSOLUTE rounding error that grows with the coordinates (~1e-6 x |p|): two
+     * triangles sharing the nearest edge report distances a few ulps apart and the reference, which looks at both, keeps
+     * the smaller.  A box is therefore skipped only when it is farther than best + slack, slack = 1e-5 x (1 + |p|_inf) --
+     * ten times that error (a relative slack on the square, the round-1 form, let the warm-started walk keep 2 of
+     * 69.8 M config-4 factors one ulp above the brute-force minimum: profiles/r02_ab_runs.md). */
+    const float slack = 1e-5f * (1.0f + fmaxf(fmaxf(fabsf(p.x), fabsf(p.y)), fabsf(p.z)));
+#define LB_PRUNE2(B) (((B) + slack) * ((B) + slack))
+    float best2 = LB_PRUNE2(best);
+    /* HINT (the shadow march): *hint is the triangle that was nearest at the previous step of the same march (-1: none).
+     * It is evaluated first, so the walk starts with the bound it usually ends with and only visits what is nearer than
+     * that -- the minimum over the triangles within `radius` does not depend on the order they are looked at, so the
+     * result is the same float.  On return *hint is the nearest triangle found (-1 when nothing is within radius). */
+    int hint_in = -1, best_slot = -1;
+    if (HINT) {
+        hint_in = *hint;
+        if (hint_in >= 0) {
+            PreparedTri T;
+            load_prepared(tris + hint_in, T);
+            ts.tris++;
+            const float d = point_tri_distance_prepared(p, T);
+            if (d < best) {
+                best = d; best2 = LB_PRUNE2(best); best_slot = hint_in;
+                if (best < stop_below) return best;
+            }
+        }
+    }
     int node = 0;
     for (;;) {
         while (node >= 0) {
@@ -278,22 +304,26 @@ __device__ __forceinline__ float bvh_distance(const BvhNode *__restrict__ nodes,
         while (nq > 0) {
             --nq;
             if (tqd[nq] > best2) continue;               /* the best distance has improved since this leaf was queued */
+            if (HINT && tq[nq] == hint_in) continue;     /* evaluated before the walk */
             PreparedTri T;
             load_prepared(tris + tq[nq], T);
             ts.tris++;
             float d = point_tri_distance_prepared(p, T);
             if (d < best) {
                 best = d;
-                best2 = best * best * 1.000001f;
+                best2 = LB_PRUNE2(best);
+                if (HINT) best_slot = tq[nq];
                 if (best < stop_below) return best;
             }
         }
         if (node < 0) {
             /* the stack may still hold sub-trees that were skipped at pop time with an older bound: they stay skipped
              * (the bound only shrinks), so an empty `node` with nothing pending means the walk is complete */
+            if (HINT) *hint = best_slot;
             return best;
         }
     }
+#undef LB_PRUNE2
 }
 
 /*
@@ -314,8 +344,12 @@ __device__ __forceinline__ float march_shadow(const BvhNode *__restrict__ bvh, c
     V3 rd = norm3(to - from);
     float maxt = len3(to - from);
     float res = 1.0f;
+#ifndef LB_MARCH_HINT
+#define LB_MARCH_HINT 1          /* warm start of every distance query with the previous step's nearest triangle (bvh_distance HINT) */
+#endif
+    int hint = -1;
     for (float t = 0.001f; t < maxt;) {
-        float h = bvh_distance(bvh, tris, from + rd * t, 2.0f, 0.001f, ts);
+        float h = bvh_distance<3, LB_MARCH_HINT != 0>(bvh, tris, from + rd * t, 2.0f, 0.001f, ts, &hint);
         ++queries;
         if (h < 0.001f) return 0.0f;
         res = fminr(res, h / fminr(t * k, 2.0f));
@@ -583,7 +617,7 @@ __device__ __forceinline__ bool bvh4_anyhit_core(const Bvh4Node *__restrict__ no
                 RayTri T;
                 load_raytri(tp, T);
                 ts.tris++;
-                if (seg_tri_prepared(l1, d, T) < 1.0f) return true;
+                if (seg_tri_prepared<true>(l1, d, T) < 1.0f) return true;     /* scene-BVH triangles are "useful" by construction */
             }
         }
         if (node < 0) return false;
