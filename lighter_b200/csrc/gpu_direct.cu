@@ -19,6 +19,8 @@
  */
 #include "gpu_internal.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <stdlib.h>
 
 #include <vector>
@@ -60,6 +62,23 @@ __device__ __forceinline__ ShadeTerms shade_terms(const ltrgpu_Light &L, V3 SP, 
     return o;
 }
 
+/* Work-list order of the march (LTR_MARCH_ORDER, default on).  Lumels are stored texel row by texel row, so 32 consecutive
+ * ones are a LINE (3 units long on config 4, eight BVH leaves wide); the 32 marches of a warp walk the tree side by side,
+ * and what they share of it decides how many lanes an instruction serves.  The listing pass therefore visits the rank's
+ * lumels along a Morton curve over 0.25-unit cells (coordinates wrap every 256 units: no scene bounds needed, a wrap only
+ * lets two far cells share a key), so a warp's lumels form a compact patch.  Only the ORDER of the work list changes;
+ * every (lumel, light) march and its slot in the factor table are the same. */
+__global__ void march_order_kernel(const float4 *__restrict__ lpos, uint64_t first, uint32_t n, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = lpos[first + i];
+    auto cell = [](float v) { return (uint32_t)((int)floorf(v * 4.0f)) & 1023u; };
+    auto spread = [](uint32_t x) { x &= 0x3ffu; x = (x | (x << 16)) & 0x30000ffu; x = (x | (x << 8)) & 0x300f00fu; x = (x | (x << 4)) & 0x30c30c3u; x = (x | (x << 2)) & 0x9249249u; return x; };
+    keys[i] = spread(cell(p.x)) | (spread(cell(p.y)) << 1) | (spread(cell(p.z)) << 2);
+    vals[i] = i;
+}
+
 /* cut the blocks into `world` contiguous runs of (nearly) equal weight; cuts[r] = first block of rank r, cuts[world] = nb */
 __global__ void direct_cuts_kernel(const uint32_t *__restrict__ block_w, uint32_t nb, uint32_t world, uint32_t *__restrict__ cuts)
 {
@@ -84,7 +103,8 @@ __global__ void direct_classify_kernel(const ltrgpu_Light *__restrict__ lights, 
                                        const float4 *__restrict__ lpos, const float4 *__restrict__ lnrm, const uint32_t *__restrict__ linst,
                                        uint64_t sh_begin, uint32_t n_local,
                                        uint32_t *__restrict__ block_w /* weight pass: per 1024-lumel block, or NULL */,
-                                       uint2 *__restrict__ active, uint32_t *active_count)
+                                       uint2 *__restrict__ active, uint32_t *active_count,
+                                       const uint32_t *__restrict__ order = nullptr /* listing pass: thread k looks at local lumel order[k] (march_order_kernel) */)
 {
     /* (sh_begin, n_local) is the lumel range this launch looks at.  With several GPUs a first pass over ALL lumels and ALL
      * lights (block_w != NULL) sums an integer cost estimate of the marches per 1024-lumel block -- identical on every rank --
@@ -93,11 +113,12 @@ __global__ void direct_classify_kernel(const ltrgpu_Light *__restrict__ lights, 
      * was measured 30 % slower per march: every rank then streams the whole 200 MB scene through its L2); equal cost,
      * because march work is concentrated around the lights (equal lumel counts: 17 ms on the slowest of 8 ranks against a
      * 6 ms mean). */
-    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t k_thread = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t li = (order && k_thread < n_local) ? order[k_thread] : k_thread;
     const uint32_t l = l0 + blockIdx.y;
     bool want = false;
     const uint32_t blk = (uint32_t)((sh_begin + li) >> 10);
-    if (li < n_local && l < l1) {
+    if (k_thread < n_local && l < l1) {
         const ltrgpu_Light L = lights[l];
         const uint64_t g = sh_begin + li;
         if (light_is_supported(L.type) && light_inst[(size_t)l * n_inst + linst[g]]) {
@@ -388,6 +409,28 @@ extern "C" int ltrgpu_direct_light(ltrgpu_Ctx *ctx)
     if (sampled && dev_alloc(ctx, &ctx->d_smask, (size_t)chunk * tab_n)) return 1;
     ctx->fvis_tab_base = tab_base; ctx->fvis_tab_n = tab_n;
 
+    /* the march's work-list order (march_order_kernel) */
+    uint32_t *d_order = nullptr;
+    {
+        const char *e = getenv("LTR_MARCH_ORDER");
+        if (tab_n > 1024 && ctx->n_lights && !(e && e[0] == '0')) {
+            uint32_t *k0 = nullptr, *k1 = nullptr, *v0 = nullptr, *v1 = nullptr;
+            void *tmp = nullptr;
+            size_t tmp_bytes = 0;
+            if (dev_alloc(ctx, &k0, tab_n) || dev_alloc(ctx, &k1, tab_n) || dev_alloc(ctx, &v0, tab_n) || dev_alloc(ctx, &v1, tab_n)) return 1;
+            march_order_kernel<<<grid_for(tab_n, 256), 256, 0, st>>>(ctx->d_lpos, tab_base, tab_n, k0, v0);
+            CU_LAUNCH_CHECK(ctx);
+            cub::DoubleBuffer<uint32_t> kb(k0, k1), vb(v0, v1);
+            CU_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb, vb, (int)tab_n, 0, 30, st));
+            CU_TRY(ctx, lb_malloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+            CU_TRY(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, kb, vb, (int)tab_n, 0, 30, st));
+            ctx->host_counters.kernel_launches += 4;
+            d_order = vb.Current();
+            CU_TRY(ctx, cudaStreamSynchronize(st));
+            lb_free(tmp); lb_free(k0); lb_free(k1); lb_free(d_order == v0 ? v1 : v0);
+        }
+    }
+
     std::vector<cudaEvent_t> mev;
     for (uint32_t l0 = 0; tab_n && l0 < ctx->n_lights; l0 += chunk) {
         uint32_t l1 = l0 + chunk < ctx->n_lights ? l0 + chunk : ctx->n_lights;
@@ -395,7 +438,7 @@ extern "C" int ltrgpu_direct_light(ltrgpu_Ctx *ctx)
         CU_TRY(ctx, cudaMemsetAsync(ctx->d_fvis, 0, (size_t)(l1 - l0) * tab_n * 4, st));
         dim3 grid(grid_for(tab_n, 256), l1 - l0);
         direct_classify_kernel<<<grid, 256, 0, st>>>(ctx->d_lights, l0, l1, ctx->d_light_inst, ctx->n_inst, ctx->d_lpos, ctx->d_lnrm,
-                                                     ctx->d_linst, tab_base, tab_n, nullptr, ctx->d_active, ctx->d_active_count);
+                                                     ctx->d_linst, tab_base, tab_n, nullptr, ctx->d_active, ctx->d_active_count, d_order);
         CU_LAUNCH_CHECK(ctx);
         cudaEvent_t m0, m1;
         CU_TRY(ctx, cudaEventCreate(&m0)); mev.push_back(m0);
@@ -423,6 +466,7 @@ extern "C" int ltrgpu_direct_light(ltrgpu_Ctx *ctx)
                                                                       ctx->d_lnrm, ctx->d_linst, tab_base, tab_n, ctx->d_fvis, tab_base, tab_n, ctx->d_lrgb);
         CU_LAUNCH_CHECK(ctx);
     }
+    if (d_order) { CU_TRY(ctx, cudaStreamSynchronize(st)); lb_free(d_order); d_order = nullptr; }      /* lb_free recycles at once: the listing passes must be done with it */
     if (ctx->params.normalmap) {
         /* also without any light: the reference then writes normalize(N * ambient brightness), focus 1 (lighter.cpp:977-1012) */
         if (dev_alloc(ctx, &ctx->d_lnmap, ctx->n_lumels + LB_PAD)) return 1;
