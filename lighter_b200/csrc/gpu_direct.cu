@@ -413,7 +413,7 @@ extern "C" int ltrgpu_direct_light(ltrgpu_Ctx *ctx)
     uint32_t *d_order = nullptr;
     {
         const char *e = getenv("LTR_MARCH_ORDER");
-        if (tab_n > 1024 && ctx->n_lights && !(e && e[0] == '0')) {
+        if (tab_n >= (1u << 18) && ctx->n_lights && !(e && e[0] == '0')) {
             uint32_t *k0 = nullptr, *k1 = nullptr, *v0 = nullptr, *v1 = nullptr;
             void *tmp = nullptr;
             size_t tmp_bytes = 0;

@@ -983,12 +983,14 @@ extern "C" int ltrgpu_radiosity_ex(ltrgpu_Ctx *ctx, ltrgpu_materials_fn material
 
         /* ---- 2b-4. candidates and visibility, in batches of work items bounded by the candidate buffer ---- */
         RAD_TRY(dev_alloc(ctx, &d_cnt, 4));
-        /* candidate buffer: an eighth of the free HBM, between 16 Mi and 1 Gi records (12 B each) */
+        /* candidate buffer: a sixteenth of the device's TOTAL memory, between 16 Mi and 1 Gi records (12 B each).  Not of the
+         * FREE memory: blocks cached by lb_malloc count as used, so a size derived from it drifted from bake to bake, missed
+         * the cache every time it crossed a size class and paid a 12 GB cudaMalloc (~42 ms, seen as bake-time outliers). */
         unsigned long long cand_cap = 16ull << 20;
         {
             size_t free_b = 0, total_b = 0;
             if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-                unsigned long long want = (unsigned long long)(free_b / 8 / sizeof(RadCand));
+                unsigned long long want = (unsigned long long)(total_b / 16 / sizeof(RadCand));
                 if (want > cand_cap) cand_cap = want;
                 if (cand_cap > (1024ull << 20)) cand_cap = 1024ull << 20;
             }
