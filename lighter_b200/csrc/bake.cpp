@@ -366,11 +366,21 @@ void host_prepare(ltr_Scene *S, bool force_host_bvh = false)
     B.device_bvh = !force_host_bvh && !getenv("LTR_BVH_HOST") && nst > (size_t)leaf_max;
     B.scene_tris = nullptr; B.n_scene_tris = 0;
     std::thread bvh_thread;
+    int early_rc = 0;
     if (B.device_bvh) {
         B.bvh = SceneBvh();
         if (all_cast) { B.bvh_tris.clear(); B.scene_tris = B.rtree_tris.data(); }
         else { B.bvh_tris.swap(scene_compact); B.scene_tris = B.bvh_tris.data(); }
         B.n_scene_tris = nst;
+        /* every instance casts (the usual case): the scene BVH is built over the very array that is ready now, so the
+         * triangles go up at once (sharded: one collective, here on the bake thread) and the device builds the tree on its
+         * second stream while this host builds the reference-order trees below; upload() finds both done */
+        if (all_cast && B.gpu && !(getenv("LTR_BVH_LATE") && getenv("LTR_BVH_LATE")[0] == '1')) {      /* LTR_BVH_LATE=1: build during upload() instead (A/B) */
+            std::vector<uint64_t> sh;
+            if (world > 1) for (int r = 0; r <= world; ++r) sh.push_back(o_tri[B.inst_cut[r]]);
+            gpu_check(S, ltrgpu_upload_tris_early(B.gpu, B.rtree_tris.data(), (uint32_t)o_tri[ni], sh.empty() ? nullptr : sh.data()), "early triangle upload");
+            bvh_thread = std::thread([&B, &early_rc, leaf_max]() { early_rc = ltrgpu_build_bvh_early(B.gpu, leaf_max); });
+        }
     } else bvh_thread = std::thread([&]() {
         build_scene_bvh(scene_tris, nst, B.bvh, leaf_max, 0);
         /* triangles in BVH order */
@@ -453,6 +463,7 @@ void host_prepare(ltr_Scene *S, bool force_host_bvh = false)
     lap("concatenate + raster list");
     /* flat scene BVH over the shadow-casting triangles: built in the background since the world triangles were ready */
     if (bvh_thread.joinable()) bvh_thread.join();
+    if (early_rc) { Fail f; f.msg = std::string("early scene-BVH build: ") + ltrgpu_early_error(B.gpu); throw f; }
     lap("scene BVH (overlapped) + reorder");
     /* lights and the light -> instance table */
     const size_t nl = S->lights.size();

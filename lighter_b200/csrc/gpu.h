@@ -122,6 +122,16 @@ int ltrgpu_bvh_info(ltrgpu_Ctx *ctx, uint32_t *n_nodes, int *height, float *buil
 
 /* stage: lumel generation (raster -> ordered compaction -> concave-edge offset -> overlap correction).
  * inst_lumel_off receives n_inst+1 prefix offsets into the global lumel array (probes first). */
+/* Early start of the device-built scene BVH, so that it runs beside the host's reference-order tree builds instead of after
+ * them (bake.cpp host_prepare).  _tris_early: the reference-order triangle array goes up now (sharded: completed by a
+ * collective -- call it on the bake thread, at the same point on every rank).  _bvh_early: builds the scene BVH over those
+ * triangles on the context's SECOND stream and blocks until the build has been queued to its end; it contains no collective
+ * and may run on another host thread.  ltrgpu_upload_scene then skips both steps (it checks the triangle count) and makes
+ * the bake stream wait for the build. */
+int ltrgpu_upload_tris_early(ltrgpu_Ctx *ctx, const float *rtree_tris9, uint32_t n_rtree_tris, const uint64_t *shard_tris /* NULL or world + 1 prefix offsets */);
+int ltrgpu_build_bvh_early(ltrgpu_Ctx *ctx, int bvh_leaf_max);
+const char *ltrgpu_early_error(ltrgpu_Ctx *ctx);
+
 int ltrgpu_generate_lumels(ltrgpu_Ctx *ctx, uint64_t *inst_lumel_off);
 
 /* multi-GPU identity of this context and the all-gather hook; call before ltrgpu_generate_lumels */

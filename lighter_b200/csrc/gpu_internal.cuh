@@ -113,6 +113,13 @@ struct ltrgpu_Ctx {
     uint32_t *h_out_w = nullptr, *h_out_h = nullptr;
     float *d_out = nullptr;                   /* output images after optional ds2x */
 
+    /* ---- early scene-BVH build (second stream; ltrgpu_upload_tris_early / ltrgpu_build_bvh_early) ---- */
+    uint32_t early_tris = 0;                  /* > 0: d_rtree_tris already holds that many triangles of this scene */
+    bool early_bvh = false;                   /* the scene BVH over them has been built (d_bvh, d_bvh4, d_tri_orig, d_ptris, d_raytris) */
+    cudaEvent_t ev_early = nullptr;           /* end of that build on the second stream */
+    unsigned early_launches = 0;
+    char early_err[256] = {0};
+
     /* ---- sample_fn batching (second stream; touched by the material thread only, see gpu.h) ---- */
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_lumels = nullptr, ev_req[2] = { nullptr, nullptr };

@@ -723,11 +723,9 @@ __global__ void sample_request_kernel(const float4 *__restrict__ lpos, const flo
 extern "C" int ltrgpu_sample_requests_begin(ltrgpu_Ctx *ctx)
 {
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    if (!ctx->aux_stream) {
-        CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
-        CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_lumels, cudaEventDisableTiming));
-        for (int b = 0; b < 2; ++b) CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_req[b], cudaEventDisableTiming));
-    }
+    if (!ctx->aux_stream) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    if (!ctx->ev_lumels) CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_lumels, cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) if (!ctx->ev_req[b]) CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_req[b], cudaEventDisableTiming));
     /* the second stream may read the lumel arrays once everything queued on the bake stream so far has run */
     CU_TRY(ctx, cudaEventRecord(ctx->ev_lumels, ctx->stream));
     CU_TRY(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_lumels, 0));

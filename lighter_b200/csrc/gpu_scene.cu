@@ -298,6 +298,7 @@ extern "C" void ltrgpu_destroy(ltrgpu_Ctx *ctx)
     for (int b = 0; b < 2; ++b) { ltrgpu_host_free(ctx->stage_buf[b]); if (ctx->stage_ev[b]) cudaEventDestroy(ctx->stage_ev[b]); }
     for (int b = 0; b < 2; ++b) { if (ctx->d_req[b]) lb_free(ctx->d_req[b]); if (ctx->ev_req[b]) cudaEventDestroy(ctx->ev_req[b]); }
     if (ctx->ev_lumels) cudaEventDestroy(ctx->ev_lumels);
+    if (ctx->ev_early) cudaEventDestroy(ctx->ev_early);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     /* cached device blocks stay in the pool for the next bake of this process (ltrgpu_release_memory drops them) */
@@ -369,9 +370,67 @@ template <class T> static int upload_sharded(ltrgpu_Ctx *ctx, T **p, const T *ho
     return 0;
 }
 
+static int ensure_aux_stream(ltrgpu_Ctx *ctx)
+{
+    if (!ctx->aux_stream) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    if (!ctx->ev_early) CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_early, cudaEventDisableTiming));
+    return 0;
+}
+
+extern "C" int ltrgpu_upload_tris_early(ltrgpu_Ctx *ctx, const float *rtree_tris9, uint32_t n_rtree_tris, const uint64_t *shard_tris)
+{
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    ctx->early_tris = 0; ctx->early_bvh = false;
+    if (!n_rtree_tris) return 0;
+    if (ensure_aux_stream(ctx)) return 1;
+    if (upload_sharded(ctx, &ctx->d_rtree_tris, rtree_tris9, n_rtree_tris, 9, shard_tris)) return 1;
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));           /* the second stream reads them next */
+    ctx->early_tris = n_rtree_tris;
+    return 0;
+}
+
+extern "C" int ltrgpu_build_bvh_early(ltrgpu_Ctx *ctx, int bvh_leaf_max)
+{
+    /* errors go to early_err: the bake thread may be writing ctx->err at the same time */
+#define EARLY_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(ctx->early_err, sizeof(ctx->early_err), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return 1; } } while (0)
+    EARLY_TRY(cudaSetDevice(ctx->device));
+    ctx->early_err[0] = 0;
+    const uint32_t n = ctx->early_tris;
+    if (!n) { snprintf(ctx->early_err, sizeof(ctx->early_err), "early BVH build without triangles"); return 1; }
+    cudaStream_t st = ctx->aux_stream;
+    if (ctx->d_bvh) { lb_free(ctx->d_bvh); ctx->d_bvh = nullptr; }
+    if (ctx->d_bvh4) { lb_free(ctx->d_bvh4); ctx->d_bvh4 = nullptr; }
+    if (ctx->d_tri_orig) { lb_free(ctx->d_tri_orig); ctx->d_tri_orig = nullptr; }
+    if (ctx->d_ptris) { lb_free(ctx->d_ptris); ctx->d_ptris = nullptr; }
+    if (ctx->d_raytris) { lb_free(ctx->d_raytris); ctx->d_raytris = nullptr; }
+    EARLY_TRY(lb_malloc(&ctx->d_ptris, (size_t)n * sizeof(PreparedTri)));
+    EARLY_TRY(lb_malloc(&ctx->d_raytris, (size_t)n * sizeof(RayTri)));
+    LbDeviceBvh T;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;                    /* own timing events: ev_k0 / ev_k1 belong to the bake thread */
+    EARLY_TRY(cudaEventCreate(&e0)); EARLY_TRY(cudaEventCreate(&e1));
+    EARLY_TRY(cudaEventRecord(e0, st));
+    if (lb_build_bvh_device(st, ctx->d_rtree_tris, n, bvh_leaf_max, ctx->num_sms, &T, ctx->early_err, sizeof(ctx->early_err))) return 1;
+    EARLY_TRY(cudaEventRecord(e1, st));
+    ctx->d_bvh = T.nodes; ctx->d_bvh4 = T.nodes4; ctx->d_tri_orig = T.order;
+    ctx->n_bvh_nodes = T.n_nodes; ctx->bvh_height = T.height; ctx->n_bvh4_nodes = T.n_nodes4;
+    ctx->early_launches = T.launches + 1;
+    prepare_tris_kernel<<<grid_for(n, 256), 256, 0, st>>>(ctx->d_rtree_tris, ctx->d_tri_orig, n, ctx->d_ptris, ctx->d_raytris);
+    EARLY_TRY(cudaGetLastError());
+    EARLY_TRY(cudaEventRecord(ctx->ev_early, st));
+    EARLY_TRY(cudaEventSynchronize(e1));
+    EARLY_TRY(cudaEventElapsedTime(&ctx->bvh_build_ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    ctx->early_bvh = true;
+    return 0;
+#undef EARLY_TRY
+}
+
+extern "C" const char *ltrgpu_early_error(ltrgpu_Ctx *ctx) { return ctx->early_err; }
+
 extern "C" int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *d)
 {
     CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint32_t early_nodes = ctx->n_bvh_nodes;             /* set by ltrgpu_build_bvh_early, if it ran */
     ctx->params = d->params;
     ctx->n_inst = d->n_inst; ctx->n_verts = d->n_verts; ctx->n_rtris = d->n_rtris;
     ctx->n_rnodes = d->n_rnodes; ctx->n_ritems = d->n_ritems; ctx->n_rtree_tris = d->n_rtree_tris;
@@ -395,7 +454,8 @@ extern "C" int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *d)
     if (upload_sharded(ctx, &ctx->d_rtris, d->rtris, d->n_rtris, 1, d->shard_rtris)) return 1;
     if (upload_sharded(ctx, &ctx->d_rnodes, d->rnodes, d->n_rnodes, 1, d->shard_rnodes)) return 1;
     if (upload_sharded(ctx, &ctx->d_ritems, d->ritems, d->n_ritems, 1, d->shard_ritems)) return 1;
-    if (upload_sharded(ctx, &ctx->d_rtree_tris, d->rtree_tris9, d->n_rtree_tris, 9, d->shard_tris)) return 1;
+    const bool tris_early = ctx->early_tris && ctx->early_tris == d->n_rtree_tris;      /* already up (ltrgpu_upload_tris_early) */
+    if (!tris_early && upload_sharded(ctx, &ctx->d_rtree_tris, d->rtree_tris9, d->n_rtree_tris, 9, d->shard_tris)) return 1;
     if (dev_upload(ctx, &ctx->d_lights, d->lights, d->n_lights)) return 1;
     if (dev_upload(ctx, &ctx->d_light_inst, d->light_inst, (size_t)d->n_lights * d->n_inst)) return 1;
     if (dev_upload(ctx, &ctx->d_light_samples, d->light_samples4, d->n_light_samples)) return 1;
@@ -409,12 +469,20 @@ extern "C" int ltrgpu_upload_scene(ltrgpu_Ctx *ctx, const ltrgpu_SceneDesc *d)
     /* scene BVH + its triangles: raw triangles up, expanded on the device into the two prepared records, raw dropped */
     float *d_raw = nullptr;
     const bool raw_is_rtree = d->bvh == nullptr && d->tris9 == d->rtree_tris9 && d->n_tris == d->n_rtree_tris;
+    const bool bvh_early = tris_early && ctx->early_bvh && raw_is_rtree;                /* built beside the host pre-pass (ltrgpu_build_bvh_early) */
+    ctx->early_tris = 0; ctx->early_bvh = false;
     if (raw_is_rtree) d_raw = ctx->d_rtree_tris;
     else if (dev_upload(ctx, &d_raw, d->tris9, (size_t)d->n_tris * 9)) return 1;
-    if (dev_alloc(ctx, &ctx->d_ptris, d->n_tris)) return 1;
-    if (dev_alloc(ctx, &ctx->d_raytris, d->n_tris)) return 1;
-    ctx->bvh_build_ms = 0.f;
-    if (d->bvh) {
+    if (!bvh_early) {
+        if (dev_alloc(ctx, &ctx->d_ptris, d->n_tris)) return 1;
+        if (dev_alloc(ctx, &ctx->d_raytris, d->n_tris)) return 1;
+        ctx->bvh_build_ms = 0.f;
+    }
+    if (bvh_early) {
+        CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_early, 0));
+        ctx->host_counters.kernel_launches += ctx->early_launches;
+        ctx->n_bvh_nodes = early_nodes;
+    } else if (d->bvh) {
         if (dev_upload(ctx, &ctx->d_bvh, d->bvh, d->n_bvh_nodes)) return 1;
         if (dev_upload(ctx, &ctx->d_bvh4, d->bvh4, d->n_bvh4_nodes)) return 1;
         if (dev_upload(ctx, &ctx->d_tri_orig, d->tri_orig, d->n_tris)) return 1;
