@@ -741,14 +741,17 @@ void gpu_stages(ltr_Scene *S)
      * the direct-light and radiosity stages (7.8 M draws = ~0.1 s of host time otherwise exposed).
      * RAII: the thread is always joined, also when a later stage throws. */
     struct RandJob {
-        std::vector<float> v;
+        float *v = nullptr;                         /* page-locked, from the cache: no 31 MB of fresh page faults per bake, and the upload is a plain DMA */
         std::thread th;
-        ~RandJob() { if (th.joinable()) th.join(); }
+        ~RandJob() { if (th.joinable()) th.join(); ltrgpu_host_free(v); }
     } randjob;
     const bool user_code_before_ao = cfg.bounce_count && cfg.sample_fn;   /* a material callback might itself call rand(): keep the reference's order */
-    if (cfg.ao_distance) randjob.v.resize(n ? n : 1);
+    if (cfg.ao_distance) {
+        randjob.v = (float *)ltrgpu_host_alloc((n ? n : 1) * sizeof(float));
+        if (!randjob.v) { Fail f; f.msg = "out of host memory for the AO offsets"; throw f; }
+    }
     if (cfg.ao_distance && !user_code_before_ao) {
-        randjob.th = std::thread([&randjob, n]() { rand_fill(randjob.v.data(), n); });
+        randjob.th = std::thread([&randjob, n]() { rand_fill(randjob.v, n); });
     }
 
     t0 = now_s();
@@ -791,8 +794,8 @@ void gpu_stages(ltr_Scene *S)
         /* replay of the reference's rand() consumption: one randf() per lumel, instance by
          * instance (probe container first), lumel index ascending (lighter.cpp:819,1130-1135) */
         if (randjob.th.joinable()) randjob.th.join();
-        else rand_fill(randjob.v.data(), n);
-        gpu_check(S, ltrgpu_ambient_occlusion(B.gpu, randjob.v.data() + sb), "ambient occlusion");
+        else rand_fill(randjob.v, n);
+        gpu_check(S, ltrgpu_ambient_occlusion(B.gpu, randjob.v + sb), "ambient occlusion");
         S->completion.store(1.f);
     }
     S->stats.t_ao = now_s() - t0;
@@ -899,14 +902,19 @@ void bake_main(ltr_Scene *S)
     S->error.clear();
     S->failed_stage.clear();
     if (!S->bake) S->bake = new Bake;
+    const bool trace = getenv("LTR_TRACE") != nullptr;
+    double tc = 0, th = 0, tu = 0, tg = 0, tr = 0;
     guarded(S, [&]() {
-        connect(S);
-        host_prepare(S);
-        upload(S);
-        gpu_stages(S);
-        readback(S);
+        connect(S);      tc = now_s();
+        host_prepare(S); th = now_s();
+        upload(S);       tu = now_s();
+        gpu_stages(S);   tg = now_s();
+        readback(S);     tr = now_s();
     });
     S->stats.t_total = now_s() - t0;
+    if (trace && tr > 0)
+        fprintf(stderr, "[ltr host] bake thread: connect %.2f  host pre-pass %.2f  upload %.2f  gpu stages %.2f  read-back + counters %.2f  total %.2f ms\n",
+                (tc - t0) * 1e3, (th - tc) * 1e3, (tu - th) * 1e3, (tg - tu) * 1e3, (tr - tg) * 1e3, S->stats.t_total * 1e3);
     S->completion.store(1.f);
     S->stage.store(nullptr, std::memory_order_release);
 }

@@ -128,7 +128,13 @@ extern "C" void ltrgpu_host_free(void *p)
 int lb_upload_staged(ltrgpu_Ctx *ctx, void *dst, const void *src, size_t bytes)
 {
     const size_t CHUNK = (size_t)8 << 20;
-    if (bytes < ((size_t)1 << 20)) {
+    bool pinned = false;                                          /* page-locked source (ltrgpu_host_alloc, or the caller's own): one plain DMA */
+    if (bytes >= ((size_t)1 << 20)) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, src) == cudaSuccess) pinned = at.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+    }
+    if (pinned || bytes < ((size_t)1 << 20)) {
         CU_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
         return 0;
     }
