@@ -167,6 +167,22 @@ int nccl_gatherv_cb(void *user, void *buf, const uint64_t *off, void *stream)
     return rc;
 }
 
+/* personalised exchange (mirrored radiosity links go to the rank that owns their row): grouped ncclSend / ncclRecv */
+int nccl_alltoallv_cb(void *user, const void *send, const uint64_t *soff, void *recv, const uint64_t *roff, void *stream)
+{
+    Bake *B = (Bake *)user;
+    if (!B->nccl || !B->comm) return 1;
+    int rc = B->nccl->GroupStart();
+    for (int r = 0; rc == 0 && r < B->world; ++r) {
+        if (soff[r + 1] > soff[r]) rc = B->nccl->Send((const char *)send + soff[r], (size_t)(soff[r + 1] - soff[r]), /*ncclUint8*/ 1, r, B->comm, stream);
+        if (rc == 0 && roff[r + 1] > roff[r]) rc = B->nccl->Recv((char *)recv + roff[r], (size_t)(roff[r + 1] - roff[r]), /*ncclUint8*/ 1, r, B->comm, stream);
+    }
+    const int rc2 = B->nccl->GroupEnd();
+    if (rc == 0) rc = rc2;
+    if (rc != 0) fprintf(stderr, "lighter_b200: ncclSend/ncclRecv group failed: %s\n", B->nccl->GetErrorString(rc));
+    return rc;
+}
+
 struct Fail { std::string msg; };
 
 void gpu_check(ltr_Scene *S, int rc, const char *what)
@@ -564,6 +580,7 @@ void connect(ltr_Scene *S)
     B.world = S->world;
     gpu_check(S, ltrgpu_set_world(B.gpu, S->rank, S->world, S->world > 1 ? nccl_allgather_cb : nullptr, &B), "world");
     gpu_check(S, ltrgpu_set_gatherv(B.gpu, S->world > 1 ? nccl_gatherv_cb : nullptr), "world");
+    gpu_check(S, ltrgpu_set_alltoallv(B.gpu, S->world > 1 ? nccl_alltoallv_cb : nullptr), "world");
 }
 
 void upload(ltr_Scene *S)
@@ -718,6 +735,7 @@ void gpu_stages(ltr_Scene *S)
     gpu_check(S, ltrgpu_set_world(B.gpu, S->rank, S->world, S->world > 1 ? nccl_allgather_cb : nullptr, &B), "world");
     B.world = S->world;
     gpu_check(S, ltrgpu_set_gatherv(B.gpu, S->world > 1 ? nccl_gatherv_cb : nullptr), "world");
+    gpu_check(S, ltrgpu_set_alltoallv(B.gpu, S->world > 1 ? nccl_alltoallv_cb : nullptr), "world");
     gpu_check(S, ltrgpu_generate_lumels(B.gpu, B.lumel_off.data()), "lumel generation");
     const uint64_t n = B.lumel_off[ni];
     uint64_t sb = 0, se = n;

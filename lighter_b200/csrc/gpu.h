@@ -137,6 +137,10 @@ int ltrgpu_generate_lumels(ltrgpu_Ctx *ctx, uint64_t *inst_lumel_off);
 /* multi-GPU identity of this context and the all-gather hook; call before ltrgpu_generate_lumels */
 int ltrgpu_set_world(ltrgpu_Ctx *ctx, int rank, int world, ltrgpu_allgather_fn allgather, void *allgather_user);
 int ltrgpu_set_gatherv(ltrgpu_Ctx *ctx, ltrgpu_gatherv_fn gatherv);
+/* personalised exchange: bytes [send_off[r], send_off[r+1]) of `send` go to rank r, the bytes from rank r land at
+ * [recv_off[r], recv_off[r+1]) of `recv` (offsets: world + 1 entries each; nothing is sent to oneself) */
+typedef int (*ltrgpu_alltoallv_fn)(void *user, const void *send, const uint64_t *send_off, void *recv, const uint64_t *recv_off, void *cuda_stream);
+int ltrgpu_set_alltoallv(ltrgpu_Ctx *ctx, ltrgpu_alltoallv_fn fn);
 /* all-gather of a small HOST table through the device and the all-gather hook: recv = world x bytes, rank-major (synchronous) */
 int ltrgpu_host_allgather(ltrgpu_Ctx *ctx, const void *send, void *recv, size_t bytes);            /* same user pointer as the all-gather hook */
 

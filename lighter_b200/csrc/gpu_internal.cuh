@@ -88,6 +88,7 @@ struct ltrgpu_Ctx {
     int rank = 0, world = 1;
     ltrgpu_allgather_fn allgather = nullptr;
     ltrgpu_gatherv_fn gatherv = nullptr;
+    ltrgpu_alltoallv_fn alltoallv = nullptr;
     void *allgather_user = nullptr;
 
     /* ---- direct light ---- */

@@ -724,6 +724,46 @@ __global__ void rad_mirror_filter_kernel(const uint4 *__restrict__ all, unsigned
     }
 }
 
+/* personalised exchange of the mirrored links (ctx->alltoallv): records are bucketed by the rank that owns their row
+ * (rows are dealt in contiguous runs of rows_per_rank sorted positions), so that a record crosses NVLink once, to one
+ * rank, instead of reaching all of them in an all-gather (8 ranks on config 4: 2.1 GB into every rank -> 0.26 GB). */
+__global__ void rad_mirror_count_kernel(const uint4 *__restrict__ rec, unsigned long long n, uint32_t rows_per_rank, uint32_t world, unsigned long long *__restrict__ counts)
+{
+    __shared__ unsigned s_cnt[64];
+    if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (unsigned long long)gridDim.x * blockDim.x)
+        atomicAdd(&s_cnt[rec[e].x / rows_per_rank], 1u);
+    __syncthreads();
+    if (threadIdx.x < world && s_cnt[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+__global__ void rad_mirror_bucket_kernel(const uint4 *__restrict__ rec, unsigned long long n, uint32_t rows_per_rank, const unsigned long long *__restrict__ bucket_off,
+                                         unsigned long long *__restrict__ cursor, uint4 *__restrict__ out)
+{
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < ((n + 31ull) & ~31ull); e += (unsigned long long)gridDim.x * blockDim.x) {
+        const bool valid = e < n;
+        const uint4 r = valid ? rec[e] : make_uint4(0, 0, 0, 0);
+        const unsigned owner = valid ? r.x / rows_per_rank : 0xffffffffu;
+        /* lanes of the same owner reserve their slots with one atomic */
+        const unsigned peers = __match_any_sync(0xffffffffu, owner);
+        const unsigned lane = threadIdx.x & 31u, leader = (unsigned)__ffs(peers) - 1u;
+        unsigned long long base = 0;
+        if (valid && lane == leader) base = atomicAdd(cursor + owner, (unsigned long long)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (valid) out[bucket_off[owner] + base + __popc(peers & ((1u << lane) - 1u))] = r;
+    }
+}
+
+__global__ void rad_mirror_append_kernel(const uint4 *__restrict__ rec, unsigned long long n, unsigned long long *__restrict__ keys, float *__restrict__ factors)
+{
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint4 r = rec[e];
+        keys[e] = ((unsigned long long)r.x << 32) | r.y;
+        factors[e] = __uint_as_float(r.z);
+    }
+}
+
 __global__ void rad_row_offsets_kernel(const unsigned long long *__restrict__ keys, unsigned long long n_links, uint64_t row_begin,
                                        uint64_t n_rows, uint64_t *__restrict__ rowoff)
 {
@@ -1084,7 +1124,57 @@ extern "C" int ltrgpu_radiosity_ex(ltrgpu_Ctx *ctx, ltrgpu_materials_fn material
 
         /* ---- 4b. exchange the mirrored links: each rank's records are all-gathered (padded to the largest
          *          count), every rank keeps the ones whose row it owns.  ~16 B per cross-rank link. ---- */
-        if (world > 1) {
+        const char *env_a2a = getenv("LTR_RAD_MIRROR_ALLGATHER");
+        if (world > 1 && world <= 64 && ctx->alltoallv && !(env_a2a && env_a2a[0] == '1')) {
+            /* counts[r] = my records whose row rank r owns; the world x world matrix of them is all-gathered (tiny) */
+            unsigned long long *d_cur = nullptr, *d_boff = nullptr, *d_matrix = nullptr;
+            uint4 *bucketed = nullptr, *incoming = nullptr;
+            RAD_TRY(dev_alloc(ctx, &d_matrix, (size_t)world * world)); RAD_TRY(dev_alloc(ctx, &d_cur, world)); RAD_TRY(dev_alloc(ctx, &d_boff, world + 1));
+            unsigned long long *my_row = d_matrix + (size_t)ctx->rank * world;
+            RAD_CU(cudaMemsetAsync(my_row, 0, 8 * world, st));
+            RAD_CU(cudaMemsetAsync(d_cur, 0, 8 * world, st));
+            if (mirror_used) {
+                rad_mirror_count_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(mirror, mirror_used, (uint32_t)n_rows, world, my_row);
+                RAD_LAUNCHED();
+            }
+            if (!ctx->allgather || ctx->allgather(ctx->allgather_user, my_row, d_matrix, 8 * (size_t)world, st)) {
+                snprintf(ctx->err, sizeof(ctx->err), "radiosity: all-gather of the mirrored-link counts failed"); goto done;
+            }
+            std::vector<unsigned long long> M((size_t)world * world);
+            RAD_CU(cudaMemcpyAsync(M.data(), d_matrix, 8 * M.size(), cudaMemcpyDeviceToHost, st));
+            RAD_CU(cudaStreamSynchronize(st));
+            std::vector<uint64_t> soff(world + 1, 0), roff(world + 1, 0);
+            std::vector<unsigned long long> boff(world + 1, 0);
+            for (uint32_t r = 0; r < world; ++r) {
+                const unsigned long long to_r = r == (uint32_t)ctx->rank ? 0 : M[(size_t)ctx->rank * world + r], from_r = r == (uint32_t)ctx->rank ? 0 : M[(size_t)r * world + ctx->rank];
+                boff[r + 1] = boff[r] + M[(size_t)ctx->rank * world + r];
+                soff[r] = boff[r] * sizeof(uint4);
+                roff[r + 1] = roff[r] + from_r * sizeof(uint4);
+                (void)to_r;
+            }
+            soff[world] = boff[world] * sizeof(uint4);
+            /* send ranges are the buckets themselves (the bucket of my own rank is empty: my rows never go to the mirror list) */
+            const unsigned long long n_in = roff[world] / sizeof(uint4);
+            RAD_TRY(dev_alloc(ctx, &bucketed, mirror_used ? mirror_used : 1)); RAD_TRY(dev_alloc(ctx, &incoming, n_in ? n_in : 1));
+            RAD_CU(cudaMemcpyAsync(d_boff, boff.data(), 8 * (world + 1), cudaMemcpyHostToDevice, st));
+            if (mirror_used) {
+                rad_mirror_bucket_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(mirror, mirror_used, (uint32_t)n_rows, d_boff, d_cur, bucketed);
+                RAD_LAUNCHED();
+            }
+            if (ctx->alltoallv(ctx->allgather_user, bucketed, soff.data(), incoming, roff.data(), st)) {
+                snprintf(ctx->err, sizeof(ctx->err), "radiosity: exchange of the mirrored links failed"); goto done;
+            }
+            RAD_TRY(grow_buf(ctx, &keys, &link_cap, link_used, link_used + n_in));
+            RAD_TRY(grow_buf(ctx, &fac, &link_cap_f, link_used, link_used + n_in));
+            if (n_in) {
+                rad_mirror_append_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(incoming, n_in, keys + link_used, fac + link_used);
+                RAD_LAUNCHED();
+            }
+            RAD_CU(cudaStreamSynchronize(st));
+            link_used += n_in;
+            dev_free(&d_matrix); dev_free(&d_cur); dev_free(&d_boff); dev_free(&bucketed); dev_free(&incoming); dev_free(&mirror);
+            RAD_TRACE("mirror link exchange (personalised)");
+        } else if (world > 1) {
             RAD_TRY(dev_alloc(ctx, &d_mcounts, world));
             RAD_CU(cudaMemsetAsync(d_mcounts, 0, 8 * world, st));
             unsigned long long mine_cnt = mirror_used;

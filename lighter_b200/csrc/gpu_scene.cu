@@ -584,6 +584,7 @@ extern "C" int ltrgpu_set_world(ltrgpu_Ctx *ctx, int rank, int world, ltrgpu_all
 }
 
 extern "C" int ltrgpu_set_gatherv(ltrgpu_Ctx *ctx, ltrgpu_gatherv_fn gatherv) { ctx->gatherv = gatherv; return 0; }
+extern "C" int ltrgpu_set_alltoallv(ltrgpu_Ctx *ctx, ltrgpu_alltoallv_fn fn) { ctx->alltoallv = fn; return 0; }
 
 extern "C" int ltrgpu_set_shard(ltrgpu_Ctx *ctx, uint64_t begin, uint64_t end, int rank, int world,
                                 ltrgpu_allgather_fn allgather, void *allgather_user)

@@ -24,10 +24,12 @@ static void load_once()
     g_api.CommDestroy = (int (*)(void *))dlsym(lib, "ncclCommDestroy");
     g_api.AllGather = (int (*)(const void *, void *, size_t, int, void *, void *))dlsym(lib, "ncclAllGather");
     g_api.Broadcast = (int (*)(const void *, void *, size_t, int, int, void *, void *))dlsym(lib, "ncclBroadcast");
+    g_api.Send = (int (*)(const void *, size_t, int, int, void *, void *))dlsym(lib, "ncclSend");
+    g_api.Recv = (int (*)(void *, size_t, int, int, void *, void *))dlsym(lib, "ncclRecv");
     g_api.GroupStart = (int (*)(void))dlsym(lib, "ncclGroupStart");
     g_api.GroupEnd = (int (*)(void))dlsym(lib, "ncclGroupEnd");
     g_api.GetErrorString = (const char *(*)(int))dlsym(lib, "ncclGetErrorString");
-    if (!g_api.GetUniqueId || !g_api.CommInitRank || !g_api.CommDestroy || !g_api.AllGather || !g_api.Broadcast || !g_api.GroupStart || !g_api.GroupEnd || !g_api.GetErrorString) {
+    if (!g_api.GetUniqueId || !g_api.CommInitRank || !g_api.CommDestroy || !g_api.AllGather || !g_api.Broadcast || !g_api.Send || !g_api.Recv || !g_api.GroupStart || !g_api.GroupEnd || !g_api.GetErrorString) {
         snprintf(g_err, sizeof(g_err), "libnccl is missing a required symbol");
         return;
     }

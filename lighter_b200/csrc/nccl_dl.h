@@ -16,6 +16,8 @@ struct NcclApi {
     int (*CommDestroy)(void *comm);
     int (*AllGather)(const void *send, void *recv, size_t count, int dtype, void *comm, void *stream);
     int (*Broadcast)(const void *send, void *recv, size_t count, int dtype, int root, void *comm, void *stream);
+    int (*Send)(const void *send, size_t count, int dtype, int peer, void *comm, void *stream);
+    int (*Recv)(void *recv, size_t count, int dtype, int peer, void *comm, void *stream);
     int (*GroupStart)(void);
     int (*GroupEnd)(void);
     const char *(*GetErrorString)(int);

@@ -115,6 +115,22 @@ def main():
     print("walk cost per segment (model): %.0f slots; lock-step batches use %.0f %% of their lane slots, lane refill within a chunk %.0f %%"
           % (useful / ns, 100 * useful / lock, 100 * useful / refill))
     print("=> upper bound of the gain from lane refill on the traversal part: %.0f %%" % (100 * (1 - refill / lock)))
+    # upper bound of ANY reordering of a chunk's segments before they are cut into lock-step batches: sorted by their true cost
+    tot = 0.0
+    for b in range(len(offs) - 1):
+        c = np.sort(cost[offs[b]:offs[b + 1]])
+        pad = (-len(c)) % 32
+        tot += np.concatenate([c, np.zeros(pad)]).reshape(-1, 32).max(1).sum() * 32
+    print("   lock-step batches of a chunk sorted by TRUE cost (bound of any reordering): %.0f %% of the lane slots used" % (100 * useful / tot))
+    # by segment length (a key a kernel could compute)
+    tot = 0.0
+    seglen = np.linalg.norm(segs[:, 3:6] - segs[:, 0:3], axis=1)
+    for b in range(len(offs) - 1):
+        o = np.argsort(seglen[offs[b]:offs[b + 1]], kind="stable")
+        c = cost[offs[b]:offs[b + 1]][o]
+        pad = (-len(c)) % 32
+        tot += np.concatenate([c, np.zeros(pad)]).reshape(-1, 32).max(1).sum() * 32
+    print("   lock-step batches of a chunk sorted by segment LENGTH: %.0f %% of the lane slots used" % (100 * useful / tot))
     # refill inside groups of G segments only (a per-warp ring of G prepared rays, drained before the next G are prepared)
     for G in (64, 128, 256, 512):
         tot = 0.0
