@@ -1124,8 +1124,11 @@ extern "C" int ltrgpu_radiosity_ex(ltrgpu_Ctx *ctx, ltrgpu_materials_fn material
 
         /* ---- 4b. exchange the mirrored links: each rank's records are all-gathered (padded to the largest
          *          count), every rank keeps the ones whose row it owns.  ~16 B per cross-rank link. ---- */
+        /* From 4 ranks up (with 2 an all-gather moves the same bytes).  NCCL opens its point-to-point connections at the first
+         * send/recv of a communicator: seconds, once per process (8 ranks: 6.6 s measured) -- a caller that bakes once on many
+         * GPUs can keep the all-gather with LTR_RAD_MIRROR_ALLGATHER=1. */
         const char *env_a2a = getenv("LTR_RAD_MIRROR_ALLGATHER");
-        if (world > 1 && world <= 64 && ctx->alltoallv && !(env_a2a && env_a2a[0] == '1')) {
+        if (world >= 4 && world <= 64 && ctx->alltoallv && !(env_a2a && env_a2a[0] == '1')) {
             /* counts[r] = my records whose row rank r owns; the world x world matrix of them is all-gathered (tiny) */
             unsigned long long *d_cur = nullptr, *d_boff = nullptr, *d_matrix = nullptr;
             uint4 *bucketed = nullptr, *incoming = nullptr;
