@@ -922,22 +922,11 @@ void bake_main(ltr_Scene *S)
     if (!S->bake) S->bake = new Bake;
     const bool trace = getenv("LTR_TRACE") != nullptr;
     double tc = 0, th = 0, tu = 0, tg = 0, tr = 0;
-    std::thread prewarm;                                          /* first bake of a process: see ltrgpu_prewarm */
-    struct PrewarmJoin { std::thread &t; ~PrewarmJoin() { if (t.joinable()) t.join(); } } prewarm_join{ prewarm };
     guarded(S, [&]() {
         connect(S);      tc = now_s();
         host_prepare(S); th = now_s();
-        {
-            size_t out_bytes = 0;                                  /* the read-back arena, when this rank reads back and the images keep their size */
-            if (!S->config.ds2x && !(S->output_root_only && S->world > 1 && S->rank != 0))
-                for (size_t i = 1; i < S->instances.size(); ++i) out_bytes += (size_t)S->instances[i]->lm_width * S->instances[i]->lm_height * 12;
-            ltrgpu_Ctx *g = S->bake->gpu;
-            const int rad = S->config.bounce_count > 0;
-            prewarm = std::thread([g, rad, out_bytes]() { ltrgpu_prewarm(g, rad, out_bytes); });
-        }
         upload(S);       tu = now_s();
         gpu_stages(S);   tg = now_s();
-        if (prewarm.joinable()) prewarm.join();
         readback(S);     tr = now_s();
     });
     S->stats.t_total = now_s() - t0;

@@ -195,11 +195,6 @@ int ltrgpu_download_outputs_all(ltrgpu_Ctx *ctx, float *rgb_all);
 void *ltrgpu_host_alloc(size_t bytes);
 void ltrgpu_host_free(void *p);
 
-/* First bake of a process: the two big allocations whose size is known early -- the radiosity candidate buffer (cudaMalloc
- * of ~11 GB: ~40 ms) and the page-locked block the lightmaps are read back into (~80 ms per 200 MB) -- are made (and put
- * back into the caches) on a background thread while the pre-pass and the first stages run.  With warm caches it does nothing. */
-int ltrgpu_prewarm(ltrgpu_Ctx *ctx, int with_radiosity, size_t host_output_bytes);
-
 int ltrgpu_sync(ltrgpu_Ctx *ctx);
 int ltrgpu_get_counters(ltrgpu_Ctx *ctx, ltrgpu_Counters *out);
 int ltrgpu_reset_bake(ltrgpu_Ctx *ctx);     /* drop lumels/results, keep the uploaded scene (bench re-runs) */

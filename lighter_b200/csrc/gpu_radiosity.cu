@@ -861,33 +861,6 @@ static int rad_allgather(ltrgpu_Ctx *ctx, float4 *buf, uint64_t chunk_elems, con
     return 0;
 }
 
-/* candidate buffer: a sixteenth of the device's TOTAL memory, between 16 Mi and 1 Gi records (12 B each).  Not of the
- * FREE memory: blocks cached by lb_malloc count as used, so a size derived from it drifted from bake to bake, missed
- * the cache every time it crossed a size class and paid a 12 GB cudaMalloc (~42 ms, seen as bake-time outliers). */
-static unsigned long long rad_candidate_capacity()
-{
-    unsigned long long cand_cap = 16ull << 20;
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-        unsigned long long want = (unsigned long long)(total_b / 16 / sizeof(RadCand));
-        if (want > cand_cap) cand_cap = want;
-        if (cand_cap > (1024ull << 20)) cand_cap = 1024ull << 20;
-    }
-    if (const char *e = getenv("LTR_RAD_CAND_CAP")) { const unsigned long long v = strtoull(e, nullptr, 10); if (v >= 4096) cand_cap = v; }   /* tests: force many batches */
-    return cand_cap;
-}
-
-extern "C" int ltrgpu_prewarm(ltrgpu_Ctx *ctx, int with_radiosity, size_t host_output_bytes)
-{
-    if (cudaSetDevice(ctx->device) != cudaSuccess) return 1;       /* runs on its own host thread; failures are not errors: the real allocation will report them */
-    if (with_radiosity) {
-        void *p = nullptr;
-        if (lb_malloc(&p, (size_t)rad_candidate_capacity() * sizeof(RadCand)) == cudaSuccess) lb_free(p); else cudaGetLastError();
-    }
-    if (host_output_bytes) ltrgpu_host_free(ltrgpu_host_alloc(host_output_bytes));
-    return 0;
-}
-
 struct RadHostMaterials { const float *diffuse3, *emissive3; };
 static int rad_host_materials(void *user, const float **d, const float **e)
 {
@@ -1050,7 +1023,19 @@ extern "C" int ltrgpu_radiosity_ex(ltrgpu_Ctx *ctx, ltrgpu_materials_fn material
 
         /* ---- 2b-4. candidates and visibility, in batches of work items bounded by the candidate buffer ---- */
         RAD_TRY(dev_alloc(ctx, &d_cnt, 4));
-        unsigned long long cand_cap = rad_candidate_capacity();
+        /* candidate buffer: a sixteenth of the device's TOTAL memory, between 16 Mi and 1 Gi records (12 B each).  Not of the
+         * FREE memory: blocks cached by lb_malloc count as used, so a size derived from it drifted from bake to bake, missed
+         * the cache every time it crossed a size class and paid a 12 GB cudaMalloc (~42 ms, seen as bake-time outliers). */
+        unsigned long long cand_cap = 16ull << 20;
+        {
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+                unsigned long long want = (unsigned long long)(total_b / 16 / sizeof(RadCand));
+                if (want > cand_cap) cand_cap = want;
+                if (cand_cap > (1024ull << 20)) cand_cap = 1024ull << 20;
+            }
+        }
+        if (const char *e = getenv("LTR_RAD_CAND_CAP")) { const unsigned long long v = strtoull(e, nullptr, 10); if (v >= 4096) cand_cap = v; }   /* tests: force many batches */
         RAD_TRY(dev_alloc(ctx, &cand, cand_cap));
         /* batch of items: probe with a small one, then size each batch from the measured yield */
         uint32_t batch = (uint32_t)ctx->num_sms * (uint32_t)sweep_ctas * RAD_WARPS * 8u;
