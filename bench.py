@@ -394,7 +394,7 @@ def main():
 
     line = {
         "metric": "rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": total_ms / args.steps, "step_ms": [round(x, 3) for x in step_ms], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD_DESC.get(args.workload, args.workload), "name": args.workload, "triangles": sc.triangle_count(),
                    "lumels": int(stats["n_lumels_total"]), "lights": len(sc.lights), "parallelism": f"lumel-shard x{world}",
