@@ -181,7 +181,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 }
 
 #define RAD_STAGE 288            /* per-warp stage: 31 left over + 8 pairs x 32 lanes, (row lane << 7 | k) each */
-#define RAD_CHUNK 1024u          /* candidate slots a warp reserves from the global counter at a time */
+#ifndef RAD_CHUNK
+#define RAD_CHUNK 1024u          /* candidate slots a warp reserves from the global counter at a time (512 / 2048 measured: profiles/r02_ab_runs.md) */
+#endif
 #define RAD_WARPS 4              /* warps per CTA; the warps do not interact */
 
 template <int G> struct __align__(128) RadColBuf {          /* one staged column tile */
