@@ -142,6 +142,9 @@ LTRAPI int ltrx_test_host_prepare(ltr_Scene *scene, uint64_t out_hash[12]);
 /* host-only: entry sets of segment bundles (csrc/bvh_entry.h) -- reachability self-check, root walk vs entry walk */
 LTRAPI int ltrx_test_bvh_entry(const float *tris9, u32 ntris, int leaf_max, const float *segs6, const u32 *bundle_off, u32 n_bundles,
                                u32 *entries_out, uint64_t *visits_root, uint64_t *visits_entry, uint64_t *entry_tests, u32 *mismatches);
+/* host-only: version-2 entry sets (shaft-culled search, leaf entries): root walk vs entry walk incl. triangle-test counts */
+LTRAPI int ltrx_test_bvh_entry2(const float *tris9, u32 ntris, int leaf_max, const float *segs6, const u32 *bundle_off, u32 n_bundles,
+                                int max_entries, int use_shaft, u32 *entries_out, uint64_t *stats4, u32 *mismatches, u32 *test_diffs);
 
 #ifdef __cplusplus
 }

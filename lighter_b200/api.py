@@ -124,6 +124,23 @@ def test_bvh_entry(tris: np.ndarray, segs: np.ndarray, bundle_off: np.ndarray, l
                 mismatches=mm.value)
 
 
+def test_bvh_entry2(tris: np.ndarray, segs: np.ndarray, bundle_off: np.ndarray, leaf_max: int = 2, max_entries: int = 8, shaft: bool = True) -> dict:
+    """Host-only: version-2 entry sets (csrc/bvh_entry.h: shaft-culled search, leaf entries) of bundles of segments whose first
+    end points form one box and whose second end points another -- root walk vs entry walk on every segment, hit / miss AND
+    number of triangles tested."""
+    tris = np.ascontiguousarray(tris, np.float32)
+    segs = np.ascontiguousarray(segs, np.float32).reshape(-1, 6)
+    off = np.ascontiguousarray(bundle_off, np.uint32)
+    nb = len(off) - 1
+    entries = np.zeros(max(nb, 1), np.uint32)
+    stats = (C.c_uint64 * 4)()
+    mm, td = u32(), u32()
+    ok = lib().ltrx_test_bvh_entry2(_fp(tris), len(tris), leaf_max, _fp(segs), off.ctypes.data, nb, int(max_entries), int(bool(shaft)),
+                                    entries.ctypes.data, stats, C.byref(mm), C.byref(td))
+    return dict(ok=bool(ok), entries=entries[:nb], visits_root=stats[0], visits_entry=stats[1], entry_tests=stats[2], tri_tests=stats[3],
+                mismatches=mm.value, test_diffs=td.value)
+
+
 def test_bvh_entry_cost(tris: np.ndarray, segs: np.ndarray, bundle_off: np.ndarray, leaf_max: int = 2):
     """Host-only: per-segment (4-wide node reads, triangle tests) of the any-hit walk from each bundle's entry set."""
     tris = np.ascontiguousarray(tris, np.float32)
@@ -160,7 +177,7 @@ LTRX_SYMBOLS = ["ltrx_Version", "ltrx_SampleFnChecker", "ltrx_SetDevice", "ltrx_
                 "ltrx_GetError", "ltrx_Prepare", "ltrx_BakeResident", "ltrx_Finish", "ltrx_OutputHash", "ltrx_SetDebug", "ltrx_GetLumels",
                 "ltrx_GetLinks", "ltrx_GetShadowFactors", "ltrx_SetShadowMode", "ltrx_GetShadowMasks", "ltrx_ShadowSampleSegment",
                 "ltrx_test_point_tri_distance", "ltrx_test_seg_tri",
-                "ltrx_test_scene_queries", "ltrx_test_device_bvh", "ltrx_test_march", "ltrx_test_spiral_dirs", "ltrx_test_reftree", "ltrx_test_bvh", "ltrx_test_bvh_entry", "ltrx_test_bvh_entry_cost", "ltrx_test_host_prepare", "ltrx_test_rad_cull",
+                "ltrx_test_scene_queries", "ltrx_test_device_bvh", "ltrx_test_march", "ltrx_test_spiral_dirs", "ltrx_test_reftree", "ltrx_test_bvh", "ltrx_test_bvh_entry", "ltrx_test_bvh_entry2", "ltrx_test_bvh_entry_cost", "ltrx_test_host_prepare", "ltrx_test_rad_cull",
                 "ltrx_test_rand_fill"]
 
 _lib = None
@@ -232,6 +249,8 @@ def lib() -> C.CDLL:
     L.ltrx_test_rad_cull.argtypes = [fp, fp, u32, fp, fp, u32, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
     L.ltrx_test_bvh_entry.argtypes = [fp, u32, C.c_int, fp, C.c_void_p, u32, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                       C.POINTER(C.c_uint64), C.POINTER(u32)]
+    L.ltrx_test_bvh_entry2.argtypes = [fp, u32, C.c_int, fp, C.c_void_p, u32, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint64),
+                                       C.POINTER(u32), C.POINTER(u32)]
     _lib = L
     return L
 

@@ -1353,6 +1353,98 @@ int ltrx_test_bvh_entry(const float *tris9, u32 ntris, int leaf_max, const float
     return ok;
 }
 
+/* host-only model of the version-2 entry sets (bvh_entry.h: shaft-culled search, leaf entries, <= 16 entries) on bundles of
+ * segments whose FIRST end points form box R and whose SECOND end points form box C, as in rad_visibility_kernel.  Every
+ * segment is walked from the root and from its bundle's entry set, counting the triangles each walk TESTS as well: the two
+ * walks must not only agree on hit / miss (*mismatches) but test the same number of triangles when the segment is free
+ * (*test_diffs) -- a dropped box that a ray would have entered shows up there even if it held no blocker.
+ * stats[0..3] = 4-wide node reads from the root, from the entry sets, entry boxes tested, triangle tests of the entry walk. */
+int ltrx_test_bvh_entry2(const float *tris9, u32 ntris, int leaf_max, const float *segs6, const u32 *bundle_off, u32 n_bundles,
+                         int max_entries, int use_shaft, u32 *entries_out, uint64_t *stats4, u32 *mismatches, u32 *test_diffs)
+{
+    SceneBvh bvh;
+    build_scene_bvh(tris9, ntris, bvh, leaf_max, 0);
+    if (bvh.nodes4.empty()) return 0;
+    if (max_entries < 1 || max_entries > BVH_ENTRY2_MAX) max_entries = BVH_ENTRY2_MAX;
+    std::vector<RayTri> rt(ntris);
+    for (u32 t = 0; t < ntris; ++t) {
+        const float *v = tris9 + 9 * (size_t)bvh.order[t];
+        prepare_raytri(mk3(v[0], v[1], v[2]), mk3(v[3], v[4], v[5]), mk3(v[6], v[7], v[8]), rt[t]);
+    }
+    stats4[0] = stats4[1] = stats4[2] = stats4[3] = 0; *mismatches = 0; *test_diffs = 0;
+    std::vector<int32_t> stack;
+    /* walk that tests every triangle of every accepted leaf (no early out), from a stack of nodes + a list of leaf codes */
+    auto walk = [&](V3 l1, V3 l2, std::vector<int32_t> &st, const std::vector<int32_t> &leaves, uint64_t *visits, uint64_t *tests) {
+        const V3 d = l2 - l1;
+        const float ix = lb_slab_inv(d.x), iy = lb_slab_inv(d.y), iz = lb_slab_inv(d.z);
+        bool hit = false;
+        auto leaf = [&](int32_t c) { const uint32_t code = ~c; for (uint32_t t = code >> 3; t < (code >> 3) + (code & 7u); ++t) { ++*tests; if (seg_tri_prepared(l1, d, rt[t]) < 1.0f) hit = true; } };
+        for (int32_t c : leaves) leaf(c);
+        while (!st.empty()) {
+            const Bvh4Node &n = bvh.nodes4[st.back()]; st.pop_back();
+            ++*visits;
+            for (int c = 0; c < 4; ++c) {
+                if (n.c[c] == BVH4_EMPTY) continue;
+                const float x0 = (n.lox[c] - l1.x) * ix, x1 = (n.hix[c] - lb_slab_origin_hi(l1.x, d.x)) * ix, y0 = (n.loy[c] - l1.y) * iy, y1 = (n.hiy[c] - lb_slab_origin_hi(l1.y, d.y)) * iy;
+                const float z0 = (n.loz[c] - l1.z) * iz, z1 = (n.hiz[c] - lb_slab_origin_hi(l1.z, d.z)) * iz;
+                const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
+                const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));
+                if (!(t0 <= t1 + 2e-6f)) continue;
+                if (n.c[c] < 0) leaf(n.c[c]); else st.push_back(n.c[c]);
+            }
+        }
+        return hit;
+    };
+    std::vector<int32_t> leaves, none;
+    for (u32 b = 0; b < n_bundles; ++b) {
+        float q[6] = { INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY };
+        float RC[12] = { INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY, INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY };
+        for (u32 s = bundle_off[b]; s < bundle_off[b + 1]; ++s)
+            for (int e = 0; e < 2; ++e) {
+                const float *p = segs6 + 6 * (size_t)s + 3 * e;
+                for (int k = 0; k < 3; ++k) {
+                    q[k] = fminf(q[k], p[k]); q[3 + k] = fmaxf(q[3 + k], p[k]);
+                    RC[6 * e + k] = fminf(RC[6 * e + k], p[k]); RC[6 * e + 3 + k] = fmaxf(RC[6 * e + 3 + k], p[k]);
+                }
+            }
+        BvhEntrySet2 E;
+        E.n = 0;
+        if (q[0] <= q[3]) {
+            const float maxabs = fmaxf(fmaxf(fmaxf(fabsf(q[0]), fabsf(q[3])), fmaxf(fabsf(q[1]), fabsf(q[4]))), fmaxf(fabsf(q[2]), fabsf(q[5])));
+            bvh_entry_pad(q[0], q[1], q[2], q[3], q[4], q[5]);
+            BvhShaft S;
+            bvh_shaft_build(RC, RC + 6, maxabs, S);
+            bvh4_entry_search2(bvh.nodes4.data(), q[0], q[1], q[2], q[3], q[4], q[5], use_shaft ? &S : nullptr, E, max_entries);
+        }
+        if (entries_out) entries_out[b] = (u32)E.n;
+        for (u32 s = bundle_off[b]; s < bundle_off[b + 1]; ++s) {
+            const float *p = segs6 + 6 * (size_t)s;
+            const V3 A = mk3(p[0], p[1], p[2]), B = mk3(p[3], p[4], p[5]);
+            uint64_t t_root = 0, t_entry = 0;
+            stack.assign(1, 0);
+            const bool h_root = walk(A, B, stack, none, &stats4[0], &t_root);
+            const V3 d = B - A;
+            const float ix = lb_slab_inv(d.x), iy = lb_slab_inv(d.y), iz = lb_slab_inv(d.z);
+            stack.clear(); leaves.clear();
+            for (int i = 0; i < E.n; ++i) {
+                const float x0 = (E.lo[i][0] - A.x) * ix, x1 = (E.hi[i][0] - lb_slab_origin_hi(A.x, d.x)) * ix, y0 = (E.lo[i][1] - A.y) * iy, y1 = (E.hi[i][1] - lb_slab_origin_hi(A.y, d.y)) * iy;
+                const float z0 = (E.lo[i][2] - A.z) * iz, z1 = (E.hi[i][2] - lb_slab_origin_hi(A.z, d.z)) * iz;
+                const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
+                const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));
+                if (!(t0 <= t1 + 2e-6f)) continue;
+                int32_t code; memcpy(&code, &E.lo[i][3], 4);
+                if (code >= 0) stack.push_back(code); else leaves.push_back(code);
+            }
+            stats4[2] += (uint64_t)E.n;
+            const bool h_entry = walk(A, B, stack, leaves, &stats4[1], &t_entry);
+            stats4[3] += t_entry;
+            if (h_root != h_entry) ++*mismatches;
+            if (t_root != t_entry) ++*test_diffs;
+        }
+    }
+    return 1;
+}
+
 int ltrx_test_bvh(const float *tris9, u32 ntris, int leaf_max, u32 *n_nodes, u32 *depth, u32 *order_out, float *bounds6)
 {
     SceneBvh bvh;

@@ -10,6 +10,9 @@
 #include "gpu.h"
 #include "bvh_entry.h"
 
+#ifndef LB_VIS_SKIPEMPTY
+#define LB_VIS_SKIPEMPTY 1                /* 1 = the any-hit node loop branches around the two last slots of a 4-wide node when both are unused (209.9 -> 208.6 ms on config 4) */
+#endif
 #ifndef LB_VIS_LEAFQ
 #define LB_VIS_LEAFQ 1                    /* 1 = the any-hit walk of the 4-wide tree queues leaf codes instead of triangle indices (bvh4_anyhit_core) */
 #endif
@@ -568,22 +571,18 @@ __device__ __forceinline__ bool bvh_anyhit(const BvhNode *__restrict__ nodes, co
  * The same any-hit walk on the 4-wide tree (bvh.h Bvh4Node): one iteration tests four boxes (six float4 loads for the
  * boxes, one for the child codes).  A visit is counted as two node units (128 bytes = two 64-byte binary nodes).
  */
-template <int FLUSH>
-__device__ __forceinline__ bool bvh4_anyhit_core(const Bvh4Node *__restrict__ nodes, const RayTri *__restrict__ tris, const V3 l1, const V3 l1h, const V3 d,
-                                                 const float ix, const float iy, const float iz, int (&stack_n)[BVH_STACK], int sp, int node, TravStats &ts,
-                                                 const Bvh4Node *sm_nodes = nullptr /* LB_VIS_SMEMNODES: shared-memory copies of the entry nodes, addressed as LB_SM_TAG + slot */)
+/* The walk proper, with the leaf queue handed in: `tq` may already hold nq leaf codes (version-2 entry sets queue the leaf
+ * entries a ray touches); TQN >= max(nq on entry, (FLUSH + 1) / 2 - 1) + 4. */
+template <int FLUSH, int TQN>
+__device__ __forceinline__ bool bvh4_anyhit_core_q(const Bvh4Node *__restrict__ nodes, const RayTri *__restrict__ tris, const V3 l1, const V3 l1h, const V3 d,
+                                                   const float ix, const float iy, const float iz, int (&stack_n)[BVH_STACK], int sp, int node,
+                                                   unsigned (&tq)[TQN], int nq, TravStats &ts, const Bvh4Node *sm_nodes = nullptr)
 {
-    /* Measured and NOT adopted (B200, config 4): picking the near / far plane of every slab by the sign of the direction
-     * (bit-identical to min/max, 4 three-way min/max per child instead of 10 two-way) needs a separate address per
-     * float4 of the node; the extra pointers cost 16-24 registers and the kernel is more sensitive to occupancy than to
-     * those instructions: 265 ms vs 236 ms for this form at 56 registers. */
-#if LB_VIS_LEAFQ
     /* The queue holds LEAF CODES (first << 3 | count), one store per leaf met; the triangles of a leaf are enumerated in the
      * test phase.  (The round-1 form stored every triangle index: a chain of up to seven store + branch steps per leaf in
      * the node loop.)  The test phase starts after (FLUSH + 1) / 2 queued leaves (leaves hold <= 2 triangles by default). */
     constexpr int LQ = (FLUSH + 1) / 2;
-    unsigned tq[LQ + 3];                             /* LQ - 1 pending + the four children of one node */
-    int nq = 0;
+    {
     for (;;) {
         while (node >= 0) {
 #if LB_VIS_SMEMNODES
@@ -612,8 +611,16 @@ __device__ __forceinline__ bool bvh4_anyhit_core(const Bvh4Node *__restrict__ no
             }
             LB_BVH4_CHILD(lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, k.x)
             LB_BVH4_CHILD(lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, k.y)
+#if LB_VIS_SKIPEMPTY
+            /* a node of two leaf children uses two slots: when every active lane is on such a node the warp skips half the box arithmetic */
+            if (k.z != BVH4_EMPTY || k.w != BVH4_EMPTY) {
+                LB_BVH4_CHILD(lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, k.z)
+                LB_BVH4_CHILD(lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, k.w)
+            }
+#else
             LB_BVH4_CHILD(lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, k.z)
             LB_BVH4_CHILD(lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, k.w)
+#endif
 #undef LB_BVH4_CHILD
             node = next >= 0 ? next : (sp ? stack_n[--sp] : -1);
             if (nq >= LQ) break;
@@ -630,6 +637,22 @@ __device__ __forceinline__ bool bvh4_anyhit_core(const Bvh4Node *__restrict__ no
         }
         if (node < 0) return false;
     }
+    }
+}
+
+template <int FLUSH>
+__device__ __forceinline__ bool bvh4_anyhit_core(const Bvh4Node *__restrict__ nodes, const RayTri *__restrict__ tris, const V3 l1, const V3 l1h, const V3 d,
+                                                 const float ix, const float iy, const float iz, int (&stack_n)[BVH_STACK], int sp, int node, TravStats &ts,
+                                                 const Bvh4Node *sm_nodes = nullptr /* LB_VIS_SMEMNODES: shared-memory copies of the entry nodes, addressed as LB_SM_TAG + slot */)
+{
+    /* Measured and NOT adopted (B200, config 4): picking the near / far plane of every slab by the sign of the direction
+     * (bit-identical to min/max, 4 three-way min/max per child instead of 10 two-way) needs a separate address per
+     * float4 of the node; the extra pointers cost 16-24 registers and the kernel is more sensitive to occupancy than to
+     * those instructions: 265 ms vs 236 ms for this form at 56 registers. */
+#if LB_VIS_LEAFQ
+    constexpr int LQ = (FLUSH + 1) / 2;
+    unsigned tq[LQ + 3];                             /* LQ - 1 pending + the four children of one node */
+    return bvh4_anyhit_core_q<FLUSH>(nodes, tris, l1, l1h, d, ix, iy, iz, stack_n, sp, node, tq, 0, ts, sm_nodes);
 #else
     constexpr int TQ = FLUSH + 28;                   /* FLUSH - 1 pending + four leaves of up to 7 triangles */
     int tq[TQ];
@@ -1040,6 +1063,132 @@ __device__ __forceinline__ void bvh_entry_search_warp(const typename A::Node *__
     }
     if (lane == 0) E.n = n;
     __syncwarp();
+}
+
+/*
+ * Warp-cooperative form of bvh4_entry_search2 (bvh_entry.h, version 2: shaft planes, leaf entries, <= BVH_ENTRY2_MAX <= 16
+ * entries): the same frontier, picks and slot assignment as the scalar model.  Entry i lives in the registers of lane i.
+ * A child of the picked node is tested by the eight lanes c, c + 4, ..: every lane holds two of the twelve shaft planes
+ * (lane >> 2 and, for lanes < 16, 8 + (lane >> 2)) in registers, so the four boxes meet all planes in one step and a ballot
+ * collects the verdicts.  All 32 lanes must call it with the same arguments; E.rc must hold the boxes R and C (written by
+ * the caller, warp-synchronised); q is the padded bundle box.  The result is written to E (shared memory).
+ */
+template <bool SHAFT>
+__device__ __forceinline__ void bvh4_entry_search2_warp(const Bvh4Node *__restrict__ nodes, float qlx, float qly, float qlz, float qhx, float qhy, float qhz,
+                                                        float maxabs, BvhEntrySet2 &E, const unsigned lane)
+{
+    const unsigned FULL = 0xffffffffu;
+    float p_nu0 = 0.f, p_nv0 = 0.f, p_ru0 = 0.f, p_rv0 = 0.f, p_lim0 = 0.f, p_nu1 = 0.f, p_nv1 = 0.f, p_ru1 = 0.f, p_rv1 = 0.f, p_lim1 = 0.f;
+    const int pa0 = (int)(lane >> 4);                       /* axis pair of plane lane >> 2 (planes 0-3: 0, 4-7: 1); the second plane's is 2 */
+    if (SHAFT) {
+        bvh_shaft_plane(E.rc, E.rc + 6, maxabs, (int)(lane >> 2), p_nu0, p_nv0, p_ru0, p_rv0, p_lim0);
+        if (lane < 16u) bvh_shaft_plane(E.rc, E.rc + 6, maxabs, 8 + (int)(lane >> 2), p_nu1, p_nv1, p_ru1, p_rv1, p_lim1);
+    }
+    int e_code = 0;
+    float e_lx = -INFINITY, e_ly = -INFINITY, e_lz = -INFINITY, e_hx = INFINITY, e_hy = INFINITY, e_hz = INFINITY;
+    bool e_fin = false;
+    int n = 1;
+    for (int it = 0; it < 128; ++it) {
+        /* pick: the first non-final entry of largest extent */
+        float key = ((int)lane < n && !e_fin) ? (e_hx - e_lx) + (e_hy - e_ly) + (e_hz - e_lz) : -1.f;
+        int who = (int)lane;
+#pragma unroll
+        for (int o = BVH_ENTRY2_MAX > 8 ? 8 : 4; o > 0; o >>= 1) {      /* entries live in lanes 0..BVH_ENTRY2_MAX-1 */
+            const float k2 = __shfl_xor_sync(FULL, key, o);
+            const int w2 = __shfl_xor_sync(FULL, who, o);
+            if (k2 > key || (k2 == key && w2 < who)) { key = k2; who = w2; }
+        }
+        key = __shfl_sync(FULL, key, 0); who = __shfl_sync(FULL, who, 0);
+        if (!(key >= 0.f)) break;
+        const int pick = who;
+        const int pnode = __shfl_sync(FULL, e_code, pick);
+        /* child lane & 3 of the picked node on every lane */
+        const int c = (int)(lane & 3u);
+        const Bvh4Node &N = nodes[pnode];
+        const int code = N.c[c];
+        const float lx = N.lox[c], ly = N.loy[c], lz = N.loz[c], hx = N.hix[c], hy = N.hiy[c], hz = N.hiz[c];
+        unsigned om = 0u;
+        if (SHAFT) {
+            bool out;
+            {
+                const float lu = pa0 == 0 ? lx : ly, hu = pa0 == 0 ? hx : hy, lv = pa0 == 0 ? ly : lz, hv = pa0 == 0 ? hy : hz;
+                const float bu = p_nu0 > 0.f ? lu : hu, bv = p_nv0 > 0.f ? lv : hv;
+                out = p_nu0 * (bu - p_ru0) + p_nv0 * (bv - p_rv0) > p_lim0;
+            }
+            {                                             /* axis pair 2 = (z, x); lanes >= 16 hold a null plane (0 > 0 is false) */
+                const float bu = p_nu1 > 0.f ? lz : hz, bv = p_nv1 > 0.f ? lx : hx;
+                out = out || (p_nu1 * (bu - p_ru1) + p_nv1 * (bv - p_rv1) > p_lim1);
+            }
+            om = __ballot_sync(FULL, out);
+        }
+        const bool in = lane < 4u && code != BVH4_EMPTY && lx <= qhx && hx >= qlx && ly <= qhy && hy >= qly && lz <= qhz && hz >= qlz &&
+                        !(om & (0x11111111u << c));
+        const unsigned hm = __ballot_sync(FULL, in);
+        const int nh = __popc(hm);
+        if (n - 1 + nh > BVH_ENTRY2_MAX) { if ((int)lane == pick) e_fin = true; continue; }
+        if (nh == 0) {                                   /* drop the entry: the last one takes its slot */
+            const int last = n - 1;
+            const int t_code = __shfl_sync(FULL, e_code, last);
+            const float t_lx = __shfl_sync(FULL, e_lx, last), t_ly = __shfl_sync(FULL, e_ly, last), t_lz = __shfl_sync(FULL, e_lz, last);
+            const float t_hx = __shfl_sync(FULL, e_hx, last), t_hy = __shfl_sync(FULL, e_hy, last), t_hz = __shfl_sync(FULL, e_hz, last);
+            const int t_fin = __shfl_sync(FULL, (int)e_fin, last);
+            if ((int)lane == pick && pick != last) { e_code = t_code; e_lx = t_lx; e_ly = t_ly; e_lz = t_lz; e_hx = t_hx; e_hy = t_hy; e_hz = t_hz; e_fin = t_fin != 0; }
+            if ((int)lane == last) e_fin = false;
+            n = last;
+            continue;
+        }
+        /* the k-th child in range goes to slot pick (k = 0) or n + k - 1; seen from the destination lane: */
+        int k = -1;
+        if ((int)lane == pick) k = 0;
+        else if ((int)lane >= n && (int)lane < n + nh - 1) k = (int)lane - n + 1;
+        const int src = k >= 0 ? (int)__fns(hm, 0, k + 1) : 0;
+        const int t_code = __shfl_sync(FULL, code, src);
+        const float t_lx = __shfl_sync(FULL, lx, src), t_ly = __shfl_sync(FULL, ly, src), t_lz = __shfl_sync(FULL, lz, src);
+        const float t_hx = __shfl_sync(FULL, hx, src), t_hy = __shfl_sync(FULL, hy, src), t_hz = __shfl_sync(FULL, hz, src);
+        if (k >= 0) { e_code = t_code; e_lx = t_lx; e_ly = t_ly; e_lz = t_lz; e_hx = t_hx; e_hy = t_hy; e_hz = t_hz; e_fin = t_code < 0; }   /* a leaf is final at once */
+        n += nh - 1;
+    }
+    __syncwarp();
+    if ((int)lane < n) {
+        *reinterpret_cast<float4 *>(E.lo[lane]) = make_float4(e_lx, e_ly, e_lz, __int_as_float(e_code));
+        *reinterpret_cast<float4 *>(E.hi[lane]) = make_float4(e_hx, e_hy, e_hz, 0.f);
+    }
+    if (lane == 0) E.n = n;
+    __syncwarp();
+}
+
+/*
+ * Any-hit walk from a version-2 entry set: the ray tests the <= 16 entry boxes (two 16-byte shared-memory loads each, the
+ * same words on every lane), pushes the inner nodes it touches and queues the leaves it touches for the triangle phase.
+ */
+template <int FLUSH = 10>
+__device__ __forceinline__ bool bvh4_anyhit_entries2(const Bvh4Node *__restrict__ nodes, const RayTri *__restrict__ tris, const BvhEntrySet2 &E,
+                                                     V3 l1, V3 l2, TravStats &ts)
+{
+    int stack_n[BVH_STACK];
+    int sp = 0;
+    constexpr int LQ = (FLUSH + 1) / 2;
+    unsigned tq[(LQ + 3 > BVH_ENTRY2_MAX ? LQ + 3 : BVH_ENTRY2_MAX) + 4];
+    int nq = 0;
+    const V3 d = l2 - l1;
+    const float ix = lb_slab_inv(d.x), iy = lb_slab_inv(d.y), iz = lb_slab_inv(d.z);
+    const V3 l1h = mk3(lb_slab_origin_hi(l1.x, d.x), lb_slab_origin_hi(l1.y, d.y), lb_slab_origin_hi(l1.z, d.z));
+    const int n = E.n;
+    for (int i = 0; i < n; ++i) {
+        const float4 lo = *reinterpret_cast<const float4 *>(E.lo[i]), hi = *reinterpret_cast<const float4 *>(E.hi[i]);
+        const float x0 = (lo.x - l1.x) * ix, x1 = (hi.x - l1h.x) * ix, y0 = (lo.y - l1.y) * iy, y1 = (hi.y - l1h.y) * iy;
+        const float z0 = (lo.z - l1.z) * iz, z1 = (hi.z - l1h.z) * iz;
+        const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
+        const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));
+        if (t0 <= t1 + 2e-6f) {
+            const int code = __float_as_int(lo.w);
+            if (code >= 0) stack_n[sp++] = code; else tq[nq++] = ~(unsigned)code;
+        }
+    }
+    ts.entries += (unsigned)n;
+    if ((sp | nq) == 0) return false;
+    const int node = sp ? stack_n[--sp] : -1;
+    return bvh4_anyhit_core_q<FLUSH>(nodes, tris, l1, l1h, d, ix, iy, iz, stack_n, sp, node, tq, nq, ts);
 }
 
 /* warp-aggregated counter add */

@@ -142,7 +142,8 @@ __global__ void rad_tile_bounds_kernel(const float4 *__restrict__ spos, const fl
         }
         if (G < 32 && o * 2 == G && (threadIdx.x & (G - 1)) == 0) {                            /* the xor butterfly has just covered a G-lane group */
             TileBounds w;
-            w.plo = make_float4(v[0], v[1], v[2], 0.f); w.nlo = make_float4(v[3], v[4], v[5], 0.f);
+            w.plo = make_float4(v[0], v[1], v[2], (v[3] == v[9] && v[4] == v[10] && v[5] == v[11]) ? 1.f : 0.f);      /* .w: the group has one normal (rad_cull.h LB_RAD_FLATN) */
+            w.nlo = make_float4(v[3], v[4], v[5], 0.f);
             w.phi = make_float4(v[6], v[7], v[8], 0.f); w.nhi = make_float4(v[9], v[10], v[11], 0.f);
             tbg[(size_t)blockIdx.x * (RAD_TILE / G) + threadIdx.x / G] = w;
         }
@@ -475,6 +476,12 @@ template <int G> static size_t rad_sweep_smem() { return sizeof(RadColBuf<G>) * 
 #ifndef LB_VIS_LEAN
 #define LB_VIS_LEAN 1           /* register-lean batch loop of the visibility kernel (see there); 0 = the round-1 software pipeline */
 #endif
+#ifndef LB_VIS_ENTRY2
+#define LB_VIS_ENTRY2 1         /* 1 = version-2 entry sets (bvh_entry.h: shaft-culled search, leaf entries, <= BVH_ENTRY2_MAX entries): 224.5 -> 211.1 ms on config 4; 0 = version 1 (A/B) */
+#endif
+#ifndef LB_VIS_SHAFT
+#define LB_VIS_SHAFT 1          /* version-2 entry sets: 0 = bounding-box search only (A/B) */
+#endif
 #ifndef LB_VIS_MINBLOCKS
 #define LB_VIS_MINBLOCKS 9      /* 56 registers: measured optimum on B200 (48 regs: +2 %, 40: +10 %, 72-80 uncapped: +12 %) */
 #endif
@@ -486,7 +493,11 @@ rad_visibility_kernel(const Bvh4Node *__restrict__ bvh, const Bvh4QNode *__restr
                       unsigned long long *link_count, uint4 *__restrict__ mirror, unsigned long long mirror_cap, unsigned long long *mirror_count,
                       uint32_t *chunk_cursor, unsigned long long *counters)
 {
+#if LB_VIS_ENTRY2
+    __shared__ BvhEntrySet2 s_entry[LB_BLOCK / 32];
+#else
     __shared__ BvhEntrySet s_entry[LB_BLOCK / 32];
+#endif
 #if LB_VIS_SMEMNODES
     __shared__ __align__(16) Bvh4Node s_enode[LB_BLOCK / 32][BVH_ENTRY_MAX];
     const Bvh4Node *sm_nodes = s_enode[threadIdx.x >> 5];
@@ -503,7 +514,11 @@ rad_visibility_kernel(const Bvh4Node *__restrict__ bvh, const Bvh4QNode *__restr
     unsigned segs = 0;
     TravStats ts = { 0, 0 };
     const unsigned lane = threadIdx.x & 31u;
+#if LB_VIS_ENTRY2
+    BvhEntrySet2 &E = s_entry[threadIdx.x >> 5];
+#else
     BvhEntrySet &E = s_entry[threadIdx.x >> 5];
+#endif
     const unsigned long long n_chunks = (n_cand + RAD_CHUNK - 1ull) / RAD_CHUNK;
     for (;;) {                                        /* persistent warps: chunks differ a lot in cost, so they are pulled from a cursor */
         uint32_t ch = 0;
@@ -511,6 +526,51 @@ rad_visibility_kernel(const Bvh4Node *__restrict__ bvh, const Bvh4QNode *__restr
         ch = __shfl_sync(0xffffffffu, ch, 0);
         if (ch >= n_chunks) break;
         const unsigned long long e0 = (unsigned long long)ch * RAD_CHUNK;
+#if LB_VIS_ENTRY2
+        if (ENTRY) {
+            /* boxes of the chunk's row ends (R: the lumels of one row warp) and column ends (C) apart: the segments lie in their hull */
+            float r[12];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { r[a] = r[6 + a] = INFINITY; r[3 + a] = r[9 + a] = -INFINITY; }
+            for (unsigned i = 0; i < RAD_CHUNK; i += 128u) {          /* four independent candidate -> position load chains in flight */
+                RadCand c4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned long long e = e0 + i + 32u * u + lane;
+                    c4[u].a = RAD_PAD;
+                    if (e < n_cand) c4[u] = cand[e];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const bool used = c4[u].a != RAD_PAD;
+                    const float4 A = spos[used ? c4[u].a : 0u], B = spos[used ? c4[u].b : 0u];
+                    if (used) {
+                        r[0] = fminf(r[0], A.x); r[1] = fminf(r[1], A.y); r[2] = fminf(r[2], A.z); r[3] = fmaxf(r[3], A.x); r[4] = fmaxf(r[4], A.y); r[5] = fmaxf(r[5], A.z);
+                        r[6] = fminf(r[6], B.x); r[7] = fminf(r[7], B.y); r[8] = fminf(r[8], B.z); r[9] = fmaxf(r[9], B.x); r[10] = fmaxf(r[10], B.y); r[11] = fmaxf(r[11], B.z);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int a = 0; a < 12; ++a) {
+                    const float t = __shfl_xor_sync(0xffffffffu, r[a], o);
+                    r[a] = (a % 6) < 3 ? fminf(r[a], t) : fmaxf(r[a], t);
+                }
+            }
+            if (!(r[0] <= r[3])) continue;            /* warp-uniform: the chunk holds only unused slots */
+            float lx = fminf(r[0], r[6]), ly = fminf(r[1], r[7]), lz = fminf(r[2], r[8]), hx = fmaxf(r[3], r[9]), hy = fmaxf(r[4], r[10]), hz = fmaxf(r[5], r[11]);
+            const float maxabs = fmaxf(fmaxf(fmaxf(fabsf(lx), fabsf(hx)), fmaxf(fabsf(ly), fabsf(hy))), fmaxf(fabsf(lz), fabsf(hz)));
+            bvh_entry_pad(lx, ly, lz, hx, hy, hz);
+            __syncwarp();                             /* the previous chunk's set is no longer read */
+            if (lane == 0) {
+#pragma unroll
+                for (int a = 0; a < 12; ++a) E.rc[a] = r[a];
+            }
+            __syncwarp();
+            bvh4_entry_search2_warp<LB_VIS_SHAFT != 0>(bvh, lx, ly, lz, hx, hy, hz, maxabs, E, lane);
+        }
+#else
         if (ENTRY) {
             float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
             for (unsigned i = 0; i < RAD_CHUNK; i += 128u) {          /* four independent candidate -> position load chains in flight */
@@ -545,6 +605,7 @@ rad_visibility_kernel(const Bvh4Node *__restrict__ bvh, const Bvh4QNode *__restr
             __syncwarp();
 #endif
         }
+#endif
 #if LB_VIS_LEAN
         /* Register-lean batch loop.  Across the walk only `blocked`, the batch position and the lane's statistics slots are
          * alive: the candidate record, the two lumel indices and the factor are READ AGAIN for the 4 % of segments that are
@@ -578,7 +639,9 @@ rad_visibility_kernel(const Bvh4Node *__restrict__ bvh, const Bvh4QNode *__restr
                     const V3 dn = norm3(B - A);
                     const V3 mA = A + dn * LB_SMALL, mB = B - dn * LB_SMALL;
                     TravStats t1 = { 0, 0, 0 };
-#if LB_VIS_Q8
+#if LB_VIS_ENTRY2
+                    blocked = ENTRY ? bvh4_anyhit_entries2<LB_VIS_FLUSH>(bvh, raytris, E, mA, mB, t1) : bvh4_anyhit<LB_VIS_FLUSH>(bvh, raytris, mA, mB, t1);
+#elif LB_VIS_Q8
                     blocked = ENTRY ? bvh4q_anyhit_entries<LB_VIS_FLUSH>(bvhq, raytris, E, mA, mB, t1) : bvh4_anyhit<LB_VIS_FLUSH>(bvh, raytris, mA, mB, t1);
 #elif LB_VIS_FMA == 2
                     blocked = ENTRY ? bvh4_anyhit_entries_f2<LB_VIS_FLUSH>(bvh, raytris, E, mA, mB, t1) : bvh4_anyhit<LB_VIS_FLUSH>(bvh, raytris, mA, mB, t1);
@@ -1030,8 +1093,12 @@ extern "C" int ltrgpu_radiosity_ex(ltrgpu_Ctx *ctx, ltrgpu_materials_fn material
          * the cache every time it crossed a size class and paid a 12 GB cudaMalloc (~42 ms, seen as bake-time outliers). */
         unsigned long long cand_cap = 16ull << 20;
         {
-            size_t free_b = 0, total_b = 0;
-            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            /* asked ONCE per device and process: cudaMemGetInfo takes the driver's memory lock -- 0.5 ms usually, but 13 / 49 / 79 ms
+             * in 3 of 28 resident bakes of one measurement (profiles/r02_ab_runs.md, "step jitter"), all of it on the bake's span */
+            static size_t total_of_device[64];
+            size_t free_b = 0, total_b = (ctx->device >= 0 && ctx->device < 64) ? total_of_device[ctx->device] : 0;
+            if (total_b || cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+                if (ctx->device >= 0 && ctx->device < 64) total_of_device[ctx->device] = total_b;
                 unsigned long long want = (unsigned long long)(total_b / 16 / sizeof(RadCand));
                 if (want > cand_cap) cand_cap = want;
                 if (cand_cap > (1024ull << 20)) cand_cap = 1024ull << 20;

@@ -11,6 +11,9 @@
 #include <vector_functions.h>    /* make_float4 on the host */
 #include "vmath.h"
 
+#ifndef LB_RAD_FLATN
+#define LB_RAD_FLATN 0          /* 1 = flat-normal fast path of row_group_may_link (A/B variant) */
+#endif
 #define RAD_CUTOFF 17.85f       /* > sqrt(1/(0.001*pi)) = 17.8412; conservative */
 #define RAD_SKIP_BELOW 0.0009f  /* interval bounds below this cannot reach the 0.001 thresholds even with rounding */
 
@@ -48,7 +51,14 @@ LB_HD bool row_group_may_link(const V3 &P, const V3 &N, const TileBounds &C)
     const float min_len2 = gx * gx + gy * gy + gz * gz;
     if (!(min_len2 <= RAD_CUTOFF * RAD_CUTOFF)) return false;
     const float maxA = fmaxf(N.x * lx, N.x * hx) + fmaxf(N.y * ly, N.y * hy) + fmaxf(N.z * lz, N.z * hz);
-    const float maxB = imax_prod(C.nlo.x, C.nhi.x, -hx, -lx) + imax_prod(C.nlo.y, C.nhi.y, -hy, -ly) + imax_prod(C.nlo.z, C.nhi.z, -hz, -lz);
+    float maxB;
+#if LB_RAD_FLATN
+    /* a group on a flat face has ONE normal (nlo == nhi, flagged in plo.w by rad_tile_bounds_kernel): the four interval
+     * products per axis collapse to two, with the same value bit for bit.  The branch is warp-uniform (one group per step). */
+    if (C.plo.w != 0.f) maxB = fmaxf(C.nlo.x * -hx, C.nlo.x * -lx) + fmaxf(C.nlo.y * -hy, C.nlo.y * -ly) + fmaxf(C.nlo.z * -hz, C.nlo.z * -lz);
+    else
+#endif
+    maxB = imax_prod(C.nlo.x, C.nhi.x, -hx, -lx) + imax_prod(C.nlo.y, C.nhi.y, -hy, -ly) + imax_prod(C.nlo.z, C.nhi.z, -hz, -lz);
     if (maxA < RAD_SKIP_BELOW || maxB < RAD_SKIP_BELOW) return false;
     if (min_len2 > 0.f && maxA * maxB < RAD_SKIP_BELOW * 3.14159265f * min_len2 * min_len2) return false;
     return true;

@@ -287,6 +287,43 @@ def test_bvh_entry_set_keeps_every_triangle_in_range_reachable():
             assert r["visits_entry"] < 0.8 * r["visits_root"], r
 
 
+def test_bvh_entry_set_v2_shaft_and_leaf_entries_change_no_ray():
+    """csrc/bvh_entry.h version 2 (rad_visibility_kernel): bundles whose segments run from one box to another.  With the shaft
+    planes, leaf entries and up to 16 entries, every segment must get the SAME answer as on a walk from the root and -- the
+    sharper check -- test exactly the same number of triangles: a box dropped by the shaft test that a ray would have entered
+    shows up as a difference even if it held no blocker."""
+    rng = np.random.default_rng(12)
+    for n, leaf in ((1, 2), (3, 2), (400, 2), (30000, 2), (30000, 7)):
+        tris = (rng.uniform(-20, 20, (n, 1, 3)) * np.array([1, 1, 0.15]) + rng.uniform(-0.5, 0.5, (n, 3, 3))).astype(np.float32).reshape(n, 9)
+        segs, off = [], [0]
+        for b in range(60):
+            k = int(rng.integers(1, 300))
+            r0 = rng.uniform(-18, 18, 3) * np.array([1, 1, 0.15])
+            c0 = r0 + rng.uniform(-1, 1, 3) * np.array([12, 12, 2]) * (b % 3 != 0)      # every third bundle: R and C overlap
+            a = r0 + rng.uniform(-0.4, 0.4, (k, 3))
+            e = c0 + rng.uniform(-1.5, 1.5, (k, 3))
+            if b == 5:
+                e = a.copy()                         # zero-length segments
+            if b == 6:
+                a[:, 0] = e[:, 0] = 1.5              # axis-parallel: zero direction components, flat boxes
+            if b == 7:
+                a[:] = a[0]                          # R is a point
+            if b == 8:                               # grazing: segments in the plane z = const of flat triangles
+                a[:, 2] = e[:, 2] = 0.0
+            segs.append(np.c_[a, e]); off.append(off[-1] + k)
+        off.append(off[-1])                          # an empty bundle
+        segs = np.concatenate(segs)
+        for me, shaft in ((8, True), (8, False), (5, True), (3, True)):
+            r = api.test_bvh_entry2(tris, segs, np.array(off, np.uint32), leaf, me, shaft)
+            assert r["ok"], (n, leaf, me, shaft)
+            assert r["mismatches"] == 0 and r["test_diffs"] == 0, (n, leaf, me, shaft, r["mismatches"], r["test_diffs"])
+            assert r["entries"].max() <= me and r["entries"][-1] == 0
+        if n >= 30000 and leaf == 2:
+            r1 = api.test_bvh_entry2(tris, segs, np.array(off, np.uint32), leaf, 8, True)
+            r0 = api.test_bvh_entry2(tris, segs, np.array(off, np.uint32), leaf, 8, False)
+            assert r1["visits_entry"] < r0["visits_entry"] < r0["visits_root"], (r0, r1)
+
+
 def test_rand_replay_equals_libc_stream_and_leaves_libc_in_step():
     """The AO pass consumes one libc rand() per lumel (lighter.cpp:819).  The library's fast replay must give
     exactly rand()/RAND_MAX, and the libc generator must afterwards stand where that many rand() calls leave
