@@ -257,7 +257,16 @@ __device__ __forceinline__ void rad_sweep_tile(const RadColBuf<G> &B, const Tile
         /* lumel x group: every lane tests ITS row lumel (exact position and normal) against the group's bounds; the group
          * is swept only if some lane can link.  The warp-level interval test above loses the correlation between a row's
          * position and its normal; this one keeps it and rejects about half of the groups that pass it (config 4). */
+#if LB_RAD_TWOSTAGE
+        {
+            RowGroupA ta;
+            const bool a_ok = row_group_step_a(Pr, Nr, B.gb[g], ta);
+            if (!__any_sync(0xffffffffu, a_ok)) continue;
+            if (!__any_sync(0xffffffffu, a_ok && row_group_step_b(B.gb[g], ta))) continue;
+        }
+#else
         if (!__any_sync(0xffffffffu, row_group_may_link(Pr, Nr, B.gb[g]))) continue;
+#endif
         tested += G;                                       /* per lane: pairs this lane goes on to test */
 #pragma unroll 1
         for (unsigned q0 = 0; q0 < (unsigned)G; q0 += CH) {

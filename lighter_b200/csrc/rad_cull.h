@@ -14,6 +14,9 @@
 #ifndef LB_RAD_FLATN
 #define LB_RAD_FLATN 0          /* 1 = flat-normal fast path of row_group_may_link (A/B variant) */
 #endif
+#ifndef LB_RAD_TWOSTAGE
+#define LB_RAD_TWOSTAGE 0       /* 1 = the sweep's per-row group test votes after its cheap half (A/B variant) */
+#endif
 #define RAD_CUTOFF 17.85f       /* > sqrt(1/(0.001*pi)) = 17.8412; conservative */
 #define RAD_SKIP_BELOW 0.0009f  /* interval bounds below this cannot reach the 0.001 thresholds even with rounding */
 
@@ -64,6 +67,27 @@ LB_HD bool row_group_may_link(const V3 &P, const V3 &N, const TileBounds &C)
     return true;
 }
 
+
+/* row_group_may_link in two steps for the sweep (LB_RAD_TWOSTAGE): step A decides on the distance and on the row's own side
+ * (maxA, exact per row -- this is what the per-row test adds over the warp-level interval test), step B adds the group's side
+ * and the factor bound.  A AND B == row_group_may_link; the sweep votes after A and only evaluates B when some lane passed. */
+struct RowGroupA { float lx, hx, ly, hy, lz, hz, min_len2, maxA; };
+LB_HD bool row_group_step_a(const V3 &P, const V3 &N, const TileBounds &C, RowGroupA &t)
+{
+    t.lx = C.plo.x - P.x; t.hx = C.phi.x - P.x; t.ly = C.plo.y - P.y; t.hy = C.phi.y - P.y; t.lz = C.plo.z - P.z; t.hz = C.phi.z - P.z;
+    const float gx = fmaxf(fmaxf(t.lx, -t.hx), 0.f), gy = fmaxf(fmaxf(t.ly, -t.hy), 0.f), gz = fmaxf(fmaxf(t.lz, -t.hz), 0.f);
+    t.min_len2 = gx * gx + gy * gy + gz * gz;
+    if (!(t.min_len2 <= RAD_CUTOFF * RAD_CUTOFF)) return false;
+    t.maxA = fmaxf(N.x * t.lx, N.x * t.hx) + fmaxf(N.y * t.ly, N.y * t.hy) + fmaxf(N.z * t.lz, N.z * t.hz);
+    return !(t.maxA < RAD_SKIP_BELOW);
+}
+LB_HD bool row_group_step_b(const TileBounds &C, const RowGroupA &t)
+{
+    const float maxB = imax_prod(C.nlo.x, C.nhi.x, -t.hx, -t.lx) + imax_prod(C.nlo.y, C.nhi.y, -t.hy, -t.ly) + imax_prod(C.nlo.z, C.nhi.z, -t.hz, -t.lz);
+    if (maxB < RAD_SKIP_BELOW) return false;
+    if (t.min_len2 > 0.f && t.maxA * maxB < RAD_SKIP_BELOW * 3.14159265f * t.min_len2 * t.min_len2) return false;
+    return true;
+}
 
 /* lumel x lumel fast filter of the sweep's lock-step phase: an FMA dot differs from the reference's mul/add dot by < 1e-5 for
  * any pair close enough to link (|d| <= 17.85), and the factor inequality dr*dj >= 0.001*pi*len^4 is evaluated with relative
