@@ -38,6 +38,7 @@ __global__ void t_queries_kernel(const BvhNode *bvh, const Bvh4Node *bvh4, const
                                  uint32_t n, float *dist, int *anyhit, float *closest, int *closest_tri)
 {
     __shared__ BvhEntrySet s_entry[4], s_entry1[4];  /* launched with 128 threads */
+    __shared__ BvhEntrySet2 s_entry2[4], s_entry2m[4];
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
     const uint32_t q = valid ? i : 0;                /* idle lanes of the last warp stay for the warp-wide reduction below */
@@ -63,7 +64,30 @@ __global__ void t_queries_kernel(const BvhNode *bvh, const Bvh4Node *bvh4, const
         const int h0 = bvh_segment<true>(bvh, rt, orig, A, B, nullptr, ts) < 1.0f ? 1 : 0;
         const int h1 = bvh_anyhit(bvh, rt, A, B, ts) ? 1 : 0, h2 = bvh4_anyhit(bvh4, rt, A, B, ts) ? 1 : 0, h3 = bvh4_anyhit<2>(bvh4, rt, A, B, ts) ? 1 : 0;
         const int h4 = bvh4_anyhit_entries(bvh4, rt, E, A, B, ts) ? 1 : 0;
-        if (valid) anyhit[i] = (h0 == h1 && h1 == h2 && h2 == h3 && h3 == h4 && same) ? h0 : 2 + h0 + 2 * h1 + 4 * h2 + 8 * h3 + 16 * h4 + (same ? 0 : 32);
+        /* version-2 entry sets (rad_visibility_kernel): R = the first end points of the warp's segments, C = the second ones;
+         * the scalar model against the warp-cooperative search, and the walk from that set */
+        BvhEntrySet2 &F = s_entry2[threadIdx.x >> 5], &F1 = s_entry2m[threadIdx.x >> 5];
+        float r[12] = { A.x, A.y, A.z, A.x, A.y, A.z, B.x, B.y, B.z, B.x, B.y, B.z };
+        for (int o = 16; o > 0; o >>= 1)
+            for (int k = 0; k < 12; ++k) { const float t = __shfl_xor_sync(0xffffffffu, r[k], o); r[k] = (k % 6) < 3 ? fminf(r[k], t) : fmaxf(r[k], t); }
+        float qx = fminf(r[0], r[6]), qy = fminf(r[1], r[7]), qz = fminf(r[2], r[8]), Qx = fmaxf(r[3], r[9]), Qy = fmaxf(r[4], r[10]), Qz = fmaxf(r[5], r[11]);
+        const float maxabs = fmaxf(fmaxf(fmaxf(fabsf(qx), fabsf(Qx)), fmaxf(fabsf(qy), fabsf(Qy))), fmaxf(fabsf(qz), fabsf(Qz)));
+        bvh_entry_pad(qx, qy, qz, Qx, Qy, Qz);
+        __syncwarp();
+        if ((threadIdx.x & 31u) == 0) {
+            for (int k = 0; k < 12; ++k) F.rc[k] = r[k];
+            BvhShaft S;
+            bvh_shaft_build(r, r + 6, maxabs, S);
+            bvh4_entry_search2(bvh4, qx, qy, qz, Qx, Qy, Qz, &S, F1);
+        }
+        __syncwarp();
+        bvh4_entry_search2_warp<true>(bvh4, qx, qy, qz, Qx, Qy, Qz, maxabs, F, threadIdx.x & 31u);
+        bool same2 = F.n == F1.n;
+        for (int e = 0; same2 && e < F.n; ++e)
+            for (int k = 0; k < 4; ++k) same2 = same2 && __float_as_int(F.lo[e][k]) == __float_as_int(F1.lo[e][k]) && (k == 3 || F.hi[e][k] == F1.hi[e][k]);
+        const int h5 = bvh4_anyhit_entries2(bvh4, rt, F, A, B, ts) ? 1 : 0;
+        if (valid) anyhit[i] = (h0 == h1 && h1 == h2 && h2 == h3 && h3 == h4 && h4 == h5 && same && same2) ? h0
+                               : 2 + h0 + 2 * h1 + 4 * h2 + 8 * h3 + 16 * h4 + (same ? 0 : 32) + 64 * h5 + (same2 ? 0 : 128);
     }
     if (closest && valid) {
         int slot = -1;
