@@ -144,7 +144,8 @@ LTRAPI int ltrx_test_bvh_entry(const float *tris9, u32 ntris, int leaf_max, cons
                                u32 *entries_out, uint64_t *visits_root, uint64_t *visits_entry, uint64_t *entry_tests, u32 *mismatches);
 /* host-only: version-2 entry sets (shaft-culled search, leaf entries): root walk vs entry walk incl. triangle-test counts */
 LTRAPI int ltrx_test_bvh_entry2(const float *tris9, u32 ntris, int leaf_max, const float *segs6, const u32 *bundle_off, u32 n_bundles,
-                                int max_entries, int use_shaft, u32 *entries_out, uint64_t *stats4, u32 *mismatches, u32 *test_diffs);
+                                int max_entries, int use_shaft, int batch /* > 0: packet form, leaves listed per `batch` segments */,
+                                u32 *entries_out, uint64_t *stats4, u32 *mismatches, u32 *test_diffs);
 
 #ifdef __cplusplus
 }

@@ -124,10 +124,11 @@ def test_bvh_entry(tris: np.ndarray, segs: np.ndarray, bundle_off: np.ndarray, l
                 mismatches=mm.value)
 
 
-def test_bvh_entry2(tris: np.ndarray, segs: np.ndarray, bundle_off: np.ndarray, leaf_max: int = 2, max_entries: int = 8, shaft: bool = True) -> dict:
+def test_bvh_entry2(tris: np.ndarray, segs: np.ndarray, bundle_off: np.ndarray, leaf_max: int = 2, max_entries: int = 8, shaft: bool = True, batch: int = 0) -> dict:
     """Host-only: version-2 entry sets (csrc/bvh_entry.h: shaft-culled search, leaf entries) of bundles of segments whose first
     end points form one box and whose second end points another -- root walk vs entry walk on every segment, hit / miss AND
-    number of triangles tested."""
+    number of triangles tested.  batch > 0: the packet form (per `batch` consecutive segments one walk lists the leaves in the
+    batch's shaft; a ray tests only those leaf boxes): visits_entry = node reads of those walks, entry_tests = listed boxes tested."""
     tris = np.ascontiguousarray(tris, np.float32)
     segs = np.ascontiguousarray(segs, np.float32).reshape(-1, 6)
     off = np.ascontiguousarray(bundle_off, np.uint32)
@@ -135,7 +136,7 @@ def test_bvh_entry2(tris: np.ndarray, segs: np.ndarray, bundle_off: np.ndarray, 
     entries = np.zeros(max(nb, 1), np.uint32)
     stats = (C.c_uint64 * 4)()
     mm, td = u32(), u32()
-    ok = lib().ltrx_test_bvh_entry2(_fp(tris), len(tris), leaf_max, _fp(segs), off.ctypes.data, nb, int(max_entries), int(bool(shaft)),
+    ok = lib().ltrx_test_bvh_entry2(_fp(tris), len(tris), leaf_max, _fp(segs), off.ctypes.data, nb, int(max_entries), int(bool(shaft)), int(batch),
                                     entries.ctypes.data, stats, C.byref(mm), C.byref(td))
     return dict(ok=bool(ok), entries=entries[:nb], visits_root=stats[0], visits_entry=stats[1], entry_tests=stats[2], tri_tests=stats[3],
                 mismatches=mm.value, test_diffs=td.value)
@@ -249,7 +250,7 @@ def lib() -> C.CDLL:
     L.ltrx_test_rad_cull.argtypes = [fp, fp, u32, fp, fp, u32, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
     L.ltrx_test_bvh_entry.argtypes = [fp, u32, C.c_int, fp, C.c_void_p, u32, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                       C.POINTER(C.c_uint64), C.POINTER(u32)]
-    L.ltrx_test_bvh_entry2.argtypes = [fp, u32, C.c_int, fp, C.c_void_p, u32, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint64),
+    L.ltrx_test_bvh_entry2.argtypes = [fp, u32, C.c_int, fp, C.c_void_p, u32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint64),
                                        C.POINTER(u32), C.POINTER(u32)]
     _lib = L
     return L

@@ -1360,7 +1360,7 @@ int ltrx_test_bvh_entry(const float *tris9, u32 ntris, int leaf_max, const float
  * (*test_diffs) -- a dropped box that a ray would have entered shows up there even if it held no blocker.
  * stats[0..3] = 4-wide node reads from the root, from the entry sets, entry boxes tested, triangle tests of the entry walk. */
 int ltrx_test_bvh_entry2(const float *tris9, u32 ntris, int leaf_max, const float *segs6, const u32 *bundle_off, u32 n_bundles,
-                         int max_entries, int use_shaft, u32 *entries_out, uint64_t *stats4, u32 *mismatches, u32 *test_diffs)
+                         int max_entries, int use_shaft, int batch, u32 *entries_out, uint64_t *stats4, u32 *mismatches, u32 *test_diffs)
 {
     SceneBvh bvh;
     build_scene_bvh(tris9, ntris, bvh, leaf_max, 0);
@@ -1417,7 +1417,63 @@ int ltrx_test_bvh_entry2(const float *tris9, u32 ntris, int leaf_max, const floa
             bvh4_entry_search2(bvh.nodes4.data(), q[0], q[1], q[2], q[3], q[4], q[5], use_shaft ? &S : nullptr, E, max_entries);
         }
         if (entries_out) entries_out[b] = (u32)E.n;
-        for (u32 s = bundle_off[b]; s < bundle_off[b + 1]; ++s) {
+        /* batch > 0: the PACKET form of rad_visibility_kernel -- per `batch` consecutive segments the leaves in the batch's own
+         * shaft are listed by one walk from the bundle's entry set (stats4[1] counts its node reads), and a ray only tests the
+         * listed leaf boxes (stats4[2]) */
+        for (u32 s0 = bundle_off[b]; batch > 0 && s0 < bundle_off[b + 1]; s0 += (u32)batch) {
+            const u32 s1 = std::min<u32>(s0 + (u32)batch, bundle_off[b + 1]);
+            float bq[6] = { INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY };
+            float brc[12] = { INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY, INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY };
+            for (u32 s = s0; s < s1; ++s)
+                for (int e = 0; e < 2; ++e) {
+                    const float *p = segs6 + 6 * (size_t)s + 3 * e;
+                    for (int k = 0; k < 3; ++k) {
+                        bq[k] = fminf(bq[k], p[k]); bq[3 + k] = fmaxf(bq[3 + k], p[k]);
+                        brc[6 * e + k] = fminf(brc[6 * e + k], p[k]); brc[6 * e + 3 + k] = fmaxf(brc[6 * e + 3 + k], p[k]);
+                    }
+                }
+            const float bmaxabs = fmaxf(fmaxf(fmaxf(fabsf(bq[0]), fabsf(bq[3])), fmaxf(fabsf(bq[1]), fabsf(bq[4]))), fmaxf(fabsf(bq[2]), fabsf(bq[5])));
+            bvh_entry_pad(bq[0], bq[1], bq[2], bq[3], bq[4], bq[5]);
+            BvhShaft BS;
+            bvh_shaft_build(brc, brc + 6, bmaxabs, BS);
+            struct LeafBox { float b[6]; int32_t code; };
+            std::vector<LeafBox> list;
+            auto consider = [&](int32_t code, float lx, float ly, float lz, float hx, float hy, float hz) {
+                if (!(lx <= bq[3] && hx >= bq[0] && ly <= bq[4] && hy >= bq[1] && lz <= bq[5] && hz >= bq[2])) return;
+                if (use_shaft && bvh_shaft_outside(BS, lx, ly, lz, hx, hy, hz)) return;
+                if (code < 0) list.push_back(LeafBox{ { lx, ly, lz, hx, hy, hz }, code }); else stack.push_back(code);
+            };
+            stack.clear();
+            for (int i = 0; i < E.n; ++i) { int32_t code; memcpy(&code, &E.lo[i][3], 4); consider(code, E.lo[i][0], E.lo[i][1], E.lo[i][2], E.hi[i][0], E.hi[i][1], E.hi[i][2]); }
+            while (!stack.empty()) {
+                const Bvh4Node &n = bvh.nodes4[stack.back()]; stack.pop_back();
+                ++stats4[1];
+                for (int c = 0; c < 4; ++c) if (n.c[c] != BVH4_EMPTY) consider(n.c[c], n.lox[c], n.loy[c], n.loz[c], n.hix[c], n.hiy[c], n.hiz[c]);
+            }
+            for (u32 s = s0; s < s1; ++s) {
+                const float *p = segs6 + 6 * (size_t)s;
+                const V3 A = mk3(p[0], p[1], p[2]), B = mk3(p[3], p[4], p[5]), d = B - A;
+                uint64_t t_root = 0, t_entry = 0;
+                stack.assign(1, 0);
+                const bool h_root = walk(A, B, stack, none, &stats4[0], &t_root);
+                const float ix = lb_slab_inv(d.x), iy = lb_slab_inv(d.y), iz = lb_slab_inv(d.z);
+                bool h_entry = false;
+                for (const LeafBox &L : list) {
+                    const float x0 = (L.b[0] - A.x) * ix, x1 = (L.b[3] - lb_slab_origin_hi(A.x, d.x)) * ix, y0 = (L.b[1] - A.y) * iy, y1 = (L.b[4] - lb_slab_origin_hi(A.y, d.y)) * iy;
+                    const float z0 = (L.b[2] - A.z) * iz, z1 = (L.b[5] - lb_slab_origin_hi(A.z, d.z)) * iz;
+                    const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
+                    const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));
+                    if (!(t0 <= t1 + 2e-6f)) continue;
+                    const uint32_t code = ~L.code;
+                    for (uint32_t t = code >> 3; t < (code >> 3) + (code & 7u); ++t) { ++t_entry; if (seg_tri_prepared(A, d, rt[t]) < 1.0f) h_entry = true; }
+                }
+                stats4[2] += list.size();
+                stats4[3] += t_entry;
+                if (h_root != h_entry) ++*mismatches;
+                if (t_root != t_entry) ++*test_diffs;
+            }
+        }
+        for (u32 s = bundle_off[b]; batch <= 0 && s < bundle_off[b + 1]; ++s) {
             const float *p = segs6 + 6 * (size_t)s;
             const V3 A = mk3(p[0], p[1], p[2]), B = mk3(p[3], p[4], p[5]);
             uint64_t t_root = 0, t_entry = 0;

@@ -488,6 +488,19 @@ template <int G> static size_t rad_sweep_smem() { return sizeof(RadColBuf<G>) * 
 #ifndef LB_VIS_ENTRY2
 #define LB_VIS_ENTRY2 1         /* 1 = version-2 entry sets (bvh_entry.h: shaft-culled search, leaf entries, <= BVH_ENTRY2_MAX entries): 224.5 -> 211.1 ms on config 4; 0 = version 1 (A/B) */
 #endif
+#ifndef LB_VIS_PACKET
+#define LB_VIS_PACKET 0         /* 1 = per batch of 32 segments the WARP walks the tree once for the batch's shaft and lists the leaves in it; a ray only tests
+                                 * the listed leaf boxes (needs LB_VIS_ENTRY2).  Bit-identical, and measured 3.8x SLOWER on config 4 (785.7 vs 208.6 ms,
+                                 * profiles/r02_ab_runs.md): real batches are not thin (35 listed boxes per ray, not the 7 of the offline model) and the
+                                 * warp's walk is one serial chain of dependent node loads.  Kept for A/B only */
+#endif
+#define VIS_LMAX 32             /* leaves listed per ray phase: one bit each in a ray's hit mask */
+struct __align__(16) VisPacket {                  /* per warp, shared memory */
+    float lo[VIS_LMAX][4];                        /* leaf box lo xyz + leaf code (raw bits) */
+    float hi[VIS_LMAX][4];
+    int stack[BVH_STACK];                         /* the warp's walk (uniform) */
+    float rc[12];                                 /* the batch's boxes R and C */
+};
 #ifndef LB_VIS_SHAFT
 #define LB_VIS_SHAFT 1          /* version-2 entry sets: 0 = bounding-box search only (A/B) */
 #endif
@@ -504,6 +517,10 @@ rad_visibility_kernel(const Bvh4Node *__restrict__ bvh, const Bvh4QNode *__restr
 {
 #if LB_VIS_ENTRY2
     __shared__ BvhEntrySet2 s_entry[LB_BLOCK / 32];
+#if LB_VIS_PACKET
+    __shared__ VisPacket s_packet[LB_BLOCK / 32];
+    VisPacket &P = s_packet[threadIdx.x >> 5];
+#endif
 #else
     __shared__ BvhEntrySet s_entry[LB_BLOCK / 32];
 #endif
@@ -642,6 +659,135 @@ rad_visibility_kernel(const Bvh4Node *__restrict__ bvh, const Bvh4QNode *__restr
                 if (e < n_cand) c = *cp;
                 valid = c.a != RAD_PAD;
                 if (!__any_sync(0xffffffffu, valid)) continue;
+#if LB_VIS_ENTRY2 && LB_VIS_PACKET
+                if (ENTRY) {
+                    /*
+                     * Packet form.  The 32 segments of a batch come from one row warp and one or two 8-lumel column groups: a thin
+                     * shaft.  The WARP walks the tree once for that shaft, from the chunk's entry set, with the bounding-box and
+                     * shaft-plane tests of the entry search (bvh_entry.h), and lists the leaves in it (7.4 on average on config 4,
+                     * after 5 node visits); every ray then tests the listed leaf boxes with the plain slab test -- all lanes in
+                     * lock step, no stack, no node loads -- and the triangles of the boxes it enters.  A ray tests a triangle iff
+                     * its slab test accepts the leaf box, exactly as on a walk from the root (accepting a leaf box implies
+                     * accepting its ancestors' boxes, and a leaf dropped by the shaft lies farther from every segment of the
+                     * batch than the slab test's slack: bvh_entry.h).  Lists longer than VIS_LMAX are handled in rounds.
+                     */
+                    V3 mA = mk3(0.f, 0.f, 0.f), dseg = mA, l1h = mA;
+                    float ix = 0.f, iy = 0.f, iz = 0.f;
+                    float r[12];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) { r[a] = r[6 + a] = INFINITY; r[3 + a] = r[9 + a] = -INFINITY; }
+                    if (valid) {
+                        const float4 Pa = spos[c.a], Pb = spos[c.b];          /* row end, column end */
+                        const bool a_first = sidx[c.a] < sidx[c.b];            /* the reference traces from the lower lumel index */
+                        const V3 A = ld3(a_first ? Pa : Pb), B = ld3(a_first ? Pb : Pa);
+                        const V3 dn = norm3(B - A);
+                        mA = A + dn * LB_SMALL;
+                        const V3 mB = B - dn * LB_SMALL;
+                        dseg = mB - mA;
+                        ix = lb_slab_inv(dseg.x); iy = lb_slab_inv(dseg.y); iz = lb_slab_inv(dseg.z);
+                        l1h = mk3(lb_slab_origin_hi(mA.x, dseg.x), lb_slab_origin_hi(mA.y, dseg.y), lb_slab_origin_hi(mA.z, dseg.z));
+                        r[0] = r[3] = Pa.x; r[1] = r[4] = Pa.y; r[2] = r[5] = Pa.z; r[6] = r[9] = Pb.x; r[7] = r[10] = Pb.y; r[8] = r[11] = Pb.z;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int a = 0; a < 12; ++a) {
+                            const float t = __shfl_xor_sync(0xffffffffu, r[a], o);
+                            r[a] = (a % 6) < 3 ? fminf(r[a], t) : fmaxf(r[a], t);
+                        }
+                    }
+                    float qlx = fminf(r[0], r[6]), qly = fminf(r[1], r[7]), qlz = fminf(r[2], r[8]), qhx = fmaxf(r[3], r[9]), qhy = fmaxf(r[4], r[10]), qhz = fmaxf(r[5], r[11]);
+                    const float maxabs = fmaxf(fmaxf(fmaxf(fabsf(qlx), fabsf(qhx)), fmaxf(fabsf(qly), fabsf(qhy))), fmaxf(fabsf(qlz), fabsf(qhz)));
+                    bvh_entry_pad(qlx, qly, qlz, qhx, qhy, qhz);
+                    __syncwarp();
+                    if (lane < 12u) P.rc[lane] = r[lane];
+                    __syncwarp();
+                    float p_nu0, p_nv0, p_ru0, p_rv0, p_lim0, p_nu1 = 0.f, p_nv1 = 0.f, p_ru1 = 0.f, p_rv1 = 0.f, p_lim1 = 0.f;
+                    bvh_shaft_plane(P.rc, P.rc + 6, maxabs, (int)(lane >> 2), p_nu0, p_nv0, p_ru0, p_rv0, p_lim0);
+                    if (lane < 16u) bvh_shaft_plane(P.rc, P.rc + 6, maxabs, 8 + (int)(lane >> 2), p_nu1, p_nv1, p_ru1, p_rv1, p_lim1);
+                    const int pa0 = (int)(lane >> 4);
+                    const unsigned cc = lane & 3u;
+                    int sp = 0, nl = 0;
+                    unsigned visits = 0, ntri = 0, nbox = 0;
+                    /* one step of the warp's walk: box `cc` of a node (or of a group of four entries), seen by the eight lanes cc, cc + 4, .. */
+#define VIS_CONSIDER(HAS, CODE, LX, LY, LZ, HX, HY, HZ)                                                                                  \
+                    {                                                                                                                    \
+                        bool out_;                                                                                                       \
+                        {                                                                                                                \
+                            const float lu = pa0 == 0 ? (LX) : (LY), hu = pa0 == 0 ? (HX) : (HY), lv = pa0 == 0 ? (LY) : (LZ), hv = pa0 == 0 ? (HY) : (HZ); \
+                            const float bu = p_nu0 > 0.f ? lu : hu, bv = p_nv0 > 0.f ? lv : hv;                                           \
+                            out_ = p_nu0 * (bu - p_ru0) + p_nv0 * (bv - p_rv0) > p_lim0;                                                 \
+                        }                                                                                                                \
+                        {                                                                                                                \
+                            const float bu = p_nu1 > 0.f ? (LZ) : (HZ), bv = p_nv1 > 0.f ? (LX) : (HX);                                   \
+                            out_ = out_ || (p_nu1 * (bu - p_ru1) + p_nv1 * (bv - p_rv1) > p_lim1);                                       \
+                        }                                                                                                                \
+                        const unsigned om_ = LB_VIS_SHAFT ? __ballot_sync(0xffffffffu, out_) : 0u;                                       \
+                        const bool in_ = lane < 4u && (HAS) && (CODE) != BVH4_EMPTY && (LX) <= qhx && (HX) >= qlx && (LY) <= qhy && (HY) >= qly && \
+                                         (LZ) <= qhz && (HZ) >= qlz && !(om_ & (0x11111111u << cc));                                     \
+                        const unsigned hm_ = __ballot_sync(0xffffffffu, in_), lm_ = __ballot_sync(0xffffffffu, in_ && (CODE) < 0), im_ = hm_ & ~lm_; \
+                        if (in_) {                                                                                                       \
+                            if ((CODE) < 0) {                                                                                            \
+                                const int at_ = nl + __popc(lm_ & ((1u << lane) - 1u));                                                  \
+                                *reinterpret_cast<float4 *>(P.lo[at_]) = make_float4((LX), (LY), (LZ), __int_as_float(CODE));            \
+                                *reinterpret_cast<float4 *>(P.hi[at_]) = make_float4((HX), (HY), (HZ), 0.f);                             \
+                            } else P.stack[sp + __popc(im_ & ((1u << lane) - 1u))] = (CODE);                                             \
+                        }                                                                                                                \
+                        nl += __popc(lm_); sp += __popc(im_);                                                                            \
+                        __syncwarp();                                                                                                    \
+                    }
+                    for (int e4 = 0; e4 < E.n; e4 += 4) {                  /* seed: the chunk's entries, four at a time */
+                        const int ei = e4 + (int)cc;
+                        const bool has = ei < E.n;
+                        const float4 lo = *reinterpret_cast<const float4 *>(E.lo[has ? ei : 0]), hi = *reinterpret_cast<const float4 *>(E.hi[has ? ei : 0]);
+                        const int code = __float_as_int(lo.w);
+                        VIS_CONSIDER(has, code, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z)
+                    }
+                    bool more;
+                    do {
+                        while (sp > 0 && nl <= VIS_LMAX - 4) {
+                            const int node = P.stack[sp - 1];
+                            __syncwarp();                             /* every lane has read the top before a push overwrites it */
+                            --sp;
+                            const Bvh4Node &N = bvh[node];
+                            const int code = __ldg(&N.c[cc]);
+                            const float lx = __ldg(&N.lox[cc]), ly = __ldg(&N.loy[cc]), lz = __ldg(&N.loz[cc]), hx = __ldg(&N.hix[cc]), hy = __ldg(&N.hiy[cc]), hz = __ldg(&N.hiz[cc]);
+                            ++visits;
+                            VIS_CONSIDER(true, code, lx, ly, lz, hx, hy, hz)
+                        }
+                        more = sp > 0;
+                        if (valid && !blocked && nl) {                    /* the rays' turn: nl listed leaf boxes, the same words on every lane */
+                            unsigned m = 0;
+                            for (int j = 0; j < nl; ++j) {
+                                const float4 lo = *reinterpret_cast<const float4 *>(P.lo[j]), hi = *reinterpret_cast<const float4 *>(P.hi[j]);
+                                const float x0 = (lo.x - mA.x) * ix, x1 = (hi.x - l1h.x) * ix, y0 = (lo.y - mA.y) * iy, y1 = (hi.y - l1h.y) * iy;
+                                const float z0 = (lo.z - mA.z) * iz, z1 = (hi.z - l1h.z) * iz;
+                                const float t0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
+                                const float t1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), 1.f));
+                                if (t0 <= t1 + 2e-6f) m |= 1u << j;
+                            }
+                            nbox += (unsigned)nl;
+                            while (m && !blocked) {
+                                const int j = __ffs(m) - 1;
+                                m &= m - 1u;
+                                const unsigned code = ~(unsigned)__float_as_int(P.lo[j][3]);
+                                const RayTri *tp = raytris + (code >> 3);
+                                for (unsigned t = code & 7u; t; --t, ++tp) {
+                                    RayTri T;
+                                    load_raytri(tp, T);
+                                    ++ntri;
+                                    if (seg_tri_prepared<true>(mA, dseg, T) < 1.0f) blocked = true;     /* scene-BVH triangles are "useful" by construction */
+                                }
+                            }
+                        }
+                        __syncwarp();                                 /* the list is rewritten in the next round */
+                        nl = 0;
+                    } while (more);
+#undef VIS_CONSIDER
+                    if (valid) { s_stat[0][threadIdx.x] += 1u; s_stat[2][threadIdx.x] += ntri; s_stat[3][threadIdx.x] += nbox; }
+                    if (lane == 0) s_stat[1][threadIdx.x] += 2u * visits;
+                } else
+#endif
                 if (valid) {                              /* RAD_PAD: unused slot of a warp's output chunk */
                     const bool a_first = sidx[c.a] < sidx[c.b];         /* the reference traces from the lower lumel index */
                     const V3 A = ld3(spos[a_first ? c.a : c.b]), B = ld3(spos[a_first ? c.b : c.a]);

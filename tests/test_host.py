@@ -318,6 +318,9 @@ def test_bvh_entry_set_v2_shaft_and_leaf_entries_change_no_ray():
             assert r["ok"], (n, leaf, me, shaft)
             assert r["mismatches"] == 0 and r["test_diffs"] == 0, (n, leaf, me, shaft, r["mismatches"], r["test_diffs"])
             assert r["entries"].max() <= me and r["entries"][-1] == 0
+        for batch, shaft in ((32, True), (32, False), (7, True), (1, True)):       # packet form: leaves listed per batch of segments
+            r = api.test_bvh_entry2(tris, segs, np.array(off, np.uint32), leaf, 8, shaft, batch)
+            assert r["ok"] and r["mismatches"] == 0 and r["test_diffs"] == 0, (n, leaf, batch, shaft, r["mismatches"], r["test_diffs"])
         if n >= 30000 and leaf == 2:
             r1 = api.test_bvh_entry2(tris, segs, np.array(off, np.uint32), leaf, 8, True)
             r0 = api.test_bvh_entry2(tris, segs, np.array(off, np.uint32), leaf, 8, False)
