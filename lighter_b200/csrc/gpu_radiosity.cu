@@ -186,6 +186,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 #define RAD_CHUNK 1024u          /* candidate slots a warp reserves from the global counter at a time (512 / 2048 measured: profiles/r02_ab_runs.md) */
 #endif
 #define RAD_WARPS 4              /* warps per CTA; the warps do not interact */
+/* Work items are taken from the cursor in RUNS of consecutive items.  Items are row-warp-major (a row warp has ~38 of them on
+ * config 4), so a run is mostly ONE row warp against neighbouring super-tiles, and the 1024-slot candidate chunks a sweep warp
+ * fills -- one entry set each in the visibility pass -- hold one row warp instead of two or three that lie units apart:
+ * visibility 208.6 -> 195.6 ms (run 1 / 2 / 4 / 8 / 16 / 32 / 64 / 128: 208.6 / 205.7 / 204.6 / 199.9 / 197.8 / 196.5 / 195.6 / 195.3).
+ * GUIDED: towards the end of a launch the runs shrink to a quarter of a warp's fair share of what is left, so that the last warps
+ * finish together (fixed runs of 16 cost the sweep itself 73.5 -> 76.8 ms; guided 73.6). */
+#ifndef RAD_ITEM_GUIDED
+#define RAD_ITEM_GUIDED 1
+#endif
+#ifndef RAD_ITEM_RUN
+#define RAD_ITEM_RUN 64
+#endif
 
 template <int G> struct __align__(128) RadColBuf {          /* one staged column tile */
     float4 sp[RAD_TILE], sn[RAD_TILE];
@@ -357,11 +369,24 @@ rad_candidates_kernel(const float4 *__restrict__ spos, const float4 *__restrict_
     unsigned nb = 0;                                       /* buffer the next copy goes into */
     RadOut o = { 0, 0, false };
     unsigned tested = 0, tile_loads = 0;
-    for (;;) {
-        uint32_t it = 0;
-        if (lane == 0) it = atomicAdd(item_cursor, 1u);
-        it = __shfl_sync(0xffffffffu, it, 0);
-        if (it >= n_items) break;
+    for (uint32_t it = 0, it_end = 0;; ++it) {
+        if (it >= it_end) {                                /* next run of up to RAD_ITEM_RUN consecutive items */
+            uint32_t run = (uint32_t)RAD_ITEM_RUN;
+            if (lane == 0) {
+#if RAD_ITEM_GUIDED
+                /* guided: towards the end of a launch the runs shrink (what is left / 4 runs per warp), so that the last warps finish together */
+                const uint32_t seen = *(volatile uint32_t *)item_cursor;
+                const uint32_t left = seen < n_items ? n_items - seen : 0u;
+                const uint32_t fair = left / (gridDim.x * (uint32_t)RAD_WARPS * 4u);
+                run = fair < run ? (fair ? fair : 1u) : run;
+#endif
+                it = atomicAdd(item_cursor, run);
+            }
+            it = __shfl_sync(0xffffffffu, it, 0);
+            run = __shfl_sync(0xffffffffu, run, 0);
+            if (it >= n_items) break;
+            it_end = it + run < n_items ? it + run : n_items;
+        }
         const uint2 item = items[it];
         const uint32_t rw = item.x;                        /* rows rw*32 .. rw*32+31 (storage order) */
         const uint32_t rt = rw / (RAD_TILE / 32);
