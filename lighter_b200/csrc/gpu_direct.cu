@@ -150,7 +150,7 @@ __global__ void direct_classify_kernel(const ltrgpu_Light *__restrict__ lights, 
 #define LB_MARCH_MINBLOCKS 8      /* 64 registers: measured on B200 (config 4): 41.3 ms vs 42.3 uncapped (72 regs), 52.8 at 10 blocks (spills) */
 #endif
 __global__ void __launch_bounds__(LB_BLOCK, LB_MARCH_MINBLOCKS)
-direct_march_kernel(const ltrgpu_Light *__restrict__ lights, const BvhNode *__restrict__ bvh, const PreparedTri *__restrict__ tris,
+direct_march_kernel(const ltrgpu_Light *__restrict__ lights, const BvhNode *__restrict__ bvh, const Bvh4Node *__restrict__ bvh4, const PreparedTri *__restrict__ tris,
                     const float4 *__restrict__ lpos, const float4 *__restrict__ lnrm, uint64_t sh_begin, uint32_t n_local,
                     const uint2 *__restrict__ active, const uint32_t *__restrict__ active_count, uint32_t *cursor, uint32_t l0,
                     float *__restrict__ fvis, unsigned long long *counters)
@@ -178,7 +178,7 @@ direct_march_kernel(const ltrgpu_Light *__restrict__ lights, const BvhNode *__re
             const uint64_t g = sh_begin + a.x;
             const V3 SP = ld3(lpos[g]), SN = ld3(lnrm[g]);
             const V3 to = (L.type == 3u) ? SP + L.dir * L.range : L.pos;
-            float f = march_shadow(bvh, tris, SP + SN * 0.005f, to, L.radius, queries, ts);
+            float f = march_shadow(bvh, bvh4, tris, SP + SN * 0.005f, to, L.radius, queries, ts);
             fvis[(size_t)(a.y - l0) * n_local + a.x] = f;
             ++marches;
         }
@@ -446,7 +446,7 @@ extern "C" int ltrgpu_direct_light(ltrgpu_Ctx *ctx)
         CU_TRY(ctx, cudaEventRecord(m0, st));
         unsigned blocks = (unsigned)ctx->num_sms * 16;
         if (!sampled) {
-            direct_march_kernel<<<blocks, LB_BLOCK, 0, st>>>(ctx->d_lights, ctx->d_bvh, ctx->d_ptris, ctx->d_lpos, ctx->d_lnrm, tab_base,
+            direct_march_kernel<<<blocks, LB_BLOCK, 0, st>>>(ctx->d_lights, ctx->d_bvh, ctx->d_bvh4, ctx->d_ptris, ctx->d_lpos, ctx->d_lnrm, tab_base,
                                                              tab_n, ctx->d_active, ctx->d_active_count, ctx->d_active_count + 1, l0, ctx->d_fvis, ctx->d_counters);
             CU_LAUNCH_CHECK(ctx);
         } else {

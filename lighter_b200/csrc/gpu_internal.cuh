@@ -338,6 +338,97 @@ __device__ __forceinline__ float bvh_distance(const BvhNode *__restrict__ nodes,
 }
 
 /*
+ * The same nearest-distance query on the 4-wide tree (bvh.h Bvh4Node): one node read decides four boxes, so the chain of
+ * dependent node loads a query waits for is half as long -- and the march is bound by exactly that wait (ncu: 29 % of its
+ * stall samples sit on the two lines that consume a freshly loaded node).  The nearest inner child in range is walked next,
+ * the others are pushed with their box distances; leaves are queued as leaf CODES and expanded in the evaluation phase.
+ * Unused slots hold an inverted box of +-FLT_MAX: their box distance overflows to +inf and they are pruned like any far box.
+ * The result is the minimum over the same set of triangles as on the binary tree (everything whose box is not farther than
+ * best + slack), hence the same float.
+ */
+template <int LEAVES = 2, bool HINT = false>
+__device__ __forceinline__ float bvh4_distance(const Bvh4Node *__restrict__ nodes, const PreparedTri *__restrict__ tris,
+                                               V3 p, float radius, float stop_below, TravStats &ts, int *hint = nullptr)
+{
+    constexpr int TQ = LEAVES + 3;                   /* LEAVES - 1 pending + the four children of one node */
+    int   stack_n[BVH_STACK];
+    float stack_d[BVH_STACK];
+    unsigned tq[TQ];
+    float tqd[TQ];
+    int sp = 0, nq = 0;
+    float best = radius;
+    const float slack = 1e-5f * (1.0f + fmaxf(fmaxf(fabsf(p.x), fabsf(p.y)), fabsf(p.z)));      /* see bvh_distance */
+#define LB_PRUNE2(B) (((B) + slack) * ((B) + slack))
+    float best2 = LB_PRUNE2(best);
+    int hint_in = -1, best_slot = -1;
+    if (HINT) {
+        hint_in = *hint;
+        if (hint_in >= 0) {
+            PreparedTri T;
+            load_prepared(tris + hint_in, T);
+            ts.tris++;
+            const float d = point_tri_distance_prepared(p, T);
+            if (d < best) {
+                best = d; best2 = LB_PRUNE2(best); best_slot = hint_in;
+                if (best < stop_below) return best;
+            }
+        }
+    }
+    int node = 0;
+    for (;;) {
+        while (node >= 0) {
+            const float4 *n4 = reinterpret_cast<const float4 *>(nodes + node);
+            const float4 lx = __ldg(n4), ly = __ldg(n4 + 1), lz = __ldg(n4 + 2), hx = __ldg(n4 + 3), hy = __ldg(n4 + 4), hz = __ldg(n4 + 5);
+            const int4 k = __ldg(reinterpret_cast<const int4 *>(n4 + 6));
+            ts.nodes += 2;
+            int next = -1;
+            float nextd = 0.f;
+#define LB_D4_CHILD(LX, LY, LZ, HX, HY, HZ, C)                                                                    \
+            {                                                                                                     \
+                const float dd = box_dist2(p, (LX), (LY), (LZ), (HX), (HY), (HZ));                                \
+                if (!(dd > best2)) {                                                                              \
+                    if ((C) < 0) { tq[nq] = ~(unsigned)(C); tqd[nq] = dd; ++nq; }                                 \
+                    else if (next < 0) { next = (C); nextd = dd; }                                                \
+                    else if (dd < nextd) { stack_n[sp] = next; stack_d[sp] = nextd; ++sp; next = (C); nextd = dd; } \
+                    else { stack_n[sp] = (C); stack_d[sp] = dd; ++sp; }                                           \
+                }                                                                                                 \
+            }
+            LB_D4_CHILD(lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, k.x)
+            LB_D4_CHILD(lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, k.y)
+            LB_D4_CHILD(lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, k.z)
+            LB_D4_CHILD(lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, k.w)
+#undef LB_D4_CHILD
+            node = next;
+            while (node < 0 && sp > 0) { --sp; if (stack_d[sp] <= best2) node = stack_n[sp]; }
+            if (nq >= LEAVES) break;
+        }
+        while (nq > 0) {
+            --nq;
+            if (tqd[nq] > best2) continue;               /* the best distance has improved since this leaf was queued */
+            const unsigned code = tq[nq];
+            for (unsigned t = 0, slot = code >> 3; t < (code & 7u); ++t, ++slot) {
+                if (HINT && (int)slot == hint_in) continue;                /* evaluated before the walk */
+                PreparedTri T;
+                load_prepared(tris + slot, T);
+                ts.tris++;
+                const float d = point_tri_distance_prepared(p, T);
+                if (d < best) {
+                    best = d;
+                    best2 = LB_PRUNE2(best);
+                    if (HINT) best_slot = (int)slot;
+                    if (best < stop_below) return best;
+                }
+            }
+        }
+        if (node < 0) {
+            if (HINT) *hint = best_slot;
+            return best;
+        }
+    }
+#undef LB_PRUNE2
+}
+
+/*
  * ref: lighter.cpp:190-207 (CalcInvShadowFactor): sphere tracing from the lumel to the light, every step a nearest-distance
  * query capped at 2 (MAX_PENUMBRA_SIZE), steps capped at 1 (MAX_PENUMBRA_STEP).  Shared by direct_march_kernel and the test
  * entry point (ltrx_test_march).
@@ -349,7 +440,10 @@ __device__ __forceinline__ float bvh_distance(const BvhNode *__restrict__ nodes,
  * neighbours leave the lock step in which the 32 marches of a warp read the same nodes, and the walks of a warp stop
  * sharing cache lines.  The cost of a march is its near-surface steps, not the open-air ones (2-3 node visits each).
  */
-__device__ __forceinline__ float march_shadow(const BvhNode *__restrict__ bvh, const PreparedTri *__restrict__ tris,
+#ifndef LB_MARCH_BVH4
+XX
+#endif
+__device__ __forceinline__ float march_shadow(const BvhNode *__restrict__ bvh, const Bvh4Node *__restrict__ bvh4, const PreparedTri *__restrict__ tris,
                                               V3 from, V3 to, float k, unsigned &queries, TravStats &ts)
 {
     V3 rd = norm3(to - from);
@@ -360,7 +454,11 @@ __device__ __forceinline__ float march_shadow(const BvhNode *__restrict__ bvh, c
 #endif
     int hint = -1;
     for (float t = 0.001f; t < maxt;) {
+#if LB_MARCH_BVH4
+        float h = bvh4_distance<2, LB_MARCH_HINT != 0>(bvh4, tris, from + rd * t, 2.0f, 0.001f, ts, &hint);
+#else
         float h = bvh_distance<3, LB_MARCH_HINT != 0>(bvh, tris, from + rd * t, 2.0f, 0.001f, ts, &hint);
+#endif
         ++queries;
         if (h < 0.001f) return 0.0f;
         res = fminr(res, h / fminr(t * k, 2.0f));

@@ -11,10 +11,10 @@
 #include "lighter_b200.h"
 
 /* the production march (gpu_internal.cuh march_shadow) */
-__device__ __forceinline__ float march_shadow_test(const BvhNode *bvh, const PreparedTri *tris, V3 from, V3 to, float k, unsigned &queries)
+__device__ __forceinline__ float march_shadow_test(const BvhNode *bvh, const Bvh4Node *bvh4, const PreparedTri *tris, V3 from, V3 to, float k, unsigned &queries)
 {
     TravStats ts = { 0, 0 };
-    return march_shadow(bvh, tris, from, to, k, queries, ts);
+    return march_shadow(bvh, bvh4, tris, from, to, k, queries, ts);
 }
 
 __global__ void t_ptd_kernel(const float *pts, const float *tris, uint32_t n, float *out)
@@ -44,7 +44,10 @@ __global__ void t_queries_kernel(const BvhNode *bvh, const Bvh4Node *bvh4, const
     const uint32_t q = valid ? i : 0;                /* idle lanes of the last warp stay for the warp-wide reduction below */
     TravStats ts = { 0, 0 };
     V3 A = mk3(a[3 * q], a[3 * q + 1], a[3 * q + 2]), B = mk3(b[3 * q], b[3 * q + 1], b[3 * q + 2]);
-    if (dist && valid) dist[i] = bvh_distance(bvh, pt, A, 2.0f, -1.0f, ts);
+    if (dist && valid) {
+        const float db = bvh_distance(bvh, pt, A, 2.0f, -1.0f, ts), d4 = bvh4_distance(bvh4, pt, A, 2.0f, -1.0f, ts);
+        dist[i] = db == d4 ? db : -1.0f;          /* the binary and the 4-wide walk must return the same float */
+    }
     if (anyhit) {
         /* the bundle of this warp's 32 segments: box, entry set (bvh_entry.h), walk from the entry set */
         float lx = fminf(A.x, B.x), ly = fminf(A.y, B.y), lz = fminf(A.z, B.z), hx = fmaxf(A.x, B.x), hy = fmaxf(A.y, B.y), hz = fmaxf(A.z, B.z);
@@ -96,13 +99,13 @@ __global__ void t_queries_kernel(const BvhNode *bvh, const Bvh4Node *bvh4, const
     }
 }
 
-__global__ void t_march_kernel(const BvhNode *bvh, const PreparedTri *pt, const float *from, const float *to, const float *k, uint32_t n,
+__global__ void t_march_kernel(const BvhNode *bvh, const Bvh4Node *bvh4, const PreparedTri *pt, const float *from, const float *to, const float *k, uint32_t n,
                                float *out, uint32_t *steps)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     unsigned q = 0;
-    out[i] = march_shadow_test(bvh, pt, mk3(from[3 * i], from[3 * i + 1], from[3 * i + 2]), mk3(to[3 * i], to[3 * i + 1], to[3 * i + 2]), k[i], q);
+    out[i] = march_shadow_test(bvh, bvh4, pt, mk3(from[3 * i], from[3 * i + 1], from[3 * i + 2]), mk3(to[3 * i], to[3 * i + 1], to[3 * i + 2]), k[i], q);
     if (steps) steps[i] = q;
 }
 
@@ -268,7 +271,7 @@ int ltrx_test_march(const float *tris9, u32 ntris, const float *from3, const flo
     float *df = D.up(from3, (size_t)n * 3), *dt = D.up(to3, (size_t)n * 3), *dk = D.up(k, n), *dout = D.alloc<float>(n);
     u32 *ds = steps_out ? D.alloc<u32>(n) : nullptr;
     if (!D.ok) return 0;
-    if (n) t_march_kernel<<<(n + 127) / 128, 128>>>(S.bvh, S.pt, df, dt, dk, n, dout, ds);
+    if (n) t_march_kernel<<<(n + 127) / 128, 128>>>(S.bvh, S.bvh4, S.pt, df, dt, dk, n, dout, ds);
     if (cudaDeviceSynchronize() != cudaSuccess) return 0;
     D.down(out, dout, n); D.down(steps_out, ds, n);
     return D.ok;
