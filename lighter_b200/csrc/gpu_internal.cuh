@@ -441,7 +441,9 @@ __device__ __forceinline__ float bvh4_distance(const Bvh4Node *__restrict__ node
  * sharing cache lines.  The cost of a march is its near-surface steps, not the open-air ones (2-3 node visits each).
  */
 #ifndef LB_MARCH_BVH4
-XX
+#define LB_MARCH_BVH4 0          /* 1 = the march's distance queries walk the 4-wide tree (bvh4_distance).  Same floats (device test + hashes), no gain:
+                                  * config 4 march 37.8 -> 38.7 ms, config 3 69.8 -> 68.3 (profiles/r02_ab_runs.md): half the node reads, twice the box
+                                  * arithmetic per read, and the nearer-child-first order of the binary walk prunes better.  Kept for A/B */
 #endif
 __device__ __forceinline__ float march_shadow(const BvhNode *__restrict__ bvh, const Bvh4Node *__restrict__ bvh4, const PreparedTri *__restrict__ tris,
                                               V3 from, V3 to, float k, unsigned &queries, TravStats &ts)
