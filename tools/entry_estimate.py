@@ -4,6 +4,13 @@ does; for a sample of row warps the linking candidates are generated in sweep or
 ltrx_test_bvh_entry walks every segment from the root and from its chunk's entry set on the REAL scene BVH.
 
     python tools/entry_estimate.py [config4] [window] [row_warps] [chunk]
+
+What this model got right and wrong (round 2, profiles/r02_ab_runs.md): its CHUNK-level predictions held on the real bake
+(entry sets, version-2 shaft planes: node reads per ray within 10 % of the GPU's counters).  Its BATCH-level prediction did not:
+the synthetic cloud yields ~40 linking lumels per (row warp, 8-lumel column group), the real bake 1-4 in most groups, so 32
+consecutive candidates span many more groups there and a per-batch shaft is several times fatter than modelled (7 leaves per
+batch here, 35 on the GPU -- the packet form of the visibility kernel was built on this number and retired).  Candidates are
+also generated row-major here, not in the sweep's (column group, row, column) order.
 """
 import sys, os, time
 import numpy as np
