@@ -516,7 +516,7 @@ template <int G> static size_t rad_sweep_smem() { return sizeof(RadColBuf<G>) * 
 #ifndef LB_VIS_PACKET
 #define LB_VIS_PACKET 0         /* 1 = per batch of 32 segments the WARP walks the tree once for the batch's shaft and lists the leaves in it; a ray only tests
                                  * the listed leaf boxes (needs LB_VIS_ENTRY2).  Bit-identical, and measured 3.8x SLOWER on config 4 (785.7 vs 208.6 ms,
-                                 * profiles/r02_ab_runs.md): real batches are not thin (35 listed boxes per ray, not the 7 of the offline model) and the
+                                 * profiles/r02_ab_runs.md): a real batch's shaft holds 35 leaves, not the 7 of the offline model, and the
                                  * warp's walk is one serial chain of dependent node loads.  Kept for A/B only */
 #endif
 #define VIS_LMAX 32             /* leaves listed per ray phase: one bit each in a ray's hit mask */

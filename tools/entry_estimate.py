@@ -7,10 +7,10 @@ ltrx_test_bvh_entry walks every segment from the root and from its chunk's entry
 
 What this model got right and wrong (round 2, profiles/r02_ab_runs.md): its CHUNK-level predictions held on the real bake
 (entry sets, version-2 shaft planes: node reads per ray within 10 % of the GPU's counters).  Its BATCH-level prediction did not:
-the synthetic cloud yields ~40 linking lumels per (row warp, 8-lumel column group), the real bake 1-4 in most groups, so 32
-consecutive candidates span many more groups there and a per-batch shaft is several times fatter than modelled (7 leaves per
-batch here, 35 on the GPU -- the packet form of the visibility kernel was built on this number and retired).  Candidates are
-also generated row-major here, not in the sweep's (column group, row, column) order.
+it promised 7 leaves in the shaft of a batch of 32 consecutive candidates, the GPU's counters say 35 (the packet form of the
+visibility kernel was built on this number and retired).  Known differences from the real bake: a 60-unit window of the scene,
+lumels scattered at random instead of on texel grids, candidates generated row-major instead of in the sweep's (column group,
+row, column) order.
 """
 import sys, os, time
 import numpy as np
